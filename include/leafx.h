@@ -1,0 +1,187 @@
+/*
+ * leafx.h -- C ABI of libleafx.so: the B200 (sm_100a) implementation of leaffliction's
+ * per-image preprocessing hot path.
+ *
+ * The reference (Kiripiro/leaffliction) is pure Python and has no FFI of its own; its boundary
+ * for this path is the Python call surface listed below.  Each entry point here is what a
+ * ctypes binding for the cited reference function calls (see INTEGRATION.md for the stub a
+ * maintainer would add on the reference side).
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Unless a parameter is documented "host", every pointer is
+ *     a DEVICE pointer; images are contiguous uint8 [B,H,W,3] (HWC, RGB), masks uint8 [B,H,W]
+ *     (0/255), histograms int32 [B,9,256].
+ *   - `stream` is a cudaStream_t passed as void*.  No entry point allocates device memory or
+ *     synchronises with the host; scratch comes from the caller (`*_workspace` queries).
+ *   - Return value: 0 on success, negative LFX_ERR_* otherwise; lfx_last_error() returns a
+ *     thread-local message.  There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with LFX_ERR_CUDA.
+ *   - Per-image parameters (angles, coefficients, crop boxes ...) are drawn on the host by the
+ *     Python shim with the same `random` / `np.random` calls, in the same order, as the
+ *     reference (image_augmenter.py:23,36,48,77,79,101,105,106,121,127), then uploaded.
+ */
+#ifndef LEAFX_H
+#define LEAFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LFX_OK 0
+#define LFX_ERR_ARG (-1)
+#define LFX_ERR_CUDA (-2)
+#define LFX_ERR_UNSUPPORTED (-3)
+#define LFX_ERR_WORKSPACE (-4)
+
+typedef void* lfx_stream_t;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int lfx_version(void);
+/* Select `device`, upload the colour LUTs, raise the dynamic shared-memory limits. */
+int lfx_init(int device);
+const char* lfx_last_error(void);
+
+/* ---- augmentations: srcs/preprocessing/image_augmenter.py ------------------------------------ */
+
+/* ImageAugmenter.flip (image_augmenter.py:20-31; PIL transpose :24,:26).
+ * mode[B]: 0 = FLIP_LEFT_RIGHT, 1 = FLIP_TOP_BOTTOM. */
+int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode,
+             lfx_stream_t stream);
+
+/* ImageAugmenter.rotate (image_augmenter.py:33-42; PIL rotate NEAREST, expand, white fill :37).
+ * params[B][8] = {a0,a1,a2,a3,a4,a5 (16.16 fixed point, libImaging affine_fixed), nw, nh}.
+ * Output image i is written at dst + i*dst_image_stride as [nh_i, nw_i, 3] contiguous;
+ * pixels that map outside the source get `fill` in every channel. */
+int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,
+                  const int32_t* params, int fill, lfx_stream_t stream);
+
+/* ImageAugmenter.skew / .shear (image_augmenter.py:44-71, :73-94; PIL transform BICUBIC :61-66,:84-89).
+ * coef[B][8] = PIL's inverse-map coefficients a..h (fp64); perspective[B] != 0 selects the
+ * PERSPECTIVE divide.  Bit-exact with Pillow's fp64 arithmetic. */
+int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, const double* coef,
+                     const int32_t* perspective, lfx_stream_t stream);
+
+/* HOST helpers: Pillow's 8-bit Lanczos coefficient tables (libImaging Resample.c
+ * precompute_coeffs + normalize_coeffs_8bpc).  lfx_lanczos_ksize returns the tap count;
+ * lfx_lanczos_table fills host arrays bounds[out_size][2] = {first, count} and
+ * kk[out_size][kstride] (2^22 fixed point, zero padded), kstride >= ksize. */
+int lfx_lanczos_ksize(int in_size, int out_size);
+int lfx_lanczos_table(int in_size, int out_size, int kstride, int32_t* bounds, int32_t* kk);
+
+/* ImageAugmenter.crop (image_augmenter.py:96-114; PIL crop + resize LANCZOS :108-109) and
+ * ImageTransforms.resize_image (image_utils.py:109-114).
+ * box[B][4] = {left, top, crop_w, crop_h}; every image is resized to [OH,OW].
+ * tab_bounds / tab_kk: device copies of concatenated tables (lfx_lanczos_table layout, common
+ * kstride); tab_off[B][4] = {x_bounds_row, x_ksize, y_bounds_row, y_ksize} where *_row is the
+ * first row of that image's table inside the concatenation.
+ * If dst_f32 is non-NULL the kernel also writes float32 [B,OH,OW,3] = u8 / 255.0f
+ * (ImageTransforms.normalize_array, image_utils.py:117-130; sequence.py:84-88). */
+int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, int H, int W,
+                     const int32_t* box, int OH, int OW, const int32_t* tab_bounds,
+                     const int32_t* tab_kk, int kstride, const int32_t* tab_off,
+                     lfx_stream_t stream);
+
+/* ImageAugmenter.distortion (image_augmenter.py:116-133): x = src + noise (uint8 wrap-around,
+ * :121-124), per-channel ImageOps.autocontrast(cutoff) (:127).
+ * noise[B,H,W,3]: the uint8-cast Gaussian noise; cut[B] = int(H*W*cutoff // 100) computed on the
+ * host; hist_ws: device scratch int32 [B][3][256]. */
+int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W,
+                const int32_t* cut, int32_t* hist_ws, lfx_stream_t stream);
+
+/* Same, with the noise generated on the device: NumPy's legacy MT19937 + polar-method normal
+ * stream (np.random.seed(seed[i]); np.random.normal(0, 5, (H,W,3)).astype(uint8)),
+ * image_augmenter.py:16-18,121.  mt_ws: device scratch, lfx_distort_seeded_workspace() bytes. */
+size_t lfx_distort_seeded_workspace(int B, int H, int W);
+int lfx_distort_seeded(const uint8_t* src, uint8_t* dst, int B, int H, int W, const uint32_t* seed,
+                       const int32_t* cut, int32_t* hist_ws, void* mt_ws, lfx_stream_t stream);
+
+/* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
+
+/* cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}) (mask.py:87,103; blur.py:27; hist.py:184).
+ * code: 0 = GRAY (dst [B,H,W]), 1 = HSV, 2 = LAB (dst [B,H,W,3]). */
+int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int W, int code,
+                  lfx_stream_t stream);
+
+/* The TransformConfig fields the numeric path reads (Transformation.py:63-93). */
+typedef struct lfx_mask_cfg {
+    int32_t strategy;        /* 0 hsv_h, 1 lab, 2 hsv_s, 3 hsv_v_dark, 4 external raw mask */
+    int32_t green_lo, green_hi;          /* green_hue_range */
+    int32_t fill_size;                   /* pcv.fill size */
+    int32_t morph_kernel;                /* 3,5,7 or 9 */
+    int32_t brown_lo, brown_hi;          /* brown_hue_range */
+    int32_t brown_s_min, brown_v_max;
+    int32_t brown_min_area_px;
+    int32_t brown_morph_kernel;
+    int32_t use_lab_brown, lab_a_min, lab_b_min;
+    int32_t fallback_channel;            /* hsv_channel_for_mask: 0 h, 1 s, 2 v */
+    int32_t bg_dark;                     /* bg_bias == "dark_bg" */
+    int32_t extend_brown;                /* 1 = run _extend_mask_with_brown_regions (make_mask) */
+    int32_t reserved[3];
+} lfx_mask_cfg;
+
+/* Threshold strategies _create_hsv_masks.mask_hsv_green / _create_lab_mask (mask.py:86-91,101-106)
+ * fused with the colour conversion: raw candidate mask, no post-processing.
+ * strategy 0 (hsv_h) or 1 (lab). */
+int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int H, int W,
+                       const lfx_mask_cfg* cfg /* host */, lfx_stream_t stream);
+
+/* make_mask (mask.py:548-582) under parity profile P0/P1 (grabcut_refine false, no upscale):
+ * strategy mask -> _postprocess_mask (:53-69: fill, close, open, largest filled external contour)
+ * -> Otsu fallback (:395-411) -> brown extension (:335-392).  One thread block per image.
+ * raw: NULL for strategies 0-3 (computed from src in the kernel); for strategy 4 the raw
+ * candidate [B,H,W] produced elsewhere (inclusive / enhanced front ends).
+ * info[B][8] = {found, x, y, w, h, 2*contourArea, pixels, status}; (x,y,w,h) =
+ * cv2.boundingRect of the returned contour (roi.py:26). */
+size_t lfx_make_mask_workspace(int B, int H, int W);
+int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B,
+                  int H, int W, const lfx_mask_cfg* cfg /* host */, void* workspace,
+                  size_t workspace_bytes, lfx_stream_t stream);
+
+/* _postprocess_mask alone (mask.py:53-69) on a raw mask. */
+int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
+                         int fill_size, int morph_kernel, void* workspace, size_t workspace_bytes,
+                         lfx_stream_t stream);
+
+/* apply_mask (mask_utils.py:10-83): dst = mask > 127 ? src : color_val. */
+int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,
+                   int color_val, lfx_stream_t stream);
+
+/* HOST helper: OpenCV's 8-bit Gaussian taps (8 fractional bits, error-diffused, sum 256). */
+int lfx_gauss_taps(int ksize, double sigma, int32_t* taps /* host [ksize] */);
+
+/* cv2.GaussianBlur(img,(k,k),sigma) for uint8, BORDER_REFLECT_101 (blur.py:61,72; mask.py:223,770).
+ * C = 1 or 3 interleaved channels; ksize odd <= 15. Bit-exact fixed point (8.8 then 16.16). */
+int lfx_gauss_u8(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, int ksize,
+                 double sigma, lfx_stream_t stream);
+
+/* apply_roi_filter canvas (roi.py:20-46): crop info's bounding box from apply_mask(src, mask,
+ * white) (mask may be NULL = no masking), letterbox with cv2.resize(INTER_AREA) into a zero
+ * [RH,RW,3] canvas.  Images with info.found == 0 get an all-zero canvas. */
+int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* info, uint8_t* dst,
+                      int B, int H, int W, int RH, int RW, lfx_stream_t stream);
+
+/* Colour statistics.  hist9[B][9][256]: histograms of R,G,B,H,S,V,L,a,b over mask > 0 (whole
+ * image when mask is NULL) -- PIL histogram inside autocontrast (image_augmenter.py:127), LAB-L
+ * percentiles (mask.py:206-219), dataset colour histograms.  hsv3[B][3][256] and
+ * counters[B][16]: apply_histogram_filter's numeric core on apply_mask(src, mask, white)
+ * (hist.py:188 leaf_mask, :38-65 eight categories, :248-256 five hue ranges):
+ * counters = {leaf_px, 8 categories, 5 hue ranges, 0, 0}.  Any output may be NULL.
+ * Outputs are ACCUMULATED into (zero them first). */
+int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t* hist9, int32_t* hsv3,
+                    int32_t* counters, int B, int H, int W, lfx_stream_t stream);
+
+/* Fused core transform profile (BASELINE config 2: blur + mask + ROI + histograms), equivalent to
+ * lfx_gauss_u8(5x5) + lfx_make_mask + lfx_roi_letterbox + lfx_color_stats in one submission. */
+size_t lfx_pipeline_core_workspace(int B, int H, int W);
+int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info,
+                      uint8_t* roi, int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H,
+                      int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg /* host */,
+                      void* workspace, size_t workspace_bytes, lfx_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEAFX_H */

@@ -1,0 +1,533 @@
+// Class-balancing augmentations (srcs/preprocessing/image_augmenter.py): flip, rotate (nearest,
+// 16.16 fixed point), bicubic affine/perspective warp (Pillow fp64 semantics), crop + Lanczos
+// resize (22-bit fixed point, H pass -> u8 -> V pass) and distortion (noise + autocontrast).
+// All integer / byte work: HBM-bound, no tensor cores.
+#include "lfx_common.cuh"
+
+namespace {
+
+constexpr int THREADS = 256;
+
+// ------------------------------------------------------------------------------ flip
+// grid (row chunks, B); a block moves ROWS rows through shared memory and writes them mirrored.
+constexpr int FLIP_SMEM = 32 * 1024;
+
+__global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                                  int rows_per_block, const int32_t* __restrict__ mode) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int img = blockIdx.y;
+    const int y0 = blockIdx.x * rows_per_block;
+    const int rows = min(rows_per_block, H - y0);
+    if (rows <= 0) return;
+    const int rb = W * 3;
+    uint8_t* s_in = sm;
+    uint8_t* s_out = sm + ((rows_per_block * rb + 15) & ~15);
+    const uint8_t* simg = src + (size_t)img * H * rb;
+    uint8_t* dimg = dst + (size_t)img * H * rb;
+    block_load_bytes(s_in, simg + (size_t)y0 * rb, rows * rb);
+    __syncthreads();
+    const int m = mode[img];
+    if (m == 0) {  // FLIP_LEFT_RIGHT: rows stay, pixels reverse
+        for (int i = threadIdx.x; i < rows * rb; i += THREADS) {
+            const int y = i / rb, o = i - y * rb;
+            const int x = o / 3, c = o - x * 3;
+            s_out[i] = s_in[y * rb + (W - 1 - x) * 3 + c];
+        }
+        __syncthreads();
+        block_store_bytes(dimg + (size_t)y0 * rb, s_out, rows * rb);
+    } else {  // FLIP_TOP_BOTTOM: rows reverse; the chunk lands at H - y0 - rows
+        for (int i = threadIdx.x; i < rows * rb; i += THREADS) {
+            const int y = i / rb, o = i - y * rb;
+            s_out[i] = s_in[(rows - 1 - y) * rb + o];
+        }
+        __syncthreads();
+        block_store_bytes(dimg + (size_t)(H - y0 - rows) * rb, s_out, rows * rb);
+    }
+}
+
+// ------------------------------------------------------------------------------ rotate (nearest)
+// One thread produces 4 consecutive output pixels of the FLAT [nh*nw] pixel array -> three
+// 32-bit coalesced stores; sources are gathered through L1/L2 (rotated scanlines are coherent).
+__global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                       long long dst_stride, int H, int W,
+                                                       const int32_t* __restrict__ params, int fill) {
+    const int img = blockIdx.y;
+    const int32_t* p = params + img * 8;
+    const int a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5];
+    const int nw = p[6], nh = p[7];
+    const long long npx = (long long)nw * nh;
+    const long long q0 = ((long long)blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (q0 >= npx) return;
+    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    uint8_t* dimg = dst + (size_t)img * dst_stride;
+    uint8_t out[12];
+    int y = (int)(q0 / nw), x = (int)(q0 - (long long)y * nw);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        // libImaging affine_fixed: 32-bit int arithmetic, arithmetic shift
+        const int xin = (a2 + y * a1 + x * a0) >> 16;
+        const int yin = (a5 + y * a4 + x * a3) >> 16;
+        uint8_t r = (uint8_t)fill, g = (uint8_t)fill, b = (uint8_t)fill;
+        if (xin >= 0 && xin < W && yin >= 0 && yin < H) {
+            const uint8_t* s = simg + ((size_t)yin * W + xin) * 3;
+            r = __ldg(s);
+            g = __ldg(s + 1);
+            b = __ldg(s + 2);
+        }
+        out[k * 3] = r;
+        out[k * 3 + 1] = g;
+        out[k * 3 + 2] = b;
+        if (++x == nw) {
+            x = 0;
+            ++y;
+        }
+    }
+    const long long rem = npx - q0;
+    uint8_t* d = dimg + q0 * 3;
+    if (rem >= 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+    } else {
+        const int nb = (int)min(rem, 4ll) * 3;
+        for (int i = 0; i < nb; ++i) d[i] = out[i];
+    }
+}
+
+// ------------------------------------------------------------------------------ bicubic warp
+// Pillow Geometry.c bicubic_filter32RGB in fp64 with round-to-nearest mul/add kept separate
+// (x86-64 Pillow wheels do not contract to FMA).  A cheap fp32 evaluation decides first; only
+// results that land within LFX_WARP_EPS of a truncation boundary are re-evaluated in fp64, so
+// the output is bit-identical to the fp64 path at a fraction of its cost.
+#define LFX_WARP_EPS 0.03125f
+
+__device__ __forceinline__ double cubic64(double v1, double v2, double v3, double v4, double d) {
+    const double p1 = v2;
+    const double p2 = __dadd_rn(-v1, v3);
+    const double p3 = __dadd_rn(__dadd_rn(__dmul_rn(2.0, __dadd_rn(v1, -v2)), v3), -v4);
+    const double p4 = __dadd_rn(__dadd_rn(__dadd_rn(-v1, v2), -v3), v4);
+    return __dadd_rn(p1, __dmul_rn(d, __dadd_rn(p2, __dmul_rn(d, __dadd_rn(p3, __dmul_rn(d, p4))))));
+}
+__device__ __forceinline__ float cubic32(float v1, float v2, float v3, float v4, float d) {
+    const float p2 = v3 - v1;
+    const float p3 = 2.f * (v1 - v2) + v3 - v4;
+    const float p4 = -v1 + v2 - v3 + v4;
+    return v2 + d * (p2 + d * (p3 + d * p4));
+}
+
+__global__ void __launch_bounds__(THREADS) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
+                                                          int W, const double* __restrict__ coef,
+                                                          const int32_t* __restrict__ persp) {
+    const int img = blockIdx.y;
+    const long long npx = (long long)H * W;
+    const long long q0 = ((long long)blockIdx.x * THREADS + threadIdx.x) * 4;
+    if (q0 >= npx) return;
+    const double* a = coef + img * 8;
+    const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6], a7 = a[7];
+    const bool is_persp = persp[img] != 0;
+    const uint8_t* simg = src + (size_t)img * npx * 3;
+    uint8_t* dimg = dst + (size_t)img * npx * 3;
+    uint8_t out[12];
+    int y = (int)(q0 / W), x = (int)(q0 - (long long)y * W);
+#pragma unroll 1
+    for (int k = 0; k < 4; ++k) {
+        uint8_t res[3] = {0, 0, 0};
+        if ((long long)y * W + x < npx) {
+            const double xc = (double)x + 0.5, yc = (double)y + 0.5;
+            double xin = __dadd_rn(__dadd_rn(__dmul_rn(a0, xc), __dmul_rn(a1, yc)), a2);
+            double yin = __dadd_rn(__dadd_rn(__dmul_rn(a3, xc), __dmul_rn(a4, yc)), a5);
+            if (is_persp) {
+                const double den = __dadd_rn(__dadd_rn(__dmul_rn(a6, xc), __dmul_rn(a7, yc)), 1.0);
+                xin = __ddiv_rn(xin, den);
+                yin = __ddiv_rn(yin, den);
+            }
+            if (!(xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H)) {
+                xin = __dadd_rn(xin, -0.5);
+                yin = __dadd_rn(yin, -0.5);
+                const int xf = (int)floor(xin), yf = (int)floor(yin);
+                const double dx = __dadd_rn(xin, -(double)xf), dy = __dadd_rn(yin, -(double)yf);
+                const int xb = xf - 1, yb = yf - 1;
+                int xo[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) xo[t] = min(max(xb + t, 0), W - 1) * 3;
+                // gather the 4x4x3 taps (row 0 clamped, rows 1..3 reuse the previous row's VALUE
+                // when outside -- Geometry.c BICUBIC_BODY)
+                uint8_t tap[4][4][3];
+                bool rowok[4];
+#pragma unroll
+                for (int rj = 0; rj < 4; ++rj) {
+                    const int yy = yb + rj;
+                    rowok[rj] = (rj == 0) || (yy >= 0 && yy < H);
+                    const int yc2 = min(max(yy, 0), H - 1);
+                    const uint8_t* row = simg + (size_t)yc2 * W * 3;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        tap[rj][t][0] = __ldg(row + xo[t]);
+                        tap[rj][t][1] = __ldg(row + xo[t] + 1);
+                        tap[rj][t][2] = __ldg(row + xo[t] + 2);
+                    }
+                }
+                const float fdx = (float)dx, fdy = (float)dy;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float rv[4];
+#pragma unroll
+                    for (int rj = 0; rj < 4; ++rj) {
+                        const float v = cubic32(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], fdx);
+                        rv[rj] = rowok[rj] ? v : rv[rj > 0 ? rj - 1 : 0];
+                    }
+                    const float f = cubic32(rv[0], rv[1], rv[2], rv[3], fdy);
+                    const float fr = f - floorf(f);
+                    const bool risky = (fr < LFX_WARP_EPS) || (fr > 1.f - LFX_WARP_EPS) || (f < LFX_WARP_EPS) ||
+                                       (f > 255.f - LFX_WARP_EPS);
+                    if (!risky) {
+                        res[c] = (uint8_t)(int)f;  // 0 < f < 255 here: plain truncation
+                    } else {
+                        double dv[4];
+#pragma unroll
+                        for (int rj = 0; rj < 4; ++rj) {
+                            const double v = cubic64(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], dx);
+                            dv[rj] = rowok[rj] ? v : dv[rj > 0 ? rj - 1 : 0];
+                        }
+                        const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
+                        res[c] = v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
+                    }
+                }
+            }
+        }
+        out[k * 3] = res[0];
+        out[k * 3 + 1] = res[1];
+        out[k * 3 + 2] = res[2];
+        if (++x == W) {
+            x = 0;
+            ++y;
+        }
+    }
+    const long long rem = npx - q0;
+    uint8_t* d = dimg + q0 * 3;
+    if (rem >= 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+    } else {
+        const int nb = (int)min(rem, 4ll) * 3;
+        for (int i = 0; i < nb; ++i) d[i] = out[i];
+    }
+}
+
+// ------------------------------------------------------------------------------ crop + Lanczos
+// grid (column strips, B).  A block owns LZ_TW output columns: horizontal pass over every crop
+// row into a shared uint8 strip (Pillow materialises the uint8 intermediate), then the vertical
+// pass writes the [OH, LZ_TW] output strip (and its /255 float32 twin when requested).
+constexpr int LZ_TW = 16;
+
+__device__ __forceinline__ uint8_t clip8(int v) { return (uint8_t)min(255, max(0, v)); }
+
+__global__ void __launch_bounds__(THREADS) k_crop_lanczos(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                          float* __restrict__ dstf, int H, int W,
+                                                          const int32_t* __restrict__ box, int OH, int OW,
+                                                          const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
+                                                          int kstride, const int32_t* __restrict__ toff) {
+    extern __shared__ __align__(16) uint8_t s_mid[];  // [crop_h][LZ_TW][3]
+    const int img = blockIdx.y;
+    const int c0 = blockIdx.x * LZ_TW;
+    const int ncol = min(LZ_TW, OW - c0);
+    const int left = box[img * 4], top = box[img * 4 + 1], cw = box[img * 4 + 2], ch = box[img * 4 + 3];
+    const int32_t* xb = tb + (size_t)toff[img * 4 + 0] * 2;
+    const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
+    const int32_t* yb = tb + (size_t)toff[img * 4 + 2] * 2;
+    const int32_t* yk = tk + (size_t)toff[img * 4 + 2] * kstride;
+    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const bool need_h = (cw != OW);
+    const bool need_v = (ch != OH);
+    // horizontal pass (or plain copy of the crop when widths match -- Pillow skips the pass)
+    for (int i = threadIdx.x; i < ch * ncol; i += THREADS) {
+        const int y = i / ncol, c = i - y * ncol;
+        const int oc = c0 + c;
+        const uint8_t* row = simg + ((size_t)(top + y) * W + left) * 3;
+        uint8_t* o = s_mid + ((size_t)y * LZ_TW + c) * 3;
+        if (need_h) {
+            const int xmin = xb[oc * 2], cnt = xb[oc * 2 + 1];
+            const int32_t* k = xk + (size_t)oc * kstride;
+            int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+            const uint8_t* px = row + (size_t)xmin * 3;
+            for (int t = 0; t < cnt; ++t) {
+                const int kv = __ldg(k + t);
+                s0 += __ldg(px + t * 3) * kv;
+                s1 += __ldg(px + t * 3 + 1) * kv;
+                s2 += __ldg(px + t * 3 + 2) * kv;
+            }
+            o[0] = clip8(s0 >> 22);
+            o[1] = clip8(s1 >> 22);
+            o[2] = clip8(s2 >> 22);
+        } else {
+            o[0] = __ldg(row + oc * 3);
+            o[1] = __ldg(row + oc * 3 + 1);
+            o[2] = __ldg(row + oc * 3 + 2);
+        }
+    }
+    __syncthreads();
+    uint8_t* dimg = dst + (size_t)img * OH * OW * 3;
+    float* fimg = dstf ? dstf + (size_t)img * OH * OW * 3 : nullptr;
+    const int rowb = ncol * 3;
+    for (int i = threadIdx.x; i < OH * rowb; i += THREADS) {
+        const int oy = i / rowb, o = i - oy * rowb;  // o = c*3 + channel inside the strip
+        uint8_t v;
+        if (need_v) {
+            const int ymin = yb[oy * 2], cnt = yb[oy * 2 + 1];
+            const int32_t* k = yk + (size_t)oy * kstride;
+            int s = 1 << 21;
+            for (int t = 0; t < cnt; ++t) s += s_mid[(size_t)(ymin + t) * LZ_TW * 3 + o] * __ldg(k + t);
+            v = clip8(s >> 22);
+        } else {
+            v = s_mid[(size_t)oy * LZ_TW * 3 + o];
+        }
+        const size_t di = ((size_t)oy * OW + c0) * 3 + o;
+        dimg[di] = v;
+        if (fimg) fimg[di] = (float)v / 255.0f;
+    }
+}
+
+// ------------------------------------------------------------------------------ distortion
+// (1) histogram of x = src + noise (mod 256) per image/channel, (2) autocontrast LUT per
+// image/channel (ImageOps.autocontrast), (3) dst = lut[x].
+constexpr int DREP = 8;
+
+__global__ void __launch_bounds__(THREADS) k_distort_hist(const uint8_t* __restrict__ src, const uint8_t* __restrict__ noise,
+                                                          int32_t* __restrict__ hist, int nbytes, int bytes_per_block) {
+    __shared__ uint32_t sh[DREP][3 * 256];
+    const int img = blockIdx.y;
+    const int begin = blockIdx.x * bytes_per_block;
+    const int end = min(nbytes, begin + bytes_per_block);
+    if (begin >= end) return;
+    for (int i = threadIdx.x; i < DREP * 768; i += THREADS) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t* my = sh[(threadIdx.x >> 5) % DREP];
+    const uint8_t* s = src + (size_t)img * nbytes;
+    const uint8_t* nz = noise + (size_t)img * nbytes;
+    // begin is a multiple of 48 (16 pixels): 16-byte vectors keep channel phase = (j % 3)
+    const bool vec = (((reinterpret_cast<uintptr_t>(s + begin) | reinterpret_cast<uintptr_t>(nz + begin)) & 15) == 0);
+    const int n16 = vec ? (end - begin) >> 4 : 0;
+    for (int i = threadIdx.x; i < n16; i += THREADS) {
+        const uint4 a = ld_stream16(s + begin + (size_t)i * 16);
+        const uint4 b = ld_stream16(nz + begin + (size_t)i * 16);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        int ch = (i * 16) % 3;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t sum = __vadd4(aw[w], bw[w]);  // per-byte wrap-around add
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                atomicAdd(&my[ch * 256 + ((sum >> (8 * j)) & 255)], 1u);
+                ch = ch == 2 ? 0 : ch + 1;
+            }
+        }
+    }
+    for (int i = begin + (n16 << 4) + threadIdx.x; i < end; i += THREADS) {
+        const int v = (s[i] + nz[i]) & 255;
+        atomicAdd(&my[(i % 3) * 256 + v], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 768; i += THREADS) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < DREP; ++r) v += sh[r][i];
+        if (v) atomicAdd(&hist[(size_t)img * 768 + i], (int)v);
+    }
+}
+
+// One warp per (image, channel): sequential cut logic is 256 steps -- lane 0 runs it.
+__global__ void k_distort_lut(int32_t* __restrict__ hist, const int32_t* __restrict__ cut_arr, int B) {
+    const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (idx >= B * 3) return;
+    const int img = idx / 3;
+    int32_t* h = hist + (size_t)idx * 256;
+    const int lane = threadIdx.x & 31;
+    __shared__ int s_lohi[8][2];
+    int* lohi = s_lohi[threadIdx.x >> 5];
+    if (lane == 0) {
+        int cut = cut_arr[img];
+        if (cut > 0) {  // ImageOps.autocontrast: remove `cut` pixels from the low end ...
+            for (int lo = 0; lo < 256; ++lo) {
+                if (cut > h[lo]) {
+                    cut -= h[lo];
+                    h[lo] = 0;
+                } else {
+                    h[lo] -= cut;
+                    cut = 0;
+                }
+                if (cut <= 0) break;
+            }
+            cut = cut_arr[img];  // ... and from the high end
+            for (int hi = 255; hi >= 0; --hi) {
+                if (cut > h[hi]) {
+                    cut -= h[hi];
+                    h[hi] = 0;
+                } else {
+                    h[hi] -= cut;
+                    cut = 0;
+                }
+                if (cut <= 0) break;
+            }
+        }
+        int lo = 0, hi = 255;
+        for (lo = 0; lo < 256; ++lo)
+            if (h[lo]) break;
+        if (lo == 256) lo = 255;  // Python's `for lo in range(256)` leaves lo = 255 on exhaustion
+        for (hi = 255; hi >= 0; --hi)
+            if (h[hi]) break;
+        if (hi < 0) hi = 0;
+        lohi[0] = lo;
+        lohi[1] = hi;
+    }
+    __syncwarp();
+    const int lo = lohi[0], hi = lohi[1];
+    __syncwarp();
+    // the LUT replaces the histogram in place (int32 per entry)
+    for (int ix = lane; ix < 256; ix += 32) {
+        int v = ix;
+        if (hi > lo) {
+            const double scale = __ddiv_rn(255.0, (double)(hi - lo));
+            const double offset = __dmul_rn(-(double)lo, scale);
+            const double t = __dadd_rn(__dmul_rn((double)ix, scale), offset);
+            v = (int)t;  // Python int(): truncate toward zero
+            v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        }
+        h[ix] = v;
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) k_distort_apply(const uint8_t* __restrict__ src, const uint8_t* __restrict__ noise,
+                                                           uint8_t* __restrict__ dst, const int32_t* __restrict__ lut,
+                                                           int nbytes, int bytes_per_block) {
+    __shared__ uint8_t sl[768];
+    const int img = blockIdx.y;
+    const int begin = blockIdx.x * bytes_per_block;
+    const int end = min(nbytes, begin + bytes_per_block);
+    if (begin >= end) return;
+    for (int i = threadIdx.x; i < 768; i += THREADS) sl[i] = (uint8_t)lut[(size_t)img * 768 + i];
+    __syncthreads();
+    const uint8_t* s = src + (size_t)img * nbytes;
+    const uint8_t* nz = noise + (size_t)img * nbytes;
+    uint8_t* d = dst + (size_t)img * nbytes;
+    const bool vec = (((reinterpret_cast<uintptr_t>(s + begin) | reinterpret_cast<uintptr_t>(nz + begin) |
+                        reinterpret_cast<uintptr_t>(d + begin)) & 15) == 0);
+    const int n16 = vec ? (end - begin) >> 4 : 0;
+    for (int i = threadIdx.x; i < n16; i += THREADS) {
+        const uint4 a = ld_stream16(s + begin + (size_t)i * 16);
+        const uint4 b = ld_stream16(nz + begin + (size_t)i * 16);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+        uint32_t ow[4];
+        int ch = (i * 16) % 3;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t sum = __vadd4(aw[w], bw[w]);
+            uint32_t o = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                o |= (uint32_t)sl[ch * 256 + ((sum >> (8 * j)) & 255)] << (8 * j);
+                ch = ch == 2 ? 0 : ch + 1;
+            }
+            ow[w] = o;
+        }
+        st_stream16(d + begin + (size_t)i * 16, make_uint4(ow[0], ow[1], ow[2], ow[3]));
+    }
+    for (int i = begin + (n16 << 4) + threadIdx.x; i < end; i += THREADS)
+        d[i] = sl[(i % 3) * 256 + ((s[i] + nz[i]) & 255)];
+}
+
+int chunking(int total, int unit, int B, int* per_block) {
+    // split `total` items (multiple-of-`unit` chunks) so that the grid has >= 4 blocks per SM
+    int chunks = lfx_div_up((long long)LFX_NUM_SMS * 4, B);
+    const int max_chunks = max(1, total / (unit * 4));
+    chunks = max(1, min(chunks, max_chunks));
+    int pb = lfx_div_up(total, chunks);
+    pb = lfx_div_up(pb, unit) * unit;
+    *per_block = pb;
+    return lfx_div_up(total, pb);
+}
+
+}  // namespace
+
+extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && dst && mode && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG, "flip: bad arguments");
+    LFX_REQUIRE(W * 3 * 2 + 32 <= FLIP_SMEM, LFX_ERR_UNSUPPORTED, "flip: W > %d unsupported", (FLIP_SMEM - 32) / 6);
+    if (B == 0) return LFX_OK;
+    const int rb = W * 3;
+    int rows = max(1, (FLIP_SMEM - 32) / 2 / rb);
+    rows = min(rows, H);
+    // keep chunk byte offsets 16-byte aligned when possible (fast vector path)
+    if (rows >= 16) rows &= ~15;
+    const size_t smem = (size_t)((rows * rb + 15) & ~15) * 2;
+    dim3 grid(lfx_div_up(H, rows), B);
+    k_flip<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, rows, mode);
+    return lfx_check_launch("flip");
+}
+
+extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,
+                             const int32_t* params, int fill, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && dst && params && B >= 0 && H > 0 && W > 0 && B <= 65535 && dst_image_stride > 0, LFX_ERR_ARG,
+                "rotate_nn: bad arguments");
+    LFX_REQUIRE(H < 32768 && W < 32768, LFX_ERR_UNSUPPORTED, "rotate_nn: fixed-point path needs sizes < 32768");
+    if (B == 0) return LFX_OK;
+    const long long max_px = dst_image_stride / 3;
+    dim3 grid(lfx_div_up(max_px, THREADS * 4), B);
+    k_rotate_nn<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill);
+    return lfx_check_launch("rotate_nn");
+}
+
+extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, const double* coef,
+                                const int32_t* perspective, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
+                "warp_bicubic: bad arguments");
+    if (B == 0) return LFX_OK;
+    dim3 grid(lfx_div_up((long long)H * W, THREADS * 4), B);
+    k_warp_bicubic<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective);
+    return lfx_check_launch("warp_bicubic");
+}
+
+extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, int H, int W, const int32_t* box,
+                                int OH, int OW, const int32_t* tab_bounds, const int32_t* tab_kk, int kstride,
+                                const int32_t* tab_off, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && dst && box && tab_bounds && tab_kk && tab_off && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 &&
+                    kstride > 0 && B <= 65535,
+                LFX_ERR_ARG, "crop_lanczos: bad arguments");
+    const size_t smem = (size_t)H * LZ_TW * 3;
+    LFX_REQUIRE(smem <= 200 * 1024, LFX_ERR_UNSUPPORTED, "crop_lanczos: H > %d unsupported", 200 * 1024 / (LZ_TW * 3));
+    if (B == 0) return LFX_OK;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(k_crop_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    dim3 grid(lfx_div_up(OW, LZ_TW), B);
+    k_crop_lanczos<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
+                                                                  kstride, tab_off);
+    return lfx_check_launch("crop_lanczos");
+}
+
+extern "C" int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W, const int32_t* cut,
+                           int32_t* hist_ws, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && noise && dst && cut && hist_ws && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
+                "distort: bad arguments");
+    LFX_REQUIRE((long long)H * W * 3 < (1ll << 31), LFX_ERR_UNSUPPORTED, "distort: image too large");
+    if (B == 0) return LFX_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nbytes = H * W * 3;
+    cudaError_t e = cudaMemsetAsync(hist_ws, 0, (size_t)B * 768 * sizeof(int32_t), st);
+    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "distort memset: %s", cudaGetErrorString(e));
+    int pb = 0;
+    const int chunks = chunking(nbytes, 48 * 64, B, &pb);
+    dim3 grid(chunks, B);
+    k_distort_hist<<<grid, THREADS, 0, st>>>(src, noise, hist_ws, nbytes, pb);
+    k_distort_lut<<<lfx_div_up((long long)B * 3, 8), 256, 0, st>>>(hist_ws, cut, B);
+    k_distort_apply<<<grid, THREADS, 0, st>>>(src, noise, dst, hist_ws, nbytes, pb);
+    return lfx_check_launch("distort");
+}

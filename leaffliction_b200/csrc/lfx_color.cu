@@ -1,0 +1,314 @@
+// Per-pixel colour kernels: cvtColor, fused threshold masks, apply_mask, colour statistics.
+// HBM-bound streaming kernels: 16-byte coalesced loads into shared tiles, 4 pixels per thread,
+// LUTs in shared memory, warp-private histogram updates merged with atomics.
+#include "lfx_common.cuh"
+
+namespace {
+
+constexpr int TILE_PX = 1024;  // pixels per block iteration (256 threads x 4 pixels)
+constexpr int THREADS = 256;
+
+// ------------------------------------------------------------------------------ cvtColor
+template <int CODE>
+__global__ void __launch_bounds__(THREADS) k_cvt_color(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                       long long npix, const LfxTables* __restrict__ tab) {
+    __shared__ __align__(16) uint8_t s_in[TILE_PX * 3];
+    __shared__ __align__(16) uint8_t s_out[TILE_PX * 3];
+    __shared__ HsvLut s_hsv;
+    __shared__ LabLut s_lab;
+    if (CODE == 1) load_hsv_lut(&s_hsv, tab);
+    if (CODE == 2) load_lab_lut(&s_lab, tab);
+    const long long ntiles = (npix + TILE_PX - 1) / TILE_PX;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * TILE_PX;
+        const int n = (int)min((long long)TILE_PX, npix - base);
+        block_load_bytes(s_in, src + base * 3, n * 3);
+        __syncthreads();
+        const int p0 = threadIdx.x * 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = p0 + k;
+            if (p < n) {
+                const int r = s_in[p * 3], g = s_in[p * 3 + 1], b = s_in[p * 3 + 2];
+                if (CODE == 0) {
+                    s_out[p] = (uint8_t)rgb2gray(r, g, b);
+                } else if (CODE == 1) {
+                    int h, s, v;
+                    rgb2hsv(r, g, b, &s_hsv, h, s, v);
+                    s_out[p * 3] = (uint8_t)h;
+                    s_out[p * 3 + 1] = (uint8_t)s;
+                    s_out[p * 3 + 2] = (uint8_t)v;
+                } else {
+                    int L, A, Bv;
+                    rgb2lab(r, g, b, &s_lab, L, A, Bv);
+                    s_out[p * 3] = (uint8_t)L;
+                    s_out[p * 3 + 1] = (uint8_t)A;
+                    s_out[p * 3 + 2] = (uint8_t)Bv;
+                }
+            }
+        }
+        __syncthreads();
+        if (CODE == 0)
+            block_store_bytes(dst + base, s_out, n);
+        else
+            block_store_bytes(dst + base * 3, s_out, n * 3);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ threshold masks
+struct ThreshParams {
+    int strategy;  // 0 hsv_h, 1 lab
+    int green_lo, green_hi;
+};
+
+__global__ void __launch_bounds__(THREADS) k_threshold_mask(const uint8_t* __restrict__ src, uint8_t* __restrict__ mask,
+                                                            long long npix, ThreshParams prm,
+                                                            const LfxTables* __restrict__ tab) {
+    __shared__ __align__(16) uint8_t s_in[TILE_PX * 3];
+    __shared__ __align__(16) uint8_t s_out[TILE_PX];
+    __shared__ HsvLut s_hsv;
+    __shared__ LabLut s_lab;
+    if (prm.strategy == 0)
+        load_hsv_lut(&s_hsv, tab);
+    else
+        load_lab_lut(&s_lab, tab);
+    const long long ntiles = (npix + TILE_PX - 1) / TILE_PX;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * TILE_PX;
+        const int n = (int)min((long long)TILE_PX, npix - base);
+        block_load_bytes(s_in, src + base * 3, n * 3);
+        __syncthreads();
+        const int p0 = threadIdx.x * 4;
+        uint32_t packed = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int p = p0 + k;
+            bool on = false;
+            if (p < n) {
+                const int r = s_in[p * 3], g = s_in[p * 3 + 1], b = s_in[p * 3 + 2];
+                if (prm.strategy == 0) {
+                    int h, s, v;
+                    rgb2hsv(r, g, b, &s_hsv, h, s, v);
+                    on = (h >= prm.green_lo) && (h <= prm.green_hi) && (s >= 40);  // mask.py:90
+                } else {
+                    int L, A, Bv;
+                    rgb2lab(r, g, b, &s_lab, L, A, Bv);
+                    on = (A <= 135) && (Bv >= 115) && (Bv <= 170);  // mask.py:105
+                }
+            }
+            packed |= (on ? 0xFFu : 0u) << (8 * k);
+        }
+        reinterpret_cast<uint32_t*>(s_out)[threadIdx.x] = packed;
+        __syncthreads();
+        block_store_bytes(mask + base, s_out, n);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ apply_mask
+__global__ void __launch_bounds__(THREADS) k_apply_mask(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                        uint8_t* __restrict__ dst, long long npix, int color_val) {
+    __shared__ __align__(16) uint8_t s_in[TILE_PX * 3];
+    __shared__ __align__(16) uint8_t s_m[TILE_PX];
+    const long long ntiles = (npix + TILE_PX - 1) / TILE_PX;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long base = tile * TILE_PX;
+        const int n = (int)min((long long)TILE_PX, npix - base);
+        block_load_bytes(s_in, src + base * 3, n * 3);
+        block_load_bytes(s_m, mask + base, n);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n * 3; i += THREADS) {
+            if (!(s_m[i / 3] > 127)) s_in[i] = (uint8_t)color_val;  // mask_utils.py:68,76
+        }
+        __syncthreads();
+        block_store_bytes(dst + base * 3, s_in, n * 3);
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------ colour statistics
+// One block handles a contiguous pixel range of ONE image.  Histograms live in shared memory,
+// replicated per warp pair to cut same-address contention, merged to global with atomicAdd.
+constexpr int HREP = 4;  // replicas of the 12x256 table (warp w uses replica w % HREP)
+
+__global__ void __launch_bounds__(THREADS) k_color_stats(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                         int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3,
+                                                         int32_t* __restrict__ counters, int HW, int px_per_block,
+                                                         const LfxTables* __restrict__ tab) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    // layout: hist[HREP][12][256] u32 | cnt[16] | in tile | mask tile | luts
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* s_cnt = s_hist + HREP * 12 * 256;
+    uint8_t* s_in = reinterpret_cast<uint8_t*>(s_cnt + 16);
+    uint8_t* s_m = s_in + TILE_PX * 3;
+    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(s_m + TILE_PX);
+    LabLut* s_lab = reinterpret_cast<LabLut*>(s_hsv + 1);
+
+    const int img = blockIdx.y;
+    const int begin = blockIdx.x * px_per_block;
+    const int end = min(HW, begin + px_per_block);
+    if (begin >= end) return;
+    const bool want9 = hist9 != nullptr;
+    const bool wantS = (hsv3 != nullptr) || (counters != nullptr);
+
+    for (int i = threadIdx.x; i < HREP * 12 * 256 + 16; i += THREADS) s_hist[i] = 0;
+    load_hsv_lut(s_hsv, tab);
+    if (want9) load_lab_lut(s_lab, tab);
+    __syncthreads();
+
+    uint32_t* myh = s_hist + ((threadIdx.x >> 5) % HREP) * 12 * 256;
+    uint32_t c[14];
+#pragma unroll
+    for (int i = 0; i < 14; ++i) c[i] = 0;
+
+    const uint8_t* simg = src + (size_t)img * HW * 3;
+    const uint8_t* mimg = mask ? mask + (size_t)img * HW : nullptr;
+    for (int base = begin; base < end; base += TILE_PX) {
+        const int n = min(TILE_PX, end - base);
+        block_load_bytes(s_in, simg + (size_t)base * 3, n * 3);
+        if (mimg) block_load_bytes(s_m, mimg + base, n);
+        __syncthreads();
+        // stride-THREADS pixel assignment: lanes of a warp read neighbouring pixels (bank-friendly)
+        for (int p = threadIdx.x; p < n; p += THREADS) {
+            const int mk = mimg ? s_m[p] : 255;
+            if (mk == 0) continue;
+            const int r = s_in[p * 3], g = s_in[p * 3 + 1], b = s_in[p * 3 + 2];
+            int h, s, v;
+            rgb2hsv(r, g, b, s_hsv, h, s, v);
+            if (want9) {
+                int L, A, Bv;
+                rgb2lab(r, g, b, s_lab, L, A, Bv);
+                atomicAdd(&myh[0 * 256 + r], 1u);
+                atomicAdd(&myh[1 * 256 + g], 1u);
+                atomicAdd(&myh[2 * 256 + b], 1u);
+                atomicAdd(&myh[3 * 256 + h], 1u);
+                atomicAdd(&myh[4 * 256 + s], 1u);
+                atomicAdd(&myh[5 * 256 + v], 1u);
+                atomicAdd(&myh[6 * 256 + L], 1u);
+                atomicAdd(&myh[7 * 256 + A], 1u);
+                atomicAdd(&myh[8 * 256 + Bv], 1u);
+            }
+            // apply_mask binarises at >127 and paints the rest white (s = 0): never in leaf_mask
+            if (wantS && mk > 127 && s > 10 && v > 15 && v < 245) {  // hist.py:188
+                atomicAdd(&myh[9 * 256 + h], 1u);
+                atomicAdd(&myh[10 * 256 + s], 1u);
+                atomicAdd(&myh[11 * 256 + v], 1u);
+                c[0] += 1;
+                c[1] += (h >= 35 && h <= 85 && s >= 40 && v >= 30);                 // Vert Sain
+                c[2] += (h >= 20 && h <= 40 && s >= 25 && v >= 30);                 // Vert Jaunatre
+                c[3] += (h >= 15 && h <= 35 && s >= 50 && v >= 50);                 // Jaune
+                c[4] += ((h <= 25 || h >= 160) && s >= 30 && v >= 20);              // Brun/Orange
+                c[5] += (((h >= 160 && h <= 180) || h <= 10) && s >= 40 && v >= 30);  // Rouge
+                c[6] += (v <= 50 && s >= 20);                                       // Zones Sombres
+                c[7] += (v >= 200 && s <= 30);                                      // Zones Claires
+                c[8] += (h >= 120 && h <= 160 && s >= 20);                          // Violet/Pourpre
+                c[9] += (h >= 35 && h <= 85);                                       // hue ranges :248-256
+                c[10] += (h >= 15 && h <= 35);
+                c[11] += (h <= 15 || h >= 160);
+                c[12] += (h >= 120 && h <= 160);
+                c[13] += (h > 85 && h < 120);
+            }
+        }
+        __syncthreads();
+    }
+    if (counters) {
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            uint32_t v = c[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[i], v);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 12 * 256; i += THREADS) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int rj = 0; rj < HREP; ++rj) v += s_hist[rj * 12 * 256 + i];
+        if (!v) continue;
+        if (i < 9 * 256) {
+            if (hist9) atomicAdd(&hist9[(size_t)img * 9 * 256 + i], (int)v);
+        } else if (hsv3) {
+            atomicAdd(&hsv3[(size_t)img * 3 * 256 + (i - 9 * 256)], (int)v);
+        }
+    }
+    if (counters && threadIdx.x < 14 && s_cnt[threadIdx.x])
+        atomicAdd(&counters[(size_t)img * 16 + threadIdx.x], (int)s_cnt[threadIdx.x]);
+}
+
+constexpr size_t STATS_SMEM = (HREP * 12 * 256 + 16) * 4 + TILE_PX * 3 + TILE_PX + sizeof(HsvLut) + sizeof(LabLut);
+
+int stream_grid(long long npix) {
+    const long long ntiles = (npix + TILE_PX - 1) / TILE_PX;
+    const long long cap = (long long)LFX_NUM_SMS * 8;
+    return (int)(ntiles < cap ? ntiles : cap);
+}
+
+}  // namespace
+
+extern "C" int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int W, int code, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && dst && B >= 0 && H > 0 && W > 0 && code >= 0 && code <= 2, LFX_ERR_ARG, "cvt_color: bad arguments");
+    if (B == 0) return LFX_OK;
+    const long long npix = (long long)B * H * W;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = stream_grid(npix);
+    if (code == 0)
+        k_cvt_color<0><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
+    else if (code == 1)
+        k_cvt_color<1><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
+    else
+        k_cvt_color<2><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
+    return lfx_check_launch("cvt_color");
+}
+
+extern "C" int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int H, int W, const lfx_mask_cfg* cfg,
+                                  lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && mask && cfg && B >= 0 && H > 0 && W > 0, LFX_ERR_ARG, "threshold_mask: bad arguments");
+    LFX_REQUIRE(cfg->strategy == 0 || cfg->strategy == 1, LFX_ERR_UNSUPPORTED,
+                "threshold_mask: strategy %d needs lfx_make_mask (Otsu) or an external front end", cfg->strategy);
+    if (B == 0) return LFX_OK;
+    const long long npix = (long long)B * H * W;
+    ThreshParams prm{cfg->strategy, cfg->green_lo, cfg->green_hi};
+    k_threshold_mask<<<stream_grid(npix), THREADS, 0, (cudaStream_t)stream>>>(src, mask, npix, prm, lfx_tables());
+    return lfx_check_launch("threshold_mask");
+}
+
+extern "C" int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,
+                              int color_val, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && mask && dst && B >= 0 && H > 0 && W > 0 && color_val >= 0 && color_val <= 255, LFX_ERR_ARG,
+                "apply_mask: bad arguments");
+    if (B == 0) return LFX_OK;
+    const long long npix = (long long)B * H * W;
+    k_apply_mask<<<stream_grid(npix), THREADS, 0, (cudaStream_t)stream>>>(src, mask, dst, npix, color_val);
+    return lfx_check_launch("apply_mask");
+}
+
+extern "C" int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t* hist9, int32_t* hsv3,
+                               int32_t* counters, int B, int H, int W, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(src && B >= 0 && H > 0 && W > 0 && (hist9 || hsv3 || counters), LFX_ERR_ARG, "color_stats: bad arguments");
+    LFX_REQUIRE((long long)H * W < (1ll << 31), LFX_ERR_UNSUPPORTED, "color_stats: image too large");
+    if (B == 0) return LFX_OK;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_color_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STATS_SMEM);
+        attr_set = true;
+    }
+    const int HW = H * W;
+    // enough blocks to fill the GPU (>= 4 per SM) without shrinking chunks below 4 tiles
+    int chunks = lfx_div_up((long long)LFX_NUM_SMS * 4, B);
+    const int max_chunks = max(1, HW / (TILE_PX * 4));
+    chunks = max(1, min(chunks, max_chunks));
+    int px_per_block = lfx_div_up(HW, chunks);
+    px_per_block = lfx_div_up(px_per_block, TILE_PX) * TILE_PX;
+    chunks = lfx_div_up(HW, px_per_block);
+    dim3 grid(chunks, B);
+    LFX_REQUIRE(B <= 65535, LFX_ERR_UNSUPPORTED, "color_stats: B > 65535, split the batch");
+    k_color_stats<<<grid, THREADS, STATS_SMEM, (cudaStream_t)stream>>>(src, mask, hist9, hsv3, counters, HW, px_per_block,
+                                                                       lfx_tables());
+    return lfx_check_launch("color_stats");
+}

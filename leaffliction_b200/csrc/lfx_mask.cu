@@ -1,0 +1,780 @@
+// make_mask / _postprocess_mask on the GPU (srcs/transform/filters/mask.py:53-69,335-411,548-582).
+//
+// One persistent thread block per image.  Masks are bit-packed (32 px / word) and live in shared
+// memory for images up to ~512x512 (global scratch otherwise); morphology is word-parallel funnel
+// shifts; connected components are run-based union-find (runs found with bit tricks, ids by
+// prefix-sum of run starts, unions with atomicMin); findContours -> max(contourArea) ->
+// drawContours(filled) is restated with local counts:
+//   outside  = 4-connected background touching the border,  filled = ~outside,
+//   2*contourArea(component) = 2N - (P - Q1) - 2  over 8-connected components of `filled`.
+#include <float.h>
+#include <math.h>
+
+#include "lfx_common.cuh"
+
+namespace {
+
+constexpr int MT = 512;          // threads per block
+constexpr int NPLANES = 6;       // P0 raw, PB brown, PR result, T1..T3 temps
+constexpr int RCAP_SMEM = 2048;  // runs kept in shared memory; larger tables use global scratch
+constexpr int STAGE_BYTES = 6144;
+
+struct FootRow {
+    int8_t dy, o1, o2, pad;
+};
+struct Footprint {
+    int n;
+    FootRow r[20];
+};
+
+struct MaskParams {
+    lfx_mask_cfg cfg;
+    Footprint fp_morph, fp_brown, fp_search;
+    int H, W, WPR, NW;
+    uint32_t lastmask;
+    int planes_in_smem;
+    int rcap_glob;
+    int stage_rows;
+    int mode;  // 0 make_mask, 1 postprocess only
+    unsigned long long ws_per_block;
+};
+
+struct Ctx {
+    int H, W, WPR, NW;
+    uint32_t lastmask;
+    uint32_t* plane[NPLANES];
+    int* wbase;
+    // run tables (current selection) + both backing stores
+    int* parent;
+    uint32_t* geom;
+    int* acc;
+    uint16_t* ry;
+    int *sm_parent, *gl_parent;
+    uint32_t *sm_geom, *gl_geom;
+    int *sm_acc, *gl_acc;
+    uint16_t *sm_ry, *gl_ry;
+    int rcap_glob;
+    int R;
+    // scratch
+    int* s_tmp;                  // [40]
+    unsigned long long* s_best;  // [1]
+    int* s_bb;                   // [8]
+    int* s_hist;                 // [256]
+    int status;
+};
+
+__device__ __forceinline__ uint32_t valid_mask(const Ctx& c, int w) { return (w == c.WPR - 1) ? c.lastmask : 0xFFFFFFFFu; }
+
+// ---------------------------------------------------------------- block primitives
+__device__ int block_exscan(int v, int* s_tmp, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < MT / 32) ? s_tmp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < MT / 32) s_tmp[lane] = winc - w;
+        if (lane == 31) s_tmp[32] = winc;
+    }
+    __syncthreads();
+    const int res = s_tmp[wid] + inc - v;
+    total = s_tmp[32];
+    __syncthreads();
+    return res;
+}
+
+__device__ __forceinline__ void plane_zero(uint32_t* p, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) p[i] = 0;
+}
+__device__ __forceinline__ void plane_copy(uint32_t* d, const uint32_t* s, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------- morphology
+template <bool DIL>
+__device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        const int y = i / c.WPR, w = i - y * c.WPR;
+        uint32_t acc = DIL ? 0u : 0xFFFFFFFFu;
+        for (int k = 0; k < fp.n; ++k) {
+            const int yy = y + fp.r[k].dy;
+            if (yy < 0 || yy >= c.H) continue;  // outside rows are ignored by both min and max
+            const uint32_t* row = in + yy * c.WPR;
+            const uint32_t oob = DIL ? 0u : 0xFFFFFFFFu;
+            uint32_t cur = row[w];
+            if (!DIL && w == c.WPR - 1) cur |= ~c.lastmask;
+            uint32_t prev = (w > 0) ? row[w - 1] : oob;
+            uint32_t next = oob;
+            if (w + 1 < c.WPR) {
+                next = row[w + 1];
+                if (!DIL && w + 1 == c.WPR - 1) next |= ~c.lastmask;
+            }
+            const int o1 = fp.r[k].o1, o2 = fp.r[k].o2;
+            for (int o = o1; o <= o2; ++o) {
+                // bit x of v = source bit (x + o)
+                const uint32_t v = (o < 0) ? __funnelshift_r(prev, cur, 32 + o) : __funnelshift_r(cur, next, o);
+                acc = DIL ? (acc | v) : (acc & v);
+            }
+        }
+        out[i] = acc & valid_mask(c, w);
+    }
+}
+
+// ---------------------------------------------------------------- runs + union-find
+__device__ __forceinline__ uint32_t starts_of(const uint32_t* m, int idx, int w) {
+    const uint32_t cur = m[idx];
+    const uint32_t pb = (w > 0) ? (m[idx - 1] >> 31) : 0u;
+    return cur & ~((cur << 1) | pb);
+}
+
+__device__ __forceinline__ int uf_find(const int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        x = p;
+        p = parent[x];
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
+// (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
+template <int CONN>
+__device__ void ccl(const uint32_t* m, Ctx& c) {
+    const int per = (c.NW + MT - 1) / MT;
+    const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += __popc(starts_of(m, i, i % c.WPR));
+    int total;
+    int base = block_exscan(cnt, c.s_tmp, total);
+    for (int i = i0; i < i1; ++i) {
+        c.wbase[i] = base;
+        base += __popc(starts_of(m, i, i % c.WPR));
+    }
+    c.R = total;
+    if (total <= RCAP_SMEM) {
+        c.parent = c.sm_parent; c.geom = c.sm_geom; c.acc = c.sm_acc; c.ry = c.sm_ry;
+    } else {
+        c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
+        c.status |= 2;
+    }
+    __syncthreads();
+    int* parent = c.parent;
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        const int y = i / c.WPR, w = i - y * c.WPR;
+        uint32_t st = starts_of(m, i, w);
+        int id = c.wbase[i];
+        const uint32_t word = m[i];
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            const int x0 = w * 32 + b;
+            const uint32_t inv = ~(word >> b);
+            const int z = __ffs(inv) - 1;  // first zero at/after b (relative); -1 if none
+            int x1;
+            if (inv != 0 && z < 32 - b) {
+                x1 = x0 + z - 1;
+            } else {
+                x1 = w * 32 + 31;
+                int ww = w + 1;
+                while (ww < c.WPR) {
+                    const uint32_t nx = m[y * c.WPR + ww];
+                    if (nx == 0xFFFFFFFFu) {
+                        x1 += 32;
+                        ++ww;
+                        continue;
+                    }
+                    x1 += __ffs(~nx) - 1;
+                    break;
+                }
+            }
+            c.geom[id] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+            c.ry[id] = (uint16_t)y;
+            parent[id] = id;
+            c.acc[id] = 0;
+            ++id;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int y = c.ry[r];
+        if (y == 0) continue;
+        const uint32_t g = c.geom[r];
+        const int x0 = g & 0xFFFF, x1 = g >> 16;
+        const int lo = max(0, x0 - (CONN == 8 ? 1 : 0)), hi = min(c.W - 1, x1 + (CONN == 8 ? 1 : 0));
+        const uint32_t* up = m + (y - 1) * c.WPR;
+        int p = lo;
+        while (p <= hi) {
+            int wi = p >> 5;
+            uint32_t v = up[wi] & (0xFFFFFFFFu << (p & 31));
+            while (v == 0) {
+                ++wi;
+                if (wi * 32 > hi) break;
+                v = up[wi];
+            }
+            if (v == 0) break;
+            const int b = __ffs(v) - 1;
+            if (wi * 32 + b > hi) break;
+            const int idxw = (y - 1) * c.WPR + wi;
+            const uint32_t st = starts_of(m, idxw, wi);
+            const int id2 = c.wbase[idxw] + __popc(st & ((2u << b) - 1u)) - 1;
+            uf_unite(parent, r, id2);
+            p = (int)(c.geom[id2] >> 16) + 1;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int root = uf_find(parent, r);
+        // benign race: other threads may still chase through parent[r]; any value on the
+        // path is an ancestor, so their walks still end at the same root
+        parent[r] = root;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void set_run(uint32_t* out, int y, int x0, int x1, const Ctx& c) {
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t mk = 0xFFFFFFFFu;
+        if (w == w0) mk &= 0xFFFFFFFFu << (x0 & 31);
+        if (w == w1) mk &= 0xFFFFFFFFu >> (31 - (x1 & 31));
+        atomicOr(&out[y * c.WPR + w], mk);
+    }
+}
+
+__device__ __forceinline__ int popc_range(const uint32_t* row, int x0, int x1) {
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    int n = 0;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t mk = 0xFFFFFFFFu;
+        if (w == w0) mk &= 0xFFFFFFFFu << (x0 & 31);
+        if (w == w1) mk &= 0xFFFFFFFFu >> (31 - (x1 & 31));
+        n += __popc(row[w] & mk);
+    }
+    return n;
+}
+__device__ __forceinline__ int get_bit(const uint32_t* m, int y, int x, const Ctx& c) {
+    if (y < 0 || y >= c.H || x < 0 || x >= c.W) return 0;
+    return (m[y * c.WPR + (x >> 5)] >> (x & 31)) & 1;
+}
+
+// acc[root] += pixels
+__device__ void measure_area(Ctx& c) {
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        const uint32_t g = c.geom[r];
+        atomicAdd(&c.acc[c.parent[r]], (int)(g >> 16) - (int)(g & 0xFFFF) + 1);
+    }
+    __syncthreads();
+}
+
+// out = runs whose component has >= min_area pixels (out must be zeroed + synced by the caller)
+__device__ void keep_area_ge(uint32_t* out, int min_area, Ctx& c) {
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        if (c.acc[c.parent[r]] >= min_area) {
+            const uint32_t g = c.geom[r];
+            set_run(out, c.ry[r], g & 0xFFFF, g >> 16, c);
+        }
+    }
+    __syncthreads();
+}
+
+// largest_contour + contour_to_mask (Transformation.py:285-299) on plane `in`.
+// Temps: tA (inverted / filled), out receives the selected filled component (zero when none).
+// info8: {found,x,y,w,h,area2,npix,-}.  Returns found (block-uniform).
+__device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out, int* info8, Ctx& c) {
+    // outside = 4-connected background reachable from the border
+    for (int i = threadIdx.x; i < c.NW; i += MT) tA[i] = ~in[i] & valid_mask(c, i % c.WPR);
+    __syncthreads();
+    ccl<4>(tA, c);
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        const uint32_t g = c.geom[r];
+        const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+        if (y == 0 || y == c.H - 1 || x0 == 0 || x1 == c.W - 1) atomicOr(&c.acc[c.parent[r]], 1);
+    }
+    __syncthreads();
+    // filled = in | enclosed background.  Built in `out`, then moved to tA (tA is still the ccl input).
+    plane_copy(out, in, c);
+    __syncthreads();
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        if (!c.acc[c.parent[r]]) {
+            const uint32_t g = c.geom[r];
+            set_run(out, c.ry[r], g & 0xFFFF, g >> 16, c);
+        }
+    }
+    __syncthreads();
+    plane_copy(tA, out, c);
+    __syncthreads();
+    ccl<8>(tA, c);
+    // per-run contribution to 2N - (P - Q1):  popc(up) + popc(down) - 2 + Q1
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        const uint32_t g = c.geom[r];
+        const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+        int v = -2;
+        if (y > 0) v += popc_range(tA + (y - 1) * c.WPR, x0, x1);
+        if (y < c.H - 1) v += popc_range(tA + (y + 1) * c.WPR, x0, x1);
+        v += (!get_bit(tA, y + 1, x1, c) && !get_bit(tA, y + 1, x1 + 1, c));
+        v += (!get_bit(tA, y + 1, x0, c) && !get_bit(tA, y + 1, x0 - 1, c));
+        v += (!get_bit(tA, y - 1, x1, c) && !get_bit(tA, y - 1, x1 + 1, c));
+        v += (!get_bit(tA, y - 1, x0, c) && !get_bit(tA, y - 1, x0 - 1, c));
+        atomicAdd(&c.acc[c.parent[r]], v);
+    }
+    if (threadIdx.x == 0) {
+        *c.s_best = 0ull;
+        c.s_bb[0] = 0x7fffffff; c.s_bb[1] = 0x7fffffff; c.s_bb[2] = -1; c.s_bb[3] = -1; c.s_bb[4] = 0;
+    }
+    __syncthreads();
+    // argmax of (area2, first-pixel order): ties go to the LARGEST root id (reverse discovery order)
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        if (c.parent[r] == r) {
+            const unsigned long long key = ((unsigned long long)(uint32_t)(c.acc[r] - 2 + 1) << 32) | (uint32_t)r;
+            atomicMax(c.s_best, key);
+        }
+    }
+    __syncthreads();
+    const unsigned long long best = *c.s_best;
+    plane_zero(out, c);
+    __syncthreads();
+    if (best == 0ull) {
+        if (threadIdx.x < 8) info8[threadIdx.x] = 0;
+        __syncthreads();
+        return false;
+    }
+    const int win = (int)(best & 0xFFFFFFFFu);
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        if (c.parent[r] == win) {
+            const uint32_t g = c.geom[r];
+            const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+            set_run(out, y, x0, x1, c);
+            atomicMin(&c.s_bb[0], x0);
+            atomicMin(&c.s_bb[1], y);
+            atomicMax(&c.s_bb[2], x1);
+            atomicMax(&c.s_bb[3], y);
+            atomicAdd(&c.s_bb[4], x1 - x0 + 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info8[0] = 1;
+        info8[1] = c.s_bb[0];
+        info8[2] = c.s_bb[1];
+        info8[3] = c.s_bb[2] - c.s_bb[0] + 1;
+        info8[4] = c.s_bb[3] - c.s_bb[1] + 1;
+        info8[5] = (int)(best >> 32) - 1;
+        info8[6] = c.s_bb[4];
+    }
+    __syncthreads();
+    return true;
+}
+
+// _postprocess_mask (mask.py:53-69): raw -> result plane `out`; temps t1..t3.
+// When no contour exists, `out` holds the opened mask (reference returns (opened, None)).
+__device__ bool postprocess(const uint32_t* raw, uint32_t* out, uint32_t* t1, uint32_t* t2, uint32_t* t3, int* info8,
+                            const MaskParams& P, Ctx& c) {
+    // pcv.fill: drop 4-connected components with < fill_size pixels
+    ccl<4>(raw, c);
+    measure_area(c);
+    plane_zero(t1, c);
+    __syncthreads();
+    keep_area_ge(t1, P.cfg.fill_size, c);
+    // close = erode(dilate), open = dilate(erode)
+    morph<true>(t1, t2, P.fp_morph, c);
+    __syncthreads();
+    morph<false>(t2, t3, P.fp_morph, c);
+    __syncthreads();
+    morph<false>(t3, t2, P.fp_morph, c);
+    __syncthreads();
+    morph<true>(t2, t1, P.fp_morph, c);
+    __syncthreads();
+    // t1 = opened
+    const bool found = largest_external(t1, t2, out, info8, c);
+    if (!found) {
+        plane_copy(out, t1, c);
+        __syncthreads();
+    }
+    return found;
+}
+
+// cv::getThreshVal_Otsu_8u on a 256-bin histogram (float64, no FMA contraction).
+__device__ int otsu_threshold(const int* h, int n) {
+    const double scale = __ddiv_rn(1.0, (double)n);
+    double mu = 0.0;
+    for (int i = 0; i < 256; ++i) mu = __dadd_rn(mu, __dmul_rn((double)i, (double)h[i]));
+    mu = __dmul_rn(mu, scale);
+    double mu1 = 0.0, q1 = 0.0, max_sigma = 0.0;
+    int max_val = 0;
+    const double eps = (double)FLT_EPSILON, one_m_eps = 1.0 - (double)FLT_EPSILON;
+    for (int i = 0; i < 256; ++i) {
+        const double p_i = __dmul_rn((double)h[i], scale);
+        mu1 = __dmul_rn(mu1, q1);
+        q1 = __dadd_rn(q1, p_i);
+        const double q2 = __dadd_rn(1.0, -q1);
+        if (fmin(q1, q2) < eps || fmax(q1, q2) > one_m_eps) continue;
+        mu1 = __ddiv_rn(__dadd_rn(mu1, __dmul_rn((double)i, p_i)), q1);
+        const double mu2 = __ddiv_rn(__dadd_rn(mu, -__dmul_rn(q1, mu1)), q2);
+        const double dm = __dadd_rn(mu1, -mu2);
+        const double sigma = __dmul_rn(__dmul_rn(__dmul_rn(q1, q2), dm), dm);
+        if (sigma > max_sigma) {
+            max_sigma = sigma;
+            max_val = i;
+        }
+    }
+    return max_val;
+}
+
+// Pixel pass over the RGB image.  PASS 0: strategy predicate -> p0 (strategies 0/1) and brown
+// predicate -> pb.  PASS 1: histogram of HSV channel `chan` into c.s_hist.  PASS 2: p0 = chan > thr
+// (light) or chan <= thr (dark).
+template <int PASS>
+__device__ void pixel_pass(const uint8_t* img, uint8_t* s_stage, const HsvLut* hsv, const LabLut* lab, uint32_t* p0,
+                           uint32_t* pb, int chan, int thr, bool dark, const MaskParams& P, Ctx& c) {
+    const int rb = c.W * 3;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int y0 = 0; y0 < c.H; y0 += P.stage_rows) {
+        const int nrows = min(P.stage_rows, c.H - y0);
+        block_load_bytes(s_stage, img + (size_t)y0 * rb, nrows * rb);
+        __syncthreads();
+        for (int item = wid; item < nrows * c.WPR; item += MT / 32) {
+            const int ry = item / c.WPR, w = item - ry * c.WPR;
+            const int x = w * 32 + lane;
+            bool b0 = false, b1 = false;
+            if (x < c.W) {
+                const uint8_t* px = s_stage + ry * rb + x * 3;
+                const int r = px[0], g = px[1], b = px[2];
+                int h, s, v;
+                if (PASS == 0) {
+                    rgb2hsv(r, g, b, hsv, h, s, v);
+                    if (P.cfg.strategy == 0) b0 = (h >= P.cfg.green_lo) && (h <= P.cfg.green_hi) && (s >= 40);
+                    int L = 0, A = 0, Bv = 0;
+                    if (P.cfg.strategy == 1 || P.cfg.use_lab_brown) rgb2lab(r, g, b, lab, L, A, Bv);
+                    if (P.cfg.strategy == 1) b0 = (A <= 135) && (Bv >= 115) && (Bv <= 170);
+                    b1 = P.cfg.use_lab_brown
+                             ? ((A >= P.cfg.lab_a_min) && (Bv >= P.cfg.lab_b_min))
+                             : ((h >= P.cfg.brown_lo) && (h <= P.cfg.brown_hi) && (s >= P.cfg.brown_s_min) &&
+                                (v <= P.cfg.brown_v_max));
+                } else {
+                    // PlantCV's rgb2gray_hsv reads the array as BGR: only the hue channel differs
+                    if (chan == 0)
+                        rgb2hsv(b, g, r, hsv, h, s, v);
+                    else
+                        rgb2hsv(r, g, b, hsv, h, s, v);
+                    const int val = chan == 0 ? h : (chan == 1 ? s : v);
+                    if (PASS == 1) atomicAdd(&c.s_hist[val], 1);
+                    if (PASS == 2) b0 = dark ? (val <= thr) : (val > thr);
+                }
+            }
+            if (PASS != 1) {
+                const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
+                const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
+                if (lane == 0) {
+                    const int idx = (y0 + ry) * c.WPR + w;
+                    if (PASS == 2 || P.cfg.strategy <= 1) p0[idx] = m0;
+                    if (PASS == 0) pb[idx] = m1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// raw mask bytes -> bit plane
+__device__ void bytes_to_plane(const uint8_t* raw, uint32_t* p, const Ctx& c) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int item = wid; item < c.NW; item += MT / 32) {
+        const int y = item / c.WPR, w = item - y * c.WPR;
+        const int x = w * 32 + lane;
+        const bool on = (x < c.W) && (__ldg(raw + (size_t)y * c.W + x) > 0);
+        const uint32_t m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) p[item] = m;
+    }
+}
+
+__device__ void plane_to_bytes(const uint32_t* p, uint8_t* mask, const Ctx& c) {
+    if ((c.W & 3) == 0) {
+        const int gpr = c.W >> 2;
+        for (int i = threadIdx.x; i < c.H * gpr; i += MT) {
+            const int y = i / gpr, gx = i - y * gpr;
+            const int x = gx * 4;
+            const uint32_t bits = (p[y * c.WPR + (x >> 5)] >> (x & 31)) & 0xF;
+            const uint32_t v = ((bits & 1) ? 0xFFu : 0u) | ((bits & 2) ? 0xFF00u : 0u) | ((bits & 4) ? 0xFF0000u : 0u) |
+                               ((bits & 8) ? 0xFF000000u : 0u);
+            reinterpret_cast<uint32_t*>(mask)[(size_t)y * gpr + gx] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < c.H * c.W; i += MT) {
+            const int y = i / c.W, x = i - y * c.W;
+            mask[i] = ((p[y * c.WPR + (x >> 5)] >> (x & 31)) & 1) ? 255 : 0;
+        }
+    }
+}
+
+__device__ void otsu_plane(const uint8_t* img, uint8_t* s_stage, const HsvLut* hsv, uint32_t* p0, int chan, bool dark,
+                           const MaskParams& P, Ctx& c) {
+    for (int i = threadIdx.x; i < 256; i += MT) c.s_hist[i] = 0;
+    __syncthreads();
+    pixel_pass<1>(img, s_stage, hsv, nullptr, p0, nullptr, chan, 0, dark, P, c);
+    if (threadIdx.x == 0) c.s_tmp[33] = otsu_threshold(c.s_hist, c.H * c.W);
+    __syncthreads();
+    const int thr = c.s_tmp[33];
+    pixel_pass<2>(img, s_stage, hsv, nullptr, p0, nullptr, chan, thr, dark, P, c);
+}
+
+__global__ void __launch_bounds__(MT, 2) k_make_mask(const uint8_t* __restrict__ src, const uint8_t* __restrict__ raw,
+                                                     uint8_t* __restrict__ mask, int32_t* __restrict__ info, int B,
+                                                     const MaskParams P, uint8_t* __restrict__ ws,
+                                                     const LfxTables* __restrict__ tab) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    __shared__ int s_tmp[40];
+    __shared__ unsigned long long s_best;
+    __shared__ int s_bb[8];
+    __shared__ int s_hist[256];
+    __shared__ int s_info[8];
+
+    Ctx c;
+    c.H = P.H; c.W = P.W; c.WPR = P.WPR; c.NW = P.NW; c.lastmask = P.lastmask;
+    c.s_tmp = s_tmp; c.s_best = &s_best; c.s_bb = s_bb; c.s_hist = s_hist;
+    c.rcap_glob = P.rcap_glob;
+    // ---- carve shared memory
+    uint8_t* sp = sm;
+    uint8_t* gp = ws + (size_t)blockIdx.x * P.ws_per_block;
+    auto take = [](uint8_t*& p, size_t bytes) {
+        uint8_t* r = p;
+        p += (bytes + 15) & ~(size_t)15;
+        return r;
+    };
+    for (int k = 0; k < NPLANES; ++k)
+        c.plane[k] = reinterpret_cast<uint32_t*>(P.planes_in_smem ? take(sp, (size_t)P.NW * 4) : take(gp, (size_t)P.NW * 4));
+    c.wbase = reinterpret_cast<int*>(P.planes_in_smem ? take(sp, (size_t)(P.NW + 1) * 4) : take(gp, (size_t)(P.NW + 1) * 4));
+    c.sm_parent = reinterpret_cast<int*>(take(sp, RCAP_SMEM * 4));
+    c.sm_geom = reinterpret_cast<uint32_t*>(take(sp, RCAP_SMEM * 4));
+    c.sm_acc = reinterpret_cast<int*>(take(sp, RCAP_SMEM * 4));
+    c.sm_ry = reinterpret_cast<uint16_t*>(take(sp, RCAP_SMEM * 2));
+    c.gl_parent = reinterpret_cast<int*>(take(gp, (size_t)P.rcap_glob * 4));
+    c.gl_geom = reinterpret_cast<uint32_t*>(take(gp, (size_t)P.rcap_glob * 4));
+    c.gl_acc = reinterpret_cast<int*>(take(gp, (size_t)P.rcap_glob * 4));
+    c.gl_ry = reinterpret_cast<uint16_t*>(take(gp, (size_t)P.rcap_glob * 2));
+    uint8_t* s_stage = take(sp, (size_t)P.stage_rows * P.W * 3);
+    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(take(sp, sizeof(HsvLut)));
+    LabLut* s_lab = reinterpret_cast<LabLut*>(take(sp, sizeof(LabLut)));
+    const bool need_lab = (P.mode == 0) && (P.cfg.strategy == 1 || P.cfg.use_lab_brown);
+    load_hsv_lut(s_hsv, tab);
+    if (need_lab) load_lab_lut(s_lab, tab);
+    __syncthreads();
+
+    uint32_t *P0 = c.plane[0], *PB = c.plane[1], *PR = c.plane[2], *T1 = c.plane[3], *T2 = c.plane[4], *T3 = c.plane[5];
+    const size_t img_px = (size_t)P.H * P.W;
+
+    for (int img = blockIdx.x; img < B; img += gridDim.x) {
+        c.status = 0;
+        const uint8_t* simg = src ? src + img * img_px * 3 : nullptr;
+        // ---- raw candidate
+        if (P.mode == 1 || P.cfg.strategy == 4) {
+            bytes_to_plane(raw + img * img_px, P0, c);
+            if (P.mode == 0 && P.cfg.extend_brown) {
+                // brown predicate still comes from the RGB image; pixel_pass<0> leaves P0 alone
+                // when strategy > 1
+                __syncthreads();
+                pixel_pass<0>(simg, s_stage, s_hsv, s_lab, P0, PB, 0, 0, false, P, c);
+            }
+        } else if (P.cfg.strategy <= 1) {
+            pixel_pass<0>(simg, s_stage, s_hsv, s_lab, P0, PB, 0, 0, false, P, c);
+        } else {
+            // hsv_s (Otsu on S, 'light' unless dark_bg) / hsv_v_dark (Otsu on V, 'dark')
+            const int chan = P.cfg.strategy == 2 ? 1 : 2;
+            const bool dark = P.cfg.strategy == 2 ? (P.cfg.bg_dark != 0) : true;
+            otsu_plane(simg, s_stage, s_hsv, P0, chan, dark, P, c);
+            if (P.cfg.extend_brown) pixel_pass<0>(simg, s_stage, s_hsv, s_lab, P0, PB, 0, 0, false, P, c);
+        }
+        __syncthreads();
+
+        bool found = postprocess(P0, PR, T1, T2, T3, s_info, P, c);
+        if (P.mode == 0) {
+            // _find_best_mask rejects a lone candidate only when cnt is None or contourArea <= 1
+            if (!found || s_info[5] <= 2) {
+                c.status |= 1;
+                otsu_plane(simg, s_stage, s_hsv, P0, P.cfg.fallback_channel, false, P, c);
+                __syncthreads();
+                found = postprocess(P0, PR, T1, T2, T3, s_info, P, c);
+            }
+            if (P.cfg.extend_brown) {
+                // _extend_mask_with_brown_regions (mask.py:335-392)
+                morph<true>(PR, T1, P.fp_search, c);
+                __syncthreads();
+                morph<true>(T1, T2, P.fp_search, c);
+                __syncthreads();
+                for (int i = threadIdx.x; i < c.NW; i += MT) T1[i] = PB[i] & T2[i];
+                __syncthreads();
+                morph<false>(T1, T2, P.fp_brown, c);  // open
+                __syncthreads();
+                morph<true>(T2, T1, P.fp_brown, c);
+                __syncthreads();
+                morph<true>(T1, T2, P.fp_brown, c);  // close
+                __syncthreads();
+                morph<false>(T2, T1, P.fp_brown, c);
+                __syncthreads();
+                ccl<8>(T1, c);
+                measure_area(c);
+                plane_copy(T3, PR, c);  // ext = best | filtered brown
+                __syncthreads();
+                keep_area_ge(T3, P.cfg.brown_min_area_px, c);
+                // contour of the extended mask; the returned mask is the UNFILLED union
+                __shared__ int s_info2[8];
+                const bool f2 = largest_external(T3, T1, T2, s_info2, c);
+                if (f2) {
+                    plane_copy(PR, T3, c);
+                    if (threadIdx.x < 8) s_info[threadIdx.x] = s_info2[threadIdx.x];
+                } else {
+                    if (threadIdx.x < 8) s_info[threadIdx.x] = 0;  // (best_mask, None)
+                }
+                __syncthreads();
+            }
+        }
+        plane_to_bytes(PR, mask + img * img_px, c);
+        if (threadIdx.x < 8) {
+            int v = s_info[threadIdx.x];
+            if (threadIdx.x == 7) v = c.status;
+            info[(size_t)img * 8 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+Footprint make_ellipse(int k) {
+    // cv::getStructuringElement(MORPH_ELLIPSE, (k,k)), anchor (k/2, k/2)
+    Footprint f;
+    f.n = 0;
+    const int r = k / 2, cc = k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < k; ++i) {
+        const int dy = i - r;
+        if (abs(dy) > r) continue;
+        const int dx = (int)nearbyint(cc * sqrt((r * r - dy * dy) * inv_r2));
+        const int j1 = max(cc - dx, 0), j2 = min(cc + dx + 1, k);
+        if (j2 <= j1) continue;
+        f.r[f.n].dy = (int8_t)dy;
+        f.r[f.n].o1 = (int8_t)(j1 - cc);
+        f.r[f.n].o2 = (int8_t)(j2 - 1 - cc);
+        f.r[f.n].pad = 0;
+        ++f.n;
+    }
+    return f;
+}
+
+struct Plan {
+    MaskParams P;
+    size_t smem;
+    size_t ws_per_block;
+    int grid;
+};
+
+int make_plan(int B, int H, int W, const lfx_mask_cfg* cfg, int mode, Plan* out) {
+    MaskParams& P = out->P;
+    memset(&P, 0, sizeof(P));
+    if (cfg) P.cfg = *cfg;
+    P.H = H; P.W = W; P.WPR = (W + 31) / 32; P.NW = H * P.WPR;
+    P.lastmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu;
+    P.mode = mode;
+    P.rcap_glob = H * ((W + 1) / 2);
+    auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t plane_bytes = al((size_t)P.NW * 4) * NPLANES + al((size_t)(P.NW + 1) * 4);
+    P.planes_in_smem = plane_bytes <= 72 * 1024;
+    const int rb = W * 3;
+    P.stage_rows = max(1, STAGE_BYTES / rb);
+    if (P.stage_rows > H) P.stage_rows = H;
+    size_t smem = al(RCAP_SMEM * 4) * 3 + al(RCAP_SMEM * 2) + al((size_t)P.stage_rows * rb) + al(sizeof(HsvLut)) + al(sizeof(LabLut));
+    if (P.planes_in_smem) smem += plane_bytes;
+    size_t wsb = al((size_t)P.rcap_glob * 4) * 3 + al((size_t)P.rcap_glob * 2);
+    if (!P.planes_in_smem) wsb += plane_bytes;
+    P.ws_per_block = wsb;
+    out->smem = smem;
+    out->ws_per_block = wsb;
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    out->grid = max(1, min(B, LFX_NUM_SMS * per_sm));
+    if (smem > 220 * 1024) return LFX_ERR_UNSUPPORTED;
+    return LFX_OK;
+}
+
+int launch(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
+           const lfx_mask_cfg* cfg, int mode, void* ws, size_t ws_bytes, cudaStream_t st) {
+    LFX_REQUIRE(H > 0 && W > 0 && H <= 65535 && W <= 65535 && B >= 0, LFX_ERR_ARG, "make_mask: bad shape");
+    if (B == 0) return LFX_OK;
+    Plan pl;
+    int rc = make_plan(B, H, W, cfg, mode, &pl);
+    LFX_REQUIRE(rc == LFX_OK, rc, "make_mask: image %dx%d needs %zu bytes of shared memory", H, W, pl.smem);
+    LFX_REQUIRE(ws && ws_bytes >= pl.ws_per_block * pl.grid, LFX_ERR_WORKSPACE, "make_mask: workspace %zu < %zu bytes",
+                ws_bytes, pl.ws_per_block * pl.grid);
+    if (mode == 0) {
+        const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
+        LFX_REQUIRE(mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1), LFX_ERR_UNSUPPORTED,
+                    "make_mask: morph kernels must be odd <= 19 (got %d, %d)", mk, bk);
+        LFX_REQUIRE(cfg->strategy >= 0 && cfg->strategy <= 4, LFX_ERR_UNSUPPORTED, "make_mask: strategy %d", cfg->strategy);
+        LFX_REQUIRE(cfg->strategy != 4 || raw, LFX_ERR_ARG, "make_mask: strategy 4 needs a raw mask");
+        LFX_REQUIRE(src, LFX_ERR_ARG, "make_mask: src is NULL");
+    }
+    pl.P.fp_morph = make_ellipse(pl.P.cfg.morph_kernel);
+    pl.P.fp_brown = make_ellipse(pl.P.cfg.brown_morph_kernel > 0 ? pl.P.cfg.brown_morph_kernel : 3);
+    pl.P.fp_search = make_ellipse(20);
+    static size_t attr = 0;
+    if (pl.smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_make_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "make_mask smem attr: %s", cudaGetErrorString(e));
+        attr = pl.smem;
+    }
+    k_make_mask<<<pl.grid, MT, pl.smem, st>>>(src, raw, mask, info, B, pl.P, (uint8_t*)ws, lfx_tables());
+    return lfx_check_launch("make_mask");
+}
+
+}  // namespace
+
+extern "C" size_t lfx_make_mask_workspace(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    Plan pl;
+    make_plan(B, H, W, nullptr, 0, &pl);
+    return pl.ws_per_block * (size_t)min(B, LFX_NUM_SMS * 2) + 256;
+}
+
+extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
+                             const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(mask && info && cfg, LFX_ERR_ARG, "make_mask: NULL argument");
+    return launch(src, raw, mask, info, B, H, W, cfg, 0, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W, int fill_size,
+                                    int morph_kernel, void* workspace, size_t workspace_bytes, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    LFX_REQUIRE(raw && mask && info, LFX_ERR_ARG, "postprocess_mask: NULL argument");
+    LFX_REQUIRE(morph_kernel >= 1 && morph_kernel <= 19 && (morph_kernel & 1), LFX_ERR_UNSUPPORTED,
+                "postprocess_mask: morph kernel %d", morph_kernel);
+    lfx_mask_cfg cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.strategy = 4;
+    cfg.fill_size = fill_size;
+    cfg.morph_kernel = morph_kernel;
+    cfg.brown_morph_kernel = 3;
+    return launch(nullptr, raw, mask, info, B, H, W, &cfg, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+}

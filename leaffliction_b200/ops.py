@@ -1,0 +1,320 @@
+"""Batched device ops: thin torch-tensor wrappers over the C ABI (include/leafx.h).
+
+torch is plumbing only (device memory, streams); every op below launches the hand-written
+sm_100a kernels in libleafx.so on the current CUDA stream.  Inputs are CUDA uint8 tensors
+[B,H,W,3]; per-image parameters are host arrays uploaded here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MaskCfg
+
+STRATEGY_IDS = {"hsv_h": 0, "lab": 1, "hsv_s": 2, "hsv_v_dark": 3, "external": 4}
+
+
+def _ready(x: torch.Tensor):
+    if not x.is_cuda:
+        raise _lib.LeafxError(_lib.ERR_CUDA, "leaffliction_b200 ops need CUDA tensors (no CPU fallback)")
+    return _lib.init(x.device.index if x.device.index is not None else torch.cuda.current_device())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _chk_img(x: torch.Tensor, ch: Optional[int] = 3):
+    if x.dtype != torch.uint8 or not x.is_contiguous():
+        raise ValueError("expected a contiguous uint8 tensor")
+    if ch is not None and (x.dim() != 4 or x.shape[-1] != ch):
+        raise ValueError(f"expected shape [B,H,W,{ch}], got {tuple(x.shape)}")
+
+
+def _dev(a, dtype, device):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).to(device, non_blocking=True)
+
+
+# --------------------------------------------------------------------------- colour / masks
+def cvt_color(x: torch.Tensor, code: str) -> torch.Tensor:
+    """cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}); code in {'gray','hsv','lab'}."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    ci = {"gray": 0, "hsv": 1, "lab": 2}[code]
+    out = torch.empty((B, H, W) if ci == 0 else (B, H, W, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.lfx_cvt_color(_p(x), _p(out), B, H, W, ci, _stream()))
+    return out
+
+
+def mask_cfg(strategy="hsv_h", green_hue_range=(25, 100), fill_size=1000, morph_kernel=3,
+             brown_hue_range=(0, 30), brown_s_min=20, brown_v_max=200, brown_min_area_px=25,
+             brown_morph_kernel=3, use_lab_brown=False, lab_a_min=125, lab_b_min=125,
+             hsv_channel_for_mask="s", bg_bias="light_bg", extend_brown=True) -> MaskCfg:
+    c = MaskCfg()
+    c.strategy = STRATEGY_IDS[strategy] if isinstance(strategy, str) else int(strategy)
+    c.green_lo, c.green_hi = int(green_hue_range[0]), int(green_hue_range[1])
+    c.fill_size, c.morph_kernel = int(fill_size), int(morph_kernel)
+    c.brown_lo, c.brown_hi = int(brown_hue_range[0]), int(brown_hue_range[1])
+    c.brown_s_min, c.brown_v_max = int(brown_s_min), int(brown_v_max)
+    c.brown_min_area_px, c.brown_morph_kernel = int(brown_min_area_px), int(brown_morph_kernel)
+    c.use_lab_brown, c.lab_a_min, c.lab_b_min = int(bool(use_lab_brown)), int(lab_a_min), int(lab_b_min)
+    c.fallback_channel = "hsv".index(str(hsv_channel_for_mask))
+    c.bg_dark = int((bg_bias or "auto").lower() == "dark_bg")
+    c.extend_brown = int(bool(extend_brown))
+    return c
+
+
+def threshold_mask(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.lfx_threshold_mask(_p(x), _p(out), B, H, W, C.byref(cfg), _stream()))
+    return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def make_mask(x: torch.Tensor, cfg: MaskCfg, raw: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Batched make_mask (mask.py:548-582, profile P0/P1). Returns (mask [B,H,W] u8, info [B,8] i32)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    mask = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    info = torch.empty((B, 8), dtype=torch.int32, device=x.device)
+    nws = lib.lfx_make_mask_workspace(B, H, W)
+    ws = _workspace(nws, x.device)
+    _lib.check(lib.lfx_make_mask(_p(x), _p(raw), _p(mask), _p(info), B, H, W, C.byref(cfg), _p(ws), ws.numel(), _stream()))
+    return mask, info
+
+
+def postprocess_mask(raw: torch.Tensor, fill_size=1000, morph_kernel=3):
+    _chk_img(raw, None)
+    lib = _ready(raw)
+    B, H, W = raw.shape
+    mask = torch.empty_like(raw)
+    info = torch.empty((B, 8), dtype=torch.int32, device=raw.device)
+    ws = _workspace(lib.lfx_make_mask_workspace(B, H, W), raw.device)
+    _lib.check(lib.lfx_postprocess_mask(_p(raw), _p(mask), _p(info), B, H, W, int(fill_size), int(morph_kernel),
+                                        _p(ws), ws.numel(), _stream()))
+    return mask, info
+
+
+def apply_mask(x: torch.Tensor, mask: torch.Tensor, color_val: int = 255) -> torch.Tensor:
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty_like(x)
+    _lib.check(lib.lfx_apply_mask(_p(x), _p(mask), _p(out), B, H, W, int(color_val), _stream()))
+    return out
+
+
+def gauss_taps(ksize: int, sigma: float) -> np.ndarray:
+    lib = _lib.load()
+    out = np.zeros(ksize, np.int32)
+    _lib.check(lib.lfx_gauss_taps(int(ksize), float(sigma), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def gauss_u8(x: torch.Tensor, ksize: int, sigma: float = 0.0) -> torch.Tensor:
+    """cv2.GaussianBlur(x,(k,k),sigma) on [B,H,W,3] or [B,H,W] uint8."""
+    if x.dtype != torch.uint8 or not x.is_contiguous() or x.dim() not in (3, 4):
+        raise ValueError("expected contiguous uint8 [B,H,W] or [B,H,W,3]")
+    lib = _ready(x)
+    B, H, W = x.shape[:3]
+    ch = 1 if x.dim() == 3 else x.shape[3]
+    out = torch.empty_like(x)
+    _lib.check(lib.lfx_gauss_u8(_p(x), _p(out), B, H, W, ch, int(ksize), float(sigma), _stream()))
+    return out
+
+
+def roi_letterbox(x: torch.Tensor, mask: Optional[torch.Tensor], info: torch.Tensor, roi_size=(256, 256)) -> torch.Tensor:
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    RH, RW = int(roi_size[0]), int(roi_size[1])
+    out = torch.empty((B, RH, RW, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.lfx_roi_letterbox(_p(x), _p(mask), _p(info), _p(out), B, H, W, RH, RW, _stream()))
+    return out
+
+
+def color_stats(x: torch.Tensor, mask: Optional[torch.Tensor], hist9=True, hsv3=True, counters=True):
+    """Returns (hist9 [B,9,256] | None, hsv3 [B,3,256] | None, counters [B,16] | None) int32."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    h9 = torch.zeros((B, 9, 256), dtype=torch.int32, device=x.device) if hist9 else None
+    h3 = torch.zeros((B, 3, 256), dtype=torch.int32, device=x.device) if hsv3 else None
+    cn = torch.zeros((B, 16), dtype=torch.int32, device=x.device) if counters else None
+    _lib.check(lib.lfx_color_stats(_p(x), _p(mask), _p(h9), _p(h3), _p(cn), B, H, W, _stream()))
+    return h9, h3, cn
+
+
+@dataclass
+class CoreOutputs:
+    blur: torch.Tensor
+    mask: torch.Tensor
+    info: torch.Tensor
+    roi: torch.Tensor
+    hist9: torch.Tensor
+    hsv3: torch.Tensor
+    counters: torch.Tensor
+
+
+def alloc_core_outputs(B, H, W, roi_size, device) -> CoreOutputs:
+    u8 = dict(dtype=torch.uint8, device=device)
+    i32 = dict(dtype=torch.int32, device=device)
+    return CoreOutputs(torch.empty((B, H, W, 3), **u8), torch.empty((B, H, W), **u8), torch.empty((B, 8), **i32),
+                       torch.empty((B, roi_size[0], roi_size[1], 3), **u8), torch.empty((B, 9, 256), **i32),
+                       torch.empty((B, 3, 256), **i32), torch.empty((B, 16), **i32))
+
+
+def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
+                  out: Optional[CoreOutputs] = None) -> CoreOutputs:
+    """Core transform profile (BASELINE config 2): 5x5 Gaussian blur + make_mask + masked ROI
+    letterbox + RGB/HSV/LAB histograms and hist.py counters, one submission."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    if out is None:
+        out = alloc_core_outputs(B, H, W, roi_size, x.device)
+    ws = _workspace(lib.lfx_pipeline_core_workspace(B, H, W), x.device)
+    _lib.check(lib.lfx_pipeline_core(_p(x), _p(out.blur), _p(out.mask), _p(out.info), _p(out.roi), _p(out.hist9),
+                                     _p(out.hsv3), _p(out.counters), B, H, W, int(roi_size[0]), int(roi_size[1]),
+                                     float(gaussian_sigma), C.byref(cfg), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------- augmentations
+def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    mode = _dev([0 if lr else 1 for lr in left_right], np.int32, x.device)
+    out = torch.empty_like(x)
+    _lib.check(lib.lfx_flip(_p(x), _p(out), B, H, W, _p(mode), _stream()))
+    return out
+
+
+def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255):
+    """params[B][8] = a0..a5 (16.16 fixed point), nw, nh.  Returns (slab [B, stride] u8, stride):
+    image i is slab[i, : nh_i*nw_i*3].view(nh_i, nw_i, 3)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    params = np.ascontiguousarray(params, np.int32).reshape(B, 8)
+    max_px = int((params[:, 6].astype(np.int64) * params[:, 7]).max()) if B else 0
+    stride = ((max_px * 3 + 15) // 16) * 16
+    slab = torch.empty((B, max(stride, 16)), dtype=torch.uint8, device=x.device)
+    dp = _dev(params, np.int32, x.device)
+    _lib.check(lib.lfx_rotate_nn(_p(x), _p(slab), slab.shape[1], B, H, W, _p(dp), int(fill), _stream()))
+    return slab, slab.shape[1]
+
+
+def warp_bicubic(x: torch.Tensor, coeffs: np.ndarray, perspective: Sequence[bool]) -> torch.Tensor:
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    dc = _dev(np.asarray(coeffs, np.float64).reshape(B, 8), np.float64, x.device)
+    dpz = _dev([1 if p else 0 for p in perspective], np.int32, x.device)
+    out = torch.empty_like(x)
+    _lib.check(lib.lfx_warp_bicubic(_p(x), _p(out), B, H, W, _p(dc), _p(dpz), _stream()))
+    return out
+
+
+class LanczosTables:
+    """Host cache of Pillow's fixed-point Lanczos coefficient tables, concatenated for upload."""
+
+    def __init__(self):
+        self.rows = {}      # (in,out) -> (row offset, ksize)
+        self.bounds = []
+        self.kk = []
+        self.kstride = 0
+        self.nrows = 0
+        self._dev = None
+
+    def _ensure_stride(self, ks):
+        if ks > self.kstride:
+            new = ((ks + 7) // 8) * 8
+            self.kk = [np.pad(k, ((0, 0), (0, new - k.shape[1]))) for k in self.kk]
+            self.kstride = new
+            self._dev = None
+
+    def get(self, in_size: int, out_size: int):
+        key = (int(in_size), int(out_size))
+        if key not in self.rows:
+            lib = _lib.load()
+            ks = lib.lfx_lanczos_ksize(*key)
+            if ks < 0:
+                raise ValueError(f"bad Lanczos sizes {key}")
+            self._ensure_stride(ks)
+            b = np.zeros((key[1], 2), np.int32)
+            k = np.zeros((key[1], self.kstride), np.int32)
+            rc = lib.lfx_lanczos_table(key[0], key[1], self.kstride, b.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p))
+            if rc < 0:
+                _lib.check(rc)
+            self.rows[key] = (self.nrows, ks)
+            self.bounds.append(b)
+            self.kk.append(k)
+            self.nrows += key[1]
+            self._dev = None
+        return self.rows[key]
+
+    def device(self, device):
+        if self._dev is None or self._dev[0].device != device:
+            self._dev = (_dev(np.concatenate(self.bounds), np.int32, device), _dev(np.concatenate(self.kk), np.int32, device))
+        return self._dev
+
+
+_lanczos = LanczosTables()
+
+
+def crop_lanczos(x: torch.Tensor, boxes: np.ndarray, out_hw: Tuple[int, int], want_f32: bool = False):
+    """img.crop(box).resize((OW,OH), LANCZOS) per image; boxes[B][4] = left, top, w, h."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    boxes = np.ascontiguousarray(boxes, np.int32).reshape(B, 4)
+    off = np.zeros((B, 4), np.int32)
+    for i in range(B):
+        xr, xk = _lanczos.get(boxes[i, 2], OW)
+        yr, yk = _lanczos.get(boxes[i, 3], OH)
+        off[i] = (xr, xk, yr, yk)
+    tb, tk = _lanczos.device(x.device)
+    out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
+    outf = torch.empty((B, OH, OW, 3), dtype=torch.float32, device=x.device) if want_f32 else None
+    _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf), B, H, W, _p(_dev(boxes, np.int32, x.device)), OH, OW,
+                                    _p(tb), _p(tk), _lanczos.kstride, _p(_dev(off, np.int32, x.device)), _stream()))
+    return (out, outf) if want_f32 else out
+
+
+def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int]) -> torch.Tensor:
+    """(x + noise) mod 256 then per-channel autocontrast; cuts[i] = int(H*W*cutoff_i // 100)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty_like(x)
+    hist = torch.empty((B, 3, 256), dtype=torch.int32, device=x.device)
+    _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(_dev(cuts, np.int32, x.device)), _p(hist), _stream()))
+    return out
