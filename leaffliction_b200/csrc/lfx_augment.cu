@@ -453,6 +453,7 @@ int chunking(int total, int unit, int B, int* per_block) {
 
 extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && mode && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG, "flip: bad arguments");
     LFX_REQUIRE(W * 3 * 2 + 32 <= FLIP_SMEM, LFX_ERR_UNSUPPORTED, "flip: W > %d unsupported", (FLIP_SMEM - 32) / 6);
     if (B == 0) return LFX_OK;
@@ -470,6 +471,7 @@ extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, c
 extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,
                              const int32_t* params, int fill, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && params && B >= 0 && H > 0 && W > 0 && B <= 65535 && dst_image_stride > 0, LFX_ERR_ARG,
                 "rotate_nn: bad arguments");
     LFX_REQUIRE(H < 32768 && W < 32768, LFX_ERR_UNSUPPORTED, "rotate_nn: fixed-point path needs sizes < 32768");
@@ -483,6 +485,7 @@ extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image
 extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, const double* coef,
                                 const int32_t* perspective, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "warp_bicubic: bad arguments");
     if (B == 0) return LFX_OK;
@@ -495,6 +498,7 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
                                 int OH, int OW, const int32_t* tab_bounds, const int32_t* tab_kk, int kstride,
                                 const int32_t* tab_off, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && box && tab_bounds && tab_kk && tab_off && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 &&
                     kstride > 0 && B <= 65535,
                 LFX_ERR_ARG, "crop_lanczos: bad arguments");
@@ -515,6 +519,7 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
 extern "C" int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W, const int32_t* cut,
                            int32_t* hist_ws, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && noise && dst && cut && hist_ws && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "distort: bad arguments");
     LFX_REQUIRE((long long)H * W * 3 < (1ll << 31), LFX_ERR_UNSUPPORTED, "distort: image too large");

@@ -249,6 +249,7 @@ int stream_grid(long long npix) {
 
 extern "C" int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int W, int code, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && B >= 0 && H > 0 && W > 0 && code >= 0 && code <= 2, LFX_ERR_ARG, "cvt_color: bad arguments");
     if (B == 0) return LFX_OK;
     const long long npix = (long long)B * H * W;
@@ -266,6 +267,7 @@ extern "C" int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int
 extern "C" int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int H, int W, const lfx_mask_cfg* cfg,
                                   lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && mask && cfg && B >= 0 && H > 0 && W > 0, LFX_ERR_ARG, "threshold_mask: bad arguments");
     LFX_REQUIRE(cfg->strategy == 0 || cfg->strategy == 1, LFX_ERR_UNSUPPORTED,
                 "threshold_mask: strategy %d needs lfx_make_mask (Otsu) or an external front end", cfg->strategy);
@@ -279,6 +281,7 @@ extern "C" int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int 
 extern "C" int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,
                               int color_val, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && mask && dst && B >= 0 && H > 0 && W > 0 && color_val >= 0 && color_val <= 255, LFX_ERR_ARG,
                 "apply_mask: bad arguments");
     if (B == 0) return LFX_OK;
@@ -290,6 +293,7 @@ extern "C" int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* 
 extern "C" int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t* hist9, int32_t* hsv3,
                                int32_t* counters, int B, int H, int W, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && B >= 0 && H > 0 && W > 0 && (hist9 || hsv3 || counters), LFX_ERR_ARG, "color_stats: bad arguments");
     LFX_REQUIRE((long long)H * W < (1ll << 31), LFX_ERR_UNSUPPORTED, "color_stats: image too large");
     if (B == 0) return LFX_OK;

@@ -78,6 +78,7 @@ constexpr size_t G_SMEM = (((G_TH + 2 * G_MAXK) * (G_TWB + 2 * G_MAXK * 3) + 15)
 extern "C" int lfx_gauss_u8(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, int ksize, double sigma,
                             lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && B >= 0 && H > 0 && W > 0 && (C == 1 || C == 3), LFX_ERR_ARG, "gauss_u8: bad arguments");
     LFX_REQUIRE(ksize >= 1 && (ksize & 1) && ksize <= G_MAXK, LFX_ERR_UNSUPPORTED, "gauss_u8: ksize %d (odd <= %d)", ksize,
                 G_MAXK);

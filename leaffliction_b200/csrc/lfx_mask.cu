@@ -760,6 +760,7 @@ extern "C" size_t lfx_make_mask_workspace(int B, int H, int W) {
 extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
                              const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(mask && info && cfg, LFX_ERR_ARG, "make_mask: NULL argument");
     return launch(src, raw, mask, info, B, H, W, cfg, 0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -767,6 +768,7 @@ extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* ma
 extern "C" int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W, int fill_size,
                                     int morph_kernel, void* workspace, size_t workspace_bytes, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(raw && mask && info, LFX_ERR_ARG, "postprocess_mask: NULL argument");
     LFX_REQUIRE(morph_kernel >= 1 && morph_kernel <= 19 && (morph_kernel & 1), LFX_ERR_UNSUPPORTED,
                 "postprocess_mask: morph kernel %d", morph_kernel);

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(THREADS) k_roi(const uint8_t* __restrict__ src
 extern "C" int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* info, uint8_t* dst, int B, int H,
                                  int W, int RH, int RW, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && info && dst && B >= 0 && H > 0 && W > 0 && RH > 0 && RW > 0 && B <= 65535, LFX_ERR_ARG,
                 "roi_letterbox: bad arguments");
     LFX_REQUIRE(RW >= W && RH >= H, LFX_ERR_UNSUPPORTED,
@@ -153,6 +154,7 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
                                  double gaussian_sigma, const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes,
                                  lfx_stream_t stream) {
     LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     int rc;

@@ -304,8 +304,10 @@ def crop_lanczos(x: torch.Tensor, boxes: np.ndarray, out_hw: Tuple[int, int], wa
     tb, tk = _lanczos.device(x.device)
     out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
     outf = torch.empty((B, OH, OW, 3), dtype=torch.float32, device=x.device) if want_f32 else None
-    _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf), B, H, W, _p(_dev(boxes, np.int32, x.device)), OH, OW,
-                                    _p(tb), _p(tk), _lanczos.kstride, _p(_dev(off, np.int32, x.device)), _stream()))
+    dbox = _dev(boxes, np.int32, x.device)   # keep both alive until the launch is enqueued
+    doff = _dev(off, np.int32, x.device)
+    _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf), B, H, W, _p(dbox), OH, OW,
+                                    _p(tb), _p(tk), _lanczos.kstride, _p(doff), _stream()))
     return (out, outf) if want_f32 else out
 
 
@@ -316,5 +318,6 @@ def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int]) -> tor
     B, H, W, _ = x.shape
     out = torch.empty_like(x)
     hist = torch.empty((B, 3, 256), dtype=torch.int32, device=x.device)
-    _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(_dev(cuts, np.int32, x.device)), _p(hist), _stream()))
+    dcut = _dev(cuts, np.int32, x.device)
+    _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(dcut), _p(hist), _stream()))
     return out
