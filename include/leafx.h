@@ -91,13 +91,6 @@ int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, in
 int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W,
                 const int32_t* cut, int32_t* hist_ws, lfx_stream_t stream);
 
-/* Same, with the noise generated on the device: NumPy's legacy MT19937 + polar-method normal
- * stream (np.random.seed(seed[i]); np.random.normal(0, 5, (H,W,3)).astype(uint8)),
- * image_augmenter.py:16-18,121.  mt_ws: device scratch, lfx_distort_seeded_workspace() bytes. */
-size_t lfx_distort_seeded_workspace(int B, int H, int W);
-int lfx_distort_seeded(const uint8_t* src, uint8_t* dst, int B, int H, int W, const uint32_t* seed,
-                       const int32_t* cut, int32_t* hist_ws, void* mt_ws, lfx_stream_t stream);
-
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
 /* cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}) (mask.py:87,103; blur.py:27; hist.py:184).
@@ -133,8 +126,10 @@ int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int H, int W,
  * -> Otsu fallback (:395-411) -> brown extension (:335-392).  One thread block per image.
  * raw: NULL for strategies 0-3 (computed from src in the kernel); for strategy 4 the raw
  * candidate [B,H,W] produced elsewhere (inclusive / enhanced front ends).
- * info[B][8] = {found, x, y, w, h, 2*contourArea, pixels, status}; (x,y,w,h) =
- * cv2.boundingRect of the returned contour (roi.py:26). */
+ * info[B][8] = {found, x, y, w, h, 2*contourArea, pixels, status | start_x << 8}; (x,y,w,h) =
+ * cv2.boundingRect of the returned contour (roi.py:26); (start_x, y) is the contour's first raster
+ * pixel (input of lfx_trace_contour); status bit0 = Otsu fallback used, bit1 = run table spilled
+ * to global scratch. */
 size_t lfx_make_mask_workspace(int B, int H, int W);
 int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B,
                   int H, int W, const lfx_mask_cfg* cfg /* host */, void* workspace,
@@ -144,6 +139,15 @@ int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t
 int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
                          int fill_size, int morph_kernel, void* workspace, size_t workspace_bytes,
                          lfx_stream_t stream);
+
+/* largest_contour (Transformation.py:285-292): the external contour of the component selected by
+ * lfx_make_mask / lfx_postprocess_mask, as cv2.findContours(RETR_EXTERNAL, CHAIN_APPROX_SIMPLE)
+ * returns it.  points[B][max_pts][2] (x,y) int32; counts[B] = number of points (negative = -needed
+ * when max_pts is too small; 0 = no contour); sums[B][3] (optional) = Green-formula sums
+ * {a00, a10, a01} of the polygon: cv2.moments m00 = |a00|/2, m10 = a10/6, m01 = a01/6 (sign of a00)
+ * (analyze.py:43-46). */
+int lfx_trace_contour(const uint8_t* mask, const int32_t* info, int32_t* points, int32_t* counts,
+                      int64_t* sums, int B, int H, int W, int max_pts, lfx_stream_t stream);
 
 /* apply_mask (mask_utils.py:10-83): dst = mask > 127 ? src : color_val. */
 int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,

@@ -45,6 +45,7 @@ _SIGS = {
     "lfx_make_mask_workspace": (C.c_size_t, [_I, _I, _I]),
     "lfx_make_mask": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
     "lfx_postprocess_mask": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _P]),
+    "lfx_trace_contour": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "lfx_apply_mask": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "lfx_gauss_taps": (C.c_int, [_I, C.c_double, _P]),
     "lfx_gauss_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, C.c_double, _P]),

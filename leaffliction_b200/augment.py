@@ -1,0 +1,255 @@
+"""Drop-in for srcs/preprocessing/image_augmenter.py: the six class-balancing augmentations.
+
+`ImageAugmenter` keeps the reference's constructor and method signatures
+(`ImageAugmenter(seed=None)`, `.flip/.rotate/.skew/.shear/.crop/.distortion(image_path,
+output_path) -> bool`, image_augmenter.py:15-133) and its error convention (catch everything, log,
+return False).  Every parameter is drawn on the host with the SAME `random` / `np.random` calls in
+the SAME order as the reference, so a given seed yields the reference's parameters by
+construction; the pixel work runs in libleafx's CUDA kernels.  JPEG decode/encode stays on the
+host (Pillow, quality 95 -- image_utils.py:19-59; out of scope per SURVEY.md section 8).
+
+`augment_arrays` is the batched array-in/array-out form used by the dataset balancer and benches.
+"""
+from __future__ import annotations
+
+import logging
+import math
+import random
+from pathlib import Path
+from typing import List, Sequence
+
+import numpy as np
+
+logger = logging.getLogger(__name__)
+
+TRANSFORMATIONS = ["flip", "rotate", "skew", "shear", "crop", "distortion"]
+SUPPORTED_EXTENSIONS = {".jpg"}
+NOISE_LEVEL = 5
+
+
+# --------------------------------------------------------------------------- host parameter maths
+def rotate_matrix(angle: float, w: int, h: int):
+    """PIL Image.rotate(angle, expand=True) geometry -> (inverse affine matrix[6], nw, nh),
+    or a transpose tag for multiples of 90 degrees (PIL/Image.py rotate)."""
+    angle = angle % 360.0
+    if angle == 0:
+        return "copy", w, h
+    if angle == 180:
+        return "rot180", w, h
+    if angle == 90:
+        return "rot90", h, w
+    if angle == 270:
+        return "rot270", h, w
+    cx, cy = w / 2.0, h / 2.0
+    a = -math.radians(angle)
+    m = [round(math.cos(a), 15), round(math.sin(a), 15), 0.0, round(-math.sin(a), 15), round(math.cos(a), 15), 0.0]
+
+    def tf(x, y):
+        return m[0] * x + m[1] * y + m[2], m[3] * x + m[4] * y + m[5]
+    m[2], m[5] = tf(-cx, -cy)
+    m[2] += cx
+    m[5] += cy
+    xs, ys = zip(*(tf(x, y) for x, y in ((0, 0), (w, 0), (w, h), (0, h))))
+    nw = math.ceil(max(xs)) - math.floor(min(xs))
+    nh = math.ceil(max(ys)) - math.floor(min(ys))
+    m[2], m[5] = tf(-(nw - w) / 2.0, -(nh - h) / 2.0)
+    return m, nw, nh
+
+
+def fixed_affine(m):
+    """libImaging affine_fixed 16.16 coefficients (half-pixel centre folded into a2, a5)."""
+    fix = lambda v: int(math.floor(v * 65536.0 + 0.5))  # noqa: E731
+    return [fix(m[0]), fix(m[1]), fix(m[2] + m[0] * 0.5 + m[1] * 0.5),
+            fix(m[3]), fix(m[4]), fix(m[5] + m[3] * 0.5 + m[4] * 0.5)]
+
+
+# --------------------------------------------------------------------------- GPU execution
+def _ops():
+    from . import ops  # imports torch; raises loudly without CUDA when an op is called
+    return ops
+
+
+def _to_dev(arrs: Sequence[np.ndarray]):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("leaffliction_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.from_numpy(np.ascontiguousarray(np.stack(arrs))).cuda()
+
+
+def gpu_flip(imgs, left_right):
+    return _ops().flip(_to_dev(imgs), list(left_right)).cpu().numpy()
+
+
+def gpu_rotate(imgs, angles) -> List[np.ndarray]:
+    ops = _ops()
+    h, w = imgs[0].shape[:2]
+    outs: List = [None] * len(imgs)
+    idx, params = [], []
+    for i, ang in enumerate(angles):
+        m, nw, nh = rotate_matrix(ang, w, h)
+        if isinstance(m, str):  # PIL's transpose fast paths: pure index permutations
+            im = imgs[i]
+            outs[i] = {"copy": im.copy(), "rot180": im[::-1, ::-1].copy(),
+                       "rot90": np.transpose(im, (1, 0, 2))[::-1].copy(),
+                       "rot270": np.transpose(im, (1, 0, 2))[:, ::-1].copy()}[m]
+        else:
+            idx.append(i)
+            params.append(fixed_affine(m) + [nw, nh])
+    if idx:
+        slab, _ = ops.rotate_nn(_to_dev([imgs[i] for i in idx]), np.array(params, np.int32), 255)
+        slab = slab.cpu().numpy()
+        for k, i in enumerate(idx):
+            nw, nh = params[k][6], params[k][7]
+            outs[i] = slab[k, : nh * nw * 3].reshape(nh, nw, 3).copy()
+    return outs
+
+
+def gpu_warp(imgs, coeffs, perspective):
+    return _ops().warp_bicubic(_to_dev(imgs), np.asarray(coeffs, np.float64), list(perspective)).cpu().numpy()
+
+
+def gpu_crop(imgs, boxes):
+    h, w = imgs[0].shape[:2]
+    return _ops().crop_lanczos(_to_dev(imgs), np.asarray(boxes, np.int32), (h, w)).cpu().numpy()
+
+
+def gpu_distort(imgs, noises_u8, cutoffs):
+    h, w = imgs[0].shape[:2]
+    cuts = [int(h * w * c // 100) for c in cutoffs]      # ImageOps.autocontrast: int(n * cutoff // 100)
+    return _ops().distort(_to_dev(imgs), _to_dev(noises_u8), cuts).cpu().numpy()
+
+
+# --------------------------------------------------------------------------- file-level drop-in
+def _load_rgb(image_path) -> np.ndarray:
+    """ImageLoader.load_pil_image semantics (image_utils.py:19-39): .jpg only, RGB."""
+    from PIL import Image
+    p = Path(image_path)
+    if not p.exists():
+        raise FileNotFoundError(f"Image not found: {p}")
+    if p.suffix.lower() not in SUPPORTED_EXTENSIONS:
+        raise ValueError(f"Unsupported image format: {p.suffix}")
+    with Image.open(p) as im:
+        if im.mode != "RGB":
+            im = im.convert("RGB")
+        return np.array(im)
+
+
+def _save_rgb(arr: np.ndarray, output_path, quality: int = 95) -> None:
+    from PIL import Image
+    out = Path(output_path)
+    out.parent.mkdir(parents=True, exist_ok=True)
+    Image.fromarray(arr).save(out, quality=quality)
+
+
+class ImageAugmenter:
+    NOISE_LEVEL = NOISE_LEVEL
+
+    def __init__(self, seed=None):
+        if seed:  # reference quirk: seed 0 / None leaves both RNGs unseeded (image_augmenter.py:16-18)
+            random.seed(seed)
+            np.random.seed(seed)
+
+    def _run(self, image_path, output_path, fn) -> bool:
+        try:
+            _save_rgb(fn(_load_rgb(image_path)), output_path)
+            return True
+        except Exception as e:  # same convention as the reference: log, return False, never raise
+            logger.error(f"Failed to process {image_path} - {e}")
+            return False
+
+    def flip(self, image_path, output_path):
+        return self._run(image_path, output_path, lambda im: gpu_flip([im], [random.choice([True, False])])[0])
+
+    def rotate(self, image_path, output_path):
+        return self._run(image_path, output_path, lambda im: gpu_rotate([im], [random.uniform(-30, 30)])[0])
+
+    def skew(self, image_path, output_path):
+        def fn(im):
+            h, w = im.shape[:2]
+            s = random.uniform(0.05, 0.15)
+            return gpu_warp([im], [[1 + s, 0, -s * w, 0, 1 + s, -s * h, 0, 0]], [True])[0]
+        return self._run(image_path, output_path, fn)
+
+    def shear(self, image_path, output_path):
+        def fn(im):
+            k = random.uniform(-0.2, 0.2)
+            c = [1, k, 0, 0, 1, 0, 0, 0] if random.choice([True, False]) else [1, 0, 0, k, 1, 0, 0, 0]
+            return gpu_warp([im], [c], [False])[0]
+        return self._run(image_path, output_path, fn)
+
+    def crop(self, image_path, output_path):
+        def fn(im):
+            h, w = im.shape[:2]
+            r = random.uniform(0.8, 0.95)
+            nw, nh = int(w * r), int(h * r)
+            left = random.randint(0, w - nw)
+            top = random.randint(0, h - nh)
+            return gpu_crop([im], [(left, top, nw, nh)])[0]
+        return self._run(image_path, output_path, fn)
+
+    def distortion(self, image_path, output_path):
+        def fn(im):
+            noise = np.random.normal(0, self.NOISE_LEVEL, im.shape).astype(np.uint8)
+            return gpu_distort([im], [noise], [random.uniform(0, 2)])[0]
+        return self._run(image_path, output_path, fn)
+
+
+def augment_arrays(images: Sequence[np.ndarray], transforms: Sequence[str], seeds: Sequence[int]) -> List[np.ndarray]:
+    """Batched form of `_process_single_transformation` (dataset_balancer.py:201-207): task i applies
+    transforms[i] to images[i] with a fresh ImageAugmenter(seed=seeds[i]).  Parameters are drawn per
+    task exactly as the reference would, then tasks are grouped per transform and executed as one
+    GPU batch each."""
+    n = len(images)
+    outs: List = [None] * n
+    groups = {t: [] for t in TRANSFORMATIONS}
+    params = [None] * n
+    for i, (t, sd) in enumerate(zip(transforms, seeds)):
+        if sd:
+            random.seed(sd)
+            np.random.seed(sd)
+        h, w = images[i].shape[:2]
+        if t == "flip":
+            params[i] = random.choice([True, False])
+        elif t == "rotate":
+            params[i] = random.uniform(-30, 30)
+        elif t == "skew":
+            s = random.uniform(0.05, 0.15)
+            params[i] = ([1 + s, 0, -s * w, 0, 1 + s, -s * h, 0, 0], True)
+        elif t == "shear":
+            k = random.uniform(-0.2, 0.2)
+            params[i] = (([1, k, 0, 0, 1, 0, 0, 0] if random.choice([True, False]) else [1, 0, 0, k, 1, 0, 0, 0]), False)
+        elif t == "crop":
+            r = random.uniform(0.8, 0.95)
+            nw, nh = int(w * r), int(h * r)
+            left = random.randint(0, w - nw)
+            params[i] = (left, random.randint(0, h - nh), nw, nh)
+        elif t == "distortion":
+            noise = np.random.normal(0, NOISE_LEVEL, images[i].shape).astype(np.uint8)
+            params[i] = (noise, random.uniform(0, 2))
+        else:
+            raise ValueError(f"unknown transform {t!r}")
+        groups[t].append(i)
+
+    def by_shape(ids):
+        d = {}
+        for i in ids:
+            d.setdefault(images[i].shape, []).append(i)
+        return d.values()
+    for ids in by_shape(groups["flip"]):
+        for i, o in zip(ids, gpu_flip([images[i] for i in ids], [params[i] for i in ids])):
+            outs[i] = o
+    for ids in by_shape(groups["rotate"]):
+        for i, o in zip(ids, gpu_rotate([images[i] for i in ids], [params[i] for i in ids])):
+            outs[i] = o
+    for ids in by_shape(groups["skew"] + groups["shear"]):
+        res = gpu_warp([images[i] for i in ids], [params[i][0] for i in ids], [params[i][1] for i in ids])
+        for i, o in zip(ids, res):
+            outs[i] = o
+    for ids in by_shape(groups["crop"]):
+        for i, o in zip(ids, gpu_crop([images[i] for i in ids], [params[i] for i in ids])):
+            outs[i] = o
+    for ids in by_shape(groups["distortion"]):
+        res = gpu_distort([images[i] for i in ids], [params[i][0] for i in ids], [params[i][1] for i in ids])
+        for i, o in zip(ids, res):
+            outs[i] = o
+    return outs

@@ -386,6 +386,7 @@ __device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out
         info8[4] = c.s_bb[3] - c.s_bb[1] + 1;
         info8[5] = (int)(best >> 32) - 1;
         info8[6] = c.s_bb[4];
+        info8[7] = (int)(c.geom[win] & 0xFFFF);  // x of the component's first raster pixel (its y is info8[2])
     }
     __syncthreads();
     return true;
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(MT, 2) k_make_mask(const uint8_t* __restrict__
         plane_to_bytes(PR, mask + img * img_px, c);
         if (threadIdx.x < 8) {
             int v = s_info[threadIdx.x];
-            if (threadIdx.x == 7) v = c.status;
+            if (threadIdx.x == 7) v = (c.status & 0xFF) | (v << 8);  // status | start_x << 8
             info[(size_t)img * 8 + threadIdx.x] = v;
         }
         __syncthreads();

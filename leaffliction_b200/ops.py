@@ -120,6 +120,19 @@ def postprocess_mask(raw: torch.Tensor, fill_size=1000, morph_kernel=3):
     return mask, info
 
 
+def trace_contour(mask: torch.Tensor, info: torch.Tensor, max_pts: int = 4096):
+    """External contour of the selected component (cv2.findContours RETR_EXTERNAL/CHAIN_APPROX_SIMPLE).
+    Returns (points [B,max_pts,2] i32, counts [B] i32, sums [B,3] i64)."""
+    _chk_img(mask, None)
+    lib = _ready(mask)
+    B, H, W = mask.shape
+    pts = torch.empty((B, max_pts, 2), dtype=torch.int32, device=mask.device)
+    cnt = torch.empty((B,), dtype=torch.int32, device=mask.device)
+    sums = torch.empty((B, 3), dtype=torch.int64, device=mask.device)
+    _lib.check(lib.lfx_trace_contour(_p(mask), _p(info), _p(pts), _p(cnt), _p(sums), B, H, W, int(max_pts), _stream()))
+    return pts, cnt, sums
+
+
 def apply_mask(x: torch.Tensor, mask: torch.Tensor, color_val: int = 255) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)
