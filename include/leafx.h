@@ -100,7 +100,7 @@ int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int W, int cod
 
 /* The TransformConfig fields the numeric path reads (Transformation.py:63-93). */
 typedef struct lfx_mask_cfg {
-    int32_t strategy;        /* 0 hsv_h, 1 lab, 2 hsv_s, 3 hsv_v_dark, 4 external raw mask */
+    int32_t strategy;        /* 0 hsv_h, 1 lab, 2 hsv_s, 3 hsv_v_dark, 4 external raw mask (lfx_raw_mask) */
     int32_t green_lo, green_hi;          /* green_hue_range */
     int32_t fill_size;                   /* pcv.fill size */
     int32_t morph_kernel;                /* 3,5,7 or 9 */
@@ -176,6 +176,39 @@ int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* in
  * Outputs are ACCUMULATED into (zero them first). */
 int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t* hist9, int32_t* hsv3,
                     int32_t* counters, int B, int H, int W, lfx_stream_t stream);
+
+/* ---- per-image front ends (one thread block per image, everything in shared memory; images with
+ *      H*W <= 65536 such as PlantVillage's 256x256 -- larger ones return LFX_ERR_UNSUPPORTED) ------ */
+
+/* Scratch for the four entry points below (run tables that outgrow shared memory + float planes). */
+size_t lfx_front_workspace(int B, int H, int W);
+
+/* cv2.Canny(gray, low, high, apertureSize=3, L2gradient) (mask.py:679-680,789; blur.py:30;
+ * analyze.py:120): gray [B,H,W] -> edges [B,H,W] (0/255).  Bit-exact. */
+int lfx_canny(const uint8_t* gray, uint8_t* edges, int B, int H, int W, double low, double high,
+              int l2gradient, void* workspace, size_t workspace_bytes, lfx_stream_t stream);
+
+/* Raw candidate masks of the composite strategies: which = 0 _create_inclusive_mask (mask.py:727-831,
+ * the reference's default strategy), which = 1 _create_enhanced_mask (mask.py:610-724).  The result
+ * feeds lfx_make_mask with strategy 4. */
+int lfx_raw_mask(const uint8_t* src, uint8_t* raw, int B, int H, int W, int which,
+                 const lfx_mask_cfg* cfg /* host */, void* workspace, size_t workspace_bytes,
+                 lfx_stream_t stream);
+
+/* apply_brown_filter numeric core (brown.py:21-89): brown predicate & leaf mask -> open/close ->
+ * 8-connected components with area >= brown_min_area_px.  spots [B,H,W] (0/255);
+ * stats[B][4] = {leaf_pixels, spot_count, spot_pixels, status}. */
+int lfx_brown_spots(const uint8_t* src, const uint8_t* mask, uint8_t* spots, int32_t* stats, int B,
+                    int H, int W, const lfx_mask_cfg* cfg /* host */, void* workspace,
+                    size_t workspace_bytes, lfx_stream_t stream);
+
+/* apply_blur_filter (blur.py:18-79): saliency map (Canny 50/150 L2 + Sobel magnitude + brown regions
+ * + colour difference to a 15x15 blur, three min-max normalisations) -> GaussianBlur 5x5
+ * (gaussian_sigma) -> zero outside `mask` -> grey replicated to RGB.  dst [B,H,W,3].
+ * Integer stages are exact; the float32 normalisations make this a +-1 LSB op. */
+int lfx_saliency_blur(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,
+                      double gaussian_sigma, const lfx_mask_cfg* cfg /* host */, void* workspace,
+                      size_t workspace_bytes, lfx_stream_t stream);
 
 /* Fused core transform profile (BASELINE config 2: blur + mask + ROI + histograms), equivalent to
  * lfx_gauss_u8(5x5) + lfx_make_mask + lfx_roi_letterbox + lfx_color_stats in one submission. */

@@ -51,6 +51,11 @@ _SIGS = {
     "lfx_gauss_u8": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, C.c_double, _P]),
     "lfx_roi_letterbox": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "lfx_color_stats": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "lfx_front_workspace": (C.c_size_t, [_I, _I, _I]),
+    "lfx_canny": (C.c_int, [_P, _P, _I, _I, _I, C.c_double, C.c_double, _I, _P, C.c_size_t, _P]),
+    "lfx_raw_mask": (C.c_int, [_P, _P, _I, _I, _I, _I, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
+    "lfx_brown_spots": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
+    "lfx_saliency_blur": (C.c_int, [_P, _P, _P, _I, _I, _I, C.c_double, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
     "lfx_pipeline_core_workspace": (C.c_size_t, [_I, _I, _I]),
     "lfx_pipeline_core": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_double,
                                     C.POINTER(MaskCfg), _P, C.c_size_t, _P]),

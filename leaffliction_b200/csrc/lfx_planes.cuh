@@ -1,0 +1,325 @@
+// Bit-packed mask planes for one image per thread block: word-parallel morphology, run-based
+// union-find connected components, per-component measures.  Shared by lfx_mask.cu (make_mask) and
+// lfx_front.cu (Canny, inclusive/enhanced front ends, saliency, brown spots).
+#pragma once
+#include <math.h>
+#include <string.h>
+
+#include "lfx_common.cuh"
+
+namespace {
+
+constexpr int MT = 512;          // threads per block
+constexpr int NPLANES = 6;       // P0 raw, PB brown, PR result, T1..T3 temps
+constexpr int RCAP_SMEM = 2048;  // runs kept in shared memory; larger tables use global scratch
+constexpr int STAGE_BYTES = 6144;
+
+struct FootRow {
+    int8_t dy, o1, o2, pad;
+};
+struct Footprint {
+    int n;
+    FootRow r[20];
+};
+
+struct MaskParams {
+    lfx_mask_cfg cfg;
+    Footprint fp_morph, fp_brown, fp_search;
+    int H, W, WPR, NW;
+    uint32_t lastmask;
+    int planes_in_smem;
+    int rcap_glob;
+    int stage_rows;
+    int mode;  // 0 make_mask, 1 postprocess only
+    unsigned long long ws_per_block;
+};
+
+struct Ctx {
+    int H, W, WPR, NW;
+    uint32_t lastmask;
+    uint32_t* plane[NPLANES];
+    int* wbase;
+    // run tables (current selection) + both backing stores
+    int* parent;
+    uint32_t* geom;
+    int* acc;
+    uint16_t* ry;
+    int *sm_parent, *gl_parent;
+    uint32_t *sm_geom, *gl_geom;
+    int *sm_acc, *gl_acc;
+    uint16_t *sm_ry, *gl_ry;
+    int rcap_glob;
+    int rcap_smem;
+    int R;
+    // scratch
+    int* s_tmp;                  // [40]
+    unsigned long long* s_best;  // [1]
+    int* s_bb;                   // [8]
+    int* s_hist;                 // [256]
+    int status;
+};
+
+__device__ __forceinline__ uint32_t valid_mask(const Ctx& c, int w) { return (w == c.WPR - 1) ? c.lastmask : 0xFFFFFFFFu; }
+
+// ---------------------------------------------------------------- block primitives
+__device__ int block_exscan(int v, int* s_tmp, int& total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_tmp[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < MT / 32) ? s_tmp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < MT / 32) s_tmp[lane] = winc - w;
+        if (lane == 31) s_tmp[32] = winc;
+    }
+    __syncthreads();
+    const int res = s_tmp[wid] + inc - v;
+    total = s_tmp[32];
+    __syncthreads();
+    return res;
+}
+
+__device__ __forceinline__ void plane_zero(uint32_t* p, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) p[i] = 0;
+}
+__device__ __forceinline__ void plane_copy(uint32_t* d, const uint32_t* s, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------- morphology
+template <bool DIL>
+__device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        const int y = i / c.WPR, w = i - y * c.WPR;
+        uint32_t acc = DIL ? 0u : 0xFFFFFFFFu;
+        for (int k = 0; k < fp.n; ++k) {
+            const int yy = y + fp.r[k].dy;
+            if (yy < 0 || yy >= c.H) continue;  // outside rows are ignored by both min and max
+            const uint32_t* row = in + yy * c.WPR;
+            const uint32_t oob = DIL ? 0u : 0xFFFFFFFFu;
+            uint32_t cur = row[w];
+            if (!DIL && w == c.WPR - 1) cur |= ~c.lastmask;
+            uint32_t prev = (w > 0) ? row[w - 1] : oob;
+            uint32_t next = oob;
+            if (w + 1 < c.WPR) {
+                next = row[w + 1];
+                if (!DIL && w + 1 == c.WPR - 1) next |= ~c.lastmask;
+            }
+            const int o1 = fp.r[k].o1, o2 = fp.r[k].o2;
+            for (int o = o1; o <= o2; ++o) {
+                // bit x of v = source bit (x + o)
+                const uint32_t v = (o < 0) ? __funnelshift_r(prev, cur, 32 + o) : __funnelshift_r(cur, next, o);
+                acc = DIL ? (acc | v) : (acc & v);
+            }
+        }
+        out[i] = acc & valid_mask(c, w);
+    }
+}
+
+// ---------------------------------------------------------------- runs + union-find
+__device__ __forceinline__ uint32_t starts_of(const uint32_t* m, int idx, int w) {
+    const uint32_t cur = m[idx];
+    const uint32_t pb = (w > 0) ? (m[idx - 1] >> 31) : 0u;
+    return cur & ~((cur << 1) | pb);
+}
+
+__device__ __forceinline__ int uf_find(const int* parent, int x) {
+    int p = parent[x];
+    while (p != x) {
+        x = p;
+        p = parent[x];
+    }
+    return x;
+}
+__device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+// Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
+// (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
+template <int CONN>
+__device__ void ccl(const uint32_t* m, Ctx& c) {
+    const int per = (c.NW + MT - 1) / MT;
+    const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += __popc(starts_of(m, i, i % c.WPR));
+    int total;
+    int base = block_exscan(cnt, c.s_tmp, total);
+    for (int i = i0; i < i1; ++i) {
+        c.wbase[i] = base;
+        base += __popc(starts_of(m, i, i % c.WPR));
+    }
+    c.R = total;
+    if (total <= c.rcap_smem) {
+        c.parent = c.sm_parent; c.geom = c.sm_geom; c.acc = c.sm_acc; c.ry = c.sm_ry;
+    } else {
+        c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
+        c.status |= 2;
+    }
+    __syncthreads();
+    int* parent = c.parent;
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        const int y = i / c.WPR, w = i - y * c.WPR;
+        uint32_t st = starts_of(m, i, w);
+        int id = c.wbase[i];
+        const uint32_t word = m[i];
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            const int x0 = w * 32 + b;
+            const uint32_t inv = ~(word >> b);
+            const int z = __ffs(inv) - 1;  // first zero at/after b (relative); -1 if none
+            int x1;
+            if (inv != 0 && z < 32 - b) {
+                x1 = x0 + z - 1;
+            } else {
+                x1 = w * 32 + 31;
+                int ww = w + 1;
+                while (ww < c.WPR) {
+                    const uint32_t nx = m[y * c.WPR + ww];
+                    if (nx == 0xFFFFFFFFu) {
+                        x1 += 32;
+                        ++ww;
+                        continue;
+                    }
+                    x1 += __ffs(~nx) - 1;
+                    break;
+                }
+            }
+            c.geom[id] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+            c.ry[id] = (uint16_t)y;
+            parent[id] = id;
+            c.acc[id] = 0;
+            ++id;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int y = c.ry[r];
+        if (y == 0) continue;
+        const uint32_t g = c.geom[r];
+        const int x0 = g & 0xFFFF, x1 = g >> 16;
+        const int lo = max(0, x0 - (CONN == 8 ? 1 : 0)), hi = min(c.W - 1, x1 + (CONN == 8 ? 1 : 0));
+        const uint32_t* up = m + (y - 1) * c.WPR;
+        int p = lo;
+        while (p <= hi) {
+            int wi = p >> 5;
+            uint32_t v = up[wi] & (0xFFFFFFFFu << (p & 31));
+            while (v == 0) {
+                ++wi;
+                if (wi * 32 > hi) break;
+                v = up[wi];
+            }
+            if (v == 0) break;
+            const int b = __ffs(v) - 1;
+            if (wi * 32 + b > hi) break;
+            const int idxw = (y - 1) * c.WPR + wi;
+            const uint32_t st = starts_of(m, idxw, wi);
+            const int id2 = c.wbase[idxw] + __popc(st & ((2u << b) - 1u)) - 1;
+            uf_unite(parent, r, id2);
+            p = (int)(c.geom[id2] >> 16) + 1;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int root = uf_find(parent, r);
+        // benign race: other threads may still chase through parent[r]; any value on the
+        // path is an ancestor, so their walks still end at the same root
+        parent[r] = root;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void set_run(uint32_t* out, int y, int x0, int x1, const Ctx& c) {
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t mk = 0xFFFFFFFFu;
+        if (w == w0) mk &= 0xFFFFFFFFu << (x0 & 31);
+        if (w == w1) mk &= 0xFFFFFFFFu >> (31 - (x1 & 31));
+        atomicOr(&out[y * c.WPR + w], mk);
+    }
+}
+
+__device__ __forceinline__ int popc_range(const uint32_t* row, int x0, int x1) {
+    const int w0 = x0 >> 5, w1 = x1 >> 5;
+    int n = 0;
+    for (int w = w0; w <= w1; ++w) {
+        uint32_t mk = 0xFFFFFFFFu;
+        if (w == w0) mk &= 0xFFFFFFFFu << (x0 & 31);
+        if (w == w1) mk &= 0xFFFFFFFFu >> (31 - (x1 & 31));
+        n += __popc(row[w] & mk);
+    }
+    return n;
+}
+__device__ __forceinline__ int get_bit(const uint32_t* m, int y, int x, const Ctx& c) {
+    if (y < 0 || y >= c.H || x < 0 || x >= c.W) return 0;
+    return (m[y * c.WPR + (x >> 5)] >> (x & 31)) & 1;
+}
+
+// acc[root] += pixels
+__device__ void measure_area(Ctx& c) {
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        const uint32_t g = c.geom[r];
+        atomicAdd(&c.acc[c.parent[r]], (int)(g >> 16) - (int)(g & 0xFFFF) + 1);
+    }
+    __syncthreads();
+}
+
+// out = runs whose component has >= min_area pixels (out must be zeroed + synced by the caller)
+__device__ void keep_area_ge(uint32_t* out, int min_area, Ctx& c) {
+    for (int r = threadIdx.x; r < c.R; r += MT) {
+        if (c.acc[c.parent[r]] >= min_area) {
+            const uint32_t g = c.geom[r];
+            set_run(out, c.ry[r], g & 0xFFFF, g >> 16, c);
+        }
+    }
+    __syncthreads();
+}
+
+
+static inline Footprint make_ellipse(int k) {
+    // cv::getStructuringElement(MORPH_ELLIPSE, (k,k)), anchor (k/2, k/2)
+    Footprint f;
+    f.n = 0;
+    const int r = k / 2, cc = k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < k; ++i) {
+        const int dy = i - r;
+        if (abs(dy) > r) continue;
+        const int dx = (int)nearbyint(cc * sqrt((r * r - dy * dy) * inv_r2));
+        const int j1 = max(cc - dx, 0), j2 = min(cc + dx + 1, k);
+        if (j2 <= j1) continue;
+        f.r[f.n].dy = (int8_t)dy;
+        f.r[f.n].o1 = (int8_t)(j1 - cc);
+        f.r[f.n].o2 = (int8_t)(j2 - 1 - cc);
+        f.r[f.n].pad = 0;
+        ++f.n;
+    }
+    return f;
+}
+
+
+}  // namespace

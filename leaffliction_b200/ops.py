@@ -120,6 +120,53 @@ def postprocess_mask(raw: torch.Tensor, fill_size=1000, morph_kernel=3):
     return mask, info
 
 
+def canny(gray: torch.Tensor, low: float, high: float, l2: bool = False) -> torch.Tensor:
+    """cv2.Canny(gray, low, high, L2gradient=l2) on [B,H,W] uint8."""
+    _chk_img(gray, None)
+    lib = _ready(gray)
+    B, H, W = gray.shape
+    out = torch.empty_like(gray)
+    ws = _workspace(lib.lfx_front_workspace(B, H, W), gray.device)
+    _lib.check(lib.lfx_canny(_p(gray), _p(out), B, H, W, float(low), float(high), int(bool(l2)), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def raw_mask_front_end(x: torch.Tensor, which: str, cfg: MaskCfg) -> torch.Tensor:
+    """Raw candidate of the 'inclusive' / 'enhanced' strategies (mask.py:727-831, :610-724)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    ws = _workspace(lib.lfx_front_workspace(B, H, W), x.device)
+    _lib.check(lib.lfx_raw_mask(_p(x), _p(out), B, H, W, {"inclusive": 0, "enhanced": 1}[which], C.byref(cfg),
+                                _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def brown_spots(x: torch.Tensor, mask: torch.Tensor, cfg: MaskCfg):
+    """apply_brown_filter core: (spots [B,H,W] u8, stats [B,4] = leaf_px, count, spot_px, status)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    stats = torch.empty((B, 4), dtype=torch.int32, device=x.device)
+    ws = _workspace(lib.lfx_front_workspace(B, H, W), x.device)
+    _lib.check(lib.lfx_brown_spots(_p(x), _p(mask), _p(out), _p(stats), B, H, W, C.byref(cfg), _p(ws), ws.numel(), _stream()))
+    return out, stats
+
+
+def saliency_blur(x: torch.Tensor, mask: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5) -> torch.Tensor:
+    """apply_blur_filter given the leaf mask of make_mask(x): [B,H,W,3] u8."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty_like(x)
+    ws = _workspace(lib.lfx_front_workspace(B, H, W), x.device)
+    _lib.check(lib.lfx_saliency_blur(_p(x), _p(mask), _p(out), B, H, W, float(gaussian_sigma), C.byref(cfg),
+                                     _p(ws), ws.numel(), _stream()))
+    return out
+
+
 def trace_contour(mask: torch.Tensor, info: torch.Tensor, max_pts: int = 4096):
     """External contour of the selected component (cv2.findContours RETR_EXTERNAL/CHAIN_APPROX_SIMPLE).
     Returns (points [B,max_pts,2] i32, counts [B] i32, sums [B,3] i64)."""
