@@ -1,0 +1,716 @@
+// Fused core transform profile (BASELINE config 2: 5x5 Gaussian blur + make_mask + masked ROI letterbox +
+// RGB/HSV/LAB histograms) -- one persistent thread block per image, everything between the first read
+// of the image and the last output store stays in shared memory.
+//
+//   phase A  32-row source tiles arrive by TMA bulk copy (cp.async.bulk + mbarrier).  Vertical blur pass
+//            on packed byte pairs -> de-interleaved 16-bit planes in shared memory; horizontal pass with
+//            dp2a (two taps per instruction) -> blur rows to HBM.  Same tile: RGB->HSV(/Lab) threshold and
+//            brown predicates -> bit planes (warp ballots).
+//   phase B  mask_finish (lfx_maskops.cuh): _postprocess_mask, Otsu fallback, brown extension on the bit
+//            planes; mask bytes + info to HBM.
+//   phase C  tiles again (L2 hits): histograms / category counters of the masked pixels (shared-memory
+//            atomics, LUT-packed counters), apply_mask(white) in place, INTER_AREA letterbox of the
+//            bounding box, canvas rows leave by TMA bulk store.
+//
+// Reference: srcs/transform/filters/blur.py:72 (GaussianBlur 5x5), mask.py:548-582 (make_mask),
+// roi.py:20-46, hist.py:22-67,188,248-256, utils/mask_utils.py:10-83.  Arithmetic identical to the
+// stand-alone kernels (lfx_gauss.cu, lfx_mask.cu, lfx_roi.cu, lfx_color.cu), which remain the general path.
+#include "lfx_maskops.cuh"
+
+namespace {
+
+constexpr int TR = 32;     // image rows per staged tile
+constexpr int CHUNK = 16;  // ROI canvas rows per bulk store
+constexpr int NWARPS = MT / 32;
+
+struct Tap {
+    int s;       // source index
+    short a, b;  // weights (x2048) for s and s+1
+};
+
+struct CoreParams {
+    MaskParams M;
+    uint32_t K01, K23, K4_, K_0, K12, K34;  // horizontal taps paired for dp2a
+    int t0, t1, t2;                         // symmetric vertical taps (t0 = taps[0] = taps[4], ...)
+    int RH, RW;
+    int need_lab_a;                         // Lab needed in phase A (lab strategy / lab brown)
+    // shared-memory byte offsets
+    int off_planes, off_hsv, off_lab, off_union;
+    int off_src, off_v;                              // phase A (inside the union)
+    int off_t, off_wbase, off_runs, off_stage;       // phase B
+    int off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A)
+    int smem_bytes;
+    unsigned long long ws_per_block;
+};
+
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_90+ PTX)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ int refl101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// Rows y0-2 .. y0+nr+1 of the image (BORDER_REFLECT_101 above/below) -> s_src, one mbarrier phase.
+// Called by ONE thread.  H >= 3.
+__device__ void issue_tile_load(const uint8_t* simg, uint8_t* s_src, uint64_t* bar, int y0, int nr, int H, int RB,
+                                const void* extra_g, void* extra_s, uint32_t extra_bytes) {
+    const int first = y0 - 2, rows = nr + 4;
+    const int lo = max(first, 0), hi = min(first + rows - 1, H - 1);
+    fence_async_smem();
+    mbar_expect_tx(bar, (uint32_t)rows * RB + extra_bytes);
+    bulk_g2s(s_src + (size_t)(lo - first) * RB, simg + (size_t)lo * RB, (uint32_t)(hi - lo + 1) * RB, bar);
+    for (int t = 0; t < lo - first; ++t) bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar);
+    for (int t = hi - first + 1; t < rows; ++t)
+        bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar);
+    if (extra_bytes) bulk_g2s(extra_s, extra_g, extra_bytes, bar);
+}
+
+// ---------------------------------------------------------------- phase A: blur
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+
+// Vertical 5-tap pass on 4 pixels (12 bytes = 3 words) x 4 output rows per thread, packed 2x16-bit
+// (sums <= 255*256 fit), results de-interleaved into the 16-bit channel planes s_v[c][row][x+2].
+__device__ __forceinline__ void vpass_item(const uint8_t* s_src, uint16_t* s_v, int g, int r0, int RB, int VP, int G,
+                                           const CoreParams& P) {
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s_src + (size_t)r0 * RB) + 3 * g;
+    const int rw = RB >> 2;
+    uint32_t lo[5][3], hi[5][3];
+#pragma unroll
+    for (int step = 0; step < 8; ++step) {
+        const int slot = step % 5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t w = sp[step * rw + k];
+            lo[slot][k] = w & 0x00FF00FFu;
+            hi[slot][k] = (w >> 8) & 0x00FF00FFu;
+        }
+        if (step >= 4) {
+            // window rows step-4 .. step live in slots (step-4)%5 .. step%5
+            const int s0 = (step + 1) % 5, s1 = (step + 2) % 5, s2 = (step + 3) % 5, s3 = (step + 4) % 5, s4 = slot;
+            uint32_t l[3], h[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                l[k] = (lo[s0][k] + lo[s4][k]) * P.t0 + (lo[s1][k] + lo[s3][k]) * P.t1 + lo[s2][k] * P.t2;
+                h[k] = (hi[s0][k] + hi[s4][k]) * P.t0 + (hi[s1][k] + hi[s3][k]) * P.t1 + hi[s2][k] * P.t2;
+            }
+            // bytes: w0 = (R0,G0,B0,R1) w1 = (G1,B1,R2,G2) w2 = (B2,R3,G3,B3);  l = even bytes, h = odd bytes
+            const uint32_t R01 = prmt(l[0], h[0], 0x7610), R23 = prmt(l[1], h[2], 0x5432);
+            const uint32_t G01 = prmt(h[0], l[1], 0x5410), G23 = prmt(h[1], l[2], 0x7632);
+            const uint32_t B01 = prmt(l[0], h[1], 0x5432), B23 = prmt(l[2], h[2], 0x7610);
+            const int orow = r0 + step - 4;
+            uint32_t* vr = reinterpret_cast<uint32_t*>(s_v + (size_t)orow * VP) + 2 * g + 1;  // element 4g+2
+            const int cs = (TR * VP) >> 1;                                                     // channel stride in words
+            vr[0] = R01; vr[1] = R23;
+            vr[cs] = G01; vr[cs + 1] = G23;
+            vr[2 * cs] = B01; vr[2 * cs + 1] = B23;
+            if (g == 0) {  // x = -2,-1 mirror x = 2,1
+                vr[-1] = prmt(R01, R23, 0x3254);
+                vr[cs - 1] = prmt(G01, G23, 0x3254);
+                vr[2 * cs - 1] = prmt(B01, B23, 0x3254);
+            }
+            if (g == G - 1) {  // x = W,W+1 mirror x = W-2,W-3
+                vr[2] = prmt(R01, R23, 0x3254);
+                vr[cs + 2] = prmt(G01, G23, 0x3254);
+                vr[2 * cs + 2] = prmt(B01, B23, 0x3254);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t pack4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return prmt(prmt(a, b, 0x0062), prmt(c, d, 0x0062), 0x5410);  // byte 2 of each accumulator
+}
+
+// Horizontal 5-tap pass for 4 pixels of one row: 3 dp2a per output value, (v + 32768) >> 16 = byte 2.
+__device__ __forceinline__ void hpass_item(const uint16_t* s_v, uint8_t* brow, int g, int r, int VP, const CoreParams& P) {
+    uint32_t acc[3][4];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const uint2* q = reinterpret_cast<const uint2*>(s_v + (size_t)(c * TR + r) * VP) + g;
+        const uint2 q0 = q[0], q1 = q[1];
+        const uint32_t w0 = q0.x, w1 = q0.y, w2 = q1.x, w3 = q1.y;
+        acc[c][0] = __dp2a_lo(w2, P.K4_, __dp2a_lo(w1, P.K23, __dp2a_lo(w0, P.K01, 32768u)));
+        acc[c][1] = __dp2a_lo(w2, P.K34, __dp2a_lo(w1, P.K12, __dp2a_lo(w0, P.K_0, 32768u)));
+        acc[c][2] = __dp2a_lo(w3, P.K4_, __dp2a_lo(w2, P.K23, __dp2a_lo(w1, P.K01, 32768u)));
+        acc[c][3] = __dp2a_lo(w3, P.K34, __dp2a_lo(w2, P.K12, __dp2a_lo(w1, P.K_0, 32768u)));
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(brow) + 3 * g;
+    o[0] = pack4(acc[0][0], acc[1][0], acc[2][0], acc[0][1]);
+    o[1] = pack4(acc[1][1], acc[2][1], acc[0][2], acc[1][2]);
+    o[2] = pack4(acc[2][2], acc[0][3], acc[1][3], acc[2][3]);
+}
+
+// ---------------------------------------------------------------- phase C helpers
+// cv::resize area-mode 2-tap coefficients for destination index d (src -> dst upscale); lfx_roi.cu.
+__device__ __forceinline__ Tap area_tap2(int d, int src, int dst) {
+    const double inv = __ddiv_rn((double)dst, (double)src);
+    const double scale = __ddiv_rn(1.0, inv);
+    int sx = (int)floor(__dmul_rn((double)d, scale));
+    float fx = __double2float_rn(__dadd_rn((double)(d + 1), -__dmul_rn((double)(sx + 1), inv)));
+    fx = fx <= 0.f ? 0.f : __fadd_rn(fx, -floorf(fx));
+    if (sx < 0) {
+        fx = 0.f;
+        sx = 0;
+    }
+    if (sx >= src - 1) {
+        fx = 0.f;
+        sx = src - 1;
+    }
+    Tap t;
+    t.s = sx;
+    t.a = (short)__float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f));
+    t.b = (short)__float2int_rn(__fmul_rn(fx, 2048.f));
+    return t;
+}
+
+struct Geo {
+    int found, bx, by, bw, bh, nw, nh, ox, oy;
+};
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(MT, 2)
+    k_core(const uint8_t* __restrict__ src, uint8_t* __restrict__ blur, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
+           uint8_t* __restrict__ roi, int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3, int32_t* __restrict__ counters,
+           int B, const CoreParams P, uint8_t* __restrict__ ws, const LfxTables* __restrict__ tab,
+           const uint4* __restrict__ cat_lut) {
+    extern __shared__ __align__(128) uint8_t sm[];
+    __shared__ int s_tmp[40];
+    __shared__ unsigned long long s_best;
+    __shared__ int s_bb[8];
+    __shared__ int s_hist256[256];
+    __shared__ int s_info[8];
+    __shared__ int s_info2[8];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_next;
+    __shared__ Geo s_geo;
+    __shared__ int s_dlo[TR + 2];  // first canvas row of each source tile (H <= TR*(TR+1) rows is plenty: H*W <= 65536, W >= 32)
+    __shared__ uint32_t s_cnt[16];
+
+    const MaskParams& M = P.M;
+    const int H = M.H, W = M.W, WPR = M.WPR, NW = M.NW, RB = W * 3, VP = W + 4, G = W >> 2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int ntiles = (H + TR - 1) / TR;
+
+    Ctx c;
+    ctx_init_geometry(c, H, W, WPR, NW, M.lastmask);
+    c.s_tmp = s_tmp; c.s_best = &s_best; c.s_bb = s_bb; c.s_hist = s_hist256;
+    c.rcap_glob = M.rcap_glob;
+    c.rcap_smem = RCAP_SMEM;
+    uint32_t* P0 = reinterpret_cast<uint32_t*>(sm + P.off_planes);
+    uint32_t* PB = P0 + NW;
+    uint32_t* PR = PB + NW;
+    uint32_t* T1 = reinterpret_cast<uint32_t*>(sm + P.off_t);
+    uint32_t* T2 = T1 + NW;
+    uint32_t* T3 = T2 + NW;
+    c.plane[0] = P0; c.plane[1] = PB; c.plane[2] = PR; c.plane[3] = T1; c.plane[4] = T2; c.plane[5] = T3;
+    c.wbase = reinterpret_cast<int*>(sm + P.off_wbase);
+    c.sm_parent = reinterpret_cast<int*>(sm + P.off_runs);
+    c.sm_geom = reinterpret_cast<uint32_t*>(sm + P.off_runs + RCAP_SMEM * 4);
+    c.sm_acc = reinterpret_cast<int*>(sm + P.off_runs + RCAP_SMEM * 8);
+    c.sm_ry = reinterpret_cast<uint16_t*>(sm + P.off_runs + RCAP_SMEM * 12);
+    {
+        uint8_t* gp = ws + 256 + (size_t)blockIdx.x * P.ws_per_block;
+        auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+        c.gl_parent = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
+        c.gl_geom = reinterpret_cast<uint32_t*>(gp); gp += al((size_t)M.rcap_glob * 4);
+        c.gl_acc = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
+        c.gl_ry = reinterpret_cast<uint16_t*>(gp);
+    }
+    if ((size_t)NW * 12 <= (size_t)RCAP_SMEM * 14) {
+        c.hp[0] = P0; c.hp[1] = T3; c.hp[2] = reinterpret_cast<uint32_t*>(c.wbase);
+        for (int k = 0; k < 3; ++k) c.hp[3 + k] = reinterpret_cast<uint32_t*>(c.sm_parent) + (size_t)k * NW;
+    }
+    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(sm + P.off_hsv);
+    LabLut* s_lab = reinterpret_cast<LabLut*>(sm + P.off_lab);
+    uint8_t* s_src = sm + P.off_src;
+    uint16_t* s_v = reinterpret_cast<uint16_t*>(sm + P.off_v);
+    uint8_t* s_stage = sm + P.off_stage;
+    uint8_t* s_out = sm + P.off_out;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(sm + P.off_hist);
+    const uint4* s_cat = reinterpret_cast<const uint4*>(sm + P.off_cat);
+    Tap* s_xt = reinterpret_cast<Tap*>(sm + P.off_xt);
+    Tap* s_yt = reinterpret_cast<Tap*>(sm + P.off_yt);
+
+    load_hsv_lut(s_hsv, tab);
+    load_lab_lut(s_lab, tab);
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t par = 0;
+    int* work_counter = reinterpret_cast<int*>(ws);
+    const size_t img_px = (size_t)H * W;
+    const bool want_stats = hist9 || hsv3 || counters;
+
+    for (;;) {
+        if (threadIdx.x == 0) s_next = atomicAdd(work_counter, 1);
+        __syncthreads();
+        const int img = s_next;
+        if (img >= B) break;
+        const uint8_t* simg = src + (size_t)img * img_px * 3;
+
+        // =========================================================== phase A
+        if (threadIdx.x == 0) issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, nullptr, nullptr, 0);
+        for (int t = 0; t < ntiles; ++t) {
+            const int y0 = t * TR, nr = min(TR, H - y0);
+            mbar_wait(&s_bar, par);
+            par ^= 1;
+            if (blur) {
+                const int nstrips = (nr + 3) >> 2;
+                for (int item = threadIdx.x; item < G * nstrips; item += MT) {
+                    const int strip = item / G, g = item - strip * G;
+                    vpass_item(s_src, s_v, g, strip * 4, RB, VP, G, P);
+                }
+            }
+            for (int item = wid; item < nr * WPR; item += NWARPS) {
+                int ry, w;
+                split_index(c, item, ry, w);
+                const uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
+                const int r = px[0], g = px[1], b = px[2];
+                int h, s, v;
+                rgb2hsv(r, g, b, s_hsv, h, s, v);
+                bool b0, b1;
+                if (P.need_lab_a) {
+                    int L, A, Bv;
+                    rgb2lab(r, g, b, s_lab, L, A, Bv);
+                    b0 = (M.cfg.strategy == 1) ? ((A <= 135) && (Bv >= 115) && (Bv <= 170))
+                                               : ((h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40));
+                    b1 = M.cfg.use_lab_brown ? ((A >= M.cfg.lab_a_min) && (Bv >= M.cfg.lab_b_min))
+                                             : ((h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) &&
+                                                (v <= M.cfg.brown_v_max));
+                } else {
+                    b0 = (h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40);  // mask.py:90
+                    b1 = (h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
+                }
+                const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
+                const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
+                if (lane == 0) {
+                    const int idx = (y0 + ry) * WPR + w;
+                    P0[idx] = m0;
+                    PB[idx] = m1;
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0 && t + 1 < ntiles)
+                issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
+            if (blur) {
+                uint8_t* bimg = blur + (size_t)img * img_px * 3;
+                for (int item = threadIdx.x; item < G * nr; item += MT) {
+                    const int r = item / G, g = item - r * G;
+                    hpass_item(s_v, bimg + (size_t)(y0 + r) * RB, g, r, VP, P);
+                }
+                __syncthreads();
+            }
+        }
+
+        // =========================================================== phase B
+        c.status = 0;
+        mask_finish(simg, s_stage, s_hsv, P0, PB, PR, T1, T2, T3, s_info, s_info2, M, c);
+        plane_to_bytes(PR, mask + (size_t)img * img_px, c);
+        if (threadIdx.x < 8) {
+            int v = s_info[threadIdx.x];
+            if (threadIdx.x == 7) v = (c.status & 0xFF) | (v << 8);
+            info[(size_t)img * 8 + threadIdx.x] = v;
+        }
+        if (!roi && !want_stats) {
+            __syncthreads();
+            continue;
+        }
+
+        // =========================================================== phase C
+        if (threadIdx.x == 0) {
+            Geo gq;
+            gq.found = s_info[0]; gq.bx = s_info[1]; gq.by = s_info[2]; gq.bw = s_info[3]; gq.bh = s_info[4];
+            gq.nw = gq.nh = gq.ox = gq.oy = 0;
+            if (roi && gq.found && gq.bw > 0 && gq.bh > 0) {
+                // scale = min(W / max(w,1), H / max(h,1)); nw = max(int(w*scale),1)   (roi.py:35-36)
+                const double sc = fmin(__ddiv_rn((double)P.RW, (double)max(gq.bw, 1)), __ddiv_rn((double)P.RH, (double)max(gq.bh, 1)));
+                gq.nw = max((int)__dmul_rn((double)gq.bw, sc), 1);
+                gq.nh = max((int)__dmul_rn((double)gq.bh, sc), 1);
+                gq.ox = (P.RW - gq.nw) / 2;
+                gq.oy = (P.RH - gq.nh) / 2;
+            } else {
+                gq.found = 0;
+            }
+            s_geo = gq;
+        }
+        for (int i = threadIdx.x; i < 12 * 256; i += MT) s_hist[i] = 0;
+        if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < CHUNK * P.RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();  // also: every phase-B reader of the union region is done
+        const Geo geo = s_geo;
+        if (threadIdx.x == 0)
+            issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, cat_lut, sm + P.off_cat, want_stats ? 3 * 256 * 16 : 0);
+        uint8_t* rimg = roi ? roi + (size_t)img * P.RH * P.RW * 3 : nullptr;
+        if (roi) {
+            for (int i = threadIdx.x; i < geo.nw; i += MT) s_xt[i] = area_tap2(i, geo.bw, geo.nw);
+            for (int i = threadIdx.x; i < geo.nh; i += MT) s_yt[i] = area_tap2(i, geo.bh, geo.nh);
+            // letterbox bands above / below the resized box (the whole canvas when nothing was found)
+            if (threadIdx.x == 0) {
+                fence_async_smem();
+                const int top = geo.found ? geo.oy : P.RH;
+                for (int r0 = 0; r0 < top; r0 += CHUNK)
+                    bulk_s2g(rimg + (size_t)r0 * P.RW * 3, s_out, (uint32_t)min(CHUNK, top - r0) * P.RW * 3);
+                if (geo.found)
+                    for (int r0 = geo.oy + geo.nh; r0 < P.RH; r0 += CHUNK)
+                        bulk_s2g(rimg + (size_t)r0 * P.RW * 3, s_out, (uint32_t)min(CHUNK, P.RH - r0) * P.RW * 3);
+                bulk_commit();
+            }
+            __syncthreads();
+            // first canvas row whose upper source row lies in tile t (monotone in d): binary search
+            if (threadIdx.x <= ntiles) {
+                int lo = 0, hi = geo.nh;
+                const int ylim = threadIdx.x * TR;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (geo.by + s_yt[mid].s >= ylim) hi = mid; else lo = mid + 1;
+                }
+                s_dlo[threadIdx.x] = lo;
+            }
+        }
+        uint32_t cacc[4] = {0u, 0u, 0u, 0u};
+        for (int t = 0; t < ntiles; ++t) {
+            const int y0 = t * TR, nr = min(TR, H - y0);
+            mbar_wait(&s_bar, par);
+            par ^= 1;
+            __syncthreads();  // s_dlo / taps visible (t == 0)
+            if (want_stats) {
+                for (int item = wid; item < nr * WPR; item += NWARPS) {
+                    int ry, w;
+                    split_index(c, item, ry, w);
+                    const uint32_t m = PR[(y0 + ry) * WPR + w];
+                    if (m == 0u) continue;
+                    if ((m >> lane) & 1u) {
+                        const uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
+                        const int r = px[0], g = px[1], b = px[2];
+                        int h, s, v, L, A, Bv;
+                        rgb2hsv(r, g, b, s_hsv, h, s, v);
+                        rgb2lab(r, g, b, s_lab, L, A, Bv);
+                        atomicAdd(&s_hist[0 * 256 + r], 1u);
+                        atomicAdd(&s_hist[1 * 256 + g], 1u);
+                        atomicAdd(&s_hist[2 * 256 + b], 1u);
+                        atomicAdd(&s_hist[3 * 256 + h], 1u);
+                        atomicAdd(&s_hist[4 * 256 + s], 1u);
+                        atomicAdd(&s_hist[5 * 256 + v], 1u);
+                        atomicAdd(&s_hist[6 * 256 + L], 1u);
+                        atomicAdd(&s_hist[7 * 256 + A], 1u);
+                        atomicAdd(&s_hist[8 * 256 + Bv], 1u);
+                        // leaf mask + 8 categories + 5 hue ranges (hist.py:188,38-65,248-256): per-channel LUTs of
+                        // byte-packed 0/1 flags, AND = joint predicate, packed 8-bit counters (<= 128 px / thread)
+                        const uint4 qh = s_cat[h], qs = s_cat[256 + s], qv = s_cat[512 + v];
+                        const uint32_t q0 = qh.x & qs.x & qv.x;
+                        cacc[0] += q0;
+                        cacc[1] += qh.y & qs.y & qv.y;
+                        cacc[2] += qh.z & qs.z & qv.z;
+                        cacc[3] += qh.w & qs.w & qv.w;
+                        if (q0 & 1u) {
+                            atomicAdd(&s_hist[9 * 256 + h], 1u);
+                            atomicAdd(&s_hist[10 * 256 + s], 1u);
+                            atomicAdd(&s_hist[11 * 256 + v], 1u);
+                        }
+                    }
+                }
+            }
+            if (roi && geo.found) {
+                __syncthreads();
+                // apply_mask(rgb, mask, "white") in place on the staged rows y0 .. y0+nr (Transformation.py:451)
+                const int mrows = min(nr + 1, H - y0);
+                for (int item = wid; item < mrows * WPR; item += NWARPS) {
+                    int ry, w;
+                    split_index(c, item, ry, w);
+                    const uint32_t m = PR[(y0 + ry) * WPR + w];
+                    if (m == 0xFFFFFFFFu) continue;
+                    if (!((m >> lane) & 1u)) {
+                        uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
+                        px[0] = 255; px[1] = 255; px[2] = 255;
+                    }
+                }
+                __syncthreads();
+                const int dA = s_dlo[t], dB = s_dlo[t + 1];
+                const int cols = min(geo.nw, MT);
+                const int strips = max(1, MT / cols);
+                const int strip = threadIdx.x / cols, col0 = threadIdx.x - strip * cols;
+                for (int d0 = dA; d0 < dB; d0 += CHUNK) {
+                    const int rows = min(CHUNK, dB - d0);
+                    if (threadIdx.x == 0) bulk_wait_read();  // the previous store has drained s_out
+                    __syncthreads();
+                    if (geo.nw < P.RW) {
+                        for (int i = threadIdx.x; i < rows * P.RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+                        __syncthreads();
+                    }
+                    if (strip < strips) {
+                        const int per = (rows + strips - 1) / strips;
+                        const int da = d0 + strip * per, db = min(d0 + rows, da + per);
+                        for (int cx = col0; cx < geo.nw; cx += cols) {
+                            const Tap tx = s_xt[cx];
+                            const uint8_t* colp = s_src + (geo.bx + tx.s) * 3;
+                            int prev_s = -4, h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
+                            for (int d = da; d < db; ++d) {
+                                const Tap ty = s_yt[d];
+                                const uint8_t* p = colp + (size_t)(geo.by + ty.s - y0 + 2) * RB;
+                                if (ty.s != prev_s) {
+                                    if (ty.s == prev_s + 1) {
+#pragma unroll
+                                        for (int ch = 0; ch < 3; ++ch) h0[ch] = h1[ch];
+                                    } else {
+#pragma unroll
+                                        for (int ch = 0; ch < 3; ++ch) h0[ch] = ((int)p[ch] * tx.a + (int)p[ch + 3] * tx.b) >> 4;
+                                    }
+#pragma unroll
+                                    for (int ch = 0; ch < 3; ++ch) h1[ch] = ((int)p[RB + ch] * tx.a + (int)p[RB + ch + 3] * tx.b) >> 4;
+                                    prev_s = ty.s;
+                                }
+                                uint8_t* o = s_out + ((size_t)(d - d0) * P.RW + geo.ox + cx) * 3;
+#pragma unroll
+                                for (int ch = 0; ch < 3; ++ch) {
+                                    // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>
+                                    int res = ((((int)ty.a * h0[ch]) >> 16) + (((int)ty.b * h1[ch]) >> 16) + 2) >> 2;
+                                    res = min(255, max(0, res));
+                                    o[ch] = (uint8_t)res;
+                                }
+                            }
+                        }
+                    }
+                    fence_async_smem();
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        bulk_s2g(rimg + (size_t)(geo.oy + d0) * P.RW * 3, s_out, (uint32_t)rows * P.RW * 3);
+                        bulk_commit();
+                    }
+                }
+            }
+            __syncthreads();  // every reader of s_src is done
+            if (threadIdx.x == 0 && t + 1 < ntiles)
+                issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
+        }
+        if (want_stats) {
+            if (counters) {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) {
+                    const uint32_t v = __reduce_add_sync(0xffffffffu, (cacc[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+                    if (lane == 0 && v) atomicAdd(&s_cnt[k], v);
+                }
+            }
+            __syncthreads();
+            if (hist9)
+                for (int i = threadIdx.x; i < 9 * 256; i += MT) hist9[(size_t)img * 9 * 256 + i] = (int)s_hist[i];
+            if (hsv3)
+                for (int i = threadIdx.x; i < 3 * 256; i += MT) hsv3[(size_t)img * 3 * 256 + i] = (int)s_hist[9 * 256 + i];
+            if (counters && threadIdx.x < 16) counters[(size_t)img * 16 + threadIdx.x] = threadIdx.x < 14 ? (int)s_cnt[threadIdx.x] : 0;
+        }
+        if (threadIdx.x == 0) bulk_wait_read();  // s_out is reused as part of the phase-A/B union next image
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+}
+
+// ---------------------------------------------------------------- host side
+// hist.py:38-65 categories and :248-256 hue ranges as per-channel byte flags.  Field k (byte k%4 of word k/4):
+// 0 leaf (hist.py:188), 1..8 the categories, 9..13 the hue ranges.
+void build_cat_lut(uint32_t* lut /* [3][256][4] */) {
+    memset(lut, 0, 3 * 256 * 16);
+    for (int i = 0; i < 256; ++i) {
+        const int h = i, s = i, v = i;
+        const bool leaf_s = s > 10, leaf_v = v > 15 && v < 245;
+        bool fh[14], fs[14], fv[14];
+        fh[0] = true; fs[0] = leaf_s; fv[0] = leaf_v;
+        fh[1] = h >= 35 && h <= 85; fs[1] = s >= 40; fv[1] = v >= 30;
+        fh[2] = h >= 20 && h <= 40; fs[2] = s >= 25; fv[2] = v >= 30;
+        fh[3] = h >= 15 && h <= 35; fs[3] = s >= 50; fv[3] = v >= 50;
+        fh[4] = h <= 25 || h >= 160; fs[4] = s >= 30; fv[4] = v >= 20;
+        fh[5] = (h >= 160 && h <= 180) || h <= 10; fs[5] = s >= 40; fv[5] = v >= 30;
+        fh[6] = true; fs[6] = s >= 20; fv[6] = v <= 50;
+        fh[7] = true; fs[7] = s <= 30; fv[7] = v >= 200;
+        fh[8] = h >= 120 && h <= 160; fs[8] = s >= 20; fv[8] = true;
+        fh[9] = h >= 35 && h <= 85; fs[9] = true; fv[9] = true;
+        fh[10] = h >= 15 && h <= 35; fs[10] = true; fv[10] = true;
+        fh[11] = h <= 15 || h >= 160; fs[11] = true; fv[11] = true;
+        fh[12] = h >= 120 && h <= 160; fs[12] = true; fv[12] = true;
+        fh[13] = h > 85 && h < 120; fs[13] = true; fv[13] = true;
+        for (int k = 0; k < 14; ++k) {
+            const uint32_t bit = 1u << (8 * (k & 3));
+            if (fh[k]) lut[(0 * 256 + i) * 4 + (k >> 2)] |= bit;
+            if (fs[k] && leaf_s) lut[(1 * 256 + i) * 4 + (k >> 2)] |= bit;
+            if (fv[k] && leaf_v) lut[(2 * 256 + i) * 4 + (k >> 2)] |= bit;
+        }
+    }
+}
+
+uint4* g_cat_lut = nullptr;
+
+int ensure_cat_lut() {
+    if (g_cat_lut) return LFX_OK;
+    static uint32_t host[3 * 256 * 4];
+    build_cat_lut(host);
+    cudaError_t e = cudaMalloc(&g_cat_lut, sizeof(host));
+    if (e == cudaSuccess) e = cudaMemcpy(g_cat_lut, host, sizeof(host), cudaMemcpyHostToDevice);
+    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core: category LUT upload: %s", cudaGetErrorString(e));
+    return LFX_OK;
+}
+
+// Shared-memory plan of the fused kernel; false when this shape / config takes the general path.
+bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, const int32_t* taps, CoreParams* out, int* per_sm) {
+    if (W % 32 != 0 || W < 32 || H < 3 || (long long)H * W > 65536 || H > TR * TR) return false;
+    if (!cfg || cfg->strategy < 0 || cfg->strategy > 1) return false;
+    if ((RW * 3) % 16 != 0 || RW < W || RH < H || RW > 1024 || RH > 1024) return false;
+    if (taps[0] != taps[4] || taps[1] != taps[3]) return false;
+    for (int i = 0; i < 5; ++i)
+        if (taps[i] < 0 || taps[i] > 255) return false;
+    CoreParams& P = *out;
+    memset(&P, 0, sizeof(P));
+    MaskParams& M = P.M;
+    M.cfg = *cfg;
+    M.H = H; M.W = W; M.WPR = W / 32; M.NW = H * M.WPR;
+    M.lastmask = 0xFFFFFFFFu;
+    M.mode = 0;
+    M.rcap_glob = H * ((W + 1) / 2);
+    M.planes_in_smem = 1;
+    const int rb = W * 3;
+    M.stage_rows = max(1, min(H, STAGE_BYTES / rb));
+    M.fp_morph = make_ellipse(cfg->morph_kernel);
+    M.fp_brown = make_ellipse(cfg->brown_morph_kernel > 0 ? cfg->brown_morph_kernel : 3);
+    M.fp_search = make_ellipse(20);
+    M.search_is_e20 = is_ellipse20(M.fp_search) ? 1 : 0;
+    P.t0 = taps[0]; P.t1 = taps[1]; P.t2 = taps[2];
+    P.K01 = taps[0] | (taps[1] << 8); P.K23 = taps[2] | (taps[3] << 8); P.K4_ = taps[4];
+    P.K_0 = taps[0] << 8; P.K12 = taps[1] | (taps[2] << 8); P.K34 = taps[3] | (taps[4] << 8);
+    P.RH = RH; P.RW = RW;
+    P.need_lab_a = (cfg->strategy == 1 || cfg->use_lab_brown) ? 1 : 0;
+    auto al = [](size_t b) { return (int)((b + 127) & ~(size_t)127); };
+    int off = 0;
+    P.off_planes = off; off += al((size_t)M.NW * 4 * 3);
+    P.off_hsv = off; off += al(sizeof(HsvLut));
+    P.off_lab = off; off += al(sizeof(LabLut));
+    P.off_union = off;
+    // phase A
+    int a = off;
+    P.off_src = a; a += al((size_t)(TR + 4) * rb + 16);
+    P.off_v = a; a += al((size_t)3 * TR * (W + 4) * 2);
+    // phase B
+    int b = off;
+    P.off_t = b; b += al((size_t)M.NW * 4 * 3);
+    P.off_wbase = b; b += al((size_t)(M.NW + 1) * 4);
+    P.off_runs = b; b += al((size_t)RCAP_SMEM * 14);
+    P.off_stage = b; b += al((size_t)M.stage_rows * rb);
+    // phase C (off_src as in A)
+    int c3 = P.off_src + al((size_t)(TR + 4) * rb + 16);
+    P.off_out = c3; c3 += al((size_t)CHUNK * RW * 3);
+    P.off_hist = c3; c3 += al(12 * 256 * 4);
+    P.off_cat = c3; c3 += al(3 * 256 * 16);
+    P.off_xt = c3; c3 += al((size_t)RW * 8);
+    P.off_yt = c3; c3 += al((size_t)RH * 8);
+    P.smem_bytes = max(a, max(b, c3));
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2);
+    if (P.smem_bytes > 226 * 1024) return false;
+    *per_sm = max(1, min(2, (228 * 1024) / (P.smem_bytes + 1024 + 1536)));  // + static shared + per-block reserve
+    (void)B;
+    return true;
+}
+
+}  // namespace
+
+extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    const size_t general = lfx_make_mask_workspace(B, H, W);
+    auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t rcap = (size_t)H * ((W + 1) / 2);
+    const size_t fused = 256 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
+    return general > fused ? general : fused;
+}
+
+extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi,
+                                 int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H, int W, int RH, int RW,
+                                 double gaussian_sigma, const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes,
+                                 lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
+    LFX_REQUIRE(B > 0 && H > 0 && W > 0, LFX_ERR_ARG, "pipeline_core: bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+
+    // ---- fused kernel (one block per image) when the shape and config allow it
+    int32_t taps[31];
+    CoreParams P;
+    int per_sm = 1;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(roi) | reinterpret_cast<uintptr_t>(mask)) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(blur) % 4 == 0);
+    const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
+    const bool morph_ok = mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1);
+    if (aligned && morph_ok && lfx_gauss_taps(5, gaussian_sigma, taps) == LFX_OK && core_plan(B, H, W, RH, RW, cfg, taps, &P, &per_sm)) {
+        rc = ensure_cat_lut();
+        if (rc) return rc;
+        const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
+        const size_t need = 256 + (size_t)P.ws_per_block * grid;
+        LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
+        static int attr = 0;
+        if (P.smem_bytes > attr) {
+            cudaError_t e = cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_core, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.smem_bytes, cudaGetErrorString(e));
+            attr = P.smem_bytes;
+        }
+        cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
+        k_core<<<grid, MT, P.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                              (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+        return lfx_check_launch("pipeline_core(fused)");
+    }
+
+    // ---- general path: the stand-alone kernels back to back
+    if (blur) {
+        rc = lfx_gauss_u8(src, blur, B, H, W, 3, 5, gaussian_sigma, stream);
+        if (rc) return rc;
+    }
+    rc = lfx_make_mask(src, nullptr, mask, info, B, H, W, cfg, workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    if (roi) {
+        rc = lfx_roi_letterbox(src, mask, info, roi, B, H, W, RH, RW, stream);
+        if (rc) return rc;
+    }
+    if (hist9 || hsv3 || counters) {
+        cudaError_t e = cudaSuccess;
+        if (hist9) e = cudaMemsetAsync(hist9, 0, (size_t)B * 9 * 256 * 4, st);
+        if (e == cudaSuccess && hsv3) e = cudaMemsetAsync(hsv3, 0, (size_t)B * 3 * 256 * 4, st);
+        if (e == cudaSuccess && counters) e = cudaMemsetAsync(counters, 0, (size_t)B * 16 * 4, st);
+        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
+        rc = lfx_color_stats(src, mask, hist9, hsv3, counters, B, H, W, stream);
+        if (rc) return rc;
+    }
+    return LFX_OK;
+}

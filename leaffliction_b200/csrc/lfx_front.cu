@@ -230,15 +230,15 @@ __device__ void keep_largest8(uint32_t* m, uint32_t* tmp, Ctx& c) {
 }
 
 __device__ void open_(uint32_t* m, uint32_t* t, const Footprint& fp, Ctx& c) {
-    morph<false>(m, t, fp, c);
+    morph_any<false>(m, t, fp, c);
     __syncthreads();
-    morph<true>(t, m, fp, c);
+    morph_any<true>(t, m, fp, c);
     __syncthreads();
 }
 __device__ void close_(uint32_t* m, uint32_t* t, const Footprint& fp, Ctx& c) {
-    morph<true>(m, t, fp, c);
+    morph_any<true>(m, t, fp, c);
     __syncthreads();
-    morph<false>(t, m, fp, c);
+    morph_any<false>(t, m, fp, c);
     __syncthreads();
 }
 
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
     __shared__ int s_mm[8];
 
     Ctx c;
-    c.H = P.H; c.W = P.W; c.WPR = P.WPR; c.NW = P.NW; c.lastmask = P.lastmask;
+    ctx_init_geometry(c, P.H, P.W, P.WPR, P.NW, P.lastmask);
     c.s_tmp = s_tmp; c.s_best = &s_best; c.s_bb = s_bb; c.s_hist = s_hist;
     c.rcap_glob = P.rcap_glob;
     c.rcap_smem = RCAP_SMEM;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
             for (int i = threadIdx.x; i < P.NW; i += MT) PL[1][i] |= (PL[2][i] & PL[3][i]);  // full background plane
             __syncthreads();
             canny(M.gray, 30, 100, false, PL[2], PL[3], PL[4], P, M, c);   // edges -> PL[4]
-            morph<true>(PL[4], PL[5], P.fp3, c);                             // dilated edges
+            morph_any<true>(PL[4], PL[5], P.fp3, c);                             // dilated edges
             __syncthreads();
             for (int i = threadIdx.x; i < P.NW; i += MT) PL[2][i] = (PL[0][i] | PL[5][i]) & ~PL[1][i] & valid_mask(c, i % P.WPR);
             __syncthreads();
@@ -458,12 +458,12 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
             for (int i = threadIdx.x; i < P.NW; i += MT) PL[1][i] &= PL[0][i];   // brown & leaf
             __syncthreads();
             close_(PL[1], PL[2], P.fp3, c);
-            morph<true>(PL[1], PL[2], P.fp3, c);
+            morph_any<true>(PL[1], PL[2], P.fp3, c);
             __syncthreads();
-            morph<true>(PL[2], PL[1], P.fp3, c);                              // PL[1] = brown_dilated
+            morph_any<true>(PL[2], PL[1], P.fp3, c);                              // PL[1] = brown_dilated
             __syncthreads();
             canny(M.gray, P.canny_lo, P.canny_hi, P.canny_l2 != 0, PL[2], PL[3], PL[4], P, M, c);
-            morph<true>(PL[4], PL[2], P.fp3, c);                              // PL[2] = edges_dilated
+            morph_any<true>(PL[4], PL[2], P.fp3, c);                              // PL[2] = edges_dilated
             if (threadIdx.x < 8) s_mm[threadIdx.x] = (threadIdx.x & 1) ? 0 : 0x7f800000;   // {min,max} x 3 (+inf / 0)
             __syncthreads();
             // gradient magnitude (Sobel BORDER_REFLECT_101, float32) -> F0, min/max

@@ -31,6 +31,7 @@ struct MaskParams {
     int rcap_glob;
     int stage_rows;
     int mode;  // 0 make_mask, 1 postprocess only
+    int search_is_e20;  // fp_search is the hard-coded 20x20 ellipse of dilate_ellipse20
     unsigned long long ws_per_block;
 };
 
@@ -57,9 +58,29 @@ struct Ctx {
     int* s_bb;                   // [8]
     int* s_hist;                 // [256]
     int status;
+    int wshift;          // log2(WPR) when WPR is a power of two, else -1
+    uint32_t* hp[6];     // scratch planes for dilate_ellipse20 (nullptr = use the generic morph)
 };
 
+// word index -> (row, word-in-row) without an integer division when WPR is a power of two
+__device__ __forceinline__ void split_index(const Ctx& c, int i, int& y, int& w) {
+    if (c.wshift >= 0) {
+        y = i >> c.wshift;
+        w = i & (c.WPR - 1);
+    } else {
+        y = i / c.WPR;
+        w = i - y * c.WPR;
+    }
+}
+
 __device__ __forceinline__ uint32_t valid_mask(const Ctx& c, int w) { return (w == c.WPR - 1) ? c.lastmask : 0xFFFFFFFFu; }
+
+__device__ __forceinline__ void ctx_init_geometry(Ctx& c, int H, int W, int WPR, int NW, uint32_t lastmask) {
+    c.H = H; c.W = W; c.WPR = WPR; c.NW = NW; c.lastmask = lastmask;
+    c.wshift = ((WPR & (WPR - 1)) == 0) ? (31 - __clz(WPR)) : -1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c.hp[k] = nullptr;
+}
 
 // ---------------------------------------------------------------- block primitives
 __device__ int block_exscan(int v, int* s_tmp, int& total) {
@@ -101,7 +122,8 @@ __device__ __forceinline__ void plane_copy(uint32_t* d, const uint32_t* s, const
 template <bool DIL>
 __device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
     for (int i = threadIdx.x; i < c.NW; i += MT) {
-        const int y = i / c.WPR, w = i - y * c.WPR;
+        int y, w;
+        split_index(c, i, y, w);
         uint32_t acc = DIL ? 0u : 0xFFFFFFFFu;
         for (int k = 0; k < fp.n; ++k) {
             const int yy = y + fp.r[k].dy;
@@ -125,6 +147,111 @@ __device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, co
         }
         out[i] = acc & valid_mask(c, w);
     }
+}
+
+// 3x3 MORPH_ELLIPSE = cross (010/111/010): the footprint of every open/close on the default path
+// (morph_kernel = brown_morph_kernel = 3, config.yaml).  5 words in, 2 funnel shifts.
+template <bool DIL>
+__device__ void morph_cross3(const uint32_t* in, uint32_t* out, const Ctx& c) {
+    const uint32_t oob = DIL ? 0u : 0xFFFFFFFFu;
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        int y, w;
+        split_index(c, i, y, w);
+        const bool last = (w == c.WPR - 1);
+        uint32_t cur = in[i];
+        uint32_t prev = (w > 0) ? in[i - 1] : oob;
+        uint32_t next = oob;
+        if (!last) {
+            next = in[i + 1];
+            if (!DIL && w + 1 == c.WPR - 1) next |= ~c.lastmask;
+        }
+        if (!DIL && last) cur |= ~c.lastmask;
+        uint32_t up = (y > 0) ? in[i - c.WPR] : oob;
+        uint32_t dn = (y < c.H - 1) ? in[i + c.WPR] : oob;
+        if (!DIL && last) {
+            up |= ~c.lastmask;
+            dn |= ~c.lastmask;
+        }
+        const uint32_t l = __funnelshift_r(prev, cur, 31);  // bit x = source bit x-1
+        const uint32_t r = __funnelshift_r(cur, next, 1);   // bit x = source bit x+1
+        const uint32_t v = DIL ? (cur | l | r | up | dn) : (cur & l & r & up & dn);
+        out[i] = v & valid_mask(c, w);
+    }
+}
+
+__device__ __forceinline__ bool is_cross3(const Footprint& fp) {
+    return fp.n == 3 && fp.r[0].dy == -1 && fp.r[0].o1 == 0 && fp.r[0].o2 == 0 && fp.r[1].dy == 0 && fp.r[1].o1 == -1 &&
+           fp.r[1].o2 == 1 && fp.r[2].dy == 1 && fp.r[2].o1 == 0 && fp.r[2].o2 == 0;
+}
+
+template <bool DIL>
+__device__ __forceinline__ void morph_any(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
+    if (is_cross3(fp))
+        morph_cross3<DIL>(in, out, c);
+    else
+        morph<DIL>(in, out, fp, c);
+}
+
+// Dilation by cv2.getStructuringElement(MORPH_ELLIPSE, (20, 20)) (mask.py:341, anchor (10,10)):
+// row spans are nested -- dy -10: [0,0]; +-9: [-4,4]; +-8: [-6,6]; +-7: [-7,7]; +-6: [-8,8]; +-5,+-4: [-9,9];
+// -3..3: [-10,9] -- so the six wider horizontal dilations are built incrementally from one
+// (prev,cur,next) word triple into six scratch planes (20 funnel shifts per word instead of 325),
+// then each output word ORs 20 plane rows.  Needs c.hp[0..5]; ends with a block barrier.
+__device__ void dilate_ellipse20(const uint32_t* in, uint32_t* out, const Ctx& c) {
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        int y, w;
+        split_index(c, i, y, w);
+        const uint32_t cur = in[i];
+        const uint32_t prev = (w > 0) ? in[i - 1] : 0u;
+        const uint32_t next = (w + 1 < c.WPR) ? in[i + 1] : 0u;
+#define LFX_SL(o) __funnelshift_r(cur, next, (o))        /* bit x = source bit x+o */
+#define LFX_SR(o) __funnelshift_r(prev, cur, 32 - (o))   /* bit x = source bit x-o */
+        uint32_t h = cur | LFX_SL(1) | LFX_SL(2) | LFX_SL(3) | LFX_SL(4) | LFX_SR(1) | LFX_SR(2) | LFX_SR(3) | LFX_SR(4);
+        c.hp[0][i] = h;  // [-4,4]
+        h |= LFX_SL(5) | LFX_SL(6) | LFX_SR(5) | LFX_SR(6);
+        c.hp[1][i] = h;  // [-6,6]
+        h |= LFX_SL(7) | LFX_SR(7);
+        c.hp[2][i] = h;  // [-7,7]
+        h |= LFX_SL(8) | LFX_SR(8);
+        c.hp[3][i] = h;  // [-8,8]
+        h |= LFX_SL(9) | LFX_SR(9);
+        c.hp[4][i] = h;  // [-9,9]
+        h |= LFX_SR(10);
+        c.hp[5][i] = h;  // [-10,9]
+#undef LFX_SL
+#undef LFX_SR
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        int y, w;
+        split_index(c, i, y, w);
+        const int wp = c.WPR;
+        uint32_t acc = 0;
+        auto row = [&](const uint32_t* p, int dy) {
+            const int yy = y + dy;
+            if (yy >= 0 && yy < c.H) acc |= p[i + dy * wp];
+        };
+        row(in, -10);
+        row(c.hp[0], -9); row(c.hp[0], 9);
+        row(c.hp[1], -8); row(c.hp[1], 8);
+        row(c.hp[2], -7); row(c.hp[2], 7);
+        row(c.hp[3], -6); row(c.hp[3], 6);
+        row(c.hp[4], -5); row(c.hp[4], 5); row(c.hp[4], -4); row(c.hp[4], 4);
+#pragma unroll
+        for (int dy = -3; dy <= 3; ++dy) row(c.hp[5], dy);
+        out[i] = acc & valid_mask(c, w);
+    }
+    __syncthreads();
+}
+
+// true when fp is exactly the 20x20 ellipse dilate_ellipse20 hard-codes
+static inline bool is_ellipse20(const Footprint& fp) {
+    static const int8_t o1[20] = {0, -4, -6, -7, -8, -9, -9, -10, -10, -10, -10, -10, -10, -10, -9, -9, -8, -7, -6, -4};
+    static const int8_t o2[20] = {0, 4, 6, 7, 8, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 9, 8, 7, 6, 4};
+    if (fp.n != 20) return false;
+    for (int k = 0; k < 20; ++k)
+        if (fp.r[k].dy != k - 10 || fp.r[k].o1 != o1[k] || fp.r[k].o2 != o2[k]) return false;
+    return true;
 }
 
 // ---------------------------------------------------------------- runs + union-find
@@ -182,7 +309,8 @@ __device__ void ccl(const uint32_t* m, Ctx& c) {
     __syncthreads();
     int* parent = c.parent;
     for (int i = threadIdx.x; i < c.NW; i += MT) {
-        const int y = i / c.WPR, w = i - y * c.WPR;
+        int y, w;
+        split_index(c, i, y, w);
         uint32_t st = starts_of(m, i, w);
         int id = c.wbase[i];
         const uint32_t word = m[i];

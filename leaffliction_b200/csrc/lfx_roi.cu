@@ -1,7 +1,6 @@
 // apply_roi_filter canvas (srcs/transform/filters/roi.py:20-46): crop the contour's bounding box
 // from the white-masked image, letterbox with cv2.resize(INTER_AREA) (an upscale here: 2-tap
 // fixed-point bilinear with area-mode offsets, OpenCV resize.cpp) into a zero canvas.
-// Also hosts lfx_pipeline_core, the fused submission of the core transform profile.
 #include "lfx_common.cuh"
 
 namespace {
@@ -145,37 +144,4 @@ extern "C" int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const 
     dim3 grid(lfx_div_up(RH, ROI_ROWS), B);
     k_roi<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, mask, info, dst, H, W, RH, RW);
     return lfx_check_launch("roi_letterbox");
-}
-
-extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) { return lfx_make_mask_workspace(B, H, W); }
-
-extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi,
-                                 int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H, int W, int RH, int RW,
-                                 double gaussian_sigma, const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes,
-                                 lfx_stream_t stream) {
-    LFX_REQUIRE_READY();
-    if (B == 0) return LFX_OK;
-    LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
-    cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (blur) {
-        rc = lfx_gauss_u8(src, blur, B, H, W, 3, 5, gaussian_sigma, stream);
-        if (rc) return rc;
-    }
-    rc = lfx_make_mask(src, nullptr, mask, info, B, H, W, cfg, workspace, workspace_bytes, stream);
-    if (rc) return rc;
-    if (roi) {
-        rc = lfx_roi_letterbox(src, mask, info, roi, B, H, W, RH, RW, stream);
-        if (rc) return rc;
-    }
-    if (hist9 || hsv3 || counters) {
-        cudaError_t e = cudaSuccess;
-        if (hist9) e = cudaMemsetAsync(hist9, 0, (size_t)B * 9 * 256 * 4, st);
-        if (e == cudaSuccess && hsv3) e = cudaMemsetAsync(hsv3, 0, (size_t)B * 3 * 256 * 4, st);
-        if (e == cudaSuccess && counters) e = cudaMemsetAsync(counters, 0, (size_t)B * 16 * 4, st);
-        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
-        rc = lfx_color_stats(src, mask, hist9, hsv3, counters, B, H, W, stream);
-        if (rc) return rc;
-    }
-    return LFX_OK;
 }

@@ -290,6 +290,75 @@ def test_pipeline_core(dev):
         assert np.array_equal(out.counters.cpu().numpy()[i, :14], sm.hist_counters(masked))
 
 
+def _check_core(out, imgs, scfg, roi_size):
+    for i in range(len(imgs)):
+        m, einfo = sm.make_mask(imgs[i], scfg)
+        masked = sm.apply_mask(imgs[i], m, "white")
+        assert np.array_equal(out.blur[i].cpu().numpy(), sf.gaussian_blur_u8(imgs[i], 5, scfg.gaussian_sigma)), f"blur {i}"
+        assert np.array_equal(out.mask[i].cpu().numpy(), m), f"mask {i}"
+        if einfo is None:
+            assert int(out.info[i, 0]) == 0, f"found {i}"
+            assert int(out.roi[i].sum()) == 0, f"roi (no contour) {i}"
+        else:
+            assert tuple(out.info[i, 1:5].cpu().numpy()) == einfo["bbox"], f"bbox {i}"
+            assert np.array_equal(out.roi[i].cpu().numpy(), sm.roi_letterbox(masked, einfo["bbox"], roi_size)), f"roi {i}"
+        assert np.array_equal(out.hist9[i].cpu().numpy(), sm.hist9(imgs[i], m)), f"hist9 {i}"
+        assert np.array_equal(out.hsv3[i].cpu().numpy(), sm.hsv_hist_leaf(masked)), f"hsv3 {i}"
+        assert np.array_equal(out.counters[i, :14].cpu().numpy(), sm.hist_counters(masked)), f"counters {i}"
+
+
+# fused kernel (W % 32 == 0, H*W <= 65536) and the general path (other shapes) through the same entry point
+@pytest.mark.parametrize("hw,roi", [((256, 256), (256, 256)), ((64, 64), (64, 64)), ((96, 64), (128, 64)), ((40, 32), (48, 48)),
+                                    ((35, 128), (64, 128)), ((128, 512), (128, 512)), ((61, 97), (64, 100))])
+@pytest.mark.parametrize("strategy", ["hsv_h", "lab"])
+def test_pipeline_core_shapes(dev, hw, roi, strategy):
+    imgs = synth.leaf_batch(5, hw[0], hw[1], seed=77)
+    cfg = ops.mask_cfg(strategy, fill_size=60)
+    out = ops.pipeline_core(up(imgs, dev), cfg, 1.5, roi)
+    _check_core(out, imgs, sm.Cfg(mask_strategy=strategy, fill_size=60, roi_size=roi), roi)
+
+
+def test_pipeline_core_adversarial(dev):
+    adv = synth.adversarial_images(64, 64)
+    imgs = np.stack(list(adv.values()))
+    cfg = ops.mask_cfg("hsv_h", fill_size=20)
+    out = ops.pipeline_core(up(imgs, dev), cfg, 1.5, (64, 64))
+    _check_core(out, imgs, sm.Cfg(mask_strategy="hsv_h", fill_size=20, roi_size=(64, 64)), (64, 64))
+
+
+@pytest.mark.parametrize("kw", [dict(extend_brown=False), dict(use_lab_brown=True), dict(gaussian_sigma=0.8),
+                                dict(brown_hue_range=(5, 40), brown_min_area_px=5), dict(hsv_channel_for_mask="v")])
+def test_pipeline_core_configs(dev, kw):
+    imgs = np.concatenate([leaf_set(3), np.stack([synth.adversarial_images(256, 256)[k] for k in ("black", "salt", "frame")])])
+    sigma = kw.pop("gaussian_sigma", 1.5)
+    extend = kw.pop("extend_brown", True)
+    cfg = ops.mask_cfg("hsv_h", extend_brown=extend, **kw)
+    out = ops.pipeline_core(up(imgs, dev), cfg, sigma, (256, 256))
+    scfg = sm.Cfg(mask_strategy="hsv_h", gaussian_sigma=sigma, **kw)
+    if extend:
+        _check_core(out, imgs, scfg, (256, 256))
+    else:  # the spec always extends; compare the pre-extension stage
+        for i in range(len(imgs)):
+            raw = sm.raw_candidate(imgs[i], scfg)
+            m, einfo = sm.postprocess(raw, scfg)
+            if einfo is None or einfo["area2"] <= 2:
+                m, einfo = sm.postprocess(sm.mask_hsv_otsu(imgs[i], scfg.hsv_channel_for_mask, "light"), scfg)
+            assert np.array_equal(out.mask[i].cpu().numpy(), m)
+
+
+def test_pipeline_core_many_images(dev):
+    """More images than resident thread blocks (dynamic image queue), each checked against the batch-1 result."""
+    base = synth.leaf_batch(24, 256, 256, seed=5)
+    imgs = np.concatenate([base] * 30)          # 720 images > 296 resident blocks
+    out = ops.pipeline_core(up(imgs, dev), ops.mask_cfg("hsv_h"), 1.5, (256, 256))
+    ref = ops.pipeline_core(up(base, dev), ops.mask_cfg("hsv_h"), 1.5, (256, 256))
+    for name in ("blur", "mask", "roi", "hist9", "hsv3", "counters"):
+        a = getattr(out, name).view(30, 24, *getattr(ref, name).shape[1:])
+        assert bool((a == getattr(ref, name)[None]).all()), name
+    assert bool((out.info.view(30, 24, 8)[:, :, :7] == ref.info[None, :, :7]).all())
+    _check_core(ref, base[:4], sm.Cfg(mask_strategy="hsv_h"), (256, 256))
+
+
 def test_empty_batch(dev):
     x = torch.empty((0, 64, 64, 3), dtype=torch.uint8, device=dev)
     assert ops.cvt_color(x, "hsv").shape == (0, 64, 64, 3)
