@@ -15,6 +15,8 @@
 // Reference: srcs/transform/filters/blur.py:72 (GaussianBlur 5x5), mask.py:548-582 (make_mask),
 // roi.py:20-46, hist.py:22-67,188,248-256, utils/mask_utils.py:10-83.  Arithmetic identical to the
 // stand-alone kernels (lfx_gauss.cu, lfx_mask.cu, lfx_roi.cu, lfx_color.cu), which remain the general path.
+#include <type_traits>
+
 #include "lfx_maskops.cuh"
 
 namespace {
@@ -23,10 +25,41 @@ constexpr int TR = 32;     // image rows per staged tile
 constexpr int CHUNK = 16;  // ROI canvas rows per bulk store
 constexpr int NWARPS = MT / 32;
 
-struct Tap {
-    int s;       // source index
-    short a, b;  // weights (x2048) for s and s+1
+// Shared-memory byte offsets.  Fixed part: raw / brown / result planes and the colour LUTs; the rest is a
+// union over the three phases.  constexpr so that the 256x256 instantiation folds every address.
+struct Lay {
+    int off_planes, off_hsv, off_lab;
+    int off_src, off_v;                              // phase A (inside the union)
+    int off_t, off_wbase, off_runs, off_stage;       // phase B
+    int off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A)
+    int smem_bytes;
 };
+__host__ __device__ constexpr int lay_al(long long b) { return (int)((b + 127) & ~127ll); }
+__host__ __device__ constexpr Lay make_lay(int H, int W, int RH, int RW) {
+    Lay L{};
+    const int NW = H * (W / 32), rb = W * 3;
+    const int stage_rows = (STAGE_BYTES / rb) < 1 ? 1 : ((STAGE_BYTES / rb) > H ? H : (STAGE_BYTES / rb));
+    int off = 0;
+    L.off_planes = off; off += lay_al((long long)NW * 4 * 3);
+    L.off_hsv = off; off += lay_al(sizeof(HsvLut));
+    L.off_lab = off; off += lay_al(sizeof(LabLut));
+    int a = off;
+    L.off_src = a; a += lay_al((long long)(TR + 4) * rb + 16);
+    L.off_v = a; a += lay_al((long long)3 * TR * (W + 4) * 2);
+    int b = off;
+    L.off_t = b; b += lay_al((long long)NW * 4 * 3);
+    L.off_wbase = b; b += lay_al((long long)(NW + 1) * 4);
+    L.off_runs = b; b += lay_al((long long)RCAP_SMEM * 14);
+    L.off_stage = b; b += lay_al((long long)stage_rows * rb);
+    int c3 = L.off_src + lay_al((long long)(TR + 4) * rb + 16);
+    L.off_out = c3; c3 += lay_al((long long)CHUNK * RW * 3);
+    L.off_hist = c3; c3 += lay_al(12 * 256 * 4);
+    L.off_cat = c3; c3 += lay_al(3 * 256 * 16);
+    L.off_xt = c3; c3 += lay_al((long long)RW * 8);
+    L.off_yt = c3; c3 += lay_al((long long)RH * 8);
+    L.smem_bytes = a > b ? (a > c3 ? a : c3) : (b > c3 ? b : c3);
+    return L;
+}
 
 struct CoreParams {
     MaskParams M;
@@ -34,12 +67,7 @@ struct CoreParams {
     int t0, t1, t2;                         // symmetric vertical taps (t0 = taps[0] = taps[4], ...)
     int RH, RW;
     int need_lab_a;                         // Lab needed in phase A (lab strategy / lab brown)
-    // shared-memory byte offsets
-    int off_planes, off_hsv, off_lab, off_union;
-    int off_src, off_v;                              // phase A (inside the union)
-    int off_t, off_wbase, off_runs, off_stage;       // phase B
-    int off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A)
-    int smem_bytes;
+    Lay lay;
     unsigned long long ws_per_block;
 };
 
@@ -175,7 +203,8 @@ __device__ __forceinline__ void hpass_item(const uint16_t* s_v, uint8_t* brow, i
 
 // ---------------------------------------------------------------- phase C helpers
 // cv::resize area-mode 2-tap coefficients for destination index d (src -> dst upscale); lfx_roi.cu.
-__device__ __forceinline__ Tap area_tap2(int d, int src, int dst) {
+// Packed as {source index, a | b << 16} (weights x2048 for s and s+1; a + b in [2047, 2049]).
+__device__ __forceinline__ int2 area_tap2(int d, int src, int dst) {
     const double inv = __ddiv_rn((double)dst, (double)src);
     const double scale = __ddiv_rn(1.0, inv);
     int sx = (int)floor(__dmul_rn((double)d, scale));
@@ -189,11 +218,9 @@ __device__ __forceinline__ Tap area_tap2(int d, int src, int dst) {
         fx = 0.f;
         sx = src - 1;
     }
-    Tap t;
-    t.s = sx;
-    t.a = (short)__float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f));
-    t.b = (short)__float2int_rn(__fmul_rn(fx, 2048.f));
-    return t;
+    const int a = __float2int_rn(__fmul_rn(__fadd_rn(1.f, -fx), 2048.f));
+    const int b = __float2int_rn(__fmul_rn(fx, 2048.f));
+    return make_int2(sx, a | (b << 16));
 }
 
 struct Geo {
@@ -201,6 +228,9 @@ struct Geo {
 };
 
 // ---------------------------------------------------------------- the kernel
+// S = true: compile-time 256x256 image, 256x256 canvas (PlantVillage, BASELINE configs 1-3); S = false: any
+// W % 32 == 0, H*W <= 65536 shape with run-time geometry.
+template <bool S>
 __global__ void __launch_bounds__(MT, 2)
     k_core(const uint8_t* __restrict__ src, uint8_t* __restrict__ blur, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
            uint8_t* __restrict__ roi, int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3, int32_t* __restrict__ counters,
@@ -216,31 +246,38 @@ __global__ void __launch_bounds__(MT, 2)
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ int s_next;
     __shared__ Geo s_geo;
-    __shared__ int s_dlo[TR + 2];  // first canvas row of each source tile (H <= TR*(TR+1) rows is plenty: H*W <= 65536, W >= 32)
+    __shared__ int s_dlo[TR + 2];  // first canvas row of each source tile (at most TR tiles: H <= TR*TR)
     __shared__ uint32_t s_cnt[16];
 
     const MaskParams& M = P.M;
-    const int H = M.H, W = M.W, WPR = M.WPR, NW = M.NW, RB = W * 3, VP = W + 4, G = W >> 2;
+    const int H = S ? 256 : M.H, W = S ? 256 : M.W, RH = S ? 256 : P.RH, RW = S ? 256 : P.RW;
+    const int WPR = W >> 5, NW = H * WPR, RB = W * 3, VP = W + 4, G = W >> 2;
+    const Lay L = S ? make_lay(256, 256, 256, 256) : P.lay;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ntiles = (H + TR - 1) / TR;
 
-    Ctx c;
-    ctx_init_geometry(c, H, W, WPR, NW, M.lastmask);
+    using Geom = typename std::conditional<S, StaticGeom<256, 256>, DynGeom>::type;
+    CtxT<Geom> c;
+    if constexpr (!S) {
+        ctx_init_geometry(c, H, W, WPR, NW, M.lastmask);
+    } else {
+        ctx_clear_hp(c);
+    }
     c.s_tmp = s_tmp; c.s_best = &s_best; c.s_bb = s_bb; c.s_hist = s_hist256;
     c.rcap_glob = M.rcap_glob;
     c.rcap_smem = RCAP_SMEM;
-    uint32_t* P0 = reinterpret_cast<uint32_t*>(sm + P.off_planes);
+    uint32_t* P0 = reinterpret_cast<uint32_t*>(sm + L.off_planes);
     uint32_t* PB = P0 + NW;
     uint32_t* PR = PB + NW;
-    uint32_t* T1 = reinterpret_cast<uint32_t*>(sm + P.off_t);
+    uint32_t* T1 = reinterpret_cast<uint32_t*>(sm + L.off_t);
     uint32_t* T2 = T1 + NW;
     uint32_t* T3 = T2 + NW;
     c.plane[0] = P0; c.plane[1] = PB; c.plane[2] = PR; c.plane[3] = T1; c.plane[4] = T2; c.plane[5] = T3;
-    c.wbase = reinterpret_cast<int*>(sm + P.off_wbase);
-    c.sm_parent = reinterpret_cast<int*>(sm + P.off_runs);
-    c.sm_geom = reinterpret_cast<uint32_t*>(sm + P.off_runs + RCAP_SMEM * 4);
-    c.sm_acc = reinterpret_cast<int*>(sm + P.off_runs + RCAP_SMEM * 8);
-    c.sm_ry = reinterpret_cast<uint16_t*>(sm + P.off_runs + RCAP_SMEM * 12);
+    c.wbase = reinterpret_cast<int*>(sm + L.off_wbase);
+    c.sm_parent = reinterpret_cast<int*>(sm + L.off_runs);
+    c.sm_geom = reinterpret_cast<uint32_t*>(sm + L.off_runs + RCAP_SMEM * 4);
+    c.sm_acc = reinterpret_cast<int*>(sm + L.off_runs + RCAP_SMEM * 8);
+    c.sm_ry = reinterpret_cast<uint16_t*>(sm + L.off_runs + RCAP_SMEM * 12);
     {
         uint8_t* gp = ws + 256 + (size_t)blockIdx.x * P.ws_per_block;
         auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
@@ -253,16 +290,16 @@ __global__ void __launch_bounds__(MT, 2)
         c.hp[0] = P0; c.hp[1] = T3; c.hp[2] = reinterpret_cast<uint32_t*>(c.wbase);
         for (int k = 0; k < 3; ++k) c.hp[3 + k] = reinterpret_cast<uint32_t*>(c.sm_parent) + (size_t)k * NW;
     }
-    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(sm + P.off_hsv);
-    LabLut* s_lab = reinterpret_cast<LabLut*>(sm + P.off_lab);
-    uint8_t* s_src = sm + P.off_src;
-    uint16_t* s_v = reinterpret_cast<uint16_t*>(sm + P.off_v);
-    uint8_t* s_stage = sm + P.off_stage;
-    uint8_t* s_out = sm + P.off_out;
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(sm + P.off_hist);
-    const uint4* s_cat = reinterpret_cast<const uint4*>(sm + P.off_cat);
-    Tap* s_xt = reinterpret_cast<Tap*>(sm + P.off_xt);
-    Tap* s_yt = reinterpret_cast<Tap*>(sm + P.off_yt);
+    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(sm + L.off_hsv);
+    LabLut* s_lab = reinterpret_cast<LabLut*>(sm + L.off_lab);
+    uint8_t* s_src = sm + L.off_src;
+    uint16_t* s_v = reinterpret_cast<uint16_t*>(sm + L.off_v);
+    uint8_t* s_stage = sm + L.off_stage;
+    uint8_t* s_out = sm + L.off_out;
+    uint32_t* s_hist = reinterpret_cast<uint32_t*>(sm + L.off_hist);
+    const uint4* s_cat = reinterpret_cast<const uint4*>(sm + L.off_cat);
+    int2* s_xt = reinterpret_cast<int2*>(sm + L.off_xt);
+    int2* s_yt = reinterpret_cast<int2*>(sm + L.off_yt);
 
     load_hsv_lut(s_hsv, tab);
     load_lab_lut(s_lab, tab);
@@ -299,27 +336,29 @@ __global__ void __launch_bounds__(MT, 2)
             for (int item = wid; item < nr * WPR; item += NWARPS) {
                 int ry, w;
                 split_index(c, item, ry, w);
-                const uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
+                const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
                 const int r = px[0], g = px[1], b = px[2];
                 int h, s, v;
                 rgb2hsv(r, g, b, s_hsv, h, s, v);
                 bool b0, b1;
                 if (P.need_lab_a) {
-                    int L, A, Bv;
-                    rgb2lab(r, g, b, s_lab, L, A, Bv);
+                    int Ll, A, Bv;
+                    rgb2lab(r, g, b, s_lab, Ll, A, Bv);
                     b0 = (M.cfg.strategy == 1) ? ((A <= 135) && (Bv >= 115) && (Bv <= 170))
                                                : ((h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40));
                     b1 = M.cfg.use_lab_brown ? ((A >= M.cfg.lab_a_min) && (Bv >= M.cfg.lab_b_min))
                                              : ((h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) &&
                                                 (v <= M.cfg.brown_v_max));
                 } else {
-                    b0 = (h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40);  // mask.py:90
-                    b1 = (h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
+                    // unsigned range checks: (h - lo) <= (hi - lo)
+                    b0 = ((unsigned)(h - M.cfg.green_lo) <= (unsigned)(M.cfg.green_hi - M.cfg.green_lo)) && (s >= 40);  // mask.py:90
+                    b1 = ((unsigned)(h - M.cfg.brown_lo) <= (unsigned)(M.cfg.brown_hi - M.cfg.brown_lo)) &&
+                         (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
                 }
                 const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
                 const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
                 if (lane == 0) {
-                    const int idx = (y0 + ry) * WPR + w;
+                    const int idx = y0 * WPR + item;
                     P0[idx] = m0;
                     PB[idx] = m1;
                 }
@@ -328,10 +367,10 @@ __global__ void __launch_bounds__(MT, 2)
             if (threadIdx.x == 0 && t + 1 < ntiles)
                 issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
             if (blur) {
-                uint8_t* bimg = blur + (size_t)img * img_px * 3;
+                uint8_t* bimg = blur + (size_t)img * img_px * 3 + (size_t)y0 * RB;
                 for (int item = threadIdx.x; item < G * nr; item += MT) {
                     const int r = item / G, g = item - r * G;
-                    hpass_item(s_v, bimg + (size_t)(y0 + r) * RB, g, r, VP, P);
+                    hpass_item(s_v, bimg + r * RB, g, r, VP, P);
                 }
                 __syncthreads();
             }
@@ -340,7 +379,7 @@ __global__ void __launch_bounds__(MT, 2)
         // =========================================================== phase B
         c.status = 0;
         mask_finish(simg, s_stage, s_hsv, P0, PB, PR, T1, T2, T3, s_info, s_info2, M, c);
-        plane_to_bytes(PR, mask + (size_t)img * img_px, c);
+        plane_to_bytes16(PR, mask + (size_t)img * img_px, c);
         if (threadIdx.x < 8) {
             int v = s_info[threadIdx.x];
             if (threadIdx.x == 7) v = (c.status & 0xFF) | (v << 8);
@@ -358,11 +397,11 @@ __global__ void __launch_bounds__(MT, 2)
             gq.nw = gq.nh = gq.ox = gq.oy = 0;
             if (roi && gq.found && gq.bw > 0 && gq.bh > 0) {
                 // scale = min(W / max(w,1), H / max(h,1)); nw = max(int(w*scale),1)   (roi.py:35-36)
-                const double sc = fmin(__ddiv_rn((double)P.RW, (double)max(gq.bw, 1)), __ddiv_rn((double)P.RH, (double)max(gq.bh, 1)));
+                const double sc = fmin(__ddiv_rn((double)RW, (double)max(gq.bw, 1)), __ddiv_rn((double)RH, (double)max(gq.bh, 1)));
                 gq.nw = max((int)__dmul_rn((double)gq.bw, sc), 1);
                 gq.nh = max((int)__dmul_rn((double)gq.bh, sc), 1);
-                gq.ox = (P.RW - gq.nw) / 2;
-                gq.oy = (P.RH - gq.nh) / 2;
+                gq.ox = (RW - gq.nw) / 2;
+                gq.oy = (RH - gq.nh) / 2;
             } else {
                 gq.found = 0;
             }
@@ -370,24 +409,28 @@ __global__ void __launch_bounds__(MT, 2)
         }
         for (int i = threadIdx.x; i < 12 * 256; i += MT) s_hist[i] = 0;
         if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
-        for (int i = threadIdx.x; i < CHUNK * P.RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+        for (int i = threadIdx.x; i < CHUNK * RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();  // also: every phase-B reader of the union region is done
         const Geo geo = s_geo;
         if (threadIdx.x == 0)
-            issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, cat_lut, sm + P.off_cat, want_stats ? 3 * 256 * 16 : 0);
-        uint8_t* rimg = roi ? roi + (size_t)img * P.RH * P.RW * 3 : nullptr;
+            issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, cat_lut, sm + L.off_cat, want_stats ? 3 * 256 * 16 : 0);
+        uint8_t* rimg = roi ? roi + (size_t)img * RH * RW * 3 : nullptr;
         if (roi) {
-            for (int i = threadIdx.x; i < geo.nw; i += MT) s_xt[i] = area_tap2(i, geo.bw, geo.nw);
+            for (int i = threadIdx.x; i < geo.nw; i += MT) {
+                int2 t2 = area_tap2(i, geo.bw, geo.nw);
+                t2.x = (geo.bx + t2.x) * 3;  // byte offset of the left source pixel inside a staged row
+                s_xt[i] = t2;
+            }
             for (int i = threadIdx.x; i < geo.nh; i += MT) s_yt[i] = area_tap2(i, geo.bh, geo.nh);
             // letterbox bands above / below the resized box (the whole canvas when nothing was found)
             if (threadIdx.x == 0) {
                 fence_async_smem();
-                const int top = geo.found ? geo.oy : P.RH;
+                const int top = geo.found ? geo.oy : RH;
                 for (int r0 = 0; r0 < top; r0 += CHUNK)
-                    bulk_s2g(rimg + (size_t)r0 * P.RW * 3, s_out, (uint32_t)min(CHUNK, top - r0) * P.RW * 3);
+                    bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, top - r0) * RW * 3);
                 if (geo.found)
-                    for (int r0 = geo.oy + geo.nh; r0 < P.RH; r0 += CHUNK)
-                        bulk_s2g(rimg + (size_t)r0 * P.RW * 3, s_out, (uint32_t)min(CHUNK, P.RH - r0) * P.RW * 3);
+                    for (int r0 = geo.oy + geo.nh; r0 < RH; r0 += CHUNK)
+                        bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, RH - r0) * RW * 3);
                 bulk_commit();
             }
             __syncthreads();
@@ -397,7 +440,7 @@ __global__ void __launch_bounds__(MT, 2)
                 const int ylim = threadIdx.x * TR;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (geo.by + s_yt[mid].s >= ylim) hi = mid; else lo = mid + 1;
+                    if (geo.by + s_yt[mid].x >= ylim) hi = mid; else lo = mid + 1;
                 }
                 s_dlo[threadIdx.x] = lo;
             }
@@ -410,23 +453,23 @@ __global__ void __launch_bounds__(MT, 2)
             __syncthreads();  // s_dlo / taps visible (t == 0)
             if (want_stats) {
                 for (int item = wid; item < nr * WPR; item += NWARPS) {
-                    int ry, w;
-                    split_index(c, item, ry, w);
-                    const uint32_t m = PR[(y0 + ry) * WPR + w];
+                    const uint32_t m = PR[y0 * WPR + item];
                     if (m == 0u) continue;
                     if ((m >> lane) & 1u) {
-                        const uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
+                        int ry, w;
+                        split_index(c, item, ry, w);
+                        const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
                         const int r = px[0], g = px[1], b = px[2];
-                        int h, s, v, L, A, Bv;
+                        int h, s, v, Ll, A, Bv;
                         rgb2hsv(r, g, b, s_hsv, h, s, v);
-                        rgb2lab(r, g, b, s_lab, L, A, Bv);
+                        rgb2lab(r, g, b, s_lab, Ll, A, Bv);
                         atomicAdd(&s_hist[0 * 256 + r], 1u);
                         atomicAdd(&s_hist[1 * 256 + g], 1u);
                         atomicAdd(&s_hist[2 * 256 + b], 1u);
                         atomicAdd(&s_hist[3 * 256 + h], 1u);
                         atomicAdd(&s_hist[4 * 256 + s], 1u);
                         atomicAdd(&s_hist[5 * 256 + v], 1u);
-                        atomicAdd(&s_hist[6 * 256 + L], 1u);
+                        atomicAdd(&s_hist[6 * 256 + Ll], 1u);
                         atomicAdd(&s_hist[7 * 256 + A], 1u);
                         atomicAdd(&s_hist[8 * 256 + Bv], 1u);
                         // leaf mask + 8 categories + 5 hue ranges (hist.py:188,38-65,248-256): per-channel LUTs of
@@ -447,16 +490,21 @@ __global__ void __launch_bounds__(MT, 2)
             }
             if (roi && geo.found) {
                 __syncthreads();
-                // apply_mask(rgb, mask, "white") in place on the staged rows y0 .. y0+nr (Transformation.py:451)
-                const int mrows = min(nr + 1, H - y0);
-                for (int item = wid; item < mrows * WPR; item += NWARPS) {
-                    int ry, w;
-                    split_index(c, item, ry, w);
-                    const uint32_t m = PR[(y0 + ry) * WPR + w];
-                    if (m == 0xFFFFFFFFu) continue;
-                    if (!((m >> lane) & 1u)) {
-                        uint8_t* px = s_src + (size_t)(ry + 2) * RB + (w * 32 + lane) * 3;
-                        px[0] = 255; px[1] = 255; px[2] = 255;
+                // apply_mask(rgb, mask, "white") in place (Transformation.py:451) -- only the bounding box is ever
+                // sampled: rows by .. by+bh-1 of this tile (+ the next row as lower tap), words covering bx .. bx+bw-1
+                {
+                    const int ra = max(y0, geo.by), rb2 = min(min(y0 + nr + 1, H), geo.by + geo.bh);
+                    const int wa = geo.bx >> 5, nwd = ((geo.bx + geo.bw - 1) >> 5) - wa + 1;
+                    const int nitems = max(0, rb2 - ra) * nwd;
+                    for (int item = wid; item < nitems; item += NWARPS) {
+                        const int rr = item / nwd, w = wa + (item - rr * nwd);
+                        const int y = ra + rr;
+                        const uint32_t m = PR[y * WPR + w];
+                        if (m == 0xFFFFFFFFu) continue;
+                        if (!((m >> lane) & 1u)) {
+                            uint8_t* px = s_src + ((y - y0 + 2) * RB + (w * 32 + lane) * 3);
+                            px[0] = 255; px[1] = 255; px[2] = 255;
+                        }
                     }
                 }
                 __syncthreads();
@@ -464,51 +512,52 @@ __global__ void __launch_bounds__(MT, 2)
                 const int cols = min(geo.nw, MT);
                 const int strips = max(1, MT / cols);
                 const int strip = threadIdx.x / cols, col0 = threadIdx.x - strip * cols;
+                const uint8_t* tile0 = s_src + (geo.by - y0 + 2) * RB;  // staged row of source row `by`
                 for (int d0 = dA; d0 < dB; d0 += CHUNK) {
                     const int rows = min(CHUNK, dB - d0);
                     if (threadIdx.x == 0) bulk_wait_read();  // the previous store has drained s_out
                     __syncthreads();
-                    if (geo.nw < P.RW) {
-                        for (int i = threadIdx.x; i < rows * P.RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
+                    if (geo.nw < RW) {
+                        for (int i = threadIdx.x; i < rows * RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
                         __syncthreads();
                     }
                     if (strip < strips) {
                         const int per = (rows + strips - 1) / strips;
                         const int da = d0 + strip * per, db = min(d0 + rows, da + per);
                         for (int cx = col0; cx < geo.nw; cx += cols) {
-                            const Tap tx = s_xt[cx];
-                            const uint8_t* colp = s_src + (geo.bx + tx.s) * 3;
-                            int prev_s = -4, h0[3] = {0, 0, 0}, h1[3] = {0, 0, 0};
-                            for (int d = da; d < db; ++d) {
-                                const Tap ty = s_yt[d];
-                                const uint8_t* p = colp + (size_t)(geo.by + ty.s - y0 + 2) * RB;
-                                if (ty.s != prev_s) {
-                                    if (ty.s == prev_s + 1) {
-#pragma unroll
-                                        for (int ch = 0; ch < 3; ++ch) h0[ch] = h1[ch];
+                            const int2 tx = s_xt[cx];
+                            const int xa = tx.y & 0xFFFF, xb = tx.y >> 16;
+                            const uint8_t* colp = tile0 + tx.x;
+                            uint8_t* o = s_out + ((da - d0) * RW + geo.ox + cx) * 3;
+                            int prev_s = -4, h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
+                            for (int d = da; d < db; ++d, o += RW * 3) {
+                                const int2 ty = s_yt[d];
+                                if (ty.x != prev_s) {
+                                    const uint8_t* p = colp + ty.x * RB;
+                                    if (ty.x == prev_s + 1) {
+                                        h0r = h1r; h0g = h1g; h0b = h1b;
                                     } else {
-#pragma unroll
-                                        for (int ch = 0; ch < 3; ++ch) h0[ch] = ((int)p[ch] * tx.a + (int)p[ch + 3] * tx.b) >> 4;
+                                        h0r = (p[0] * xa + p[3] * xb) >> 4;  // HResizeLinear x2048, >> 4 as in VResizeLinear
+                                        h0g = (p[1] * xa + p[4] * xb) >> 4;
+                                        h0b = (p[2] * xa + p[5] * xb) >> 4;
                                     }
-#pragma unroll
-                                    for (int ch = 0; ch < 3; ++ch) h1[ch] = ((int)p[RB + ch] * tx.a + (int)p[RB + ch + 3] * tx.b) >> 4;
-                                    prev_s = ty.s;
+                                    h1r = (p[RB] * xa + p[RB + 3] * xb) >> 4;
+                                    h1g = (p[RB + 1] * xa + p[RB + 4] * xb) >> 4;
+                                    h1b = (p[RB + 2] * xa + p[RB + 5] * xb) >> 4;
+                                    prev_s = ty.x;
                                 }
-                                uint8_t* o = s_out + ((size_t)(d - d0) * P.RW + geo.ox + cx) * 3;
-#pragma unroll
-                                for (int ch = 0; ch < 3; ++ch) {
-                                    // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>
-                                    int res = ((((int)ty.a * h0[ch]) >> 16) + (((int)ty.b * h1[ch]) >> 16) + 2) >> 2;
-                                    res = min(255, max(0, res));
-                                    o[ch] = (uint8_t)res;
-                                }
+                                // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255
+                                const int ya = ty.y & 0xFFFF, yb = ty.y >> 16;
+                                o[0] = (uint8_t)((((ya * h0r) >> 16) + ((yb * h1r) >> 16) + 2) >> 2);
+                                o[1] = (uint8_t)((((ya * h0g) >> 16) + ((yb * h1g) >> 16) + 2) >> 2);
+                                o[2] = (uint8_t)((((ya * h0b) >> 16) + ((yb * h1b) >> 16) + 2) >> 2);
                             }
                         }
                     }
                     fence_async_smem();
                     __syncthreads();
                     if (threadIdx.x == 0) {
-                        bulk_s2g(rimg + (size_t)(geo.oy + d0) * P.RW * 3, s_out, (uint32_t)rows * P.RW * 3);
+                        bulk_s2g(rimg + (size_t)(geo.oy + d0) * RW * 3, s_out, (uint32_t)rows * RW * 3);
                         bulk_commit();
                     }
                 }
@@ -610,34 +659,11 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
     P.K_0 = taps[0] << 8; P.K12 = taps[1] | (taps[2] << 8); P.K34 = taps[3] | (taps[4] << 8);
     P.RH = RH; P.RW = RW;
     P.need_lab_a = (cfg->strategy == 1 || cfg->use_lab_brown) ? 1 : 0;
-    auto al = [](size_t b) { return (int)((b + 127) & ~(size_t)127); };
-    int off = 0;
-    P.off_planes = off; off += al((size_t)M.NW * 4 * 3);
-    P.off_hsv = off; off += al(sizeof(HsvLut));
-    P.off_lab = off; off += al(sizeof(LabLut));
-    P.off_union = off;
-    // phase A
-    int a = off;
-    P.off_src = a; a += al((size_t)(TR + 4) * rb + 16);
-    P.off_v = a; a += al((size_t)3 * TR * (W + 4) * 2);
-    // phase B
-    int b = off;
-    P.off_t = b; b += al((size_t)M.NW * 4 * 3);
-    P.off_wbase = b; b += al((size_t)(M.NW + 1) * 4);
-    P.off_runs = b; b += al((size_t)RCAP_SMEM * 14);
-    P.off_stage = b; b += al((size_t)M.stage_rows * rb);
-    // phase C (off_src as in A)
-    int c3 = P.off_src + al((size_t)(TR + 4) * rb + 16);
-    P.off_out = c3; c3 += al((size_t)CHUNK * RW * 3);
-    P.off_hist = c3; c3 += al(12 * 256 * 4);
-    P.off_cat = c3; c3 += al(3 * 256 * 16);
-    P.off_xt = c3; c3 += al((size_t)RW * 8);
-    P.off_yt = c3; c3 += al((size_t)RH * 8);
-    P.smem_bytes = max(a, max(b, c3));
+    P.lay = make_lay(H, W, RH, RW);
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2);
-    if (P.smem_bytes > 226 * 1024) return false;
-    *per_sm = max(1, min(2, (228 * 1024) / (P.smem_bytes + 1024 + 1536)));  // + static shared + per-block reserve
+    if (P.lay.smem_bytes > 226 * 1024) return false;
+    *per_sm = max(1, min(2, (228 * 1024) / (P.lay.smem_bytes + 1024 + 1536)));  // + static shared + per-block reserve
     (void)B;
     return true;
 }
@@ -678,17 +704,23 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
         const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
         const size_t need = 256 + (size_t)P.ws_per_block * grid;
         LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
-        static int attr = 0;
-        if (P.smem_bytes > attr) {
-            cudaError_t e = cudaFuncSetAttribute(k_core, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_core, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.smem_bytes, cudaGetErrorString(e));
-            attr = P.smem_bytes;
+        const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
+        static int attr[2] = {0, 0};
+        if (P.lay.smem_bytes > attr[s256]) {
+            const void* fn = s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.lay.smem_bytes);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.lay.smem_bytes, cudaGetErrorString(e));
+            attr[s256] = P.lay.smem_bytes;
         }
         cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
-        k_core<<<grid, MT, P.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                              (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+        if (s256)
+            k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                                            (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+        else
+            k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                                             (uint8_t*)workspace, lfx_tables(), g_cat_lut);
         return lfx_check_launch("pipeline_core(fused)");
     }
 

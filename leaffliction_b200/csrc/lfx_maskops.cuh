@@ -12,7 +12,8 @@ namespace {
 // largest_contour + contour_to_mask (Transformation.py:285-299) on plane `in`.
 // Temps: tA (inverted / filled), out receives the selected filled component (zero when none).
 // info8: {found,x,y,w,h,area2,npix,-}.  Returns found (block-uniform).
-__device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out, int* info8, Ctx& c) {
+template <class C>
+__device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out, int* info8, C& c) {
     // outside = 4-connected background reachable from the border
     for (int i = threadIdx.x; i < c.NW; i += MT) tA[i] = ~in[i] & valid_mask(c, i % c.WPR);
     __syncthreads();
@@ -100,8 +101,9 @@ __device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out
 
 // _postprocess_mask (mask.py:53-69): raw -> result plane `out`; temps t1..t3.
 // When no contour exists, `out` holds the opened mask (reference returns (opened, None)).
+template <class C>
 __device__ bool postprocess(const uint32_t* raw, uint32_t* out, uint32_t* t1, uint32_t* t2, uint32_t* t3, int* info8,
-                            const MaskParams& P, Ctx& c) {
+                            const MaskParams& P, C& c) {
     // pcv.fill: drop 4-connected components with < fill_size pixels
     ccl<4>(raw, c);
     measure_area(c);
@@ -156,9 +158,9 @@ __device__ int otsu_threshold(const int* h, int n) {
 // Pixel pass over the RGB image.  PASS 0: strategy predicate -> p0 (strategies 0/1) and brown
 // predicate -> pb.  PASS 1: histogram of HSV channel `chan` into c.s_hist.  PASS 2: p0 = chan > thr
 // (light) or chan <= thr (dark).
-template <int PASS>
+template <int PASS, class C>
 __device__ void pixel_pass(const uint8_t* img, uint8_t* s_stage, const HsvLut* hsv, const LabLut* lab, uint32_t* p0,
-                           uint32_t* pb, int chan, int thr, bool dark, const MaskParams& P, Ctx& c) {
+                           uint32_t* pb, int chan, int thr, bool dark, const MaskParams& P, C& c) {
     const int rb = c.W * 3;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int y0 = 0; y0 < c.H; y0 += P.stage_rows) {
@@ -209,7 +211,8 @@ __device__ void pixel_pass(const uint8_t* img, uint8_t* s_stage, const HsvLut* h
 }
 
 // raw mask bytes -> bit plane
-__device__ void bytes_to_plane(const uint8_t* raw, uint32_t* p, const Ctx& c) {
+template <class C>
+__device__ void bytes_to_plane(const uint8_t* raw, uint32_t* p, const C& c) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int item = wid; item < c.NW; item += MT / 32) {
         const int y = item / c.WPR, w = item - y * c.WPR;
@@ -220,7 +223,8 @@ __device__ void bytes_to_plane(const uint8_t* raw, uint32_t* p, const Ctx& c) {
     }
 }
 
-__device__ void plane_to_bytes(const uint32_t* p, uint8_t* mask, const Ctx& c) {
+template <class C>
+__device__ void plane_to_bytes(const uint32_t* p, uint8_t* mask, const C& c) {
     if ((c.W & 3) == 0) {
         const int gpr = c.W >> 2;
         for (int i = threadIdx.x; i < c.H * gpr; i += MT) {
@@ -239,8 +243,26 @@ __device__ void plane_to_bytes(const uint32_t* p, uint8_t* mask, const Ctx& c) {
     }
 }
 
+
+// plane -> 0/255 bytes, 16 pixels (one 128-bit store) per thread; needs W % 16 == 0 and a 16-byte aligned mask.
+template <class C>
+__device__ void plane_to_bytes16(const uint32_t* p, uint8_t* mask, const C& c) {
+    uint4* out = reinterpret_cast<uint4*>(mask);
+    for (int i = threadIdx.x; i < c.NW * 2; i += MT) {
+        const uint32_t bits = (p[i >> 1] >> ((i & 1) * 16)) & 0xFFFFu;
+        uint4 v;
+        // nibble -> 4 bytes: spread bit k to bit 8k (x 0x00204081, disjoint partial products), then x 0xFF
+        v.x = (((bits & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        v.w = (((bits >> 12) * 0x00204081u) & 0x01010101u) * 0xFFu;
+        out[i] = v;
+    }
+}
+
+template <class C>
 __device__ void otsu_plane(const uint8_t* img, uint8_t* s_stage, const HsvLut* hsv, uint32_t* p0, int chan, bool dark,
-                           const MaskParams& P, Ctx& c) {
+                           const MaskParams& P, C& c) {
     for (int i = threadIdx.x; i < 256; i += MT) c.s_hist[i] = 0;
     __syncthreads();
     pixel_pass<1>(img, s_stage, hsv, nullptr, p0, nullptr, chan, 0, dark, P, c);
@@ -255,9 +277,10 @@ __device__ void otsu_plane(const uint8_t* img, uint8_t* s_stage, const HsvLut* h
 // fallback of _handle_fallback_and_extension (:495-523) and _extend_mask_with_brown_regions
 // (:335-392).  P0 = raw candidate, PB = brown predicate; the result lands in PR / s_info.
 // `simg` is the image in global memory (only read by the rare Otsu fallback, staged via s_stage).
+template <class C>
 __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut* s_hsv, uint32_t* P0, uint32_t* PB,
                             uint32_t* PR, uint32_t* T1, uint32_t* T2, uint32_t* T3, int* s_info, int* s_info2,
-                            const MaskParams& P, Ctx& c) {
+                            const MaskParams& P, C& c) {
     bool found = postprocess(P0, PR, T1, T2, T3, s_info, P, c);
     if (P.mode == 0) {
         // _find_best_mask rejects a lone candidate only when cnt is None or contourArea <= 1
@@ -278,8 +301,16 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
                 morph_any<true>(T1, T2, P.fp_search, c);
                 __syncthreads();
             }
-            for (int i = threadIdx.x; i < c.NW; i += MT) T1[i] = PB[i] & T2[i];
-            __syncthreads();
+            int any = 0;
+            for (int i = threadIdx.x; i < c.NW; i += MT) {
+                const uint32_t v = PB[i] & T2[i];
+                T1[i] = v;
+                any |= (v != 0u);
+            }
+            // No brown pixel near the leaf (or none survives open/close): the extended mask equals the best
+            // mask, a single filled component whose contour statistics are already in s_info -- the
+            // reference recomputes the same contour (mask.py:383-392), so the result is unchanged.
+            if (!__syncthreads_or(any)) return;
             morph_any<false>(T1, T2, P.fp_brown, c);  // open
             __syncthreads();
             morph_any<true>(T2, T1, P.fp_brown, c);
@@ -287,7 +318,9 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
             morph_any<true>(T1, T2, P.fp_brown, c);  // close
             __syncthreads();
             morph_any<false>(T2, T1, P.fp_brown, c);
-            __syncthreads();
+            any = 0;
+            for (int i = threadIdx.x; i < c.NW; i += MT) any |= (T1[i] != 0u);   // own words only: no barrier needed yet
+            if (!__syncthreads_or(any)) return;
             ccl<8>(T1, c);
             measure_area(c);
             plane_copy(T3, PR, c);  // ext = best | filtered brown

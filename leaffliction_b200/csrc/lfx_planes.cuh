@@ -35,9 +35,23 @@ struct MaskParams {
     unsigned long long ws_per_block;
 };
 
-struct Ctx {
+// Image geometry of the planes: runtime (any shape) or compile-time (the fused kernel's 256x256 fast
+// path -- index math becomes shifts by immediates, loops unroll, no address rematerialisation).
+struct DynGeom {
     int H, W, WPR, NW;
     uint32_t lastmask;
+    int wshift;  // log2(WPR) when WPR is a power of two, else -1
+};
+template <int H_, int W_>
+struct StaticGeom {
+    static_assert(W_ % 32 == 0 && ((W_ / 32) & (W_ / 32 - 1)) == 0, "StaticGeom: W must be 32 * 2^k");
+    static constexpr int H = H_, W = W_, WPR = W_ / 32, NW = H_ * (W_ / 32);
+    static constexpr uint32_t lastmask = 0xFFFFFFFFu;
+    static constexpr int wshift = (WPR == 1) ? 0 : (WPR == 2) ? 1 : (WPR == 4) ? 2 : (WPR == 8) ? 3 : (WPR == 16) ? 4 : 5;
+};
+
+template <class G>
+struct CtxT : G {
     uint32_t* plane[NPLANES];
     int* wbase;
     // run tables (current selection) + both backing stores
@@ -58,12 +72,13 @@ struct Ctx {
     int* s_bb;                   // [8]
     int* s_hist;                 // [256]
     int status;
-    int wshift;          // log2(WPR) when WPR is a power of two, else -1
     uint32_t* hp[6];     // scratch planes for dilate_ellipse20 (nullptr = use the generic morph)
 };
+using Ctx = CtxT<DynGeom>;
 
 // word index -> (row, word-in-row) without an integer division when WPR is a power of two
-__device__ __forceinline__ void split_index(const Ctx& c, int i, int& y, int& w) {
+template <class C>
+__device__ __forceinline__ void split_index(const C& c, int i, int& y, int& w) {
     if (c.wshift >= 0) {
         y = i >> c.wshift;
         w = i & (c.WPR - 1);
@@ -73,11 +88,17 @@ __device__ __forceinline__ void split_index(const Ctx& c, int i, int& y, int& w)
     }
 }
 
-__device__ __forceinline__ uint32_t valid_mask(const Ctx& c, int w) { return (w == c.WPR - 1) ? c.lastmask : 0xFFFFFFFFu; }
+template <class C>
+__device__ __forceinline__ uint32_t valid_mask(const C& c, int w) { return (w == c.WPR - 1) ? c.lastmask : 0xFFFFFFFFu; }
 
 __device__ __forceinline__ void ctx_init_geometry(Ctx& c, int H, int W, int WPR, int NW, uint32_t lastmask) {
     c.H = H; c.W = W; c.WPR = WPR; c.NW = NW; c.lastmask = lastmask;
     c.wshift = ((WPR & (WPR - 1)) == 0) ? (31 - __clz(WPR)) : -1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) c.hp[k] = nullptr;
+}
+template <class C>
+__device__ __forceinline__ void ctx_clear_hp(C& c) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) c.hp[k] = nullptr;
 }
@@ -111,16 +132,18 @@ __device__ int block_exscan(int v, int* s_tmp, int& total) {
     return res;
 }
 
-__device__ __forceinline__ void plane_zero(uint32_t* p, const Ctx& c) {
+template <class C>
+__device__ __forceinline__ void plane_zero(uint32_t* p, const C& c) {
     for (int i = threadIdx.x; i < c.NW; i += MT) p[i] = 0;
 }
-__device__ __forceinline__ void plane_copy(uint32_t* d, const uint32_t* s, const Ctx& c) {
+template <class C>
+__device__ __forceinline__ void plane_copy(uint32_t* d, const uint32_t* s, const C& c) {
     for (int i = threadIdx.x; i < c.NW; i += MT) d[i] = s[i];
 }
 
 // ---------------------------------------------------------------- morphology
-template <bool DIL>
-__device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
+template <bool DIL, class C>
+__device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, const C& c) {
     for (int i = threadIdx.x; i < c.NW; i += MT) {
         int y, w;
         split_index(c, i, y, w);
@@ -151,8 +174,8 @@ __device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, co
 
 // 3x3 MORPH_ELLIPSE = cross (010/111/010): the footprint of every open/close on the default path
 // (morph_kernel = brown_morph_kernel = 3, config.yaml).  5 words in, 2 funnel shifts.
-template <bool DIL>
-__device__ void morph_cross3(const uint32_t* in, uint32_t* out, const Ctx& c) {
+template <bool DIL, class C>
+__device__ void morph_cross3(const uint32_t* in, uint32_t* out, const C& c) {
     const uint32_t oob = DIL ? 0u : 0xFFFFFFFFu;
     for (int i = threadIdx.x; i < c.NW; i += MT) {
         int y, w;
@@ -184,8 +207,8 @@ __device__ __forceinline__ bool is_cross3(const Footprint& fp) {
            fp.r[1].o2 == 1 && fp.r[2].dy == 1 && fp.r[2].o1 == 0 && fp.r[2].o2 == 0;
 }
 
-template <bool DIL>
-__device__ __forceinline__ void morph_any(const uint32_t* in, uint32_t* out, const Footprint& fp, const Ctx& c) {
+template <bool DIL, class C>
+__device__ __forceinline__ void morph_any(const uint32_t* in, uint32_t* out, const Footprint& fp, const C& c) {
     if (is_cross3(fp))
         morph_cross3<DIL>(in, out, c);
     else
@@ -197,7 +220,8 @@ __device__ __forceinline__ void morph_any(const uint32_t* in, uint32_t* out, con
 // -3..3: [-10,9] -- so the six wider horizontal dilations are built incrementally from one
 // (prev,cur,next) word triple into six scratch planes (20 funnel shifts per word instead of 325),
 // then each output word ORs 20 plane rows.  Needs c.hp[0..5]; ends with a block barrier.
-__device__ void dilate_ellipse20(const uint32_t* in, uint32_t* out, const Ctx& c) {
+template <class C>
+__device__ void dilate_ellipse20(const uint32_t* in, uint32_t* out, const C& c) {
     for (int i = threadIdx.x; i < c.NW; i += MT) {
         int y, w;
         split_index(c, i, y, w);
@@ -287,8 +311,8 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
 
 // Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
 // (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
-template <int CONN>
-__device__ void ccl(const uint32_t* m, Ctx& c) {
+template <int CONN, class C>
+__device__ void ccl(const uint32_t* m, C& c) {
     const int per = (c.NW + MT - 1) / MT;
     const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
     int cnt = 0;
@@ -381,7 +405,8 @@ __device__ void ccl(const uint32_t* m, Ctx& c) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void set_run(uint32_t* out, int y, int x0, int x1, const Ctx& c) {
+template <class C>
+__device__ __forceinline__ void set_run(uint32_t* out, int y, int x0, int x1, const C& c) {
     const int w0 = x0 >> 5, w1 = x1 >> 5;
     for (int w = w0; w <= w1; ++w) {
         uint32_t mk = 0xFFFFFFFFu;
@@ -402,13 +427,15 @@ __device__ __forceinline__ int popc_range(const uint32_t* row, int x0, int x1) {
     }
     return n;
 }
-__device__ __forceinline__ int get_bit(const uint32_t* m, int y, int x, const Ctx& c) {
+template <class C>
+__device__ __forceinline__ int get_bit(const uint32_t* m, int y, int x, const C& c) {
     if (y < 0 || y >= c.H || x < 0 || x >= c.W) return 0;
     return (m[y * c.WPR + (x >> 5)] >> (x & 31)) & 1;
 }
 
 // acc[root] += pixels
-__device__ void measure_area(Ctx& c) {
+template <class C>
+__device__ void measure_area(C& c) {
     for (int r = threadIdx.x; r < c.R; r += MT) {
         const uint32_t g = c.geom[r];
         atomicAdd(&c.acc[c.parent[r]], (int)(g >> 16) - (int)(g & 0xFFFF) + 1);
@@ -417,7 +444,8 @@ __device__ void measure_area(Ctx& c) {
 }
 
 // out = runs whose component has >= min_area pixels (out must be zeroed + synced by the caller)
-__device__ void keep_area_ge(uint32_t* out, int min_area, Ctx& c) {
+template <class C>
+__device__ void keep_area_ge(uint32_t* out, int min_area, C& c) {
     for (int r = threadIdx.x; r < c.R; r += MT) {
         if (c.acc[c.parent[r]] >= min_area) {
             const uint32_t g = c.geom[r];
