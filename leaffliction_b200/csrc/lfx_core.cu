@@ -15,6 +15,8 @@
 // Reference: srcs/transform/filters/blur.py:72 (GaussianBlur 5x5), mask.py:548-582 (make_mask),
 // roi.py:20-46, hist.py:22-67,188,248-256, utils/mask_utils.py:10-83.  Arithmetic identical to the
 // stand-alone kernels (lfx_gauss.cu, lfx_mask.cu, lfx_roi.cu, lfx_color.cu), which remain the general path.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "lfx_maskops.cuh"
@@ -30,7 +32,7 @@ constexpr int NWARPS = MT / 32;
 struct Lay {
     int off_planes, off_hsv, off_lab;
     int off_src, off_v;                              // phase A (inside the union)
-    int off_t, off_wbase, off_runs, off_stage;       // phase B
+    int off_t, off_wbase, off_wbase2, off_runs, off_stage;  // phase B
     int off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A)
     int smem_bytes;
 };
@@ -49,6 +51,7 @@ __host__ __device__ constexpr Lay make_lay(int H, int W, int RH, int RW) {
     int b = off;
     L.off_t = b; b += lay_al((long long)NW * 4 * 3);
     L.off_wbase = b; b += lay_al((long long)(NW + 1) * 4);
+    L.off_wbase2 = b; b += lay_al((long long)(NW + 1) * 4);
     L.off_runs = b; b += lay_al((long long)RCAP_SMEM * 14);
     L.off_stage = b; b += lay_al((long long)stage_rows * rb);
     int c3 = L.off_src + lay_al((long long)(TR + 4) * rb + 16);
@@ -67,6 +70,7 @@ struct CoreParams {
     int t0, t1, t2;                         // symmetric vertical taps (t0 = taps[0] = taps[4], ...)
     int RH, RW;
     int need_lab_a;                         // Lab needed in phase A (lab strategy / lab brown)
+    int timing;                             // debug: accumulate per-phase cycles (LFX_CORE_TIMING=1)
     Lay lay;
     unsigned long long ws_per_block;
 };
@@ -129,21 +133,22 @@ __device__ void issue_tile_load(const uint8_t* simg, uint8_t* s_src, uint64_t* b
 // ---------------------------------------------------------------- phase A: blur
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
 
-// Vertical 5-tap pass on 4 pixels (12 bytes = 3 words) x 4 output rows per thread, packed 2x16-bit
+// Vertical 5-tap pass on 4 pixels (12 bytes = 3 words) x VRS output rows per thread, packed 2x16-bit
 // (sums <= 255*256 fit), results de-interleaved into the 16-bit channel planes s_v[c][row][x+2].
+constexpr int VRS = 8;
 __device__ __forceinline__ void vpass_item(const uint8_t* s_src, uint16_t* s_v, int g, int r0, int RB, int VP, int G,
                                            const CoreParams& P) {
-    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s_src + (size_t)r0 * RB) + 3 * g;
+    const uint32_t* sp = reinterpret_cast<const uint32_t*>(s_src + r0 * RB) + 3 * g;
     const int rw = RB >> 2;
     uint32_t lo[5][3], hi[5][3];
 #pragma unroll
-    for (int step = 0; step < 8; ++step) {
+    for (int step = 0; step < VRS + 4; ++step) {
         const int slot = step % 5;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const uint32_t w = sp[step * rw + k];
-            lo[slot][k] = w & 0x00FF00FFu;
-            hi[slot][k] = (w >> 8) & 0x00FF00FFu;
+            lo[slot][k] = prmt(w, 0u, 0x4240);  // bytes 0,2 -> 16-bit lanes
+            hi[slot][k] = prmt(w, 0u, 0x4341);  // bytes 1,3
         }
         if (step >= 4) {
             // window rows step-4 .. step live in slots (step-4)%5 .. step%5
@@ -159,8 +164,8 @@ __device__ __forceinline__ void vpass_item(const uint8_t* s_src, uint16_t* s_v, 
             const uint32_t G01 = prmt(h[0], l[1], 0x5410), G23 = prmt(h[1], l[2], 0x7632);
             const uint32_t B01 = prmt(l[0], h[1], 0x5432), B23 = prmt(l[2], h[2], 0x7610);
             const int orow = r0 + step - 4;
-            uint32_t* vr = reinterpret_cast<uint32_t*>(s_v + (size_t)orow * VP) + 2 * g + 1;  // element 4g+2
-            const int cs = (TR * VP) >> 1;                                                     // channel stride in words
+            uint32_t* vr = reinterpret_cast<uint32_t*>(s_v + orow * VP) + 2 * g + 1;  // element 4g+2
+            const int cs = (TR * VP) >> 1;                                             // channel stride in words
             vr[0] = R01; vr[1] = R23;
             vr[cs] = G01; vr[cs + 1] = G23;
             vr[2 * cs] = B01; vr[2 * cs + 1] = B23;
@@ -274,6 +279,7 @@ __global__ void __launch_bounds__(MT, 2)
     uint32_t* T3 = T2 + NW;
     c.plane[0] = P0; c.plane[1] = PB; c.plane[2] = PR; c.plane[3] = T1; c.plane[4] = T2; c.plane[5] = T3;
     c.wbase = reinterpret_cast<int*>(sm + L.off_wbase);
+    c.wbase2 = reinterpret_cast<int*>(sm + L.off_wbase2);
     c.sm_parent = reinterpret_cast<int*>(sm + L.off_runs);
     c.sm_geom = reinterpret_cast<uint32_t*>(sm + L.off_runs + RCAP_SMEM * 4);
     c.sm_acc = reinterpret_cast<int*>(sm + L.off_runs + RCAP_SMEM * 8);
@@ -313,12 +319,22 @@ __global__ void __launch_bounds__(MT, 2)
     const size_t img_px = (size_t)H * W;
     const bool want_stats = hist9 || hsv3 || counters;
 
+    // LFX_CORE_TIMING=1 (debug): per-phase SM-clock cycles summed over images into ws[64..]
+    unsigned long long* tacc = P.timing ? reinterpret_cast<unsigned long long*>(ws + 64) : nullptr;
+    long long tk0 = 0;
+#define LFX_TICK(slot)                                                        \
+    if (tacc && threadIdx.x == 0) {                                           \
+        const long long now = clock64();                                      \
+        atomicAdd(&tacc[slot], (unsigned long long)(now - tk0));              \
+        tk0 = now;                                                            \
+    }
     for (;;) {
         if (threadIdx.x == 0) s_next = atomicAdd(work_counter, 1);
         __syncthreads();
         const int img = s_next;
         if (img >= B) break;
         const uint8_t* simg = src + (size_t)img * img_px * 3;
+        if (tacc && threadIdx.x == 0) tk0 = clock64();
 
         // =========================================================== phase A
         if (threadIdx.x == 0) issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, nullptr, nullptr, 0);
@@ -326,14 +342,29 @@ __global__ void __launch_bounds__(MT, 2)
             const int y0 = t * TR, nr = min(TR, H - y0);
             mbar_wait(&s_bar, par);
             par ^= 1;
-            if (blur) {
-                const int nstrips = (nr + 3) >> 2;
-                for (int item = threadIdx.x; item < G * nstrips; item += MT) {
+            // The vertical blur pass has G * ceil(nr / VRS) items (256 for a full 256-wide tile = 8 warps); the
+            // warps it leaves idle take a head start of `extra` pixel-pass items each so both groups finish together.
+            const int nvitems = blur ? G * ((nr + VRS - 1) / VRS) : 0;
+            const int nvw = min(NWARPS, (nvitems + 31) >> 5);
+            if (wid < nvw) {
+                for (int item = threadIdx.x; item < nvitems; item += nvw * 32) {
                     const int strip = item / G, g = item - strip * G;
-                    vpass_item(s_src, s_v, g, strip * 4, RB, VP, G, P);
+                    vpass_item(s_src, s_v, g, strip * VRS, RB, VP, G, P);
                 }
             }
-            for (int item = wid; item < nr * WPR; item += NWARPS) {
+            const int nfree = NWARPS - nvw;                                       // warps without vertical-pass work
+            const int npix = nr * WPR;
+            const int extra = (nvw > 0 && nfree > 0) ? min(npix / nfree, 8) : 0;  // ~ one vpass item = 8 pixel items
+            const int head = extra * nfree;
+            for (int k = 0; k < 2; ++k) {
+              int item, iend, istep;
+              if (k == 0) {
+                  if (wid < nvw || extra == 0) continue;
+                  item = wid - nvw; iend = head; istep = nfree;
+              } else {
+                  item = head + wid; iend = npix; istep = NWARPS;
+              }
+              for (; item < iend; item += istep) {
                 int ry, w;
                 split_index(c, item, ry, w);
                 const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
@@ -362,6 +393,7 @@ __global__ void __launch_bounds__(MT, 2)
                     P0[idx] = m0;
                     PB[idx] = m1;
                 }
+              }
             }
             __syncthreads();
             if (threadIdx.x == 0 && t + 1 < ntiles)
@@ -376,8 +408,11 @@ __global__ void __launch_bounds__(MT, 2)
             }
         }
 
+        LFX_TICK(0)
         // =========================================================== phase B
         c.status = 0;
+        c.tacc = tacc;
+        c.tk0 = tk0;
         mask_finish(simg, s_stage, s_hsv, P0, PB, PR, T1, T2, T3, s_info, s_info2, M, c);
         plane_to_bytes16(PR, mask + (size_t)img * img_px, c);
         if (threadIdx.x < 8) {
@@ -390,6 +425,8 @@ __global__ void __launch_bounds__(MT, 2)
             continue;
         }
 
+        tk0 = c.tk0;
+        LFX_TICK(1)
         // =========================================================== phase C
         if (threadIdx.x == 0) {
             Geo gq;
@@ -445,6 +482,11 @@ __global__ void __launch_bounds__(MT, 2)
                 s_dlo[threadIdx.x] = lo;
             }
         }
+        // ROI thread mapping for this image: one canvas column per thread, MT / cols row strips (power of two)
+        const int roi_cols = max(1, min(geo.nw, MT));
+        const int roi_sshift = 31 - __clz(max(1, MT / roi_cols));
+        const int roi_strips = 1 << roi_sshift;
+        const int roi_strip = threadIdx.x / roi_cols, roi_col0 = threadIdx.x - roi_strip * roi_cols;
         uint32_t cacc[4] = {0u, 0u, 0u, 0u};
         for (int t = 0; t < ntiles; ++t) {
             const int y0 = t * TR, nr = min(TR, H - y0);
@@ -452,7 +494,10 @@ __global__ void __launch_bounds__(MT, 2)
             par ^= 1;
             __syncthreads();  // s_dlo / taps visible (t == 0)
             if (want_stats) {
-                for (int item = wid; item < nr * WPR; item += NWARPS) {
+                // contiguous rows per warp: every warp sees all word columns (the leaf sits in the middle ones)
+                const int ipw = (nr * WPR + NWARPS - 1) / NWARPS;
+                const int iend = min(nr * WPR, (wid + 1) * ipw);
+                for (int item = wid * ipw; item < iend; ++item) {
                     const uint32_t m = PR[y0 * WPR + item];
                     if (m == 0u) continue;
                     if ((m >> lane) & 1u) {
@@ -495,41 +540,37 @@ __global__ void __launch_bounds__(MT, 2)
                 {
                     const int ra = max(y0, geo.by), rb2 = min(min(y0 + nr + 1, H), geo.by + geo.bh);
                     const int wa = geo.bx >> 5, nwd = ((geo.bx + geo.bw - 1) >> 5) - wa + 1;
-                    const int nitems = max(0, rb2 - ra) * nwd;
-                    for (int item = wid; item < nitems; item += NWARPS) {
-                        const int rr = item / nwd, w = wa + (item - rr * nwd);
-                        const int y = ra + rr;
-                        const uint32_t m = PR[y * WPR + w];
-                        if (m == 0xFFFFFFFFu) continue;
-                        if (!((m >> lane) & 1u)) {
-                            uint8_t* px = s_src + ((y - y0 + 2) * RB + (w * 32 + lane) * 3);
-                            px[0] = 255; px[1] = 255; px[2] = 255;
+                    for (int y = ra + wid; y < rb2; y += NWARPS) {
+                        const uint32_t* prow = PR + y * WPR;
+                        uint8_t* srow = s_src + ((y - y0 + 2) * RB + lane * 3);
+                        for (int w = wa; w < wa + nwd; ++w) {
+                            const uint32_t m = prow[w];
+                            if (m == 0xFFFFFFFFu) continue;
+                            if (!((m >> lane) & 1u)) {
+                                uint8_t* px = srow + w * 96;
+                                px[0] = 255; px[1] = 255; px[2] = 255;
+                            }
                         }
                     }
                 }
                 __syncthreads();
                 const int dA = s_dlo[t], dB = s_dlo[t + 1];
-                const int cols = min(geo.nw, MT);
-                const int strips = max(1, MT / cols);
-                const int strip = threadIdx.x / cols, col0 = threadIdx.x - strip * cols;
                 const uint8_t* tile0 = s_src + (geo.by - y0 + 2) * RB;  // staged row of source row `by`
                 for (int d0 = dA; d0 < dB; d0 += CHUNK) {
                     const int rows = min(CHUNK, dB - d0);
                     if (threadIdx.x == 0) bulk_wait_read();  // the previous store has drained s_out
                     __syncthreads();
-                    if (geo.nw < RW) {
-                        for (int i = threadIdx.x; i < rows * RW * 3 / 16; i += MT) reinterpret_cast<uint4*>(s_out)[i] = make_uint4(0, 0, 0, 0);
-                        __syncthreads();
-                    }
-                    if (strip < strips) {
-                        const int per = (rows + strips - 1) / strips;
-                        const int da = d0 + strip * per, db = min(d0 + rows, da + per);
-                        for (int cx = col0; cx < geo.nw; cx += cols) {
+                    // the side bands of s_out stay zero from the start of phase C: only [ox, ox+nw) is rewritten
+                    if (roi_strip < roi_strips) {
+                        const int per = (rows + roi_strips - 1) >> roi_sshift;
+                        const int da = d0 + roi_strip * per, db = min(d0 + rows, da + per);
+                        for (int cx = roi_col0; cx < geo.nw; cx += roi_cols) {
                             const int2 tx = s_xt[cx];
-                            const int xa = tx.y & 0xFFFF, xb = tx.y >> 16;
+                            const uint32_t xa = tx.y & 0xFFFF, xb = (uint32_t)tx.y >> 16;
                             const uint8_t* colp = tile0 + tx.x;
                             uint8_t* o = s_out + ((da - d0) * RW + geo.ox + cx) * 3;
-                            int prev_s = -4, h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
+                            int prev_s = -4;
+                            uint32_t h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
                             for (int d = da; d < db; ++d, o += RW * 3) {
                                 const int2 ty = s_yt[d];
                                 if (ty.x != prev_s) {
@@ -546,11 +587,12 @@ __global__ void __launch_bounds__(MT, 2)
                                     h1b = (p[RB + 2] * xa + p[RB + 5] * xb) >> 4;
                                     prev_s = ty.x;
                                 }
-                                // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255
-                                const int ya = ty.y & 0xFFFF, yb = ty.y >> 16;
-                                o[0] = (uint8_t)((((ya * h0r) >> 16) + ((yb * h1r) >> 16) + 2) >> 2);
-                                o[1] = (uint8_t)((((ya * h0g) >> 16) + ((yb * h1g) >> 16) + 2) >> 2);
-                                o[2] = (uint8_t)((((ya * h0b) >> 16) + ((yb * h1b) >> 16) + 2) >> 2);
+                                // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255.
+                                // (ya*h >> 16) as the high word of (ya << 16) * h: one IMAD.HI with the addend fused
+                                const uint32_t ya = (uint32_t)ty.y << 16, yb = (uint32_t)ty.y & 0xFFFF0000u;
+                                o[0] = (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2);
+                                o[1] = (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2);
+                                o[2] = (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2);
                             }
                         }
                     }
@@ -583,7 +625,9 @@ __global__ void __launch_bounds__(MT, 2)
         }
         if (threadIdx.x == 0) bulk_wait_read();  // s_out is reused as part of the phase-A/B union next image
         __syncthreads();
+        LFX_TICK(2)
     }
+#undef LFX_TICK
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
@@ -646,7 +690,7 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
     M.H = H; M.W = W; M.WPR = W / 32; M.NW = H * M.WPR;
     M.lastmask = 0xFFFFFFFFu;
     M.mode = 0;
-    M.rcap_glob = H * ((W + 1) / 2);
+    M.rcap_glob = H * (W + 2);  // ccl2 labels foreground and background runs together
     M.planes_in_smem = 1;
     const int rb = W * 3;
     M.stage_rows = max(1, min(H, STAGE_BYTES / rb));
@@ -674,7 +718,7 @@ extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     const size_t general = lfx_make_mask_workspace(B, H, W);
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t rcap = (size_t)H * ((W + 1) / 2);
+    const size_t rcap = (size_t)H * (W + 2);
     const size_t fused = 256 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
     return general > fused ? general : fused;
 }
@@ -715,12 +759,26 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
         }
         cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
+        static const bool timing = getenv("LFX_CORE_TIMING") && atoi(getenv("LFX_CORE_TIMING")) > 0;
+        P.timing = timing ? 1 : 0;
         if (s256)
             k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
                                                             (uint8_t*)workspace, lfx_tables(), g_cat_lut);
         else
             k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
                                                              (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+        if (timing) {  // debug only: synchronises and prints the phase split
+            unsigned long long t[16] = {0};
+            cudaStreamSynchronize(st);
+            cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost);
+            double tb = (double)t[1];
+            for (int k = 3; k < 10; ++k) tb += (double)t[k];
+            const double tot = (double)t[0] + tb + (double)t[2];
+            fprintf(stderr, "[lfx] k_core B=%d phase cycles/image: A %.0f (%.1f%%)  B %.0f (%.1f%%)  C %.0f (%.1f%%)\n", B, t[0] / (double)B,
+                    100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, t[2] / (double)B, 100.0 * t[2] / tot);
+            fprintf(stderr, "[lfx]   B split: fill-ccl4 %.0f  close/open %.0f  largest#1 %.0f  dilate20x2 %.0f  brown-morph %.0f  brown-ccl8 %.0f  largest#2 %.0f  tail %.0f\n",
+                    t[3] / (double)B, t[4] / (double)B, t[5] / (double)B, t[6] / (double)B, t[7] / (double)B, t[8] / (double)B, t[9] / (double)B, t[1] / (double)B);
+        }
         return lfx_check_launch("pipeline_core(fused)");
     }
 

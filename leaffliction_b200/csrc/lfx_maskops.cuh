@@ -9,11 +9,108 @@
 
 namespace {
 
+// largest_contour + contour_to_mask (Transformation.py:285-299) with ONE labeling pass (ccl2): the 8-connected
+// components of `in` and the 4-connected components of its complement are labelled together.  A complement
+// component that does not touch the border is a hole; it is enclosed by exactly one foreground component
+// (8/4 duality), so hole filling never merges components: each hole run is re-parented to the component of
+// the foreground pixel on its left.  2*contourArea = 2N - (P - Q1) - 2 is accumulated per run on the filled
+// plane (tA) with run-end terms that do not assume maximal runs.  Same outputs as largest_external.
+template <class C>
+__device__ bool largest_external2(const uint32_t* in, uint32_t* tA, uint32_t* out, int* info8, C& c) {
+    ccl2(in, c);
+    const int R1 = c.R1, R = c.R;
+    // background components that touch the border are "outside"
+    for (int r = R1 + threadIdx.x; r < R; r += MT) {
+        const uint32_t g = c.geom[r];
+        const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+        if (y == 0 || y == c.H - 1 || x0 == 0 || x1 == c.W - 1) atomicOr(&c.acc[c.parent[r]], 1);
+    }
+    for (int i = threadIdx.x; i < c.NW; i += MT) {
+        tA[i] = in[i];
+        out[i] = 0;
+    }
+    if (threadIdx.x == 0) {
+        *c.s_best = 0ull;
+        c.s_bb[0] = 0x7fffffff; c.s_bb[1] = 0x7fffffff; c.s_bb[2] = -1; c.s_bb[3] = -1; c.s_bb[4] = 0;
+    }
+    __syncthreads();
+    // holes: fill them in tA and hand each hole run to its enclosing foreground component
+    for (int r = R1 + threadIdx.x; r < R; r += MT) {
+        if (c.acc[c.parent[r]]) {
+            c.parent[r] = -1;  // outside
+        } else {
+            const uint32_t g = c.geom[r];
+            const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+            set_run(tA, y, x0, x1, c);
+            c.parent[r] = c.parent[fg_run_at(in, y, x0 - 1, c)];  // x0 > 0: a run starting at the border is outside
+        }
+    }
+    __syncthreads();
+    // per-run contribution to 2N - (P - Q1) on the filled plane
+    for (int r = threadIdx.x; r < R; r += MT) {
+        const int root = c.parent[r];
+        if (root < 0) continue;
+        const uint32_t g = c.geom[r];
+        const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+        const int eL = !get_bit(tA, y, x0 - 1, c), eR = !get_bit(tA, y, x1 + 1, c);  // run ends that are component ends
+        int v = -(eL + eR);
+        if (y > 0) v += popc_range(tA + (y - 1) * c.WPR, x0, x1);
+        if (y < c.H - 1) v += popc_range(tA + (y + 1) * c.WPR, x0, x1);
+        v += (eR && !get_bit(tA, y + 1, x1, c) && !get_bit(tA, y + 1, x1 + 1, c));
+        v += (eL && !get_bit(tA, y + 1, x0, c) && !get_bit(tA, y + 1, x0 - 1, c));
+        v += (eR && !get_bit(tA, y - 1, x1, c) && !get_bit(tA, y - 1, x1 + 1, c));
+        v += (eL && !get_bit(tA, y - 1, x0, c) && !get_bit(tA, y - 1, x0 - 1, c));
+        atomicAdd(&c.acc[root], v);
+    }
+    __syncthreads();
+    // argmax of (area2, first-pixel order): ties go to the LARGEST root id (reverse discovery order)
+    for (int r = threadIdx.x; r < R1; r += MT) {
+        if (c.parent[r] == r) {
+            const unsigned long long key = ((unsigned long long)(uint32_t)(c.acc[r] - 2 + 1) << 32) | (uint32_t)r;
+            atomicMax(c.s_best, key);
+        }
+    }
+    __syncthreads();
+    const unsigned long long best = *c.s_best;
+    if (best == 0ull) {
+        if (threadIdx.x < 8) info8[threadIdx.x] = 0;
+        __syncthreads();
+        return false;
+    }
+    const int win = (int)(best & 0xFFFFFFFFu);
+    for (int r = threadIdx.x; r < R; r += MT) {
+        if (c.parent[r] == win) {
+            const uint32_t g = c.geom[r];
+            const int y = c.ry[r], x0 = g & 0xFFFF, x1 = g >> 16;
+            set_run(out, y, x0, x1, c);
+            atomicMin(&c.s_bb[0], x0);
+            atomicMin(&c.s_bb[1], y);
+            atomicMax(&c.s_bb[2], x1);
+            atomicMax(&c.s_bb[3], y);
+            atomicAdd(&c.s_bb[4], x1 - x0 + 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info8[0] = 1;
+        info8[1] = c.s_bb[0];
+        info8[2] = c.s_bb[1];
+        info8[3] = c.s_bb[2] - c.s_bb[0] + 1;
+        info8[4] = c.s_bb[3] - c.s_bb[1] + 1;
+        info8[5] = (int)(best >> 32) - 1;
+        info8[6] = c.s_bb[4];
+        info8[7] = (int)(c.geom[win] & 0xFFFF);  // x of the component's first raster pixel (its y is info8[2])
+    }
+    __syncthreads();
+    return true;
+}
+
 // largest_contour + contour_to_mask (Transformation.py:285-299) on plane `in`.
 // Temps: tA (inverted / filled), out receives the selected filled component (zero when none).
 // info8: {found,x,y,w,h,area2,npix,-}.  Returns found (block-uniform).
 template <class C>
 __device__ bool largest_external(const uint32_t* in, uint32_t* tA, uint32_t* out, int* info8, C& c) {
+    if (c.wbase2) return largest_external2(in, tA, out, info8, c);
     // outside = 4-connected background reachable from the border
     for (int i = threadIdx.x; i < c.NW; i += MT) tA[i] = ~in[i] & valid_mask(c, i % c.WPR);
     __syncthreads();
@@ -110,6 +207,7 @@ __device__ bool postprocess(const uint32_t* raw, uint32_t* out, uint32_t* t1, ui
     plane_zero(t1, c);
     __syncthreads();
     keep_area_ge(t1, P.cfg.fill_size, c);
+    LFX_CTX_TICK(c, 3)
     // close = erode(dilate), open = dilate(erode)
     morph_any<true>(t1, t2, P.fp_morph, c);
     __syncthreads();
@@ -120,7 +218,9 @@ __device__ bool postprocess(const uint32_t* raw, uint32_t* out, uint32_t* t1, ui
     morph_any<true>(t2, t1, P.fp_morph, c);
     __syncthreads();
     // t1 = opened
+    LFX_CTX_TICK(c, 4)
     const bool found = largest_external(t1, t2, out, info8, c);
+    LFX_CTX_TICK(c, 5)
     if (!found) {
         plane_copy(out, t1, c);
         __syncthreads();
@@ -301,6 +401,7 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
                 morph_any<true>(T1, T2, P.fp_search, c);
                 __syncthreads();
             }
+            LFX_CTX_TICK(c, 6)
             int any = 0;
             for (int i = threadIdx.x; i < c.NW; i += MT) {
                 const uint32_t v = PB[i] & T2[i];
@@ -321,13 +422,16 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
             any = 0;
             for (int i = threadIdx.x; i < c.NW; i += MT) any |= (T1[i] != 0u);   // own words only: no barrier needed yet
             if (!__syncthreads_or(any)) return;
+            LFX_CTX_TICK(c, 7)
             ccl<8>(T1, c);
             measure_area(c);
             plane_copy(T3, PR, c);  // ext = best | filtered brown
             __syncthreads();
             keep_area_ge(T3, P.cfg.brown_min_area_px, c);
+            LFX_CTX_TICK(c, 8)
             // contour of the extended mask; the returned mask is the UNFILLED union
             const bool f2 = largest_external(T3, T1, T2, s_info2, c);
+            LFX_CTX_TICK(c, 9)
             if (f2) {
                 plane_copy(PR, T3, c);
                 if (threadIdx.x < 8) s_info[threadIdx.x] = s_info2[threadIdx.x];

@@ -19,6 +19,7 @@ struct FootRow {
 };
 struct Footprint {
     int n;
+    int cross3;  // 1 when this is the 3x3 cross (set by make_ellipse): morph_cross3 fast path
     FootRow r[20];
 };
 
@@ -54,6 +55,8 @@ template <class G>
 struct CtxT : G {
     uint32_t* plane[NPLANES];
     int* wbase;
+    int* wbase2;  // second per-word base table (background runs of ccl2); nullptr = ccl2 unavailable
+    int R1;       // ccl2: number of foreground runs (ids [0,R1) foreground, [R1,R) background)
     // run tables (current selection) + both backing stores
     int* parent;
     uint32_t* geom;
@@ -73,7 +76,17 @@ struct CtxT : G {
     int* s_hist;                 // [256]
     int status;
     uint32_t* hp[6];     // scratch planes for dilate_ellipse20 (nullptr = use the generic morph)
+    unsigned long long* tacc;  // debug phase timing (LFX_CORE_TIMING), nullptr otherwise
+    long long tk0;
 };
+
+// debug: add the cycles since the last tick to slot `slot`
+#define LFX_CTX_TICK(c, slot)                                                     \
+    if ((c).tacc && threadIdx.x == 0) {                                           \
+        const long long now_ = clock64();                                         \
+        atomicAdd(&(c).tacc[slot], (unsigned long long)(now_ - (c).tk0));         \
+        (c).tk0 = now_;                                                           \
+    }
 using Ctx = CtxT<DynGeom>;
 
 // word index -> (row, word-in-row) without an integer division when WPR is a power of two
@@ -96,14 +109,25 @@ __device__ __forceinline__ void ctx_init_geometry(Ctx& c, int H, int W, int WPR,
     c.wshift = ((WPR & (WPR - 1)) == 0) ? (31 - __clz(WPR)) : -1;
 #pragma unroll
     for (int k = 0; k < 6; ++k) c.hp[k] = nullptr;
+    c.tacc = nullptr;
+    c.tk0 = 0;
+    c.wbase2 = nullptr;
+    c.R1 = 0;
 }
 template <class C>
 __device__ __forceinline__ void ctx_clear_hp(C& c) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) c.hp[k] = nullptr;
+    c.tacc = nullptr;
+    c.tk0 = 0;
+    c.wbase2 = nullptr;
+    c.R1 = 0;
 }
 
 // ---------------------------------------------------------------- block primitives
+// Exclusive block scan with ONE barrier: warp scans by shuffle, warp totals through s_tmp[0..15], then every
+// warp re-scans the 16 totals itself.  The caller must pass a block barrier before the next call (s_tmp reuse);
+// ccl() does (the barrier after run extraction).
 __device__ int block_exscan(int v, int* s_tmp, int& total) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     int inc = v;
@@ -114,22 +138,16 @@ __device__ int block_exscan(int v, int* s_tmp, int& total) {
     }
     if (lane == 31) s_tmp[wid] = inc;
     __syncthreads();
-    if (wid == 0) {
-        int w = (lane < MT / 32) ? s_tmp[lane] : 0;
-        int winc = w;
+    int w = (lane < MT / 32) ? s_tmp[lane] : 0;
+    int winc = w;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += t;
-        }
-        if (lane < MT / 32) s_tmp[lane] = winc - w;
-        if (lane == 31) s_tmp[32] = winc;
+    for (int o = 1; o < MT / 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
     }
-    __syncthreads();
-    const int res = s_tmp[wid] + inc - v;
-    total = s_tmp[32];
-    __syncthreads();
-    return res;
+    total = __shfl_sync(0xffffffffu, winc, MT / 32 - 1);
+    const int wexc = __shfl_sync(0xffffffffu, winc - w, wid);
+    return wexc + inc - v;
 }
 
 template <class C>
@@ -202,14 +220,14 @@ __device__ void morph_cross3(const uint32_t* in, uint32_t* out, const C& c) {
     }
 }
 
-__device__ __forceinline__ bool is_cross3(const Footprint& fp) {
+static inline bool is_cross3(const Footprint& fp) {
     return fp.n == 3 && fp.r[0].dy == -1 && fp.r[0].o1 == 0 && fp.r[0].o2 == 0 && fp.r[1].dy == 0 && fp.r[1].o1 == -1 &&
            fp.r[1].o2 == 1 && fp.r[2].dy == 1 && fp.r[2].o1 == 0 && fp.r[2].o2 == 0;
 }
 
 template <bool DIL, class C>
 __device__ __forceinline__ void morph_any(const uint32_t* in, uint32_t* out, const Footprint& fp, const C& c) {
-    if (is_cross3(fp))
+    if (fp.cross3)
         morph_cross3<DIL>(in, out, c);
     else
         morph<DIL>(in, out, fp, c);
@@ -309,6 +327,50 @@ __device__ __forceinline__ void uf_unite(int* parent, int a, int b) {
     }
 }
 
+// Flatten the union-find forest so that parent[r] is the root.  Links always point to smaller ids, so one warp
+// can sweep the ids in ascending batches of 32: parents below the batch are already roots (one hop), chains
+// inside the batch shrink by pointer jumping (<= 6 rounds).  For large run tables the whole block does
+// pointer jumping instead (three hops per round; racing reads see ancestors only).  Ends with a block barrier.
+template <class C>
+__device__ void uf_flatten(int total, C& c) {
+    int* parent = c.parent;
+    if (total <= 64) {  // tiny tables only: measured slower than block-wide jumping beyond a couple of batches
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            for (int base = 0; base < total; base += 32) {
+                const int r = base + lane;
+                int p = (r < total) ? parent[r] : 0;
+                for (;;) {
+                    int q = p;
+                    if (r < total) q = parent[p];
+                    const bool moved = (q != p);
+                    if (moved) {
+                        parent[r] = q;
+                        p = q;
+                    }
+                    if (!__any_sync(0xffffffffu, moved)) break;
+                    __syncwarp();
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    for (;;) {
+        int moved = 0;
+        for (int r = threadIdx.x; r < total; r += MT) {
+            const int p1 = parent[r];
+            const int p2 = parent[p1];
+            if (p2 != p1) {
+                parent[r] = parent[p2];
+                moved = 1;
+            }
+        }
+        if (!__syncthreads_or(moved)) break;
+    }
+}
+
 // Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
 // (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
 template <int CONN, class C>
@@ -319,6 +381,7 @@ __device__ void ccl(const uint32_t* m, C& c) {
     for (int i = i0; i < i1; ++i) cnt += __popc(starts_of(m, i, i % c.WPR));
     int total;
     int base = block_exscan(cnt, c.s_tmp, total);
+    const int base0 = base;
     for (int i = i0; i < i1; ++i) {
         c.wbase[i] = base;
         base += __popc(starts_of(m, i, i % c.WPR));
@@ -330,13 +393,15 @@ __device__ void ccl(const uint32_t* m, C& c) {
         c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
         c.status |= 2;
     }
-    __syncthreads();
     int* parent = c.parent;
-    for (int i = threadIdx.x; i < c.NW; i += MT) {
+    // Run extraction on the thread's own contiguous words (same mapping as the count above: each thread
+    // sees a mix of word columns, so speckled borders and clean interiors balance out; ids follow from the
+    // thread's scan base, no barrier needed before this loop).
+    int id = base0;
+    for (int i = i0; i < i1; ++i) {
         int y, w;
         split_index(c, i, y, w);
         uint32_t st = starts_of(m, i, w);
-        int id = c.wbase[i];
         const uint32_t word = m[i];
         while (st) {
             const int b = __ffs(st) - 1;
@@ -396,13 +461,148 @@ __device__ void ccl(const uint32_t* m, C& c) {
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < total; r += MT) {
-        const int root = uf_find(parent, r);
-        // benign race: other threads may still chase through parent[r]; any value on the
-        // path is an ancestor, so their walks still end at the same root
-        parent[r] = root;
+    uf_flatten(total, c);
+}
+
+// ---------------------------------------------------------------- ccl2: foreground + background in one pass
+// word i of the plane (INV = false) or of its complement restricted to the image (INV = true)
+template <bool INV, class C>
+__device__ __forceinline__ uint32_t plane_word(const uint32_t* m, int idx, int w, const C& c) {
+    return INV ? (~m[idx] & valid_mask(c, w)) : m[idx];
+}
+template <bool INV, class C>
+__device__ __forceinline__ uint32_t starts_of2(const uint32_t* m, int idx, int w, const C& c) {
+    const uint32_t cur = plane_word<INV>(m, idx, w, c);
+    const uint32_t pb = (w > 0) ? (plane_word<INV>(m, idx - 1, w - 1, c) >> 31) : 0u;
+    return cur & ~((cur << 1) | pb);
+}
+
+// runs of word i -> tables, ids from `id` upwards; returns the next free id
+template <bool INV, class C>
+__device__ __forceinline__ int extract_runs(const uint32_t* m, int i, int id, C& c) {
+    int y, w;
+    split_index(c, i, y, w);
+    uint32_t st = starts_of2<INV>(m, i, w, c);
+    const uint32_t word = plane_word<INV>(m, i, w, c);
+    while (st) {
+        const int b = __ffs(st) - 1;
+        st &= st - 1;
+        const int x0 = w * 32 + b;
+        const uint32_t inv = ~(word >> b);
+        const int z = __ffs(inv) - 1;  // first zero at/after b (relative); -1 if none
+        int x1;
+        if (inv != 0 && z < 32 - b) {
+            x1 = x0 + z - 1;
+        } else {  // the run reaches bit 31: it may continue in the next words
+            x1 = w * 32 + 31;
+            int ww = w + 1;
+            while (ww < c.WPR) {
+                const uint32_t nx = plane_word<INV>(m, y * c.WPR + ww, ww, c);
+                if (nx == 0xFFFFFFFFu) {
+                    x1 += 32;
+                    ++ww;
+                    continue;
+                }
+                x1 += __ffs(~nx) - 1;
+                break;
+            }
+        }
+        c.geom[id] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        c.ry[id] = (uint16_t)y;
+        c.parent[id] = id;
+        c.acc[id] = 0;
+        ++id;
+    }
+    return id;
+}
+
+// unite run r (row y > 0, columns lo..hi already widened for 8-connectivity) with the runs of the row above
+template <bool INV, class C>
+__device__ __forceinline__ void unite_up(const uint32_t* m, int r, int y, int lo, int hi, const int* wb, int idbase, C& c) {
+    int p = lo;
+    while (p <= hi) {
+        int wi = p >> 5;
+        uint32_t v = plane_word<INV>(m, (y - 1) * c.WPR + wi, wi, c) & (0xFFFFFFFFu << (p & 31));
+        while (v == 0) {
+            ++wi;
+            if (wi * 32 > hi) break;
+            v = plane_word<INV>(m, (y - 1) * c.WPR + wi, wi, c);
+        }
+        if (v == 0) break;
+        const int b = __ffs(v) - 1;
+        if (wi * 32 + b > hi) break;
+        const int idxw = (y - 1) * c.WPR + wi;
+        const uint32_t st = starts_of2<INV>(m, idxw, wi, c);
+        const int id2 = idbase + wb[idxw] + __popc(st & ((2u << b) - 1u)) - 1;
+        uf_unite(c.parent, r, id2);
+        p = (int)(c.geom[id2] >> 16) + 1;
+    }
+}
+
+// id of the foreground run that contains pixel (y, x) of plane m (the pixel must be set); after ccl2
+template <class C>
+__device__ __forceinline__ int fg_run_at(const uint32_t* m, int y, int x, const C& c) {
+    const int wi = x >> 5, idxw = y * c.WPR + wi;
+    const uint32_t st = starts_of2<false>(m, idxw, wi, c);
+    return c.wbase[idxw] + __popc(st & ((2u << (x & 31)) - 1u)) - 1;
+}
+
+// Labels the 8-connected runs of plane m (ids [0, R1)) AND the 4-connected runs of its complement (ids
+// [R1, R)) with one scan / extract / union / flatten sequence -- the two labelings largest_external needs,
+// for the latency of one.  Needs c.wbase2.
+template <class C>
+__device__ void ccl2(const uint32_t* m, C& c) {
+    const int per = (c.NW + MT - 1) / MT;
+    const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
+    int cf = 0, cb = 0;
+    for (int i = i0; i < i1; ++i) {
+        int y, w;
+        split_index(c, i, y, w);
+        cf += __popc(starts_of2<false>(m, i, w, c));
+        cb += __popc(starts_of2<true>(m, i, w, c));
+    }
+    // both counts ride one scan when each total fits 16 bits (<= 16 runs per word and kind)
+    int tot_f, tot_b, bf, bb;
+    if (c.NW <= 2048) {
+        int total;
+        const unsigned base = (unsigned)block_exscan((int)((unsigned)cf | ((unsigned)cb << 16)), c.s_tmp, total);
+        bf = (int)(base & 0xFFFFu); bb = (int)(base >> 16);
+        tot_f = (int)((unsigned)total & 0xFFFFu); tot_b = (int)((unsigned)total >> 16);
+        // a total of exactly 65536 foreground runs cannot happen (NW * 16 <= 32768)
+    } else {
+        bf = block_exscan(cf, c.s_tmp, tot_f);
+        __syncthreads();
+        bb = block_exscan(cb, c.s_tmp, tot_b);
+    }
+    const int R1 = tot_f, total = tot_f + tot_b;
+    c.R1 = R1;
+    c.R = total;
+    if (total <= c.rcap_smem) {
+        c.parent = c.sm_parent; c.geom = c.sm_geom; c.acc = c.sm_acc; c.ry = c.sm_ry;
+    } else {
+        c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
+        c.status |= 2;
+    }
+    int idf = bf, idb = R1 + bb;
+    for (int i = i0; i < i1; ++i) {
+        c.wbase[i] = idf;
+        c.wbase2[i] = idb - R1;
+        idf = extract_runs<false>(m, i, idf, c);
+        idb = extract_runs<true>(m, i, idb, c);
     }
     __syncthreads();
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int y = c.ry[r];
+        if (y == 0) continue;
+        const uint32_t g = c.geom[r];
+        const int x0 = g & 0xFFFF, x1 = g >> 16;
+        if (r < R1)
+            unite_up<false>(m, r, y, max(0, x0 - 1), min(c.W - 1, x1 + 1), c.wbase, 0, c);
+        else
+            unite_up<true>(m, r, y, x0, x1, c.wbase2, R1, c);
+    }
+    __syncthreads();
+    uf_flatten(total, c);
 }
 
 template <class C>
@@ -474,6 +674,7 @@ static inline Footprint make_ellipse(int k) {
         f.r[f.n].pad = 0;
         ++f.n;
     }
+    f.cross3 = is_cross3(f) ? 1 : 0;
     return f;
 }
 
