@@ -100,7 +100,10 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
 // (x86-64 Pillow wheels do not contract to FMA).  A cheap fp32 evaluation decides first; only
 // results that land within LFX_WARP_EPS of a truncation boundary are re-evaluated in fp64, so
 // the output is bit-identical to the fp64 path at a fraction of its cost.
-#define LFX_WARP_EPS 0.03125f
+// fp32 Horner error bound: each of the 3 steps rounds at magnitude < 2048 (half ulp 1.2e-4), row results feed the
+// column evaluation with |weights| summing to < 1.7 -> < 1.1e-3 in total; 2^-8 leaves a 3.5x margin and sends
+// 0.8 % of the values (instead of 6 %) down the fp64 path.
+#define LFX_WARP_EPS 0.00390625f
 
 __device__ __forceinline__ double cubic64(double v1, double v2, double v3, double v4, double d) {
     const double p1 = v2;
@@ -116,104 +119,148 @@ __device__ __forceinline__ float cubic32(float v1, float v2, float v3, float v4,
     return v2 + d * (p2 + d * (p3 + d * p4));
 }
 
-__global__ void __launch_bounds__(THREADS) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
-                                                          int W, const double* __restrict__ coef,
-                                                          const int32_t* __restrict__ persp) {
-    const int img = blockIdx.y;
-    const long long npx = (long long)H * W;
-    const long long q0 = ((long long)blockIdx.x * THREADS + threadIdx.x) * 4;
-    if (q0 >= npx) return;
-    const double* a = coef + img * 8;
-    const double a0 = a[0], a1 = a[1], a2 = a[2], a3 = a[3], a4 = a[4], a5 = a[5], a6 = a[6], a7 = a[7];
-    const bool is_persp = persp[img] != 0;
-    const uint8_t* simg = src + (size_t)img * npx * 3;
-    uint8_t* dimg = dst + (size_t)img * npx * 3;
-    uint8_t out[12];
-    int y = (int)(q0 / W), x = (int)(q0 - (long long)y * W);
-#pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
-        uint8_t res[3] = {0, 0, 0};
-        if ((long long)y * W + x < npx) {
-            const double xc = (double)x + 0.5, yc = (double)y + 0.5;
-            double xin = __dadd_rn(__dadd_rn(__dmul_rn(a0, xc), __dmul_rn(a1, yc)), a2);
-            double yin = __dadd_rn(__dadd_rn(__dmul_rn(a3, xc), __dmul_rn(a4, yc)), a5);
-            if (is_persp) {
-                const double den = __dadd_rn(__dadd_rn(__dmul_rn(a6, xc), __dmul_rn(a7, yc)), 1.0);
-                xin = __ddiv_rn(xin, den);
-                yin = __ddiv_rn(yin, den);
-            }
-            if (!(xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H)) {
-                xin = __dadd_rn(xin, -0.5);
-                yin = __dadd_rn(yin, -0.5);
-                const int xf = (int)floor(xin), yf = (int)floor(yin);
-                const double dx = __dadd_rn(xin, -(double)xf), dy = __dadd_rn(yin, -(double)yf);
-                const int xb = xf - 1, yb = yf - 1;
-                int xo[4];
+// One output pixel of PIL's transform(..., BICUBIC): `rows` points at image row `r0` (global image: r0 = 0;
+// staged band in shared memory: r0 = first staged row); rows outside [0,H) are never dereferenced.
+__device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H, int W, int x, int y, const double* a,
+                                              bool is_persp, uint8_t res[3]) {
+    res[0] = res[1] = res[2] = 0;
+    const double xc = (double)x + 0.5, yc = (double)y + 0.5;
+    double xin = __dadd_rn(__dadd_rn(__dmul_rn(a[0], xc), __dmul_rn(a[1], yc)), a[2]);
+    double yin = __dadd_rn(__dadd_rn(__dmul_rn(a[3], xc), __dmul_rn(a[4], yc)), a[5]);
+    if (is_persp) {
+        const double den = __dadd_rn(__dadd_rn(__dmul_rn(a[6], xc), __dmul_rn(a[7], yc)), 1.0);
+        xin = __ddiv_rn(xin, den);
+        yin = __ddiv_rn(yin, den);
+    }
+    if (xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H) return;
+    xin = __dadd_rn(xin, -0.5);
+    yin = __dadd_rn(yin, -0.5);
+    const int xf = (int)floor(xin), yf = (int)floor(yin);
+    const double dx = __dadd_rn(xin, -(double)xf), dy = __dadd_rn(yin, -(double)yf);
+    const int xb = xf - 1, yb = yf - 1;
+    int xo[4];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) xo[t] = min(max(xb + t, 0), W - 1) * 3;
-                // gather the 4x4x3 taps (row 0 clamped, rows 1..3 reuse the previous row's VALUE
-                // when outside -- Geometry.c BICUBIC_BODY)
-                uint8_t tap[4][4][3];
-                bool rowok[4];
+    for (int t = 0; t < 4; ++t) xo[t] = min(max(xb + t, 0), W - 1) * 3;
+    // gather the 4x4x3 taps (row 0 clamped, rows 1..3 reuse the previous row's VALUE when outside --
+    // Geometry.c BICUBIC_BODY)
+    uint8_t tap[4][4][3];
+    bool rowok[4];
 #pragma unroll
-                for (int rj = 0; rj < 4; ++rj) {
-                    const int yy = yb + rj;
-                    rowok[rj] = (rj == 0) || (yy >= 0 && yy < H);
-                    const int yc2 = min(max(yy, 0), H - 1);
-                    const uint8_t* row = simg + (size_t)yc2 * W * 3;
+    for (int rj = 0; rj < 4; ++rj) {
+        const int yy = yb + rj;
+        rowok[rj] = (rj == 0) || (yy >= 0 && yy < H);
+        const int yc2 = min(max(yy, 0), H - 1);
+        const uint8_t* row = rows + (size_t)(yc2 - r0) * W * 3;
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        tap[rj][t][0] = __ldg(row + xo[t]);
-                        tap[rj][t][1] = __ldg(row + xo[t] + 1);
-                        tap[rj][t][2] = __ldg(row + xo[t] + 2);
-                    }
-                }
-                const float fdx = (float)dx, fdy = (float)dy;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    float rv[4];
-#pragma unroll
-                    for (int rj = 0; rj < 4; ++rj) {
-                        const float v = cubic32(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], fdx);
-                        rv[rj] = rowok[rj] ? v : rv[rj > 0 ? rj - 1 : 0];
-                    }
-                    const float f = cubic32(rv[0], rv[1], rv[2], rv[3], fdy);
-                    const float fr = f - floorf(f);
-                    const bool risky = (fr < LFX_WARP_EPS) || (fr > 1.f - LFX_WARP_EPS) || (f < LFX_WARP_EPS) ||
-                                       (f > 255.f - LFX_WARP_EPS);
-                    if (!risky) {
-                        res[c] = (uint8_t)(int)f;  // 0 < f < 255 here: plain truncation
-                    } else {
-                        double dv[4];
-#pragma unroll
-                        for (int rj = 0; rj < 4; ++rj) {
-                            const double v = cubic64(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], dx);
-                            dv[rj] = rowok[rj] ? v : dv[rj > 0 ? rj - 1 : 0];
-                        }
-                        const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
-                        res[c] = v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
-                    }
-                }
-            }
-        }
-        out[k * 3] = res[0];
-        out[k * 3 + 1] = res[1];
-        out[k * 3 + 2] = res[2];
-        if (++x == W) {
-            x = 0;
-            ++y;
+        for (int t = 0; t < 4; ++t) {
+            tap[rj][t][0] = row[xo[t]];
+            tap[rj][t][1] = row[xo[t] + 1];
+            tap[rj][t][2] = row[xo[t] + 2];
         }
     }
-    const long long rem = npx - q0;
-    uint8_t* d = dimg + q0 * 3;
-    if (rem >= 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
-        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
-    } else {
-        const int nb = (int)min(rem, 4ll) * 3;
-        for (int i = 0; i < nb; ++i) d[i] = out[i];
+    const float fdx = (float)dx, fdy = (float)dy;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        float rv[4];
+#pragma unroll
+        for (int rj = 0; rj < 4; ++rj) {
+            const float v = cubic32(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], fdx);
+            rv[rj] = rowok[rj] ? v : rv[rj > 0 ? rj - 1 : 0];
+        }
+        const float f = cubic32(rv[0], rv[1], rv[2], rv[3], fdy);
+        const float fr = f - floorf(f);
+        const bool risky = (fr < LFX_WARP_EPS) || (fr > 1.f - LFX_WARP_EPS) || (f < LFX_WARP_EPS) || (f > 255.f - LFX_WARP_EPS);
+        if (!risky) {
+            res[c] = (uint8_t)(int)f;  // 0 < f < 255 here: plain truncation
+        } else {
+            double dv[4];
+#pragma unroll
+            for (int rj = 0; rj < 4; ++rj) {
+                const double v = cubic64(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], dx);
+                dv[rj] = rowok[rj] ? v : dv[rj > 0 ? rj - 1 : 0];
+            }
+            const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
+            res[c] = v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
+        }
+    }
+}
+
+// grid (bands of WB_ROWS output rows, B).  The source rows a band can touch follow from its four corners
+// (the map is affine whenever a6 = a7 = 0, which covers the reference's skew and shear); when they fit in
+// shared memory they are staged with 16-byte loads and the 48 taps per pixel come from shared memory,
+// otherwise (general perspective, very tall source spans) the taps are read from global memory.
+constexpr int WB_ROWS = 32;
+
+__global__ void __launch_bounds__(THREADS) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
+                                                          int W, const double* __restrict__ coef,
+                                                          const int32_t* __restrict__ persp, int max_rows) {
+    extern __shared__ __align__(16) uint8_t s_rows[];
+    const int img = blockIdx.y;
+    const int y0 = blockIdx.x * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
+    const double* ap = coef + img * 8;
+    double a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = ap[i];
+    const bool affine = (a[6] == 0.0 && a[7] == 0.0);
+    const bool is_persp = (persp[img] != 0) && !affine;   // x / 1.0 == x exactly: the divide is skipped
+    const size_t npx = (size_t)H * W;
+    const uint8_t* simg = src + (size_t)img * npx * 3;
+    uint8_t* dimg = dst + (size_t)img * npx * 3;
+    // source row span of the band (affine): yin is linear, extremes at the corner pixel centres
+    int r0 = 0, r1 = H - 1;
+    bool staged = false;
+    if (affine) {
+        const double xs[2] = {0.5, (double)W - 0.5}, ys[2] = {(double)y0 + 0.5, (double)y1 - 0.5};
+        double lo = 1e300, hi = -1e300;
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                const double v = a[3] * xs[i] + a[4] * ys[j] + a[5];
+                lo = fmin(lo, v);
+                hi = fmax(hi, v);
+            }
+        // taps use rows floor(yin - 0.5) - 1 .. + 2; one more row of slack for the fused-vs-separate rounding above
+        const double lof = fmax(lo - 3.5, 0.0), hif = fmin(hi + 3.5, (double)(H - 1));
+        r0 = (int)lof;
+        r1 = max(r0, (int)hif);
+        staged = (r1 - r0 + 1) <= max_rows;
+    }
+    if (staged) {
+        block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
+        __syncthreads();
+    }
+    const uint8_t* rows = staged ? s_rows : simg;
+    const int rbase = staged ? r0 : 0;
+    const int band_px = (y1 - y0) * W;
+    for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
+        uint8_t out[12];
+        int y = y0 + q / W, x = q - (q / W) * W;
+        const int n = min(4, band_px - q);
+#pragma unroll 1
+        for (int k = 0; k < 4; ++k) {
+            uint8_t res[3] = {0, 0, 0};
+            if (k < n) {
+                if (staged)
+                    bicubic_pixel(s_rows, rbase, H, W, x, y, a, is_persp, res);
+                else
+                    bicubic_pixel(rows, rbase, H, W, x, y, a, is_persp, res);
+            }
+            out[k * 3] = res[0];
+            out[k * 3 + 1] = res[1];
+            out[k * 3 + 2] = res[2];
+            if (++x == W) {
+                x = 0;
+                ++y;
+            }
+        }
+        uint8_t* d = dimg + ((size_t)y0 * W + q) * 3;
+        if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+            uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+            d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+            d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+            d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+        } else {
+            for (int i = 0; i < n * 3; ++i) d[i] = out[i];
+        }
     }
 }
 
@@ -287,6 +334,120 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos(const uint8_t* __restr
         const size_t di = ((size_t)oy * OW + c0) * 3 + o;
         dimg[di] = v;
         if (fimg) fimg[di] = (float)v / 255.0f;
+    }
+}
+
+
+// ---- strip version: a block owns LZ_TO output rows of one image at FULL width.  Horizontal pass for the
+// crop rows the strip needs (one output column per thread walking down the rows, its <= 8 taps in
+// registers) -> u8 intermediate in shared memory (Pillow's ImagingResampleHorizontal_8bpc result), vertical
+// pass on 4 output bytes per thread (32-bit shared loads, row coefficients broadcast from shared memory),
+// 32-bit / 128-bit coalesced stores.  Needs OW % 4 == 0.
+constexpr int LZ_TO = 32;
+
+template <int KMAX>
+__global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                                float* __restrict__ dstf, int H, int W,
+                                                                const int32_t* __restrict__ box, int OH, int OW,
+                                                                const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
+                                                                int kstride, const int32_t* __restrict__ toff, int mrows_cap) {
+    extern __shared__ __align__(16) uint8_t sm_lz[];
+    const int OWB = OW * 3;
+    uint8_t* s_mid = sm_lz;                                                               // [mrows_cap][OWB]
+    int32_t* s_yk = reinterpret_cast<int32_t*>(sm_lz + (((size_t)mrows_cap * OWB + 15) & ~(size_t)15));  // [LZ_TO][kstride]
+    int32_t* s_yb = s_yk + LZ_TO * kstride;                                               // [LZ_TO][2]
+    const int img = blockIdx.y;
+    const int o0 = blockIdx.x * LZ_TO;
+    const int nrow = min(LZ_TO, OH - o0);
+    const int left = box[img * 4], top = box[img * 4 + 1], cw = box[img * 4 + 2], ch = box[img * 4 + 3];
+    const int32_t* xb = tb + (size_t)toff[img * 4 + 0] * 2;
+    const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
+    const int32_t* yb = tb + (size_t)toff[img * 4 + 2] * 2;
+    const int32_t* yk = tk + (size_t)toff[img * 4 + 2] * kstride;
+    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const bool need_h = (cw != OW), need_v = (ch != OH);
+    // crop rows this strip reads
+    int m0, m1;
+    if (need_v) {
+        m0 = yb[o0 * 2];
+        m1 = yb[(o0 + nrow - 1) * 2] + yb[(o0 + nrow - 1) * 2 + 1];
+        for (int i = threadIdx.x; i < nrow * kstride; i += THREADS) s_yk[i] = yk[(size_t)o0 * kstride + i];
+        for (int i = threadIdx.x; i < nrow * 2; i += THREADS) s_yb[i] = yb[o0 * 2 + i];
+    } else {
+        m0 = o0;
+        m1 = o0 + nrow;
+    }
+    const int mrows = m1 - m0;   // <= mrows_cap by construction of the launch
+    // ---- horizontal pass
+    for (int oc = threadIdx.x; oc < OW; oc += THREADS) {
+        uint8_t* o = s_mid + oc * 3;
+        if (need_h) {
+            const int xmin = xb[oc * 2], cnt = xb[oc * 2 + 1];
+            int kreg[KMAX];
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) kreg[t] = (t < cnt) ? xk[(size_t)oc * kstride + t] : 0;
+            const uint8_t* px = simg + ((size_t)(top + m0) * W + left + xmin) * 3;
+            // taps beyond cnt have weight 0; clamp their address to the last valid tap so no byte outside the image is read
+            int toff3[KMAX];
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) toff3[t] = min(t, cnt - 1) * 3;
+            for (int r = 0; r < mrows; ++r, px += (size_t)W * 3, o += OWB) {
+                int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
+#pragma unroll
+                for (int t = 0; t < KMAX; ++t) {
+                    s0 += __ldg(px + toff3[t]) * kreg[t];
+                    s1 += __ldg(px + toff3[t] + 1) * kreg[t];
+                    s2 += __ldg(px + toff3[t] + 2) * kreg[t];
+                }
+                o[0] = clip8(s0 >> 22);
+                o[1] = clip8(s1 >> 22);
+                o[2] = clip8(s2 >> 22);
+            }
+        } else {
+            const uint8_t* px = simg + ((size_t)(top + m0) * W + left + oc) * 3;
+            for (int r = 0; r < mrows; ++r, px += (size_t)W * 3, o += OWB) {
+                o[0] = __ldg(px);
+                o[1] = __ldg(px + 1);
+                o[2] = __ldg(px + 2);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- vertical pass: 4 bytes per thread
+    const int wpr = OWB >> 2;
+    uint8_t* dimg = dst + ((size_t)img * OH + o0) * OWB;
+    float* fimg = dstf ? dstf + ((size_t)img * OH + o0) * OWB : nullptr;
+    const uint32_t* mid32 = reinterpret_cast<const uint32_t*>(s_mid);
+    for (int i = threadIdx.x; i < nrow * wpr; i += THREADS) {
+        const int r = i / wpr, j4 = i - r * wpr;
+        uint32_t outw;
+        if (need_v) {
+            const int ymin = s_yb[r * 2] - m0, cnt = s_yb[r * 2 + 1];
+            const int32_t* k = s_yk + r * kstride;
+            int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21, s3 = 1 << 21;
+            const uint32_t* p = mid32 + (size_t)ymin * wpr + j4;
+            for (int t = 0; t < cnt; ++t, p += wpr) {
+                const uint32_t w = *p;
+                const int kv = k[t];
+                s0 += (int)(w & 0xFFu) * kv;
+                s1 += (int)((w >> 8) & 0xFFu) * kv;
+                s2 += (int)((w >> 16) & 0xFFu) * kv;
+                s3 += (int)(w >> 24) * kv;
+            }
+            outw = (uint32_t)clip8(s0 >> 22) | ((uint32_t)clip8(s1 >> 22) << 8) | ((uint32_t)clip8(s2 >> 22) << 16) |
+                   ((uint32_t)clip8(s3 >> 22) << 24);
+        } else {
+            outw = mid32[(size_t)r * wpr + j4];
+        }
+        reinterpret_cast<uint32_t*>(dimg)[(size_t)r * wpr + j4] = outw;
+        if (fimg) {
+            float4 f;
+            f.x = (float)(outw & 0xFFu) / 255.0f;
+            f.y = (float)((outw >> 8) & 0xFFu) / 255.0f;
+            f.z = (float)((outw >> 16) & 0xFFu) / 255.0f;
+            f.w = (float)(outw >> 24) / 255.0f;
+            reinterpret_cast<float4*>(fimg)[(size_t)r * wpr + j4] = f;
+        }
     }
 }
 
@@ -489,8 +650,18 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "warp_bicubic: bad arguments");
     if (B == 0) return LFX_OK;
-    dim3 grid(lfx_div_up((long long)H * W, THREADS * 4), B);
-    k_warp_bicubic<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective);
+    // shared-memory band of source rows: up to ~100 KB so that two blocks share an SM
+    const int rb = W * 3;
+    const int max_rows = (100 * 1024) / rb;
+    const size_t smem = max_rows >= 8 ? (size_t)max_rows * rb : 0;
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_bicubic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "warp_bicubic smem attr: %s", cudaGetErrorString(e));
+        attr = smem;
+    }
+    dim3 grid(lfx_div_up(H, WB_ROWS), B);
+    k_warp_bicubic<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem ? max_rows : 0);
     return lfx_check_launch("warp_bicubic");
 }
 
@@ -502,6 +673,30 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
     LFX_REQUIRE(src && dst && box && tab_bounds && tab_kk && tab_off && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 &&
                     kstride > 0 && B <= 65535,
                 LFX_ERR_ARG, "crop_lanczos: bad arguments");
+    // strip kernel: full-width row strips, taps in registers (every upscale and mild downscale: <= 8 taps per axis)
+    {
+        const int mrows_cap = (int)(((long long)LZ_TO * H + OH - 1) / OH) + kstride + 2;   // crop_h <= H
+        const size_t smem2 = (((size_t)mrows_cap * OW * 3 + 15) & ~(size_t)15) + (size_t)LZ_TO * kstride * 4 + LZ_TO * 8;
+        const bool ok = (OW % 4 == 0) && kstride <= 16 && smem2 <= 200 * 1024 &&
+                        ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) && (!dst_f32 || (reinterpret_cast<uintptr_t>(dst_f32) & 15) == 0);
+        if (ok) {
+            static size_t attr2[2] = {0, 0};
+            const int wide = kstride > 8;
+            const void* fn = wide ? (const void*)k_crop_lanczos_strip<16> : (const void*)k_crop_lanczos_strip<8>;
+            if (smem2 > 48 * 1024 && smem2 > attr2[wide]) {
+                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                attr2[wide] = smem2;
+            }
+            dim3 grid2(lfx_div_up(OH, LZ_TO), B);
+            if (wide)
+                k_crop_lanczos_strip<16><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds,
+                                                                                     tab_kk, kstride, tab_off, mrows_cap);
+            else
+                k_crop_lanczos_strip<8><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds,
+                                                                                    tab_kk, kstride, tab_off, mrows_cap);
+            return lfx_check_launch("crop_lanczos(strip)");
+        }
+    }
     const size_t smem = (size_t)H * LZ_TW * 3;
     LFX_REQUIRE(smem <= 200 * 1024, LFX_ERR_UNSUPPORTED, "crop_lanczos: H > %d unsupported", 200 * 1024 / (LZ_TW * 3));
     if (B == 0) return LFX_OK;
