@@ -112,6 +112,13 @@ __device__ __forceinline__ double cubic64(double v1, double v2, double v3, doubl
     const double p4 = __dadd_rn(__dadd_rn(__dadd_rn(-v1, v2), -v3), v4);
     return __dadd_rn(p1, __dmul_rn(d, __dadd_rn(p2, __dmul_rn(d, __dadd_rn(p3, __dmul_rn(d, p4))))));
 }
+// cubic32 on inputs carrying a 2^23 bias (integers 0..255): differences are exact, the bias cancels
+__device__ __forceinline__ float cubic32b(float v1, float v2, float v3, float v4, float d) {
+    const float p2 = v3 - v1;
+    const float p3 = 2.f * (v1 - v2) + v3 - v4;
+    const float p4 = -v1 + v2 - v3 + v4;
+    return (v2 - 8388608.f) + d * (p2 + d * (p3 + d * p4));
+}
 __device__ __forceinline__ float cubic32(float v1, float v2, float v3, float v4, float d) {
     const float p2 = v3 - v1;
     const float p3 = 2.f * (v1 - v2) + v3 - v4;
@@ -141,30 +148,30 @@ __device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H
     int xo[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xo[t] = min(max(xb + t, 0), W - 1) * 3;
-    // gather the 4x4x3 taps (row 0 clamped, rows 1..3 reuse the previous row's VALUE when outside --
-    // Geometry.c BICUBIC_BODY)
-    uint8_t tap[4][4][3];
+    // rows 1..3 of the 4x4 window reuse the previous row's VALUE when outside the image (Geometry.c BICUBIC_BODY)
+    const uint8_t* rowp[4];
     bool rowok[4];
 #pragma unroll
     for (int rj = 0; rj < 4; ++rj) {
         const int yy = yb + rj;
         rowok[rj] = (rj == 0) || (yy >= 0 && yy < H);
-        const int yc2 = min(max(yy, 0), H - 1);
-        const uint8_t* row = rows + (size_t)(yc2 - r0) * W * 3;
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            tap[rj][t][0] = row[xo[t]];
-            tap[rj][t][1] = row[xo[t] + 1];
-            tap[rj][t][2] = row[xo[t] + 2];
-        }
+        rowp[rj] = rows + (size_t)(min(max(yy, 0), H - 1) - r0) * W * 3;
     }
     const float fdx = (float)dx, fdy = (float)dy;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        // taps as 2^23 + v (0x4B000000 | byte: a LOP3, not a conversion on the quarter-rate XU pipe); every
+        // difference in cubic32b is exact with the bias cancelling, only the leading v2 is un-biased
+        uint8_t tap[4][4];
+#pragma unroll
+        for (int rj = 0; rj < 4; ++rj)
+#pragma unroll
+            for (int t = 0; t < 4; ++t) tap[rj][t] = rowp[rj][xo[t] + c];
         float rv[4];
 #pragma unroll
         for (int rj = 0; rj < 4; ++rj) {
-            const float v = cubic32(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], fdx);
+            const float v = cubic32b(__uint_as_float(0x4B000000u | tap[rj][0]), __uint_as_float(0x4B000000u | tap[rj][1]),
+                                     __uint_as_float(0x4B000000u | tap[rj][2]), __uint_as_float(0x4B000000u | tap[rj][3]), fdx);
             rv[rj] = rowok[rj] ? v : rv[rj > 0 ? rj - 1 : 0];
         }
         const float f = cubic32(rv[0], rv[1], rv[2], rv[3], fdy);
@@ -176,7 +183,7 @@ __device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H
             double dv[4];
 #pragma unroll
             for (int rj = 0; rj < 4; ++rj) {
-                const double v = cubic64(tap[rj][0][c], tap[rj][1][c], tap[rj][2][c], tap[rj][3][c], dx);
+                const double v = cubic64(tap[rj][0], tap[rj][1], tap[rj][2], tap[rj][3], dx);
                 dv[rj] = rowok[rj] ? v : dv[rj > 0 ? rj - 1 : 0];
             }
             const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
@@ -191,7 +198,7 @@ __device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H
 // otherwise (general perspective, very tall source spans) the taps are read from global memory.
 constexpr int WB_ROWS = 32;
 
-__global__ void __launch_bounds__(THREADS) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
+__global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
                                                           int W, const double* __restrict__ coef,
                                                           const int32_t* __restrict__ persp, int max_rows) {
     extern __shared__ __align__(16) uint8_t s_rows[];
@@ -356,6 +363,9 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
     uint8_t* s_mid = sm_lz;                                                               // [mrows_cap][OWB]
     int32_t* s_yk = reinterpret_cast<int32_t*>(sm_lz + (((size_t)mrows_cap * OWB + 15) & ~(size_t)15));  // [LZ_TO][kstride]
     int32_t* s_yb = s_yk + LZ_TO * kstride;                                               // [LZ_TO][2]
+    int32_t* s_mis = s_yb + LZ_TO * 2;                                                    // [mrows_cap]
+    const int src_pitch = ((W * 3 + 15) & ~15) + 32;                                      // staged crop row pitch
+    uint8_t* s_src = reinterpret_cast<uint8_t*>(s_mis + ((mrows_cap + 3) & ~3));          // [mrows_cap][src_pitch]
     const int img = blockIdx.y;
     const int o0 = blockIdx.x * LZ_TO;
     const int nrow = min(LZ_TO, OH - o0);
@@ -378,6 +388,28 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
         m1 = o0 + nrow;
     }
     const int mrows = m1 - m0;   // <= mrows_cap by construction of the launch
+    // ---- stage the crop rows (columns left .. left+cw-1) in shared memory: 16-byte loads from the aligned span
+    const int cwb = cw * 3;
+    const size_t g0 = ((size_t)(top + m0) * W + left) * 3;
+    for (int r = threadIdx.x >> 5; r < mrows; r += THREADS / 32) {
+        const uint8_t* g = simg + g0 + (size_t)r * W * 3;
+        uint8_t* d = s_src + (size_t)r * src_pitch;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);       // d[mis + i] = g[i]: both sides 16-byte aligned
+        const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
+        const int n16 = (mis + cwb + 15) >> 4;
+        const uint8_t* img_end = src + (size_t)gridDim.y * H * W * 3;
+        for (int i = threadIdx.x & 31; i < n16; i += 32) {
+            if (reinterpret_cast<const uint8_t*>(g16 + i + 1) <= img_end)
+                reinterpret_cast<uint4*>(d)[i] = ld_stream16(g16 + i);
+            else
+                for (int b = 0; b < 16; ++b) {
+                    const uint8_t* q = reinterpret_cast<const uint8_t*>(g16 + i) + b;
+                    d[i * 16 + b] = q < img_end ? *q : 0;
+                }
+        }
+        if ((threadIdx.x & 31) == 0) s_mis[r] = mis;
+    }
+    __syncthreads();
     // ---- horizontal pass
     for (int oc = threadIdx.x; oc < OW; oc += THREADS) {
         uint8_t* o = s_mid + oc * 3;
@@ -386,29 +418,29 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
             int kreg[KMAX];
 #pragma unroll
             for (int t = 0; t < KMAX; ++t) kreg[t] = (t < cnt) ? xk[(size_t)oc * kstride + t] : 0;
-            const uint8_t* px = simg + ((size_t)(top + m0) * W + left + xmin) * 3;
-            // taps beyond cnt have weight 0; clamp their address to the last valid tap so no byte outside the image is read
+            // taps beyond cnt have weight 0; clamp their offset to the last valid tap so nothing outside the staged span is read
             int toff3[KMAX];
 #pragma unroll
-            for (int t = 0; t < KMAX; ++t) toff3[t] = min(t, cnt - 1) * 3;
-            for (int r = 0; r < mrows; ++r, px += (size_t)W * 3, o += OWB) {
+            for (int t = 0; t < KMAX; ++t) toff3[t] = (xmin + min(t, cnt - 1)) * 3;
+            for (int r = 0; r < mrows; ++r, o += OWB) {
+                const uint8_t* px = s_src + (size_t)r * src_pitch + s_mis[r];
                 int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21;
 #pragma unroll
                 for (int t = 0; t < KMAX; ++t) {
-                    s0 += __ldg(px + toff3[t]) * kreg[t];
-                    s1 += __ldg(px + toff3[t] + 1) * kreg[t];
-                    s2 += __ldg(px + toff3[t] + 2) * kreg[t];
+                    s0 += px[toff3[t]] * kreg[t];
+                    s1 += px[toff3[t] + 1] * kreg[t];
+                    s2 += px[toff3[t] + 2] * kreg[t];
                 }
                 o[0] = clip8(s0 >> 22);
                 o[1] = clip8(s1 >> 22);
                 o[2] = clip8(s2 >> 22);
             }
         } else {
-            const uint8_t* px = simg + ((size_t)(top + m0) * W + left + oc) * 3;
-            for (int r = 0; r < mrows; ++r, px += (size_t)W * 3, o += OWB) {
-                o[0] = __ldg(px);
-                o[1] = __ldg(px + 1);
-                o[2] = __ldg(px + 2);
+            for (int r = 0; r < mrows; ++r, o += OWB) {
+                const uint8_t* px = s_src + (size_t)r * src_pitch + s_mis[r] + oc * 3;
+                o[0] = px[0];
+                o[1] = px[1];
+                o[2] = px[2];
             }
         }
     }
@@ -418,21 +450,28 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
     uint8_t* dimg = dst + ((size_t)img * OH + o0) * OWB;
     float* fimg = dstf ? dstf + ((size_t)img * OH + o0) * OWB : nullptr;
     const uint32_t* mid32 = reinterpret_cast<const uint32_t*>(s_mid);
-    for (int i = threadIdx.x; i < nrow * wpr; i += THREADS) {
-        const int r = i / wpr, j4 = i - r * wpr;
+    int r = 0, j4 = threadIdx.x;
+    for (int i = threadIdx.x; i < nrow * wpr; i += THREADS, j4 += THREADS) {
+        while (j4 >= wpr) {
+            j4 -= wpr;
+            ++r;
+        }
         uint32_t outw;
         if (need_v) {
             const int ymin = s_yb[r * 2] - m0, cnt = s_yb[r * 2 + 1];
             const int32_t* k = s_yk + r * kstride;
             int s0 = 1 << 21, s1 = 1 << 21, s2 = 1 << 21, s3 = 1 << 21;
             const uint32_t* p = mid32 + (size_t)ymin * wpr + j4;
-            for (int t = 0; t < cnt; ++t, p += wpr) {
-                const uint32_t w = *p;
-                const int kv = k[t];
-                s0 += (int)(w & 0xFFu) * kv;
-                s1 += (int)((w >> 8) & 0xFFu) * kv;
-                s2 += (int)((w >> 16) & 0xFFu) * kv;
-                s3 += (int)(w >> 24) * kv;
+#pragma unroll
+            for (int t = 0; t < KMAX; ++t) {
+                if (t < cnt) {
+                    const uint32_t w = p[t * wpr];
+                    const int kv = k[t];
+                    s0 += (int)(w & 0xFFu) * kv;
+                    s1 += (int)((w >> 8) & 0xFFu) * kv;
+                    s2 += (int)((w >> 16) & 0xFFu) * kv;
+                    s3 += (int)(w >> 24) * kv;
+                }
             }
             outw = (uint32_t)clip8(s0 >> 22) | ((uint32_t)clip8(s1 >> 22) << 8) | ((uint32_t)clip8(s2 >> 22) << 16) |
                    ((uint32_t)clip8(s3 >> 22) << 24);
@@ -650,9 +689,9 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "warp_bicubic: bad arguments");
     if (B == 0) return LFX_OK;
-    // shared-memory band of source rows: up to ~100 KB so that two blocks share an SM
+    // shared-memory band of source rows: up to 72 KB so that three blocks share an SM
     const int rb = W * 3;
-    const int max_rows = (100 * 1024) / rb;
+    const int max_rows = (72 * 1024) / rb;   // three blocks per SM
     const size_t smem = max_rows >= 8 ? (size_t)max_rows * rb : 0;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
@@ -676,7 +715,8 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
     // strip kernel: full-width row strips, taps in registers (every upscale and mild downscale: <= 8 taps per axis)
     {
         const int mrows_cap = (int)(((long long)LZ_TO * H + OH - 1) / OH) + kstride + 2;   // crop_h <= H
-        const size_t smem2 = (((size_t)mrows_cap * OW * 3 + 15) & ~(size_t)15) + (size_t)LZ_TO * kstride * 4 + LZ_TO * 8;
+        const size_t smem2 = (((size_t)mrows_cap * OW * 3 + 15) & ~(size_t)15) + (size_t)LZ_TO * kstride * 4 + LZ_TO * 8 +
+                             (size_t)((mrows_cap + 3) & ~3) * 4 + (size_t)mrows_cap * (((W * 3 + 15) & ~15) + 32);
         const bool ok = (OW % 4 == 0) && kstride <= 16 && smem2 <= 200 * 1024 &&
                         ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) && (!dst_f32 || (reinterpret_cast<uintptr_t>(dst_f32) & 15) == 0);
         if (ok) {

@@ -41,10 +41,13 @@ def _chk_img(x: torch.Tensor, ch: Optional[int] = 3):
 
 
 def _dev(a, dtype, device):
-    return torch.as_tensor(np.ascontiguousarray(a, dtype=dtype)).to(device, non_blocking=True)
+    """Host array / list -> device tensor; a tensor already on the device passes through (hot loops
+    pre-upload their per-image parameters once)."""
+    if isinstance(a, torch.Tensor) and a.device == device:
+        return a
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device)
 
 
-# --------------------------------------------------------------------------- colour / masks
 def cvt_color(x: torch.Tensor, code: str) -> torch.Tensor:
     """cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}); code in {'gray','hsv','lab'}."""
     _chk_img(x)
@@ -295,8 +298,8 @@ def warp_bicubic(x: torch.Tensor, coeffs: np.ndarray, perspective: Sequence[bool
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
-    dc = _dev(np.asarray(coeffs, np.float64).reshape(B, 8), np.float64, x.device)
-    dpz = _dev([1 if p else 0 for p in perspective], np.int32, x.device)
+    dc = coeffs if isinstance(coeffs, torch.Tensor) else _dev(np.asarray(coeffs, np.float64).reshape(B, 8), np.float64, x.device)
+    dpz = perspective if isinstance(perspective, torch.Tensor) else _dev([1 if p else 0 for p in perspective], np.int32, x.device)
     out = torch.empty_like(x)
     _lib.check(lib.lfx_warp_bicubic(_p(x), _p(out), B, H, W, _p(dc), _p(dpz), _stream()))
     return out
@@ -349,25 +352,37 @@ class LanczosTables:
 _lanczos = LanczosTables()
 
 
-def crop_lanczos(x: torch.Tensor, boxes: np.ndarray, out_hw: Tuple[int, int], want_f32: bool = False):
-    """img.crop(box).resize((OW,OH), LANCZOS) per image; boxes[B][4] = left, top, w, h."""
+class CropPlan:
+    """Device-side parameters of one crop_lanczos batch (boxes, table offsets), built once and reusable."""
+
+    def __init__(self, boxes: np.ndarray, out_hw: Tuple[int, int], device):
+        OH, OW = int(out_hw[0]), int(out_hw[1])
+        boxes = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
+        off = np.zeros((len(boxes), 4), np.int32)
+        for i in range(len(boxes)):
+            xr, xk = _lanczos.get(boxes[i, 2], OW)
+            yr, yk = _lanczos.get(boxes[i, 3], OH)
+            off[i] = (xr, xk, yr, yk)
+        self.out_hw = (OH, OW)
+        self.tb, self.tk = _lanczos.device(device)
+        self.kstride = _lanczos.kstride
+        self.box = _dev(boxes, np.int32, device)
+        self.off = _dev(off, np.int32, device)
+
+
+def crop_lanczos(x: torch.Tensor, boxes, out_hw: Tuple[int, int] = None, want_f32: bool = False, out=None, outf=None):
+    """img.crop(box).resize((OW,OH), LANCZOS) per image; boxes[B][4] = left, top, w, h (or a prebuilt CropPlan)."""
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
-    OH, OW = int(out_hw[0]), int(out_hw[1])
-    boxes = np.ascontiguousarray(boxes, np.int32).reshape(B, 4)
-    off = np.zeros((B, 4), np.int32)
-    for i in range(B):
-        xr, xk = _lanczos.get(boxes[i, 2], OW)
-        yr, yk = _lanczos.get(boxes[i, 3], OH)
-        off[i] = (xr, xk, yr, yk)
-    tb, tk = _lanczos.device(x.device)
-    out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
-    outf = torch.empty((B, OH, OW, 3), dtype=torch.float32, device=x.device) if want_f32 else None
-    dbox = _dev(boxes, np.int32, x.device)   # keep both alive until the launch is enqueued
-    doff = _dev(off, np.int32, x.device)
-    _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf), B, H, W, _p(dbox), OH, OW,
-                                    _p(tb), _p(tk), _lanczos.kstride, _p(doff), _stream()))
+    plan = boxes if isinstance(boxes, CropPlan) else CropPlan(boxes, out_hw, x.device)
+    OH, OW = plan.out_hw
+    if out is None:
+        out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
+    if want_f32 and outf is None:
+        outf = torch.empty((B, OH, OW, 3), dtype=torch.float32, device=x.device)
+    _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf) if want_f32 else None, B, H, W, _p(plan.box), OH, OW,
+                                    _p(plan.tb), _p(plan.tk), plan.kstride, _p(plan.off), _stream()))
     return (out, outf) if want_f32 else out
 
 

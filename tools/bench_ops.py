@@ -82,7 +82,10 @@ def main():
         res["brown_spots(1024 img)"] = {"ms": round(t, 4), "images_per_s": round(nsub / (t / 1e3))}
 
     # ---- augmentations (parameters drawn like the reference)
-    add("flip", lambda: ops.flip(x, [True] * B), 6 * N)
+    dmode = torch.zeros(B, dtype=torch.int32, device=dev)
+    fout = torch.empty_like(x)
+    lib = ops._lib.load()
+    add("flip", lambda: ops._lib.check(lib.lfx_flip(ops._p(x), ops._p(fout), B, S, S, ops._p(dmode), ops._stream())), 6 * N)
     angles = [rng.uniform(-30, 30) for _ in range(B)]
     params = np.zeros((B, 8), np.int32)
     out_px = 0
@@ -91,9 +94,15 @@ def main():
         params[i, :6] = augment.fixed_affine(m)
         params[i, 6:] = (nw, nh)
         out_px += nw * nh
-    add("rotate_nn", lambda: ops.rotate_nn(x, params), 3 * N + 3 * out_px / B)
+    add("rotate_nn (incl. host param upload)", lambda: ops.rotate_nn(x, params), 3 * N + 3 * out_px / B)
     coeffs = np.array([[1 + s, 0, -s * S, 0, 1 + s, -s * S, 0, 0] for s in (rng.uniform(0.05, 0.15) for _ in range(B))])
-    add("warp_bicubic_skew", lambda: ops.warp_bicubic(x, coeffs, [True] * B), 6 * N)
+    dco = torch.from_numpy(coeffs).to(dev)
+    dpe = torch.ones(B, dtype=torch.int32, device=dev)
+    add("warp_bicubic_skew", lambda: ops.warp_bicubic(x, dco, dpe), 6 * N)
+    sh = np.array([[1, k, 0, 0, 1, 0, 0, 0] if rng.random() < 0.5 else [1, 0, 0, k, 1, 0, 0, 0] for k in (rng.uniform(-0.2, 0.2) for _ in range(B))], np.float64)
+    dsh = torch.from_numpy(sh).to(dev)
+    dpa = torch.zeros(B, dtype=torch.int32, device=dev)
+    add("warp_bicubic_shear", lambda: ops.warp_bicubic(x, dsh, dpa), 6 * N)
     boxes = np.zeros((B, 4), np.int32)
     crop_px = 0
     for i in range(B):
@@ -101,8 +110,13 @@ def main():
         nw, nh = int(S * r), int(S * r)
         boxes[i] = (rng.randint(0, S - nw), rng.randint(0, S - nh), nw, nh)
         crop_px += nw * nh
-    add("crop_lanczos", lambda: ops.crop_lanczos(x, boxes, (S, S)), 3 * crop_px / B + 3 * N)
-    add("resize224_normalize", lambda: ops.crop_lanczos(x, np.tile(np.array([0, 0, S, S], np.int32), (B, 1)), (224, 224), want_f32=True),
+    plan = ops.CropPlan(boxes, (S, S), dev)
+    cout = torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev)
+    add("crop_lanczos", lambda: ops.crop_lanczos(x, plan, out=cout), 3 * crop_px / B + 3 * N)
+    plan224 = ops.CropPlan(np.tile(np.array([0, 0, S, S], np.int32), (B, 1)), (224, 224), dev)
+    o8 = torch.empty((B, 224, 224, 3), dtype=torch.uint8, device=dev)
+    of = torch.empty((B, 224, 224, 3), dtype=torch.float32, device=dev)
+    add("resize224_normalize", lambda: ops.crop_lanczos(x, plan224, want_f32=True, out=o8, outf=of),
         3 * N + 224 * 224 * 3 + 224 * 224 * 3 * 4)
     noise = torch.randint(0, 256, x.shape, dtype=torch.uint8, device=dev)
     cuts = [int(N * rng.uniform(0, 2) // 100) for _ in range(B)]
