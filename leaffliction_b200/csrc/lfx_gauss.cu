@@ -3,6 +3,8 @@
 // Shared-memory halo tiles; both passes fused so the intermediate never touches HBM.
 #include "lfx_common.cuh"
 
+int lfx_gauss_tma_try(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, int ksize, const int32_t* taps, cudaStream_t st);
+
 namespace {
 
 constexpr int THREADS = 256;
@@ -183,6 +185,8 @@ extern "C" int lfx_gauss_u8(const uint8_t* src, uint8_t* dst, int B, int H, int 
     const int rc = lfx_gauss_taps(ksize, sigma, k);
     if (rc != LFX_OK) return rc;
     for (int i = 0; i < G_MAXK; ++i) taps.k[i] = i < ksize ? k[i] : 0;
+    // TMA-tiled kernel (lfx_gauss_tma.cu) for 5x5 / 15x15 on 16-byte rows; everything else below
+    if (lfx_gauss_tma_try(src, dst, B, H, W, C, ksize, k, (cudaStream_t)stream) == 0) return lfx_check_launch("gauss_u8(tma)");
     // fast path: 32-bit aligned rows, the two kernel sizes the reference uses (blur.py:61,72; mask.py:770)
     const bool aligned = ((W * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) % 4 == 0) &&
                          W > ksize && lfx_div_up(H, 32) <= 65535;

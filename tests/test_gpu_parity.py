@@ -110,6 +110,24 @@ def test_gauss(dev, hw, ks):
     assert np.array_equal(got[0], sf.gaussian_blur_u8(gray[0], k, s))
 
 
+# TMA-tiled blur (rows that are a multiple of 16 bytes): sizes that cross tile borders, tall / wide / tiny images
+@pytest.mark.parametrize("hw", [(256, 256), (64, 64), (100, 48), (17, 32), (300, 128), (64, 1024), (9, 16)])
+@pytest.mark.parametrize("ks", [(5, 1.5), (15, 0.0), (5, 0.8)])
+def test_gauss_tma_shapes(dev, hw, ks):
+    rng = np.random.default_rng(hw[0] * 7 + ks[0])
+    k, s = ks
+    img = rng.integers(0, 256, (3, *hw, 3), dtype=np.uint8)
+    img[1] = 255
+    img[1, ::2, ::3] = 0                                   # worst case for the packed 16-bit sums
+    got = ops.gauss_u8(up(img, dev), k, s).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], sf.gaussian_blur_u8(img[i], k, s)), (hw, ks, i)
+    gray = np.ascontiguousarray(img[..., 1])
+    got = ops.gauss_u8(up(gray, dev), k, s).cpu().numpy()
+    for i in range(3):
+        assert np.array_equal(got[i], sf.gaussian_blur_u8(gray[i], k, s)), (hw, ks, i, "gray")
+
+
 # ----------------------------------------------------------------------------- augment
 @pytest.mark.parametrize("hw", SHAPES)
 def test_flip(dev, hw):
