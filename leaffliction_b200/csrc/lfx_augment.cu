@@ -12,6 +12,52 @@ constexpr int THREADS = 256;
 // grid (row chunks, B); a block moves ROWS rows through shared memory and writes them mirrored.
 constexpr int FLIP_SMEM = 32 * 1024;
 
+// Vectorised flip for rows that are a multiple of 16 bytes with W % 4 == 0 (a row is then a whole number of
+// 12-byte groups of 4 pixels).  A block moves FV_ROWS rows: 128-bit coalesced loads into shared memory;
+// FLIP_TOP_BOTTOM just stores them to the mirrored rows, FLIP_LEFT_RIGHT reverses the pixel order of each row
+// on 12-byte groups (3 words in, 4 byte-permutes, 3 words out: P0 P1 P2 P3 -> P3 P2 P1 P0) before the
+// 128-bit stores.  Pure data movement: HBM-bound.
+constexpr int FV_ROWS = 16;
+__global__ void __launch_bounds__(THREADS) k_flip_vec(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
+                                                      const int32_t* __restrict__ mode) {
+    extern __shared__ __align__(16) uint8_t sm[];
+    const int img = blockIdx.y;
+    const int y0 = blockIdx.x * FV_ROWS;
+    const int rows = min(FV_ROWS, H - y0);
+    const int rb = W * 3, rb16 = rb >> 4;
+    const uint4* simg = reinterpret_cast<const uint4*>(src + ((size_t)img * H + y0) * rb);
+    uint8_t* dimg = dst + (size_t)img * H * rb;
+    const int m = mode[img];
+    uint4* s4 = reinterpret_cast<uint4*>(sm);
+    if (m != 0) {  // FLIP_TOP_BOTTOM: no shared memory needed
+        for (int i = threadIdx.x; i < rows * rb16; i += THREADS) {
+            const int y = i / rb16, j = i - y * rb16;
+            st_stream16(dimg + (size_t)(H - 1 - (y0 + y)) * rb + (size_t)j * 16, ld_stream16(simg + i));
+        }
+        return;
+    }
+    for (int i = threadIdx.x; i < rows * rb16; i += THREADS) s4[i] = ld_stream16(simg + i);
+    __syncthreads();
+    uint32_t* s_in = reinterpret_cast<uint32_t*>(sm);
+    uint32_t* s_out = s_in + (size_t)FV_ROWS * (rb >> 2);
+    const int G = W >> 2;  // 12-byte groups per row
+    for (int i = threadIdx.x; i < rows * G; i += THREADS) {
+        const int y = i / G, g = i - y * G;
+        const uint32_t* p = s_in + (size_t)y * (rb >> 2) + 3 * (G - 1 - g);
+        const uint32_t w0 = p[0], w1 = p[1], w2 = p[2];  // R0 G0 B0 R1 | G1 B1 R2 G2 | B2 R3 G3 B3
+        uint32_t* o = s_out + (size_t)y * (rb >> 2) + 3 * g;
+        o[0] = __byte_perm(w2, w1, 0x6321);                                // R3 G3 B3 R2
+        o[1] = __byte_perm(__byte_perm(w1, w2, 0x0043), w0, 0x3710);       // G2 B2 R1 G1
+        o[2] = __byte_perm(w0, w1, 0x2105);                                // B1 R0 G0 B0
+    }
+    __syncthreads();
+    const uint4* o4 = reinterpret_cast<const uint4*>(s_out);
+    uint8_t* drow = dimg + (size_t)y0 * rb;
+    for (int i = threadIdx.x; i < rows * rb16; i += THREADS) st_stream16(drow + (size_t)i * 16, o4[i]);
+}
+
+
+
 __global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
                                                   int rows_per_block, const int32_t* __restrict__ mode) {
     extern __shared__ __align__(16) uint8_t sm[];
@@ -655,9 +701,21 @@ extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, c
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && mode && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG, "flip: bad arguments");
+    const int rb = W * 3;
+    if (rb % 16 == 0 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 &&
+        (size_t)FV_ROWS * rb * 2 <= 96 * 1024) {
+        const size_t smem_v = (size_t)FV_ROWS * rb * 2;
+        static size_t attr_v = 0;
+        if (smem_v > 48 * 1024 && smem_v > attr_v) {
+            cudaFuncSetAttribute(k_flip_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
+            attr_v = smem_v;
+        }
+        dim3 gridv(lfx_div_up(H, FV_ROWS), B);
+        k_flip_vec<<<gridv, THREADS, smem_v, (cudaStream_t)stream>>>(src, dst, H, W, mode);
+        return lfx_check_launch("flip(vec)");
+    }
     LFX_REQUIRE(W * 3 * 2 + 32 <= FLIP_SMEM, LFX_ERR_UNSUPPORTED, "flip: W > %d unsupported", (FLIP_SMEM - 32) / 6);
     if (B == 0) return LFX_OK;
-    const int rb = W * 3;
     int rows = max(1, (FLIP_SMEM - 32) / 2 / rb);
     rows = min(rows, H);
     // keep chunk byte offsets 16-byte aligned when possible (fast vector path)

@@ -118,8 +118,20 @@ __global__ void __launch_bounds__(THREADS) k_apply_mask(const uint8_t* __restric
         block_load_bytes(s_in, src + base * 3, n * 3);
         block_load_bytes(s_m, mask + base, n);
         __syncthreads();
-        for (int i = threadIdx.x; i < n * 3; i += THREADS) {
-            if (!(s_m[i / 3] > 127)) s_in[i] = (uint8_t)color_val;  // mask_utils.py:68,76
+        // 4 pixels per thread: mask bytes > 127 -> 0xFF selectors (bit 7), spread over the 12 RGB bytes
+        const uint32_t c32 = (uint32_t)color_val * 0x01010101u;
+        const int n4 = n >> 2;
+        for (int t = threadIdx.x; t < n4; t += THREADS) {
+            const uint32_t m = reinterpret_cast<const uint32_t*>(s_m)[t];
+            const uint32_t k = ((m >> 7) & 0x01010101u) * 0xFFu;      // mask_utils.py:68: keep where mask > 127
+            uint32_t* p = reinterpret_cast<uint32_t*>(s_in) + 3 * t;
+            const uint32_t k0 = __byte_perm(k, k, 0x1000), k1 = __byte_perm(k, k, 0x2211), k2 = __byte_perm(k, k, 0x3332);
+            p[0] = (p[0] & k0) | (c32 & ~k0);                          // :76: paint the rest
+            p[1] = (p[1] & k1) | (c32 & ~k1);
+            p[2] = (p[2] & k2) | (c32 & ~k2);
+        }
+        for (int i = n4 * 12 + threadIdx.x; i < n * 3; i += THREADS) {
+            if (!(s_m[i / 3] > 127)) s_in[i] = (uint8_t)color_val;
         }
         __syncthreads();
         block_store_bytes(dst + base * 3, s_in, n * 3);
