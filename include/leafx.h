@@ -91,6 +91,13 @@ int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, in
 int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W,
                 const int32_t* cut, int32_t* hist_ws, lfx_stream_t stream);
 
+/* The noise of ImageAugmenter.distortion generated on the device: out[b, 0..n) =
+ * np.random.normal(loc, scale, n).astype(np.uint8) after np.random.seed(seeds[b]) -- NumPy's legacy MT19937 +
+ * polar-method stream that ImageAugmenter(seed) seeds (image_augmenter.py:16-18,121-123).  seeds[B]: device
+ * uint32 (non-zero: seed 0 leaves the reference unseeded).  Feeds lfx_distort's `noise`. */
+int lfx_legacy_normal_u8(const uint32_t* seeds, uint8_t* out, int B, int n, double loc, double scale,
+                         lfx_stream_t stream);
+
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
 /* cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}) (mask.py:87,103; blur.py:27; hist.py:184).

@@ -253,3 +253,83 @@ def augment_arrays(images: Sequence[np.ndarray], transforms: Sequence[str], seed
         for i, o in zip(ids, res):
             outs[i] = o
     return outs
+
+
+# --------------------------------------------------------------------------- device-resident batches (BASELINE config 3)
+def draw_task_params(transform: str, seed: int, h: int, w: int, want_noise: bool = True):
+    """The parameters `_process_single_transformation` (dataset_balancer.py:201-207) would draw for one task:
+    a fresh ImageAugmenter(seed) seeds `random` / `np.random` (only `if seed:`), then the method draws in the
+    reference's order.  Returns a tuple whose layout depends on the transform."""
+    if seed:
+        random.seed(seed)
+        np.random.seed(seed)
+    if transform == "flip":
+        return (random.choice([True, False]),)
+    if transform == "rotate":
+        return (random.uniform(-30, 30),)
+    if transform == "skew":
+        s = random.uniform(0.05, 0.15)
+        return ([1 + s, 0, -s * w, 0, 1 + s, -s * h, 0, 0], True)
+    if transform == "shear":
+        k = random.uniform(-0.2, 0.2)
+        return (([1, k, 0, 0, 1, 0, 0, 0] if random.choice([True, False]) else [1, 0, 0, k, 1, 0, 0, 0]), False)
+    if transform == "crop":
+        r = random.uniform(0.8, 0.95)
+        nw, nh = int(w * r), int(h * r)
+        left = random.randint(0, w - nw)
+        return (left, random.randint(0, h - nh), nw, nh)
+    if transform == "distortion":
+        noise = np.random.normal(0, NOISE_LEVEL, (h, w, 3)).astype(np.uint8) if want_noise else None
+        return (noise, random.uniform(0, 2))
+    raise ValueError(f"unknown transform {transform!r}")
+
+
+def augment_device(x, tasks, device_noise: bool = True):
+    """Run balance tasks on images already resident in HBM.  `x`: uint8 [N,H,W,3] CUDA tensor; `tasks`: objects with
+    .transform_name, .seed, .source_index.  Returns {transform: (task indices, output tensor or rotate slab + sizes)}.
+    With `device_noise` the distortion noise (NumPy's legacy MT19937 normal stream of the task seed) is generated on
+    the GPU (ops.legacy_normal_noise) instead of by np.random on the host."""
+    import torch
+    ops = _ops()
+    h, w = int(x.shape[1]), int(x.shape[2])
+    groups = {t: [] for t in TRANSFORMATIONS}
+    for i, t in enumerate(tasks):
+        groups[t.transform_name].append(i)
+    out = {}
+    dev = x.device
+
+    def gather(ids):
+        return x.index_select(0, torch.tensor([tasks[i].source_index for i in ids], dtype=torch.int64, device=dev))
+
+    ids = groups["flip"]
+    if ids:
+        lr = [draw_task_params("flip", tasks[i].seed, h, w)[0] for i in ids]
+        out["flip"] = (ids, ops.flip(gather(ids), lr))
+    ids = groups["rotate"]
+    if ids:
+        params = []
+        for i in ids:
+            m, nw, nh = rotate_matrix(draw_task_params("rotate", tasks[i].seed, h, w)[0], w, h)
+            if isinstance(m, str):       # multiples of 90 degrees cannot come out of uniform(-30, 30) except 0.0
+                m, nw, nh = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0], w, h
+            params.append(fixed_affine(m) + [nw, nh])
+        slab, stride = ops.rotate_nn(gather(ids), np.array(params, np.int32), 255)
+        out["rotate"] = (ids, slab, [(p[7], p[6]) for p in params])
+    ids = groups["skew"] + groups["shear"]
+    if ids:
+        pr = [draw_task_params(tasks[i].transform_name, tasks[i].seed, h, w) for i in ids]
+        out["warp"] = (ids, ops.warp_bicubic(gather(ids), np.array([p[0] for p in pr], np.float64), [p[1] for p in pr]))
+    ids = groups["crop"]
+    if ids:
+        boxes = np.array([draw_task_params("crop", tasks[i].seed, h, w) for i in ids], np.int32)
+        out["crop"] = (ids, ops.crop_lanczos(gather(ids), boxes, (h, w)))
+    ids = groups["distortion"]
+    if ids:
+        pr = [draw_task_params("distortion", tasks[i].seed, h, w, want_noise=not device_noise) for i in ids]
+        cuts = [int(h * w * p[1] // 100) for p in pr]
+        if device_noise:
+            noise = ops.legacy_normal_noise([tasks[i].seed for i in ids], h * w * 3, NOISE_LEVEL, dev).view(len(ids), h, w, 3)
+        else:
+            noise = torch.from_numpy(np.stack([p[0] for p in pr])).to(dev)
+        out["distortion"] = (ids, ops.distort(gather(ids), noise, cuts))
+    return out

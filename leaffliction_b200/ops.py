@@ -396,3 +396,20 @@ def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int]) -> tor
     dcut = _dev(cuts, np.int32, x.device)
     _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(dcut), _p(hist), _stream()))
     return out
+
+
+def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc: float = 0.0) -> torch.Tensor:
+    """uint8 [len(seeds), n]: row i = np.random.normal(loc, scale, n).astype(np.uint8) after np.random.seed(seeds[i]),
+    generated on the GPU (NumPy legacy MT19937 + polar gauss, lfx_rng.cu).  Seed 0 means "unseeded" in the reference
+    (image_augmenter.py:16: `if seed:`): those rows are drawn from the host's current np.random state."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("leaffliction_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
+    seeds = [int(s) for s in seeds]
+    out = torch.empty((len(seeds), int(n)), dtype=torch.uint8, device=device)
+    ds = _dev(np.array([s & 0xFFFFFFFF for s in seeds], np.uint32).view(np.int32), np.int32, device)
+    _lib.check(lib.lfx_legacy_normal_u8(_p(ds), _p(out), len(seeds), int(n), float(loc), float(scale), _stream()))
+    for i, s in enumerate(seeds):
+        if s == 0:
+            out[i] = torch.from_numpy(np.random.normal(loc, scale, int(n)).astype(np.uint8)).to(device)
+    return out

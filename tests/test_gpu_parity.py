@@ -377,6 +377,26 @@ def test_pipeline_core_many_images(dev):
     _check_core(ref, base[:4], sm.Cfg(mask_strategy="hsv_h"), (256, 256))
 
 
+@pytest.mark.parametrize("seed", [42, 7, 999983, 1, 123456])
+def test_device_legacy_normal_stream(dev, seed):
+    """GPU MT19937 + polar gauss == np.random.seed(seed); np.random.normal(0, 5, n).astype(np.uint8) (image_augmenter.py:121-123)."""
+    n = 256 * 256 * 3
+    got = ops.legacy_normal_noise([seed], n, 5.0, dev).cpu().numpy()[0]
+    np.random.seed(seed)
+    exp = np.random.normal(0, 5, n).astype(np.uint8)
+    assert np.array_equal(got, exp), int((got != exp).sum())
+    assert np.array_equal(got, sa.noise_u8(sa.MT19937(seed).normals(n, 0.0, 5.0)))   # and == the oracle's restatement
+
+
+def test_device_legacy_normal_batch_and_sizes(dev):
+    seeds = [3, 999999, 31337, 2**31 + 5, 17, 65536, 8, 77, 1000000]
+    for n in (1, 2, 311, 64 * 64 * 3):
+        got = ops.legacy_normal_noise(seeds, n, 5.0, dev).cpu().numpy()
+        for i, sd in enumerate(seeds):
+            np.random.seed(sd)
+            assert np.array_equal(got[i], np.random.normal(0, 5, n).astype(np.uint8)), (n, sd)
+
+
 def test_empty_batch(dev):
     x = torch.empty((0, 64, 64, 3), dtype=torch.uint8, device=dev)
     assert ops.cvt_color(x, "hsv").shape == (0, 64, 64, 3)
