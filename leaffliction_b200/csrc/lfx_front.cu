@@ -176,13 +176,60 @@ __device__ void gauss_gray_pass(const uint8_t* gray, const int* taps, uint32_t* 
     for (int ys = 0; ys < H; ys += srows) {
         const int ye = min(H, ys + srows);
         const int hrows = ye - ys + 2 * R;
-        for (int i = threadIdx.x; i < hrows * W; i += MT) {
-            const int ry = i / W, x = i - ry * W;
-            const uint8_t* row = gray + refl101(ys - R + ry, H) * W;
-            int acc = 0;
+        // horizontal pass, 4 pixels per thread.  Interior groups: aligned 32-bit loads of the byte window, the K
+        // taps (all < 256) as dp4a byte weights on funnel-shifted 4-byte windows; groups that touch the left /
+        // right border take the reflecting scalar path.
+        const int G4 = (W + 3) >> 2;
+        const bool vec_ok = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(gray) & 3) == 0);
+        uint32_t wq[(K + 3) / 4];
 #pragma unroll
-            for (int t = 0; t < K; ++t) acc += row[refl101(x + t - R, W)] * taps[t];
-            hbuf[i] = (uint16_t)acc;
+        for (int j = 0; j < (K + 3) / 4; ++j) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+                if (4 * j + b < K) v |= (uint32_t)taps[4 * j + b] << (8 * b);
+            wq[j] = v;
+        }
+        constexpr int NQ = (K + 3) / 4;                          // dp4a per output
+        constexpr int RP = (R + 3) & ~3;
+        constexpr int NWORD = (3 + RP - R + 4 * NQ + 3) / 4;     // aligned words covering every 4-byte tap window of the 4 outputs
+        // interior groups [gl, gr): the whole aligned window x-RP .. x-RP+4*NWORD-1 lies inside the row.  They get
+        // their own loop so that warps stay convergent (a few border lanes would drag every warp down the slow path).
+        const int gl = vec_ok ? RP / 4 : 0;
+        const int gr = vec_ok ? max(gl, (W + RP - 4 * NWORD) / 4 + 1) : 0;
+        const int nint = gr - gl, nedge = G4 - nint;
+        for (int i = threadIdx.x; i < hrows * nint; i += MT) {
+            const int ry = i / nint, x = (gl + i - ry * nint) * 4;
+            const uint8_t* row = gray + refl101(ys - R + ry, H) * W;
+            uint16_t* hb = hbuf + ry * W + x;
+            const uint32_t* p = reinterpret_cast<const uint32_t*>(row + x - RP);
+            uint32_t w[NWORD];
+#pragma unroll
+            for (int k = 0; k < NWORD; ++k) w[k] = p[k];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int off = e + (RP - R);   // first tap of output x+e inside the window (compile-time after unrolling)
+                uint32_t acc = 0;
+#pragma unroll
+                for (int j = 0; j < NQ; ++j) {
+                    const int bo = off + 4 * j, wi = bo >> 2, sh = (bo & 3) * 8;
+                    const uint32_t win = sh ? __funnelshift_r(w[wi], w[wi + 1 < NWORD ? wi + 1 : wi], sh) : w[wi];
+                    acc = __dp4a(win, wq[j], acc);
+                }
+                hb[e] = (uint16_t)acc;
+            }
+        }
+        for (int i = threadIdx.x; i < hrows * nedge; i += MT) {
+            const int ry = i / nedge, ge = i - ry * nedge;
+            const int x = (ge < gl ? ge : gr + (ge - gl)) * 4;
+            const uint8_t* row = gray + refl101(ys - R + ry, H) * W;
+            uint16_t* hb = hbuf + ry * W + x;
+            for (int e = 0; e < 4 && x + e < W; ++e) {
+                int acc = 0;
+#pragma unroll
+                for (int t = 0; t < K; ++t) acc += row[refl101(x + e + t - R, W)] * taps[t];
+                hb[e] = (uint16_t)acc;
+            }
         }
         __syncthreads();
         for (int item = wid; item < (ye - ys) * P.WPR; item += MT / 32) {
@@ -190,10 +237,12 @@ __device__ void gauss_gray_pass(const uint8_t* gray, const int* taps, uint32_t* 
             const int y = ys + ry, x = w * 32 + lane;
             bool bit = false;
             if (x < W) {
-                uint32_t acc = 0;
+                // OpenCV's fixed-point kernel is symmetric: taps t and K-1-t share a multiply
+                const uint16_t* hc = hbuf + ry * W + x;
+                uint32_t acc = (uint32_t)hc[R * W] * (uint32_t)taps[R] + 32768u;
 #pragma unroll
-                for (int t = 0; t < K; ++t) acc += (uint32_t)hbuf[(ry + t) * W + x] * (uint32_t)taps[t];
-                const int bl = (int)((acc + 32768u) >> 16);
+                for (int t = 0; t < R; ++t) acc += ((uint32_t)hc[t * W] + (uint32_t)hc[(K - 1 - t) * W]) * (uint32_t)taps[t];
+                const int bl = (int)(acc >> 16);
                 if (out_u8) out_u8[y * W + x] = (uint8_t)bl;
                 bit = fn(y, x, bl);
             }
