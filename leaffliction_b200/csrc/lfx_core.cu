@@ -714,13 +714,70 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
 
 }  // namespace
 
-extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
-    if (B <= 0 || H <= 0 || W <= 0) return 0;
-    const size_t general = lfx_make_mask_workspace(B, H, W);
+// scratch of the fused kernel: image queue counter + per-block run-table spill (H*(W+2) runs: ccl2 labels both kinds)
+size_t lfx_core_workspace_bytes(int H, int W) {
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t rcap = (size_t)H * (W + 2);
-    const size_t fused = 256 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
-    return general > fused ? general : fused;
+    return 256 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
+}
+
+extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
+    if (B <= 0 || H <= 0 || W <= 0) return 0;
+    return lfx_make_mask_workspace(B, H, W);   // already the maximum of the general and the fused requirement
+}
+
+// Fused kernel when the shape and config allow it: LFX_OK = launched, 1 = not eligible (use the general path),
+// negative = error.  Also serves lfx_make_mask (blur / roi / stats pointers NULL: phases A-pixel + B only).
+int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
+                 int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
+                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    int rc;
+    int32_t taps[31];
+    CoreParams P;
+    int per_sm = 1;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(roi) | reinterpret_cast<uintptr_t>(mask)) % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(blur) % 4 == 0);
+    const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
+    const bool morph_ok = mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1);
+    if (!(aligned && morph_ok && lfx_gauss_taps(5, gaussian_sigma, taps) == LFX_OK && core_plan(B, H, W, RH, RW, cfg, taps, &P, &per_sm)))
+        return 1;
+    rc = ensure_cat_lut();
+    if (rc) return rc;
+    const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
+    const size_t need = 256 + (size_t)P.ws_per_block * grid;
+    LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
+    const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
+    static int attr[2] = {0, 0};
+    if (P.lay.smem_bytes > attr[s256]) {
+        const void* fn = s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.lay.smem_bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.lay.smem_bytes, cudaGetErrorString(e));
+        attr[s256] = P.lay.smem_bytes;
+    }
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
+    static const bool timing = getenv("LFX_CORE_TIMING") && atoi(getenv("LFX_CORE_TIMING")) > 0;
+    P.timing = timing ? 1 : 0;
+    if (s256)
+        k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                                        (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+    else
+        k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                                         (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+    if (timing) {  // debug only: synchronises and prints the phase split
+        unsigned long long t[16] = {0};
+        cudaStreamSynchronize(st);
+        cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost);
+        double tb = (double)t[1];
+        for (int k = 3; k < 10; ++k) tb += (double)t[k];
+        const double tot = (double)t[0] + tb + (double)t[2];
+        fprintf(stderr, "[lfx] k_core B=%d phase cycles/image: A %.0f (%.1f%%)  B %.0f (%.1f%%)  C %.0f (%.1f%%)\n", B, t[0] / (double)B,
+                100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, t[2] / (double)B, 100.0 * t[2] / tot);
+        fprintf(stderr, "[lfx]   B split: fill-ccl4 %.0f  close/open %.0f  largest#1 %.0f  dilate20x2 %.0f  brown-morph %.0f  brown-ccl8 %.0f  largest#2 %.0f  tail %.0f\n",
+                t[3] / (double)B, t[4] / (double)B, t[5] / (double)B, t[6] / (double)B, t[7] / (double)B, t[8] / (double)B, t[9] / (double)B, t[1] / (double)B);
+    }
+    return lfx_check_launch("pipeline_core(fused)");
 }
 
 extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi,
@@ -732,55 +789,9 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
     LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
     LFX_REQUIRE(B > 0 && H > 0 && W > 0, LFX_ERR_ARG, "pipeline_core: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-
-    // ---- fused kernel (one block per image) when the shape and config allow it
-    int32_t taps[31];
-    CoreParams P;
-    int per_sm = 1;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(roi) | reinterpret_cast<uintptr_t>(mask)) % 16 == 0) &&
-                         (reinterpret_cast<uintptr_t>(blur) % 4 == 0);
-    const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
-    const bool morph_ok = mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1);
-    if (aligned && morph_ok && lfx_gauss_taps(5, gaussian_sigma, taps) == LFX_OK && core_plan(B, H, W, RH, RW, cfg, taps, &P, &per_sm)) {
-        rc = ensure_cat_lut();
-        if (rc) return rc;
-        const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
-        const size_t need = 256 + (size_t)P.ws_per_block * grid;
-        LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
-        const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
-        static int attr[2] = {0, 0};
-        if (P.lay.smem_bytes > attr[s256]) {
-            const void* fn = s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
-            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.lay.smem_bytes);
-            if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.lay.smem_bytes, cudaGetErrorString(e));
-            attr[s256] = P.lay.smem_bytes;
-        }
-        cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
-        LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
-        static const bool timing = getenv("LFX_CORE_TIMING") && atoi(getenv("LFX_CORE_TIMING")) > 0;
-        P.timing = timing ? 1 : 0;
-        if (s256)
-            k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                            (uint8_t*)workspace, lfx_tables(), g_cat_lut);
-        else
-            k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                             (uint8_t*)workspace, lfx_tables(), g_cat_lut);
-        if (timing) {  // debug only: synchronises and prints the phase split
-            unsigned long long t[16] = {0};
-            cudaStreamSynchronize(st);
-            cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost);
-            double tb = (double)t[1];
-            for (int k = 3; k < 10; ++k) tb += (double)t[k];
-            const double tot = (double)t[0] + tb + (double)t[2];
-            fprintf(stderr, "[lfx] k_core B=%d phase cycles/image: A %.0f (%.1f%%)  B %.0f (%.1f%%)  C %.0f (%.1f%%)\n", B, t[0] / (double)B,
-                    100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, t[2] / (double)B, 100.0 * t[2] / tot);
-            fprintf(stderr, "[lfx]   B split: fill-ccl4 %.0f  close/open %.0f  largest#1 %.0f  dilate20x2 %.0f  brown-morph %.0f  brown-ccl8 %.0f  largest#2 %.0f  tail %.0f\n",
-                    t[3] / (double)B, t[4] / (double)B, t[5] / (double)B, t[6] / (double)B, t[7] / (double)B, t[8] / (double)B, t[9] / (double)B, t[1] / (double)B);
-        }
-        return lfx_check_launch("pipeline_core(fused)");
-    }
+    int rc = lfx_core_try(src, blur, mask, info, roi, hist9, hsv3, counters, B, H, W, RH, RW, gaussian_sigma, cfg, workspace,
+                          workspace_bytes, st);
+    if (rc <= 0) return rc;
 
     // ---- general path: the stand-alone kernels back to back
     if (blur) {

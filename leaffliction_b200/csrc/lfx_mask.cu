@@ -9,6 +9,11 @@
 //   2*contourArea(component) = 2N - (P - Q1) - 2  over 8-connected components of `filled`.
 #include "lfx_maskops.cuh"
 
+size_t lfx_core_workspace_bytes(int H, int W);
+int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
+                 int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
+                 void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 namespace {
 
 __global__ void __launch_bounds__(MT, 2) k_make_mask(const uint8_t* __restrict__ src, const uint8_t* __restrict__ raw,
@@ -168,7 +173,9 @@ extern "C" size_t lfx_make_mask_workspace(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     Plan pl;
     make_plan(B, H, W, nullptr, 0, &pl);
-    return pl.ws_per_block * (size_t)min(B, LFX_NUM_SMS * 2) + 256;
+    const size_t general = pl.ws_per_block * (size_t)min(B, LFX_NUM_SMS * 2) + 256;
+    const size_t fused = lfx_core_workspace_bytes(H, W);
+    return general > fused ? general : fused;
 }
 
 extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info, int B, int H, int W,
@@ -176,6 +183,12 @@ extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* ma
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(mask && info && cfg, LFX_ERR_ARG, "make_mask: NULL argument");
+    if (!raw && src && (cfg->strategy == 0 || cfg->strategy == 1) && B > 0 && H > 0 && W > 0) {
+        // threshold strategies on fused-kernel shapes: k_core without its blur / ROI / statistics phases
+        const int rc = lfx_core_try(src, nullptr, mask, info, nullptr, nullptr, nullptr, nullptr, B, H, W, H, W, 1.5, cfg, workspace,
+                                    workspace_bytes, (cudaStream_t)stream);
+        if (rc <= 0) return rc;
+    }
     return launch(src, raw, mask, info, B, H, W, cfg, 0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
