@@ -768,14 +768,16 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     if (timing) {  // debug only: synchronises and prints the phase split
         unsigned long long t[16] = {0};
         cudaStreamSynchronize(st);
-        cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 10, cudaMemcpyDeviceToHost);
+        cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
         double tb = (double)t[1];
-        for (int k = 3; k < 10; ++k) tb += (double)t[k];
+        for (int k = 3; k < 16; ++k) tb += (double)t[k];
         const double tot = (double)t[0] + tb + (double)t[2];
         fprintf(stderr, "[lfx] k_core B=%d phase cycles/image: A %.0f (%.1f%%)  B %.0f (%.1f%%)  C %.0f (%.1f%%)\n", B, t[0] / (double)B,
                 100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, t[2] / (double)B, 100.0 * t[2] / tot);
         fprintf(stderr, "[lfx]   B split: fill-ccl4 %.0f  close/open %.0f  largest#1 %.0f  dilate20x2 %.0f  brown-morph %.0f  brown-ccl8 %.0f  largest#2 %.0f  tail %.0f\n",
                 t[3] / (double)B, t[4] / (double)B, t[5] / (double)B, t[6] / (double)B, t[7] / (double)B, t[8] / (double)B, t[9] / (double)B, t[1] / (double)B);
+        fprintf(stderr, "[lfx]   ccl2 (both largest_external calls; NOT included in largest#N above): count %.0f  scan+extract %.0f  union %.0f  flatten %.0f\n",
+                t[15] / (double)B, t[10] / (double)B, t[11] / (double)B, t[12] / (double)B);
     }
     return lfx_check_launch("pipeline_core(fused)");
 }

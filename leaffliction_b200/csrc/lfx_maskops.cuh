@@ -392,7 +392,15 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
         }
         if (P.cfg.extend_brown) {
             // _extend_mask_with_brown_regions (mask.py:335-392)
-            if (c.hp[0] && P.search_is_e20) {
+            // search_area = dilate^2(best) only constrains brown pixels OUTSIDE the best mask (dilation is extensive:
+            // best is a subset of search_area).  When every brown-predicate pixel already lies inside the best mask,
+            // brown & search_area == brown and the two 20x20 dilations can be skipped.
+            int outside = 0;
+            for (int i = threadIdx.x; i < c.NW; i += MT) outside |= ((PB[i] & ~PR[i]) != 0u);
+            if (!__syncthreads_or(outside)) {
+                for (int i = threadIdx.x; i < c.NW; i += MT) T2[i] = 0xFFFFFFFFu;   // stands for search_area in the AND below
+                __syncthreads();
+            } else if (c.hp[0] && P.search_is_e20) {
                 dilate_ellipse20(PR, T1, c);
                 dilate_ellipse20(T1, T2, c);
             } else {
@@ -419,8 +427,10 @@ __device__ void mask_finish(const uint8_t* simg, uint8_t* s_stage, const HsvLut*
             morph_any<true>(T1, T2, P.fp_brown, c);  // close
             __syncthreads();
             morph_any<false>(T2, T1, P.fp_brown, c);
+            // Cleaned brown regions that add no pixel outside the best mask (spots ON the leaf, the usual case) leave
+            // the extended mask equal to the best mask whatever the area filter keeps: same early exit as above.
             any = 0;
-            for (int i = threadIdx.x; i < c.NW; i += MT) any |= (T1[i] != 0u);   // own words only: no barrier needed yet
+            for (int i = threadIdx.x; i < c.NW; i += MT) any |= ((T1[i] & ~PR[i]) != 0u);   // own words only: no barrier needed yet
             if (!__syncthreads_or(any)) return;
             LFX_CTX_TICK(c, 7)
             ccl<8>(T1, c);

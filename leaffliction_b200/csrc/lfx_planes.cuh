@@ -361,107 +361,17 @@ __device__ void uf_flatten(int total, C& c) {
         int moved = 0;
         for (int r = threadIdx.x; r < total; r += MT) {
             const int p1 = parent[r];
-            const int p2 = parent[p1];
-            if (p2 != p1) {
-                parent[r] = parent[p2];
+            int q = parent[p1];
+            if (q != p1) {
+                q = parent[q];       // up to four hops per round: the depth shrinks fivefold
+                q = parent[q];
+                q = parent[q];
+                parent[r] = q;
                 moved = 1;
             }
         }
         if (!__syncthreads_or(moved)) break;
     }
-}
-
-// Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
-// (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
-template <int CONN, class C>
-__device__ void ccl(const uint32_t* m, C& c) {
-    const int per = (c.NW + MT - 1) / MT;
-    const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
-    int cnt = 0;
-    for (int i = i0; i < i1; ++i) cnt += __popc(starts_of(m, i, i % c.WPR));
-    int total;
-    int base = block_exscan(cnt, c.s_tmp, total);
-    const int base0 = base;
-    for (int i = i0; i < i1; ++i) {
-        c.wbase[i] = base;
-        base += __popc(starts_of(m, i, i % c.WPR));
-    }
-    c.R = total;
-    if (total <= c.rcap_smem) {
-        c.parent = c.sm_parent; c.geom = c.sm_geom; c.acc = c.sm_acc; c.ry = c.sm_ry;
-    } else {
-        c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
-        c.status |= 2;
-    }
-    int* parent = c.parent;
-    // Run extraction on the thread's own contiguous words (same mapping as the count above: each thread
-    // sees a mix of word columns, so speckled borders and clean interiors balance out; ids follow from the
-    // thread's scan base, no barrier needed before this loop).
-    int id = base0;
-    for (int i = i0; i < i1; ++i) {
-        int y, w;
-        split_index(c, i, y, w);
-        uint32_t st = starts_of(m, i, w);
-        const uint32_t word = m[i];
-        while (st) {
-            const int b = __ffs(st) - 1;
-            st &= st - 1;
-            const int x0 = w * 32 + b;
-            const uint32_t inv = ~(word >> b);
-            const int z = __ffs(inv) - 1;  // first zero at/after b (relative); -1 if none
-            int x1;
-            if (inv != 0 && z < 32 - b) {
-                x1 = x0 + z - 1;
-            } else {
-                x1 = w * 32 + 31;
-                int ww = w + 1;
-                while (ww < c.WPR) {
-                    const uint32_t nx = m[y * c.WPR + ww];
-                    if (nx == 0xFFFFFFFFu) {
-                        x1 += 32;
-                        ++ww;
-                        continue;
-                    }
-                    x1 += __ffs(~nx) - 1;
-                    break;
-                }
-            }
-            c.geom[id] = (uint32_t)x0 | ((uint32_t)x1 << 16);
-            c.ry[id] = (uint16_t)y;
-            parent[id] = id;
-            c.acc[id] = 0;
-            ++id;
-        }
-    }
-    __syncthreads();
-    for (int r = threadIdx.x; r < total; r += MT) {
-        const int y = c.ry[r];
-        if (y == 0) continue;
-        const uint32_t g = c.geom[r];
-        const int x0 = g & 0xFFFF, x1 = g >> 16;
-        const int lo = max(0, x0 - (CONN == 8 ? 1 : 0)), hi = min(c.W - 1, x1 + (CONN == 8 ? 1 : 0));
-        const uint32_t* up = m + (y - 1) * c.WPR;
-        int p = lo;
-        while (p <= hi) {
-            int wi = p >> 5;
-            uint32_t v = up[wi] & (0xFFFFFFFFu << (p & 31));
-            while (v == 0) {
-                ++wi;
-                if (wi * 32 > hi) break;
-                v = up[wi];
-            }
-            if (v == 0) break;
-            const int b = __ffs(v) - 1;
-            if (wi * 32 + b > hi) break;
-            const int idxw = (y - 1) * c.WPR + wi;
-            const uint32_t st = starts_of(m, idxw, wi);
-            const int id2 = c.wbase[idxw] + __popc(st & ((2u << b) - 1u)) - 1;
-            uf_unite(parent, r, id2);
-            p = (int)(c.geom[id2] >> 16) + 1;
-        }
-    }
-    __syncthreads();
-    uf_flatten(total, c);
 }
 
 // ---------------------------------------------------------------- ccl2: foreground + background in one pass
@@ -547,6 +457,127 @@ __device__ __forceinline__ int fg_run_at(const uint32_t* m, int y, int x, const 
     return c.wbase[idxw] + __popc(st & ((2u << (x & 31)) - 1u)) - 1;
 }
 
+// Calls fn(id2, k) for the k-th run of row y-1 (plane m, or its complement when INV) that overlaps columns lo..hi.
+// wb = per-word first-run id table of that kind (relative to idbase).
+template <bool INV, class C, class F>
+__device__ __forceinline__ void for_upper_runs(const uint32_t* m, int y, int lo, int hi, const int* wb, int idbase, const C& c, F fn) {
+    int p = lo, k = 0;
+    while (p <= hi) {
+        int wi = p >> 5;
+        uint32_t v = plane_word<INV>(m, (y - 1) * c.WPR + wi, wi, c) & (0xFFFFFFFFu << (p & 31));
+        while (v == 0) {
+            ++wi;
+            if (wi * 32 > hi) break;
+            v = plane_word<INV>(m, (y - 1) * c.WPR + wi, wi, c);
+        }
+        if (v == 0) break;
+        const int b = __ffs(v) - 1;
+        if (wi * 32 + b > hi) break;
+        const int idxw = (y - 1) * c.WPR + wi;
+        const uint32_t st = starts_of2<INV>(m, idxw, wi, c);
+        const int id2 = idbase + wb[idxw] + __popc(st & ((2u << b) - 1u)) - 1;
+        fn(id2, k++);
+        p = (int)(c.geom[id2] >> 16) + 1;
+    }
+}
+
+// Union phase in two sweeps.  (1) LINK: every run points at the FIRST overlapping run of the row above -- a plain
+// store, no search, no atomic (ids in the row above are smaller, so links still point to smaller ids); flatten.
+// (2) MERGE: only runs with further overlapping neighbours unite the (now shallow) trees with atomicMin; flatten.
+// A blob with one run per row -- the usual leaf -- needs no atomic at all.
+template <class C, class RANGE>
+__device__ void uf_link_merge(const uint32_t* m, int total, C& c, RANGE range) {
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int y = c.ry[r];
+        if (y == 0) continue;
+        range(r, y, [&](int id2, int k) { if (k == 0) c.parent[r] = id2; });
+    }
+    __syncthreads();
+    uf_flatten(total, c);
+    int any = 0;
+    for (int r = threadIdx.x; r < total; r += MT) {
+        const int y = c.ry[r];
+        if (y == 0) continue;
+        range(r, y, [&](int id2, int k) {
+            if (k > 0) {
+                uf_unite(c.parent, r, id2);
+                any = 1;
+            }
+        });
+    }
+    if (__syncthreads_or(any)) uf_flatten(total, c);
+}
+
+// Labels the runs of plane m (CONN = 4 or 8).  After return: c.R runs, c.parent[r] = root run id
+// (the smallest id of the component = its first run in raster order), c.geom / c.ry, c.acc = 0.
+template <int CONN, class C>
+__device__ void ccl(const uint32_t* m, C& c) {
+    const int per = (c.NW + MT - 1) / MT;
+    const int i0 = min(c.NW, (int)threadIdx.x * per), i1 = min(c.NW, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += __popc(starts_of(m, i, i % c.WPR));
+    int total;
+    int base = block_exscan(cnt, c.s_tmp, total);
+    const int base0 = base;
+    for (int i = i0; i < i1; ++i) {
+        c.wbase[i] = base;
+        base += __popc(starts_of(m, i, i % c.WPR));
+    }
+    c.R = total;
+    if (total <= c.rcap_smem) {
+        c.parent = c.sm_parent; c.geom = c.sm_geom; c.acc = c.sm_acc; c.ry = c.sm_ry;
+    } else {
+        c.parent = c.gl_parent; c.geom = c.gl_geom; c.acc = c.gl_acc; c.ry = c.gl_ry;
+        c.status |= 2;
+    }
+    int* parent = c.parent;
+    // Run extraction on the thread's own contiguous words (same mapping as the count above: each thread
+    // sees a mix of word columns, so speckled borders and clean interiors balance out; ids follow from the
+    // thread's scan base, no barrier needed before this loop).
+    int id = base0;
+    for (int i = i0; i < i1; ++i) {
+        int y, w;
+        split_index(c, i, y, w);
+        uint32_t st = starts_of(m, i, w);
+        const uint32_t word = m[i];
+        while (st) {
+            const int b = __ffs(st) - 1;
+            st &= st - 1;
+            const int x0 = w * 32 + b;
+            const uint32_t inv = ~(word >> b);
+            const int z = __ffs(inv) - 1;  // first zero at/after b (relative); -1 if none
+            int x1;
+            if (inv != 0 && z < 32 - b) {
+                x1 = x0 + z - 1;
+            } else {
+                x1 = w * 32 + 31;
+                int ww = w + 1;
+                while (ww < c.WPR) {
+                    const uint32_t nx = m[y * c.WPR + ww];
+                    if (nx == 0xFFFFFFFFu) {
+                        x1 += 32;
+                        ++ww;
+                        continue;
+                    }
+                    x1 += __ffs(~nx) - 1;
+                    break;
+                }
+            }
+            c.geom[id] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+            c.ry[id] = (uint16_t)y;
+            parent[id] = id;
+            c.acc[id] = 0;
+            ++id;
+        }
+    }
+    __syncthreads();
+    uf_link_merge(m, total, c, [&](int r, int y, auto fn) {
+        const uint32_t g = c.geom[r];
+        const int x0 = g & 0xFFFF, x1 = g >> 16;
+        for_upper_runs<false>(m, y, max(0, x0 - (CONN == 8 ? 1 : 0)), min(c.W - 1, x1 + (CONN == 8 ? 1 : 0)), c.wbase, 0, c, fn);
+    });
+}
+
 // Labels the 8-connected runs of plane m (ids [0, R1)) AND the 4-connected runs of its complement (ids
 // [R1, R)) with one scan / extract / union / flatten sequence -- the two labelings largest_external needs,
 // for the latency of one.  Needs c.wbase2.
@@ -562,6 +593,7 @@ __device__ void ccl2(const uint32_t* m, C& c) {
         cb += __popc(starts_of2<true>(m, i, w, c));
     }
     // both counts ride one scan when each total fits 16 bits (<= 16 runs per word and kind)
+    LFX_CTX_TICK(c, 15)
     int tot_f, tot_b, bf, bb;
     if (c.NW <= 2048) {
         int total;
@@ -591,18 +623,16 @@ __device__ void ccl2(const uint32_t* m, C& c) {
         idb = extract_runs<true>(m, i, idb, c);
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < total; r += MT) {
-        const int y = c.ry[r];
-        if (y == 0) continue;
+    LFX_CTX_TICK(c, 10)
+    uf_link_merge(m, total, c, [&](int r, int y, auto fn) {
         const uint32_t g = c.geom[r];
         const int x0 = g & 0xFFFF, x1 = g >> 16;
         if (r < R1)
-            unite_up<false>(m, r, y, max(0, x0 - 1), min(c.W - 1, x1 + 1), c.wbase, 0, c);
+            for_upper_runs<false>(m, y, max(0, x0 - 1), min(c.W - 1, x1 + 1), c.wbase, 0, c, fn);
         else
-            unite_up<true>(m, r, y, x0, x1, c.wbase2, R1, c);
-    }
-    __syncthreads();
-    uf_flatten(total, c);
+            for_upper_runs<true>(m, y, x0, x1, c.wbase2, R1, c, fn);
+    });
+    LFX_CTX_TICK(c, 11)
 }
 
 template <class C>
