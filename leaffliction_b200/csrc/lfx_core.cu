@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(MT, 2)
     c.sm_acc = reinterpret_cast<int*>(sm + L.off_runs + RCAP_SMEM * 8);
     c.sm_ry = reinterpret_cast<uint16_t*>(sm + L.off_runs + RCAP_SMEM * 12);
     {
-        uint8_t* gp = ws + 256 + (size_t)blockIdx.x * P.ws_per_block;
+        uint8_t* gp = ws + 512 + (size_t)blockIdx.x * P.ws_per_block;
         auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
         c.gl_parent = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
         c.gl_geom = reinterpret_cast<uint32_t*>(gp); gp += al((size_t)M.rcap_glob * 4);
@@ -465,9 +465,13 @@ __global__ void __launch_bounds__(MT, 2)
                 const int top = geo.found ? geo.oy : RH;
                 for (int r0 = 0; r0 < top; r0 += CHUNK)
                     bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, top - r0) * RW * 3);
-                if (geo.found)
-                    for (int r0 = geo.oy + geo.nh; r0 < RH; r0 += CHUNK)
+                if (geo.found) {
+                    // rows of the box itself only when it is narrower than the canvas (side bands); the pixels are
+                    // stored over them later, after bulk_wait_all()
+                    const int from = (geo.nw < RW) ? geo.oy : geo.oy + geo.nh;
+                    for (int r0 = from; r0 < RH; r0 += CHUNK)
                         bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, RH - r0) * RW * 3);
+                }
                 bulk_commit();
             }
             __syncthreads();
@@ -488,11 +492,13 @@ __global__ void __launch_bounds__(MT, 2)
         const int roi_strips = 1 << roi_sshift;
         const int roi_strip = threadIdx.x / roi_cols, roi_col0 = threadIdx.x - roi_strip * roi_cols;
         uint32_t cacc[4] = {0u, 0u, 0u, 0u};
+        LFX_TICK(16)
         for (int t = 0; t < ntiles; ++t) {
             const int y0 = t * TR, nr = min(TR, H - y0);
             mbar_wait(&s_bar, par);
             par ^= 1;
             __syncthreads();  // s_dlo / taps visible (t == 0)
+            LFX_TICK(17)
             if (want_stats) {
                 // contiguous rows per warp: every warp sees all word columns (the leaf sits in the middle ones)
                 const int ipw = (nr * WPR + NWARPS - 1) / NWARPS;
@@ -535,6 +541,7 @@ __global__ void __launch_bounds__(MT, 2)
             }
             if (roi && geo.found) {
                 __syncthreads();
+                LFX_TICK(18)
                 // apply_mask(rgb, mask, "white") in place (Transformation.py:451) -- only the bounding box is ever
                 // sampled: rows by .. by+bh-1 of this tile (+ the next row as lower tap), words covering bx .. bx+bw-1
                 {
@@ -553,58 +560,51 @@ __global__ void __launch_bounds__(MT, 2)
                         }
                     }
                 }
+                if (t == 0 && threadIdx.x == 0) bulk_wait_all();   // the zero rows have landed before pixels are stored over them
                 __syncthreads();
+                LFX_TICK(19)
                 const int dA = s_dlo[t], dB = s_dlo[t + 1];
                 const uint8_t* tile0 = s_src + (geo.by - y0 + 2) * RB;  // staged row of source row `by`
-                for (int d0 = dA; d0 < dB; d0 += CHUNK) {
-                    const int rows = min(CHUNK, dB - d0);
-                    if (threadIdx.x == 0) bulk_wait_read();  // the previous store has drained s_out
-                    __syncthreads();
-                    // the side bands of s_out stay zero from the start of phase C: only [ox, ox+nw) is rewritten
-                    if (roi_strip < roi_strips) {
-                        const int per = (rows + roi_strips - 1) >> roi_sshift;
-                        const int da = d0 + roi_strip * per, db = min(d0 + rows, da + per);
-                        for (int cx = roi_col0; cx < geo.nw; cx += roi_cols) {
-                            const int2 tx = s_xt[cx];
-                            const uint32_t xa = tx.y & 0xFFFF, xb = (uint32_t)tx.y >> 16;
-                            const uint8_t* colp = tile0 + tx.x;
-                            uint8_t* o = s_out + ((da - d0) * RW + geo.ox + cx) * 3;
-                            int prev_s = -4;
-                            uint32_t h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
-                            for (int d = da; d < db; ++d, o += RW * 3) {
-                                const int2 ty = s_yt[d];
-                                if (ty.x != prev_s) {
-                                    const uint8_t* p = colp + ty.x * RB;
-                                    if (ty.x == prev_s + 1) {
-                                        h0r = h1r; h0g = h1g; h0b = h1b;
-                                    } else {
-                                        h0r = (p[0] * xa + p[3] * xb) >> 4;  // HResizeLinear x2048, >> 4 as in VResizeLinear
-                                        h0g = (p[1] * xa + p[4] * xb) >> 4;
-                                        h0b = (p[2] * xa + p[5] * xb) >> 4;
-                                    }
-                                    h1r = (p[RB] * xa + p[RB + 3] * xb) >> 4;
-                                    h1g = (p[RB + 1] * xa + p[RB + 4] * xb) >> 4;
-                                    h1b = (p[RB + 2] * xa + p[RB + 5] * xb) >> 4;
-                                    prev_s = ty.x;
+                // canvas rows dA .. dB-1 take their upper source row from this tile: one column per thread, the rows split
+                // into roi_strips strips; pixels go straight to HBM (3 byte stores per pixel; L2 merges the sectors)
+                if (roi_strip < roi_strips && dB > dA) {
+                    const int per = (dB - dA + roi_strips - 1) >> roi_sshift;
+                    const int da = dA + roi_strip * per, db = min(dB, da + per);
+                    for (int cx = roi_col0; cx < geo.nw; cx += roi_cols) {
+                        const int2 tx = s_xt[cx];
+                        const uint32_t xa = tx.y & 0xFFFF, xb = (uint32_t)tx.y >> 16;
+                        const uint8_t* colp = tile0 + tx.x;
+                        uint8_t* o = rimg + ((size_t)(geo.oy + da) * RW + geo.ox + cx) * 3;
+                        int prev_s = -4;
+                        uint32_t h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
+                        for (int d = da; d < db; ++d, o += RW * 3) {
+                            const int2 ty = s_yt[d];
+                            if (ty.x != prev_s) {
+                                const uint8_t* p = colp + ty.x * RB;
+                                if (ty.x == prev_s + 1) {
+                                    h0r = h1r; h0g = h1g; h0b = h1b;
+                                } else {
+                                    h0r = (p[0] * xa + p[3] * xb) >> 4;  // HResizeLinear x2048, >> 4 as in VResizeLinear
+                                    h0g = (p[1] * xa + p[4] * xb) >> 4;
+                                    h0b = (p[2] * xa + p[5] * xb) >> 4;
                                 }
-                                // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255.
-                                // (ya*h >> 16) as the high word of (ya << 16) * h: one IMAD.HI with the addend fused
-                                const uint32_t ya = (uint32_t)ty.y << 16, yb = (uint32_t)ty.y & 0xFFFF0000u;
-                                o[0] = (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2);
-                                o[1] = (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2);
-                                o[2] = (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2);
+                                h1r = (p[RB] * xa + p[RB + 3] * xb) >> 4;
+                                h1g = (p[RB + 1] * xa + p[RB + 4] * xb) >> 4;
+                                h1b = (p[RB + 2] * xa + p[RB + 5] * xb) >> 4;
+                                prev_s = ty.x;
                             }
+                            // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255.
+                            // (ya*h >> 16) as the high word of (ya << 16) * h: one IMAD.HI with the addend fused
+                            const uint32_t ya = (uint32_t)ty.y << 16, yb = (uint32_t)ty.y & 0xFFFF0000u;
+                            o[0] = (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2);
+                            o[1] = (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2);
+                            o[2] = (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2);
                         }
-                    }
-                    fence_async_smem();
-                    __syncthreads();
-                    if (threadIdx.x == 0) {
-                        bulk_s2g(rimg + (size_t)(geo.oy + d0) * RW * 3, s_out, (uint32_t)rows * RW * 3);
-                        bulk_commit();
                     }
                 }
             }
             __syncthreads();  // every reader of s_src is done
+            LFX_TICK(20)
             if (threadIdx.x == 0 && t + 1 < ntiles)
                 issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
         }
@@ -718,7 +718,7 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
 size_t lfx_core_workspace_bytes(int H, int W) {
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t rcap = (size_t)H * (W + 2);
-    return 256 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
+    return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
 }
 
 extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
@@ -744,7 +744,7 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     rc = ensure_cat_lut();
     if (rc) return rc;
     const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
-    const size_t need = 256 + (size_t)P.ws_per_block * grid;
+    const size_t need = 512 + (size_t)P.ws_per_block * grid;
     LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
     const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
     static int attr[2] = {0, 0};
@@ -755,7 +755,7 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.lay.smem_bytes, cudaGetErrorString(e));
         attr[s256] = P.lay.smem_bytes;
     }
-    cudaError_t e = cudaMemsetAsync(workspace, 0, 256, st);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, 512, st);
     LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
     static const bool timing = getenv("LFX_CORE_TIMING") && atoi(getenv("LFX_CORE_TIMING")) > 0;
     P.timing = timing ? 1 : 0;
@@ -766,14 +766,18 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
         k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
                                                          (uint8_t*)workspace, lfx_tables(), g_cat_lut);
     if (timing) {  // debug only: synchronises and prints the phase split
-        unsigned long long t[16] = {0};
+        unsigned long long t[32] = {0};
         cudaStreamSynchronize(st);
-        cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 16, cudaMemcpyDeviceToHost);
+        cudaMemcpy(t, (uint8_t*)workspace + 64, sizeof(unsigned long long) * 24, cudaMemcpyDeviceToHost);
         double tb = (double)t[1];
         for (int k = 3; k < 16; ++k) tb += (double)t[k];
-        const double tot = (double)t[0] + tb + (double)t[2];
+        double tc = (double)t[2];
+        for (int k = 16; k < 24; ++k) tc += (double)t[k];
+        const double tot = (double)t[0] + tb + tc;
         fprintf(stderr, "[lfx] k_core B=%d phase cycles/image: A %.0f (%.1f%%)  B %.0f (%.1f%%)  C %.0f (%.1f%%)\n", B, t[0] / (double)B,
-                100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, t[2] / (double)B, 100.0 * t[2] / tot);
+                100.0 * t[0] / tot, tb / (double)B, 100.0 * tb / tot, tc / (double)B, 100.0 * tc / tot);
+        fprintf(stderr, "[lfx]   C split: prelude %.0f  tma-wait %.0f  stats %.0f  mask-paint %.0f  roi %.0f  tail %.0f\n", t[16] / (double)B,
+                t[17] / (double)B, t[18] / (double)B, t[19] / (double)B, t[20] / (double)B, t[2] / (double)B);
         fprintf(stderr, "[lfx]   B split: fill-ccl4 %.0f  close/open %.0f  largest#1 %.0f  dilate20x2 %.0f  brown-morph %.0f  brown-ccl8 %.0f  largest#2 %.0f  tail %.0f\n",
                 t[3] / (double)B, t[4] / (double)B, t[5] / (double)B, t[6] / (double)B, t[7] / (double)B, t[8] / (double)B, t[9] / (double)B, t[1] / (double)B);
         fprintf(stderr, "[lfx]   ccl2 (both largest_external calls; NOT included in largest#N above): count %.0f  scan+extract %.0f  union %.0f  flatten %.0f\n",
