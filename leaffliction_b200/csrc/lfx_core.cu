@@ -24,7 +24,7 @@
 namespace {
 
 constexpr int TR = 32;     // image rows per staged tile
-constexpr int CHUNK = 16;  // ROI canvas rows per bulk store
+constexpr int CHUNK = 4;   // rows of the zero buffer the letterbox bands are bulk-stored from
 constexpr int NWARPS = MT / 32;
 
 // Shared-memory byte offsets.  Fixed part: raw / brown / result planes and the colour LUTs; the rest is a
@@ -33,7 +33,7 @@ struct Lay {
     int off_planes, off_hsv, off_lab;
     int off_src, off_v;                              // phase A (inside the union)
     int off_t, off_wbase, off_wbase2, off_runs, off_stage;  // phase B
-    int off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A)
+    int off_src2, off_out, off_hist, off_cat, off_xt, off_yt;  // phase C (off_src shared with A; two tile buffers)
     int smem_bytes;
 };
 __host__ __device__ constexpr int lay_al(long long b) { return (int)((b + 127) & ~127ll); }
@@ -55,8 +55,14 @@ __host__ __device__ constexpr Lay make_lay(int H, int W, int RH, int RW) {
     L.off_runs = b; b += lay_al((long long)RCAP_SMEM * 14);
     L.off_stage = b; b += lay_al((long long)stage_rows * rb);
     int c3 = L.off_src + lay_al((long long)(TR + 4) * rb + 16);
+    L.off_src2 = c3; c3 += lay_al((long long)(TR + 4) * rb + 16);
     L.off_out = c3; c3 += lay_al((long long)CHUNK * RW * 3);
-    L.off_hist = c3; c3 += lay_al(12 * 256 * 4);
+    // the 12 x 256 histogram lives in the raw / brown planes (dead in phase C) when they are big enough
+    if ((long long)NW * 8 >= 12 * 256 * 4) {
+        L.off_hist = L.off_planes;
+    } else {
+        L.off_hist = c3; c3 += lay_al(12 * 256 * 4);
+    }
     L.off_cat = c3; c3 += lay_al(3 * 256 * 16);
     L.off_xt = c3; c3 += lay_al((long long)RW * 8);
     L.off_yt = c3; c3 += lay_al((long long)RH * 8);
@@ -248,7 +254,8 @@ __global__ void __launch_bounds__(MT, 2)
     __shared__ int s_hist256[256];
     __shared__ int s_info[8];
     __shared__ int s_info2[8];
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar2[2];
+    uint64_t& s_bar = s_bar2[0];
     __shared__ int s_next;
     __shared__ Geo s_geo;
     __shared__ int s_dlo[TR + 2];  // first canvas row of each source tile (at most TR tiles: H <= TR*TR)
@@ -299,6 +306,8 @@ __global__ void __launch_bounds__(MT, 2)
     HsvLut* s_hsv = reinterpret_cast<HsvLut*>(sm + L.off_hsv);
     LabLut* s_lab = reinterpret_cast<LabLut*>(sm + L.off_lab);
     uint8_t* s_src = sm + L.off_src;
+    uint8_t* const s_srcA = sm + L.off_src;    // phase C tile buffers
+    uint8_t* const s_srcB = sm + L.off_src2;
     uint16_t* s_v = reinterpret_cast<uint16_t*>(sm + L.off_v);
     uint8_t* s_stage = sm + L.off_stage;
     uint8_t* s_out = sm + L.off_out;
@@ -310,11 +319,12 @@ __global__ void __launch_bounds__(MT, 2)
     load_hsv_lut(s_hsv, tab);
     load_lab_lut(s_lab, tab);
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar2[0], 1);
+        mbar_init(&s_bar2[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    uint32_t par = 0;
+    uint32_t par = 0, par1 = 0;   // phase parity of the two tile barriers
     int* work_counter = reinterpret_cast<int*>(ws);
     const size_t img_px = (size_t)H * W;
     const bool want_stats = hist9 || hsv3 || counters;
@@ -495,9 +505,19 @@ __global__ void __launch_bounds__(MT, 2)
         LFX_TICK(16)
         for (int t = 0; t < ntiles; ++t) {
             const int y0 = t * TR, nr = min(TR, H - y0);
-            mbar_wait(&s_bar, par);
-            par ^= 1;
-            __syncthreads();  // s_dlo / taps visible (t == 0)
+            // double-buffered tiles: tile t sits in buffer t & 1; its successor is requested as soon as every thread
+            // has left tile t-1 (the barrier below), so the copy overlaps this tile's work
+            uint8_t* const s_src = (t & 1) ? s_srcB : s_srcA;
+            if (t & 1) {
+                mbar_wait(&s_bar2[1], par1);
+                par1 ^= 1;
+            } else {
+                mbar_wait(&s_bar2[0], par);
+                par ^= 1;
+            }
+            __syncthreads();  // s_dlo / taps visible (t == 0); tile t-1 fully consumed
+            if (threadIdx.x == 0 && t + 1 < ntiles)
+                issue_tile_load(simg, (t & 1) ? s_srcA : s_srcB, &s_bar2[(t + 1) & 1], y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
             LFX_TICK(17)
             if (want_stats) {
                 // contiguous rows per warp: every warp sees all word columns (the leaf sits in the middle ones)
@@ -603,10 +623,7 @@ __global__ void __launch_bounds__(MT, 2)
                     }
                 }
             }
-            __syncthreads();  // every reader of s_src is done
             LFX_TICK(20)
-            if (threadIdx.x == 0 && t + 1 < ntiles)
-                issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
         }
         if (want_stats) {
             if (counters) {
