@@ -146,10 +146,11 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
 // (x86-64 Pillow wheels do not contract to FMA).  A cheap fp32 evaluation decides first; only
 // results that land within LFX_WARP_EPS of a truncation boundary are re-evaluated in fp64, so
 // the output is bit-identical to the fp64 path at a fraction of its cost.
-// fp32 Horner error bound: each of the 3 steps rounds at magnitude < 2048 (half ulp 1.2e-4), row results feed the
-// column evaluation with |weights| summing to < 1.7 -> < 1.1e-3 in total; 2^-8 leaves a 3.5x margin and sends
-// 0.8 % of the values (instead of 6 %) down the fp64 path.
-#define LFX_WARP_EPS 0.00390625f
+// fp32 error bound: one Horner evaluation rounds three products / three sums at magnitudes below 2048 (half ulp
+// 6.1e-5 each, the first product 3.1e-5) -> < 4e-4; the cubic is linear in its four values, so the row errors reach
+// the column evaluation weighted by |w1|+..+|w4| < 1.7 -> 6.8e-4, plus the column's own 4e-4: < 1.1e-3 in total.
+// 2^-9 keeps a 1.8x margin and sends 0.4 % of the values down the fp64 path.
+#define LFX_WARP_EPS 0.001953125f
 
 __device__ __forceinline__ double cubic64(double v1, double v2, double v3, double v4, double d) {
     const double p1 = v2;

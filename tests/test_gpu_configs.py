@@ -97,3 +97,23 @@ def test_config3_device_balancing_matches_reference_calls(dev):
             assert got.shape == exp.shape and np.array_equal(got, exp), (t.transform_name, t.seed)
             seen += 1
     assert seen == len(tasks)
+
+
+def test_warp_bicubic_stress_against_pillow(dev):
+    """6.3 M interpolated values on pure-noise images (the worst case for the fp32 fast path: taps alternate over the
+    whole range) must equal Pillow's fp64 result bit for bit -- the fp32 path may only be used where it provably
+    cannot change the truncated byte."""
+    rng = np.random.default_rng(2024)
+    imgs = rng.integers(0, 256, (32, 256, 256, 3), dtype=np.uint8)
+    imgs[0] = (np.indices((256, 256)).sum(0) % 2 * 255)[..., None]          # checkerboard 0/255
+    prng = random.Random(5)
+    coeffs, persp = [], []
+    for i in range(32):
+        if i % 2 == 0:
+            coeffs.append(sa.skew_coeffs(prng.uniform(0.05, 0.15), 256, 256)); persp.append(True)
+        else:
+            coeffs.append(sa.shear_coeffs(prng.uniform(-0.2, 0.2), prng.random() < 0.5)); persp.append(False)
+    got = ops.warp_bicubic(up(imgs, dev), np.array(coeffs, np.float64), persp).cpu().numpy()
+    for i in range(32):
+        exp = rc.warp(imgs[i], coeffs[i], persp[i])
+        assert np.array_equal(got[i], exp), (i, int((got[i] != exp).sum()))
