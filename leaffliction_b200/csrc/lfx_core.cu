@@ -99,11 +99,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
+}
+// L2 eviction priorities: the image is read twice (phase A, then phase C ~200 us later) with ~1.6 MB of output
+// streamed out per image in between -- keep it (evict_last) after the first read, release it (evict_first) on the second.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
@@ -124,16 +136,16 @@ __device__ __forceinline__ int refl101(int i, int n) {
 // Rows y0-2 .. y0+nr+1 of the image (BORDER_REFLECT_101 above/below) -> s_src, one mbarrier phase.
 // Called by ONE thread.  H >= 3.
 __device__ void issue_tile_load(const uint8_t* simg, uint8_t* s_src, uint64_t* bar, int y0, int nr, int H, int RB,
-                                const void* extra_g, void* extra_s, uint32_t extra_bytes) {
+                                const void* extra_g, void* extra_s, uint32_t extra_bytes, uint64_t policy) {
     const int first = y0 - 2, rows = nr + 4;
     const int lo = max(first, 0), hi = min(first + rows - 1, H - 1);
     fence_async_smem();
     mbar_expect_tx(bar, (uint32_t)rows * RB + extra_bytes);
-    bulk_g2s(s_src + (size_t)(lo - first) * RB, simg + (size_t)lo * RB, (uint32_t)(hi - lo + 1) * RB, bar);
-    for (int t = 0; t < lo - first; ++t) bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar);
+    bulk_g2s(s_src + (size_t)(lo - first) * RB, simg + (size_t)lo * RB, (uint32_t)(hi - lo + 1) * RB, bar, policy);
+    for (int t = 0; t < lo - first; ++t) bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar, policy);
     for (int t = hi - first + 1; t < rows; ++t)
-        bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar);
-    if (extra_bytes) bulk_g2s(extra_s, extra_g, extra_bytes, bar);
+        bulk_g2s(s_src + (size_t)t * RB, simg + (size_t)refl101(first + t, H) * RB, RB, bar, policy);
+    if (extra_bytes) bulk_g2s(extra_s, extra_g, extra_bytes, bar, l2_policy_evict_last());
 }
 
 // ---------------------------------------------------------------- phase A: blur
@@ -207,9 +219,10 @@ __device__ __forceinline__ void hpass_item(const uint16_t* s_v, uint8_t* brow, i
         acc[c][3] = __dp2a_lo(w3, P.K34, __dp2a_lo(w2, P.K12, __dp2a_lo(w1, P.K_0, 32768u)));
     }
     uint32_t* o = reinterpret_cast<uint32_t*>(brow) + 3 * g;
-    o[0] = pack4(acc[0][0], acc[1][0], acc[2][0], acc[0][1]);
-    o[1] = pack4(acc[1][1], acc[2][1], acc[0][2], acc[1][2]);
-    o[2] = pack4(acc[2][2], acc[0][3], acc[1][3], acc[2][3]);
+    // streaming stores (evict-first): outputs are written once and must not push the image out of L2
+    __stcs(o + 0, pack4(acc[0][0], acc[1][0], acc[2][0], acc[0][1]));
+    __stcs(o + 1, pack4(acc[1][1], acc[2][1], acc[0][2], acc[1][2]));
+    __stcs(o + 2, pack4(acc[2][2], acc[0][3], acc[1][3], acc[2][3]));
 }
 
 // ---------------------------------------------------------------- phase C helpers
@@ -325,6 +338,7 @@ __global__ void __launch_bounds__(MT, 2)
     }
     __syncthreads();
     uint32_t par = 0, par1 = 0;   // phase parity of the two tile barriers
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     int* work_counter = reinterpret_cast<int*>(ws);
     const size_t img_px = (size_t)H * W;
     const bool want_stats = hist9 || hsv3 || counters;
@@ -347,7 +361,7 @@ __global__ void __launch_bounds__(MT, 2)
         if (tacc && threadIdx.x == 0) tk0 = clock64();
 
         // =========================================================== phase A
-        if (threadIdx.x == 0) issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, nullptr, nullptr, 0);
+        if (threadIdx.x == 0) issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, nullptr, nullptr, 0, pol_keep);
         for (int t = 0; t < ntiles; ++t) {
             const int y0 = t * TR, nr = min(TR, H - y0);
             mbar_wait(&s_bar, par);
@@ -407,7 +421,7 @@ __global__ void __launch_bounds__(MT, 2)
             }
             __syncthreads();
             if (threadIdx.x == 0 && t + 1 < ntiles)
-                issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
+                issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0, pol_keep);
             if (blur) {
                 uint8_t* bimg = blur + (size_t)img * img_px * 3 + (size_t)y0 * RB;
                 for (int item = threadIdx.x; item < G * nr; item += MT) {
@@ -460,7 +474,7 @@ __global__ void __launch_bounds__(MT, 2)
         __syncthreads();  // also: every phase-B reader of the union region is done
         const Geo geo = s_geo;
         if (threadIdx.x == 0)
-            issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, cat_lut, sm + L.off_cat, want_stats ? 3 * 256 * 16 : 0);
+            issue_tile_load(simg, s_src, &s_bar, 0, min(TR, H), H, RB, cat_lut, sm + L.off_cat, want_stats ? 3 * 256 * 16 : 0, pol_drop);
         uint8_t* rimg = roi ? roi + (size_t)img * RH * RW * 3 : nullptr;
         if (roi) {
             for (int i = threadIdx.x; i < geo.nw; i += MT) {
@@ -517,7 +531,7 @@ __global__ void __launch_bounds__(MT, 2)
             }
             __syncthreads();  // s_dlo / taps visible (t == 0); tile t-1 fully consumed
             if (threadIdx.x == 0 && t + 1 < ntiles)
-                issue_tile_load(simg, (t & 1) ? s_srcA : s_srcB, &s_bar2[(t + 1) & 1], y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0);
+                issue_tile_load(simg, (t & 1) ? s_srcA : s_srcB, &s_bar2[(t + 1) & 1], y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0, pol_drop);
             LFX_TICK(17)
             if (want_stats) {
                 // contiguous rows per warp: every warp sees all word columns (the leaf sits in the middle ones)
@@ -616,9 +630,9 @@ __global__ void __launch_bounds__(MT, 2)
                             // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255.
                             // (ya*h >> 16) as the high word of (ya << 16) * h: one IMAD.HI with the addend fused
                             const uint32_t ya = (uint32_t)ty.y << 16, yb = (uint32_t)ty.y & 0xFFFF0000u;
-                            o[0] = (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2);
-                            o[1] = (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2);
-                            o[2] = (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2);
+                            __stcs(o + 0, (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2));
+                            __stcs(o + 1, (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2));
+                            __stcs(o + 2, (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2));
                         }
                     }
                 }

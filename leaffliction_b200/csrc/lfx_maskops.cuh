@@ -356,7 +356,7 @@ __device__ void plane_to_bytes16(const uint32_t* p, uint8_t* mask, const C& c) {
         v.y = ((((bits >> 4) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
         v.z = ((((bits >> 8) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu;
         v.w = (((bits >> 12) * 0x00204081u) & 0x01010101u) * 0xFFu;
-        out[i] = v;
+        __stcs(&out[i], v);   // streaming store: written once, never re-read by this kernel
     }
 }
 
