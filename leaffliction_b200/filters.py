@@ -73,9 +73,48 @@ def analyze_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray) -> Di
     gray = ops.cvt_color(_dev(rgb[None]), "gray")
     edges = ops.canny(gray, 80, 160, True).cpu().numpy()[0]
     veins = (edges > 0) & (_mask2d(mask) > 0)
+    hull = convex_hull(p)
+    mean, evecs, evals, ends = pca_axes(p)
     return dict(centroid=(cx, cy), area=m00, n_points=n,
                 left=tuple(p[p[:, 0].argmin()]), right=tuple(p[p[:, 0].argmax()]),
-                top=tuple(p[p[:, 1].argmin()]), bottom=tuple(p[p[:, 1].argmax()]), veins=veins)
+                top=tuple(p[p[:, 1].argmin()]), bottom=tuple(p[p[:, 1].argmax()]), veins=veins,
+                hull=hull, pca_mean=mean, pca_eigenvectors=evecs, pca_eigenvalues=evals, axes=ends)
+
+
+def convex_hull(pts: np.ndarray) -> np.ndarray:
+    """Vertices of the convex hull of integer points [K,2] -> int32 [M,1,2] (analyze.py:77 cv2.convexHull):
+    Andrew's monotone chain in exact integer arithmetic, collinear points dropped."""
+    q = np.unique(np.asarray(pts, np.int64).reshape(-1, 2), axis=0)      # sorted by x, then y
+    if len(q) <= 2:
+        return q.astype(np.int32).reshape(-1, 1, 2)
+
+    def half(seq):
+        out = []
+        for x, y in seq:
+            while len(out) >= 2 and (out[-1][0] - out[-2][0]) * (y - out[-2][1]) - (out[-1][1] - out[-2][1]) * (x - out[-2][0]) <= 0:
+                out.pop()
+            out.append((int(x), int(y)))
+        return out
+    lower, upper = half(q), half(q[::-1])
+    return np.array(lower[:-1] + upper[:-1], np.int32).reshape(-1, 1, 2)
+
+
+def pca_axes(pts: np.ndarray):
+    """analyze.py:88-98: PCA of the contour points (cv2.PCACompute2 on float32 data) and the contour points with the
+    extreme projections on the major / minor axis -> (mean[2], eigenvectors[2,2] rows, eigenvalues[2],
+    ((p0_min, p0_max), (p1_min, p1_max)))."""
+    d = np.asarray(pts, np.float32).reshape(-1, 2)
+    mean = d.mean(axis=0, dtype=np.float64)
+    c = d.astype(np.float64) - mean
+    cov = (c.T @ c) / max(len(d), 1)
+    w, v = np.linalg.eigh(cov)
+    order = np.argsort(w)[::-1]
+    evals, evecs = w[order], v[:, order].T
+    ends = []
+    for k in range(2):
+        proj = d.astype(np.float64) @ evecs[k]
+        ends.append((tuple(int(t) for t in d[int(proj.argmin())]), tuple(int(t) for t in d[int(proj.argmax())])))
+    return mean, evecs, evals, tuple(ends)
 
 
 def apply_analyze_filter(rgb: np.ndarray, mask: Optional[np.ndarray], contour: Optional[np.ndarray],

@@ -153,3 +153,28 @@ def test_augment_arrays_matches_per_task_reference():
             noise = np.random.normal(0, 5, imgs[i].shape)
             e = rc.distortion(imgs[i], noise, random.uniform(0, 2))
         assert np.array_equal(got[i], e), (i, t)
+
+
+def test_analyze_record_hull_and_pca():
+    """analyze.py:43-98 numeric record: centroid of the contour polygon, extreme points, convex hull, PCA axes --
+    against OpenCV on the same contour."""
+    cv2 = pytest.importorskip("cv2")
+    from leaffliction_b200 import filters
+    cfg = transform.default_config(mask_strategy="hsv_h", grabcut_refine=False, mask_upscale_factor=1.0, mask_upscale_long_side=0)
+    for i in range(4):
+        im = synth.leaf_image(i)
+        mask, cnt = transform.make_mask(im, cfg)
+        rec = filters.analyze_record(im, mask, cnt)
+        M = cv2.moments(cnt)
+        assert rec["centroid"] == (int(M["m10"] / M["m00"]), int(M["m01"] / M["m00"]))
+        hull = cv2.convexHull(cnt)
+        assert {tuple(p) for p in hull[:, 0, :]} == {tuple(p) for p in rec["hull"][:, 0, :]}
+        data = cnt[:, 0, :].astype(np.float32)
+        mean, evec, evals = cv2.PCACompute2(data, mean=None)
+        assert np.allclose(rec["pca_mean"], mean[0], atol=1e-3)
+        assert np.allclose(rec["pca_eigenvalues"], evals[:, 0], rtol=1e-4)
+        for k in range(2):
+            assert abs(abs(float(np.dot(rec["pca_eigenvectors"][k], evec[k]))) - 1.0) < 1e-4       # same axis up to sign
+            proj = data @ evec[k]
+            got = {float(np.dot(np.array(p, np.float32), evec[k])) for p in rec["axes"][k]}
+            assert abs(min(got) - float(proj.min())) < 1e-2 and abs(max(got) - float(proj.max())) < 1e-2
