@@ -98,6 +98,23 @@ int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, i
 int lfx_legacy_normal_u8(const uint32_t* seeds, uint8_t* out, int B, int n, double loc, double scale,
                          lfx_stream_t stream);
 
+/* Host-side (no device work, callable without a GPU): the parameters one balancing task draws --
+ * `_process_single_transformation` (dataset_balancer.py:201-207) builds ImageAugmenter(seed), which seeds
+ * Python's `random` (image_augmenter.py:16-18), and the method consumes that stream in the reference's order
+ * (:22 flip, :35 rotate, :50 skew, :79-80 shear, :100-105 crop, :126 distortion).  Restates CPython's
+ * MT19937 `random.seed(int)` / `random()` / `choice` / `randint` and PIL's rotate geometry.
+ * transform[B]: LFX_AUG_*; seed[B]: task seeds (must be non-zero: seed 0 leaves the reference unseeded);
+ * iparams[B][8], dparams[B][8] (HOST pointers), per transform:
+ *   FLIP       i0 = lfx_flip mode (0 left-right, 1 top-bottom)
+ *   ROTATE     i0..i5 = 16.16 inverse affine, i6 = nw, i7 = nh (lfx_rotate_nn params); d0 = angle
+ *   SKEW/SHEAR d0..d7 = lfx_warp_bicubic coefficients, i0 = perspective flag
+ *   CROP       i0..i3 = left, top, nw, nh (lfx_crop_lanczos box)
+ *   DISTORTION i0 = cut = int(H*W*cutoff // 100) (lfx_distort), d0 = cutoff
+ * threads: host threads to use (0 = all). */
+enum { LFX_AUG_FLIP = 0, LFX_AUG_ROTATE = 1, LFX_AUG_SKEW = 2, LFX_AUG_SHEAR = 3, LFX_AUG_CROP = 4, LFX_AUG_DISTORTION = 5 };
+int lfx_draw_augment_params(const int32_t* transform, const uint32_t* seed, int B, int H, int W,
+                            int32_t* iparams, double* dparams, int threads);
+
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
 /* cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}) (mask.py:87,103; blur.py:27; hist.py:184).

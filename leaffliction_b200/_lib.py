@@ -58,6 +58,7 @@ _SIGS = {
     "lfx_saliency_blur": (C.c_int, [_P, _P, _P, _I, _I, _I, C.c_double, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
     "lfx_pipeline_core_workspace": (C.c_size_t, [_I, _I, _I]),
     "lfx_legacy_normal_u8": (C.c_int, [_P, _P, _I, _I, C.c_double, C.c_double, _P]),
+    "lfx_draw_augment_params": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I]),
     "lfx_pipeline_core": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_double,
                                     C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
 }

@@ -284,52 +284,110 @@ def draw_task_params(transform: str, seed: int, h: int, w: int, want_noise: bool
     raise ValueError(f"unknown transform {transform!r}")
 
 
+TRANSFORM_CODE = {name: i for i, name in enumerate(TRANSFORMATIONS)}     # == LFX_AUG_* of include/leafx.h
+
+
+def draw_params_batch(transforms, seeds, h: int, w: int, threads: int = 0):
+    """Parameters of a batch of balancing tasks, drawn natively (lfx_draw_augment_params: CPython's MT19937
+    `random` stream of each task seed, consumed in the reference's order; no GPU involved).
+    transforms: int codes (TRANSFORM_CODE) or names; seeds: ints.  Returns (iparams int32 [B,8], dparams float64 [B,8])
+    laid out as include/leafx.h documents.  Tasks with seed 0 (unseeded in the reference, image_augmenter.py:16)
+    are drawn from the interpreter's current global stream by draw_task_params."""
+    import ctypes as C
+    from . import _lib
+    tr = np.ascontiguousarray([TRANSFORM_CODE[t] if isinstance(t, str) else int(t) for t in transforms]
+                              if not isinstance(transforms, np.ndarray) else transforms, dtype=np.int32)
+    sd = np.ascontiguousarray(seeds, dtype=np.int64)
+    if sd.size and (sd.min() < 0 or sd.max() > 0xFFFFFFFF):
+        raise ValueError("task seeds must be in [0, 2^32)")
+    sd32 = sd.astype(np.uint32)
+    B = len(tr)
+    ip, dp = np.zeros((B, 8), np.int32), np.zeros((B, 8), np.float64)
+    P = C.c_void_p
+    _lib.check(_lib.load().lfx_draw_augment_params(tr.ctypes.data_as(P), sd32.ctypes.data_as(P), B, int(h), int(w),
+                                                   ip.ctypes.data_as(P), dp.ctypes.data_as(P), int(threads)))
+    for i in np.nonzero(sd == 0)[0]:
+        name = TRANSFORMATIONS[tr[i]]
+        p = draw_task_params(name, 0, h, w, want_noise=False)
+        ip[i], dp[i] = 0, 0.0
+        if name == "flip":
+            ip[i, 0] = 0 if p[0] else 1
+        elif name == "rotate":
+            m, nw, nh = rotate_matrix(p[0], w, h)
+            if isinstance(m, str):
+                m, nw, nh = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0], w, h
+            ip[i], dp[i, 0] = fixed_affine(m) + [nw, nh], p[0]
+        elif name in ("skew", "shear"):
+            dp[i], ip[i, 0] = p[0], int(p[1])
+        elif name == "crop":
+            ip[i, :4] = p
+        else:
+            ip[i, 0], dp[i, 0] = int(h * w * p[1] // 100), p[1]
+    return ip, dp
+
+
+class TaskArrays:
+    """Struct-of-arrays view of a task list: transform codes, seeds, dataset index of the source image."""
+
+    def __init__(self, tasks):
+        self.transform = np.fromiter((TRANSFORM_CODE[t.transform_name] for t in tasks), np.int32, len(tasks))
+        self.seed = np.fromiter((t.seed for t in tasks), np.int64, len(tasks))
+        self.source_index = np.fromiter((t.source_index for t in tasks), np.int64, len(tasks))
+
+    def __len__(self):
+        return len(self.transform)
+
+    def slice(self, lo, hi):
+        o = object.__new__(TaskArrays)
+        o.transform, o.seed, o.source_index = self.transform[lo:hi], self.seed[lo:hi], self.source_index[lo:hi]
+        return o
+
+
 def augment_device(x, tasks, device_noise: bool = True):
-    """Run balance tasks on images already resident in HBM.  `x`: uint8 [N,H,W,3] CUDA tensor; `tasks`: objects with
-    .transform_name, .seed, .source_index.  Returns {transform: (task indices, output tensor or rotate slab + sizes)}.
-    With `device_noise` the distortion noise (NumPy's legacy MT19937 normal stream of the task seed) is generated on
-    the GPU (ops.legacy_normal_noise) instead of by np.random on the host."""
+    """Run balance tasks on images already resident in HBM.  `x`: uint8 [N,H,W,3] CUDA tensor; `tasks`: a TaskArrays or
+    a list of objects with .transform_name, .seed, .source_index.  Returns {key: (task indices, output tensor)} with
+    key in flip / rotate / warp (skew + shear) / crop / distortion; rotate returns (indices, slab, [(nh, nw)]).
+    Parameters come from one native call (draw_params_batch); with `device_noise` the distortion noise (NumPy's
+    legacy MT19937 normal stream of the task seed) is generated on the GPU (ops.legacy_normal_noise) instead of by
+    np.random on the host."""
     import torch
     ops = _ops()
     h, w = int(x.shape[1]), int(x.shape[2])
-    groups = {t: [] for t in TRANSFORMATIONS}
-    for i, t in enumerate(tasks):
-        groups[t.transform_name].append(i)
-    out = {}
+    ta = tasks if isinstance(tasks, TaskArrays) else TaskArrays(tasks)
+    ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
     dev = x.device
+    src = torch.from_numpy(ta.source_index).to(dev)
+    out = {}
+
+    def ids_of(*names):
+        return np.nonzero(np.isin(ta.transform, [TRANSFORM_CODE[n] for n in names]))[0]
 
     def gather(ids):
-        return x.index_select(0, torch.tensor([tasks[i].source_index for i in ids], dtype=torch.int64, device=dev))
+        return x.index_select(0, src[torch.from_numpy(ids).to(dev)])
 
-    ids = groups["flip"]
-    if ids:
-        lr = [draw_task_params("flip", tasks[i].seed, h, w)[0] for i in ids]
-        out["flip"] = (ids, ops.flip(gather(ids), lr))
-    ids = groups["rotate"]
-    if ids:
-        params = []
-        for i in ids:
-            m, nw, nh = rotate_matrix(draw_task_params("rotate", tasks[i].seed, h, w)[0], w, h)
-            if isinstance(m, str):       # multiples of 90 degrees cannot come out of uniform(-30, 30) except 0.0
-                m, nw, nh = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0], w, h
-            params.append(fixed_affine(m) + [nw, nh])
-        slab, stride = ops.rotate_nn(gather(ids), np.array(params, np.int32), 255)
-        out["rotate"] = (ids, slab, [(p[7], p[6]) for p in params])
-    ids = groups["skew"] + groups["shear"]
-    if ids:
-        pr = [draw_task_params(tasks[i].transform_name, tasks[i].seed, h, w) for i in ids]
-        out["warp"] = (ids, ops.warp_bicubic(gather(ids), np.array([p[0] for p in pr], np.float64), [p[1] for p in pr]))
-    ids = groups["crop"]
-    if ids:
-        boxes = np.array([draw_task_params("crop", tasks[i].seed, h, w) for i in ids], np.int32)
-        out["crop"] = (ids, ops.crop_lanczos(gather(ids), boxes, (h, w)))
-    ids = groups["distortion"]
-    if ids:
-        pr = [draw_task_params("distortion", tasks[i].seed, h, w, want_noise=not device_noise) for i in ids]
-        cuts = [int(h * w * p[1] // 100) for p in pr]
+    ids = ids_of("flip")
+    if len(ids):
+        out["flip"] = (ids, ops.flip(gather(ids), ip[ids, 0]))
+    ids = ids_of("rotate")
+    if len(ids):
+        slab, stride = ops.rotate_nn(gather(ids), ip[ids], 255)
+        out["rotate"] = (ids, slab, ip[ids][:, [7, 6]])
+    ids = ids_of("skew", "shear")
+    if len(ids):
+        out["warp"] = (ids, ops.warp_bicubic(gather(ids), dp[ids], ip[ids, 0]))
+    ids = ids_of("crop")
+    if len(ids):
+        out["crop"] = (ids, ops.crop_lanczos(gather(ids), ip[ids, :4], (h, w)))
+    ids = ids_of("distortion")
+    if len(ids):
         if device_noise:
-            noise = ops.legacy_normal_noise([tasks[i].seed for i in ids], h * w * 3, NOISE_LEVEL, dev).view(len(ids), h, w, 3)
+            noise = ops.legacy_normal_noise(ta.seed[ids], h * w * 3, NOISE_LEVEL, dev).view(len(ids), h, w, 3)
         else:
-            noise = torch.from_numpy(np.stack([p[0] for p in pr])).to(dev)
-        out["distortion"] = (ids, ops.distort(gather(ids), noise, cuts))
+            noises = []
+            for sd in ta.seed[ids]:
+                if sd:
+                    np.random.seed(int(sd))
+                noises.append(np.random.normal(0, NOISE_LEVEL, (h, w, 3)).astype(np.uint8))
+            noise = torch.from_numpy(np.stack(noises)).to(dev)
+        out["distortion"] = (ids, ops.distort(gather(ids), noise, ip[ids, 0]))
     return out

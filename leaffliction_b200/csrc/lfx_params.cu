@@ -1,0 +1,221 @@
+// Host-side (no CUDA) batch parameter drawing for the class-balancing augment tasks: what
+// `_process_single_transformation` (srcs/preprocessing/dataset_balancer.py:201-207) draws for one task --
+// a fresh ImageAugmenter(seed) seeds Python's `random` (image_augmenter.py:16-18, only `if seed:`) and the
+// method then consumes the stream in the reference's order (image_augmenter.py:22,35,50,79-80,100-105,126).
+// At 36,864 tasks the interpreter's `random.seed()` + draws cost ~13 us per task and were 95 % of the
+// balancing wall time; this restatement runs ~1.5 us per task per host thread.
+//
+// CPython's `random` is restated from its published algorithm (MT19937ar `init_by_array` seeding with the
+// 32-bit chunks of abs(seed); `random()` = genrand_res53; `_randbelow_with_getrandbits` rejection sampling for
+// `choice` / `randint`); PIL's rotate geometry (Image.rotate with expand=True) and libImaging's 16.16 affine
+// coefficients follow SURVEY.md A.1.  tests/test_params_cpu.py checks every output against the interpreter.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <thread>
+#include <vector>
+
+#include "lfx_common.cuh"
+
+namespace {
+
+constexpr int MT_N = 624, MT_M = 397;
+
+struct PyRandom {
+    uint32_t mt[MT_N];
+    int idx;  // next word of the current block; words < idx are already twisted in place
+
+    static const uint32_t* base_state() {  // init_genrand(19650218), shared by every init_by_array
+        static uint32_t base[MT_N];
+        static bool done = [] {
+            uint32_t s = 19650218u;
+            for (int i = 0; i < MT_N; ++i) {
+                base[i] = s;
+                s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)(i + 1);
+            }
+            return true;
+        }();
+        (void)done;
+        return base;
+    }
+
+    void seed(uint32_t key) {  // random.seed(int) for 0 <= int < 2^32: init_by_array({key}, 1)
+        memcpy(mt, base_state(), sizeof(mt));
+        int i = 1;
+        for (int k = MT_N; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + key;  // + init_key[0] + j, j == 0
+            if (++i >= MT_N) {
+                mt[0] = mt[MT_N - 1];
+                i = 1;
+            }
+        }
+        for (int k = MT_N - 1; k; --k) {
+            mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+            if (++i >= MT_N) {
+                mt[0] = mt[MT_N - 1];
+                i = 1;
+            }
+        }
+        mt[0] = 0x80000000u;
+        idx = 0;
+    }
+
+    // The reference generator twists a whole block in place in ascending order; doing the same word by word on
+    // demand is identical (word i only reads words that are still old, or already new, exactly as there).
+    uint32_t next_u32() {
+        if (idx == MT_N) idx = 0;
+        const int i = idx++;
+        const int i1 = (i + 1 == MT_N) ? 0 : i + 1;
+        const int im = (i + MT_M >= MT_N) ? i + MT_M - MT_N : i + MT_M;
+        const uint32_t y = (mt[i] & 0x80000000u) | (mt[i1] & 0x7FFFFFFFu);
+        uint32_t v = mt[im] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+        mt[i] = v;
+        v ^= (v >> 11);
+        v ^= (v << 7) & 0x9D2C5680u;
+        v ^= (v << 15) & 0xEFC60000u;
+        v ^= (v >> 18);
+        return v;
+    }
+    double random() {
+        const uint32_t a = next_u32() >> 5, b = next_u32() >> 6;
+        return (a * 67108864.0 + b) * (1.0 / 9007199254740992.0);
+    }
+    double uniform(double a, double b) { return a + (b - a) * random(); }
+    uint32_t randbelow(uint32_t n) {  // n >= 1; getrandbits(k) with k = n.bit_length() <= 32
+        int k = 0;
+        for (uint32_t t = n; t; t >>= 1) ++k;
+        uint32_t r = next_u32() >> (32 - k);
+        while (r >= n) r = next_u32() >> (32 - k);
+        return r;
+    }
+};
+
+double py_round15(double v) {  // round(v, 15): correctly rounded decimal, then the nearest double
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.15f", v);
+    return strtod(buf, nullptr);
+}
+
+double py_floordiv(double vx, double wx) {  // float.__floordiv__
+    double mod = fmod(vx, wx);
+    double div = (vx - mod) / wx;
+    if (mod != 0.0 && ((wx < 0) != (mod < 0))) div -= 1.0;
+    if (div == 0.0) return copysign(0.0, vx / wx);
+    double fl = floor(div);
+    if (div - fl > 0.5) fl += 1.0;
+    return fl;
+}
+
+inline int32_t fix16(double v) { return (int32_t)floor(v * 65536.0 + 0.5); }
+
+// PIL Image.rotate(angle, resample=NEAREST, expand=True) -> 16.16 inverse-affine coefficients + output size.
+void rotate_params(double angle, int w, int h, int32_t* ip) {
+    angle = fmod(angle, 360.0);
+    if (angle < 0) angle += 360.0;
+    double m[6] = {1.0, 0.0, 0.0, 0.0, 1.0, 0.0};
+    int nw = w, nh = h;
+    if (angle != 0.0) {  // 90/180/270 cannot come out of uniform(-30, 30)
+        const double cx = w / 2.0, cy = h / 2.0;
+        const double a = -(angle * (M_PI / 180.0));
+        const double c = py_round15(cos(a)), s = py_round15(sin(a)), ns = py_round15(-sin(a));
+        m[0] = c, m[1] = s, m[2] = 0.0, m[3] = ns, m[4] = c, m[5] = 0.0;
+        const double t2 = m[0] * -cx + m[1] * -cy + m[2], t5 = m[3] * -cx + m[4] * -cy + m[5];
+        m[2] = t2 + cx;
+        m[5] = t5 + cy;
+        const double px[4] = {0.0, (double)w, (double)w, 0.0}, py[4] = {0.0, 0.0, (double)h, (double)h};
+        double xmin = 0, xmax = 0, ymin = 0, ymax = 0;
+        for (int k = 0; k < 4; ++k) {
+            const double X = m[0] * px[k] + m[1] * py[k] + m[2], Y = m[3] * px[k] + m[4] * py[k] + m[5];
+            if (k == 0 || X < xmin) xmin = X;
+            if (k == 0 || X > xmax) xmax = X;
+            if (k == 0 || Y < ymin) ymin = Y;
+            if (k == 0 || Y > ymax) ymax = Y;
+        }
+        nw = (int)(ceil(xmax) - floor(xmin));
+        nh = (int)(ceil(ymax) - floor(ymin));
+        const double ox = -(nw - w) / 2.0, oy = -(nh - h) / 2.0;
+        const double n2 = m[0] * ox + m[1] * oy + m[2], n5 = m[3] * ox + m[4] * oy + m[5];
+        m[2] = n2;
+        m[5] = n5;
+    }
+    ip[0] = fix16(m[0]);
+    ip[1] = fix16(m[1]);
+    ip[2] = fix16(m[2] + m[0] * 0.5 + m[1] * 0.5);
+    ip[3] = fix16(m[3]);
+    ip[4] = fix16(m[4]);
+    ip[5] = fix16(m[5] + m[3] * 0.5 + m[4] * 0.5);
+    ip[6] = nw;
+    ip[7] = nh;
+}
+
+void draw_one(int transform, uint32_t seed, int H, int W, int32_t* ip, double* dp) {
+    PyRandom r;
+    r.seed(seed);
+    memset(ip, 0, 8 * sizeof(int32_t));
+    for (int k = 0; k < 8; ++k) dp[k] = 0.0;
+    switch (transform) {
+        case LFX_AUG_FLIP:  // random.choice([True, False]): index 0 -> FLIP_LEFT_RIGHT
+            ip[0] = r.randbelow(2) == 0 ? 0 : 1;
+            break;
+        case LFX_AUG_ROTATE:
+            dp[0] = r.uniform(-30.0, 30.0);
+            rotate_params(dp[0], W, H, ip);
+            break;
+        case LFX_AUG_SKEW: {
+            const double s = r.uniform(0.05, 0.15);
+            dp[0] = 1 + s, dp[2] = -s * W, dp[4] = 1 + s, dp[5] = -s * H;
+            ip[0] = 1;  // PERSPECTIVE
+            break;
+        }
+        case LFX_AUG_SHEAR: {
+            const double k = r.uniform(-0.2, 0.2);
+            dp[0] = 1.0, dp[4] = 1.0;
+            if (r.randbelow(2) == 0) dp[1] = k; else dp[3] = k;
+            ip[0] = 0;  // AFFINE
+            break;
+        }
+        case LFX_AUG_CROP: {
+            const double ratio = r.uniform(0.8, 0.95);
+            const int nw = (int)(W * ratio), nh = (int)(H * ratio);
+            ip[2] = nw, ip[3] = nh;
+            ip[0] = (int32_t)r.randbelow((uint32_t)(W - nw + 1));
+            ip[1] = (int32_t)r.randbelow((uint32_t)(H - nh + 1));
+            break;
+        }
+        case LFX_AUG_DISTORTION:
+            dp[0] = r.uniform(0.0, 2.0);
+            ip[0] = (int32_t)py_floordiv((double)((long long)H * W) * dp[0], 100.0);
+            break;
+    }
+}
+
+}  // namespace
+
+extern "C" int lfx_draw_augment_params(const int32_t* transform, const uint32_t* seed, int B, int H, int W, int32_t* iparams,
+                                       double* dparams, int threads) {
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(transform && seed && iparams && dparams && B > 0 && H > 0 && W > 0, LFX_ERR_ARG, "draw_augment_params: bad arguments");
+    for (int i = 0; i < B; ++i)
+        LFX_REQUIRE(transform[i] >= LFX_AUG_FLIP && transform[i] <= LFX_AUG_DISTORTION, LFX_ERR_ARG, "draw_augment_params: unknown transform %d at task %d",
+                    transform[i], i);
+    PyRandom::base_state();
+    int nt = threads > 0 ? threads : (int)std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 64 ? 64 : nt);
+    if (B < 2048) nt = 1;
+    auto work = [&](int lo, int hi) {
+        for (int i = lo; i < hi; ++i) draw_one(transform[i], seed[i], H, W, iparams + (size_t)i * 8, dparams + (size_t)i * 8);
+    };
+    if (nt == 1) {
+        work(0, B);
+    } else {
+        std::vector<std::thread> pool;
+        const int per = (B + nt - 1) / nt;
+        for (int t = 0; t < nt; ++t) {
+            const int lo = t * per, hi = lo + per < B ? lo + per : B;
+            if (lo < hi) pool.emplace_back(work, lo, hi);
+        }
+        for (auto& th : pool) th.join();
+    }
+    return LFX_OK;
+}

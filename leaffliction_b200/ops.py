@@ -273,7 +273,10 @@ def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
-    mode = _dev([0 if lr else 1 for lr in left_right], np.int32, x.device)
+    if isinstance(left_right, np.ndarray) and left_right.dtype == np.int32:
+        mode = _dev(left_right, np.int32, x.device)                 # already lfx_flip modes (0 = left-right)
+    else:
+        mode = _dev([0 if lr else 1 for lr in left_right], np.int32, x.device)
     out = torch.empty_like(x)
     _lib.check(lib.lfx_flip(_p(x), _p(out), B, H, W, _p(mode), _stream()))
     return out
@@ -299,7 +302,7 @@ def warp_bicubic(x: torch.Tensor, coeffs: np.ndarray, perspective: Sequence[bool
     lib = _ready(x)
     B, H, W, _ = x.shape
     dc = coeffs if isinstance(coeffs, torch.Tensor) else _dev(np.asarray(coeffs, np.float64).reshape(B, 8), np.float64, x.device)
-    dpz = perspective if isinstance(perspective, torch.Tensor) else _dev([1 if p else 0 for p in perspective], np.int32, x.device)
+    dpz = perspective if isinstance(perspective, torch.Tensor) else _dev(np.asarray(perspective).astype(bool).astype(np.int32), np.int32, x.device)
     out = torch.empty_like(x)
     _lib.check(lib.lfx_warp_bicubic(_p(x), _p(out), B, H, W, _p(dc), _p(dpz), _stream()))
     return out
@@ -359,10 +362,10 @@ class CropPlan:
         OH, OW = int(out_hw[0]), int(out_hw[1])
         boxes = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
         off = np.zeros((len(boxes), 4), np.int32)
-        for i in range(len(boxes)):
-            xr, xk = _lanczos.get(boxes[i, 2], OW)
-            yr, yk = _lanczos.get(boxes[i, 3], OH)
-            off[i] = (xr, xk, yr, yk)
+        for col, osz, c0 in ((2, OW, 0), (3, OH, 2)):               # one table per distinct source size
+            sizes, inv = np.unique(boxes[:, col], return_inverse=True)
+            rows = np.array([_lanczos.get(int(sz), osz) for sz in sizes], np.int32).reshape(-1, 2)
+            off[:, c0:c0 + 2] = rows[inv.reshape(-1)]
         self.out_hw = (OH, OW)
         self.tb, self.tk = _lanczos.device(device)
         self.kstride = _lanczos.kstride
@@ -405,11 +408,10 @@ def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc:
     if not torch.cuda.is_available():
         raise RuntimeError("leaffliction_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
-    seeds = [int(s) for s in seeds]
+    seeds = np.asarray(seeds, np.int64).reshape(-1)
     out = torch.empty((len(seeds), int(n)), dtype=torch.uint8, device=device)
-    ds = _dev(np.array([s & 0xFFFFFFFF for s in seeds], np.uint32).view(np.int32), np.int32, device)
+    ds = _dev((seeds & 0xFFFFFFFF).astype(np.uint32).view(np.int32), np.int32, device)
     _lib.check(lib.lfx_legacy_normal_u8(_p(ds), _p(out), len(seeds), int(n), float(loc), float(scale), _stream()))
-    for i, s in enumerate(seeds):
-        if s == 0:
-            out[i] = torch.from_numpy(np.random.normal(loc, scale, int(n)).astype(np.uint8)).to(device)
+    for i in np.nonzero(seeds == 0)[0]:
+        out[int(i)] = torch.from_numpy(np.random.normal(loc, scale, int(n)).astype(np.uint8)).to(device)
     return out

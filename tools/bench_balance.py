@@ -25,7 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--images", type=int, default=65536)
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--chunk", type=int, default=6144)
+    ap.add_argument("--chunk", type=int, default=65536, help="tasks per augment_device call on one rank")
     ap.add_argument("--host-noise", action="store_true", help="draw the distortion noise with np.random on the host (reference way)")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -49,18 +49,22 @@ def main():
     merged, _ = balance.allreduce_histograms(part, device=dev)
     assert merged.tolist() == per_class
     plan, tasks = balance.tasks_for_labels(labels, names, plants, seed=42)     # identical on every rank
-    mine = [tasks[i] for i in balance.shard(len(tasks), rank, world)]
+    mine = augment.TaskArrays([tasks[i] for i in balance.shard(len(tasks), rank, world)])
     t_plan = time.perf_counter() - t0
 
     def run():
         n_out = 0
         for c0 in range(0, len(mine), args.chunk):
-            res = augment.augment_device(x, mine[c0:c0 + args.chunk], device_noise=not args.host_noise)
+            res = augment.augment_device(x, mine.slice(c0, c0 + args.chunk), device_noise=not args.host_noise)
             n_out += sum(len(v[0]) for v in res.values())
         return n_out
 
-    run_small = augment.augment_device(x, mine[:64], device_noise=not args.host_noise)   # warm-up (module load, tables)
-    del run_small
+    # warm-up: a strided sample that contains every transform (module load, Lanczos tables, allocator pools)
+    step = max(1, len(mine) // 512)
+    warm = [tasks[i] for i in list(balance.shard(len(tasks), rank, world))[::step]]
+    augment.augment_device(x, warm, device_noise=not args.host_noise)
+    if not args.host_noise:
+        run()                                                          # one full untimed pass (allocator pools at full size)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
