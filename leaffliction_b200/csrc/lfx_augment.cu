@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
 // 6.1e-5 each, the first product 3.1e-5) -> < 4e-4; the cubic is linear in its four values, so the row errors reach
 // the column evaluation weighted by |w1|+..+|w4| < 1.7 -> 6.8e-4, plus the column's own 4e-4: < 1.1e-3 in total.
 // 2^-9 keeps a 1.8x margin and sends 0.4 % of the values down the fp64 path.
+// The fp64 re-evaluations are DEFERRED: a risky value is pushed on a per-block queue and the whole block evaluates the
+// queue after the band (one value per thread).  Evaluated in place, one risky lane made its whole warp walk the fp64
+// code -- 12 % of all warp-level evaluations for 0.4 % of the values.
 #define LFX_WARP_EPS 0.001953125f
+constexpr int WB_QCAP = 1024;  // queue entries (u16 index of the value inside the band); overflow is evaluated in place
 
 __device__ __forceinline__ double cubic64(double v1, double v2, double v3, double v4, double d) {
     const double p1 = v2;
@@ -172,12 +176,20 @@ __device__ __forceinline__ float cubic32(float v1, float v2, float v3, float v4,
     const float p4 = -v1 + v2 - v3 + v4;
     return v2 + d * (p2 + d * (p3 + d * p4));
 }
+__device__ __forceinline__ float biased(uint8_t v) { return __uint_as_float(0x4B000000u | v); }  // 2^23 + v: a LOP3, no I2F
+// Truncated byte of the fp32 value + whether fp64 must decide.  Adding 2^23 rounds f to the nearest integer r (ties
+// irrelevant: they are risky); the low bits of that sum ARE r, so neither F2I nor FRND (quarter-rate pipe) is needed.
+// risky <=> f within EPS of an integer (either side), or outside (EPS, 255 - EPS).
+__device__ __forceinline__ uint8_t warp_trunc(float f, bool& risky) {
+    const float fb = f + 8388608.f;
+    const float r = fb - 8388608.f;
+    risky = !(fabsf(f - r) >= LFX_WARP_EPS) || !(f >= LFX_WARP_EPS) || !(f <= 255.f - LFX_WARP_EPS);   // NaN-safe
+    return (uint8_t)((__float_as_uint(fb) & 0x1FFu) - (r > f ? 1u : 0u));
+}
 
-// One output pixel of PIL's transform(..., BICUBIC): `rows` points at image row `r0` (global image: r0 = 0;
-// staged band in shared memory: r0 = first staged row); rows outside [0,H) are never dereferenced.
-__device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H, int W, int x, int y, const double* a,
-                                              bool is_persp, uint8_t res[3]) {
-    res[0] = res[1] = res[2] = 0;
+// Source coordinates of output pixel (x, y) exactly as Pillow computes them; false = outside (pixel stays 0).
+__device__ __forceinline__ bool warp_coords(int x, int y, int H, int W, const double* a, bool is_persp, int& xf, int& yf, double& dx,
+                                            double& dy) {
     const double xc = (double)x + 0.5, yc = (double)y + 0.5;
     double xin = __dadd_rn(__dadd_rn(__dmul_rn(a[0], xc), __dmul_rn(a[1], yc)), a[2]);
     double yin = __dadd_rn(__dadd_rn(__dmul_rn(a[3], xc), __dmul_rn(a[4], yc)), a[5]);
@@ -186,57 +198,94 @@ __device__ __forceinline__ void bicubic_pixel(const uint8_t* rows, int r0, int H
         xin = __ddiv_rn(xin, den);
         yin = __ddiv_rn(yin, den);
     }
-    if (xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H) return;
+    if (xin < 0.0 || xin >= (double)W || yin < 0.0 || yin >= (double)H) return false;
     xin = __dadd_rn(xin, -0.5);
     yin = __dadd_rn(yin, -0.5);
-    const int xf = (int)floor(xin), yf = (int)floor(yin);
-    const double dx = __dadd_rn(xin, -(double)xf), dy = __dadd_rn(yin, -(double)yf);
-    const int xb = xf - 1, yb = yf - 1;
+    xf = (int)floor(xin);
+    yf = (int)floor(yin);
+    dx = __dadd_rn(xin, -(double)xf);
+    dy = __dadd_rn(yin, -(double)yf);
+    return true;
+}
+
+// Rows 1..3 of the 4x4 window reuse the previous row's VALUE when they fall outside the image (Geometry.c
+// BICUBIC_BODY) and row 0 is clamped; the previous row is then itself the clamped row, so the rule equals clamping the
+// row index.  `rows` points at image row `r0`.
+__device__ __forceinline__ int warp_row_off(int yy, int r0, int H, int W) { return (min(max(yy, 0), H - 1) - r0) * W * 3; }
+
+// The reference value (fp64) of channel c of output pixel (x, y).
+__device__ __noinline__ uint8_t bicubic_value64(const uint8_t* rows, int r0, int H, int W, int x, int y, int c, const double* a,
+                                                bool is_persp) {
+    int xf, yf;
+    double dx, dy;
+    if (!warp_coords(x, y, H, W, a, is_persp, xf, yf, dx, dy)) return 0;
     int xo[4];
 #pragma unroll
-    for (int t = 0; t < 4; ++t) xo[t] = min(max(xb + t, 0), W - 1) * 3;
-    // rows 1..3 of the 4x4 window reuse the previous row's VALUE when outside the image (Geometry.c BICUBIC_BODY)
-    const uint8_t* rowp[4];
-    bool rowok[4];
+    for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3 + c;
+    double dv[4];
 #pragma unroll
     for (int rj = 0; rj < 4; ++rj) {
-        const int yy = yb + rj;
-        rowok[rj] = (rj == 0) || (yy >= 0 && yy < H);
-        rowp[rj] = rows + (size_t)(min(max(yy, 0), H - 1) - r0) * W * 3;
+        const uint8_t* rp = rows + warp_row_off(yf - 1 + rj, r0, H, W);
+        dv[rj] = cubic64(rp[xo[0]], rp[xo[1]], rp[xo[2]], rp[xo[3]], dx);
     }
+    const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
+    return v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
+}
+
+// One output pixel of PIL's transform(..., BICUBIC) by the fp32 fast path: res[] holds the truncated fp32 values,
+// the return value has bit c set when channel c must be re-evaluated in fp64.
+__device__ __forceinline__ uint32_t bicubic_pixel(const uint8_t* rows, int r0, int H, int W, int x, int y, const double* a, bool is_persp,
+                                                  uint8_t res[3]) {
+    res[0] = res[1] = res[2] = 0;
+    int xf, yf;
+    double dx, dy;
+    if (!warp_coords(x, y, H, W, a, is_persp, xf, yf, dx, dy)) return 0u;
+    int xo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
     const float fdx = (float)dx, fdy = (float)dy;
+    uint32_t risky = 0u;
+    // cubic(v1..v4, 0) == v2 exactly (v2 + 0 * finite), in fp32 and in fp64 alike.  The reference's shear maps one axis
+    // with the identity (image_augmenter.py:82: yin = yc or xin = xc), so a whole image has dy == 0 or dx == 0:
+    // dy == 0 needs only the row yf (always inside the image), dx == 0 only the column xf of each row.
+    if (dy == 0.0) {
+        const uint8_t* rp = rows + warp_row_off(yf, r0, H, W);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float fv = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+            bool rk;
+            res[c] = warp_trunc(fv, rk);
+            risky |= rk ? (1u << c) : 0u;
+        }
+        return risky;
+    }
+    const uint8_t* rp0 = rows + warp_row_off(yf - 1, r0, H, W);
+    const uint8_t* rp1 = rows + warp_row_off(yf, r0, H, W);
+    const uint8_t* rp2 = rows + warp_row_off(yf + 1, r0, H, W);
+    const uint8_t* rp3 = rows + warp_row_off(yf + 2, r0, H, W);
+    if (dx == 0.0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            // biased taps: every difference is an exact integer, so this equals cubic32 on the plain values
+            const float fv = cubic32b(biased(rp0[xo[1] + c]), biased(rp1[xo[1] + c]), biased(rp2[xo[1] + c]), biased(rp3[xo[1] + c]), fdy);
+            bool rk;
+            res[c] = warp_trunc(fv, rk);
+            risky |= rk ? (1u << c) : 0u;
+        }
+        return risky;
+    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        // taps as 2^23 + v (0x4B000000 | byte: a LOP3, not a conversion on the quarter-rate XU pipe); every
-        // difference in cubic32b is exact with the bias cancelling, only the leading v2 is un-biased
-        uint8_t tap[4][4];
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj)
-#pragma unroll
-            for (int t = 0; t < 4; ++t) tap[rj][t] = rowp[rj][xo[t] + c];
-        float rv[4];
-#pragma unroll
-        for (int rj = 0; rj < 4; ++rj) {
-            const float v = cubic32b(__uint_as_float(0x4B000000u | tap[rj][0]), __uint_as_float(0x4B000000u | tap[rj][1]),
-                                     __uint_as_float(0x4B000000u | tap[rj][2]), __uint_as_float(0x4B000000u | tap[rj][3]), fdx);
-            rv[rj] = rowok[rj] ? v : rv[rj > 0 ? rj - 1 : 0];
-        }
-        const float f = cubic32(rv[0], rv[1], rv[2], rv[3], fdy);
-        const float fr = f - floorf(f);
-        const bool risky = (fr < LFX_WARP_EPS) || (fr > 1.f - LFX_WARP_EPS) || (f < LFX_WARP_EPS) || (f > 255.f - LFX_WARP_EPS);
-        if (!risky) {
-            res[c] = (uint8_t)(int)f;  // 0 < f < 255 here: plain truncation
-        } else {
-            double dv[4];
-#pragma unroll
-            for (int rj = 0; rj < 4; ++rj) {
-                const double v = cubic64(tap[rj][0], tap[rj][1], tap[rj][2], tap[rj][3], dx);
-                dv[rj] = rowok[rj] ? v : dv[rj > 0 ? rj - 1 : 0];
-            }
-            const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
-            res[c] = v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
-        }
+        const float v0 = cubic32b(biased(rp0[xo[0] + c]), biased(rp0[xo[1] + c]), biased(rp0[xo[2] + c]), biased(rp0[xo[3] + c]), fdx);
+        const float v1 = cubic32b(biased(rp1[xo[0] + c]), biased(rp1[xo[1] + c]), biased(rp1[xo[2] + c]), biased(rp1[xo[3] + c]), fdx);
+        const float v2 = cubic32b(biased(rp2[xo[0] + c]), biased(rp2[xo[1] + c]), biased(rp2[xo[2] + c]), biased(rp2[xo[3] + c]), fdx);
+        const float v3 = cubic32b(biased(rp3[xo[0] + c]), biased(rp3[xo[1] + c]), biased(rp3[xo[2] + c]), biased(rp3[xo[3] + c]), fdx);
+        const float fv = cubic32(v0, v1, v2, v3, fdy);
+        bool rk;
+        res[c] = warp_trunc(fv, rk);
+        risky |= rk ? (1u << c) : 0u;
     }
+    return risky;
 }
 
 // grid (bands of WB_ROWS output rows, B).  The source rows a band can touch follow from its four corners
@@ -249,6 +298,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                                                           int W, const double* __restrict__ coef,
                                                           const int32_t* __restrict__ persp, int max_rows) {
     extern __shared__ __align__(16) uint8_t s_rows[];
+    __shared__ uint16_t s_queue[WB_QCAP];
+    __shared__ int s_qn;
     const int img = blockIdx.y;
     const int y0 = blockIdx.x * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
     const double* ap = coef + img * 8;
@@ -260,6 +311,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     const size_t npx = (size_t)H * W;
     const uint8_t* simg = src + (size_t)img * npx * 3;
     uint8_t* dimg = dst + (size_t)img * npx * 3;
+    if (threadIdx.x == 0) s_qn = 0;
     // source row span of the band (affine): yin is linear, extremes at the corner pixel centres
     int r0 = 0, r1 = H - 1;
     bool staged = false;
@@ -278,43 +330,123 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
         r1 = max(r0, (int)hif);
         staged = (r1 - r0 + 1) <= max_rows;
     }
-    if (staged) {
-        block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
-        __syncthreads();
-    }
+    if (staged) block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
+    __syncthreads();
     const uint8_t* rows = staged ? s_rows : simg;
     const int rbase = staged ? r0 : 0;
-    const int band_px = (y1 - y0) * W;
-    for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
-        uint8_t out[12];
-        int y = y0 + q / W, x = q - (q / W) * W;
-        const int n = min(4, band_px - q);
+    const bool can_queue = (WB_ROWS * W * 3 <= 65536);   // u16 queue entries
+    // push value (q * 3 + c) of the band on the queue, or evaluate it in place when the queue is full
+    auto defer = [&](int vidx, int x, int y, int c, uint8_t* out) {
+        int slot = WB_QCAP;
+        if (can_queue) slot = atomicAdd(&s_qn, 1);
+        if (slot < WB_QCAP)
+            s_queue[slot] = (uint16_t)vidx;
+        else
+            *out = bicubic_value64(rows, rbase, H, W, x, y, c, a, is_persp);
+    };
+
+    if (staged && a[1] == 0.0 && a[3] == 0.0) {
+        // ---- axis-aligned maps (a1 = a3 = 0: the reference's skew, image_augmenter.py:50-58, is a zoom + shift): xin
+        // depends on x only and yin on y only, so the horizontal cubic of source row r at column x serves every output
+        // row whose 4-row window contains r.  One output column per thread walking down the band with a rolling window
+        // of the four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's.
+        const int ncol = min(W, THREADS);
+        const int strips = max(1, THREADS / ncol);
+        const int strip = threadIdx.x / ncol, cx = threadIdx.x - strip * ncol;
+        const int rows_per = (y1 - y0 + strips - 1) / strips;
+        const int ya = y0 + strip * rows_per, yb_end = min(y1, ya + rows_per);
+        if (strip < strips) {
+            for (int x = cx; x < W; x += ncol) {
+                const double xc = (double)x + 0.5;
+                double xin = __dadd_rn(__dmul_rn(a[0], xc), a[2]);
+                const bool xok = !(xin < 0.0 || xin >= (double)W);
+                xin = __dadd_rn(xin, -0.5);
+                const int xf = (int)floor(xin);
+                const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                int xo[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
+                // (initialised: rotating indeterminate values is undefined behaviour, and the compiler used it)
+                float hw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                int base = -(1 << 30);  // source row of hw[.][0]
+                uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
+                for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
+                    const double yc = (double)y + 0.5;
+                    double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
+                    const bool yok = !(yin < 0.0 || yin >= (double)H);
+                    if (!(xok && yok)) {
+                        dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
+                        continue;
+                    }
+                    yin = __dadd_rn(yin, -0.5);
+                    const int yf = (int)floor(yin);
+                    const float fdy = (float)__dadd_rn(yin, -(double)yf);
+                    const int yb = yf - 1;
+                    int shift = yb - base;
+                    if (shift < 0 || shift > 4) shift = 4;
+                    for (int k = 0; k < shift; ++k) {
+                        const uint8_t* rp = s_rows + warp_row_off(yb + 4 - shift + k, r0, H, W);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
+                            hw[c][3] = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+                        }
+                    }
+                    base = yb;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float fv = cubic32(hw[c][0], hw[c][1], hw[c][2], hw[c][3], fdy);
+                        bool rk;
+                        dcol[c] = warp_trunc(fv, rk);
+                        if (rk) defer(((y - y0) * W + x) * 3 + c, x, y, c, dcol + c);
+                    }
+                }
+            }
+        }
+    } else {
+        const int band_px = (y1 - y0) * W;
+        for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
+            uint8_t out[12];
+            int y = y0 + q / W, x = q - (q / W) * W;
+            const int n = min(4, band_px - q);
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {
-            uint8_t res[3] = {0, 0, 0};
-            if (k < n) {
-                if (staged)
-                    bicubic_pixel(s_rows, rbase, H, W, x, y, a, is_persp, res);
-                else
-                    bicubic_pixel(rows, rbase, H, W, x, y, a, is_persp, res);
+            for (int k = 0; k < 4; ++k) {
+                uint8_t res[3] = {0, 0, 0};
+                if (k < n) {
+                    uint32_t risky = staged ? bicubic_pixel(s_rows, rbase, H, W, x, y, a, is_persp, res)
+                                            : bicubic_pixel(rows, rbase, H, W, x, y, a, is_persp, res);
+                    if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &res[0]);
+                    if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &res[1]);
+                    if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &res[2]);
+                }
+                out[k * 3] = res[0];
+                out[k * 3 + 1] = res[1];
+                out[k * 3 + 2] = res[2];
+                if (++x == W) {
+                    x = 0;
+                    ++y;
+                }
             }
-            out[k * 3] = res[0];
-            out[k * 3 + 1] = res[1];
-            out[k * 3 + 2] = res[2];
-            if (++x == W) {
-                x = 0;
-                ++y;
+            uint8_t* d = dimg + ((size_t)y0 * W + q) * 3;
+            if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+                d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+                d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+            } else {
+                for (int i = 0; i < n * 3; ++i) d[i] = out[i];
             }
         }
-        uint8_t* d = dimg + ((size_t)y0 * W + q) * 3;
-        if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-            uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-            d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-            d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
-            d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
-        } else {
-            for (int i = 0; i < n * 3; ++i) d[i] = out[i];
-        }
+    }
+    // ---- deferred fp64 values: one per thread; the byte overwrites the fp32 guess stored above (same block, after
+    // the barrier, so the two stores to that address are ordered)
+    __syncthreads();
+    const int nq = min(s_qn, WB_QCAP);
+    for (int i = threadIdx.x; i < nq; i += THREADS) {
+        const int vidx = s_queue[i];
+        const int pix = vidx / 3, c = vidx - pix * 3;
+        const int yy = pix / W, x = pix - yy * W;
+        dimg[((size_t)(y0 + yy) * W + x) * 3 + c] = bicubic_value64(rows, rbase, H, W, x, y0 + yy, c, a, is_persp);
     }
 }
 
@@ -748,9 +880,9 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "warp_bicubic: bad arguments");
     if (B == 0) return LFX_OK;
-    // shared-memory band of source rows: up to 72 KB so that three blocks share an SM
+    // shared-memory band of source rows: up to 70 KB (+ 2 KB queue) so that three blocks share an SM
     const int rb = W * 3;
-    const int max_rows = (72 * 1024) / rb;   // three blocks per SM
+    const int max_rows = (70 * 1024) / rb;   // three blocks per SM
     const size_t smem = max_rows >= 8 ? (size_t)max_rows * rb : 0;
     static size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {

@@ -2,7 +2,7 @@
 """Per-source-line instruction and stall-sample shares of one kernel from an .ncu-rep
 (needs -lineinfo at compile time and --import-source on at capture time).
 
-  python tools/ncu_lines.py gpurun_out/prof.ncu-rep k_make_mask [top_n]
+  python tools/ncu_lines.py gpurun_out/prof.ncu-rep k_make_mask [top_n] [launch_skip]   (one launch is read)
 """
 import csv
 import subprocess
@@ -12,8 +12,9 @@ import sys
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    skip = sys.argv[4] if len(sys.argv) > 4 else "0"
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "-k",
-                          f"regex:{kern}"], capture_output=True, text=True).stdout
+                          f"regex:{kern}", "-s", skip, "-c", "1"], capture_output=True, text=True).stdout
     csv.field_size_limit(10 ** 9)
     cur, hdr, agg = None, None, []
     for r in csv.reader(out.splitlines()):
