@@ -354,13 +354,19 @@ def augment_device(x, tasks, device_noise: bool = True):
     ops = _ops()
     h, w = int(x.shape[1]), int(x.shape[2])
     ta = tasks if isinstance(tasks, TaskArrays) else TaskArrays(tasks)
-    ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
     dev = x.device
-    src = torch.from_numpy(ta.source_index).to(dev)
-    out = {}
 
     def ids_of(*names):
         return np.nonzero(np.isin(ta.transform, [TRANSFORM_CODE[n] for n in names]))[0]
+
+    # the noise streams need only the seeds: launched first, they run on the GPU while the host draws the parameters
+    dist_ids = ids_of("distortion")
+    noise = None
+    if len(dist_ids) and device_noise:
+        noise = ops.legacy_normal_noise(ta.seed[dist_ids], h * w * 3, NOISE_LEVEL, dev).view(len(dist_ids), h, w, 3)
+    ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
+    src = torch.from_numpy(ta.source_index).to(dev)
+    out = {}
 
     def gather(ids):
         return x.index_select(0, src[torch.from_numpy(ids).to(dev)])
@@ -378,11 +384,9 @@ def augment_device(x, tasks, device_noise: bool = True):
     ids = ids_of("crop")
     if len(ids):
         out["crop"] = (ids, ops.crop_lanczos(gather(ids), ip[ids, :4], (h, w)))
-    ids = ids_of("distortion")
+    ids = dist_ids
     if len(ids):
-        if device_noise:
-            noise = ops.legacy_normal_noise(ta.seed[ids], h * w * 3, NOISE_LEVEL, dev).view(len(ids), h, w, 3)
-        else:
+        if noise is None:
             noises = []
             for sd in ta.seed[ids]:
                 if sd:

@@ -393,12 +393,19 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                         }
                     }
                     base = yb;
+                    uint32_t risky = 0u;
 #pragma unroll
                     for (int c = 0; c < 3; ++c) {
                         const float fv = cubic32(hw[c][0], hw[c][1], hw[c][2], hw[c][3], fdy);
                         bool rk;
                         dcol[c] = warp_trunc(fv, rk);
-                        if (rk) defer(((y - y0) * W + x) * 3 + c, x, y, c, dcol + c);
+                        risky |= rk ? (1u << c) : 0u;
+                    }
+                    if (risky) {
+                        const int v0 = ((y - y0) * W + x) * 3;
+                        if (risky & 1u) defer(v0 + 0, x, y, 0, dcol + 0);
+                        if (risky & 2u) defer(v0 + 1, x, y, 1, dcol + 1);
+                        if (risky & 4u) defer(v0 + 2, x, y, 2, dcol + 2);
                     }
                 }
             }
@@ -415,9 +422,11 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                 if (k < n) {
                     uint32_t risky = staged ? bicubic_pixel(s_rows, rbase, H, W, x, y, a, is_persp, res)
                                             : bicubic_pixel(rows, rbase, H, W, x, y, a, is_persp, res);
-                    if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &res[0]);
-                    if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &res[1]);
-                    if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &res[2]);
+                    if (risky) {
+                        if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &res[0]);
+                        if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &res[1]);
+                        if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &res[2]);
+                    }
                 }
                 out[k * 3] = res[0];
                 out[k * 3 + 1] = res[1];

@@ -4,17 +4,26 @@
 // gauss with its one-value cache -- restated in parallel form: attempt t consumes
 // words 4t..4t+3; the k-th ACCEPTED attempt yields normals 2k = f*x2 and 2k+1 = f*x1.
 //
-// One warp per stream (image): the 624-word state lives in shared memory; the twist runs as one ascending pass in
-// chunks of 32 (loads, __syncwarp, stores -- every operand is then either still old or already new exactly as
-// in the sequential generator); each 624-word block is exactly 156 attempts, compacted with warp ballots.
-// All floating point is explicit round-to-nearest fp64 without FMA contraction (the host libraries are built
-// without FMA); CUDA's log() is within 1 ulp of glibc's, which can move a result only when 5*g lies within an
-// ulp of an integer (probability ~1e-15 per sample) -- the uint8 stream is otherwise identical.
+// One warp per stream (image): the 624-word state lives in shared memory.  A 624-word block is exactly 156 attempts
+// and attempt t consumes words 4t..4t+3, so lane j of round c twists the four words of attempt t = 32c + j itself
+// (ascending quads, loads - __syncwarp - stores: every operand is then either still old or already new exactly as in
+// the sequential generator: word i reads i+1 -- old, or new[0] for i = 623 -- and i+397, which is old for i < 227 and
+// was stored by an earlier round otherwise), tempers them in registers and evaluates its attempt; accepted attempts
+// are compacted with a warp ballot.
+//
+// Arithmetic.  The reference is fp64 (explicit round-to-nearest without FMA contraction: the host libraries are built
+// without FMA); CUDA's log() is within 1 ulp of glibc's, which can move a result only when 5*g lies within an ulp of
+// an integer (probability ~1e-15 per sample).  An fp32 evaluation decides first.  With u = 2^-24: x1, x2 carry 2u,
+// r2 5u, L = logf(r2) an absolute 5u + 2u|L|, and g = scale * x * sqrt(-2L / r2) the absolute error
+// |g| (2.5u/|L| + 8u).  A value with |g| >= 0.5 has |L| >= 0.005 (x^2 <= r2), so for |scale| <= 8 the error stays
+// below 7e-5; below 0.5 the byte is 0 whatever the error.  Attempts whose fp32 radius lies within 1e-6 of 1 (the
+// acceptance test) or whose value lies within 2^-12 of an integer are re-evaluated in fp64 (0.08 % of the attempts).
 #include "lfx_common.cuh"
 
 namespace {
 
 constexpr int RNG_WARPS = 8;
+#define LFX_RNG_EPS 0.000244140625f
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 11);
@@ -23,10 +32,39 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 18);
     return y;
 }
+__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
+    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7FFFFFFFu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+}
+
+// fp64 reference evaluation of one attempt -> accepted?, the two bytes
+__device__ __noinline__ bool attempt64(uint32_t a, uint32_t bq, uint32_t c, uint32_t d, double loc, double scale, uint8_t& o0, uint8_t& o1) {
+    const double d1 = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bq), 9007199254740992.0);
+    const double d2 = __ddiv_rn(__dadd_rn(__dmul_rn((double)c, 67108864.0), (double)d), 9007199254740992.0);
+    const double x1 = __dadd_rn(__dmul_rn(2.0, d1), -1.0), x2 = __dadd_rn(__dmul_rn(2.0, d2), -1.0);
+    const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
+    if (!((r2 < 1.0) && (r2 != 0.0))) return false;
+    const double f = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
+    const double g0 = __dadd_rn(loc, __dmul_rn(scale, __dmul_rn(f, x2)));  // returned first
+    const double g1 = __dadd_rn(loc, __dmul_rn(scale, __dmul_rn(f, x1)));  // the cached value, returned next
+    o0 = (uint8_t)(int)g0;  // .astype(np.uint8): truncate toward zero, wrap mod 256
+    o1 = (uint8_t)(int)g1;
+    return true;
+}
+
+// byte of an fp32 value known to within 7e-5; false when fp64 has to decide
+__device__ __forceinline__ bool byte32(float g, uint8_t& o) {
+    if (fabsf(g) < 0.5f) {
+        o = 0;
+        return true;
+    }
+    o = (uint8_t)(int)g;
+    return fabsf(g - rintf(g)) >= LFX_RNG_EPS;
+}
 
 __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint32_t* __restrict__ seeds, uint8_t* __restrict__ out, int B,
-                                                                    int n, double loc, double scale) {
-    __shared__ uint32_t s_mt[RNG_WARPS][624];
+                                                                    int n, double loc, double scale, int fast) {
+    __shared__ __align__(16) uint32_t s_mt[RNG_WARPS][624];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * RNG_WARPS + wid;
     if (b >= B) return;
@@ -40,48 +78,60 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
     }
     __syncwarp();
     uint8_t* o = out + (size_t)b * n;
-    int produced = 0;  // normals written so far (warp-uniform)
+    const bool pair_ok = ((reinterpret_cast<uintptr_t>(o) & 1) == 0);
+    const float fscale = (float)scale;
+    int produced = 0;  // normals written so far (warp-uniform, always even)
     while (produced < n) {
-        // ---- twist: next 624 words, in place, ascending chunks of 32
-        for (int c0 = 0; c0 < 624; c0 += 32) {
-            const int i = c0 + lane;
-            uint32_t v = 0;
-            if (i < 624) {
-                const int i1 = (i + 1 == 624) ? 0 : i + 1;
-                const int im = (i + 397 >= 624) ? i + 397 - 624 : i + 397;
-                const uint32_t y = (mt[i] & 0x80000000u) | (mt[i1] & 0x7FFFFFFFu);
-                v = mt[im] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
-            }
-            __syncwarp();
-            if (i < 624) mt[i] = v;
-            __syncwarp();
-        }
-        // Note on i = 623: it needs the NEW mt[0] and mt[396]; both were stored by earlier chunks.  Lanes of the
-        // last chunk read mt[i+1] of their right neighbour before anyone stores (loads precede the __syncwarp).
-        // ---- 156 attempts of this block
+#pragma unroll 1
         for (int t0 = 0; t0 < 156 && produced < n; t0 += 32) {
             const int t = t0 + lane;
+            const bool act = t < 156;
+            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+            if (act) {
+                const int i0 = 4 * t;
+                const uint4 q = *reinterpret_cast<const uint4*>(mt + i0);
+                const uint32_t nx = mt[i0 + 4 == 624 ? 0 : i0 + 4];
+                int j = i0 + 396;  // quad holding words i0+397..i0+399 in .y .z .w (i0 + 397 = 1 mod 4)
+                if (j >= 624) j -= 624;
+                const uint4 m = *reinterpret_cast<const uint4*>(mt + j);
+                const uint32_t m3 = mt[j + 4 == 624 ? 0 : j + 4];
+                w0 = mt_twist(q.x, q.y, m.y);
+                w1 = mt_twist(q.y, q.z, m.z);
+                w2 = mt_twist(q.z, q.w, m.w);
+                w3 = mt_twist(q.w, nx, m3);
+            }
+            __syncwarp();
+            if (act) *reinterpret_cast<uint4*>(mt + 4 * t) = make_uint4(w0, w1, w2, w3);
+            __syncwarp();
             bool acc = false;
-            double g0 = 0.0, g1 = 0.0;
-            if (t < 156) {
-                const uint32_t a = mt_temper(mt[4 * t]) >> 5, bq = mt_temper(mt[4 * t + 1]) >> 6;
-                const uint32_t c = mt_temper(mt[4 * t + 2]) >> 5, d = mt_temper(mt[4 * t + 3]) >> 6;
-                const double d1 = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bq), 9007199254740992.0);
-                const double d2 = __ddiv_rn(__dadd_rn(__dmul_rn((double)c, 67108864.0), (double)d), 9007199254740992.0);
-                const double x1 = __dadd_rn(__dmul_rn(2.0, d1), -1.0), x2 = __dadd_rn(__dmul_rn(2.0, d2), -1.0);
-                const double r2 = __dadd_rn(__dmul_rn(x1, x1), __dmul_rn(x2, x2));
-                acc = (r2 < 1.0) && (r2 != 0.0);
-                if (acc) {
-                    const double f = __dsqrt_rn(__ddiv_rn(__dmul_rn(-2.0, log(r2)), r2));
-                    g0 = __dadd_rn(loc, __dmul_rn(scale, __dmul_rn(f, x2)));  // returned first
-                    g1 = __dadd_rn(loc, __dmul_rn(scale, __dmul_rn(f, x1)));  // the cached value, returned next
+            uint8_t o0 = 0, o1 = 0;
+            if (act) {
+                const uint32_t a = mt_temper(w0) >> 5, bq = mt_temper(w1) >> 6, c = mt_temper(w2) >> 5, d = mt_temper(w3) >> 6;
+                bool slow = !fast;
+                if (fast) {
+                    const float x1 = fmaf((float)bq, 0x1p-52f, (float)((int)a - (1 << 26)) * 0x1p-26f);
+                    const float x2 = fmaf((float)d, 0x1p-52f, (float)((int)c - (1 << 26)) * 0x1p-26f);
+                    const float r2 = fmaf(x1, x1, x2 * x2);
+                    if (fabsf(r2 - 1.f) <= 1e-6f) {
+                        slow = true;
+                    } else if (r2 < 1.f && r2 != 0.f) {
+                        const float f = sqrtf(-2.f * logf(r2) / r2);
+                        const bool k0 = byte32(fscale * (f * x2), o0), k1 = byte32(fscale * (f * x1), o1);
+                        acc = true;
+                        slow = !(k0 && k1);
+                    }
                 }
+                if (slow) acc = attempt64(a, bq, c, d, loc, scale, o0, o1);
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, acc);
             if (acc) {
                 const int k = produced + 2 * __popc(bal & ((1u << lane) - 1u));
-                if (k < n) o[k] = (uint8_t)(int)g0;          // .astype(np.uint8): truncate toward zero, wrap mod 256
-                if (k + 1 < n) o[k + 1] = (uint8_t)(int)g1;
+                if (k + 1 < n && pair_ok) {
+                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)(o0 | (o1 << 8));
+                } else {
+                    if (k < n) o[k] = o0;
+                    if (k + 1 < n) o[k + 1] = o1;
+                }
             }
             produced += 2 * __popc(bal);
         }
@@ -94,6 +144,7 @@ extern "C" int lfx_legacy_normal_u8(const uint32_t* seeds, uint8_t* out, int B, 
     LFX_REQUIRE_READY();
     if (B == 0 || n == 0) return LFX_OK;
     LFX_REQUIRE(seeds && out && B > 0 && n > 0, LFX_ERR_ARG, "legacy_normal_u8: bad arguments");
-    k_legacy_normal_u8<<<lfx_div_up(B, RNG_WARPS), RNG_WARPS * 32, 0, (cudaStream_t)stream>>>(seeds, out, B, n, loc, scale);
+    const int fast = (loc == 0.0 && fabs(scale) <= 8.0) ? 1 : 0;   // the fp32 error bound above assumes |g| <= 8 * 12
+    k_legacy_normal_u8<<<lfx_div_up(B, RNG_WARPS), RNG_WARPS * 32, 0, (cudaStream_t)stream>>>(seeds, out, B, n, loc, scale, fast);
     return lfx_check_launch("legacy_normal_u8");
 }

@@ -397,6 +397,24 @@ def test_device_legacy_normal_batch_and_sizes(dev):
             assert np.array_equal(got[i], np.random.normal(0, 5, n).astype(np.uint8)), (n, sd)
 
 
+def test_device_legacy_normal_stress(dev):
+    """25 M samples (128 streams x 196,608): the fp32 fast path with its fp64 re-evaluation must reproduce NumPy's
+    fp64 stream bit for bit; also the general (loc, scale) form, which always runs in fp64."""
+    n = 256 * 256 * 3
+    seeds = [1000 + 7919 * i for i in range(128)]
+    got = ops.legacy_normal_noise(seeds, n, 5.0, dev).cpu().numpy()
+    bad = 0
+    for i, sd in enumerate(seeds):
+        np.random.seed(sd)
+        bad += int((got[i] != np.random.normal(0, 5, n).astype(np.uint8)).sum())
+    assert bad == 0, bad
+    for loc, scale in ((0.0, 8.0), (0.0, 0.37), (100.0, 20.0), (3.5, 5.0)):
+        got = ops.legacy_normal_noise([5, 99], 40001, scale, dev, loc=loc).cpu().numpy()     # odd n: unaligned second row
+        for i, sd in enumerate((5, 99)):
+            np.random.seed(sd)
+            assert np.array_equal(got[i], np.random.normal(loc, scale, 40001).astype(np.uint8)), (loc, scale, sd)
+
+
 def test_empty_batch(dev):
     x = torch.empty((0, 64, 64, 3), dtype=torch.uint8, device=dev)
     assert ops.cvt_color(x, "hsv").shape == (0, 64, 64, 3)
