@@ -210,31 +210,38 @@ __device__ __forceinline__ bool warp_coords(int x, int y, int H, int W, const do
 
 // Rows 1..3 of the 4x4 window reuse the previous row's VALUE when they fall outside the image (Geometry.c
 // BICUBIC_BODY) and row 0 is clamped; the previous row is then itself the clamped row, so the rule equals clamping the
-// row index.  `rows` points at image row `r0`.
-__device__ __forceinline__ int warp_row_off(int yy, int r0, int H, int W) { return (min(max(yy, 0), H - 1) - r0) * W * 3; }
+// row index.
+// Where the taps come from: the image in global memory (pitch W*3, r0 = cb = 0) or a rectangle of it staged in shared
+// memory (rows r0.., byte column cb.. of every row).  Tap (row, col, c) sits at base[(row - r0) * pitch + col*3 - cb + c].
+struct WarpView {
+    const uint8_t* base;
+    int pitch, r0, cb;
+};
+__device__ __forceinline__ int warp_row_off(const WarpView& v, int yy, int H) { return (min(max(yy, 0), H - 1) - v.r0) * v.pitch - v.cb; }
 
 // The reference value (fp64) of channel c of output pixel (x, y).
-__device__ __noinline__ uint8_t bicubic_value64(const uint8_t* rows, int r0, int H, int W, int x, int y, int c, const double* a,
-                                                bool is_persp) {
+__device__ __noinline__ uint8_t bicubic_value64(const uint8_t* base, int pitch, int r0, int cb, int H, int W, int x, int y, int c,
+                                                const double* a, bool is_persp) {
     int xf, yf;
     double dx, dy;
     if (!warp_coords(x, y, H, W, a, is_persp, xf, yf, dx, dy)) return 0;
+    const WarpView v{base, pitch, r0, cb};
     int xo[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3 + c;
     double dv[4];
 #pragma unroll
     for (int rj = 0; rj < 4; ++rj) {
-        const uint8_t* rp = rows + warp_row_off(yf - 1 + rj, r0, H, W);
+        const uint8_t* rp = base + warp_row_off(v, yf - 1 + rj, H);
         dv[rj] = cubic64(rp[xo[0]], rp[xo[1]], rp[xo[2]], rp[xo[3]], dx);
     }
-    const double v = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
-    return v <= 0.0 ? 0 : (v >= 255.0 ? 255 : (uint8_t)(int)v);
+    const double r = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
+    return r <= 0.0 ? 0 : (r >= 255.0 ? 255 : (uint8_t)(int)r);
 }
 
 // One output pixel of PIL's transform(..., BICUBIC) by the fp32 fast path: res[] holds the truncated fp32 values,
 // the return value has bit c set when channel c must be re-evaluated in fp64.
-__device__ __forceinline__ uint32_t bicubic_pixel(const uint8_t* rows, int r0, int H, int W, int x, int y, const double* a, bool is_persp,
+__device__ __forceinline__ uint32_t bicubic_pixel(const WarpView& v, int H, int W, int x, int y, const double* a, bool is_persp,
                                                   uint8_t res[3]) {
     res[0] = res[1] = res[2] = 0;
     int xf, yf;
@@ -249,7 +256,7 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const uint8_t* rows, int r0, i
     // with the identity (image_augmenter.py:82: yin = yc or xin = xc), so a whole image has dy == 0 or dx == 0:
     // dy == 0 needs only the row yf (always inside the image), dx == 0 only the column xf of each row.
     if (dy == 0.0) {
-        const uint8_t* rp = rows + warp_row_off(yf, r0, H, W);
+        const uint8_t* rp = v.base + warp_row_off(v, yf, H);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float fv = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
@@ -259,10 +266,10 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const uint8_t* rows, int r0, i
         }
         return risky;
     }
-    const uint8_t* rp0 = rows + warp_row_off(yf - 1, r0, H, W);
-    const uint8_t* rp1 = rows + warp_row_off(yf, r0, H, W);
-    const uint8_t* rp2 = rows + warp_row_off(yf + 1, r0, H, W);
-    const uint8_t* rp3 = rows + warp_row_off(yf + 2, r0, H, W);
+    const uint8_t* rp0 = v.base + warp_row_off(v, yf - 1, H);
+    const uint8_t* rp1 = v.base + warp_row_off(v, yf, H);
+    const uint8_t* rp2 = v.base + warp_row_off(v, yf + 1, H);
+    const uint8_t* rp3 = v.base + warp_row_off(v, yf + 2, H);
     if (dx == 0.0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -288,20 +295,47 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const uint8_t* rows, int r0, i
     return risky;
 }
 
-// grid (bands of WB_ROWS output rows, B).  The source rows a band can touch follow from its four corners
-// (the map is affine whenever a6 = a7 = 0, which covers the reference's skew and shear); when they fit in
-// shared memory they are staged with 16-byte loads and the 48 taps per pixel come from shared memory,
-// otherwise (general perspective, very tall source spans) the taps are read from global memory.
+// grid (column tiles x bands of WB_ROWS output rows, B): a block owns a WB_ROWS x <= WB_COLS output tile.  For affine maps
+// (a6 = a7 = 0: the reference's skew and shear) the source rectangle a tile can touch follows from its four corners;
+// it is staged in shared memory with 16-byte loads and the taps come from there.  A rectangle that does not fit
+// (tall spans of a vertical shear) is handled by splitting the tile into 2 / 4 / 8 column slices staged one after the
+// other; general perspective maps read their taps from global memory.
 constexpr int WB_ROWS = 32;
+constexpr int WB_COLS = 256;
 
+// source rectangle (rows r0..r1, columns c0..c1) of output pixels [xa, xb) x [ya, yb) under the affine map a.
+// Conservative bounds are enough, so this runs in fp32 (coordinates < 2^20: error < 0.1 px, covered by the slack).
+__device__ __forceinline__ void warp_src_rect(const double* ad, int xa, int xb, int ya, int yb, int H, int W, int& r0, int& r1, int& c0,
+                                              int& c1) {
+    const float a[6] = {(float)ad[0], (float)ad[1], (float)ad[2], (float)ad[3], (float)ad[4], (float)ad[5]};
+    const float xs0 = (float)xa + 0.5f, xs1 = (float)xb - 0.5f, ys0 = (float)ya + 0.5f, ys1 = (float)yb - 0.5f;
+    const float vy00 = a[3] * xs0 + a[4] * ys0 + a[5], vy01 = a[3] * xs0 + a[4] * ys1 + a[5];
+    const float vy10 = a[3] * xs1 + a[4] * ys0 + a[5], vy11 = a[3] * xs1 + a[4] * ys1 + a[5];
+    const float vx00 = a[0] * xs0 + a[1] * ys0 + a[2], vx01 = a[0] * xs0 + a[1] * ys1 + a[2];
+    const float vx10 = a[0] * xs1 + a[1] * ys0 + a[2], vx11 = a[0] * xs1 + a[1] * ys1 + a[2];
+    const float ylo = fminf(fminf(vy00, vy01), fminf(vy10, vy11)), yhi = fmaxf(fmaxf(vy00, vy01), fmaxf(vy10, vy11));
+    const float xlo = fminf(fminf(vx00, vx01), fminf(vx10, vx11)), xhi = fmaxf(fmaxf(vx00, vx01), fmaxf(vx10, vx11));
+    // taps use floor(v - 0.5) - 1 .. + 2 (2.5 below, 2.5 above) + slack; clamped taps of outside coordinates land on the
+    // border row / column, which the clamps below keep inside the rectangle
+    r0 = (int)fminf(fmaxf(ylo - 3.75f, 0.f), (float)(H - 1));
+    r1 = max(r0, (int)fmaxf(fminf(yhi + 3.75f, (float)(H - 1)), 0.f));
+    c0 = (int)fminf(fmaxf(xlo - 3.75f, 0.f), (float)(W - 1));
+    c1 = max(c0, (int)fmaxf(fminf(xhi + 3.75f, (float)(W - 1)), 0.f));
+}
+
+// TILED = false is the W <= WB_COLS instantiation: one tile per band, whole rows staged as one contiguous copy, no slices
+// (a rectangle that does not fit falls back to global taps) -- the column bookkeeping folds away at compile time.
+template <bool TILED>
 __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
                                                           int W, const double* __restrict__ coef,
-                                                          const int32_t* __restrict__ persp, int max_rows) {
+                                                          const int32_t* __restrict__ persp, int smem_cap, int ntx) {
     extern __shared__ __align__(16) uint8_t s_rows[];
     __shared__ uint16_t s_queue[WB_QCAP];
     __shared__ int s_qn;
     const int img = blockIdx.y;
-    const int y0 = blockIdx.x * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
+    const int band = TILED ? blockIdx.x / ntx : blockIdx.x, tx = TILED ? blockIdx.x - band * ntx : 0;
+    const int y0 = band * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
+    const int X0 = TILED ? tx * WB_COLS : 0, X1 = TILED ? min(W, X0 + WB_COLS) : W;
     const double* ap = coef + img * 8;
     double a[8];
 #pragma unroll
@@ -311,151 +345,199 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     const size_t npx = (size_t)H * W;
     const uint8_t* simg = src + (size_t)img * npx * 3;
     uint8_t* dimg = dst + (size_t)img * npx * 3;
+    const bool al16 = ((W * 3) % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);   // every row start is 16-byte aligned
     if (threadIdx.x == 0) s_qn = 0;
-    // source row span of the band (affine): yin is linear, extremes at the corner pixel centres
-    int r0 = 0, r1 = H - 1;
-    bool staged = false;
-    if (affine) {
-        const double xs[2] = {0.5, (double)W - 0.5}, ys[2] = {(double)y0 + 0.5, (double)y1 - 0.5};
-        double lo = 1e300, hi = -1e300;
-        for (int i = 0; i < 2; ++i)
-            for (int j = 0; j < 2; ++j) {
-                const double v = a[3] * xs[i] + a[4] * ys[j] + a[5];
-                lo = fmin(lo, v);
-                hi = fmax(hi, v);
+    // number of column slices: the smallest of 1, 2, 4, 8 whose source rectangles all fit in shared memory
+    int nsl = 0;
+    if (!TILED) {
+        if (affine && smem_cap > 0) {
+            int r0, r1, c0, c1;
+            warp_src_rect(a, 0, W, y0, y1, H, W, r0, r1, c0, c1);
+            nsl = ((r1 - r0 + 1) * W * 3 <= smem_cap) ? 1 : 0;
+        }
+    } else if (affine && smem_cap > 0) {
+        for (int n = 1; n <= 8 && !nsl; n *= 2) {
+            const int sw = (((X1 - X0 + n - 1) / n) + 3) & ~3;
+            bool ok = true;
+            for (int xa = X0; xa < X1 && ok; xa += sw) {
+                int r0, r1, c0, c1;
+                warp_src_rect(a, xa, min(X1, xa + sw), y0, y1, H, W, r0, r1, c0, c1);
+                if (al16) c0 &= ~15;
+                ok = (r1 - r0 + 1) * (((c1 - c0 + 1) * 3 + 15) & ~15) <= smem_cap;
             }
-        // taps use rows floor(yin - 0.5) - 1 .. + 2; one more row of slack for the fused-vs-separate rounding above
-        const double lof = fmax(lo - 3.5, 0.0), hif = fmin(hi + 3.5, (double)(H - 1));
-        r0 = (int)lof;
-        r1 = max(r0, (int)hif);
-        staged = (r1 - r0 + 1) <= max_rows;
+            if (ok) nsl = n;
+        }
     }
-    if (staged) block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
-    __syncthreads();
-    const uint8_t* rows = staged ? s_rows : simg;
-    const int rbase = staged ? r0 : 0;
-    const bool can_queue = (WB_ROWS * W * 3 <= 65536);   // u16 queue entries
-    // push value (q * 3 + c) of the band on the queue, or evaluate it in place when the queue is full
-    auto defer = [&](int vidx, int x, int y, int c, uint8_t* out) {
-        int slot = WB_QCAP;
-        if (can_queue) slot = atomicAdd(&s_qn, 1);
-        if (slot < WB_QCAP)
-            s_queue[slot] = (uint16_t)vidx;
-        else
-            *out = bicubic_value64(rows, rbase, H, W, x, y, c, a, is_persp);
-    };
-
-    if (staged && a[1] == 0.0 && a[3] == 0.0) {
-        // ---- axis-aligned maps (a1 = a3 = 0: the reference's skew, image_augmenter.py:50-58, is a zoom + shift): xin
-        // depends on x only and yin on y only, so the horizontal cubic of source row r at column x serves every output
-        // row whose 4-row window contains r.  One output column per thread walking down the band with a rolling window
-        // of the four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's.
-        const int ncol = min(W, THREADS);
-        const int strips = max(1, THREADS / ncol);
-        const int strip = threadIdx.x / ncol, cx = threadIdx.x - strip * ncol;
-        const int rows_per = (y1 - y0 + strips - 1) / strips;
-        const int ya = y0 + strip * rows_per, yb_end = min(y1, ya + rows_per);
-        if (strip < strips) {
-            for (int x = cx; x < W; x += ncol) {
-                const double xc = (double)x + 0.5;
-                double xin = __dadd_rn(__dmul_rn(a[0], xc), a[2]);
-                const bool xok = !(xin < 0.0 || xin >= (double)W);
-                xin = __dadd_rn(xin, -0.5);
-                const int xf = (int)floor(xin);
-                const float fdx = (float)__dadd_rn(xin, -(double)xf);
-                int xo[4];
-#pragma unroll
-                for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
-                // (initialised: rotating indeterminate values is undefined behaviour, and the compiler used it)
-                float hw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                int base = -(1 << 30);  // source row of hw[.][0]
-                uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
-                for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
-                    const double yc = (double)y + 0.5;
-                    double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
-                    const bool yok = !(yin < 0.0 || yin >= (double)H);
-                    if (!(xok && yok)) {
-                        dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
-                        continue;
+    const int sw = (TILED && nsl) ? ((((X1 - X0 + nsl - 1) / nsl) + 3) & ~3) : (X1 - X0);
+    for (int x0 = X0; x0 < X1; x0 += sw) {
+        const int x1 = TILED ? min(X1, x0 + sw) : W, tw = x1 - x0;
+        WarpView v{simg, W * 3, 0, 0};
+        if (!TILED) {
+            if (nsl) {
+                int r0, r1, c0, c1;
+                warp_src_rect(a, 0, W, y0, y1, H, W, r0, r1, c0, c1);
+                v = WarpView{s_rows, W * 3, r0, 0};
+                block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
+            }
+        } else if (nsl) {
+            int r0, r1, c0, c1;
+            warp_src_rect(a, x0, x1, y0, y1, H, W, r0, r1, c0, c1);
+            if (al16) c0 &= ~15;
+            const int nb = (c1 - c0 + 1) * 3, pitch = (nb + 15) & ~15;
+            v = WarpView{s_rows, pitch, r0, c0 * 3};
+            const uint8_t* g = simg + ((size_t)r0 * W + c0) * 3;
+            const int rows = r1 - r0 + 1, lane = threadIdx.x & 31;
+            if (al16) {
+                const int n16 = pitch >> 4;     // may run up to 15 bytes past c1: still inside the row or the next row / image
+                const uint8_t* lim = src + (size_t)gridDim.y * npx * 3;
+                for (int r = threadIdx.x >> 5; r < rows; r += THREADS / 32) {
+                    const uint8_t* p = g + (size_t)r * W * 3;
+                    uint4* d = reinterpret_cast<uint4*>(s_rows + r * pitch);
+                    for (int k = lane; k < n16; k += 32) {
+                        uint4 q = make_uint4(0, 0, 0, 0);
+                        if (p + k * 16 + 16 <= lim) q = ld_stream16(p + k * 16);
+                        else for (int bb = 0; bb < 16; ++bb) if (p + k * 16 + bb < lim) reinterpret_cast<uint8_t*>(&q)[bb] = p[k * 16 + bb];
+                        d[k] = q;
                     }
-                    yin = __dadd_rn(yin, -0.5);
-                    const int yf = (int)floor(yin);
-                    const float fdy = (float)__dadd_rn(yin, -(double)yf);
-                    const int yb = yf - 1;
-                    int shift = yb - base;
-                    if (shift < 0 || shift > 4) shift = 4;
-                    for (int k = 0; k < shift; ++k) {
-                        const uint8_t* rp = s_rows + warp_row_off(yb + 4 - shift + k, r0, H, W);
+                }
+            } else {
+                for (int r = threadIdx.x >> 5; r < rows; r += THREADS / 32)
+                    for (int k = lane; k < nb; k += 32) s_rows[r * pitch + k] = g[(size_t)r * W * 3 + k];
+            }
+        }
+        __syncthreads();
+        // push value vidx of the slice on the queue, or evaluate it in place when the queue is full
+        auto defer = [&](int vidx, int x, int y, int c, uint8_t* out) {
+            const int slot = atomicAdd(&s_qn, 1);
+            if (slot < WB_QCAP)
+                s_queue[slot] = (uint16_t)vidx;
+            else
+                *out = bicubic_value64(v.base, v.pitch, v.r0, v.cb, H, W, x, y, c, a, is_persp);
+        };
+
+        if (nsl && a[1] == 0.0 && a[3] == 0.0) {
+            // ---- axis-aligned maps (a1 = a3 = 0: the reference's skew, image_augmenter.py:50-58, is a zoom + shift): xin
+            // depends on x only and yin on y only, so the horizontal cubic of source row r at column x serves every
+            // output row whose 4-row window contains r.  One output column per thread walking down the band with a rolling
+            // window of the four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's.
+            const int ncol = min(tw, THREADS);
+            const int strips = max(1, THREADS / ncol);
+            const int strip = threadIdx.x / ncol, cx = threadIdx.x - strip * ncol;
+            const int rows_per = (y1 - y0 + strips - 1) / strips;
+            const int ya = y0 + strip * rows_per, yb_end = min(y1, ya + rows_per);
+            if (strip < strips) {
+                for (int x = x0 + cx; x < x1; x += ncol) {
+                    const double xc = (double)x + 0.5;
+                    double xin = __dadd_rn(__dmul_rn(a[0], xc), a[2]);
+                    const bool xok = !(xin < 0.0 || xin >= (double)W);
+                    xin = __dadd_rn(xin, -0.5);
+                    const int xf = (int)floor(xin);
+                    const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                    int xo[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
+                    // (initialised: rotating indeterminate values is undefined behaviour, and the compiler used it)
+                    float hw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+                    int base = -(1 << 30);  // source row of hw[.][0]
+                    uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
+                    for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
+                        const double yc = (double)y + 0.5;
+                        double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
+                        const bool yok = !(yin < 0.0 || yin >= (double)H);
+                        if (!(xok && yok)) {
+                            dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
+                            continue;
+                        }
+                        yin = __dadd_rn(yin, -0.5);
+                        const int yf = (int)floor(yin);
+                        const float fdy = (float)__dadd_rn(yin, -(double)yf);
+                        const int yb = yf - 1;
+                        int shift = yb - base;
+                        if (shift < 0 || shift > 4) shift = 4;
+                        for (int k = 0; k < shift; ++k) {
+                            const uint8_t* rp = s_rows + warp_row_off(v, yb + 4 - shift + k, H);   // shared loads, not generic
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
+                                hw[c][3] = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+                            }
+                        }
+                        base = yb;
+                        uint32_t risky = 0u;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
-                            hw[c][3] = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+                            const float fv = cubic32(hw[c][0], hw[c][1], hw[c][2], hw[c][3], fdy);
+                            bool rk;
+                            dcol[c] = warp_trunc(fv, rk);
+                            risky |= rk ? (1u << c) : 0u;
+                        }
+                        if (risky) {
+                            const int v0 = ((y - y0) * tw + (x - x0)) * 3;
+                            if (risky & 1u) defer(v0 + 0, x, y, 0, dcol + 0);
+                            if (risky & 2u) defer(v0 + 1, x, y, 1, dcol + 1);
+                            if (risky & 4u) defer(v0 + 2, x, y, 2, dcol + 2);
                         }
                     }
-                    base = yb;
-                    uint32_t risky = 0u;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float fv = cubic32(hw[c][0], hw[c][1], hw[c][2], hw[c][3], fdy);
-                        bool rk;
-                        dcol[c] = warp_trunc(fv, rk);
-                        risky |= rk ? (1u << c) : 0u;
-                    }
-                    if (risky) {
-                        const int v0 = ((y - y0) * W + x) * 3;
-                        if (risky & 1u) defer(v0 + 0, x, y, 0, dcol + 0);
-                        if (risky & 2u) defer(v0 + 1, x, y, 1, dcol + 1);
-                        if (risky & 4u) defer(v0 + 2, x, y, 2, dcol + 2);
-                    }
                 }
             }
-        }
-    } else {
-        const int band_px = (y1 - y0) * W;
-        for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
-            uint8_t out[12];
-            int y = y0 + q / W, x = q - (q / W) * W;
-            const int n = min(4, band_px - q);
+        } else {
+            const int band_px = (y1 - y0) * tw;
+            for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
+                uint8_t out[12];
+                const int qy = q / tw, qx = q - qy * tw;
+                const bool one_row = (qx + 4 <= tw);   // the four pixels are contiguous in memory
 #pragma unroll 1
-            for (int k = 0; k < 4; ++k) {
-                uint8_t res[3] = {0, 0, 0};
-                if (k < n) {
-                    uint32_t risky = staged ? bicubic_pixel(s_rows, rbase, H, W, x, y, a, is_persp, res)
-                                            : bicubic_pixel(rows, rbase, H, W, x, y, a, is_persp, res);
-                    if (risky) {
-                        if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &res[0]);
-                        if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &res[1]);
-                        if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &res[2]);
+                for (int k = 0; k < 4; ++k) {
+                    uint8_t res[3] = {0, 0, 0};
+                    if (q + k < band_px) {
+                        int yy = qy, xx = qx + k;
+                        while (xx >= tw) {
+                            xx -= tw;
+                            ++yy;
+                        }
+                        const int x = x0 + xx, y = y0 + yy;
+                        const uint32_t risky = nsl ? bicubic_pixel(WarpView{s_rows, v.pitch, v.r0, v.cb}, H, W, x, y, a, is_persp, res)
+                                                   : bicubic_pixel(WarpView{simg, W * 3, 0, 0}, H, W, x, y, a, is_persp, res);
+                        if (risky) {
+                            if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &res[0]);
+                            if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &res[1]);
+                            if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &res[2]);
+                        }
+                        if (!one_row) {
+                            uint8_t* d1 = dimg + ((size_t)y * W + x) * 3;
+                            d1[0] = res[0], d1[1] = res[1], d1[2] = res[2];
+                        }
+                    }
+                    out[k * 3] = res[0];
+                    out[k * 3 + 1] = res[1];
+                    out[k * 3 + 2] = res[2];
+                }
+                if (one_row) {
+                    uint8_t* d = dimg + ((size_t)(y0 + qy) * W + x0 + qx) * 3;
+                    if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+                        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+                        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+                    } else {
+                        for (int i = 0; i < 12; ++i) d[i] = out[i];
                     }
                 }
-                out[k * 3] = res[0];
-                out[k * 3 + 1] = res[1];
-                out[k * 3 + 2] = res[2];
-                if (++x == W) {
-                    x = 0;
-                    ++y;
-                }
-            }
-            uint8_t* d = dimg + ((size_t)y0 * W + q) * 3;
-            if (n == 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-                uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-                d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-                d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
-                d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
-            } else {
-                for (int i = 0; i < n * 3; ++i) d[i] = out[i];
             }
         }
-    }
-    // ---- deferred fp64 values: one per thread; the byte overwrites the fp32 guess stored above (same block, after
-    // the barrier, so the two stores to that address are ordered)
-    __syncthreads();
-    const int nq = min(s_qn, WB_QCAP);
-    for (int i = threadIdx.x; i < nq; i += THREADS) {
-        const int vidx = s_queue[i];
-        const int pix = vidx / 3, c = vidx - pix * 3;
-        const int yy = pix / W, x = pix - yy * W;
-        dimg[((size_t)(y0 + yy) * W + x) * 3 + c] = bicubic_value64(rows, rbase, H, W, x, y0 + yy, c, a, is_persp);
+        // ---- deferred fp64 values: one per thread; the byte overwrites the fp32 guess stored above (same block, after
+        // the barrier, so the two stores to that address are ordered)
+        __syncthreads();
+        const int nq = min(s_qn, WB_QCAP);
+        for (int i = threadIdx.x; i < nq; i += THREADS) {
+            const int vidx = s_queue[i];
+            const int pix = vidx / 3, c = vidx - pix * 3;
+            const int yy = pix / tw, xx = pix - yy * tw;
+            dimg[((size_t)(y0 + yy) * W + x0 + xx) * 3 + c] =
+                bicubic_value64(v.base, v.pitch, v.r0, v.cb, H, W, x0 + xx, y0 + yy, c, a, is_persp);
+        }
+        __syncthreads();   // the queue and the staged rectangle are reused by the next slice
+        if (threadIdx.x == 0) s_qn = 0;
     }
 }
 
@@ -889,18 +971,21 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
                 "warp_bicubic: bad arguments");
     if (B == 0) return LFX_OK;
-    // shared-memory band of source rows: up to 70 KB (+ 2 KB queue) so that three blocks share an SM
-    const int rb = W * 3;
-    const int max_rows = (70 * 1024) / rb;   // three blocks per SM
-    const size_t smem = max_rows >= 8 ? (size_t)max_rows * rb : 0;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_warp_bicubic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // staged source rectangle: up to 70 KB (+ 2 KB queue) so that three blocks share an SM
+    const int smem = 70 * 1024;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_warp_bicubic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_bicubic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "warp_bicubic smem attr: %s", cudaGetErrorString(e));
-        attr = smem;
+        attr = true;
     }
-    dim3 grid(lfx_div_up(H, WB_ROWS), B);
-    k_warp_bicubic<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem ? max_rows : 0);
+    const int ntx = lfx_div_up(W, WB_COLS);
+    dim3 grid(lfx_div_up(H, WB_ROWS) * ntx, B);
+    if (ntx == 1)
+        k_warp_bicubic<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx);
+    else
+        k_warp_bicubic<true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx);
     return lfx_check_launch("warp_bicubic");
 }
 

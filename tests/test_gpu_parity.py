@@ -177,6 +177,29 @@ def test_warp_bicubic(dev, hw):
         assert np.array_equal(got[i], sa.warp_bicubic(img[i], coeffs[i], persp[i])), i   # bit-exact (allowed +-1)
 
 
+@pytest.mark.parametrize("hw", [(40, 300), (64, 515), (96, 1024), (33, 259)])
+def test_warp_bicubic_tiles_and_general_maps(dev, hw):
+    """Several column tiles / slices per band (W > 256, odd widths), general affine maps (both axes mixed) and true
+    perspective maps (taps from global memory) -- against Pillow itself."""
+    from PIL import Image
+    rng = np.random.default_rng(hw[0] * 1000 + hw[1])
+    h, w = hw
+    random.seed(hw[1])
+    coeffs, persp = [], []
+    coeffs.append(sa.skew_coeffs(0.11, w, h)); persp.append(True)
+    coeffs.append(sa.shear_coeffs(0.2, True)); persp.append(False)
+    coeffs.append(sa.shear_coeffs(-0.2, False)); persp.append(False)                    # tall source span: column slices
+    coeffs.append([0.9, 0.25, 3.0, -0.3, 1.05, 7.5, 0.0, 0.0]); persp.append(False)      # general affine
+    coeffs.append([1.02, 0.03, -2.0, 0.01, 0.97, 1.0, 1e-4, -2e-4]); persp.append(True)   # true perspective
+    coeffs.append([1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]); persp.append(False)          # identity: dx = dy = 0
+    img = rng.integers(0, 256, (len(coeffs), h, w, 3), dtype=np.uint8)
+    got = ops.warp_bicubic(up(img, dev), np.array(coeffs, np.float64), persp).cpu().numpy()
+    for i, (co, p) in enumerate(zip(coeffs, persp)):
+        exp = np.asarray(Image.fromarray(img[i]).transform((w, h), Image.Transform.PERSPECTIVE if p else Image.Transform.AFFINE,
+                                                         co if p else co[:6], Image.Resampling.BICUBIC))
+        assert np.array_equal(got[i], exp), (hw, i, int((got[i] != exp).sum()))
+
+
 @pytest.mark.parametrize("hw", SHAPES)
 def test_crop_lanczos(dev, hw):
     rng = np.random.default_rng(10)
