@@ -92,52 +92,78 @@ __global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ sr
 }
 
 // ------------------------------------------------------------------------------ rotate (nearest)
-// One thread produces 4 consecutive output pixels of the FLAT [nh*nw] pixel array -> three
-// 32-bit coalesced stores; sources are gathered through L1/L2 (rotated scanlines are coherent).
+// A block produces RT_PX consecutive pixels of the FLAT [nh*nw] output array.  Lane-contiguous pixels: the 32 gathers
+// of one load instruction walk along a rotated scanline, 3 bytes apart times cos -- a handful of 32-byte sectors per
+// request (one thread owning 4 consecutive pixels spread every request over 32 sectors and the kernel was bound by
+// L1 sector throughput).  The bytes are assembled in shared memory and leave as 16-byte coalesced stores.
+constexpr int RT_STEPS = 4;
+constexpr int RT_PX = THREADS * RT_STEPS;
+
 __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                        long long dst_stride, int H, int W,
                                                        const int32_t* __restrict__ params, int fill) {
+    __shared__ __align__(16) uint8_t s_px[RT_PX * 3];
     const int img = blockIdx.y;
     const int32_t* p = params + img * 8;
     const int a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5];
     const int nw = p[6], nh = p[7];
     const long long npx = (long long)nw * nh;
-    const long long q0 = ((long long)blockIdx.x * THREADS + threadIdx.x) * 4;
+    const long long q0 = (long long)blockIdx.x * RT_PX;
     if (q0 >= npx) return;
     const uint8_t* simg = src + (size_t)img * H * W * 3;
     uint8_t* dimg = dst + (size_t)img * dst_stride;
-    uint8_t out[12];
-    int y = (int)(q0 / nw), x = (int)(q0 - (long long)y * nw);
+    const int nvalid = (int)min((long long)RT_PX, npx - q0);
+    int x, y;
+    if (npx < (1ll << 31)) {   // 32-bit divide in the common case
+        const int q = (int)q0 + threadIdx.x;
+        y = q / nw;
+        x = q - y * nw;
+    } else {
+        const long long q = q0 + threadIdx.x;
+        y = (int)(q / nw);
+        x = (int)(q - (long long)y * nw);
+    }
+    // gather phase: all loads of the RT_STEPS pixels are issued before the first use (addresses of outside pixels are
+    // redirected to byte 0 of the image and the fill colour is selected afterwards), then the bytes go to shared memory
+    const bool small = ((long long)H * W * 3 < (1ll << 31));
+    uint8_t r[RT_STEPS], g[RT_STEPS], b[RT_STEPS];
+    bool in[RT_STEPS];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < RT_STEPS; ++k) {
         // libImaging affine_fixed: 32-bit int arithmetic, arithmetic shift
         const int xin = (a2 + y * a1 + x * a0) >> 16;
         const int yin = (a5 + y * a4 + x * a3) >> 16;
-        uint8_t r = (uint8_t)fill, g = (uint8_t)fill, b = (uint8_t)fill;
-        if (xin >= 0 && xin < W && yin >= 0 && yin < H) {
-            const uint8_t* s = simg + ((size_t)yin * W + xin) * 3;
-            r = __ldg(s);
-            g = __ldg(s + 1);
-            b = __ldg(s + 2);
-        }
-        out[k * 3] = r;
-        out[k * 3 + 1] = g;
-        out[k * 3 + 2] = b;
-        if (++x == nw) {
-            x = 0;
+        in[k] = (unsigned)xin < (unsigned)W && (unsigned)yin < (unsigned)H;
+        const uint8_t* s = simg;
+        if (small) s += in[k] ? (yin * W + xin) * 3 : 0;
+        else s += in[k] ? ((size_t)yin * W + xin) * 3 : (size_t)0;
+        r[k] = __ldg(s);
+        g[k] = __ldg(s + 1);
+        b[k] = __ldg(s + 2);
+        x += THREADS;
+        while (x >= nw) {
+            x -= nw;
             ++y;
         }
     }
-    const long long rem = npx - q0;
+#pragma unroll
+    for (int k = 0; k < RT_STEPS; ++k) {
+        const int li = k * THREADS + threadIdx.x;
+        if (li < nvalid) {
+            s_px[li * 3] = in[k] ? r[k] : (uint8_t)fill;
+            s_px[li * 3 + 1] = in[k] ? g[k] : (uint8_t)fill;
+            s_px[li * 3 + 2] = in[k] ? b[k] : (uint8_t)fill;
+        }
+    }
+    __syncthreads();
     uint8_t* d = dimg + q0 * 3;
-    if (rem >= 4 && ((reinterpret_cast<uintptr_t>(d) & 3) == 0)) {
-        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
-        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+    const int nbytes = nvalid * 3;
+    if ((reinterpret_cast<uintptr_t>(d) & 15) == 0) {
+        const int n16 = nbytes >> 4;
+        for (int i = threadIdx.x; i < n16; i += THREADS) st_stream16(d + i * 16, reinterpret_cast<const uint4*>(s_px)[i]);
+        for (int i = (n16 << 4) + threadIdx.x; i < nbytes; i += THREADS) d[i] = s_px[i];
     } else {
-        const int nb = (int)min(rem, 4ll) * 3;
-        for (int i = 0; i < nb; ++i) d[i] = out[i];
+        for (int i = threadIdx.x; i < nbytes; i += THREADS) d[i] = s_px[i];
     }
 }
 
@@ -959,7 +985,7 @@ extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image
     LFX_REQUIRE(H < 32768 && W < 32768, LFX_ERR_UNSUPPORTED, "rotate_nn: fixed-point path needs sizes < 32768");
     if (B == 0) return LFX_OK;
     const long long max_px = dst_image_stride / 3;
-    dim3 grid(lfx_div_up(max_px, THREADS * 4), B);
+    dim3 grid(lfx_div_up(max_px, RT_PX), B);
     k_rotate_nn<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill);
     return lfx_check_launch("rotate_nn");
 }

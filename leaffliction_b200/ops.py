@@ -282,17 +282,20 @@ def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
     return out
 
 
-def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255):
+def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255, dparams: torch.Tensor = None, out: torch.Tensor = None):
     """params[B][8] = a0..a5 (16.16 fixed point), nw, nh.  Returns (slab [B, stride] u8, stride):
-    image i is slab[i, : nh_i*nw_i*3].view(nh_i, nw_i, 3)."""
+    image i is slab[i, : nh_i*nw_i*3].view(nh_i, nw_i, 3).  `dparams` (the same table already on the device) and
+    `out` (a slab of at least that stride) let a hot loop skip the upload and the allocation."""
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
     params = np.ascontiguousarray(params, np.int32).reshape(B, 8)
     max_px = int((params[:, 6].astype(np.int64) * params[:, 7]).max()) if B else 0
     stride = ((max_px * 3 + 15) // 16) * 16
-    slab = torch.empty((B, max(stride, 16)), dtype=torch.uint8, device=x.device)
-    dp = _dev(params, np.int32, x.device)
+    slab = out if out is not None else torch.empty((B, max(stride, 16)), dtype=torch.uint8, device=x.device)
+    if slab.shape[0] != B or slab.shape[1] < max(stride, 16) or slab.dtype != torch.uint8:
+        raise ValueError("rotate_nn: output slab too small")
+    dp = dparams if dparams is not None else _dev(params, np.int32, x.device)
     _lib.check(lib.lfx_rotate_nn(_p(x), _p(slab), slab.shape[1], B, H, W, _p(dp), int(fill), _stream()))
     return slab, slab.shape[1]
 

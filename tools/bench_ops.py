@@ -95,6 +95,9 @@ def main():
         params[i, 6:] = (nw, nh)
         out_px += nw * nh
     add("rotate_nn (incl. host param upload)", lambda: ops.rotate_nn(x, params), 3 * N + 3 * out_px / B)
+    rslab, _ = ops.rotate_nn(x, params)
+    rdp = torch.from_numpy(params).to(dev)
+    add("rotate_nn", lambda: ops.rotate_nn(x, params, 255, rdp, rslab), 3 * N + 3 * out_px / B)
     coeffs = np.array([[1 + s, 0, -s * S, 0, 1 + s, -s * S, 0, 0] for s in (rng.uniform(0.05, 0.15) for _ in range(B))])
     dco = torch.from_numpy(coeffs).to(dev)
     dpe = torch.ones(B, dtype=torch.int32, device=dev)
