@@ -400,13 +400,13 @@ __global__ void __launch_bounds__(MT, 2)
                     int Ll, A, Bv;
                     rgb2lab(r, g, b, s_lab, Ll, A, Bv);
                     b0 = (M.cfg.strategy == 1) ? ((A <= 135) && (Bv >= 115) && (Bv <= 170))
-                                               : ((h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40));
+                                               : ((M.cfg.strategy == 0) && (h >= M.cfg.green_lo) && (h <= M.cfg.green_hi) && (s >= 40));
                     b1 = M.cfg.use_lab_brown ? ((A >= M.cfg.lab_a_min) && (Bv >= M.cfg.lab_b_min))
                                              : ((h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) &&
                                                 (v <= M.cfg.brown_v_max));
                 } else {
                     // unsigned range checks: (h - lo) <= (hi - lo)
-                    b0 = ((unsigned)(h - M.cfg.green_lo) <= (unsigned)(M.cfg.green_hi - M.cfg.green_lo)) && (s >= 40);  // mask.py:90
+                    b0 = (M.cfg.strategy == 0) && ((unsigned)(h - M.cfg.green_lo) <= (unsigned)(M.cfg.green_hi - M.cfg.green_lo)) && (s >= 40);  // mask.py:90
                     b1 = ((unsigned)(h - M.cfg.brown_lo) <= (unsigned)(M.cfg.brown_hi - M.cfg.brown_lo)) &&
                          (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
                 }
@@ -437,6 +437,14 @@ __global__ void __launch_bounds__(MT, 2)
         c.status = 0;
         c.tacc = tacc;
         c.tk0 = tk0;
+        if (M.cfg.strategy >= 2) {
+            // hsv_s (Otsu on S, 'light' unless dark_bg) / hsv_v_dark (Otsu on V, 'dark'), mask.py:76-84: the threshold needs
+            // the whole histogram, so the candidate plane is built by two more passes over the (L2-resident) image
+            const int chan = M.cfg.strategy == 2 ? 1 : 2;
+            const bool dark = M.cfg.strategy == 2 ? (M.cfg.bg_dark != 0) : true;
+            otsu_plane(simg, s_stage, s_hsv, P0, chan, dark, M, c);
+            __syncthreads();
+        }
         mask_finish(simg, s_stage, s_hsv, P0, PB, PR, T1, T2, T3, s_info, s_info2, M, c);
         plane_to_bytes16(PR, mask + (size_t)img * img_px, c);
         if (threadIdx.x < 8) {
@@ -709,7 +717,7 @@ int ensure_cat_lut() {
 // Shared-memory plan of the fused kernel; false when this shape / config takes the general path.
 bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, const int32_t* taps, CoreParams* out, int* per_sm) {
     if (W % 32 != 0 || W < 32 || H < 3 || (long long)H * W > 65536 || H > TR * TR) return false;
-    if (!cfg || cfg->strategy < 0 || cfg->strategy > 1) return false;
+    if (!cfg || cfg->strategy < 0 || cfg->strategy > 3) return false;   // 2 / 3: Otsu on S / V, one extra pass in phase B
     if ((RW * 3) % 16 != 0 || RW < W || RH < H || RW > 1024 || RH > 1024) return false;
     if (taps[0] != taps[4] || taps[1] != taps[3]) return false;
     for (int i = 0; i < 5; ++i)

@@ -359,6 +359,18 @@ def test_pipeline_core_shapes(dev, hw, roi, strategy):
     _check_core(out, imgs, sm.Cfg(mask_strategy=strategy, fill_size=60, roi_size=roi), roi)
 
 
+@pytest.mark.parametrize("strategy,bias", [("hsv_s", "light_bg"), ("hsv_s", "dark_bg"), ("hsv_v_dark", "light_bg")])
+@pytest.mark.parametrize("hw", [(256, 256), (96, 64), (61, 97)])
+def test_pipeline_core_otsu_strategies(dev, strategy, bias, hw):
+    """Otsu candidates (mask.py:76-84) through the fused kernel (extra histogram + threshold passes in phase B) and the
+    general path (61x97)."""
+    imgs = synth.leaf_batch(4, hw[0], hw[1], seed=5)
+    cfg = ops.mask_cfg(strategy, fill_size=60, bg_bias=bias)
+    out = ops.pipeline_core(up(imgs, dev), cfg, 1.5, (hw[0], hw[1] if hw[1] % 16 == 0 else 112))
+    roi = (hw[0], hw[1] if hw[1] % 16 == 0 else 112)
+    _check_core(out, imgs, sm.Cfg(mask_strategy=strategy, fill_size=60, bg_bias=bias, roi_size=roi), roi)
+
+
 def test_pipeline_core_adversarial(dev):
     adv = synth.adversarial_images(64, 64)
     imgs = np.stack(list(adv.values()))
