@@ -655,6 +655,9 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
                                                                 const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
                                                                 int kstride, const int32_t* __restrict__ toff, int mrows_cap) {
     extern __shared__ __align__(16) uint8_t sm_lz[];
+    __shared__ float s_f255[256];   // v / 255.0f (normalize_array, image_utils.py:126-130): correctly rounded division, tabulated
+    if (dstf)
+        for (int i = threadIdx.x; i < 256; i += THREADS) s_f255[i] = (float)i / 255.0f;
     const int OWB = OW * 3;
     uint8_t* s_mid = sm_lz;                                                               // [mrows_cap][OWB]
     int32_t* s_yk = reinterpret_cast<int32_t*>(sm_lz + (((size_t)mrows_cap * OWB + 15) & ~(size_t)15));  // [LZ_TO][kstride]
@@ -777,11 +780,11 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
         reinterpret_cast<uint32_t*>(dimg)[(size_t)r * wpr + j4] = outw;
         if (fimg) {
             float4 f;
-            f.x = (float)(outw & 0xFFu) / 255.0f;
-            f.y = (float)((outw >> 8) & 0xFFu) / 255.0f;
-            f.z = (float)((outw >> 16) & 0xFFu) / 255.0f;
-            f.w = (float)(outw >> 24) / 255.0f;
-            reinterpret_cast<float4*>(fimg)[(size_t)r * wpr + j4] = f;
+            f.x = s_f255[outw & 0xFFu];
+            f.y = s_f255[(outw >> 8) & 0xFFu];
+            f.z = s_f255[(outw >> 16) & 0xFFu];
+            f.w = s_f255[outw >> 24];
+            __stcs(reinterpret_cast<float4*>(fimg) + (size_t)r * wpr + j4, f);
         }
     }
 }
@@ -1031,20 +1034,25 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
         const bool ok = (OW % 4 == 0) && kstride <= 16 && smem2 <= 200 * 1024 &&
                         ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) && (!dst_f32 || (reinterpret_cast<uintptr_t>(dst_f32) & 15) == 0);
         if (ok) {
-            static size_t attr2[2] = {0, 0};
-            const int wide = kstride > 8;
-            const void* fn = wide ? (const void*)k_crop_lanczos_strip<16> : (const void*)k_crop_lanczos_strip<8>;
-            if (smem2 > 48 * 1024 && smem2 > attr2[wide]) {
-                cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-                attr2[wide] = smem2;
+            // taps per output sample: bounded by the whole-image resize (the crop is never larger than the image)
+            const int kmax = max(lfx_lanczos_ksize(W, OW), lfx_lanczos_ksize(H, OH));
+            const int vi = kmax <= 8 ? 0 : (kmax <= 10 ? 1 : (kmax <= 12 ? 2 : 3));
+            static size_t attr2[4] = {0, 0, 0, 0};
+            const void* fns[4] = {(const void*)k_crop_lanczos_strip<8>, (const void*)k_crop_lanczos_strip<10>,
+                                  (const void*)k_crop_lanczos_strip<12>, (const void*)k_crop_lanczos_strip<16>};
+            if (smem2 > 48 * 1024 && smem2 > attr2[vi]) {
+                cudaFuncSetAttribute(fns[vi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+                attr2[vi] = smem2;
             }
             dim3 grid2(lfx_div_up(OH, LZ_TO), B);
-            if (wide)
-                k_crop_lanczos_strip<16><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds,
-                                                                                     tab_kk, kstride, tab_off, mrows_cap);
-            else
-                k_crop_lanczos_strip<8><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds,
-                                                                                    tab_kk, kstride, tab_off, mrows_cap);
+#define LFX_LZ_LAUNCH(K) \
+    k_crop_lanczos_strip<K><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk, kstride, \
+                                                                         tab_off, mrows_cap)
+            if (vi == 0) LFX_LZ_LAUNCH(8);
+            else if (vi == 1) LFX_LZ_LAUNCH(10);
+            else if (vi == 2) LFX_LZ_LAUNCH(12);
+            else LFX_LZ_LAUNCH(16);
+#undef LFX_LZ_LAUNCH
             return lfx_check_launch("crop_lanczos(strip)");
         }
     }
