@@ -6,8 +6,8 @@
 
 A "step" is one pass of the hot path (5x5 Gaussian blur + make_mask + masked ROI letterbox +
 RGB/HSV/LAB histograms) over one synthetic batch of 4096 256x256x3 uint8 leaf-like images PER GPU
-(weak scaling: the batch shards by image, no data-path collective; with N > 1 one NCCL allreduce
-per step merges the dataset-level colour histogram).  Prints ONE JSON line (rank 0).
+(weak scaling: the batch shards by image, no data-path collective; with N > 1 the dataset-level colour
+histogram is accumulated on each device and merged by ONE NCCL allreduce per pass, inside the timed region).  Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -190,8 +190,11 @@ def main():
 
     def step():
         engine.run_device(x, out)
-        if world > 1:  # dataset-level colour histogram merged across ranks
-            ds_hist.copy_(out.hist9.sum(dim=0, dtype=torch.int64).view(-1))
+        if world > 1:  # dataset-level colour histogram: accumulated on the device batch by batch ...
+            ds_hist.add_(out.hist9.sum(dim=0, dtype=torch.int64).view(-1))
+
+    def merge():
+        if world > 1:  # ... and merged across ranks by ONE allreduce per dataset pass, inside the timed region
             dist.all_reduce(ds_hist)
 
     def barrier():
@@ -201,6 +204,8 @@ def main():
 
     for _ in range(args.warmup):
         step()
+    merge()
+    ds_hist.zero_()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -210,6 +215,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    merge()
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
