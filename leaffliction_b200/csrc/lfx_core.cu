@@ -498,10 +498,8 @@ __global__ void __launch_bounds__(MT, 2)
                 for (int r0 = 0; r0 < top; r0 += CHUNK)
                     bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, top - r0) * RW * 3);
                 if (geo.found) {
-                    // rows of the box itself only when it is narrower than the canvas (side bands); the pixels are
-                    // stored over them later, after bulk_wait_all()
-                    const int from = (geo.nw < RW) ? geo.oy : geo.oy + geo.nh;
-                    for (int r0 = from; r0 < RH; r0 += CHUNK)
+                    // the side bands of the box rows are written by the ROI threads themselves (zero columns below)
+                    for (int r0 = geo.oy + geo.nh; r0 < RH; r0 += CHUNK)
                         bulk_s2g(rimg + (size_t)r0 * RW * 3, s_out, (uint32_t)min(CHUNK, RH - r0) * RW * 3);
                 }
                 bulk_commit();
@@ -518,8 +516,9 @@ __global__ void __launch_bounds__(MT, 2)
                 s_dlo[threadIdx.x] = lo;
             }
         }
-        // ROI thread mapping for this image: one canvas column per thread, MT / cols row strips (power of two)
-        const int roi_cols = max(1, min(geo.nw, MT));
+        // ROI thread mapping for this image: one canvas column per thread over the FULL canvas width (columns left and
+        // right of the resized box store zeros), MT / cols row strips (power of two)
+        const int roi_cols = max(1, min(RW, MT));
         const int roi_sshift = 31 - __clz(max(1, MT / roi_cols));
         const int roi_strips = 1 << roi_sshift;
         const int roi_strip = threadIdx.x / roi_cols, roi_col0 = threadIdx.x - roi_strip * roi_cols;
@@ -602,7 +601,6 @@ __global__ void __launch_bounds__(MT, 2)
                         }
                     }
                 }
-                if (t == 0 && threadIdx.x == 0) bulk_wait_all();   // the zero rows have landed before pixels are stored over them
                 __syncthreads();
                 LFX_TICK(19)
                 const int dA = s_dlo[t], dB = s_dlo[t + 1];
@@ -612,11 +610,20 @@ __global__ void __launch_bounds__(MT, 2)
                 if (roi_strip < roi_strips && dB > dA) {
                     const int per = (dB - dA + roi_strips - 1) >> roi_sshift;
                     const int da = dA + roi_strip * per, db = min(dB, da + per);
-                    for (int cx = roi_col0; cx < geo.nw; cx += roi_cols) {
+                    for (int cc = roi_col0; cc < RW; cc += roi_cols) {
+                        uint8_t* o = rimg + ((size_t)(geo.oy + da) * RW + cc) * 3;
+                        const int cx = cc - geo.ox;
+                        if ((unsigned)cx >= (unsigned)geo.nw) {   // side band of the letterbox
+                            for (int d = da; d < db; ++d, o += RW * 3) {
+                                __stcs(o + 0, (uint8_t)0);
+                                __stcs(o + 1, (uint8_t)0);
+                                __stcs(o + 2, (uint8_t)0);
+                            }
+                            continue;
+                        }
                         const int2 tx = s_xt[cx];
                         const uint32_t xa = tx.y & 0xFFFF, xb = (uint32_t)tx.y >> 16;
                         const uint8_t* colp = tile0 + tx.x;
-                        uint8_t* o = rimg + ((size_t)(geo.oy + da) * RW + geo.ox + cx) * 3;
                         int prev_s = -4;
                         uint32_t h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
                         for (int d = da; d < db; ++d, o += RW * 3) {
