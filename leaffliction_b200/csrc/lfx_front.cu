@@ -11,6 +11,17 @@
 #include "lfx_planes.cuh"
 
 namespace {
+// i -> (i / n, i % n) without an integer division when n is a power of two (256-wide images: every n below is)
+__device__ __forceinline__ void divmod_fast(int i, int n, int& q, int& r) {
+    if ((n & (n - 1)) == 0) {
+        q = i >> (31 - __clz(n));
+        r = i & (n - 1);
+    } else {
+        q = i / n;
+        r = i - q * n;
+    }
+}
+
 
 constexpr int FP_N = 6;       // planes available to the front ends
 constexpr int STRIP_BYTES = 36 * 1024;
@@ -60,7 +71,8 @@ __device__ void rgb_pass(const uint8_t* img, const FrontParams& P, const FrontMe
         block_load_bytes(M.stage, img + (size_t)y0 * rb, nrows * rb);
         __syncthreads();
         for (int item = wid; item < nrows * P.WPR; item += MT / 32) {
-            const int ry = item / P.WPR, w = item - ry * P.WPR;
+            int ry, w;
+            divmod_fast(item, P.WPR, ry, w);
             const int x = w * 32 + lane;
             int bits = 0;
             if (x < P.W) {
@@ -104,7 +116,8 @@ __device__ void canny(const uint8_t* gray, int lo, int hi, bool l2, uint32_t* ca
         // magnitudes of rows ys-1 .. ye (zero outside the image)
         const int mrows = ye - ys + 2;
         for (int i = threadIdx.x; i < mrows * W; i += MT) {
-            const int ry = i / W, x = i - ry * W;
+            int ry, x;
+            divmod_fast(i, W, ry, x);
             const int y = ys - 1 + ry;
             int m = 0;
             if (y >= 0 && y < H) {
@@ -116,7 +129,8 @@ __device__ void canny(const uint8_t* gray, int lo, int hi, bool l2, uint32_t* ca
         }
         __syncthreads();
         for (int item = wid; item < (ye - ys) * P.WPR; item += MT / 32) {
-            const int ry = item / P.WPR, w = item - ry * P.WPR;
+            int ry, w;
+            divmod_fast(item, P.WPR, ry, w);
             const int y = ys + ry, x = w * 32 + lane;
             bool bc = false, bs = false;
             if (x < W) {
@@ -233,7 +247,8 @@ __device__ void gauss_gray_pass(const uint8_t* gray, const int* taps, uint32_t* 
         }
         __syncthreads();
         for (int item = wid; item < (ye - ys) * P.WPR; item += MT / 32) {
-            const int ry = item / P.WPR, w = item - ry * P.WPR;
+            int ry, w;
+            divmod_fast(item, P.WPR, ry, w);
             const int y = ys + ry, x = w * 32 + lane;
             bool bit = false;
             if (x < W) {
@@ -293,7 +308,8 @@ __device__ void close_(uint32_t* m, uint32_t* t, const Footprint& fp, Ctx& c) {
 
 __device__ void plane_out_bytes(const uint32_t* p, uint8_t* out, int channels, const FrontParams& P) {
     for (int i = threadIdx.x; i < P.H * P.W; i += MT) {
-        const int y = i / P.W, x = i - y * P.W;
+        int y, x;
+        divmod_fast(i, P.W, y, x);
         const uint8_t v = ((p[y * P.WPR + (x >> 5)] >> (x & 31)) & 1) ? 255 : 0;
         for (int ch = 0; ch < channels; ++ch) out[(size_t)i * channels + ch] = v;
     }
@@ -301,7 +317,8 @@ __device__ void plane_out_bytes(const uint32_t* p, uint8_t* out, int channels, c
 __device__ void bytes_in_plane(const uint8_t* in, uint32_t* p, const FrontParams& P) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int item = wid; item < P.NW; item += MT / 32) {
-        const int y = item / P.WPR, w = item - y * P.WPR;
+        int y, w;
+        divmod_fast(item, P.WPR, y, w);
         const int x = w * 32 + lane;
         const bool on = (x < P.W) && (__ldg(in + (size_t)y * P.W + x) > 0);
         const uint32_t m = __ballot_sync(0xffffffffu, on);
