@@ -106,6 +106,109 @@ __global__ void __launch_bounds__(THREADS) k_threshold_mask(const uint8_t* __res
     }
 }
 
+// ------------------------------------------------------------------------------ register-only variants
+// 16 pixels per thread straight from global memory (three 16-byte loads -> byte extraction by PRMT at compile-time
+// positions -> arithmetic -> packed 16-byte stores): no shared staging, no barriers in the loop.  Used when the buffers
+// are 16-byte aligned; the shared-tile kernels above remain the general path and handle the < 16 pixel tail.
+template <int K>
+__device__ __forceinline__ int px_byte(const uint32_t (&w)[12]) {   // byte K of the 48-byte group
+    return (int)__byte_perm(w[K >> 2], 0u, 0x4440u + (K & 3));
+}
+__device__ __forceinline__ uint32_t pack4u(int a, int b, int c, int d) {
+    return __byte_perm(__byte_perm((uint32_t)a, (uint32_t)b, 0x0040), __byte_perm((uint32_t)c, (uint32_t)d, 0x0040), 0x5410);
+}
+__device__ __forceinline__ void load48(const uint8_t* p, uint32_t (&w)[12]) {
+    const uint4 a = ld_stream16(p), b = ld_stream16(p + 16), c = ld_stream16(p + 32);
+    w[0] = a.x, w[1] = a.y, w[2] = a.z, w[3] = a.w, w[4] = b.x, w[5] = b.y, w[6] = b.z, w[7] = b.w;
+    w[8] = c.x, w[9] = c.y, w[10] = c.z, w[11] = c.w;
+}
+
+template <int P>
+struct PxLoop {   // compile-time loop over the 16 pixels of a group
+    template <class F>
+    __device__ __forceinline__ static void run(const uint32_t (&w)[12], F&& f) {
+        f(P, px_byte<3 * P>(w), px_byte<3 * P + 1>(w), px_byte<3 * P + 2>(w));
+        PxLoop<P + 1>::run(w, f);
+    }
+};
+template <>
+struct PxLoop<16> {
+    template <class F>
+    __device__ __forceinline__ static void run(const uint32_t (&)[12], F&&) {}
+};
+
+template <int CODE>
+__global__ void __launch_bounds__(THREADS) k_cvt_color_vec(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                           long long ngroups, const LfxTables* __restrict__ tab) {
+    __shared__ HsvLut s_hsv;
+    __shared__ LabLut s_lab;
+    if (CODE == 1) load_hsv_lut(&s_hsv, tab);
+    if (CODE == 2) load_lab_lut(&s_lab, tab);
+    __syncthreads();
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < ngroups; g += (long long)gridDim.x * THREADS) {
+        uint32_t w[12];
+        load48(src + g * 48, w);
+        uint8_t o[48];
+        PxLoop<0>::run(w, [&](int p, int r, int gg, int b) {
+            if (CODE == 0) {
+                o[p] = (uint8_t)rgb2gray(r, gg, b);
+            } else if (CODE == 1) {
+                int h, sv, v;
+                rgb2hsv(r, gg, b, &s_hsv, h, sv, v);
+                o[p * 3] = (uint8_t)h, o[p * 3 + 1] = (uint8_t)sv, o[p * 3 + 2] = (uint8_t)v;
+            } else {
+                int L, A, Bv;
+                rgb2lab(r, gg, b, &s_lab, L, A, Bv);
+                o[p * 3] = (uint8_t)L, o[p * 3 + 1] = (uint8_t)A, o[p * 3 + 2] = (uint8_t)Bv;
+            }
+        });
+        if (CODE == 0) {
+            st_stream16(dst + g * 16, make_uint4(pack4u(o[0], o[1], o[2], o[3]), pack4u(o[4], o[5], o[6], o[7]),
+                                                 pack4u(o[8], o[9], o[10], o[11]), pack4u(o[12], o[13], o[14], o[15])));
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                st_stream16(dst + g * 48 + q * 16,
+                            make_uint4(pack4u(o[q * 16], o[q * 16 + 1], o[q * 16 + 2], o[q * 16 + 3]),
+                                       pack4u(o[q * 16 + 4], o[q * 16 + 5], o[q * 16 + 6], o[q * 16 + 7]),
+                                       pack4u(o[q * 16 + 8], o[q * 16 + 9], o[q * 16 + 10], o[q * 16 + 11]),
+                                       pack4u(o[q * 16 + 12], o[q * 16 + 13], o[q * 16 + 14], o[q * 16 + 15])));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) k_threshold_mask_vec(const uint8_t* __restrict__ src, uint8_t* __restrict__ mask,
+                                                                long long ngroups, ThreshParams prm,
+                                                                const LfxTables* __restrict__ tab) {
+    __shared__ HsvLut s_hsv;
+    __shared__ LabLut s_lab;
+    if (prm.strategy == 0)
+        load_hsv_lut(&s_hsv, tab);
+    else
+        load_lab_lut(&s_lab, tab);
+    __syncthreads();
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < ngroups; g += (long long)gridDim.x * THREADS) {
+        uint32_t w[12];
+        load48(src + g * 48, w);
+        uint8_t o[16];
+        PxLoop<0>::run(w, [&](int p, int r, int gg, int b) {
+            bool on;
+            if (prm.strategy == 0) {
+                int h, sv, v;
+                rgb2hsv(r, gg, b, &s_hsv, h, sv, v);
+                on = ((unsigned)(h - prm.green_lo) <= (unsigned)(prm.green_hi - prm.green_lo)) && (sv >= 40);  // mask.py:90
+            } else {
+                int L, A, Bv;
+                rgb2lab(r, gg, b, &s_lab, L, A, Bv);
+                on = (A <= 135) && (Bv >= 115) && (Bv <= 170);  // mask.py:105
+            }
+            o[p] = on ? 255 : 0;
+        });
+        st_stream16(mask + g * 16, make_uint4(pack4u(o[0], o[1], o[2], o[3]), pack4u(o[4], o[5], o[6], o[7]),
+                                              pack4u(o[8], o[9], o[10], o[11]), pack4u(o[12], o[13], o[14], o[15])));
+    }
+}
+
 // ------------------------------------------------------------------------------ apply_mask
 __global__ void __launch_bounds__(THREADS) k_apply_mask(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
                                                         uint8_t* __restrict__ dst, long long npix, int color_val) {
@@ -266,13 +369,31 @@ extern "C" int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int
     if (B == 0) return LFX_OK;
     const long long npix = (long long)B * H * W;
     cudaStream_t st = (cudaStream_t)stream;
-    const int grid = stream_grid(npix);
-    if (code == 0)
-        k_cvt_color<0><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
-    else if (code == 1)
-        k_cvt_color<1><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
-    else
-        k_cvt_color<2><<<grid, THREADS, 0, st>>>(src, dst, npix, lfx_tables());
+    // 16-pixel groups by the register-only kernel, the tail (and unaligned buffers) by the shared-tile kernel
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && npix >= 16) {
+        const long long ng = npix / 16;
+        const int gv = (int)min((ng + THREADS - 1) / THREADS, (long long)LFX_NUM_SMS * 16);
+        if (code == 0)
+            k_cvt_color_vec<0><<<gv, THREADS, 0, st>>>(src, dst, ng, lfx_tables());
+        else if (code == 1)
+            k_cvt_color_vec<1><<<gv, THREADS, 0, st>>>(src, dst, ng, lfx_tables());
+        else
+            k_cvt_color_vec<2><<<gv, THREADS, 0, st>>>(src, dst, ng, lfx_tables());
+        done = ng * 16;
+    }
+    if (done < npix) {
+        const long long rem = npix - done;
+        const int grid = stream_grid(rem);
+        const uint8_t* s2 = src + done * 3;
+        uint8_t* d2 = dst + done * (code == 0 ? 1 : 3);
+        if (code == 0)
+            k_cvt_color<0><<<grid, THREADS, 0, st>>>(s2, d2, rem, lfx_tables());
+        else if (code == 1)
+            k_cvt_color<1><<<grid, THREADS, 0, st>>>(s2, d2, rem, lfx_tables());
+        else
+            k_cvt_color<2><<<grid, THREADS, 0, st>>>(s2, d2, rem, lfx_tables());
+    }
     return lfx_check_launch("cvt_color");
 }
 
@@ -286,7 +407,16 @@ extern "C" int lfx_threshold_mask(const uint8_t* src, uint8_t* mask, int B, int 
     if (B == 0) return LFX_OK;
     const long long npix = (long long)B * H * W;
     ThreshParams prm{cfg->strategy, cfg->green_lo, cfg->green_hi};
-    k_threshold_mask<<<stream_grid(npix), THREADS, 0, (cudaStream_t)stream>>>(src, mask, npix, prm, lfx_tables());
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0 && npix >= 16) {
+        const long long ng = npix / 16;
+        const int gv = (int)min((ng + THREADS - 1) / THREADS, (long long)LFX_NUM_SMS * 16);
+        k_threshold_mask_vec<<<gv, THREADS, 0, (cudaStream_t)stream>>>(src, mask, ng, prm, lfx_tables());
+        done = ng * 16;
+    }
+    if (done < npix)
+        k_threshold_mask<<<stream_grid(npix - done), THREADS, 0, (cudaStream_t)stream>>>(src + done * 3, mask + done, npix - done, prm,
+                                                                                         lfx_tables());
     return lfx_check_launch("threshold_mask");
 }
 
