@@ -6,7 +6,7 @@
 namespace {
 
 constexpr int THREADS = 256;
-constexpr int ROI_ROWS = 16;  // canvas rows per block
+constexpr int ROI_ROWS = 64;  // canvas rows per block
 
 struct Tap {
     int s;       // source index
@@ -35,92 +35,90 @@ __device__ __forceinline__ Tap area_tap(int d, int src, int dst) {
     return t;
 }
 
-// grid (ceil(RH/ROI_ROWS), B)
+// grid (ceil(RH/ROI_ROWS), B).  One canvas column per thread walking down the block's rows: the horizontal stage of a
+// source row is computed once and carried to the next canvas row that uses it (upscale: consecutive canvas rows share
+// source rows), the vertical stage is two IMAD.HI; columns / rows outside the resized box store zeros.  Pixels go
+// straight to HBM as streaming byte stores (lane-contiguous: L2 merges the sectors).
 __global__ void __launch_bounds__(THREADS) k_roi(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
                                                  const int32_t* __restrict__ info, uint8_t* __restrict__ dst, int H, int W,
                                                  int RH, int RW) {
-    extern __shared__ __align__(16) uint8_t sm[];
-    uint8_t* s_out = sm;                                              // [ROI_ROWS][RW*3]
-    Tap* s_xt = reinterpret_cast<Tap*>(sm + ((ROI_ROWS * RW * 3 + 15) & ~15));  // [RW]
-    Tap* s_yt = s_xt + RW;                                             // [ROI_ROWS]
+    __shared__ Tap s_yt[ROI_ROWS];
     const int img = blockIdx.y;
     const int r0 = blockIdx.x * ROI_ROWS;
     const int rows = min(ROI_ROWS, RH - r0);
     const int32_t* inf = info + (size_t)img * 8;
     const int found = inf[0], bx = inf[1], by = inf[2], bw = inf[3], bh = inf[4];
     uint8_t* dimg = dst + ((size_t)img * RH + r0) * RW * 3;
-    for (int i = threadIdx.x; i < rows * RW * 3; i += THREADS) s_out[i] = 0;
-    if (!found || bw <= 0 || bh <= 0) {
-        __syncthreads();
-        block_store_bytes(dimg, s_out, rows * RW * 3);
-        return;
-    }
-    // scale = min(W / max(w,1), H / max(h,1)); nw = max(int(w*scale),1)   (roi.py:35-36, Python floats)
-    const double sc = fmin(__ddiv_rn((double)RW, (double)max(bw, 1)), __ddiv_rn((double)RH, (double)max(bh, 1)));
-    const int nw = max((int)__dmul_rn((double)bw, sc), 1), nh = max((int)__dmul_rn((double)bh, sc), 1);
-    const int oy = (RH - nh) / 2, ox = (RW - nw) / 2;
-    const bool same = (nw == bw && nh == bh);
-    for (int i = threadIdx.x; i < nw; i += THREADS) {
-        Tap t;
-        if (same) {
-            t.s = i; t.a = 2048; t.b = 0;
-        } else {
-            t = area_tap(i, bw, nw);
-        }
-        s_xt[i] = t;
+    int nw = 0, nh = 0, ox = 0, oy = 0;
+    if (found && bw > 0 && bh > 0) {
+        // scale = min(W / max(w,1), H / max(h,1)); nw = max(int(w*scale),1)   (roi.py:35-36, Python floats)
+        const double sc = fmin(__ddiv_rn((double)RW, (double)max(bw, 1)), __ddiv_rn((double)RH, (double)max(bh, 1)));
+        nw = max((int)__dmul_rn((double)bw, sc), 1), nh = max((int)__dmul_rn((double)bh, sc), 1);
+        oy = (RH - nh) / 2, ox = (RW - nw) / 2;
     }
     for (int i = threadIdx.x; i < rows; i += THREADS) {
         const int d = r0 + i - oy;
         Tap t;
         t.s = -1; t.a = 0; t.b = 0;
-        if (d >= 0 && d < nh) {
-            if (same) {
-                t.s = d; t.a = 2048; t.b = 0;
-            } else {
-                t = area_tap(d, bh, nh);
-            }
-        }
+        if (d >= 0 && d < nh) t = area_tap(d, bh, nh);
         s_yt[i] = t;
     }
     __syncthreads();
     const uint8_t* simg = src + (size_t)img * H * W * 3;
     const uint8_t* mimg = mask ? mask + (size_t)img * H * W : nullptr;
-    for (int i = threadIdx.x; i < rows * nw; i += THREADS) {
-        const int ry = i / nw, cx = i - ry * nw;
-        const Tap ty = s_yt[ry];
-        if (ty.s < 0) continue;
-        const Tap tx = s_xt[cx];
-        const int y0 = by + ty.s, y1 = by + min(ty.s + 1, bh - 1);
-        const int x0 = bx + tx.s, x1 = bx + min(tx.s + 1, bw - 1);
-        // masked_rgb = apply_mask(rgb, mask, "white")  (Transformation.py:451)
-        const bool m00 = !mimg || __ldg(mimg + (size_t)y0 * W + x0) > 127;
-        const bool m01 = !mimg || __ldg(mimg + (size_t)y0 * W + x1) > 127;
-        const bool m10 = !mimg || __ldg(mimg + (size_t)y1 * W + x0) > 127;
-        const bool m11 = !mimg || __ldg(mimg + (size_t)y1 * W + x1) > 127;
-        const uint8_t* p00 = simg + ((size_t)y0 * W + x0) * 3;
-        const uint8_t* p01 = simg + ((size_t)y0 * W + x1) * 3;
-        const uint8_t* p10 = simg + ((size_t)y1 * W + x0) * 3;
-        const uint8_t* p11 = simg + ((size_t)y1 * W + x1) * 3;
-        uint8_t* o = s_out + (ry * RW + ox + cx) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const int v00 = m00 ? __ldg(p00 + c) : 255, v01 = m01 ? __ldg(p01 + c) : 255;
-            const int v10 = m10 ? __ldg(p10 + c) : 255, v11 = m11 ? __ldg(p11 + c) : 255;
-            int res;
-            if (same) {
-                res = v00;
-            } else {
-                const int h0 = v00 * tx.a + v01 * tx.b;  // HResizeLinear, x2048
-                const int h1 = v10 * tx.a + v11 * tx.b;
-                // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>
-                res = ((((int)ty.a * (h0 >> 4)) >> 16) + (((int)ty.b * (h1 >> 4)) >> 16) + 2) >> 2;
-                res = min(255, max(0, res));
+    for (int cc = threadIdx.x; cc < RW; cc += THREADS) {
+        uint8_t* o = dimg + (size_t)cc * 3;
+        const int cx = cc - ox;
+        if ((unsigned)cx >= (unsigned)nw) {   // left / right band (or nothing found): zeros
+            for (int r = 0; r < rows; ++r, o += RW * 3) {
+                __stcs(o + 0, (uint8_t)0);
+                __stcs(o + 1, (uint8_t)0);
+                __stcs(o + 2, (uint8_t)0);
             }
-            o[c] = (uint8_t)res;
+            continue;
+        }
+        const Tap tx = area_tap(cx, bw, nw);
+        const int x0 = bx + tx.s, x1 = bx + min(tx.s + 1, bw - 1);
+        const uint32_t xa = (uint32_t)(uint16_t)tx.a, xb = (uint32_t)(uint16_t)tx.b;
+        // horizontal stage of source row y (of the white-masked image, Transformation.py:451): HResizeLinear x2048, >> 4
+        auto hrow = [&](int y, uint32_t& hr, uint32_t& hg, uint32_t& hb) {
+            const size_t ro = (size_t)y * W;
+            const bool m0 = !mimg || __ldg(mimg + ro + x0) > 127, m1 = !mimg || __ldg(mimg + ro + x1) > 127;
+            const uint8_t* p0 = simg + (ro + x0) * 3;
+            const uint8_t* p1 = simg + (ro + x1) * 3;
+            const uint32_t r0v = m0 ? __ldg(p0) : 255u, g0v = m0 ? __ldg(p0 + 1) : 255u, b0v = m0 ? __ldg(p0 + 2) : 255u;
+            const uint32_t r1v = m1 ? __ldg(p1) : 255u, g1v = m1 ? __ldg(p1 + 1) : 255u, b1v = m1 ? __ldg(p1 + 2) : 255u;
+            hr = (r0v * xa + r1v * xb) >> 4;
+            hg = (g0v * xa + g1v * xb) >> 4;
+            hb = (b0v * xa + b1v * xb) >> 4;
+        };
+        int prev_s = -4;
+        uint32_t h0r = 0, h0g = 0, h0b = 0, h1r = 0, h1g = 0, h1b = 0;
+        for (int r = 0; r < rows; ++r, o += RW * 3) {
+            const Tap ty = s_yt[r];
+            if (ty.s < 0) {   // top / bottom band
+                __stcs(o + 0, (uint8_t)0);
+                __stcs(o + 1, (uint8_t)0);
+                __stcs(o + 2, (uint8_t)0);
+                continue;
+            }
+            if (ty.s != prev_s) {
+                if (ty.s == prev_s + 1) {
+                    h0r = h1r, h0g = h1g, h0b = h1b;
+                } else {
+                    hrow(by + ty.s, h0r, h0g, h0b);
+                }
+                hrow(by + min(ty.s + 1, bh - 1), h1r, h1g, h1b);
+                prev_s = ty.s;
+            }
+            // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>: ((a * (h0 >> 4)) >> 16) + ((b * (h1 >> 4)) >> 16) + 2 >> 2
+            // with (a * h >> 16) taken as the high word of (a << 16) * h; a + b <= 2049 keeps the result in 0..255
+            const uint32_t ya = (uint32_t)(uint16_t)ty.a << 16, yb = (uint32_t)(uint16_t)ty.b << 16;
+            __stcs(o + 0, (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2));
+            __stcs(o + 1, (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2));
+            __stcs(o + 2, (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2));
         }
     }
-    __syncthreads();
-    block_store_bytes(dimg, s_out, rows * RW * 3);
 }
 
 }  // namespace
@@ -133,15 +131,8 @@ extern "C" int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const 
                 "roi_letterbox: bad arguments");
     LFX_REQUIRE(RW >= W && RH >= H, LFX_ERR_UNSUPPORTED,
                 "roi_letterbox: roi_size (%d,%d) smaller than the image (%d,%d) needs the INTER_AREA shrink path", RH, RW, H, W);
-    const size_t smem = ((size_t)(ROI_ROWS * RW * 3 + 15) & ~15) + (size_t)(RW + ROI_ROWS) * 8;
-    LFX_REQUIRE(smem <= 200 * 1024, LFX_ERR_UNSUPPORTED, "roi_letterbox: roi width %d too large", RW);
     if (B == 0) return LFX_OK;
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(k_roi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
     dim3 grid(lfx_div_up(RH, ROI_ROWS), B);
-    k_roi<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, mask, info, dst, H, W, RH, RW);
+    k_roi<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, mask, info, dst, H, W, RH, RW);
     return lfx_check_launch("roi_letterbox");
 }
