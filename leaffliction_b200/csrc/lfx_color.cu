@@ -243,104 +243,86 @@ __global__ void __launch_bounds__(THREADS) k_apply_mask(const uint8_t* __restric
 }
 
 // ------------------------------------------------------------------------------ colour statistics
-// One block handles a contiguous pixel range of ONE image.  Histograms live in shared memory,
-// replicated per warp pair to cut same-address contention, merged to global with atomicAdd.
-constexpr int HREP = 4;  // replicas of the 12x256 table (warp w uses replica w % HREP)
+// One block handles a contiguous pixel range of ONE image; lane-contiguous pixels straight from global memory (the
+// mask byte first: unmasked pixels cost one load), twelve 256-bin histograms in shared memory (neighbouring pixels hit
+// neighbouring bins = distinct banks, equal bins merge), merged to global with atomicAdd.  The 1 + 8 + 5 category
+// counters of hist.py:188,38-65,248-256 come from per-channel LUTs of byte-packed 0/1 flags (AND = joint predicate)
+// accumulated in packed 8-bit counters that are flushed every 128 pixels per thread (lfx_core.cu builds the LUT).
+constexpr int STATS_FLUSH = 128;
 
 __global__ void __launch_bounds__(THREADS) k_color_stats(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
                                                          int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3,
                                                          int32_t* __restrict__ counters, int HW, int px_per_block,
-                                                         const LfxTables* __restrict__ tab) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    // layout: hist[HREP][12][256] u32 | cnt[16] | in tile | mask tile | luts
-    uint32_t* s_hist = reinterpret_cast<uint32_t*>(smem_raw);
-    uint32_t* s_cnt = s_hist + HREP * 12 * 256;
-    uint8_t* s_in = reinterpret_cast<uint8_t*>(s_cnt + 16);
-    uint8_t* s_m = s_in + TILE_PX * 3;
-    HsvLut* s_hsv = reinterpret_cast<HsvLut*>(s_m + TILE_PX);
-    LabLut* s_lab = reinterpret_cast<LabLut*>(s_hsv + 1);
-
+                                                         const LfxTables* __restrict__ tab, const uint4* __restrict__ cat_lut) {
+    __shared__ uint32_t s_hist[12 * 256];
+    __shared__ uint32_t s_cnt[16];
+    __shared__ uint4 s_cat[3 * 256];
+    __shared__ HsvLut s_hsv;
+    __shared__ LabLut s_lab;
     const int img = blockIdx.y;
     const int begin = blockIdx.x * px_per_block;
     const int end = min(HW, begin + px_per_block);
     if (begin >= end) return;
     const bool want9 = hist9 != nullptr;
     const bool wantS = (hsv3 != nullptr) || (counters != nullptr);
-
-    for (int i = threadIdx.x; i < HREP * 12 * 256 + 16; i += THREADS) s_hist[i] = 0;
-    load_hsv_lut(s_hsv, tab);
-    if (want9) load_lab_lut(s_lab, tab);
+    for (int i = threadIdx.x; i < 12 * 256; i += THREADS) s_hist[i] = 0;
+    if (threadIdx.x < 16) s_cnt[threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < 3 * 256; i += THREADS) s_cat[i] = cat_lut[i];
+    load_hsv_lut(&s_hsv, tab);
+    if (want9) load_lab_lut(&s_lab, tab);
     __syncthreads();
-
-    uint32_t* myh = s_hist + ((threadIdx.x >> 5) % HREP) * 12 * 256;
-    uint32_t c[14];
-#pragma unroll
-    for (int i = 0; i < 14; ++i) c[i] = 0;
-
     const uint8_t* simg = src + (size_t)img * HW * 3;
     const uint8_t* mimg = mask ? mask + (size_t)img * HW : nullptr;
-    for (int base = begin; base < end; base += TILE_PX) {
-        const int n = min(TILE_PX, end - base);
-        block_load_bytes(s_in, simg + (size_t)base * 3, n * 3);
-        if (mimg) block_load_bytes(s_m, mimg + base, n);
-        __syncthreads();
-        // stride-THREADS pixel assignment: lanes of a warp read neighbouring pixels (bank-friendly)
-        for (int p = threadIdx.x; p < n; p += THREADS) {
-            const int mk = mimg ? s_m[p] : 255;
+    const int lane = threadIdx.x & 31;
+    for (int c0 = begin; c0 < end; c0 += STATS_FLUSH * THREADS) {
+        const int c1 = min(end, c0 + STATS_FLUSH * THREADS);
+        uint32_t cacc[4] = {0u, 0u, 0u, 0u};
+        for (int p = c0 + threadIdx.x; p < c1; p += THREADS) {
+            const int mk = mimg ? __ldg(mimg + p) : 255;
             if (mk == 0) continue;
-            const int r = s_in[p * 3], g = s_in[p * 3 + 1], b = s_in[p * 3 + 2];
-            int h, s, v;
-            rgb2hsv(r, g, b, s_hsv, h, s, v);
+            const uint8_t* px = simg + (size_t)p * 3;
+            const int r = __ldg(px), g = __ldg(px + 1), b = __ldg(px + 2);
+            int h, sv, v;
+            rgb2hsv(r, g, b, &s_hsv, h, sv, v);
             if (want9) {
                 int L, A, Bv;
-                rgb2lab(r, g, b, s_lab, L, A, Bv);
-                atomicAdd(&myh[0 * 256 + r], 1u);
-                atomicAdd(&myh[1 * 256 + g], 1u);
-                atomicAdd(&myh[2 * 256 + b], 1u);
-                atomicAdd(&myh[3 * 256 + h], 1u);
-                atomicAdd(&myh[4 * 256 + s], 1u);
-                atomicAdd(&myh[5 * 256 + v], 1u);
-                atomicAdd(&myh[6 * 256 + L], 1u);
-                atomicAdd(&myh[7 * 256 + A], 1u);
-                atomicAdd(&myh[8 * 256 + Bv], 1u);
+                rgb2lab(r, g, b, &s_lab, L, A, Bv);
+                atomicAdd(&s_hist[0 * 256 + r], 1u);
+                atomicAdd(&s_hist[1 * 256 + g], 1u);
+                atomicAdd(&s_hist[2 * 256 + b], 1u);
+                atomicAdd(&s_hist[3 * 256 + h], 1u);
+                atomicAdd(&s_hist[4 * 256 + sv], 1u);
+                atomicAdd(&s_hist[5 * 256 + v], 1u);
+                atomicAdd(&s_hist[6 * 256 + L], 1u);
+                atomicAdd(&s_hist[7 * 256 + A], 1u);
+                atomicAdd(&s_hist[8 * 256 + Bv], 1u);
             }
             // apply_mask binarises at >127 and paints the rest white (s = 0): never in leaf_mask
-            if (wantS && mk > 127 && s > 10 && v > 15 && v < 245) {  // hist.py:188
-                atomicAdd(&myh[9 * 256 + h], 1u);
-                atomicAdd(&myh[10 * 256 + s], 1u);
-                atomicAdd(&myh[11 * 256 + v], 1u);
-                c[0] += 1;
-                c[1] += (h >= 35 && h <= 85 && s >= 40 && v >= 30);                 // Vert Sain
-                c[2] += (h >= 20 && h <= 40 && s >= 25 && v >= 30);                 // Vert Jaunatre
-                c[3] += (h >= 15 && h <= 35 && s >= 50 && v >= 50);                 // Jaune
-                c[4] += ((h <= 25 || h >= 160) && s >= 30 && v >= 20);              // Brun/Orange
-                c[5] += (((h >= 160 && h <= 180) || h <= 10) && s >= 40 && v >= 30);  // Rouge
-                c[6] += (v <= 50 && s >= 20);                                       // Zones Sombres
-                c[7] += (v >= 200 && s <= 30);                                      // Zones Claires
-                c[8] += (h >= 120 && h <= 160 && s >= 20);                          // Violet/Pourpre
-                c[9] += (h >= 35 && h <= 85);                                       // hue ranges :248-256
-                c[10] += (h >= 15 && h <= 35);
-                c[11] += (h <= 15 || h >= 160);
-                c[12] += (h >= 120 && h <= 160);
-                c[13] += (h > 85 && h < 120);
+            if (wantS && mk > 127) {
+                const uint4 qh = s_cat[h], qs = s_cat[256 + sv], qv = s_cat[512 + v];
+                const uint32_t q0 = qh.x & qs.x & qv.x;
+                cacc[0] += q0;
+                cacc[1] += qh.y & qs.y & qv.y;
+                cacc[2] += qh.z & qs.z & qv.z;
+                cacc[3] += qh.w & qs.w & qv.w;
+                if (q0 & 1u) {   // leaf_mask (hist.py:188)
+                    atomicAdd(&s_hist[9 * 256 + h], 1u);
+                    atomicAdd(&s_hist[10 * 256 + sv], 1u);
+                    atomicAdd(&s_hist[11 * 256 + v], 1u);
+                }
             }
         }
-        __syncthreads();
-    }
-    if (counters) {
+        if (counters) {
 #pragma unroll
-        for (int i = 0; i < 14; ++i) {
-            uint32_t v = c[i];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_cnt[i], v);
+            for (int k = 0; k < 14; ++k) {
+                const uint32_t v = __reduce_add_sync(0xffffffffu, (cacc[k >> 2] >> (8 * (k & 3))) & 0xFFu);
+                if (lane == 0 && v) atomicAdd(&s_cnt[k], v);
+            }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 12 * 256; i += THREADS) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int rj = 0; rj < HREP; ++rj) v += s_hist[rj * 12 * 256 + i];
+        const uint32_t v = s_hist[i];
         if (!v) continue;
         if (i < 9 * 256) {
             if (hist9) atomicAdd(&hist9[(size_t)img * 9 * 256 + i], (int)v);
@@ -352,7 +334,6 @@ __global__ void __launch_bounds__(THREADS) k_color_stats(const uint8_t* __restri
         atomicAdd(&counters[(size_t)img * 16 + threadIdx.x], (int)s_cnt[threadIdx.x]);
 }
 
-constexpr size_t STATS_SMEM = (HREP * 12 * 256 + 16) * 4 + TILE_PX * 3 + TILE_PX + sizeof(HsvLut) + sizeof(LabLut);
 
 int stream_grid(long long npix) {
     const long long ntiles = (npix + TILE_PX - 1) / TILE_PX;
@@ -439,11 +420,8 @@ extern "C" int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t*
     LFX_REQUIRE(src && B >= 0 && H > 0 && W > 0 && (hist9 || hsv3 || counters), LFX_ERR_ARG, "color_stats: bad arguments");
     LFX_REQUIRE((long long)H * W < (1ll << 31), LFX_ERR_UNSUPPORTED, "color_stats: image too large");
     if (B == 0) return LFX_OK;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(k_color_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STATS_SMEM);
-        attr_set = true;
-    }
+    const uint4* cat = lfx_cat_lut();
+    LFX_REQUIRE(cat != nullptr, LFX_ERR_CUDA, "color_stats: category LUT upload failed");
     const int HW = H * W;
     // enough blocks to fill the GPU (>= 4 per SM) without shrinking chunks below 4 tiles
     int chunks = lfx_div_up((long long)LFX_NUM_SMS * 4, B);
@@ -454,7 +432,6 @@ extern "C" int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t*
     chunks = lfx_div_up(HW, px_per_block);
     dim3 grid(chunks, B);
     LFX_REQUIRE(B <= 65535, LFX_ERR_UNSUPPORTED, "color_stats: B > 65535, split the batch");
-    k_color_stats<<<grid, THREADS, STATS_SMEM, (cudaStream_t)stream>>>(src, mask, hist9, hsv3, counters, HW, px_per_block,
-                                                                       lfx_tables());
+    k_color_stats<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, mask, hist9, hsv3, counters, HW, px_per_block, lfx_tables(), cat);
     return lfx_check_launch("color_stats");
 }

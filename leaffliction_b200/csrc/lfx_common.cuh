@@ -31,6 +31,7 @@ struct LfxTables {
     uint16_t ctab[3072];
 };
 const LfxTables* lfx_tables();  // device pointer, valid after lfx_init (lfx_api.cu)
+const uint4* lfx_cat_lut();      // [3][256] byte-packed category flags of hist.py (lfx_core.cu), uploaded on first use; null on error
 
 // Shared-memory copies used by the per-pixel device functions.
 struct HsvLut {

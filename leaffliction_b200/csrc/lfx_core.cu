@@ -767,6 +767,8 @@ size_t lfx_core_workspace_bytes(int H, int W) {
     return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
 }
 
+const uint4* lfx_cat_lut() { return ensure_cat_lut() == LFX_OK ? g_cat_lut : nullptr; }
+
 extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
     return lfx_make_mask_workspace(B, H, W);   // already the maximum of the general and the fused requirement
