@@ -242,6 +242,29 @@ __global__ void __launch_bounds__(THREADS) k_apply_mask(const uint8_t* __restric
     }
 }
 
+// apply_mask, 16 pixels per thread in registers (see the register-only variants above)
+__global__ void __launch_bounds__(THREADS) k_apply_mask_vec(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                            uint8_t* __restrict__ dst, long long ngroups, int color_val) {
+    const uint32_t c32 = (uint32_t)color_val * 0x01010101u;
+    for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < ngroups; g += (long long)gridDim.x * THREADS) {
+        uint32_t w[12];
+        load48(src + g * 48, w);
+        const uint4 mq = ld_stream16(mask + g * 16);
+        const uint32_t mw[4] = {mq.x, mq.y, mq.z, mq.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k = ((mw[j] >> 7) & 0x01010101u) * 0xFFu;      // mask_utils.py:68: keep where mask > 127
+            const uint32_t k0 = __byte_perm(k, k, 0x1000), k1 = __byte_perm(k, k, 0x2211), k2 = __byte_perm(k, k, 0x3332);
+            w[3 * j] = (w[3 * j] & k0) | (c32 & ~k0);                      // :76: paint the rest
+            w[3 * j + 1] = (w[3 * j + 1] & k1) | (c32 & ~k1);
+            w[3 * j + 2] = (w[3 * j + 2] & k2) | (c32 & ~k2);
+        }
+        st_stream16(dst + g * 48, make_uint4(w[0], w[1], w[2], w[3]));
+        st_stream16(dst + g * 48 + 16, make_uint4(w[4], w[5], w[6], w[7]));
+        st_stream16(dst + g * 48 + 32, make_uint4(w[8], w[9], w[10], w[11]));
+    }
+}
+
 // ------------------------------------------------------------------------------ colour statistics
 // One block handles a contiguous pixel range of ONE image; lane-contiguous pixels straight from global memory (the
 // mask byte first: unmasked pixels cost one load), twelve 256-bin histograms in shared memory (neighbouring pixels hit
@@ -409,7 +432,16 @@ extern "C" int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* 
                 "apply_mask: bad arguments");
     if (B == 0) return LFX_OK;
     const long long npix = (long long)B * H * W;
-    k_apply_mask<<<stream_grid(npix), THREADS, 0, (cudaStream_t)stream>>>(src, mask, dst, npix, color_val);
+    long long done = 0;
+    if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(mask) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 && npix >= 16) {
+        const long long ng = npix / 16;
+        const int gv = (int)min((ng + THREADS - 1) / THREADS, (long long)LFX_NUM_SMS * 16);
+        k_apply_mask_vec<<<gv, THREADS, 0, (cudaStream_t)stream>>>(src, mask, dst, ng, color_val);
+        done = ng * 16;
+    }
+    if (done < npix)
+        k_apply_mask<<<stream_grid(npix - done), THREADS, 0, (cudaStream_t)stream>>>(src + done * 3, mask + done, dst + done * 3, npix - done,
+                                                                                     color_val);
     return lfx_check_launch("apply_mask");
 }
 
