@@ -456,3 +456,57 @@ def test_empty_batch(dev):
     assert ops.gauss_u8(x, 5, 1.5).shape == (0, 64, 64, 3)
     m, info = ops.make_mask(x, ops.mask_cfg("hsv_h"))
     assert m.shape == (0, 64, 64) and info.shape == (0, 8)
+
+
+# ----------------------------------------------------------------------------- register-only kernels: tails, unaligned buffers
+def _unaligned(arr, dev, off=1):
+    """Device tensor holding `arr` at an odd byte offset from the allocation (forces the shared-tile fallback kernels)."""
+    flat = torch.empty(arr.size + 16, dtype=torch.uint8, device=dev)
+    view = flat[off:off + arr.size].view(arr.shape)
+    view.copy_(torch.from_numpy(np.ascontiguousarray(arr)).to(dev))
+    assert view.data_ptr() % 16 != 0
+    return view
+
+
+@pytest.mark.parametrize("hw", [(7, 5), (64, 64), (33, 130)])
+def test_colour_kernels_tail_and_unaligned(dev, hw):
+    rng = np.random.default_rng(hw[0])
+    imgs = rng.integers(0, 256, (3, *hw, 3), dtype=np.uint8)
+    masks = rng.integers(0, 2, (3, *hw), dtype=np.uint8) * 255
+    masks[1] = rng.integers(0, 256, hw, dtype=np.uint8)                  # non-binary mask: > 127 rule
+    for x, m in ((up(imgs, dev), up(masks, dev)), (_unaligned(imgs, dev), _unaligned(masks, dev, 3))):
+        for code, fn in (("gray", sc.rgb_to_gray), ("hsv", sc.rgb_to_hsv), ("lab", sc.rgb_to_lab)):
+            got = ops.cvt_color(x, code).cpu().numpy()
+            assert np.array_equal(got, np.stack([fn(im) for im in imgs])), code
+        assert np.array_equal(ops.threshold_mask(x, ops.mask_cfg("hsv_h")).cpu().numpy(),
+                              np.stack([sm.mask_hsv_green(im, sm.Cfg()) for im in imgs]))
+        for color in (255, 0):
+            exp = np.stack([sm.apply_mask(im, mk, "white" if color else "black") for im, mk in zip(imgs, masks)])
+            assert np.array_equal(ops.apply_mask(x, m, color).cpu().numpy(), exp)
+
+
+def test_color_stats_large_image_counter_flush(dev):
+    """1024 x 1024: every thread sees > 128 pixels, so the packed 8-bit category counters are flushed many times."""
+    img = synth.leaf_image(4, 1024, 1024)
+    mask = sm.mask_hsv_green(img, sm.Cfg())
+    h9, h3, cn = ops.color_stats(up(img[None], dev), up(mask[None], dev))
+    masked = sm.apply_mask(img, mask, "white")
+    assert np.array_equal(h9.cpu().numpy()[0], sm.hist9(img, mask))
+    assert np.array_equal(h3.cpu().numpy()[0], sm.hsv_hist_leaf(masked))
+    assert np.array_equal(cn.cpu().numpy()[0, :14], sm.hist_counters(masked))
+
+
+@pytest.mark.parametrize("hw,roi", [((64, 64), (96, 512)), ((96, 64), (128, 64)), ((61, 97), (300, 100))])
+def test_roi_letterbox_canvas_shapes(dev, hw, roi):
+    """Canvases wider than the thread block (two column passes), taller than one row block, and the general-shape path."""
+    imgs = synth.leaf_batch(4, hw[0], hw[1], seed=31)
+    cfg = ops.mask_cfg("hsv_h", fill_size=60)
+    x = up(imgs, dev)
+    mask, info = ops.make_mask(x, cfg)
+    got = ops.roi_letterbox(x, mask, info, roi).cpu().numpy()
+    for i in range(len(imgs)):
+        m, einfo = sm.make_mask(imgs[i], sm.Cfg(mask_strategy="hsv_h", fill_size=60))
+        if einfo is None:
+            assert int(got[i].sum()) == 0
+        else:
+            assert np.array_equal(got[i], sm.roi_letterbox(sm.apply_mask(imgs[i], m, "white"), einfo["bbox"], roi)), i
