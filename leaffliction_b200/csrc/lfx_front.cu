@@ -6,6 +6,9 @@
 // One thread block per image; the grey image, every mask plane and the run tables stay in shared
 // memory, so HBM sees one read of the input and one write of the result.  Images must fit that
 // budget (H*W <= 65536, e.g. PlantVillage's 256x256); larger inputs return LFX_ERR_UNSUPPORTED.
+// One block per SM (the whole image lives in shared memory): 1024 threads so that the many short, barrier-separated
+// passes over the bit planes have twice the warps to hide their latency.
+#define LFX_MT 1024
 #include <float.h>
 
 #include "lfx_planes.cuh"

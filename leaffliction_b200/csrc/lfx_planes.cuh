@@ -9,7 +9,10 @@
 
 namespace {
 
-constexpr int MT = 512;          // threads per block
+#ifndef LFX_MT
+#define LFX_MT 512
+#endif
+constexpr int MT = LFX_MT;       // threads per block (a translation unit may choose its own: this header is TU-local)
 constexpr int NPLANES = 6;       // P0 raw, PB brown, PR result, T1..T3 temps
 constexpr int RCAP_SMEM = 2048;  // runs kept in shared memory; larger tables use global scratch
 constexpr int STAGE_BYTES = 6144;
