@@ -358,6 +358,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     extern __shared__ __align__(16) uint8_t s_rows[];
     __shared__ uint16_t s_queue[WB_QCAP];
     __shared__ int s_qn;
+    __shared__ int s_yf[WB_ROWS];      // axis-aligned maps: floor(yin - 0.5) of each band row (INT_MIN: row outside the source)
+    __shared__ float s_fdy[WB_ROWS];   // ... and its fractional part
     const int img = blockIdx.y;
     const int band = TILED ? blockIdx.x / ntx : blockIdx.x, tx = TILED ? blockIdx.x - band * ntx : 0;
     const int y0 = band * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
@@ -373,6 +375,15 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     uint8_t* dimg = dst + (size_t)img * npx * 3;
     const bool al16 = ((W * 3) % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);   // every row start is 16-byte aligned
     if (threadIdx.x == 0) s_qn = 0;
+    if (threadIdx.x < WB_ROWS) {   // row coordinates of an axis-aligned map depend on y only: once per band, not per pixel
+        const double yc = (double)(y0 + (int)threadIdx.x) + 0.5;
+        double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
+        const bool yok = !(yin < 0.0 || yin >= (double)H);
+        yin = __dadd_rn(yin, -0.5);
+        const int yf = (int)floor(yin);
+        s_yf[threadIdx.x] = yok ? yf : INT_MIN;
+        s_fdy[threadIdx.x] = (float)__dadd_rn(yin, -(double)yf);
+    }
     // number of column slices: the smallest of 1, 2, 4, 8 whose source rectangles all fit in shared memory
     int nsl = 0;
     if (!TILED) {
@@ -467,16 +478,12 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     int base = -(1 << 30);  // source row of hw[.][0]
                     uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
                     for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
-                        const double yc = (double)y + 0.5;
-                        double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
-                        const bool yok = !(yin < 0.0 || yin >= (double)H);
-                        if (!(xok && yok)) {
+                        const int yf = s_yf[y - y0];
+                        if (!xok || yf == INT_MIN) {
                             dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
                             continue;
                         }
-                        yin = __dadd_rn(yin, -0.5);
-                        const int yf = (int)floor(yin);
-                        const float fdy = (float)__dadd_rn(yin, -(double)yf);
+                        const float fdy = s_fdy[y - y0];
                         const int yb = yf - 1;
                         int shift = yb - base;
                         if (shift < 0 || shift > 4) shift = 4;
