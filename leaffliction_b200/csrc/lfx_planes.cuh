@@ -182,12 +182,25 @@ __device__ void morph(const uint32_t* in, uint32_t* out, const Footprint& fp, co
                 next = row[w + 1];
                 if (!DIL && w + 1 == c.WPR - 1) next |= ~c.lastmask;
             }
-            const int o1 = fp.r[k].o1, o2 = fp.r[k].o2;
-            for (int o = o1; o <= o2; ++o) {
-                // bit x of v = source bit (x + o)
-                const uint32_t v = (o < 0) ? __funnelshift_r(prev, cur, 32 + o) : __funnelshift_r(cur, next, o);
-                acc = DIL ? (acc | v) : (acc & v);
+            // OR / AND of source bits x+o1 .. x+o2 by doubling: T = the bit string re-based at offset o1 (64 bits are enough:
+            // the span is at most 32 wide), then T op (T >> 1) op ... in log2(span) steps instead of one funnel shift per offset
+            const int o1 = fp.r[k].o1, o2 = fp.r[k].o2, L = o2 - o1 + 1;
+            uint32_t tlo, thi;
+            if (o1 < 0) {
+                tlo = __funnelshift_r(prev, cur, 32 + o1);
+                thi = __funnelshift_r(cur, next, 32 + o1);
+            } else {
+                tlo = __funnelshift_r(cur, next, o1);
+                thi = next >> o1;
             }
+            unsigned long long r = ((unsigned long long)thi << 32) | tlo;
+            int cov = 1;
+            while (2 * cov <= L) {
+                r = DIL ? (r | (r >> cov)) : (r & (r >> cov));
+                cov *= 2;
+            }
+            if (cov < L) r = DIL ? (r | (r >> (L - cov))) : (r & (r >> (L - cov)));
+            acc = DIL ? (acc | (uint32_t)r) : (acc & (uint32_t)r);
         }
         out[i] = acc & valid_mask(c, w);
     }
