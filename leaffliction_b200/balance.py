@@ -14,6 +14,7 @@ Plan arithmetic, task order, RNG consumption, file naming and error conventions 
 from __future__ import annotations
 
 import logging
+import os
 import random
 import shutil
 from collections import defaultdict
@@ -169,7 +170,8 @@ class DatasetBalancer:
         self.source_dir = Path(source_dir)
         self.target_dir = Path(target_dir)
         self.transformer = augment.ImageAugmenter(seed=seed)   # seeds the GLOBAL RNGs like the reference (:31)
-        self.workers = max(1, int(workers)) if workers else 1
+        # JPEG decode / encode threads (Pillow releases the GIL there); the reference's default is one process per core
+        self.workers = max(1, int(workers)) if workers else max(1, min(8, os.cpu_count() or 1))
         self.rank, self.world, self.batch = int(rank), int(world), int(batch)
         self.counts: Dict[str, Dict[str, int]] = {}
         self.plan: Dict[str, Dict[str, int]] = {}
@@ -224,31 +226,39 @@ class DatasetBalancer:
         tasks = build_tasks(self.plan, self._get_images_by_class())
         mine = [tasks[i] for i in shard(len(tasks), self.rank, self.world)]
         logger.info(f"Starting GPU augmentation: {len(tasks)} images to generate, {len(mine)} on rank {self.rank}")
-        for b0 in range(0, len(mine), self.batch):
-            chunk = mine[b0:b0 + self.batch]
-            imgs, ok = [], []
-            for t in chunk:
-                try:
-                    imgs.append(augment._load_rgb(t.source_img))
-                    ok.append(True)
-                except Exception as e:      # reference convention: log, count as failed, never raise
-                    logger.error(f"Failed to process {t.source_img} - {e}")
-                    ok.append(False)
-            good = [t for t, k in zip(chunk, ok) if k]
+        from concurrent.futures import ThreadPoolExecutor
+
+        def try_load(t):
             try:
-                outs = augment.augment_arrays(imgs, [t.transform_name for t in good], [t.seed for t in good])
+                return augment._load_rgb(t.source_img)
+            except Exception as e:      # reference convention: log, count as failed, never raise
+                logger.error(f"Failed to process {t.source_img} - {e}")
+                return None
+
+        def try_save(pair):
+            t, o = pair
+            try:
+                augment._save_rgb(o, t.output_path)
+                return True
             except Exception as e:
-                logger.error(f"Batch failed - {e}")
-                self.failed += len(chunk)
-                continue
-            for t, o in zip(good, outs):
+                logger.error(f"Failed: {t.output_path} - {e}")
+                return False
+
+        with ThreadPoolExecutor(max_workers=self.workers) as io:
+            for b0 in range(0, len(mine), self.batch):
+                chunk = mine[b0:b0 + self.batch]
+                loaded = list(io.map(try_load, chunk))
+                good = [t for t, a in zip(chunk, loaded) if a is not None]
+                imgs = [a for a in loaded if a is not None]
                 try:
-                    augment._save_rgb(o, t.output_path)
-                    self.completed += 1
+                    outs = augment.augment_arrays(imgs, [t.transform_name for t in good], [t.seed for t in good])
                 except Exception as e:
-                    logger.error(f"Failed: {t.output_path} - {e}")
-                    self.failed += 1
-            self.failed += len(chunk) - len(good)
+                    logger.error(f"Batch failed - {e}")
+                    self.failed += len(chunk)
+                    continue
+                ok = list(io.map(try_save, zip(good, outs)))
+                self.completed += sum(ok)
+                self.failed += len(chunk) - sum(ok)
         done, _ = allreduce_histograms(np.array([self.completed, self.failed], np.int64))
         logger.info(f"Augmentation complete: {int(done[0])} images generated, {int(done[1])} failed")
         self._barrier()

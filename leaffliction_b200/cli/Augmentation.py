@@ -42,7 +42,7 @@ def build_parser() -> argparse.ArgumentParser:
     parser.add_argument("-out", "--output", help="Output directory (default: artifacts/augmented_directory for datasets, "
                                                    "artifacts/example for single images)")
     parser.add_argument("-seed", "--seed", type=int, default=DEFAULT_SEED, help="Random seed for reproducible results")
-    parser.add_argument("--workers", type=int, default=None, help="Number of parallel workers (accepted; GPU batches ignore it)")
+    parser.add_argument("--workers", type=int, default=None, help="JPEG I/O threads (default min(8, cores)); the GPU batches themselves ignore it")
     return parser
 
 

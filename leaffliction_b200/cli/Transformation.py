@@ -41,7 +41,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("-dst", "--dst", default=None, help="Destination directory (folder mode)")
     p.add_argument("--types", default=",".join(T.DEFAULT_TYPES), help="Comma-separated transforms to run")
     p.add_argument("--config", default=DEFAULT_CONFIG, help="YAML config path (optional)")
-    p.add_argument("--workers", type=int, default=0, help="Number of processes (0=auto); accepted, GPU batches ignore it")
+    p.add_argument("--workers", type=int, default=0, help="JPEG I/O threads (0=auto); the GPU batches themselves ignore it")
     p.add_argument("--skip-existing", action="store_true", help="Skip images whose outputs already exist")
     p.add_argument("--overwrite", action="store_true", help="Overwrite existing outputs")
     p.add_argument("--preview", action="store_true", help="Force saving outputs (no GUI popups)")
@@ -102,8 +102,19 @@ def process_single_image(params: ProcessArgs, premade=None) -> List[Path]:
     return saved
 
 
-def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: bool, overwrite: bool, batch: int = 256):
-    """Folder mode (:664-699): images grouped by shape, make_mask batched per group on the GPU."""
+def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: bool, overwrite: bool, batch: int = 256,
+               workers: int = 0):
+    """Folder mode (:664-699): images grouped by shape, make_mask batched per group on the GPU; `workers` threads
+    decode the JPEGs (0 = auto = min(8, cpu // 2), the reference's rule :672-674)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    nthreads = workers if workers and workers > 0 else max(1, min(8, (os.cpu_count() or 2) // 2))
+
+    def try_read(ip):
+        try:
+            return T.pil_read_rgb(ip)
+        except Exception:
+            return None
     imgs = list(T.iter_images_in_dir(src))
     if not imgs:
         logging.warning("No images found in %s", src)
@@ -112,12 +123,8 @@ def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: b
     total = 0
     for b0 in range(0, len(imgs), batch):
         chunk = imgs[b0:b0 + batch]
-        arrays = []
-        for ip in chunk:
-            try:
-                arrays.append(T.pil_read_rgb(ip))
-            except Exception:
-                arrays.append(None)
+        with ThreadPoolExecutor(max_workers=nthreads) as io:
+            arrays = list(io.map(try_read, chunk))
         premade = [None] * len(chunk)
         by_shape = {}
         for i, a in enumerate(arrays):
@@ -161,7 +168,7 @@ def main(argv=None) -> None:
             logging.error("Source directory does not exist: %s", src)
             return
         dst.mkdir(parents=True, exist_ok=True)
-        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite)
+        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite, workers=args.workers)
         return
     logging.error("Must specify either single image or --src/--dst for folder mode")
 
