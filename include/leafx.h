@@ -117,6 +117,18 @@ int lfx_draw_augment_params(const int32_t* transform, const uint32_t* seed, int 
 
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
+/* cv2.resize as the mask path uses it: INTER_CUBIC upscale of the working image (_prepare_working_image, mask.py:29-50)
+ * and INTER_NEAREST of the mask back to the original size (_resize_results_to_original, :526-545).
+ * lfx_cubic_table (host): first[out_size] = first source index of every destination index (tap k reads
+ * clip(first + k)), weights[out_size][4] = a = -0.75 cubic weights x2048 (OpenCV's 8-bit fixed-point path).
+ * lfx_resize_cubic: src [B,H,W,3] -> dst [B,OH,OW,3]; tables on the device (weights 16-byte aligned).  +-1 LSB
+ * against cv2 (OpenCV's SIMD and scalar paths already differ by that much); lfx_resize_nearest is exact. */
+int lfx_cubic_table(int in_size, int out_size, int32_t* first, int32_t* weights);
+int lfx_resize_cubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, int OH, int OW, const int32_t* xfirst,
+                     const int32_t* xweights, const int32_t* yfirst, const int32_t* yweights, lfx_stream_t stream);
+int lfx_resize_nearest(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, int OH, int OW,
+                       lfx_stream_t stream);
+
 /* cv2.cvtColor(rgb, COLOR_RGB2{GRAY,HSV,LAB}) (mask.py:87,103; blur.py:27; hist.py:184).
  * code: 0 = GRAY (dst [B,H,W]), 1 = HSV, 2 = LAB (dst [B,H,W,3]). */
 int lfx_cvt_color(const uint8_t* src, uint8_t* dst, int B, int H, int W, int code,

@@ -418,3 +418,43 @@ def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc:
     for i in np.nonzero(seeds == 0)[0]:
         out[int(i)] = torch.from_numpy(np.random.normal(loc, scale, int(n)).astype(np.uint8)).to(device)
     return out
+
+
+# ----------------------------------------------------------------------------- cv2.resize of the mask path
+_cubic_tabs = {}
+
+
+def _cubic_table(in_size: int, out_size: int, device):
+    key = (int(in_size), int(out_size), str(device))
+    if key not in _cubic_tabs:
+        first = np.zeros(out_size, np.int32)
+        w = np.zeros((out_size, 4), np.int32)
+        _lib.check(_lib.load().lfx_cubic_table(int(in_size), int(out_size), first.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)))
+        _cubic_tabs[key] = (_dev(first, np.int32, device), _dev(w, np.int32, device))
+    return _cubic_tabs[key]
+
+
+def resize_cubic(x: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """cv2.resize(img, (OW, OH), interpolation=cv2.INTER_CUBIC) per image (8-bit fixed-point path, +-1 LSB class)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    xf, xw = _cubic_table(W, OW, x.device)
+    yf, yw = _cubic_table(H, OH, x.device)
+    out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.lfx_resize_cubic(_p(x), _p(out), B, H, W, OH, OW, _p(xf), _p(xw), _p(yf), _p(yw), _stream()))
+    return out
+
+
+def resize_nearest(x: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
+    """cv2.resize(img, (OW, OH), interpolation=cv2.INTER_NEAREST) per image; x uint8 [B,H,W] or [B,H,W,C]."""
+    if x.dtype != torch.uint8 or x.dim() not in (3, 4) or not x.is_contiguous():
+        raise ValueError("resize_nearest: contiguous uint8 [B,H,W] or [B,H,W,C] expected")
+    lib = _ready(x)
+    B, H, W = x.shape[:3]
+    Cn = 1 if x.dim() == 3 else int(x.shape[3])
+    OH, OW = int(out_hw[0]), int(out_hw[1])
+    out = torch.empty((B, OH, OW) if x.dim() == 3 else (B, OH, OW, Cn), dtype=torch.uint8, device=x.device)
+    _lib.check(lib.lfx_resize_nearest(_p(x), _p(out), B, H, W, Cn, OH, OW, _stream()))
+    return out

@@ -217,8 +217,10 @@ def _profile_checks(cfg: TransformConfig):
     if cfg.grabcut_refine:
         _warn_once("grabcut", "grabcut_refine=true is not reproducible in the reference itself (global OpenCV RNG); "
                               "running parity profile P0 without it")
-    if (cfg.mask_upscale_factor and cfg.mask_upscale_factor > 1.0) or (cfg.mask_upscale_long_side and cfg.mask_upscale_long_side > 0):
-        _warn_once("upscale", "mask upscaling (INTER_CUBIC) is ISA-dependent in OpenCV; running parity profile P0 at native size")
+    if ((cfg.mask_upscale_factor and cfg.mask_upscale_factor > 1.0) or (cfg.mask_upscale_long_side and cfg.mask_upscale_long_side > 0)) \
+            and not upscale_enabled():
+        _warn_once("upscale", "mask upscaling (INTER_CUBIC) is ISA-dependent in OpenCV itself; running parity profile P0 at native "
+                              "size (LEAFX_MASK_UPSCALE=1 or transform.set_upscale(True) enables the +-1 LSB upscale path)")
     if cfg.shadow_suppression:
         _warn_once("shadow", "shadow_suppression uses k-means on OpenCV's global RNG (tier C); ignored")
     if cfg.mask_strategy not in GPU_STRATEGIES:
@@ -231,11 +233,25 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
     _profile_checks(cfg)
     ops = _ops()
     x = _dev(rgb_batch)
+    H, W = rgb_batch.shape[1:3]
+    scale = working_scale(H, W, cfg)
+    x0 = x
+    if abs(scale - 1.0) >= 1e-6:          # _prepare_working_image (mask.py:29-50): INTER_CUBIC upscale before masking
+        x = ops.resize_cubic(x, (int(round(H * scale)), int(round(W * scale))))
     raw = None
     if cfg.mask_strategy in ("inclusive", "enhanced"):
-        raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
+        try:
+            raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
+        except Exception as e:
+            from ._lib import ERR_UNSUPPORTED
+            if getattr(e, "code", None) != ERR_UNSUPPORTED or x is x0:
+                raise
+            # the front ends keep the whole image in shared memory (H*W <= ~65536): mask at native size instead
+            _warn_once("upscale-front", f"{cfg.mask_strategy} front end cannot take the upscaled {tuple(x.shape[1:3])} working "
+                                        "image; masking at native size")
+            x, scale = x0, 1.0
+            raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
     mask, info = ops.make_mask(x, mask_cfg_from(cfg), raw)
-    H, W = rgb_batch.shape[1:3]
     max_pts = 4096
     while True:
         pts, cnt, _ = ops.trace_contour(mask, info, max_pts)
@@ -245,7 +261,44 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
         max_pts = int(-cnt_h.min()) + 16
     pts_h = pts.cpu().numpy()
     contours = [pts_h[i, : cnt_h[i]].reshape(-1, 1, 2).copy() if cnt_h[i] > 0 else None for i in range(len(cnt_h))]
-    return mask.cpu().numpy(), info.cpu().numpy(), contours
+    info_h = info.cpu().numpy()
+    if abs(scale - 1.0) >= 1e-6:          # _resize_results_to_original (mask.py:526-545)
+        mask = ops.resize_nearest(mask, (H, W))
+        contours = [None if c is None else (c.astype(np.float32) / np.float32(scale)).astype(np.int32) for c in contours]
+        for i, c in enumerate(contours):
+            if c is not None:
+                info_h[i, 1:5] = bounding_rect(c)
+    return mask.cpu().numpy(), info_h, contours
+
+
+_UPSCALE = None
+
+
+def set_upscale(on: Optional[bool]) -> None:
+    """Honour mask_upscale_factor / mask_upscale_long_side (True), ignore them = parity profile P0 (False), or follow the
+    environment variable LEAFX_MASK_UPSCALE (None, the default)."""
+    global _UPSCALE
+    _UPSCALE = on
+
+
+def upscale_enabled() -> bool:
+    import os
+    return bool(_UPSCALE) if _UPSCALE is not None else os.environ.get("LEAFX_MASK_UPSCALE", "0") not in ("", "0", "false", "False")
+
+
+def working_scale(h: int, w: int, cfg: TransformConfig) -> float:
+    """Scale of the working image of make_mask (_prepare_working_image, mask.py:33-39); 1.0 unless the upscale path is
+    enabled (its cubic resize is only +-1 LSB from cv2's, so it is outside the bit-exact profile P0)."""
+    s = 1.0
+    if not upscale_enabled():
+        return s
+    if cfg.mask_upscale_factor and cfg.mask_upscale_factor > 1.0:
+        s = float(cfg.mask_upscale_factor)
+    elif cfg.mask_upscale_long_side and cfg.mask_upscale_long_side > 0:
+        ls = max(h, w)
+        if ls < cfg.mask_upscale_long_side:
+            s = float(cfg.mask_upscale_long_side) / float(ls)
+    return s
 
 
 def make_mask(rgb: np.ndarray, cfg: TransformConfig) -> Tuple[Optional[np.ndarray], Optional[np.ndarray]]:

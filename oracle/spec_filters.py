@@ -306,3 +306,56 @@ def normalize_minmax_f32(a: np.ndarray, lo: float, hi: float) -> np.ndarray:
     scale = (dmax - dmin) * (1.0 / (smax - smin) if smax - smin > 2.220446049250313e-16 else 0.0)
     shift = dmin - smin * scale
     return (a.astype(np.float64) * scale + shift).astype(np.float32)
+
+
+# ---------------------------------------------------------------- cv2.resize INTER_CUBIC / INTER_NEAREST (8-bit)
+# _prepare_working_image (mask.py:29-50) upscales the image with INTER_CUBIC before masking and
+# _resize_results_to_original (:526-545) brings the mask back with INTER_NEAREST.  OpenCV resize.cpp, 8-bit path:
+# a = -0.75 cubic weights in float32, quantised to 11 bits (cvRound), int32 horizontal pass, vertical pass
+# (sum + 2^21) >> 22 with saturation; taps outside the image replicate the border.  OpenCV's own SIMD and scalar code
+# paths differ from each other by 1 LSB on a few per-mille of the values, so this spec is the +-1 LSB
+# class, not bit-exact; INTER_NEAREST (sx = min(floor(dx * sw / dw), sw - 1)) is exact.
+def cubic_taps(in_size: int, out_size: int):
+    """-> (first source index [out] (tap k reads clip(s + k)), int32 weights [out, 4] x2048)."""
+    scale = np.float64(in_size) / np.float64(out_size)
+    d = np.arange(out_size, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    x = (f - s.astype(np.float32)).astype(np.float32)
+    A = np.float32(-0.75)
+    one = np.float32(1.0)
+    c0 = ((A * (x + one) - np.float32(5) * A) * (x + one) + np.float32(8) * A) * (x + one) - np.float32(4) * A
+    c1 = ((A + np.float32(2)) * x - (A + np.float32(3))) * x * x + one
+    xm = one - x
+    c2 = ((A + np.float32(2)) * xm - (A + np.float32(3))) * xm * xm + one
+    c3 = one - c0 - c1 - c2
+    c = np.stack([c0, c1, c2, c3], axis=1).astype(np.float32)
+    w = np.rint(c * np.float32(2048)).astype(np.int32)          # saturate_cast<short>(float): round half to even
+    return s - 1, w
+
+
+def resize_cubic_u8(img: np.ndarray, out_wh) -> np.ndarray:
+    """cv2.resize(img, (ow, oh), interpolation=cv2.INTER_CUBIC) for uint8 HxW[xC]."""
+    ow, oh = int(out_wh[0]), int(out_wh[1])
+    a = img if img.ndim == 3 else img[..., None]
+    H, W = a.shape[:2]
+    xs, xw = cubic_taps(W, ow)
+    ys, yw = cubic_taps(H, oh)
+    src = a.astype(np.int64)
+    hp = np.zeros((H, ow, a.shape[2]), np.int64)
+    for k in range(4):
+        hp += src[:, np.clip(xs + k, 0, W - 1), :] * xw[None, :, k, None]
+    out = np.zeros((oh, ow, a.shape[2]), np.int64)
+    for k in range(4):
+        out += hp[np.clip(ys + k, 0, H - 1)] * yw[:, k, None, None]
+    out = np.clip((out + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return out if img.ndim == 3 else out[..., 0]
+
+
+def resize_nearest_u8(img: np.ndarray, out_wh) -> np.ndarray:
+    """cv2.resize(img, (ow, oh), interpolation=cv2.INTER_NEAREST)."""
+    ow, oh = int(out_wh[0]), int(out_wh[1])
+    H, W = img.shape[:2]
+    sx = np.minimum(np.floor(np.arange(ow) * (np.float64(W) / ow)).astype(np.int64), W - 1)
+    sy = np.minimum(np.floor(np.arange(oh) * (np.float64(H) / oh)).astype(np.int64), H - 1)
+    return img[sy][:, sx]

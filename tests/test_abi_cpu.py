@@ -74,3 +74,20 @@ def test_host_lanczos_tables_match_oracle():
         assert eks == ks
         assert np.array_equal(bounds, eb)
         assert np.array_equal(kk, ek)
+
+
+def test_cubic_table_matches_oracle_taps():
+    """lfx_cubic_table (host side, no GPU) == the oracle's float32 restatement of OpenCV's cubic weights."""
+    import ctypes as C
+
+    import numpy as np
+
+    from leaffliction_b200 import _lib
+    from oracle import spec_filters as sf
+    lib = _lib.load()
+    for a, b in ((256, 333), (97, 126), (64, 1500), (333, 256), (40, 40)):
+        f = np.zeros(b, np.int32)
+        w = np.zeros((b, 4), np.int32)
+        assert lib.lfx_cubic_table(a, b, f.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)) == 0
+        s, ww = sf.cubic_taps(a, b)
+        assert np.array_equal(f, s) and np.array_equal(w, ww), (a, b)

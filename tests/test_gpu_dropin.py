@@ -178,3 +178,58 @@ def test_analyze_record_hull_and_pca():
             proj = data @ evec[k]
             got = {float(np.dot(np.array(p, np.float32), evec[k])) for p in rec["axes"][k]}
             assert abs(min(got) - float(proj.min())) < 1e-2 and abs(max(got) - float(proj.max())) < 1e-2
+
+
+def test_resize_cubic_and_nearest_kernels():
+    """lfx_resize_cubic == the oracle's restatement of OpenCV's 8-bit cubic path (bit-exact) and within 1 LSB of cv2 itself;
+    lfx_resize_nearest == cv2 exactly (mask.py:29-50, 526-545)."""
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    from leaffliction_b200 import ops
+    from oracle import spec_filters as sf
+    d = torch.device("cuda:0")
+    rng = np.random.default_rng(8)
+    for (h, w), (oh, ow) in (((256, 256), (333, 333)), ((61, 97), (79, 126)), ((64, 64), (200, 150)), ((40, 32), (40, 32))):
+        imgs = np.stack([synth.leaf_image(i, h, w) for i in range(2)] + [rng.integers(0, 256, (h, w, 3), dtype=np.uint8)])
+        got = ops.resize_cubic(torch.from_numpy(imgs).to(d), (oh, ow)).cpu().numpy()
+        for i in range(len(imgs)):
+            assert np.array_equal(got[i], sf.resize_cubic_u8(imgs[i], (ow, oh))), (h, w, i)
+            ref = cv2.resize(imgs[i], (ow, oh), interpolation=cv2.INTER_CUBIC).astype(int)
+            assert np.abs(got[i].astype(int) - ref).max() <= 1                      # the +-1 LSB class of SURVEY A.12
+        m = (rng.integers(0, 2, (3, oh, ow), dtype=np.uint8) * 255)
+        back = ops.resize_nearest(torch.from_numpy(m).to(d), (h, w)).cpu().numpy()
+        for i in range(3):
+            assert np.array_equal(back[i], cv2.resize(m[i], (w, h), interpolation=cv2.INTER_NEAREST))
+        rgb_back = ops.resize_nearest(torch.from_numpy(got).to(d), (h, w)).cpu().numpy()
+        assert np.array_equal(rgb_back[0], cv2.resize(got[0], (w, h), interpolation=cv2.INTER_NEAREST))
+
+
+def test_make_mask_with_cubic_upscale_close_to_reference_calls():
+    """mask_upscale_factor 1.3 (the reference YAML's value): upscale -> mask -> nearest back.  The working image is only
+    +-1 LSB from cv2's, so the mask is compared by IoU with the same steps done by OpenCV + the oracle."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import spec_mask as sm
+    cfg = transform.default_config(mask_strategy="hsv_h", grabcut_refine=False, mask_upscale_factor=1.3, mask_upscale_long_side=1500)
+    native, _ = transform.make_mask(synth.leaf_image(0), cfg)              # default: profile P0, the keys are ignored
+    assert np.array_equal(native, sm.make_mask(synth.leaf_image(0), sm.Cfg(mask_strategy="hsv_h"))[0])
+    transform.set_upscale(True)
+    try:
+        _check_upscaled_masks(cv2, cfg)
+    finally:
+        transform.set_upscale(None)
+
+
+def _check_upscaled_masks(cv2, cfg):
+    for i in range(3):
+        im = synth.leaf_image(i)
+        mask, cnt = transform.make_mask(im, cfg)
+        assert mask.shape == im.shape[:2] and cnt is not None
+        work = cv2.resize(im, (333, 333), interpolation=cv2.INTER_CUBIC)
+        m_work, _ = sm.make_mask(work, sm.Cfg(mask_strategy="hsv_h"))
+        exp = cv2.resize(m_work, (256, 256), interpolation=cv2.INTER_NEAREST)
+        inter = np.logical_and(mask > 0, exp > 0).sum()
+        union = np.logical_or(mask > 0, exp > 0).sum()
+        assert inter / union > 0.995, (i, inter / union)
+        x, y, w, h = transform.bounding_rect(cnt)
+        ys, xs = np.nonzero(mask)
+        assert abs(x - xs.min()) <= 2 and abs(y - ys.min()) <= 2 and abs(x + w - 1 - xs.max()) <= 2 and abs(y + h - 1 - ys.max()) <= 2

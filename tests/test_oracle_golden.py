@@ -173,3 +173,17 @@ def test_golden_is_reproducible_from_reference():
     cfg = ref_harness.ref_config(ns, mask_strategy="inclusive")
     m, _ = ns.mask.make_mask(IMGS["leaf64_1"], cfg)
     assert np.array_equal(m, G["mask/inclusive/leaf64_1"])
+
+
+def test_resize_specs_against_opencv():
+    """spec_filters.resize_cubic_u8 is within 1 LSB of cv2.resize(INTER_CUBIC) (OpenCV's own code paths differ by that much,
+    SURVEY A.12); resize_nearest_u8 is exact."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import spec_filters as sf
+    rng = np.random.default_rng(4)
+    for (h, w), (oh, ow) in (((96, 131), (125, 170)), ((64, 64), (83, 83)), ((50, 70), (100, 140))):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, (ow, oh), interpolation=cv2.INTER_CUBIC).astype(int)
+        assert np.abs(sf.resize_cubic_u8(img, (ow, oh)).astype(int) - ref).max() <= 1
+        m = rng.integers(0, 2, (oh, ow), dtype=np.uint8) * 255
+        assert np.array_equal(sf.resize_nearest_u8(m, (w, h)), cv2.resize(m, (w, h), interpolation=cv2.INTER_NEAREST))
