@@ -96,7 +96,7 @@ def test_color_stats(dev, hw):
 
 
 # ----------------------------------------------------------------------------- Gaussian
-@pytest.mark.parametrize("hw", SHAPES + [(300, 500)])
+@pytest.mark.parametrize("hw", SHAPES + [(300, 500), (48, 640), (40, 1024), (33, 512)])     # the last three: column-tiled TMA kernel
 @pytest.mark.parametrize("ks", [(5, 1.5), (15, 0.0), (3, 0.0), (7, 2.0)])
 def test_gauss(dev, hw, ks):
     rng = np.random.default_rng(6)
