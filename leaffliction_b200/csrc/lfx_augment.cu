@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
                                                                 float* __restrict__ dstf, int H, int W,
                                                                 const int32_t* __restrict__ box, int OH, int OW,
                                                                 const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
-                                                                int kstride, const int32_t* __restrict__ toff, int mrows_cap) {
+                                                                int kstride, const int32_t* __restrict__ toff, int mrows_cap, int lz_to) {
     extern __shared__ __align__(16) uint8_t sm_lz[];
     __shared__ float s_f255[256];   // v / 255.0f (normalize_array, image_utils.py:126-130): correctly rounded division, tabulated
     if (dstf)
@@ -668,13 +668,13 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
     const int OWB = OW * 3;
     uint8_t* s_mid = sm_lz;                                                               // [mrows_cap][OWB]
     int32_t* s_yk = reinterpret_cast<int32_t*>(sm_lz + (((size_t)mrows_cap * OWB + 15) & ~(size_t)15));  // [LZ_TO][kstride]
-    int32_t* s_yb = s_yk + LZ_TO * kstride;                                               // [LZ_TO][2]
-    int32_t* s_mis = s_yb + LZ_TO * 2;                                                    // [mrows_cap]
+    int32_t* s_yb = s_yk + lz_to * kstride;                                               // [lz_to][2]
+    int32_t* s_mis = s_yb + lz_to * 2;                                                    // [mrows_cap]
     const int src_pitch = ((W * 3 + 15) & ~15) + 32;                                      // staged crop row pitch
     uint8_t* s_src = reinterpret_cast<uint8_t*>(s_mis + ((mrows_cap + 3) & ~3));          // [mrows_cap][src_pitch]
     const int img = blockIdx.y;
-    const int o0 = blockIdx.x * LZ_TO;
-    const int nrow = min(LZ_TO, OH - o0);
+    const int o0 = blockIdx.x * lz_to;   // lz_to output rows per block (LZ_TO, halved for wide images until the strip fits)
+    const int nrow = min(lz_to, OH - o0);
     const int left = box[img * 4], top = box[img * 4 + 1], cw = box[img * 4 + 2], ch = box[img * 4 + 3];
     const int32_t* xb = tb + (size_t)toff[img * 4 + 0] * 2;
     const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
@@ -1035,9 +1035,14 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
                 LFX_ERR_ARG, "crop_lanczos: bad arguments");
     // strip kernel: full-width row strips, taps in registers (every upscale and mild downscale: <= 8 taps per axis)
     {
-        const int mrows_cap = (int)(((long long)LZ_TO * H + OH - 1) / OH) + kstride + 2;   // crop_h <= H
-        const size_t smem2 = (((size_t)mrows_cap * OW * 3 + 15) & ~(size_t)15) + (size_t)LZ_TO * kstride * 4 + LZ_TO * 8 +
-                             (size_t)((mrows_cap + 3) & ~3) * 4 + (size_t)mrows_cap * (((W * 3 + 15) & ~15) + 32);
+        int lz_to = LZ_TO, mrows_cap = 0;
+        size_t smem2 = 0;
+        for (;; lz_to /= 2) {
+            mrows_cap = (int)(((long long)lz_to * H + OH - 1) / OH) + kstride + 2;   // crop_h <= H
+            smem2 = (((size_t)mrows_cap * OW * 3 + 15) & ~(size_t)15) + (size_t)lz_to * kstride * 4 + lz_to * 8 +
+                    (size_t)((mrows_cap + 3) & ~3) * 4 + (size_t)mrows_cap * (((W * 3 + 15) & ~15) + 32);
+            if (smem2 <= 200 * 1024 || lz_to <= 8) break;
+        }
         const bool ok = (OW % 4 == 0) && kstride <= 16 && smem2 <= 200 * 1024 &&
                         ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) && (!dst_f32 || (reinterpret_cast<uintptr_t>(dst_f32) & 15) == 0);
         if (ok) {
@@ -1051,10 +1056,10 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
                 cudaFuncSetAttribute(fns[vi], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
                 attr2[vi] = smem2;
             }
-            dim3 grid2(lfx_div_up(OH, LZ_TO), B);
+            dim3 grid2(lfx_div_up(OH, lz_to), B);
 #define LFX_LZ_LAUNCH(K) \
     k_crop_lanczos_strip<K><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk, kstride, \
-                                                                         tab_off, mrows_cap)
+                                                                         tab_off, mrows_cap, lz_to)
             if (vi == 0) LFX_LZ_LAUNCH(8);
             else if (vi == 1) LFX_LZ_LAUNCH(10);
             else if (vi == 2) LFX_LZ_LAUNCH(12);
