@@ -359,31 +359,52 @@ def augment_device(x, tasks, device_noise: bool = True):
     def ids_of(*names):
         return np.nonzero(np.isin(ta.transform, [TRANSFORM_CODE[n] for n in names]))[0]
 
+    up = ops.PackedUpload(dev)
     # the noise streams need only the seeds: launched first, they run on the GPU while the host draws the parameters
     dist_ids = ids_of("distortion")
     noise = None
     if len(dist_ids) and device_noise:
-        noise = ops.legacy_normal_noise(ta.seed[dist_ids], h * w * 3, NOISE_LEVEL, dev).view(len(dist_ids), h, w, 3)
+        sd = ta.seed[dist_ids]
+        dseeds = up.upload({"seeds": (sd & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})["seeds"]
+        noise = ops.legacy_normal_noise(sd, h * w * 3, NOISE_LEVEL, dev, dseeds=dseeds).view(len(dist_ids), h, w, 3)
     ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
-    src = torch.from_numpy(ta.source_index).to(dev)
+    # every per-task parameter array of every op goes to the device in ONE pinned, non-blocking transfer; the kernel
+    # launches that follow never wait for the stream to drain
+    groups = {"flip": ids_of("flip"), "rotate": ids_of("rotate"), "warp": ids_of("skew", "shear"), "crop": ids_of("crop"),
+              "distortion": dist_ids}
+    host = {f"src_{k}": ta.source_index[ids].astype(np.int64) for k, ids in groups.items() if len(ids)}
+    plan = None
+    if len(groups["flip"]):
+        host["flip_mode"] = ip[groups["flip"], 0]
+    if len(groups["rotate"]):
+        host["rot"] = ip[groups["rotate"]]
+    if len(groups["warp"]):
+        host["warp_coef"], host["warp_persp"] = dp[groups["warp"]], ip[groups["warp"], 0]
+    if len(groups["crop"]):
+        plan = ops.CropPlan(ip[groups["crop"], :4], (h, w), dev, upload=False)
+        host["crop_box"], host["crop_off"] = plan.h_box, plan.h_off
+    if len(groups["distortion"]):
+        host["cuts"] = ip[groups["distortion"], 0]
+    d = up.upload(host) if host else {}
     out = {}
 
-    def gather(ids):
-        return x.index_select(0, src[torch.from_numpy(ids).to(dev)])
+    def gather(k):
+        return x.index_select(0, d[f"src_{k}"])
 
-    ids = ids_of("flip")
+    ids = groups["flip"]
     if len(ids):
-        out["flip"] = (ids, ops.flip(gather(ids), ip[ids, 0]))
-    ids = ids_of("rotate")
+        out["flip"] = (ids, ops.flip(gather("flip"), d["flip_mode"]))
+    ids = groups["rotate"]
     if len(ids):
-        slab, stride = ops.rotate_nn(gather(ids), ip[ids], 255)
+        slab, stride = ops.rotate_nn(gather("rotate"), ip[ids], 255, dparams=d["rot"])
         out["rotate"] = (ids, slab, ip[ids][:, [7, 6]])
-    ids = ids_of("skew", "shear")
+    ids = groups["warp"]
     if len(ids):
-        out["warp"] = (ids, ops.warp_bicubic(gather(ids), dp[ids], ip[ids, 0]))
-    ids = ids_of("crop")
+        out["warp"] = (ids, ops.warp_bicubic(gather("warp"), d["warp_coef"], d["warp_persp"]))
+    ids = groups["crop"]
     if len(ids):
-        out["crop"] = (ids, ops.crop_lanczos(gather(ids), ip[ids, :4], (h, w)))
+        plan.box, plan.off = d["crop_box"], d["crop_off"]
+        out["crop"] = (ids, ops.crop_lanczos(gather("crop"), plan))
     ids = dist_ids
     if len(ids):
         if noise is None:
@@ -393,5 +414,5 @@ def augment_device(x, tasks, device_noise: bool = True):
                     np.random.seed(int(sd))
                 noises.append(np.random.normal(0, NOISE_LEVEL, (h, w, 3)).astype(np.uint8))
             noise = torch.from_numpy(np.stack(noises)).to(dev)
-        out["distortion"] = (ids, ops.distort(gather(ids), noise, ip[ids, 0]))
+        out["distortion"] = (ids, ops.distort(gather("distortion"), noise, d["cuts"]))
     return out

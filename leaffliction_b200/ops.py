@@ -273,7 +273,9 @@ def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
-    if isinstance(left_right, np.ndarray) and left_right.dtype == np.int32:
+    if isinstance(left_right, torch.Tensor):
+        mode = left_right                                            # lfx_flip modes already on the device
+    elif isinstance(left_right, np.ndarray) and left_right.dtype == np.int32:
         mode = _dev(left_right, np.int32, x.device)                 # already lfx_flip modes (0 = left-right)
     else:
         mode = _dev([0 if lr else 1 for lr in left_right], np.int32, x.device)
@@ -361,7 +363,8 @@ _lanczos = LanczosTables()
 class CropPlan:
     """Device-side parameters of one crop_lanczos batch (boxes, table offsets), built once and reusable."""
 
-    def __init__(self, boxes: np.ndarray, out_hw: Tuple[int, int], device):
+    def __init__(self, boxes: np.ndarray, out_hw: Tuple[int, int], device, upload: bool = True):
+        """`upload=False` leaves `.box` / `.off` unset: the caller uploads `.h_box` / `.h_off` itself (packed transfers)."""
         OH, OW = int(out_hw[0]), int(out_hw[1])
         boxes = np.ascontiguousarray(boxes, np.int32).reshape(-1, 4)
         off = np.zeros((len(boxes), 4), np.int32)
@@ -372,8 +375,9 @@ class CropPlan:
         self.out_hw = (OH, OW)
         self.tb, self.tk = _lanczos.device(device)
         self.kstride = _lanczos.kstride
-        self.box = _dev(boxes, np.int32, device)
-        self.off = _dev(off, np.int32, device)
+        self.h_box, self.h_off = boxes, off
+        self.box = _dev(boxes, np.int32, device) if upload else None
+        self.off = _dev(off, np.int32, device) if upload else None
 
 
 def crop_lanczos(x: torch.Tensor, boxes, out_hw: Tuple[int, int] = None, want_f32: bool = False, out=None, outf=None):
@@ -404,7 +408,7 @@ def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int]) -> tor
     return out
 
 
-def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc: float = 0.0) -> torch.Tensor:
+def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc: float = 0.0, dseeds: torch.Tensor = None) -> torch.Tensor:
     """uint8 [len(seeds), n]: row i = np.random.normal(loc, scale, n).astype(np.uint8) after np.random.seed(seeds[i]),
     generated on the GPU (NumPy legacy MT19937 + polar gauss, lfx_rng.cu).  Seed 0 means "unseeded" in the reference
     (image_augmenter.py:16: `if seed:`): those rows are drawn from the host's current np.random state."""
@@ -413,7 +417,7 @@ def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc:
     lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
     seeds = np.asarray(seeds, np.int64).reshape(-1)
     out = torch.empty((len(seeds), int(n)), dtype=torch.uint8, device=device)
-    ds = _dev((seeds & 0xFFFFFFFF).astype(np.uint32).view(np.int32), np.int32, device)
+    ds = dseeds if dseeds is not None else _dev((seeds & 0xFFFFFFFF).astype(np.uint32).view(np.int32), np.int32, device)
     _lib.check(lib.lfx_legacy_normal_u8(_p(ds), _p(out), len(seeds), int(n), float(loc), float(scale), _stream()))
     for i in np.nonzero(seeds == 0)[0]:
         out[int(i)] = torch.from_numpy(np.random.normal(loc, scale, int(n)).astype(np.uint8)).to(device)
@@ -458,3 +462,52 @@ def resize_nearest(x: torch.Tensor, out_hw: Tuple[int, int]) -> torch.Tensor:
     out = torch.empty((B, OH, OW) if x.dim() == 3 else (B, OH, OW, Cn), dtype=torch.uint8, device=x.device)
     _lib.check(lib.lfx_resize_nearest(_p(x), _p(out), B, H, W, Cn, OH, OW, _stream()))
     return out
+
+
+# ----------------------------------------------------------------------------- packed asynchronous parameter uploads
+class PackedUpload:
+    """Several small host arrays -> ONE pinned staging buffer -> one non-blocking H2D copy -> typed device views.
+    A pageable `.to(device)` per array blocks the host until the stream has drained; a hot loop that uploads a dozen
+    parameter arrays between kernels serialises host and GPU that way.  A small ring of pinned buffers guarded by events
+    keeps a buffer from being refilled while its copy is still queued."""
+    _ring = {}
+
+    def __init__(self, device, slots: int = 4):
+        self.device = device
+        key = str(device)
+        if key not in PackedUpload._ring:
+            PackedUpload._ring[key] = {"bufs": [None] * slots, "events": [None] * slots, "next": 0}
+        self.state = PackedUpload._ring[key]
+
+    def upload(self, arrays):
+        """arrays: {name: np.ndarray} -> {name: device tensor of the same dtype and shape}."""
+        st = self.state
+        lay, off = {}, 0
+        for k, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            lay[k] = (off, a)
+            off += (a.nbytes + 15) & ~15
+        total = max(off, 16)
+        i = st["next"]
+        st["next"] = (i + 1) % len(st["bufs"])
+        if st["events"][i] is not None:
+            st["events"][i].synchronize()
+        if st["bufs"][i] is None or st["bufs"][i].numel() < total:
+            st["bufs"][i] = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
+        hb = st["bufs"][i]
+        hnp = hb.numpy()
+        for k, (o, a) in lay.items():
+            hnp[o:o + a.nbytes] = a.reshape(-1).view(np.uint8)
+        db = hb[:total].to(self.device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st["events"][i] = ev
+        out = {}
+        for k, (o, a) in lay.items():
+            t = db[o:o + a.nbytes].view(_TORCH_DT[a.dtype.type])
+            out[k] = t.view(a.shape)
+        return out
+
+
+_TORCH_DT = {np.int32: torch.int32, np.int64: torch.int64, np.float64: torch.float64, np.float32: torch.float32,
+             np.uint8: torch.uint8, np.uint32: torch.int32}
