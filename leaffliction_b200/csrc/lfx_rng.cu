@@ -13,17 +13,19 @@
 //
 // Arithmetic.  The reference is fp64 (explicit round-to-nearest without FMA contraction: the host libraries are built
 // without FMA); CUDA's log() is within 1 ulp of glibc's, which can move a result only when 5*g lies within an ulp of
-// an integer (probability ~1e-15 per sample).  An fp32 evaluation decides first.  With u = 2^-24: x1, x2 carry 2u,
-// r2 5u, L = logf(r2) an absolute 5u + 2u|L|, and g = scale * x * sqrt(-2L / r2) the absolute error
-// |g| (2.5u/|L| + 8u).  A value with |g| >= 0.5 has |L| >= 0.005 (x^2 <= r2), so for |scale| <= 8 the error stays
-// below 7e-5; below 0.5 the byte is 0 whatever the error.  Attempts whose fp32 radius lies within 1e-6 of 1 (the
-// acceptance test) or whose value lies within 2^-12 of an integer are re-evaluated in fp64 (0.08 % of the attempts).
+// an integer (probability ~1e-15 per sample).  An fp32 evaluation on the fast units decides first.  With u = 2^-24:
+// x1, x2 carry 2u, r2 5u, L = __logf(r2) an absolute 5u + 4e-7 (its bound on [0.5, 2]; 2 ulp elsewhere), the reciprocal
+// and the reciprocal square root a few ulp, and g = scale * x * sqrt(-2L / r2) the absolute error
+// |g| (0.5 dL/|L| + ~12u).  A value with |g| >= 0.5 has |L| >= 0.005 (x^2 <= r2), so for |scale| <= 8 the error stays
+// below 1.5e-4; below 0.5 the byte is 0 whatever the error.  Attempts whose fp32 radius lies within 1e-6 of 1 (the
+// acceptance test) or whose value lies within 2^-11 of an integer are re-evaluated in fp64 (0.15 % of the attempts).
+// q > 0 always (r2 < 1), and q * rsqrt(q) = sqrt(q).
 #include "lfx_common.cuh"
 
 namespace {
 
 constexpr int RNG_WARPS = 8;
-#define LFX_RNG_EPS 0.000244140625f
+#define LFX_RNG_EPS 0.00048828125f
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 11);
@@ -82,8 +84,9 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
     const float fscale = (float)scale;
     int produced = 0;  // normals written so far (warp-uniform, always even)
     while (produced < n) {
+        // ---- phase 1: twist the whole 624-word block in place, five rounds of one quad per lane
 #pragma unroll 1
-        for (int t0 = 0; t0 < 156 && produced < n; t0 += 32) {
+        for (int t0 = 0; t0 < 156; t0 += 32) {
             const int t = t0 + lane;
             const bool act = t < 156;
             uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
@@ -103,34 +106,57 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
             __syncwarp();
             if (act) *reinterpret_cast<uint4*>(mt + 4 * t) = make_uint4(w0, w1, w2, w3);
             __syncwarp();
-            bool acc = false;
-            uint8_t o0 = 0, o1 = 0;
-            if (act) {
-                const uint32_t a = mt_temper(w0) >> 5, bq = mt_temper(w1) >> 6, c = mt_temper(w2) >> 5, d = mt_temper(w3) >> 6;
-                bool slow = !fast;
+        }
+        // ---- phase 2: the 156 attempts of the block.  The five rounds are independent of each other (no barrier, no
+        // shared-memory write), so they are unrolled: the long fp32 chains (log, divide, square root) of one round hide
+        // behind the others -- with ~10 warps per scheduler the kernel was latency-bound with one round in flight.
+        bool acc[5], slow[5];
+        uint8_t o0[5], o1[5];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int t = c * 32 + lane;
+            acc[c] = false;
+            slow[c] = false;
+            o0[c] = o1[c] = 0;
+            if (t < 156) {
+                slow[c] = !fast;
                 if (fast) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * t);
+                    const uint32_t a = mt_temper(q.x) >> 5, bq = mt_temper(q.y) >> 6, cc = mt_temper(q.z) >> 5, d = mt_temper(q.w) >> 6;
                     const float x1 = fmaf((float)bq, 0x1p-52f, (float)((int)a - (1 << 26)) * 0x1p-26f);
-                    const float x2 = fmaf((float)d, 0x1p-52f, (float)((int)c - (1 << 26)) * 0x1p-26f);
+                    const float x2 = fmaf((float)d, 0x1p-52f, (float)((int)cc - (1 << 26)) * 0x1p-26f);
                     const float r2 = fmaf(x1, x1, x2 * x2);
                     if (fabsf(r2 - 1.f) <= 1e-6f) {
-                        slow = true;
+                        slow[c] = true;
                     } else if (r2 < 1.f && r2 != 0.f) {
-                        const float f = sqrtf(-2.f * logf(r2) / r2);
-                        const bool k0 = byte32(fscale * (f * x2), o0), k1 = byte32(fscale * (f * x1), o1);
-                        acc = true;
-                        slow = !(k0 && k1);
+                        // fast units (MUFU lg2 / rcp / rsq: a few ulp each, |L| abs 4e-7 near 1) -- inside the error budget above
+                        const float q = -2.f * __logf(r2) * __frcp_rn(r2);
+                        const float f = q * rsqrtf(q);
+                        const bool k0 = byte32(fscale * (f * x2), o0[c]), k1 = byte32(fscale * (f * x1), o1[c]);
+                        acc[c] = true;
+                        slow[c] = !(k0 && k1);
                     }
                 }
-                if (slow) acc = attempt64(a, bq, c, d, loc, scale, o0, o1);
             }
-            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-            if (acc) {
+        }
+        // the rare fp64 re-evaluations after all five fast rounds (a call in the middle would serialise them)
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            if (slow[c]) {
+                const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * (c * 32 + lane));
+                acc[c] = attempt64(mt_temper(q.x) >> 5, mt_temper(q.y) >> 6, mt_temper(q.z) >> 5, mt_temper(q.w) >> 6, loc, scale, o0[c], o1[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc[c]);
+            if (acc[c]) {
                 const int k = produced + 2 * __popc(bal & ((1u << lane) - 1u));
                 if (k + 1 < n && pair_ok) {
-                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)(o0 | (o1 << 8));
+                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)(o0[c] | (o1[c] << 8));
                 } else {
-                    if (k < n) o[k] = o0;
-                    if (k + 1 < n) o[k + 1] = o1;
+                    if (k < n) o[k] = o0[c];
+                    if (k + 1 < n) o[k + 1] = o1[c];
                 }
             }
             produced += 2 * __popc(bal);
