@@ -124,6 +124,12 @@ def main():
     noise = torch.randint(0, 256, x.shape, dtype=torch.uint8, device=dev)
     cuts = [int(N * rng.uniform(0, 2) // 100) for _ in range(B)]
     add("distort", lambda: ops.distort(x, noise, cuts), 9 * N)
+    seeds = np.array([rng.randint(1, 1000000) for _ in range(B)], np.int64)
+    dseeds = torch.from_numpy((seeds & 0xFFFFFFFF).astype(np.uint32).view(np.int32)).to(dev)
+    t = timed(lambda: ops.legacy_normal_noise(seeds, 3 * N, 5.0, dev, dseeds=dseeds), args.reps)
+    res["legacy_normal_noise (device MT19937 + polar gauss)"] = {"ms": round(t, 4), "algo_bytes_per_image": 3 * N,
+                                                                  "Gsamples/s": round(B * 3 * N / (t / 1e3) / 1e9, 1),
+                                                                  "images_per_s": round(B / (t / 1e3))}
     print(json.dumps({"batch": B, "size": S, "peak_GB/s": peak, "ops": res}, indent=1))
 
 
