@@ -490,10 +490,17 @@ class PackedUpload:
         total = max(off, 16)
         i = st["next"]
         st["next"] = (i + 1) % len(st["bufs"])
+        if st["bufs"][i] is None or st["bufs"][i].numel() < total:
+            # grow EVERY slot at once (pinned allocations cost milliseconds: none may be left for the steady state)
+            for ev in st["events"]:
+                if ev is not None:
+                    ev.synchronize()
+            cap = max(total + total // 2, 4 << 20)
+            for k in range(len(st["bufs"])):
+                st["bufs"][k] = torch.empty(cap, dtype=torch.uint8).pin_memory()
+                st["events"][k] = None
         if st["events"][i] is not None:
             st["events"][i].synchronize()
-        if st["bufs"][i] is None or st["bufs"][i].numel() < total:
-            st["bufs"][i] = torch.empty(max(total, 1 << 20), dtype=torch.uint8).pin_memory()
         hb = st["bufs"][i]
         hnp = hb.numpy()
         for k, (o, a) in lay.items():
