@@ -513,6 +513,55 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     }
                 }
             }
+        } else if (nsl && (tw & 3) == 0 && a[3] == 0.0 && a[4] == 1.0 && a[5] == 0.0) {
+            // ---- identity-y maps (the reference's horizontal shear [1, k, 0, 0, 1, 0], image_augmenter.py:82): yin = yc exactly,
+            // so yf = y, dy = 0 and cubic(.., 0) = v2: output row y is a 4-tap filter of source row y.  Same thread layout as
+            // the general path (4 consecutive pixels of a row per thread) with the row terms hoisted and no row arithmetic.
+            const int band_px = (y1 - y0) * tw;
+            const int twsh = ((tw & (tw - 1)) == 0) ? 31 - __clz(tw) : -1;
+            for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
+                const int qy = twsh >= 0 ? (q >> twsh) : q / tw, qx = q - qy * tw;
+                const int y = y0 + qy;
+                const uint8_t* rp = s_rows + (y - v.r0) * v.pitch - v.cb;
+                const double trow = __dmul_rn(a[1], (double)y + 0.5);
+                uint8_t out[12];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int x = x0 + qx + k;
+                    double xin = __dadd_rn(__dadd_rn(__dmul_rn(a[0], (double)x + 0.5), trow), a[2]);
+                    uint8_t r3[3] = {0, 0, 0};
+                    if (!(xin < 0.0 || xin >= (double)W)) {
+                        xin = __dadd_rn(xin, -0.5);
+                        const int xf = (int)floor(xin);
+                        const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                        const int xa = min(max(xf - 1, 0), W - 1) * 3, xb = min(max(xf, 0), W - 1) * 3;
+                        const int xc2 = min(max(xf + 1, 0), W - 1) * 3, xd = min(max(xf + 2, 0), W - 1) * 3;
+                        uint32_t risky = 0u;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float fv = cubic32b(biased(rp[xa + c]), biased(rp[xb + c]), biased(rp[xc2 + c]), biased(rp[xd + c]), fdx);
+                            bool rk;
+                            r3[c] = warp_trunc(fv, rk);
+                            risky |= rk ? (1u << c) : 0u;
+                        }
+                        if (risky) {
+                            if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &r3[0]);
+                            if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &r3[1]);
+                            if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &r3[2]);
+                        }
+                    }
+                    out[k * 3] = r3[0], out[k * 3 + 1] = r3[1], out[k * 3 + 2] = r3[2];
+                }
+                uint8_t* d = dimg + ((size_t)y * W + x0 + qx) * 3;
+                if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                    d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+                    d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+                    d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+                } else {
+                    for (int i = 0; i < 12; ++i) d[i] = out[i];
+                }
+            }
         } else {
             const int band_px = (y1 - y0) * tw;
             for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
