@@ -2,6 +2,8 @@
 // 16.16 fixed point), bicubic affine/perspective warp (Pillow fp64 semantics), crop + Lanczos
 // resize (22-bit fixed point, H pass -> u8 -> V pass) and distortion (noise + autocontrast).
 // All integer / byte work: HBM-bound, no tensor cores.
+#include <type_traits>
+
 #include "lfx_common.cuh"
 
 namespace {
@@ -360,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     __shared__ int s_qn;
     __shared__ int s_yf[WB_ROWS];      // axis-aligned maps: floor(yin - 0.5) of each band row (INT_MIN: row outside the source)
     __shared__ float s_fdy[WB_ROWS];   // ... and its fractional part
+    __shared__ double s_trow[WB_ROWS]; // a4 * yc of each band row (maps whose yin also depends on x add their column term)
     const int img = blockIdx.y;
     const int band = TILED ? blockIdx.x / ntx : blockIdx.x, tx = TILED ? blockIdx.x - band * ntx : 0;
     const int y0 = band * WB_ROWS, y1 = min(H, y0 + WB_ROWS);
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     if (threadIdx.x == 0) s_qn = 0;
     if (threadIdx.x < WB_ROWS) {   // row coordinates of an axis-aligned map depend on y only: once per band, not per pixel
         const double yc = (double)(y0 + (int)threadIdx.x) + 0.5;
+        s_trow[threadIdx.x] = __dmul_rn(a[4], yc);
         double yin = __dadd_rn(__dmul_rn(a[4], yc), a[5]);
         const bool yok = !(yin < 0.0 || yin >= (double)H);
         yin = __dadd_rn(yin, -0.5);
@@ -452,17 +456,20 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                 *out = bicubic_value64(v.base, v.pitch, v.r0, v.cb, H, W, x, y, c, a, is_persp);
         };
 
-        if (nsl && a[1] == 0.0 && a[3] == 0.0) {
-            // ---- axis-aligned maps (a1 = a3 = 0: the reference's skew, image_augmenter.py:50-58, is a zoom + shift): xin
-            // depends on x only and yin on y only, so the horizontal cubic of source row r at column x serves every
-            // output row whose 4-row window contains r.  One output column per thread walking down the band with a rolling
-            // window of the four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's.
+        if (nsl && a[1] == 0.0) {
+            // ---- maps whose xin depends on x only (a1 = 0): the reference's skew (image_augmenter.py:50-58: a zoom + shift,
+            // a3 = 0 too) and its vertical shear ([1, 0, 0, k, 1, 0], :82: xin = xc, so dx = 0 and the horizontal cubic is the
+            // tap itself).  The horizontal cubic of source row r at column x serves every output row of that column whose
+            // 4-row window contains r: one output column per thread walking down the band with a rolling window of the
+            // four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's, value by value.
+            const bool rowonly = (a[3] == 0.0);   // yin depends on y only: row coordinates precomputed per band
             const int ncol = min(tw, THREADS);
             const int strips = max(1, THREADS / ncol);
             const int strip = threadIdx.x / ncol, cx = threadIdx.x - strip * ncol;
             const int rows_per = (y1 - y0 + strips - 1) / strips;
             const int ya = y0 + strip * rows_per, yb_end = min(y1, ya + rows_per);
-            if (strip < strips) {
+            auto columns = [&](auto rowonly_t) {
+                constexpr bool ROWONLY = decltype(rowonly_t)::value;
                 for (int x = x0 + cx; x < x1; x += ncol) {
                     const double xc = (double)x + 0.5;
                     double xin = __dadd_rn(__dmul_rn(a[0], xc), a[2]);
@@ -470,6 +477,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     xin = __dadd_rn(xin, -0.5);
                     const int xf = (int)floor(xin);
                     const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                    const double tcol = __dmul_rn(a[3], xc);
                     int xo[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
@@ -478,12 +486,23 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     int base = -(1 << 30);  // source row of hw[.][0]
                     uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
                     for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
-                        const int yf = s_yf[y - y0];
+                        int yf;
+                        float fdy;
+                        if (ROWONLY) {
+                            yf = s_yf[y - y0];
+                            fdy = s_fdy[y - y0];
+                        } else {   // yin = (a3*xc + a4*yc) + a5, the generic path's operations in the generic path's order
+                            double yin = __dadd_rn(__dadd_rn(tcol, s_trow[y - y0]), a[5]);
+                            const bool yok = !(yin < 0.0 || yin >= (double)H);
+                            yin = __dadd_rn(yin, -0.5);
+                            yf = (int)floor(yin);
+                            fdy = (float)__dadd_rn(yin, -(double)yf);
+                            if (!yok) yf = INT_MIN;
+                        }
                         if (!xok || yf == INT_MIN) {
                             dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
                             continue;
                         }
-                        const float fdy = s_fdy[y - y0];
                         const int yb = yf - 1;
                         int shift = yb - base;
                         if (shift < 0 || shift > 4) shift = 4;
@@ -492,7 +511,10 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
                                 hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
-                                hw[c][3] = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+                                // dx = 0: cubic32b(.., 0) = (v2 - 2^23) + 0 exactly -- the tap itself
+                                hw[c][3] = (!ROWONLY && fdx == 0.f) ? biased(rp[xo[1] + c]) - 8388608.f
+                                                                    : cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]),
+                                                                   biased(rp[xo[3] + c]), fdx);
                             }
                         }
                         base = yb;
@@ -512,6 +534,12 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                         }
                     }
                 }
+            };
+            if (strip < strips) {
+                if (rowonly)
+                    columns(std::true_type{});
+                else
+                    columns(std::false_type{});
             }
         } else if (nsl && (tw & 3) == 0 && a[3] == 0.0 && a[4] == 1.0 && a[5] == 0.0) {
             // ---- identity-y maps (the reference's horizontal shear [1, k, 0, 0, 1, 0], image_augmenter.py:82): yin = yc exactly,
