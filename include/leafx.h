@@ -117,6 +117,12 @@ int lfx_draw_augment_params(const int32_t* transform, const uint32_t* seed, int 
 
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
+/* Host-side: the task list of the balancing pass for an in-memory dataset (dataset_balancer.py:115-129 after
+ * random.seed(seed), :31): group g = one (class, transform) pair in plan order with group_count[g] copies drawn from a
+ * class of group_class_size[g] images; per task local_index = random.choice's index, task_seed = randint(0, 1000000). */
+int lfx_draw_balance_tasks(uint32_t seed, int ngroups, const int32_t* group_count, const int32_t* group_class_size,
+                           int32_t* local_index, int32_t* task_seed);
+
 /* cv2.resize as the mask path uses it: INTER_CUBIC upscale of the working image (_prepare_working_image, mask.py:29-50)
  * and INTER_NEAREST of the mask back to the original size (_resize_results_to_original, :526-545).
  * lfx_cubic_table (host): first[out_size] = first source index of every destination index (tap k reads

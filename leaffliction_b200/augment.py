@@ -337,10 +337,14 @@ class TaskArrays:
     def __len__(self):
         return len(self.transform)
 
-    def slice(self, lo, hi):
+    def slice(self, lo, hi, step=1):
         o = object.__new__(TaskArrays)
-        o.transform, o.seed, o.source_index = self.transform[lo:hi], self.seed[lo:hi], self.source_index[lo:hi]
+        o.transform, o.seed, o.source_index = self.transform[lo:hi:step], self.seed[lo:hi:step], self.source_index[lo:hi:step]
         return o
+
+    def shard(self, rank: int, world: int):
+        """Tasks i with i % world == rank."""
+        return self.slice(rank, None, world)
 
 
 def augment_device(x, tasks, device_noise: bool = True):

@@ -300,3 +300,32 @@ def tasks_for_labels(labels: np.ndarray, class_names: Sequence[str], plants: Dic
                 tasks.append(Task(f"{class_name}/{j}.jpg", f"{class_name}/{j}_aug_{t}_{i + 1}.jpg", t, class_name,
                                   rng.randint(0, 1000000), j))
     return plan, tasks
+
+
+def task_arrays_for_labels(labels: np.ndarray, class_names: Sequence[str], plants: Dict[str, Sequence[str]], seed: int = 42):
+    """tasks_for_labels without the Python objects: (plan, augment.TaskArrays) with the same draws, made by the native
+    restatement of the interpreter's stream (lfx_draw_balance_tasks).  Identical on every rank."""
+    import ctypes as C
+
+    from . import _lib, augment
+    labels = np.asarray(labels)
+    per_class = np.bincount(labels, minlength=len(class_names))
+    counts = {p: {c: int(per_class[class_names.index(c)]) for c in cls if per_class[class_names.index(c)] > 0} for p, cls in plants.items()}
+    plan = calculate_plan(counts)
+    groups = [(class_names.index(cn), augment.TRANSFORM_CODE[t], n) for cn, tr in plan.items() for t, n in tr.items()]
+    gcount = np.array([g[2] for g in groups], np.int32)
+    gsize = np.array([per_class[g[0]] for g in groups], np.int32)
+    total = int(gcount.sum())
+    local = np.zeros(total, np.int32)
+    tseed = np.zeros(total, np.int32)
+    P = C.c_void_p
+    _lib.check(_lib.load().lfx_draw_balance_tasks(int(seed) & 0xFFFFFFFF, len(groups), gcount.ctypes.data_as(P), gsize.ctypes.data_as(P),
+                                                  local.ctypes.data_as(P), tseed.ctypes.data_as(P)))
+    order = np.argsort(labels, kind="stable")                    # dataset indices grouped by class, ascending inside a class
+    starts = np.concatenate([[0], np.cumsum(per_class)])[:-1]
+    gclass = np.repeat(np.array([g[0] for g in groups], np.int64), gcount)
+    ta = object.__new__(augment.TaskArrays)
+    ta.transform = np.repeat(np.array([g[1] for g in groups], np.int32), gcount)
+    ta.seed = tseed.astype(np.int64)
+    ta.source_index = order[starts[gclass] + local].astype(np.int64)
+    return plan, ta

@@ -219,3 +219,25 @@ extern "C" int lfx_draw_augment_params(const int32_t* transform, const uint32_t*
     }
     return LFX_OK;
 }
+
+// The task list of the balancing pass (dataset_balancer.py:115-129): per class, per transform, per copy the reference draws
+// `random.choice(source_images)` and `random.randint(0, 1000000)` from ONE stream seeded by `random.seed(seed)` (:31).  For
+// in-memory datasets the choice is an index: group g (one class x transform pair, in plan order) has group_count[g] tasks
+// drawn from a class of group_class_size[g] images -> local_index[t] = _randbelow(size), task_seed[t] = _randbelow(1000001).
+extern "C" int lfx_draw_balance_tasks(uint32_t seed, int ngroups, const int32_t* group_count, const int32_t* group_class_size,
+                                      int32_t* local_index, int32_t* task_seed) {
+    LFX_REQUIRE(ngroups >= 0 && (ngroups == 0 || (group_count && group_class_size && local_index && task_seed)), LFX_ERR_ARG,
+                "draw_balance_tasks: bad arguments");
+    PyRandom r;
+    r.seed(seed);
+    size_t t = 0;
+    for (int g = 0; g < ngroups; ++g) {
+        LFX_REQUIRE(group_count[g] >= 0 && group_class_size[g] > 0, LFX_ERR_ARG, "draw_balance_tasks: group %d has count %d, class size %d", g,
+                    group_count[g], group_class_size[g]);
+        for (int i = 0; i < group_count[g]; ++i, ++t) {
+            local_index[t] = (int32_t)r.randbelow((uint32_t)group_class_size[g]);
+            task_seed[t] = (int32_t)r.randbelow(1000001u);
+        }
+    }
+    return LFX_OK;
+}

@@ -75,3 +75,22 @@ def test_bad_transform_code_rejected():
     from leaffliction_b200._lib import LeafxError
     with pytest.raises(LeafxError):
         augment.draw_params_batch(np.array([9], np.int32), [5], 32, 32)
+
+
+def test_native_task_list_equals_interpreter():
+    """balance.task_arrays_for_labels (native stream) == balance.tasks_for_labels (random.Random) task for task."""
+    from leaffliction_b200 import balance
+    counts = balance.synthetic_class_counts()
+    names = [c for p in counts.values() for c in p]
+    plants = {p: list(c) for p, c in counts.items()}
+    per = [max(1, n // 16) for p in counts.values() for n in p.values()]
+    rng = np.random.default_rng(0)
+    labels = rng.permutation(np.repeat(np.arange(len(names)), per))           # shuffled: class members are not contiguous
+    for seed in (42, 7, 123456789):
+        plan, tasks = balance.tasks_for_labels(labels, names, plants, seed=seed)
+        plan2, ta = balance.task_arrays_for_labels(labels, names, plants, seed=seed)
+        assert plan == plan2 and len(ta) == len(tasks)
+        ref = augment.TaskArrays(tasks)
+        assert np.array_equal(ta.transform, ref.transform)
+        assert np.array_equal(ta.seed, ref.seed)
+        assert np.array_equal(ta.source_index, ref.source_index)

@@ -49,8 +49,8 @@ def main():
     part = np.bincount(labels[list(balance.shard(N, rank, world))], minlength=len(names)).astype(np.int64)
     merged, _ = balance.allreduce_histograms(part, device=dev)
     assert merged.tolist() == per_class
-    plan, tasks = balance.tasks_for_labels(labels, names, plants, seed=42)     # identical on every rank
-    mine = augment.TaskArrays([tasks[i] for i in balance.shard(len(tasks), rank, world)])
+    plan, all_tasks = balance.task_arrays_for_labels(labels, names, plants, seed=42)     # identical on every rank (native stream)
+    mine = all_tasks.shard(rank, world)
     t_plan = time.perf_counter() - t0
 
     def run():
@@ -62,7 +62,7 @@ def main():
 
     # warm-up: a strided sample that contains every transform (module load, Lanczos tables, allocator pools)
     step = max(1, len(mine) // 512)
-    warm = [tasks[i] for i in list(balance.shard(len(tasks), rank, world))[::step]]
+    warm = mine.slice(0, None, step)
     augment.augment_device(x, warm, device_noise=not args.host_noise)
     if not args.host_noise:
         run()                                                          # one full untimed pass (allocator pools at full size)
@@ -85,7 +85,7 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(nn)
     if rank == 0:
-        print(json.dumps({"workload": f"class balancing: {N} images {S}x{S}, 8 classes, {len(tasks)} augment tasks (6 ops), images in HBM",
+        print(json.dumps({"workload": f"class balancing: {N} images {S}x{S}, 8 classes, {len(all_tasks)} augment tasks (6 ops), images in HBM",
                           "n_gpus": world, "tasks": int(nn.item()), "seconds": float(tt.item()), "passes": args.passes, "augmented_images_per_s": float(nn.item() / tt.item()),
                           "plan_and_histogram_s": t_plan, "noise": "host np.random" if args.host_noise else "device MT19937",
                           "per_transform": {k: sum(v.values()) if isinstance(v, dict) else v for k, v in
