@@ -94,3 +94,20 @@ def test_native_task_list_equals_interpreter():
         assert np.array_equal(ta.transform, ref.transform)
         assert np.array_equal(ta.seed, ref.seed)
         assert np.array_equal(ta.source_index, ref.source_index)
+
+
+def test_task_array_shards_partition_the_task_list():
+    from leaffliction_b200 import balance
+    counts = balance.synthetic_class_counts()
+    names = [c for p in counts.values() for c in p]
+    plants = {p: list(c) for p, c in counts.items()}
+    labels = np.repeat(np.arange(len(names)), [max(1, n // 64) for p in counts.values() for n in p.values()])
+    _, ta = balance.task_arrays_for_labels(labels, names, plants, seed=42)
+    for world in (1, 2, 8):
+        parts = [ta.shard(r, world) for r in range(world)]
+        assert sum(len(p) for p in parts) == len(ta)
+        merged_seed = np.empty(len(ta), np.int64)
+        for r, p in enumerate(parts):
+            merged_seed[r::world] = p.seed
+            assert np.array_equal(p.transform, ta.transform[r::world]) and np.array_equal(p.source_index, ta.source_index[r::world])
+        assert np.array_equal(merged_seed, ta.seed)
