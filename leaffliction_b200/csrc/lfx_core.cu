@@ -76,6 +76,8 @@ struct CoreParams {
     int t0, t1, t2;                         // symmetric vertical taps (t0 = taps[0] = taps[4], ...)
     int RH, RW;
     int need_lab_a;                         // Lab needed in phase A (lab strategy / lab brown)
+    int hue_direct;                         // both hue ranges inside [0, 150): predicates compare the unshifted fixed-point values
+    int g_lo12, g_span12, b_lo12, b_span12, b_smin12;   // range bounds << 12 for that form
     int timing;                             // debug: accumulate per-phase cycles (LFX_CORE_TIMING=1)
     Lay lay;
     unsigned long long ws_per_block;
@@ -393,10 +395,20 @@ __global__ void __launch_bounds__(MT, 2)
                 split_index(c, item, ry, w);
                 const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
                 const int r = px[0], g = px[1], b = px[2];
-                int h, s, v;
-                rgb2hsv(r, g, b, s_hsv, h, s, v);
                 bool b0, b1;
-                if (P.need_lab_a) {
+                if (P.hue_direct) {
+                    // H = th >> 12 (+180 when negative), S = ts >> 12 (rgb2hsv): lo <= H <= hi  <=>  lo << 12 <= th < (hi + 1) << 12
+                    // for ranges below 150 (a negative th maps to H >= 150, so no wrap-around case), S >= T  <=>  ts >= T << 12:
+                    // the two shifts and the hue fix-up are not needed for the predicates
+                    const int v = max(r, max(g, b)), d = v - min(r, min(g, b));
+                    const int ts = d * s_hsv->sdiv[v] + 2048;
+                    const int hh = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * d) : (r - g + 4 * d);
+                    const int th = hh * s_hsv->hdiv[d] + 2048;
+                    b0 = (M.cfg.strategy == 0) && ((unsigned)(th - P.g_lo12) < (unsigned)P.g_span12) && (ts >= (40 << 12));   // mask.py:90
+                    b1 = ((unsigned)(th - P.b_lo12) < (unsigned)P.b_span12) && (ts >= P.b_smin12) && (v <= M.cfg.brown_v_max);
+                } else if (P.need_lab_a) {
+                    int h, s, v;
+                    rgb2hsv(r, g, b, s_hsv, h, s, v);
                     int Ll, A, Bv;
                     rgb2lab(r, g, b, s_lab, Ll, A, Bv);
                     b0 = (M.cfg.strategy == 1) ? ((A <= 135) && (Bv >= 115) && (Bv <= 170))
@@ -405,6 +417,8 @@ __global__ void __launch_bounds__(MT, 2)
                                              : ((h >= M.cfg.brown_lo) && (h <= M.cfg.brown_hi) && (s >= M.cfg.brown_s_min) &&
                                                 (v <= M.cfg.brown_v_max));
                 } else {
+                    int h, s, v;
+                    rgb2hsv(r, g, b, s_hsv, h, s, v);
                     // unsigned range checks: (h - lo) <= (hi - lo)
                     b0 = (M.cfg.strategy == 0) && ((unsigned)(h - M.cfg.green_lo) <= (unsigned)(M.cfg.green_hi - M.cfg.green_lo)) && (s >= 40);  // mask.py:90
                     b1 = ((unsigned)(h - M.cfg.brown_lo) <= (unsigned)(M.cfg.brown_hi - M.cfg.brown_lo)) &&
@@ -749,6 +763,16 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
     P.K_0 = taps[0] << 8; P.K12 = taps[1] | (taps[2] << 8); P.K34 = taps[3] | (taps[4] << 8);
     P.RH = RH; P.RW = RW;
     P.need_lab_a = (cfg->strategy == 1 || cfg->use_lab_brown) ? 1 : 0;
+    {
+        auto in150 = [](int lo, int hi) { return lo >= 0 && lo <= hi && hi < 150; };
+        const bool green_ok = (cfg->strategy != 0) || in150(cfg->green_lo, cfg->green_hi);
+        P.hue_direct = (!P.need_lab_a && green_ok && in150(cfg->brown_lo, cfg->brown_hi) && cfg->brown_s_min >= 0 && cfg->brown_s_min <= 255) ? 1 : 0;
+        P.g_lo12 = cfg->green_lo << 12;
+        P.g_span12 = (cfg->green_hi + 1 - cfg->green_lo) << 12;
+        P.b_lo12 = cfg->brown_lo << 12;
+        P.b_span12 = (cfg->brown_hi + 1 - cfg->brown_lo) << 12;
+        P.b_smin12 = cfg->brown_s_min << 12;
+    }
     P.lay = make_lay(H, W, RH, RW);
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2);
