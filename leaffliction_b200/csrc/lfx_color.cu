@@ -187,13 +187,23 @@ __global__ void __launch_bounds__(THREADS) k_threshold_mask_vec(const uint8_t* _
     else
         load_lab_lut(&s_lab, tab);
     __syncthreads();
+    const bool direct = prm.green_lo >= 0 && prm.green_lo <= prm.green_hi && prm.green_hi < 150;
+    const int lo12 = prm.green_lo << 12, span12 = (prm.green_hi + 1 - prm.green_lo) << 12;
     for (long long g = (long long)blockIdx.x * THREADS + threadIdx.x; g < ngroups; g += (long long)gridDim.x * THREADS) {
         uint32_t w[12];
         load48(src + g * 48, w);
         uint8_t o[16];
         PxLoop<0>::run(w, [&](int p, int r, int gg, int b) {
             bool on;
-            if (prm.strategy == 0) {
+            if (prm.strategy == 0 && direct) {
+                // lo <= H <= hi  <=>  lo << 12 <= th < (hi + 1) << 12 for ranges below 150 (negative th means H >= 150);
+                // S >= 40  <=>  ts >= 40 << 12: neither the shifts nor the hue fix-up of rgb2hsv are needed
+                const int v = max(r, max(gg, b)), d = v - min(r, min(gg, b));
+                const int ts = d * s_hsv.sdiv[v] + 2048;
+                const int hh = (v == r) ? (gg - b) : (v == gg) ? (b - r + 2 * d) : (r - gg + 4 * d);
+                const int th = hh * s_hsv.hdiv[d] + 2048;
+                on = ((unsigned)(th - lo12) < (unsigned)span12) && (ts >= (40 << 12));  // mask.py:90
+            } else if (prm.strategy == 0) {
                 int h, sv, v;
                 rgb2hsv(r, gg, b, &s_hsv, h, sv, v);
                 on = ((unsigned)(h - prm.green_lo) <= (unsigned)(prm.green_hi - prm.green_lo)) && (sv >= 40);  // mask.py:90
