@@ -111,3 +111,22 @@ def test_task_array_shards_partition_the_task_list():
             merged_seed[r::world] = p.seed
             assert np.array_equal(p.transform, ta.transform[r::world]) and np.array_equal(p.source_index, ta.source_index[r::world])
         assert np.array_equal(merged_seed, ta.seed)
+
+
+def test_native_params_property_random_shapes_and_seeds():
+    """Property test: for arbitrary image shapes and seeds the native drawer equals the interpreter (crop boxes stay inside
+    the image, rotate sizes cover the rotated corners)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.integers(8, 2048), st.integers(8, 2048), st.integers(1, 2**32 - 1), st.integers(0, 5))
+    def check(h, w, seed, code):
+        ip, dp = augment.draw_params_batch(np.array([code], np.int32), [seed], h, w, threads=1)
+        eip, edp = _python_params(augment.TRANSFORMATIONS[code], seed, h, w)
+        assert np.array_equal(ip[0], eip) and np.array_equal(dp[0].view(np.int64), edp.view(np.int64))
+        if code == 4:
+            left, top, nw, nh = ip[0, :4]
+            assert 0 <= left and left + nw <= w and 0 <= top and top + nh <= h
+        if code == 1:
+            assert ip[0, 6] >= 1 and ip[0, 7] >= 1 and -30.0 <= dp[0, 0] <= 30.0
+    check()
