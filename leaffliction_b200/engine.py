@@ -42,7 +42,9 @@ def alloc_host_outputs(B, H, W, roi_size=(256, 256)) -> HostOutputs:
 
 class TransformEngine:
     def __init__(self, H: int, W: int, cfg=None, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                 device: Optional[torch.device] = None, chunk: int = 512):
+                 device: Optional[torch.device] = None, chunk: int = 512, front: Optional[str] = None):
+        """`front`: None = the strategy in `cfg` (hsv_h / lab / hsv_s / hsv_v_dark, fused kernel where the shape allows);
+        'inclusive' (the reference's default strategy) or 'enhanced' = raw candidate by the front-end kernel first."""
         if not torch.cuda.is_available():
             raise RuntimeError("TransformEngine needs a CUDA device: leaffliction_b200 has no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -51,12 +53,20 @@ class TransformEngine:
         self.sigma = float(gaussian_sigma)
         self.roi_size = (int(roi_size[0]), int(roi_size[1]))
         self.chunk = int(chunk)
+        if front not in (None, "inclusive", "enhanced"):
+            raise ValueError(f"front must be None, 'inclusive' or 'enhanced', not {front!r}")
+        self.front = front
         self._bufs = None
         self._streams = None
 
     # ---- device-resident
-    def run_device(self, x: torch.Tensor, out: Optional[ops.CoreOutputs] = None) -> ops.CoreOutputs:
+    def _pipeline(self, x, out):
+        if self.front:
+            return ops.pipeline_front(x, self.front, self.cfg, self.sigma, self.roi_size, out)
         return ops.pipeline_core(x, self.cfg, self.sigma, self.roi_size, out)
+
+    def run_device(self, x: torch.Tensor, out: Optional[ops.CoreOutputs] = None) -> ops.CoreOutputs:
+        return self._pipeline(x, out)
 
     # ---- host buffers in, host buffers out
     def _ensure(self):
@@ -97,7 +107,7 @@ class TransformEngine:
                     s_k.wait_event(ev_out[i - 2])      # output buffers free once copied back
                 view = ops.CoreOutputs(dev_out.blur[:n], dev_out.mask[:n], dev_out.info[:n], dev_out.roi[:n],
                                        dev_out.hist9[:n], dev_out.hsv3[:n], dev_out.counters[:n])
-                ops.pipeline_core(xin[:n], self.cfg, self.sigma, self.roi_size, view)
+                self._pipeline(xin[:n], view)
                 ev_k[i].record(s_k)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_k[i])

@@ -268,6 +268,28 @@ def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, ro
     return out
 
 
+def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
+                   out: Optional[CoreOutputs] = None) -> CoreOutputs:
+    """The core transform profile with the reference's DEFAULT mask strategies ('inclusive', config.yaml:7, or 'enhanced'):
+    raw candidate by the front-end kernel (lfx_raw_mask), then make_mask on that candidate (strategy 4), 5x5 blur, masked ROI
+    letterbox and colour statistics -- the same outputs as pipeline_core."""
+    import copy
+    _chk_img(x)
+    B, H, W, _ = x.shape
+    raw = raw_mask_front_end(x, which, cfg)
+    cfg4 = copy.copy(cfg)
+    cfg4.strategy = STRATEGY_IDS["external"]
+    mask, info = make_mask(x, cfg4, raw)
+    blur = gauss_u8(x, 5, gaussian_sigma)
+    roi = roi_letterbox(x, mask, info, roi_size)
+    h9, h3, cn = color_stats(x, mask)
+    if out is None:
+        return CoreOutputs(blur, mask, info, roi, h9, h3, cn)
+    for dst, srct in ((out.blur, blur), (out.mask, mask), (out.info, info), (out.roi, roi), (out.hist9, h9), (out.hsv3, h3), (out.counters, cn)):
+        dst.copy_(srct)
+    return out
+
+
 # --------------------------------------------------------------------------- augmentations
 def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
     _chk_img(x)

@@ -117,3 +117,28 @@ def test_analyze_record_and_hist_stats():
         assert np.array_equal(st["hsv_hist"], sm.hsv_hist_leaf(masked))
         for j, k in enumerate(filters.HIST_CATEGORIES):
             assert st["color_analysis"][k] == (int(cn[1 + j]) / int(cn[0])) * 100
+
+
+def test_engine_default_strategy_pipeline():
+    """TransformEngine(front='inclusive'): the batched core profile with the reference's default strategy, device- and
+    host-resident, against the oracle (mask, bbox, blur, ROI, histograms)."""
+    import torch
+    from leaffliction_b200 import engine, ops
+    from oracle import spec_filters as sf
+    dev = torch.device("cuda:0")
+    imgs = synth.leaf_batch(6, 256, 256, seed=3)
+    cfg = ops.mask_cfg("hsv_h")            # numeric fields; the raw candidate comes from the front end
+    eng = engine.TransformEngine(256, 256, cfg, 1.5, (256, 256), dev, chunk=4, front="inclusive")
+    out = eng.run_device(torch.from_numpy(imgs).to(dev))
+    host = eng.run_host(torch.from_numpy(imgs))
+    scfg = sm.Cfg(mask_strategy="inclusive")
+    for i in range(len(imgs)):
+        m, einfo = sm.make_mask(imgs[i], scfg)
+        masked = sm.apply_mask(imgs[i], m, "white")
+        for o in (out, host):
+            assert np.array_equal(np.asarray(o.mask[i].cpu()), m), i
+            assert np.array_equal(np.asarray(o.blur[i].cpu()), sf.gaussian_blur_u8(imgs[i], 5, 1.5))
+            assert tuple(np.asarray(o.info[i, 1:5].cpu())) == einfo["bbox"]
+            assert np.array_equal(np.asarray(o.roi[i].cpu()), sm.roi_letterbox(masked, einfo["bbox"], (256, 256)))
+            assert np.array_equal(np.asarray(o.hist9[i].cpu()), sm.hist9(imgs[i], m))
+            assert np.array_equal(np.asarray(o.counters[i, :14].cpu()), sm.hist_counters(masked))
