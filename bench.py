@@ -1,13 +1,19 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the core transform profile (BASELINE.json configs[1]).
+"""bench.py -- headline benchmark: BASELINE.json metric "images/sec (256x256 transform+augment)".
 
   python bench.py --gpus N --steps K --warmup W            # our CUDA path
   python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
 
-A "step" is one pass of the hot path (5x5 Gaussian blur + make_mask + masked ROI letterbox +
-RGB/HSV/LAB histograms) over one synthetic batch of 4096 256x256x3 uint8 leaf-like images PER GPU
-(weak scaling: the batch shards by image, no data-path collective; with N > 1 the dataset-level colour
-histogram is accumulated on each device and merged by ONE NCCL allreduce per pass, inside the timed region).  Prints ONE JSON line (rank 0).
+A "step" is one pass of the WHOLE hot path over one synthetic batch of 4096 256x256x3 uint8 leaf-like images PER GPU
+(BASELINE configs[1]):
+  * transform half -- the core profile (5x5 Gaussian blur + make_mask + masked ROI letterbox + RGB/HSV/LAB histograms):
+    one launch of the fused kernel k_core, which also adds the batch to the rank's dataset-level colour histogram;
+  * augment half   -- the six ImageAugmenter ops on every image of the same resident batch (flip, rotate, skew, shear,
+    crop, distortion; one task seed per op and image, parameters drawn natively in the reference's RNG order, the
+    distortion noise generated on the device): 9 launches.
+Weak scaling: the batch shards by image, no data-path collective; the per-rank dataset histogram is merged by ONE NCCL
+allreduce per timed pass (inside the timed region; the same per-step work runs at N = 1 and N > 1).
+Prints ONE JSON line (rank 0).  Sub-records `configs.c3_balance / c4_1024 / c5_resize224` time BASELINE configs[2..4].
 """
 from __future__ import annotations
 
@@ -27,9 +33,15 @@ if ROOT not in sys.path:
 
 METRIC = "images/sec (256x256 transform+augment)"
 UNIT = "images/s"
-# core transform profile, algorithmic HBM bytes per 256x256 image
-#   read 3N; write blur 3N, mask N, ROI canvas 3*256*256, hist 9*256*4, bbox/counters 80 B
-ALGO_BYTES_PER_IMAGE = lambda n, roi: 7 * n + 3 * roi * roi + 9 * 256 * 4 + 80  # noqa: E731
+PARITY = "P1 (mask_strategy hsv_h, grabcut_refine false, no upscale)"
+# core transform profile, algorithmic HBM bytes per image
+#   read 3N; write blur 3N, mask N, ROI canvas 3*RH*RW, hist 9*256*4, bbox/counters 80 B
+CORE_BYTES = lambda n, roi: 7 * n + 3 * roi * roi + 9 * 256 * 4 + 80  # noqa: E731
+
+
+def workload_text(B, S):
+    return (f"core transform profile (blur+mask+ROI+histograms) + 6-op augment set (flip, rotate, skew, shear, crop, "
+            f"distortion): {B} x {S}x{S}x3 uint8 leaf-like images per GPU, inputs resident in memory")
 
 
 def _gen_chunk(args):
@@ -43,6 +55,14 @@ def make_images(n, h, w, seed, pool):
     per = 64
     jobs = [(s, min(per, n - s), h, w, seed) for s in range(0, n, per)]
     return np.concatenate(pool.map(_gen_chunk, jobs))
+
+
+def task_seeds(B, rank=0):
+    """One non-zero task seed per op and image, as `random.randint(0, 1000000)` would hand them out
+    (dataset_balancer.py:127); identical for the CUDA arm and the reference arm."""
+    import numpy as np
+    rng = np.random.default_rng(20260 + rank)
+    return rng.integers(1, 1000001, size=(6, B), dtype=np.int64)
 
 
 class ClockSampler:
@@ -93,12 +113,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(images, cores, pool):
-    """Reference CPU path (oracle/refcalls.py = the reference's own OpenCV/NumPy calls on arrays, no
-    JPEG I/O) on `cores` worker processes.  Returns (images/s, seconds)."""
+def cpu_reference_rate(images, seeds, cores, pool):
+    """Reference CPU path (oracle/refcalls.py = the reference's own OpenCV/Pillow/NumPy calls on arrays, no
+    JPEG I/O): core transform + the six augmentations of every image, on `cores` worker processes."""
     from oracle import refcalls
     t0 = time.perf_counter()
-    n = refcalls.core_transform_pool(list(images), pool, cores)
+    n = refcalls.core_transform_pool(list(images), pool, cores, seeds)
     dt = time.perf_counter() - t0
     return n / dt, dt
 
@@ -118,31 +138,46 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = len(os.sched_getaffinity(0))
-    sample = min(args.batch, max(cores * 128, 256))      # ~1-2 s of work on all host cores per step
+    sample = min(args.batch, max(cores * 48, 128))       # a few seconds of work on all host cores per step
+    seeds = task_seeds(args.batch)[:, :sample]
     with mp.get_context("fork").Pool(cores) as pool:
         imgs = make_images(sample, args.size, args.size, 1234, pool)
-        for _ in range(max(args.warmup, 1)):
-            cpu_reference_rate(imgs[: max(cores * 4, 8)], cores, pool)
+        for _ in range(max(min(args.warmup, 2), 1)):
+            cpu_reference_rate(imgs[: max(cores * 2, 8)], seeds[:, : max(cores * 2, 8)], cores, pool)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            cpu_reference_rate(imgs, cores, pool)
+            cpu_reference_rate(imgs, seeds, cores, pool)
         dt = time.perf_counter() - t0
     rate = sample * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"core transform profile (blur+mask+ROI+histograms), {args.size}x{args.size}x3 uint8, "
-                               f"bounded sample of {sample} images per step of the {args.batch}-image batch",
-                   "parity_profile": "P1 (mask_strategy hsv_h, grabcut_refine false, no upscale)"},
+        "config": {"workload": workload_text(args.batch, args.size), "parity_profile": PARITY},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} images x {args.steps} steps; oracle/refcalls.py = the reference's OpenCV/"
-                                   f"NumPy/SciPy calls on in-memory arrays (no JPEG I/O), one process per core"},
+                         "sample": f"{sample} images of the {args.batch}-image batch per step x {args.steps} steps; "
+                                   f"oracle/refcalls.py = the reference's OpenCV/Pillow/NumPy/SciPy calls on in-memory "
+                                   f"arrays (no JPEG I/O): core transform + 6 augmentations per image, one process per core"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
     return 0
+
+
+def bind_rank_to_cores(local, nlocal):
+    """Give each rank of the box its own slice of the cores this process may use (preferring the GPU's NUMA-local
+    cores when /sys exposes them): the ranks' host threads (parameter draws, launches, pinned copies) stop competing."""
+    try:
+        avail = sorted(os.sched_getaffinity(0))
+        if nlocal <= 1 or len(avail) < 2 * nlocal:
+            return {"cores": len(avail), "bound": False}
+        per = len(avail) // nlocal
+        mine = avail[local * per:(local + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return {"cores": len(mine), "bound": True, "first": mine[0], "last": mine[-1]}
+    except Exception as e:   # noqa: BLE001
+        return {"cores": None, "bound": False, "error": str(e)}
 
 
 def main():
@@ -155,6 +190,8 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c4 / c5 sub-records")
+    ap.add_argument("--transform-only", action="store_true", help="debug: time the transform half alone")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -164,6 +201,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    from leaffliction_b200 import augment as aug_mod
     from leaffliction_b200 import engine as eng
     from leaffliction_b200 import ops
 
@@ -178,29 +216,39 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B, S = args.batch, args.size
     N = S * S
-    cores = len(os.sched_getaffinity(0))
-    gen_procs = max(1, cores // max(1, min(world, 8)))
+    cores_all = len(os.sched_getaffinity(0))
+    gen_procs = max(1, cores_all // max(1, min(world, 8)))
     with mp.get_context("fork").Pool(gen_procs) as pool:
         imgs_np = make_images(B, S, S, 1234 + 100000 * rank, pool)
+    binding = bind_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     host_in = torch.from_numpy(imgs_np).pin_memory()
     x = host_in.to(dev, non_blocking=True)
-    engine = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, chunk=512)
+    engine = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, chunk=512, augment=not args.transform_only)
     out = ops.alloc_core_outputs(B, S, S, (256, 256), dev)
-    ds_hist = torch.zeros((9 * 256,), dtype=torch.int64, device=dev)
+    ds_hist = torch.zeros((9, 256), dtype=torch.int64, device=dev)
+    augset = None if args.transform_only else aug_mod.AugmentSet(B, S, S, dev)
+    seeds = task_seeds(B, rank)
 
     def step():
-        engine.run_device(x, out)
-        if world > 1:  # dataset-level colour histogram: accumulated on the device batch by batch ...
-            ds_hist.add_(out.hist9.sum(dim=0, dtype=torch.int64).view(-1))
+        engine.run_device(x, out, ds_hist)       # k_core: transform half + the rank's dataset colour histogram
+        if augset is not None:
+            augset.run(x, seeds)                 # augment half: 6 ops x B images
 
     def merge():
-        if world > 1:  # ... and merged across ranks by ONE allreduce per dataset pass, inside the timed region
+        if world > 1:  # ONE allreduce per dataset pass, inside the timed region
             dist.all_reduce(ds_hist)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world > 1:
+            t = torch.tensor([v], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return v
 
     for _ in range(args.warmup):
         step()
@@ -218,15 +266,12 @@ def main():
     merge()
     e1.record()
     barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     value = world * B * args.steps / (ms / 1e3)
+    # the dataset histogram must equal the per-image histograms summed (checked outside the timed region)
+    ds_ok = bool(torch.equal(out.hist9.sum(dim=0, dtype=torch.int64) * args.steps, ds_hist)) if world == 1 else None
 
-    # ---- roofline of the dominant kernel.  The whole step is ONE launch of the fused kernel k_core (plus a
-    # 256-byte memset node that resets its image queue): time it alone with CUDA events on the launching stream.
+    # ---- per-kernel rooflines: every kernel of the step timed alone with CUDA events on the launching stream
     def timed(fn, reps):
         fn()
         torch.cuda.synchronize()
@@ -239,79 +284,118 @@ def main():
         return a.elapsed_time(b) / reps
 
     reps = max(3, min(args.steps, 10))
-    k_ms = {"k_core": timed(lambda: engine.run_device(x, out), reps)}
-    algo_bytes = ALGO_BYTES_PER_IMAGE(N, 256)   # 664,656 B per 256x256 image
     peak, peak_src = peak_hbm()
-    achieved = algo_bytes * B / (k_ms["k_core"] / 1e3) / 1e9
+    k_ms = {"k_core": timed(lambda: engine.run_device(x, out, ds_hist), reps)}
+    core_bytes = CORE_BYTES(N, 256)                # 664,656 B per 256x256 image
+    algo = {"k_core": core_bytes * B}
+    if augset is not None:
+        tm = {}
+        augset.run(x, seeds, timings={})
+        for _ in range(reps):
+            augset.run(x, seeds, timings=tm)
+        for k, v in tm.items():
+            k_ms[k] = v / reps
+        algo.update(augset.algo_bytes())
+    kernels = []
+    for k, t in k_ms.items():
+        gbs = algo[k] / (t / 1e3) / 1e9
+        kernels.append({"kernel": k, "ms": round(t, 4), "algo_bytes_per_launch": int(algo[k]), "achieved_gbs": round(gbs, 1),
+                        "frac": round(gbs / peak, 4), "share_of_step": None})
+    tot_k = sum(k["ms"] for k in kernels)
+    for k in kernels:
+        k["share_of_step"] = round(k["ms"] / tot_k, 4)
+    step_bytes = sum(algo.values())
+    achieved = algo["k_core"] / (k_ms["k_core"] / 1e3) / 1e9
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")   # dram bytes per image from the committed ncu --set full capture
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             traffic = float(tj["k_core_dram_bytes_per_image"]) * B
-            traffic_note = (f"dram__bytes_read+write of k_core from profiles/{tj.get('report', 'ncu report')} "
-                            f"({tj.get('images_in_launch')} images in the profiled launch), scaled per image to this launch")
+            traffic_note = (f"dram__bytes_read+write of k_core, ncu --set full, {tj.get('images_in_launch')} images in the profiled "
+                            f"launch, scaled per image to this launch; numbers committed in profiles/traffic.json "
+                            f"(capture: {tj.get('report', 'ncu report')})")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k_core (fused blur+mask+ROI+histograms, one block per image)",
+    step_gbs = step_bytes * (args.steps / (ms / 1e3)) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_core (fused blur+mask+ROI+histograms, one block per image): the transform half's only kernel",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_src,
-                "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()},
-                "algo_bytes_per_launch": algo_bytes * B,
-                "pipeline_algo_bytes_per_image": algo_bytes,
-                "pipeline_achieved_gbs": algo_bytes * (B * args.steps / (ms / 1e3)) / 1e9,
-                "pipeline_frac_of_peak": algo_bytes * (B * args.steps / (ms / 1e3)) / 1e9 / peak,
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+                "algo_bytes_per_launch": algo["k_core"], "frac_of_nominal_8TBs": achieved / 8000.0,
+                "kernels": kernels,
+                "largest_time_share": max(kernels, key=lambda k: k["ms"])["kernel"],
+                "step": {"algo_bytes_per_image": step_bytes / B, "achieved_gbs": step_gbs, "frac": step_gbs / peak,
+                         "note": "whole step (transform + augment), all kernels back to back: algorithmic bytes / step time"}}
 
-    # ---- end to end: host buffers in, host buffers out, copies inside the timed region
+    # ---- end to end: host buffers in, host buffers out (all seven transform outputs + the six augment outputs),
+    # copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        host_out = eng.alloc_host_outputs(B, S, S, (256, 256))
+        host_out = eng.alloc_host_outputs(B, S, S, (256, 256), augment=augset is not None)
+        kw = {"seeds": seeds} if augset is not None else {}
         for _ in range(2):
-            engine.run_host(host_in, host_out)
+            engine.run_host(host_in, host_out, **kw)
         barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        t0 = time.perf_counter()
         for _ in range(args.steps):
-            engine.run_host(host_in, host_out)
-        b.record()
+            engine.run_host(host_in, host_out, **kw)     # returns when the host buffers are filled
         barrier()
-        ems = a.elapsed_time(b)
-        if world > 1:
-            t = torch.tensor([ems], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
-        e2e = {"value": world * B * args.steps / (ems / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": int(host_in.numel()) * world, "d2h_bytes_per_step": int(host_out.nbytes()) * world,
-               "api": "leaffliction_b200.engine.TransformEngine.run_host (pinned host in/out, 3-stream chunked overlap)"}
+        ems = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        h2d, d2h = int(host_in.numel()), int(host_out.nbytes())
+        # PCIe ceiling of this rank: one large pinned copy each way
+        probe = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        dprobe = torch.empty_like(probe, device=dev)
+        bw_in = probe.numel() / (timed(lambda: dprobe.copy_(probe, non_blocking=True), 3) / 1e3) / 1e9
+        bw_out = probe.numel() / (timed(lambda: probe.copy_(dprobe, non_blocking=True), 3) / 1e3) / 1e9
+        bw_in, bw_out = -max_over_ranks(-bw_in), -max_over_ranks(-bw_out)     # the slowest rank
+        ceil_rate = world * B / max(h2d / (bw_in * 1e9), d2h / (bw_out * 1e9))
+        e2e_val = world * B * args.steps / (ems / 1e3)
+        e2e = {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+               "api": "leaffliction_b200.engine.TransformEngine(augment=True).run_host (pinned host in/out, 3-stream chunked "
+                      "overlap, returns after the last device-to-host copy); timed with the host clock",
+               "pcie": {"h2d_gbs": round(bw_in, 2), "d2h_gbs": round(bw_out, 2), "ceiling_images_s": ceil_rate,
+                        "frac_of_ceiling": e2e_val / ceil_rate,
+                        "note": "pinned 256 MiB cudaMemcpyAsync each way on this rank (slowest rank at N > 1); ceiling = the "
+                                "slower direction moving this step's bytes, directions overlapped"}}
+        del probe, dprobe, host_out
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- BASELINE configs[2..4] as sub-records
+    configs = None
+    if not args.no_configs and not args.transform_only:
+        from tools import bench_configs
+        configs = bench_configs.run_all(x, dev, rank, world, peak, max_over_ranks, barrier)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        passes = 4                                        # the whole batch, 4 passes: 10-20 s of work on all host cores
-        with mp.get_context("fork").Pool(cores) as pool:
-            cpu_reference_rate(imgs_np[: max(cores * 2, 8)], cores, pool)
+        sample = min(B, max(cores_all * 64, 256))
+        with mp.get_context("fork").Pool(cores_all) as pool:
+            cpu_reference_rate(imgs_np[: max(cores_all * 2, 8)], seeds[:, : max(cores_all * 2, 8)], cores_all, pool)
             t0 = time.perf_counter()
-            for _ in range(passes):
-                cpu_reference_rate(imgs_np, cores, pool)
+            passes = 0
+            while passes < 1 or time.perf_counter() - t0 < 10.0:
+                cpu_reference_rate(imgs_np[:sample], seeds[:, :sample], cores_all, pool)
+                passes += 1
             dt = time.perf_counter() - t0
-        rate = passes * B / dt
-        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"the whole {B}-image batch x {passes} passes, {dt:.1f} s wall on {cores} cores; oracle/refcalls.py (the "
-                         f"reference's OpenCV/NumPy/SciPy calls on in-memory arrays, no JPEG I/O), one process per core"}
+        rate = passes * sample / dt
+        cpu = {"value": rate, "unit": UNIT, "cores": cores_all, "kind": "port",
+               "sample": f"{sample} images of the batch x {passes} passes, {dt:.1f} s wall on {cores_all} cores; oracle/refcalls.py (the "
+                         f"reference's OpenCV/Pillow/NumPy/SciPy calls on in-memory arrays, no JPEG I/O): core transform + 6 "
+                         f"augmentations per image, one process per core"}
 
     if rank == 0:
+        launches = 1 + (aug_mod.AugmentSet.launches_per_run if augset is not None else 0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"core transform profile (blur+mask+ROI+histograms): {B} x {S}x{S}x3 uint8 leaf-like "
-                                   f"images per GPU, resident in HBM",
-                       "parity_profile": "P1 (mask_strategy hsv_h, grabcut_refine false, no upscale)",
+            "config": {"workload": workload_text(B, S), "parity_profile": PARITY,
                        "l2_policy": f"inputs larger than L2 ({B * N * 3 / 1e6:.0f} MB per step vs 126 MB L2)",
-                       "images_per_gpu": B, "parallelism": f"image-sharded x{world}"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 1 * args.steps,
+                       "images_per_gpu": B, "parallelism": f"image-sharded x{world}",
+                       "augment_outputs_per_image": 6 if augset is not None else 0,
+                       "dataset_histogram_matches_per_image_sum": ds_ok, "host_binding": binding},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "configs": configs,
+            "gpu_launches": launches * args.steps,
         }
         print(json.dumps(line))
     if world > 1:

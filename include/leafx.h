@@ -16,6 +16,9 @@
  *   - Return value: 0 on success, negative LFX_ERR_* otherwise; lfx_last_error() returns a
  *     thread-local message.  There is no CPU fallback: without a CUDA device every compute entry
  *     point fails with LFX_ERR_CUDA.
+ *   - The augment entry points take `src_index` (device int32[B], may be NULL) and `n_src`: output image i is
+ *     computed from source image src_index[i] of the n_src images at `src` (NULL = image i of B).  This is the
+ *     balancer's `random.choice(source_images)` (dataset_balancer.py:116) without a gather copy.
  *   - Per-image parameters (angles, coefficients, crop boxes ...) are drawn on the host by the
  *     Python shim with the same `random` / `np.random` calls, in the same order, as the
  *     reference (image_augmenter.py:23,36,48,77,79,101,105,106,121,127), then uploaded.
@@ -49,20 +52,22 @@ const char* lfx_last_error(void);
 /* ImageAugmenter.flip (image_augmenter.py:20-31; PIL transpose :24,:26).
  * mode[B]: 0 = FLIP_LEFT_RIGHT, 1 = FLIP_TOP_BOTTOM. */
 int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode,
-             lfx_stream_t stream);
+             const int32_t* src_index, int n_src, lfx_stream_t stream);
 
 /* ImageAugmenter.rotate (image_augmenter.py:33-42; PIL rotate NEAREST, expand, white fill :37).
  * params[B][8] = {a0,a1,a2,a3,a4,a5 (16.16 fixed point, libImaging affine_fixed), nw, nh}.
  * Output image i is written at dst + i*dst_image_stride as [nh_i, nw_i, 3] contiguous;
  * pixels that map outside the source get `fill` in every channel. */
 int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,
-                  const int32_t* params, int fill, lfx_stream_t stream);
+                  const int32_t* params, int fill, const int32_t* src_index, int n_src,
+                  lfx_stream_t stream);
 
 /* ImageAugmenter.skew / .shear (image_augmenter.py:44-71, :73-94; PIL transform BICUBIC :61-66,:84-89).
  * coef[B][8] = PIL's inverse-map coefficients a..h (fp64); perspective[B] != 0 selects the
  * PERSPECTIVE divide.  Bit-exact with Pillow's fp64 arithmetic. */
 int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, const double* coef,
-                     const int32_t* perspective, lfx_stream_t stream);
+                     const int32_t* perspective, const int32_t* src_index, int n_src,
+                     lfx_stream_t stream);
 
 /* HOST helpers: Pillow's 8-bit Lanczos coefficient tables (libImaging Resample.c
  * precompute_coeffs + normalize_coeffs_8bpc).  lfx_lanczos_ksize returns the tap count;
@@ -82,14 +87,15 @@ int lfx_lanczos_table(int in_size, int out_size, int kstride, int32_t* bounds, i
 int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, int H, int W,
                      const int32_t* box, int OH, int OW, const int32_t* tab_bounds,
                      const int32_t* tab_kk, int kstride, const int32_t* tab_off,
-                     lfx_stream_t stream);
+                     const int32_t* src_index, int n_src, lfx_stream_t stream);
 
 /* ImageAugmenter.distortion (image_augmenter.py:116-133): x = src + noise (uint8 wrap-around,
  * :121-124), per-channel ImageOps.autocontrast(cutoff) (:127).
  * noise[B,H,W,3]: the uint8-cast Gaussian noise; cut[B] = int(H*W*cutoff // 100) computed on the
  * host; hist_ws: device scratch int32 [B][3][256]. */
 int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W,
-                const int32_t* cut, int32_t* hist_ws, lfx_stream_t stream);
+                const int32_t* cut, int32_t* hist_ws, const int32_t* src_index, int n_src,
+                lfx_stream_t stream);
 
 /* The noise of ImageAugmenter.distortion generated on the device: out[b, 0..n) =
  * np.random.normal(loc, scale, n).astype(np.uint8) after np.random.seed(seeds[b]) -- NumPy's legacy MT19937 +
@@ -253,12 +259,14 @@ int lfx_saliency_blur(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int
                       size_t workspace_bytes, lfx_stream_t stream);
 
 /* Fused core transform profile (BASELINE config 2: blur + mask + ROI + histograms), equivalent to
- * lfx_gauss_u8(5x5) + lfx_make_mask + lfx_roi_letterbox + lfx_color_stats in one submission. */
+ * lfx_gauss_u8(5x5) + lfx_make_mask + lfx_roi_letterbox + lfx_color_stats in one submission.
+ * dataset_hist9 (optional, device int64 [9][256], needs hist9): the batch's histograms are ADDED to it -- the
+ * per-rank partial of the dataset-level colour histogram that one allreduce merges. */
 size_t lfx_pipeline_core_workspace(int B, int H, int W);
 int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info,
                       uint8_t* roi, int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H,
                       int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg /* host */,
-                      void* workspace, size_t workspace_bytes, lfx_stream_t stream);
+                      void* workspace, size_t workspace_bytes, int64_t* dataset_hist9, lfx_stream_t stream);
 
 #ifdef __cplusplus
 }

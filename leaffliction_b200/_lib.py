@@ -33,13 +33,13 @@ _SIGS = {
     "lfx_version": (C.c_int, []),
     "lfx_init": (C.c_int, [_I]),
     "lfx_last_error": (C.c_char_p, []),
-    "lfx_flip": (C.c_int, [_P, _P, _I, _I, _I, _P, _P]),
-    "lfx_rotate_nn": (C.c_int, [_P, _P, C.c_int64, _I, _I, _I, _P, _I, _P]),
-    "lfx_warp_bicubic": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "lfx_flip": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "lfx_rotate_nn": (C.c_int, [_P, _P, C.c_int64, _I, _I, _I, _P, _I, _P, _I, _P]),
+    "lfx_warp_bicubic": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "lfx_lanczos_ksize": (C.c_int, [_I, _I]),
     "lfx_lanczos_table": (C.c_int, [_I, _I, _I, _P, _P]),
-    "lfx_crop_lanczos": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P]),
-    "lfx_distort": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    "lfx_crop_lanczos": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
+    "lfx_distort": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "lfx_cvt_color": (C.c_int, [_P, _P, _I, _I, _I, _I, _P]),
     "lfx_threshold_mask": (C.c_int, [_P, _P, _I, _I, _I, C.POINTER(MaskCfg), _P]),
     "lfx_make_mask_workspace": (C.c_size_t, [_I, _I, _I]),
@@ -64,7 +64,7 @@ _SIGS = {
     "lfx_resize_cubic": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "lfx_resize_nearest": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "lfx_pipeline_core": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_double,
-                                    C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
+                                    C.POINTER(MaskCfg), _P, C.c_size_t, _P, _P]),
 }
 
 _lib = None
@@ -83,9 +83,12 @@ def load() -> C.CDLL:
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            from . import build as _build
-            _build.build()
+        from . import build as _build
+        try:
+            _build.build()          # returns at once when the library is newer than every source
+        except RuntimeError:
+            if not os.path.exists(LIB_PATH):
+                raise               # a prebuilt library on a box without nvcc is fine; none at all is not
         if not os.path.exists(LIB_PATH):
             raise LeafxError(ERR_CUDA, f"{LIB_PATH} is missing and could not be built; there is no CPU fallback")
         lib = C.CDLL(LIB_PATH)

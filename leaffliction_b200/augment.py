@@ -376,7 +376,7 @@ def augment_device(x, tasks, device_noise: bool = True):
     # launches that follow never wait for the stream to drain
     groups = {"flip": ids_of("flip"), "rotate": ids_of("rotate"), "warp": ids_of("skew", "shear"), "crop": ids_of("crop"),
               "distortion": dist_ids}
-    host = {f"src_{k}": ta.source_index[ids].astype(np.int64) for k, ids in groups.items() if len(ids)}
+    host = {f"src_{k}": ta.source_index[ids].astype(np.int32) for k, ids in groups.items() if len(ids)}
     plan = None
     if len(groups["flip"]):
         host["flip_mode"] = ip[groups["flip"], 0]
@@ -392,23 +392,21 @@ def augment_device(x, tasks, device_noise: bool = True):
     d = up.upload(host) if host else {}
     out = {}
 
-    def gather(k):
-        return x.index_select(0, d[f"src_{k}"])
-
+    # the kernels read source image src_index[i] in place (no gather copy of the sources)
     ids = groups["flip"]
     if len(ids):
-        out["flip"] = (ids, ops.flip(gather("flip"), d["flip_mode"]))
+        out["flip"] = (ids, ops.flip(x, d["flip_mode"], src_index=d["src_flip"]))
     ids = groups["rotate"]
     if len(ids):
-        slab, stride = ops.rotate_nn(gather("rotate"), ip[ids], 255, dparams=d["rot"])
+        slab, stride = ops.rotate_nn(x, ip[ids], 255, dparams=d["rot"], src_index=d["src_rotate"])
         out["rotate"] = (ids, slab, ip[ids][:, [7, 6]])
     ids = groups["warp"]
     if len(ids):
-        out["warp"] = (ids, ops.warp_bicubic(gather("warp"), d["warp_coef"], d["warp_persp"]))
+        out["warp"] = (ids, ops.warp_bicubic(x, d["warp_coef"], d["warp_persp"], src_index=d["src_warp"]))
     ids = groups["crop"]
     if len(ids):
         plan.box, plan.off = d["crop_box"], d["crop_off"]
-        out["crop"] = (ids, ops.crop_lanczos(gather("crop"), plan))
+        out["crop"] = (ids, ops.crop_lanczos(x, plan, src_index=d["src_crop"]))
     ids = dist_ids
     if len(ids):
         if noise is None:
@@ -418,5 +416,97 @@ def augment_device(x, tasks, device_noise: bool = True):
                     np.random.seed(int(sd))
                 noises.append(np.random.normal(0, NOISE_LEVEL, (h, w, 3)).astype(np.uint8))
             noise = torch.from_numpy(np.stack(noises)).to(dev)
-        out["distortion"] = (ids, ops.distort(gather("distortion"), noise, d["cuts"]))
+        out["distortion"] = (ids, ops.distort(x, noise, d["cuts"], src_index=d["src_distortion"]))
     return out
+
+
+# --------------------------------------------------------------------------- the 6-op augment set on a resident batch
+class AugmentSet:
+    """Every image of a device-resident batch through all six ImageAugmenter ops (BASELINE metric "transform+augment":
+    6 augmentations per image, image_augmenter.py:20-133), each with its own task seed exactly as
+    `_process_single_transformation` runs it (dataset_balancer.py:201-207: a fresh ImageAugmenter(seed) per task).
+    Outputs, noise and scratch are allocated once; `run` draws the parameters natively (lfx_draw_augment_params), uploads
+    them in one pinned transfer and launches the kernels: noise, flip, rotate, skew, shear, crop, distort.
+    Seeds must be non-zero (seed 0 leaves the reference unseeded: such tasks go through `augment_arrays`)."""
+
+    OPS = ("flip", "rotate", "skew", "shear", "crop", "distortion")
+
+    def __init__(self, B: int, H: int, W: int, device):
+        import torch
+        self.B, self.H, self.W, self.device = int(B), int(H), int(W), device
+        u8 = dict(dtype=torch.uint8, device=device)
+        self.flip = torch.empty((B, H, W, 3), **u8)
+        self.skew = torch.empty((B, H, W, 3), **u8)
+        self.shear = torch.empty((B, H, W, 3), **u8)
+        self.crop = torch.empty((B, H, W, 3), **u8)
+        self.distortion = torch.empty((B, H, W, 3), **u8)
+        self.noise = torch.empty((B, H * W * 3), **u8)
+        self.hist_ws = torch.empty((B, 3, 256), dtype=torch.int32, device=device)
+        # rotate outputs: pitched slab, image i = rotate[i, :nh_i*nw_i*3].  nw*nh = WH + (W^2+H^2)/2 * sin(2a) grows with
+        # |a| up to 45 degrees, so the reference's +-30 degree draw (image_augmenter.py:36) is bounded by the 30-degree size
+        _, nw30, nh30 = rotate_matrix(30.0, W, H)
+        self.rotate_stride = (((nw30 + 1) * (nh30 + 1) * 3 + 15) // 16) * 16
+        self.rotate = torch.empty((B, self.rotate_stride), **u8)
+        self.rotate_hw = None              # int32 [B,2] (nh, nw) on the host
+        self._up = None
+
+    def out_bytes_per_image(self, rotate_px_mean: float) -> float:
+        n = self.H * self.W * 3
+        return 5 * n + 3 * rotate_px_mean
+
+    def run(self, x, seeds: np.ndarray, timings: dict = None):
+        """x: uint8 [B,H,W,3] on the device; seeds: int [6,B] (one task seed per op and image, non-zero).
+        `timings`: optional dict filled with per-kernel milliseconds (synchronising CUDA events: profiling runs only)."""
+        import torch
+        ops = _ops()
+        B, H, W = self.B, self.H, self.W
+        seeds = np.asarray(seeds, np.int64).reshape(6, B)
+        if (seeds == 0).any():
+            raise ValueError("AugmentSet: task seeds must be non-zero (seed 0 is 'unseeded' in the reference)")
+        if self._up is None:
+            self._up = ops.PackedUpload(self.device)
+        tr = np.repeat(np.arange(6, dtype=np.int32), B)
+        # noise first: it needs only the seeds and runs while the host draws the other parameters
+        d0 = self._up.upload({"seeds": (seeds[5] & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})
+
+        def timed(name, fn):
+            if timings is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            b.synchronize()
+            timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+            return r
+
+        timed("k_legacy_normal_u8", lambda: ops.legacy_normal_noise(seeds[5], H * W * 3, NOISE_LEVEL, self.device,
+                                                                    dseeds=d0["seeds"], out=self.noise))
+        ip, dp = draw_params_batch(tr, seeds.reshape(-1), H, W)
+        ip, dp = ip.reshape(6, B, 8), dp.reshape(6, B, 8)
+        plan = ops.CropPlan(ip[4, :, :4], (H, W), self.device, upload=False)
+        d = self._up.upload({"flip_mode": ip[0, :, 0], "rot": ip[1], "skew_coef": dp[2], "skew_persp": ip[2, :, 0],
+                             "shear_coef": dp[3], "shear_persp": ip[3, :, 0], "crop_box": plan.h_box, "crop_off": plan.h_off,
+                             "cuts": ip[5, :, 0]})
+        plan.box, plan.off = d["crop_box"], d["crop_off"]
+        self.rotate_hw = ip[1][:, [7, 6]]
+        self.crop_px = int((ip[4, :, 2].astype(np.int64) * ip[4, :, 3]).sum())
+        timed("k_flip_vec", lambda: ops.flip(x, d["flip_mode"], out=self.flip))
+        timed("k_rotate_nn", lambda: ops.rotate_nn(x, ip[1], 255, dparams=d["rot"], out=self.rotate))
+        timed("k_warp_bicubic(skew)", lambda: ops.warp_bicubic(x, d["skew_coef"], d["skew_persp"], out=self.skew))
+        timed("k_warp_bicubic(shear)", lambda: ops.warp_bicubic(x, d["shear_coef"], d["shear_persp"], out=self.shear))
+        timed("k_crop_lanczos_strip", lambda: ops.crop_lanczos(x, plan, out=self.crop))
+        timed("k_distort_hist+lut+apply", lambda: ops.distort(x, self.noise.view(B, H, W, 3), d["cuts"], out=self.distortion,
+                                                               hist_ws=self.hist_ws))
+        return self
+
+    def algo_bytes(self):
+        """Algorithmic HBM bytes per kernel for the last run, whole batch."""
+        n = self.H * self.W * 3
+        B = self.B
+        rot_px = int((self.rotate_hw[:, 0].astype(np.int64) * self.rotate_hw[:, 1]).sum())
+        return {"k_flip_vec": 2 * n * B, "k_rotate_nn": n * B + 3 * rot_px, "k_warp_bicubic(skew)": 2 * n * B,
+                "k_warp_bicubic(shear)": 2 * n * B, "k_crop_lanczos_strip": 3 * self.crop_px + n * B, "k_distort_hist+lut+apply": 3 * n * B,
+                "k_legacy_normal_u8": n * B}
+
+    launches_per_run = 9   # noise, flip, rotate, skew, shear, crop, distort hist / lut / apply (+ one memset node)

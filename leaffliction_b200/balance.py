@@ -193,13 +193,23 @@ class DatasetBalancer:
         return self.plan
 
     def _prepare_target_directory(self):
+        """rank 0 recreates target_dir as a copy of source_dir (dataset_balancer.py:61-68); every rank learns whether that
+        worked through an allreduce, so a failure on rank 0 raises everywhere instead of leaving the others in a barrier."""
+        err = None
         if self.rank == 0:
-            if self.target_dir.exists():
-                shutil.rmtree(self.target_dir)
-            if not self.source_dir.exists():
-                raise FileNotFoundError(f"Source directory not found: {self.source_dir}")
-            shutil.copytree(self.source_dir, self.target_dir)
-        self._barrier()
+            try:
+                if self.target_dir.exists():
+                    shutil.rmtree(self.target_dir)
+                if not self.source_dir.exists():
+                    raise FileNotFoundError(f"Source directory not found: {self.source_dir}")
+                shutil.copytree(self.source_dir, self.target_dir)
+            except Exception as e:   # noqa: BLE001 -- re-raised below, after the other ranks have been told
+                err = e
+        failed, _ = allreduce_histograms(np.array([1 if err is not None else 0], np.int64))
+        if err is not None:
+            raise err
+        if int(failed[0]):
+            raise RuntimeError("dataset balancing: rank 0 could not prepare the target directory")
 
     def _barrier(self):
         import torch.distributed as dist
@@ -207,14 +217,18 @@ class DatasetBalancer:
             dist.barrier()
 
     def _get_images_by_class(self):
+        """Class name -> source images inside target_dir (dataset_balancer.py:85-93).  The listing is taken from
+        SOURCE_DIR (target_dir is a fresh copy of it, so the names are the same) and rebased: ranks that are already
+        writing `*_aug_*.jpg` files into target_dir cannot change what a slower rank lists.  Unlike the reference
+        (filesystem order, quirk B.14) the lists are sorted so that every rank draws the same task list from the same
+        seeded stream."""
         images_by_class = defaultdict(list)
-        for plant_dir in self.target_dir.iterdir():
+        for plant_dir in self.source_dir.iterdir():
             if plant_dir.is_dir():
                 for class_dir in plant_dir.iterdir():
                     if class_dir.is_dir():
-                        images_by_class[class_dir.name] = list(class_dir.glob("*.JPG")) + list(class_dir.glob("*.jpg"))
-        # unlike the reference (filesystem order, quirk B.14) the lists are sorted so that every rank draws
-        # the same task list from the same seeded stream
+                        files = list(class_dir.glob("*.JPG")) + list(class_dir.glob("*.jpg"))
+                        images_by_class[class_dir.name] = [self.target_dir / f.relative_to(self.source_dir) for f in files]
         return {k: sorted(v) for k, v in images_by_class.items()}
 
     def execute_balancing(self):

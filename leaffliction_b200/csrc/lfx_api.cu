@@ -3,13 +3,29 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "lfx_common.cuh"
 #include "lfx_tables.h"
 
 static thread_local char t_err[512] = "";
-static bool g_ready = false;
+// Per-device library state (a __device__ symbol has one instance per device; its address is looked up per device).
+// Filled by lfx_init under a mutex; every other entry point only reads the slot of the CURRENT device.
 __device__ LfxTables g_lfx_tables_storage;
-static const LfxTables* g_tables_dev = nullptr;
+__device__ uint4 g_lfx_cat_lut_storage[3 * 256];
+struct LfxDeviceState {
+    bool ready;
+    const LfxTables* tables;
+    const uint4* cat_lut;
+};
+static LfxDeviceState g_state[LFX_MAX_DEVICES];
+static std::mutex g_init_mutex;
+
+int lfx_device_slot() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= LFX_MAX_DEVICES) return -1;
+    return d;
+}
 
 void lfx_set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,8 +43,49 @@ int lfx_check_launch(const char* what) {
     return LFX_OK;
 }
 
-bool lfx_ready() { return g_ready; }
-const LfxTables* lfx_tables() { return g_tables_dev; }
+bool lfx_ready() {
+    const int d = lfx_device_slot();
+    return d >= 0 && g_state[d].ready;
+}
+const LfxTables* lfx_tables() {
+    const int d = lfx_device_slot();
+    return d >= 0 ? g_state[d].tables : nullptr;
+}
+const uint4* lfx_cat_lut() {
+    const int d = lfx_device_slot();
+    return d >= 0 ? g_state[d].cat_lut : nullptr;
+}
+
+// hist.py:38-65 categories and :248-256 hue ranges as per-channel byte flags.  Field k (byte k%4 of word k/4):
+// 0 leaf (hist.py:188), 1..8 the categories, 9..13 the hue ranges.
+static void build_cat_lut(uint32_t* lut /* [3][256][4] */) {
+    memset(lut, 0, 3 * 256 * 16);
+    for (int i = 0; i < 256; ++i) {
+        const int h = i, s = i, v = i;
+        const bool leaf_s = s > 10, leaf_v = v > 15 && v < 245;
+        bool fh[14], fs[14], fv[14];
+        fh[0] = true; fs[0] = leaf_s; fv[0] = leaf_v;
+        fh[1] = h >= 35 && h <= 85; fs[1] = s >= 40; fv[1] = v >= 30;
+        fh[2] = h >= 20 && h <= 40; fs[2] = s >= 25; fv[2] = v >= 30;
+        fh[3] = h >= 15 && h <= 35; fs[3] = s >= 50; fv[3] = v >= 50;
+        fh[4] = h <= 25 || h >= 160; fs[4] = s >= 30; fv[4] = v >= 20;
+        fh[5] = (h >= 160 && h <= 180) || h <= 10; fs[5] = s >= 40; fv[5] = v >= 30;
+        fh[6] = true; fs[6] = s >= 20; fv[6] = v <= 50;
+        fh[7] = true; fs[7] = s <= 30; fv[7] = v >= 200;
+        fh[8] = h >= 120 && h <= 160; fs[8] = s >= 20; fv[8] = true;
+        fh[9] = h >= 35 && h <= 85; fs[9] = true; fv[9] = true;
+        fh[10] = h >= 15 && h <= 35; fs[10] = true; fv[10] = true;
+        fh[11] = h <= 15 || h >= 160; fs[11] = true; fv[11] = true;
+        fh[12] = h >= 120 && h <= 160; fs[12] = true; fv[12] = true;
+        fh[13] = h > 85 && h < 120; fs[13] = true; fv[13] = true;
+        for (int k = 0; k < 14; ++k) {
+            const uint32_t bit = 1u << (8 * (k & 3));
+            if (fh[k]) lut[(0 * 256 + i) * 4 + (k >> 2)] |= bit;
+            if (fs[k] && leaf_s) lut[(1 * 256 + i) * 4 + (k >> 2)] |= bit;
+            if (fv[k] && leaf_v) lut[(2 * 256 + i) * 4 + (k >> 2)] |= bit;
+        }
+    }
+}
 
 extern "C" int lfx_version(void) { return 100; }
 
@@ -39,10 +96,11 @@ extern "C" int lfx_init(int device) {
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) {
         lfx_set_error("no CUDA device: %s (libleafx has no CPU fallback)", cudaGetErrorString(e));
-        g_ready = false;
         return LFX_ERR_CUDA;
     }
-    LFX_REQUIRE(device >= 0 && device < n, LFX_ERR_ARG, "device %d out of range (0..%d)", device, n - 1);
+    LFX_REQUIRE(device >= 0 && device < n && device < LFX_MAX_DEVICES, LFX_ERR_ARG, "device %d out of range (0..%d)", device,
+                (n < LFX_MAX_DEVICES ? n : LFX_MAX_DEVICES) - 1);
+    std::lock_guard<std::mutex> lock(g_init_mutex);
     e = cudaSetDevice(device);
     LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     cudaDeviceProp prop;
@@ -60,8 +118,16 @@ extern "C" int lfx_init(int device) {
     void* p = nullptr;
     e = cudaGetSymbolAddress(&p, g_lfx_tables_storage);
     LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "cudaGetSymbolAddress: %s", cudaGetErrorString(e));
-    g_tables_dev = static_cast<const LfxTables*>(p);
-    g_ready = true;
+    static uint32_t hcat[3 * 256 * 4];
+    build_cat_lut(hcat);
+    e = cudaMemcpyToSymbol(g_lfx_cat_lut_storage, hcat, sizeof(hcat));
+    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "category LUT upload: %s", cudaGetErrorString(e));
+    void* pc = nullptr;
+    e = cudaGetSymbolAddress(&pc, g_lfx_cat_lut_storage);
+    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "cudaGetSymbolAddress: %s", cudaGetErrorString(e));
+    g_state[device].tables = static_cast<const LfxTables*>(p);
+    g_state[device].cat_lut = static_cast<const uint4*>(pc);
+    g_state[device].ready = true;
     t_err[0] = 0;
     return LFX_OK;
 }

@@ -21,13 +21,14 @@ constexpr int FLIP_SMEM = 32 * 1024;
 // 128-bit stores.  Pure data movement: HBM-bound.
 constexpr int FV_ROWS = 16;
 __global__ void __launch_bounds__(THREADS) k_flip_vec(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
-                                                      const int32_t* __restrict__ mode) {
+                                                      const int32_t* __restrict__ mode, const int32_t* __restrict__ sidx) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int img = blockIdx.y;
+    const int simg_i = sidx ? sidx[img] : img;   // source image of task `img` (dataset_balancer.py:116: random.choice(source_images))
     const int y0 = blockIdx.x * FV_ROWS;
     const int rows = min(FV_ROWS, H - y0);
     const int rb = W * 3, rb16 = rb >> 4;
-    const uint4* simg = reinterpret_cast<const uint4*>(src + ((size_t)img * H + y0) * rb);
+    const uint4* simg = reinterpret_cast<const uint4*>(src + ((size_t)simg_i * H + y0) * rb);
     uint8_t* dimg = dst + (size_t)img * H * rb;
     const int m = mode[img];
     uint4* s4 = reinterpret_cast<uint4*>(sm);
@@ -61,7 +62,8 @@ __global__ void __launch_bounds__(THREADS) k_flip_vec(const uint8_t* __restrict_
 
 
 __global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H, int W,
-                                                  int rows_per_block, const int32_t* __restrict__ mode) {
+                                                  int rows_per_block, const int32_t* __restrict__ mode,
+                                                  const int32_t* __restrict__ sidx) {
     extern __shared__ __align__(16) uint8_t sm[];
     const int img = blockIdx.y;
     const int y0 = blockIdx.x * rows_per_block;
@@ -70,7 +72,7 @@ __global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ sr
     const int rb = W * 3;
     uint8_t* s_in = sm;
     uint8_t* s_out = sm + ((rows_per_block * rb + 15) & ~15);
-    const uint8_t* simg = src + (size_t)img * H * rb;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * H * rb;
     uint8_t* dimg = dst + (size_t)img * H * rb;
     block_load_bytes(s_in, simg + (size_t)y0 * rb, rows * rb);
     __syncthreads();
@@ -103,7 +105,8 @@ constexpr int RT_PX = THREADS * RT_STEPS;
 
 __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                        long long dst_stride, int H, int W,
-                                                       const int32_t* __restrict__ params, int fill) {
+                                                       const int32_t* __restrict__ params, int fill,
+                                                       const int32_t* __restrict__ sidx) {
     __shared__ __align__(16) uint8_t s_px[RT_PX * 3];
     const int img = blockIdx.y;
     const int32_t* p = params + img * 8;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
     const long long npx = (long long)nw * nh;
     const long long q0 = (long long)blockIdx.x * RT_PX;
     if (q0 >= npx) return;
-    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * H * W * 3;
     uint8_t* dimg = dst + (size_t)img * dst_stride;
     const int nvalid = (int)min((long long)RT_PX, npx - q0);
     int x, y;
@@ -356,7 +359,8 @@ __device__ __forceinline__ void warp_src_rect(const double* ad, int xa, int xb, 
 template <bool TILED>
 __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
                                                           int W, const double* __restrict__ coef,
-                                                          const int32_t* __restrict__ persp, int smem_cap, int ntx) {
+                                                          const int32_t* __restrict__ persp, int smem_cap, int ntx,
+                                                          const int32_t* __restrict__ sidx, int nsrc) {
     extern __shared__ __align__(16) uint8_t s_rows[];
     __shared__ uint16_t s_queue[WB_QCAP];
     __shared__ int s_qn;
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     const bool affine = (a[6] == 0.0 && a[7] == 0.0);
     const bool is_persp = (persp[img] != 0) && !affine;   // x / 1.0 == x exactly: the divide is skipped
     const size_t npx = (size_t)H * W;
-    const uint8_t* simg = src + (size_t)img * npx * 3;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * npx * 3;
     uint8_t* dimg = dst + (size_t)img * npx * 3;
     const bool al16 = ((W * 3) % 16 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);   // every row start is 16-byte aligned
     if (threadIdx.x == 0) s_qn = 0;
@@ -430,7 +434,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
             const int rows = r1 - r0 + 1, lane = threadIdx.x & 31;
             if (al16) {
                 const int n16 = pitch >> 4;     // may run up to 15 bytes past c1: still inside the row or the next row / image
-                const uint8_t* lim = src + (size_t)gridDim.y * npx * 3;
+                const uint8_t* lim = src + (size_t)nsrc * npx * 3;
                 for (int r = threadIdx.x >> 5; r < rows; r += THREADS / 32) {
                     const uint8_t* p = g + (size_t)r * W * 3;
                     uint4* d = reinterpret_cast<uint4*>(s_rows + r * pitch);
@@ -663,7 +667,8 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos(const uint8_t* __restr
                                                           float* __restrict__ dstf, int H, int W,
                                                           const int32_t* __restrict__ box, int OH, int OW,
                                                           const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
-                                                          int kstride, const int32_t* __restrict__ toff) {
+                                                          int kstride, const int32_t* __restrict__ toff,
+                                                          const int32_t* __restrict__ sidx) {
     extern __shared__ __align__(16) uint8_t s_mid[];  // [crop_h][LZ_TW][3]
     const int img = blockIdx.y;
     const int c0 = blockIdx.x * LZ_TW;
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos(const uint8_t* __restr
     const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
     const int32_t* yb = tb + (size_t)toff[img * 4 + 2] * 2;
     const int32_t* yk = tk + (size_t)toff[img * 4 + 2] * kstride;
-    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * H * W * 3;
     const bool need_h = (cw != OW);
     const bool need_v = (ch != OH);
     // horizontal pass (or plain copy of the crop when widths match -- Pillow skips the pass)
@@ -737,7 +742,8 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
                                                                 float* __restrict__ dstf, int H, int W,
                                                                 const int32_t* __restrict__ box, int OH, int OW,
                                                                 const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
-                                                                int kstride, const int32_t* __restrict__ toff, int mrows_cap, int lz_to) {
+                                                                int kstride, const int32_t* __restrict__ toff, int mrows_cap, int lz_to,
+                                                                const int32_t* __restrict__ sidx, int nsrc) {
     extern __shared__ __align__(16) uint8_t sm_lz[];
     __shared__ float s_f255[256];   // v / 255.0f (normalize_array, image_utils.py:126-130): correctly rounded division, tabulated
     if (dstf)
@@ -757,7 +763,7 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
     const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
     const int32_t* yb = tb + (size_t)toff[img * 4 + 2] * 2;
     const int32_t* yk = tk + (size_t)toff[img * 4 + 2] * kstride;
-    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * H * W * 3;
     const bool need_h = (cw != OW), need_v = (ch != OH);
     // crop rows this strip reads
     int m0, m1;
@@ -780,7 +786,7 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
         const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);       // d[mis + i] = g[i]: both sides 16-byte aligned
         const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
         const int n16 = (mis + cwb + 15) >> 4;
-        const uint8_t* img_end = src + (size_t)gridDim.y * H * W * 3;
+        const uint8_t* img_end = src + (size_t)nsrc * H * W * 3;
         for (int i = threadIdx.x & 31; i < n16; i += 32) {
             if (reinterpret_cast<const uint8_t*>(g16 + i + 1) <= img_end)
                 reinterpret_cast<uint4*>(d)[i] = ld_stream16(g16 + i);
@@ -879,7 +885,8 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
 constexpr int DREP = 8;
 
 __global__ void __launch_bounds__(THREADS) k_distort_hist(const uint8_t* __restrict__ src, const uint8_t* __restrict__ noise,
-                                                          int32_t* __restrict__ hist, int nbytes, int bytes_per_block) {
+                                                          int32_t* __restrict__ hist, int nbytes, int bytes_per_block,
+                                                          const int32_t* __restrict__ sidx) {
     __shared__ uint32_t sh[DREP][3 * 256];
     const int img = blockIdx.y;
     const int begin = blockIdx.x * bytes_per_block;
@@ -888,7 +895,7 @@ __global__ void __launch_bounds__(THREADS) k_distort_hist(const uint8_t* __restr
     for (int i = threadIdx.x; i < DREP * 768; i += THREADS) (&sh[0][0])[i] = 0;
     __syncthreads();
     uint32_t* my = sh[(threadIdx.x >> 5) % DREP];
-    const uint8_t* s = src + (size_t)img * nbytes;
+    const uint8_t* s = src + (size_t)(sidx ? sidx[img] : img) * nbytes;
     const uint8_t* nz = noise + (size_t)img * nbytes;
     // begin is a multiple of 48 (16 pixels): 16-byte vectors keep channel phase = (j % 3)
     const bool vec = (((reinterpret_cast<uintptr_t>(s + begin) | reinterpret_cast<uintptr_t>(nz + begin)) & 15) == 0);
@@ -984,7 +991,7 @@ __global__ void k_distort_lut(int32_t* __restrict__ hist, const int32_t* __restr
 
 __global__ void __launch_bounds__(THREADS) k_distort_apply(const uint8_t* __restrict__ src, const uint8_t* __restrict__ noise,
                                                            uint8_t* __restrict__ dst, const int32_t* __restrict__ lut,
-                                                           int nbytes, int bytes_per_block) {
+                                                           int nbytes, int bytes_per_block, const int32_t* __restrict__ sidx) {
     __shared__ uint8_t sl[768];
     const int img = blockIdx.y;
     const int begin = blockIdx.x * bytes_per_block;
@@ -992,7 +999,7 @@ __global__ void __launch_bounds__(THREADS) k_distort_apply(const uint8_t* __rest
     if (begin >= end) return;
     for (int i = threadIdx.x; i < 768; i += THREADS) sl[i] = (uint8_t)lut[(size_t)img * 768 + i];
     __syncthreads();
-    const uint8_t* s = src + (size_t)img * nbytes;
+    const uint8_t* s = src + (size_t)(sidx ? sidx[img] : img) * nbytes;
     const uint8_t* nz = noise + (size_t)img * nbytes;
     uint8_t* d = dst + (size_t)img * nbytes;
     const bool vec = (((reinterpret_cast<uintptr_t>(s + begin) | reinterpret_cast<uintptr_t>(nz + begin) |
@@ -1034,7 +1041,9 @@ int chunking(int total, int unit, int B, int* per_block) {
 
 }  // namespace
 
-extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode, lfx_stream_t stream) {
+extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_t* mode, const int32_t* src_index,
+                        int n_src, lfx_stream_t stream) {
+    (void)n_src;
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && mode && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG, "flip: bad arguments");
@@ -1042,13 +1051,14 @@ extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, c
     if (rb % 16 == 0 && W % 4 == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0 &&
         (size_t)FV_ROWS * rb * 2 <= 96 * 1024) {
         const size_t smem_v = (size_t)FV_ROWS * rb * 2;
-        static size_t attr_v = 0;
+        static size_t attr_v_[LFX_MAX_DEVICES] = {0};
+        size_t& attr_v = attr_v_[lfx_dev()];
         if (smem_v > 48 * 1024 && smem_v > attr_v) {
             cudaFuncSetAttribute(k_flip_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v);
             attr_v = smem_v;
         }
         dim3 gridv(lfx_div_up(H, FV_ROWS), B);
-        k_flip_vec<<<gridv, THREADS, smem_v, (cudaStream_t)stream>>>(src, dst, H, W, mode);
+        k_flip_vec<<<gridv, THREADS, smem_v, (cudaStream_t)stream>>>(src, dst, H, W, mode, src_index);
         return lfx_check_launch("flip(vec)");
     }
     LFX_REQUIRE(W * 3 * 2 + 32 <= FLIP_SMEM, LFX_ERR_UNSUPPORTED, "flip: W > %d unsupported", (FLIP_SMEM - 32) / 6);
@@ -1059,12 +1069,13 @@ extern "C" int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, c
     if (rows >= 16) rows &= ~15;
     const size_t smem = (size_t)((rows * rb + 15) & ~15) * 2;
     dim3 grid(lfx_div_up(H, rows), B);
-    k_flip<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, rows, mode);
+    k_flip<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, rows, mode, src_index);
     return lfx_check_launch("flip");
 }
 
 extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,
-                             const int32_t* params, int fill, lfx_stream_t stream) {
+                             const int32_t* params, int fill, const int32_t* src_index, int n_src, lfx_stream_t stream) {
+    (void)n_src;
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && params && B >= 0 && H > 0 && W > 0 && B <= 65535 && dst_image_stride > 0, LFX_ERR_ARG,
@@ -1073,12 +1084,14 @@ extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image
     if (B == 0) return LFX_OK;
     const long long max_px = dst_image_stride / 3;
     dim3 grid(lfx_div_up(max_px, RT_PX), B);
-    k_rotate_nn<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill);
+    k_rotate_nn<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill, src_index);
     return lfx_check_launch("rotate_nn");
 }
 
 extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, int W, const double* coef,
-                                const int32_t* perspective, lfx_stream_t stream) {
+                                const int32_t* perspective, const int32_t* src_index, int n_src, lfx_stream_t stream) {
+    const int nsrc = src_index ? n_src : B;
+    LFX_REQUIRE(!src_index || n_src > 0, LFX_ERR_ARG, "warp_bicubic: src_index needs n_src");
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && coef && perspective && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
@@ -1086,7 +1099,8 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     if (B == 0) return LFX_OK;
     // staged source rectangle: up to 70 KB (+ 2 KB queue) so that three blocks share an SM
     const int smem = 70 * 1024;
-    static bool attr = false;
+    static bool attr_[LFX_MAX_DEVICES] = {false};
+    bool& attr = attr_[lfx_dev()];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_warp_bicubic<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(k_warp_bicubic<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1096,15 +1110,17 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     const int ntx = lfx_div_up(W, WB_COLS);
     dim3 grid(lfx_div_up(H, WB_ROWS) * ntx, B);
     if (ntx == 1)
-        k_warp_bicubic<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx);
+        k_warp_bicubic<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc);
     else
-        k_warp_bicubic<true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx);
+        k_warp_bicubic<true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc);
     return lfx_check_launch("warp_bicubic");
 }
 
 extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32, int B, int H, int W, const int32_t* box,
                                 int OH, int OW, const int32_t* tab_bounds, const int32_t* tab_kk, int kstride,
-                                const int32_t* tab_off, lfx_stream_t stream) {
+                                const int32_t* tab_off, const int32_t* src_index, int n_src, lfx_stream_t stream) {
+    const int nsrc = src_index ? n_src : B;
+    LFX_REQUIRE(!src_index || n_src > 0, LFX_ERR_ARG, "crop_lanczos: src_index needs n_src");
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && dst && box && tab_bounds && tab_kk && tab_off && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 &&
@@ -1126,7 +1142,8 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
             // taps per output sample: bounded by the whole-image resize (the crop is never larger than the image)
             const int kmax = max(lfx_lanczos_ksize(W, OW), lfx_lanczos_ksize(H, OH));
             const int vi = kmax <= 8 ? 0 : (kmax <= 10 ? 1 : (kmax <= 12 ? 2 : 3));
-            static size_t attr2[4] = {0, 0, 0, 0};
+            static size_t attr2_[LFX_MAX_DEVICES][4] = {{0}};
+            size_t* attr2 = attr2_[lfx_dev()];
             const void* fns[4] = {(const void*)k_crop_lanczos_strip<8>, (const void*)k_crop_lanczos_strip<10>,
                                   (const void*)k_crop_lanczos_strip<12>, (const void*)k_crop_lanczos_strip<16>};
             if (smem2 > 48 * 1024 && smem2 > attr2[vi]) {
@@ -1136,7 +1153,7 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
             dim3 grid2(lfx_div_up(OH, lz_to), B);
 #define LFX_LZ_LAUNCH(K) \
     k_crop_lanczos_strip<K><<<grid2, THREADS, smem2, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk, kstride, \
-                                                                         tab_off, mrows_cap, lz_to)
+                                                                         tab_off, mrows_cap, lz_to, src_index, nsrc)
             if (vi == 0) LFX_LZ_LAUNCH(8);
             else if (vi == 1) LFX_LZ_LAUNCH(10);
             else if (vi == 2) LFX_LZ_LAUNCH(12);
@@ -1148,19 +1165,21 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
     const size_t smem = (size_t)H * LZ_TW * 3;
     LFX_REQUIRE(smem <= 200 * 1024, LFX_ERR_UNSUPPORTED, "crop_lanczos: H > %d unsupported", 200 * 1024 / (LZ_TW * 3));
     if (B == 0) return LFX_OK;
-    static size_t attr = 0;
+    static size_t attr_[LFX_MAX_DEVICES] = {0};
+    size_t& attr = attr_[lfx_dev()];
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(k_crop_lanczos, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
     dim3 grid(lfx_div_up(OW, LZ_TW), B);
     k_crop_lanczos<<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
-                                                                  kstride, tab_off);
+                                                                  kstride, tab_off, src_index);
     return lfx_check_launch("crop_lanczos");
 }
 
 extern "C" int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* dst, int B, int H, int W, const int32_t* cut,
-                           int32_t* hist_ws, lfx_stream_t stream) {
+                           int32_t* hist_ws, const int32_t* src_index, int n_src, lfx_stream_t stream) {
+    (void)n_src;
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && noise && dst && cut && hist_ws && B >= 0 && H > 0 && W > 0 && B <= 65535, LFX_ERR_ARG,
@@ -1174,8 +1193,8 @@ extern "C" int lfx_distort(const uint8_t* src, const uint8_t* noise, uint8_t* ds
     int pb = 0;
     const int chunks = chunking(nbytes, 48 * 64, B, &pb);
     dim3 grid(chunks, B);
-    k_distort_hist<<<grid, THREADS, 0, st>>>(src, noise, hist_ws, nbytes, pb);
+    k_distort_hist<<<grid, THREADS, 0, st>>>(src, noise, hist_ws, nbytes, pb, src_index);
     k_distort_lut<<<lfx_div_up((long long)B * 3, 8), 256, 0, st>>>(hist_ws, cut, B);
-    k_distort_apply<<<grid, THREADS, 0, st>>>(src, noise, dst, hist_ws, nbytes, pb);
+    k_distort_apply<<<grid, THREADS, 0, st>>>(src, noise, dst, hist_ws, nbytes, pb, src_index);
     return lfx_check_launch("distort");
 }

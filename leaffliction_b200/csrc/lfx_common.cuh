@@ -7,6 +7,12 @@
 #include "../../include/leafx.h"
 
 #define LFX_NUM_SMS 148  // B200
+#define LFX_MAX_DEVICES 16
+
+// Index of the current CUDA device (0 .. LFX_MAX_DEVICES-1), -1 on error: per-device caches (function attributes,
+// LUT pointers) are arrays indexed by it.  Defined in lfx_api.cu.
+int lfx_device_slot();
+static inline int lfx_dev() { const int d = lfx_device_slot(); return d < 0 ? 0 : d; }
 
 // ---- error plumbing (defined in lfx_api.cu) ---------------------------------------------------
 void lfx_set_error(const char* fmt, ...);
@@ -31,7 +37,7 @@ struct LfxTables {
     uint16_t ctab[3072];
 };
 const LfxTables* lfx_tables();  // device pointer, valid after lfx_init (lfx_api.cu)
-const uint4* lfx_cat_lut();      // [3][256] byte-packed category flags of hist.py (lfx_core.cu), uploaded on first use; null on error
+const uint4* lfx_cat_lut();      // [3][256] byte-packed category flags of hist.py, uploaded by lfx_init (device pointer of the current device)
 
 // Shared-memory copies used by the per-pixel device functions.
 struct HsvLut {

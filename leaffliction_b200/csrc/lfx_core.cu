@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(MT, 2)
     k_core(const uint8_t* __restrict__ src, uint8_t* __restrict__ blur, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
            uint8_t* __restrict__ roi, int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3, int32_t* __restrict__ counters,
            int B, const CoreParams P, uint8_t* __restrict__ ws, const LfxTables* __restrict__ tab,
-           const uint4* __restrict__ cat_lut) {
+           const uint4* __restrict__ cat_lut, unsigned long long* __restrict__ ds_hist) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ int s_tmp[40];
     __shared__ unsigned long long s_best;
@@ -306,14 +306,20 @@ __global__ void __launch_bounds__(MT, 2)
     c.sm_geom = reinterpret_cast<uint32_t*>(sm + L.off_runs + RCAP_SMEM * 4);
     c.sm_acc = reinterpret_cast<int*>(sm + L.off_runs + RCAP_SMEM * 8);
     c.sm_ry = reinterpret_cast<uint16_t*>(sm + L.off_runs + RCAP_SMEM * 12);
+    uint32_t* blk_hist = nullptr;
     {
         uint8_t* gp = ws + 512 + (size_t)blockIdx.x * P.ws_per_block;
         auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
         c.gl_parent = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
         c.gl_geom = reinterpret_cast<uint32_t*>(gp); gp += al((size_t)M.rcap_glob * 4);
         c.gl_acc = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
-        c.gl_ry = reinterpret_cast<uint16_t*>(gp);
+        c.gl_ry = reinterpret_cast<uint16_t*>(gp); gp += al((size_t)M.rcap_glob * 2);
+        blk_hist = reinterpret_cast<uint32_t*>(gp);
     }
+    // dataset-level colour histogram: this block's images are summed into its own scratch slice (plain
+    // read-modify-write by the owning thread, bin i always belongs to thread i % MT) and merged into ds_hist once, at exit
+    if (ds_hist)
+        for (int i = threadIdx.x; i < 9 * 256; i += MT) blk_hist[i] = 0u;
     if ((size_t)NW * 12 <= (size_t)RCAP_SMEM * 14) {
         c.hp[0] = P0; c.hp[1] = T3; c.hp[2] = reinterpret_cast<uint32_t*>(c.wbase);
         for (int k = 0; k < 3; ++k) c.hp[3 + k] = reinterpret_cast<uint32_t*>(c.sm_parent) + (size_t)k * NW;
@@ -343,7 +349,7 @@ __global__ void __launch_bounds__(MT, 2)
     const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
     int* work_counter = reinterpret_cast<int*>(ws);
     const size_t img_px = (size_t)H * W;
-    const bool want_stats = hist9 || hsv3 || counters;
+    const bool want_stats = hist9 || hsv3 || counters || ds_hist;
 
     // LFX_CORE_TIMING=1 (debug): per-phase SM-clock cycles summed over images into ws[64..]
     unsigned long long* tacc = P.timing ? reinterpret_cast<unsigned long long*>(ws + 64) : nullptr;
@@ -679,6 +685,8 @@ __global__ void __launch_bounds__(MT, 2)
             __syncthreads();
             if (hist9)
                 for (int i = threadIdx.x; i < 9 * 256; i += MT) hist9[(size_t)img * 9 * 256 + i] = (int)s_hist[i];
+            if (ds_hist)
+                for (int i = threadIdx.x; i < 9 * 256; i += MT) blk_hist[i] += s_hist[i];
             if (hsv3)
                 for (int i = threadIdx.x; i < 3 * 256; i += MT) hsv3[(size_t)img * 3 * 256 + i] = (int)s_hist[9 * 256 + i];
             if (counters && threadIdx.x < 16) counters[(size_t)img * 16 + threadIdx.x] = threadIdx.x < 14 ? (int)s_cnt[threadIdx.x] : 0;
@@ -688,53 +696,23 @@ __global__ void __launch_bounds__(MT, 2)
         LFX_TICK(2)
     }
 #undef LFX_TICK
+    if (ds_hist)
+        for (int i = threadIdx.x; i < 9 * 256; i += MT) {
+            const uint32_t v = blk_hist[i];
+            if (v) atomicAdd(&ds_hist[i], (unsigned long long)v);
+        }
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
+// general path only: ds[i] += sum over images of hist9[b][i]   (grid (9, chunks), 256 threads = one bin each)
+__global__ void k_hist_accum(const int32_t* __restrict__ hist9, int B, unsigned long long* __restrict__ ds) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    unsigned long long acc = 0;
+    for (int b = blockIdx.y; b < B; b += gridDim.y) acc += (unsigned long long)(uint32_t)hist9[(size_t)b * 9 * 256 + i];
+    if (acc) atomicAdd(&ds[i], acc);
+}
+
 // ---------------------------------------------------------------- host side
-// hist.py:38-65 categories and :248-256 hue ranges as per-channel byte flags.  Field k (byte k%4 of word k/4):
-// 0 leaf (hist.py:188), 1..8 the categories, 9..13 the hue ranges.
-void build_cat_lut(uint32_t* lut /* [3][256][4] */) {
-    memset(lut, 0, 3 * 256 * 16);
-    for (int i = 0; i < 256; ++i) {
-        const int h = i, s = i, v = i;
-        const bool leaf_s = s > 10, leaf_v = v > 15 && v < 245;
-        bool fh[14], fs[14], fv[14];
-        fh[0] = true; fs[0] = leaf_s; fv[0] = leaf_v;
-        fh[1] = h >= 35 && h <= 85; fs[1] = s >= 40; fv[1] = v >= 30;
-        fh[2] = h >= 20 && h <= 40; fs[2] = s >= 25; fv[2] = v >= 30;
-        fh[3] = h >= 15 && h <= 35; fs[3] = s >= 50; fv[3] = v >= 50;
-        fh[4] = h <= 25 || h >= 160; fs[4] = s >= 30; fv[4] = v >= 20;
-        fh[5] = (h >= 160 && h <= 180) || h <= 10; fs[5] = s >= 40; fv[5] = v >= 30;
-        fh[6] = true; fs[6] = s >= 20; fv[6] = v <= 50;
-        fh[7] = true; fs[7] = s <= 30; fv[7] = v >= 200;
-        fh[8] = h >= 120 && h <= 160; fs[8] = s >= 20; fv[8] = true;
-        fh[9] = h >= 35 && h <= 85; fs[9] = true; fv[9] = true;
-        fh[10] = h >= 15 && h <= 35; fs[10] = true; fv[10] = true;
-        fh[11] = h <= 15 || h >= 160; fs[11] = true; fv[11] = true;
-        fh[12] = h >= 120 && h <= 160; fs[12] = true; fv[12] = true;
-        fh[13] = h > 85 && h < 120; fs[13] = true; fv[13] = true;
-        for (int k = 0; k < 14; ++k) {
-            const uint32_t bit = 1u << (8 * (k & 3));
-            if (fh[k]) lut[(0 * 256 + i) * 4 + (k >> 2)] |= bit;
-            if (fs[k] && leaf_s) lut[(1 * 256 + i) * 4 + (k >> 2)] |= bit;
-            if (fv[k] && leaf_v) lut[(2 * 256 + i) * 4 + (k >> 2)] |= bit;
-        }
-    }
-}
-
-uint4* g_cat_lut = nullptr;
-
-int ensure_cat_lut() {
-    if (g_cat_lut) return LFX_OK;
-    static uint32_t host[3 * 256 * 4];
-    build_cat_lut(host);
-    cudaError_t e = cudaMalloc(&g_cat_lut, sizeof(host));
-    if (e == cudaSuccess) e = cudaMemcpy(g_cat_lut, host, sizeof(host), cudaMemcpyHostToDevice);
-    LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core: category LUT upload: %s", cudaGetErrorString(e));
-    return LFX_OK;
-}
-
 // Shared-memory plan of the fused kernel; false when this shape / config takes the general path.
 bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, const int32_t* taps, CoreParams* out, int* per_sm) {
     if (W % 32 != 0 || W < 32 || H < 3 || (long long)H * W > 65536 || H > TR * TR) return false;
@@ -775,7 +753,7 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
     }
     P.lay = make_lay(H, W, RH, RW);
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2);
+    P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2) + 9 * 256 * 4;
     if (P.lay.smem_bytes > 226 * 1024) return false;
     *per_sm = max(1, min(2, (228 * 1024) / (P.lay.smem_bytes + 1024 + 1536)));  // + static shared + per-block reserve
     (void)B;
@@ -788,10 +766,8 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
 size_t lfx_core_workspace_bytes(int H, int W) {
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t rcap = (size_t)H * (W + 2);
-    return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
+    return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2) + 9 * 256 * 4) * (size_t)(2 * LFX_NUM_SMS) + 256;
 }
-
-const uint4* lfx_cat_lut() { return ensure_cat_lut() == LFX_OK ? g_cat_lut : nullptr; }
 
 extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
     if (B <= 0 || H <= 0 || W <= 0) return 0;
@@ -802,7 +778,7 @@ extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
 // negative = error.  Also serves lfx_make_mask (blur / roi / stats pointers NULL: phases A-pixel + B only).
 int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
                  int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
-                 void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist) {
     int rc;
     int32_t taps[31];
     CoreParams P;
@@ -813,13 +789,14 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     const bool morph_ok = mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1);
     if (!(aligned && morph_ok && lfx_gauss_taps(5, gaussian_sigma, taps) == LFX_OK && core_plan(B, H, W, RH, RW, cfg, taps, &P, &per_sm)))
         return 1;
-    rc = ensure_cat_lut();
-    if (rc) return rc;
+    const uint4* cat_lut = lfx_cat_lut();
+    LFX_REQUIRE(cat_lut != nullptr, LFX_ERR_CUDA, "pipeline_core: lfx_init() has not run on the current device");
     const int grid = max(1, min(B, LFX_NUM_SMS * per_sm));
     const size_t need = 512 + (size_t)P.ws_per_block * grid;
     LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
     const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
-    static int attr[2] = {0, 0};
+    static int attr_[LFX_MAX_DEVICES][2] = {{0}};
+    int* attr = attr_[lfx_dev()];
     if (P.lay.smem_bytes > attr[s256]) {
         const void* fn = s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.lay.smem_bytes);
@@ -833,10 +810,10 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     P.timing = timing ? 1 : 0;
     if (s256)
         k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                        (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+                                                        (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist);
     else
         k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                         (uint8_t*)workspace, lfx_tables(), g_cat_lut);
+                                                         (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist);
     if (timing) {  // debug only: synchronises and prints the phase split
         unsigned long long t[32] = {0};
         cudaStreamSynchronize(st);
@@ -861,14 +838,16 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
 extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi,
                                  int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H, int W, int RH, int RW,
                                  double gaussian_sigma, const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes,
-                                 lfx_stream_t stream) {
+                                 int64_t* dataset_hist9, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
     LFX_REQUIRE(B > 0 && H > 0 && W > 0, LFX_ERR_ARG, "pipeline_core: bad shape");
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned long long* ds_hist = reinterpret_cast<unsigned long long*>(dataset_hist9);
+    LFX_REQUIRE(!ds_hist || hist9, LFX_ERR_ARG, "pipeline_core: dataset_hist9 needs hist9");
     int rc = lfx_core_try(src, blur, mask, info, roi, hist9, hsv3, counters, B, H, W, RH, RW, gaussian_sigma, cfg, workspace,
-                          workspace_bytes, st);
+                          workspace_bytes, st, ds_hist);
     if (rc <= 0) return rc;
 
     // ---- general path: the stand-alone kernels back to back
@@ -890,6 +869,11 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
         rc = lfx_color_stats(src, mask, hist9, hsv3, counters, B, H, W, stream);
         if (rc) return rc;
+        if (ds_hist) {
+            k_hist_accum<<<dim3(9, 16), 256, 0, st>>>(hist9, B, ds_hist);
+            rc = lfx_check_launch("pipeline_core(dataset histogram)");
+            if (rc) return rc;
+        }
     }
     return LFX_OK;
 }

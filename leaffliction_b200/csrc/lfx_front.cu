@@ -658,7 +658,8 @@ int front_launch(const uint8_t* src, const uint8_t* aux, uint8_t* out, int32_t* 
     int32_t t15[31], t5[31];
     lfx_gauss_taps(15, 0.0, t15);
     for (int i = 0; i < 15; ++i) P.g15[i] = t15[i];
-    static size_t attr = 0;
+    static size_t attr_[LFX_MAX_DEVICES] = {0};
+    size_t& attr = attr_[lfx_dev()];
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_front, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "%s smem attr: %s", what, cudaGetErrorString(e));

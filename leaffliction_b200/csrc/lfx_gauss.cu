@@ -198,7 +198,8 @@ extern "C" int lfx_gauss_u8(const uint8_t* src, uint8_t* dst, int B, int H, int 
         else launch_fast<1, 15>(src, dst, B, H, W, taps, st);
         return lfx_check_launch("gauss_u8(fast)");
     }
-    static bool attr = false;
+    static bool attr_[LFX_MAX_DEVICES] = {false};
+    bool& attr = attr_[lfx_dev()];
     if (!attr) {
         cudaFuncSetAttribute(k_gauss, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM);
         attr = true;

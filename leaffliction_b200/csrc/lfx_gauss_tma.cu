@@ -230,7 +230,8 @@ int launch_tma(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int3
         P.kod[k] = (uint32_t)(o0 >= 0 ? taps[o0] : 0) | ((uint32_t)(o1 < K ? taps[o1] : 0) << 8);
     }
     const size_t smem = smem_for(TR);
-    static size_t attr[2] = {0, 0};
+    static size_t attr_[LFX_MAX_DEVICES][2] = {{0}};
+    size_t* attr = attr_[lfx_dev()];
     const int v = (TW == W) ? 1 : 0;
     if (smem > 40 * 1024 && smem > attr[v]) {  // static shared memory counts towards the 48 KB default limit
         cudaError_t e = v ? cudaFuncSetAttribute(k_gauss_tma<K, C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)

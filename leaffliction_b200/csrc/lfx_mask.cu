@@ -12,7 +12,7 @@
 size_t lfx_core_workspace_bytes(int H, int W);
 int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
                  int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
-                 void* workspace, size_t workspace_bytes, cudaStream_t st);
+                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist);
 
 namespace {
 
@@ -157,7 +157,8 @@ int launch(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info,
     pl.P.fp_brown = make_ellipse(pl.P.cfg.brown_morph_kernel > 0 ? pl.P.cfg.brown_morph_kernel : 3);
     pl.P.fp_search = make_ellipse(20);
     pl.P.search_is_e20 = is_ellipse20(pl.P.fp_search) ? 1 : 0;
-    static size_t attr = 0;
+    static size_t attr_[LFX_MAX_DEVICES] = {0};
+    size_t& attr = attr_[lfx_dev()];
     if (pl.smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_make_mask, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "make_mask smem attr: %s", cudaGetErrorString(e));
@@ -186,7 +187,7 @@ extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* ma
     if (!raw && src && (cfg->strategy == 0 || cfg->strategy == 1) && B > 0 && H > 0 && W > 0) {
         // threshold strategies on fused-kernel shapes: k_core without its blur / ROI / statistics phases
         const int rc = lfx_core_try(src, nullptr, mask, info, nullptr, nullptr, nullptr, nullptr, B, H, W, H, W, 1.5, cfg, workspace,
-                                    workspace_bytes, (cudaStream_t)stream);
+                                    workspace_bytes, (cudaStream_t)stream, nullptr);
         if (rc <= 0) return rc;
     }
     return launch(src, raw, mask, info, B, H, W, cfg, 0, workspace, workspace_bytes, (cudaStream_t)stream);

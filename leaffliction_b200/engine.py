@@ -26,25 +26,48 @@ class HostOutputs:
     hist9: torch.Tensor     # [B,9,256] i32
     hsv3: torch.Tensor      # [B,3,256] i32
     counters: torch.Tensor  # [B,16]    i32
+    ready: Optional[torch.cuda.Event] = None   # recorded after the last device-to-host copy of run_host
+    # the six augment outputs (TransformEngine(augment=True)): flip / skew / shear / crop / distortion [B,H,W,3] u8,
+    # rotate = pitched slab [B, stride] with image i = rotate[i, :nh*nw*3].reshape(nh, nw, 3), (nh, nw) = rotate_hw[i]
+    aug: Optional[dict] = None
+    rotate_hw: Optional[np.ndarray] = None
 
     def nbytes(self) -> int:
-        return sum(t.numel() * t.element_size() for t in
-                   (self.blur, self.mask, self.info, self.roi, self.hist9, self.hsv3, self.counters))
+        n = sum(t.numel() * t.element_size() for t in
+                (self.blur, self.mask, self.info, self.roi, self.hist9, self.hsv3, self.counters))
+        if self.aug:
+            n += sum(t.numel() for t in self.aug.values())   # the rotate slab is copied whole (pitched rows)
+        return n
+
+    @property
+    def rotate_bytes(self) -> int:
+        """bytes of the rotate outputs actually copied back (each image's own nh*nw*3)."""
+        return int((self.rotate_hw[:, 0].astype(np.int64) * self.rotate_hw[:, 1]).sum()) * 3
 
 
-def alloc_host_outputs(B, H, W, roi_size=(256, 256)) -> HostOutputs:
+def alloc_host_outputs(B, H, W, roi_size=(256, 256), augment: bool = False) -> HostOutputs:
     def pin(shape, dt):
         return torch.empty(shape, dtype=dt).pin_memory()
-    return HostOutputs(pin((B, H, W, 3), torch.uint8), pin((B, H, W), torch.uint8), pin((B, 8), torch.int32),
-                       pin((B, roi_size[0], roi_size[1], 3), torch.uint8), pin((B, 9, 256), torch.int32),
-                       pin((B, 3, 256), torch.int32), pin((B, 16), torch.int32))
+    out = HostOutputs(pin((B, H, W, 3), torch.uint8), pin((B, H, W), torch.uint8), pin((B, 8), torch.int32),
+                      pin((B, roi_size[0], roi_size[1], 3), torch.uint8), pin((B, 9, 256), torch.int32),
+                      pin((B, 3, 256), torch.int32), pin((B, 16), torch.int32))
+    if augment:
+        from .augment import AugmentSet, rotate_matrix
+        _, nw30, nh30 = rotate_matrix(30.0, W, H)
+        stride = (((nw30 + 1) * (nh30 + 1) * 3 + 15) // 16) * 16
+        out.aug = {k: pin((B, H, W, 3), torch.uint8) for k in AugmentSet.OPS if k != "rotate"}
+        out.aug["rotate"] = pin((B, stride), torch.uint8)
+        out.rotate_hw = np.zeros((B, 2), np.int32)
+    return out
 
 
 class TransformEngine:
     def __init__(self, H: int, W: int, cfg=None, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                 device: Optional[torch.device] = None, chunk: int = 512, front: Optional[str] = None):
+                 device: Optional[torch.device] = None, chunk: int = 512, front: Optional[str] = None,
+                 augment: bool = False):
         """`front`: None = the strategy in `cfg` (hsv_h / lab / hsv_s / hsv_v_dark, fused kernel where the shape allows);
-        'inclusive' (the reference's default strategy) or 'enhanced' = raw candidate by the front-end kernel first."""
+        'inclusive' (the reference's default strategy) or 'enhanced' = raw candidate by the front-end kernel first.
+        `augment`: run_host also produces the six ImageAugmenter outputs of every image (needs `seeds` per call)."""
         if not torch.cuda.is_available():
             raise RuntimeError("TransformEngine needs a CUDA device: leaffliction_b200 has no CPU fallback")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
@@ -56,17 +79,22 @@ class TransformEngine:
         if front not in (None, "inclusive", "enhanced"):
             raise ValueError(f"front must be None, 'inclusive' or 'enhanced', not {front!r}")
         self.front = front
+        self.augment = bool(augment)
+        self._aug = None
         self._bufs = None
         self._streams = None
 
     # ---- device-resident
-    def _pipeline(self, x, out):
+    def _pipeline(self, x, out, dataset_hist=None):
         if self.front:
-            return ops.pipeline_front(x, self.front, self.cfg, self.sigma, self.roi_size, out)
-        return ops.pipeline_core(x, self.cfg, self.sigma, self.roi_size, out)
+            return ops.pipeline_front(x, self.front, self.cfg, self.sigma, self.roi_size, out, dataset_hist)
+        return ops.pipeline_core(x, self.cfg, self.sigma, self.roi_size, out, dataset_hist)
 
-    def run_device(self, x: torch.Tensor, out: Optional[ops.CoreOutputs] = None) -> ops.CoreOutputs:
-        return self._pipeline(x, out)
+    def run_device(self, x: torch.Tensor, out: Optional[ops.CoreOutputs] = None,
+                   dataset_hist: Optional[torch.Tensor] = None) -> ops.CoreOutputs:
+        """`dataset_hist` (int64 [9,256], device): accumulates the batch's colour histograms (the per-rank partial of
+        the dataset-level histogram, merged across ranks by one allreduce -- SURVEY.md 8e)."""
+        return self._pipeline(x, out, dataset_hist)
 
     # ---- host buffers in, host buffers out
     def _ensure(self):
@@ -75,14 +103,26 @@ class TransformEngine:
             self._bufs = [(torch.empty((self.chunk, self.H, self.W, 3), dtype=torch.uint8, device=dev),
                            ops.alloc_core_outputs(self.chunk, self.H, self.W, self.roi_size, dev)) for _ in range(2)]
             self._streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+            if self.augment:
+                from .augment import AugmentSet
+                self._aug = [AugmentSet(self.chunk, self.H, self.W, dev) for _ in range(2)]
 
-    def run_host(self, images: torch.Tensor, out: Optional[HostOutputs] = None) -> HostOutputs:
-        """images: host uint8 [B,H,W,3] (torch tensor, ideally pinned; numpy is wrapped)."""
+    def run_host(self, images: torch.Tensor, out: Optional[HostOutputs] = None, sync: bool = True,
+                 seeds: Optional[np.ndarray] = None) -> HostOutputs:
+        """images: host uint8 [B,H,W,3] (torch tensor, ideally pinned; numpy is wrapped).  Returns when the host
+        buffers are filled (`sync=True`); with `sync=False` the copies may still be in flight and `out.ready`
+        (a CUDA event) must be synchronised before the buffers are read."""
         if isinstance(images, np.ndarray):
             images = torch.from_numpy(images)
         B = images.shape[0]
         if out is None:
-            out = alloc_host_outputs(B, self.H, self.W, self.roi_size)
+            out = alloc_host_outputs(B, self.H, self.W, self.roi_size, self.augment)
+        if self.augment:
+            if seeds is None or np.asarray(seeds).shape != (6, B):
+                raise ValueError("TransformEngine(augment=True).run_host needs seeds of shape [6, B] (one task seed per op and image)")
+            if out.aug is None:
+                raise ValueError("run_host: `out` was allocated without augment buffers")
+            seeds = np.asarray(seeds, np.int64)
         self._ensure()
         s_in, s_k, s_out = self._streams
         cur = torch.cuda.current_stream(self.device)
@@ -108,6 +148,15 @@ class TransformEngine:
                 view = ops.CoreOutputs(dev_out.blur[:n], dev_out.mask[:n], dev_out.info[:n], dev_out.roi[:n],
                                        dev_out.hist9[:n], dev_out.hsv3[:n], dev_out.counters[:n])
                 self._pipeline(xin[:n], view)
+                if self.augment:
+                    aug = self._aug[i % 2]
+                    if n == self.chunk:
+                        aug.run(xin, seeds[:, a:b])
+                    else:   # ragged tail: pad the seeds (the padded rows are computed on stale images and never copied back)
+                        sd = np.ones((6, self.chunk), np.int64)
+                        sd[:, :n] = seeds[:, a:b]
+                        aug.run(xin, sd)
+                    out.rotate_hw[a:b] = aug.rotate_hw[:n]
                 ev_k[i].record(s_k)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_k[i])
@@ -118,7 +167,17 @@ class TransformEngine:
                 out.hist9[a:b].copy_(dev_out.hist9[:n], non_blocking=True)
                 out.hsv3[a:b].copy_(dev_out.hsv3[:n], non_blocking=True)
                 out.counters[a:b].copy_(dev_out.counters[:n], non_blocking=True)
+                if self.augment:
+                    aug = self._aug[i % 2]
+                    for k in ("flip", "skew", "shear", "crop", "distortion"):
+                        out.aug[k][a:b].copy_(getattr(aug, k)[:n], non_blocking=True)
+                    out.aug["rotate"][a:b].copy_(aug.rotate[:n], non_blocking=True)
                 ev_out[i].record(s_out)
         for s in self._streams:
             cur.wait_stream(s)
+        if sync and n_chunks:
+            # the results are HOST buffers: the caller may read them as soon as this returns, so wait (on the host)
+            # for the last device-to-host copy.  sync=False returns at once with `out.ready` = the event to wait on.
+            ev_out[-1].synchronize()
+        out.ready = ev_out[-1] if n_chunks else None
         return out

@@ -253,9 +253,13 @@ def alloc_core_outputs(B, H, W, roi_size, device) -> CoreOutputs:
 
 
 def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                  out: Optional[CoreOutputs] = None) -> CoreOutputs:
+                  out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None) -> CoreOutputs:
     """Core transform profile (BASELINE config 2): 5x5 Gaussian blur + make_mask + masked ROI
-    letterbox + RGB/HSV/LAB histograms and hist.py counters, one submission."""
+    letterbox + RGB/HSV/LAB histograms and hist.py counters, one submission.
+    `dataset_hist` (int64 [9,256] on the device): the batch's histograms are added to it by the kernel."""
+    if dataset_hist is not None and (dataset_hist.dtype != torch.int64 or dataset_hist.numel() != 9 * 256
+                                     or not dataset_hist.is_contiguous() or dataset_hist.device != x.device):
+        raise ValueError("dataset_hist must be a contiguous int64 [9,256] tensor on the images' device")
     _chk_img(x)
     lib = _ready(x)
     B, H, W, _ = x.shape
@@ -264,12 +268,12 @@ def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, ro
     ws = _workspace(lib.lfx_pipeline_core_workspace(B, H, W), x.device)
     _lib.check(lib.lfx_pipeline_core(_p(x), _p(out.blur), _p(out.mask), _p(out.info), _p(out.roi), _p(out.hist9),
                                      _p(out.hsv3), _p(out.counters), B, H, W, int(roi_size[0]), int(roi_size[1]),
-                                     float(gaussian_sigma), C.byref(cfg), _p(ws), ws.numel(), _stream()))
+                                     float(gaussian_sigma), C.byref(cfg), _p(ws), ws.numel(), _p(dataset_hist), _stream()))
     return out
 
 
 def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                   out: Optional[CoreOutputs] = None) -> CoreOutputs:
+                   out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None) -> CoreOutputs:
     """The core transform profile with the reference's DEFAULT mask strategies ('inclusive', config.yaml:7, or 'enhanced'):
     raw candidate by the front-end kernel (lfx_raw_mask), then make_mask on that candidate (strategy 4), 5x5 blur, masked ROI
     letterbox and colour statistics -- the same outputs as pipeline_core."""
@@ -283,6 +287,8 @@ def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: fl
     blur = gauss_u8(x, 5, gaussian_sigma)
     roi = roi_letterbox(x, mask, info, roi_size)
     h9, h3, cn = color_stats(x, mask)
+    if dataset_hist is not None:
+        dataset_hist.view(-1).add_(h9.sum(dim=0, dtype=torch.int64).view(-1))
     if out is None:
         return CoreOutputs(blur, mask, info, roi, h9, h3, cn)
     for dst, srct in ((out.blur, blur), (out.mask, mask), (out.info, info), (out.roi, roi), (out.hist9, h9), (out.hsv3, h3), (out.counters, cn)):
@@ -291,28 +297,52 @@ def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: fl
 
 
 # --------------------------------------------------------------------------- augmentations
-def flip(x: torch.Tensor, left_right: Sequence[bool]) -> torch.Tensor:
+# Every augment op takes `src_index` (device int32 [B], optional): output i is computed from x[src_index[i]] -- the
+# balancer's random.choice(source_images) (dataset_balancer.py:116) read in place, no gather copy -- and `out`
+# (preallocated output, optional) so that hot loops neither allocate nor copy.
+def _src(x: torch.Tensor, src_index):
+    """(B, index pointer, number of source images)."""
+    if src_index is None:
+        return x.shape[0], None, x.shape[0]
+    if src_index.dtype != torch.int32 or src_index.device != x.device or not src_index.is_contiguous():
+        raise ValueError("src_index must be a contiguous int32 tensor on the images' device")
+    return int(src_index.numel()), src_index, x.shape[0]
+
+
+def _out_like(x, B, out, shape=None):
+    shape = tuple(shape) if shape is not None else (B,) + tuple(x.shape[1:])
+    if out is None:
+        return torch.empty(shape, dtype=torch.uint8, device=x.device)
+    if tuple(out.shape) != shape or out.dtype != torch.uint8 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError(f"out must be a contiguous uint8 tensor of shape {shape}")
+    return out
+
+
+def flip(x: torch.Tensor, left_right: Sequence[bool], src_index=None, out=None) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)
-    B, H, W, _ = x.shape
+    _, H, W, _c = x.shape
+    B, sidx, nsrc = _src(x, src_index)
     if isinstance(left_right, torch.Tensor):
         mode = left_right                                            # lfx_flip modes already on the device
     elif isinstance(left_right, np.ndarray) and left_right.dtype == np.int32:
         mode = _dev(left_right, np.int32, x.device)                 # already lfx_flip modes (0 = left-right)
     else:
         mode = _dev([0 if lr else 1 for lr in left_right], np.int32, x.device)
-    out = torch.empty_like(x)
-    _lib.check(lib.lfx_flip(_p(x), _p(out), B, H, W, _p(mode), _stream()))
+    out = _out_like(x, B, out)
+    _lib.check(lib.lfx_flip(_p(x), _p(out), B, H, W, _p(mode), _p(sidx), nsrc, _stream()))
     return out
 
 
-def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255, dparams: torch.Tensor = None, out: torch.Tensor = None):
+def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255, dparams: torch.Tensor = None, out: torch.Tensor = None,
+              src_index=None):
     """params[B][8] = a0..a5 (16.16 fixed point), nw, nh.  Returns (slab [B, stride] u8, stride):
     image i is slab[i, : nh_i*nw_i*3].view(nh_i, nw_i, 3).  `dparams` (the same table already on the device) and
     `out` (a slab of at least that stride) let a hot loop skip the upload and the allocation."""
     _chk_img(x)
     lib = _ready(x)
-    B, H, W, _ = x.shape
+    _, H, W, _c = x.shape
+    B, sidx, nsrc = _src(x, src_index)
     params = np.ascontiguousarray(params, np.int32).reshape(B, 8)
     max_px = int((params[:, 6].astype(np.int64) * params[:, 7]).max()) if B else 0
     stride = ((max_px * 3 + 15) // 16) * 16
@@ -320,18 +350,19 @@ def rotate_nn(x: torch.Tensor, params: np.ndarray, fill: int = 255, dparams: tor
     if slab.shape[0] != B or slab.shape[1] < max(stride, 16) or slab.dtype != torch.uint8:
         raise ValueError("rotate_nn: output slab too small")
     dp = dparams if dparams is not None else _dev(params, np.int32, x.device)
-    _lib.check(lib.lfx_rotate_nn(_p(x), _p(slab), slab.shape[1], B, H, W, _p(dp), int(fill), _stream()))
+    _lib.check(lib.lfx_rotate_nn(_p(x), _p(slab), slab.shape[1], B, H, W, _p(dp), int(fill), _p(sidx), nsrc, _stream()))
     return slab, slab.shape[1]
 
 
-def warp_bicubic(x: torch.Tensor, coeffs: np.ndarray, perspective: Sequence[bool]) -> torch.Tensor:
+def warp_bicubic(x: torch.Tensor, coeffs: np.ndarray, perspective: Sequence[bool], src_index=None, out=None) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)
-    B, H, W, _ = x.shape
+    _, H, W, _c = x.shape
+    B, sidx, nsrc = _src(x, src_index)
     dc = coeffs if isinstance(coeffs, torch.Tensor) else _dev(np.asarray(coeffs, np.float64).reshape(B, 8), np.float64, x.device)
     dpz = perspective if isinstance(perspective, torch.Tensor) else _dev(np.asarray(perspective).astype(bool).astype(np.int32), np.int32, x.device)
-    out = torch.empty_like(x)
-    _lib.check(lib.lfx_warp_bicubic(_p(x), _p(out), B, H, W, _p(dc), _p(dpz), _stream()))
+    out = _out_like(x, B, out)
+    _lib.check(lib.lfx_warp_bicubic(_p(x), _p(out), B, H, W, _p(dc), _p(dpz), _p(sidx), nsrc, _stream()))
     return out
 
 
@@ -402,35 +433,38 @@ class CropPlan:
         self.off = _dev(off, np.int32, device) if upload else None
 
 
-def crop_lanczos(x: torch.Tensor, boxes, out_hw: Tuple[int, int] = None, want_f32: bool = False, out=None, outf=None):
+def crop_lanczos(x: torch.Tensor, boxes, out_hw: Tuple[int, int] = None, want_f32: bool = False, out=None, outf=None,
+                 src_index=None):
     """img.crop(box).resize((OW,OH), LANCZOS) per image; boxes[B][4] = left, top, w, h (or a prebuilt CropPlan)."""
     _chk_img(x)
     lib = _ready(x)
-    B, H, W, _ = x.shape
+    _, H, W, _c = x.shape
+    B, sidx, nsrc = _src(x, src_index)
     plan = boxes if isinstance(boxes, CropPlan) else CropPlan(boxes, out_hw, x.device)
     OH, OW = plan.out_hw
-    if out is None:
-        out = torch.empty((B, OH, OW, 3), dtype=torch.uint8, device=x.device)
+    out = _out_like(x, B, out, (B, OH, OW, 3))
     if want_f32 and outf is None:
         outf = torch.empty((B, OH, OW, 3), dtype=torch.float32, device=x.device)
     _lib.check(lib.lfx_crop_lanczos(_p(x), _p(out), _p(outf) if want_f32 else None, B, H, W, _p(plan.box), OH, OW,
-                                    _p(plan.tb), _p(plan.tk), plan.kstride, _p(plan.off), _stream()))
+                                    _p(plan.tb), _p(plan.tk), plan.kstride, _p(plan.off), _p(sidx), nsrc, _stream()))
     return (out, outf) if want_f32 else out
 
 
-def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int]) -> torch.Tensor:
+def distort(x: torch.Tensor, noise_u8: torch.Tensor, cuts: Sequence[int], src_index=None, out=None, hist_ws=None) -> torch.Tensor:
     """(x + noise) mod 256 then per-channel autocontrast; cuts[i] = int(H*W*cutoff_i // 100)."""
     _chk_img(x)
     lib = _ready(x)
-    B, H, W, _ = x.shape
-    out = torch.empty_like(x)
-    hist = torch.empty((B, 3, 256), dtype=torch.int32, device=x.device)
+    _, H, W, _c = x.shape
+    B, sidx, nsrc = _src(x, src_index)
+    out = _out_like(x, B, out)
+    hist = hist_ws if hist_ws is not None else torch.empty((B, 3, 256), dtype=torch.int32, device=x.device)
     dcut = _dev(cuts, np.int32, x.device)
-    _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(dcut), _p(hist), _stream()))
+    _lib.check(lib.lfx_distort(_p(x), _p(noise_u8), _p(out), B, H, W, _p(dcut), _p(hist), _p(sidx), nsrc, _stream()))
     return out
 
 
-def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc: float = 0.0, dseeds: torch.Tensor = None) -> torch.Tensor:
+def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc: float = 0.0, dseeds: torch.Tensor = None,
+                        out: torch.Tensor = None) -> torch.Tensor:
     """uint8 [len(seeds), n]: row i = np.random.normal(loc, scale, n).astype(np.uint8) after np.random.seed(seeds[i]),
     generated on the GPU (NumPy legacy MT19937 + polar gauss, lfx_rng.cu).  Seed 0 means "unseeded" in the reference
     (image_augmenter.py:16: `if seed:`): those rows are drawn from the host's current np.random state."""
@@ -438,7 +472,8 @@ def legacy_normal_noise(seeds: Sequence[int], n: int, scale: float, device, loc:
         raise RuntimeError("leaffliction_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
     lib = _lib.init(device.index if device.index is not None else torch.cuda.current_device())
     seeds = np.asarray(seeds, np.int64).reshape(-1)
-    out = torch.empty((len(seeds), int(n)), dtype=torch.uint8, device=device)
+    if out is None:
+        out = torch.empty((len(seeds), int(n)), dtype=torch.uint8, device=device)
     ds = dseeds if dseeds is not None else _dev((seeds & 0xFFFFFFFF).astype(np.uint32).view(np.int32), np.int32, device)
     _lib.check(lib.lfx_legacy_normal_u8(_p(ds), _p(out), len(seeds), int(n), float(loc), float(scale), _stream()))
     for i in np.nonzero(seeds == 0)[0]:

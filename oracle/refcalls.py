@@ -41,6 +41,46 @@ def distortion(img, noise_f64, cutoff):          # image_augmenter.py:121-127
     return np.asarray(ImageOps.autocontrast(Image.fromarray(arr), cutoff=cutoff))
 
 
+AUGMENT_OPS = ("flip", "rotate", "skew", "shear", "crop", "distortion")
+
+
+def augment_task(img, op, seed):
+    """One balancing task on an array: `_process_single_transformation` (dataset_balancer.py:201-207) builds
+    ImageAugmenter(seed) (seeds `random` and `np.random` when seed is truthy, image_augmenter.py:16-18), then the
+    method draws its parameters in the reference's order and makes the Pillow / NumPy calls."""
+    import random
+    if seed:
+        random.seed(seed)
+        np.random.seed(seed)
+    h, w = img.shape[:2]
+    if op == "flip":
+        return flip(img, random.choice([True, False]))                                  # :23
+    if op == "rotate":
+        return rotate(img, random.uniform(-30, 30))                                     # :36
+    if op == "skew":
+        s = random.uniform(0.05, 0.15)                                                  # :48
+        return warp(img, [1 + s, 0, -s * w, 0, 1 + s, -s * h, 0, 0], True)
+    if op == "shear":
+        k = random.uniform(-0.2, 0.2)                                                   # :77
+        c = [1, k, 0, 0, 1, 0, 0, 0] if random.choice([True, False]) else [1, 0, 0, k, 1, 0, 0, 0]
+        return warp(img, c, False)
+    if op == "crop":
+        r = random.uniform(0.8, 0.95)                                                   # :101
+        nw, nh = int(w * r), int(h * r)
+        left = random.randint(0, w - nw)
+        top = random.randint(0, h - nh)
+        return crop_resize(img, left, top, nw, nh)
+    if op == "distortion":
+        noise = np.random.normal(0, 5, img.shape)                                       # :121
+        return distortion(img, noise, random.uniform(0, 2))                             # :126
+    raise ValueError(op)
+
+
+def augment_set(img, seeds6):
+    """The six augmentations of one image (BASELINE metric "transform+augment"), one task seed each."""
+    return [augment_task(img, op, int(sd)) for op, sd in zip(AUGMENT_OPS, seeds6)]
+
+
 def resize_normalize(img, size=224):             # sequence.py:84-88
     u8 = np.asarray(Image.fromarray(img).resize((size, size), Image.Resampling.LANCZOS))
     return u8, u8.astype(np.float32) / 255.0
@@ -142,16 +182,19 @@ def core_transform(rgb, sigma=1.5, roi_size=(256, 256)):
 def _core_worker(args):
     import cv2
     cv2.setNumThreads(1)
-    imgs = args
-    for im in imgs:
+    imgs, seeds = args
+    for i, im in enumerate(imgs):
         core_transform(im)
+        if seeds is not None:
+            augment_set(im, seeds[:, i])
     return len(imgs)
 
 
-def core_transform_pool(images, pool, nworkers):
-    """Run core_transform over `images` on `nworkers` processes (one task slice per worker,
-    the reference's own parallel model: Transformation.py:691-696)."""
+def core_transform_pool(images, pool, nworkers, seeds=None):
+    """Run core_transform (+ the six augmentations when `seeds` [6, n] is given) over `images` on `nworkers`
+    processes (one task slice per worker, the reference's own parallel model: Transformation.py:691-696,
+    dataset_balancer.py:137-141)."""
     n = len(images)
     per = (n + nworkers - 1) // nworkers
-    chunks = [images[i:i + per] for i in range(0, n, per)]
+    chunks = [(images[i:i + per], None if seeds is None else seeds[:, i:i + per]) for i in range(0, n, per)]
     return sum(pool.map(_core_worker, chunks))

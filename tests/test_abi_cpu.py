@@ -46,7 +46,7 @@ def test_no_cpu_fallback():
     assert lib.lfx_init(0) == -2                               # LFX_ERR_CUDA: no device
     buf = (C.c_uint8 * 64)()
     mode = (C.c_int32 * 1)(0)
-    rc = lib.lfx_flip(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1, 4, 4, C.cast(mode, C.c_void_p), None)
+    rc = lib.lfx_flip(C.cast(buf, C.c_void_p), C.cast(buf, C.c_void_p), 1, 4, 4, C.cast(mode, C.c_void_p), None, 0, None)
     assert rc == -2
     assert b"lfx_init" in lib.lfx_last_error()
     with pytest.raises(RuntimeError):

@@ -90,7 +90,8 @@ def test_roi_filter_dropin():
         assert bbox == transform.bounding_rect(cnt)
         assert np.array_equal(canvas, sm.roi_letterbox(masked, bbox, cfg.roi_size))
         assert vis.shape == im.shape
-    assert transform.apply_roi_filter(im, None, cfg) == (im, None, None) or True
+    canvas, vis, bbox = transform.apply_roi_filter(im, None, cfg)     # roi.py:23-24: no contour -> (rgb, None, None)
+    assert np.array_equal(canvas, im) and vis is None and bbox is None
 
 
 def test_image_augmenter_files(tmp_path):

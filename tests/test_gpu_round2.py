@@ -1,0 +1,148 @@
+"""GPU tests of the round-2 boundary additions: source-index gathers inside the augment kernels, the dataset-level
+histogram accumulated by k_core, the 6-op AugmentSet against the oracle, run_host's host-side completion."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from leaffliction_b200 import augment, engine, ops, synth
+from oracle import refcalls
+from oracle import spec_augment as sa
+from oracle import spec_mask as sm
+
+pytestmark = pytest.mark.gpu
+
+
+def up(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _seeds(n, seed=5):
+    return np.random.default_rng(seed).integers(1, 1000001, size=(6, n), dtype=np.int64)
+
+
+# ----------------------------------------------------------------------------- src_index == gather + op
+@pytest.mark.parametrize("hw", [(256, 256), (61, 97)])
+def test_src_index_equals_gather(dev, hw):
+    H, W = hw
+    rng = np.random.default_rng(11)
+    data = up(rng.integers(0, 256, (9, H, W, 3), dtype=np.uint8), dev)
+    idx = torch.tensor([8, 0, 3, 3, 7, 1, 8], dtype=torch.int32, device=dev)
+    g = data.index_select(0, idx.long())
+    B = len(idx)
+    mode = torch.tensor([0, 1, 0, 1, 1, 0, 0], dtype=torch.int32, device=dev)
+    assert torch.equal(ops.flip(data, mode, src_index=idx), ops.flip(g, mode))
+    ip, dp = augment.draw_params_batch(np.repeat(np.arange(6, dtype=np.int32), B), _seeds(B).reshape(-1), H, W)
+    ip, dp = ip.reshape(6, B, 8), dp.reshape(6, B, 8)
+    a, _ = ops.rotate_nn(data, ip[1], 255, src_index=idx)
+    b, _ = ops.rotate_nn(g, ip[1], 255)
+    for i in range(B):
+        n = int(ip[1, i, 6]) * int(ip[1, i, 7]) * 3
+        assert torch.equal(a[i, :n], b[i, :n])
+    for k in (2, 3):
+        assert torch.equal(ops.warp_bicubic(data, dp[k], ip[k, :, 0], src_index=idx), ops.warp_bicubic(g, dp[k], ip[k, :, 0]))
+    assert torch.equal(ops.crop_lanczos(data, ip[4, :, :4], (H, W), src_index=idx), ops.crop_lanczos(g, ip[4, :, :4], (H, W)))
+    noise = up(rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8), dev)
+    assert torch.equal(ops.distort(data, noise, ip[5, :, 0], src_index=idx), ops.distort(g, noise, ip[5, :, 0]))
+
+
+def test_src_index_validation(dev):
+    x = torch.zeros((2, 8, 8, 3), dtype=torch.uint8, device=dev)
+    with pytest.raises(ValueError):
+        ops.flip(x, [True], src_index=torch.zeros(1, dtype=torch.int64, device=dev))
+
+
+# ----------------------------------------------------------------------------- AugmentSet vs the reference's calls
+def test_augment_set_matches_reference_calls(dev):
+    """Every op of the 6-op set, with the task seeds of `_process_single_transformation`, against the reference's own
+    Pillow / NumPy calls on the same arrays (oracle/refcalls.augment_task) -- parameters AND pixels, bit-exact."""
+    B = 6
+    imgs = synth.leaf_batch(B, 256, 256, 77)
+    seeds = _seeds(B, 3)
+    s = augment.AugmentSet(B, 256, 256, dev).run(up(imgs, dev), seeds)
+    torch.cuda.synchronize()
+    got = {k: getattr(s, k).cpu().numpy() for k in ("flip", "skew", "shear", "crop", "distortion")}
+    slab = s.rotate.cpu().numpy()
+    for i in range(B):
+        for k, op in enumerate(refcalls.AUGMENT_OPS):
+            exp = refcalls.augment_task(imgs[i], op, int(seeds[k, i]))
+            if op == "rotate":
+                nh, nw = s.rotate_hw[i]
+                assert exp.shape == (nh, nw, 3)
+                assert np.array_equal(slab[i, : nh * nw * 3].reshape(nh, nw, 3), exp), f"rotate image {i}"
+            else:
+                assert np.array_equal(got[op][i], exp), f"{op} image {i}"
+
+
+def test_augment_set_rejects_seed_zero(dev):
+    x = torch.zeros((1, 32, 32, 3), dtype=torch.uint8, device=dev)
+    sd = np.ones((6, 1), np.int64)
+    sd[2, 0] = 0
+    with pytest.raises(ValueError):
+        augment.AugmentSet(1, 32, 32, dev).run(x, sd)
+
+
+# ----------------------------------------------------------------------------- dataset histogram inside k_core
+@pytest.mark.parametrize("hw,n", [((256, 256), 700), ((64, 96), 40), ((61, 97), 5)])
+def test_dataset_histogram_accumulates(dev, hw, n):
+    """dataset_hist += sum over the batch of hist9, by the fused kernel (more images than resident blocks) and by the
+    general path (61x97 is not a fused shape); two calls accumulate."""
+    H, W = hw
+    base = synth.leaf_batch(min(n, 24), H, W, 9)
+    x = up(np.concatenate([base] * ((n + len(base) - 1) // len(base)))[:n], dev)
+    ds = torch.zeros((9, 256), dtype=torch.int64, device=dev)
+    out = ops.pipeline_core(x, ops.mask_cfg("hsv_h"), 1.5, (H, W) if H * W < 65536 else (256, 256), dataset_hist=ds)
+    exp = out.hist9.sum(dim=0, dtype=torch.int64)
+    assert torch.equal(ds, exp)
+    ops.pipeline_core(x, ops.mask_cfg("hsv_h"), 1.5, (H, W) if H * W < 65536 else (256, 256), out, dataset_hist=ds)
+    assert torch.equal(ds, 2 * exp)
+    # and the per-image histograms themselves are the oracle's
+    m, _ = sm.make_mask(base[0], sm.Cfg(mask_strategy="hsv_h"))
+    assert np.array_equal(out.hist9[0].cpu().numpy(), sm.hist9(base[0], m))
+
+
+# ----------------------------------------------------------------------------- run_host returns filled host buffers
+def test_run_host_outputs_ready_on_return(dev):
+    """run_host used to return while the device-to-host copies were still queued.  A large batch read
+    IMMEDIATELY after the call must already hold the results (compared with the device-resident run)."""
+    B = 1536
+    base = synth.leaf_batch(32, 256, 256, 21)
+    imgs = torch.from_numpy(np.concatenate([base] * (B // 32))).pin_memory()
+    seeds = _seeds(B, 8)
+    eng = engine.TransformEngine(256, 256, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, chunk=512, augment=True)
+    host = engine.alloc_host_outputs(B, 256, 256, (256, 256), augment=True)
+    for t in (host.blur, host.mask, host.roi, host.aug["crop"], host.aug["distortion"], host.aug["rotate"]):
+        t.fill_(7)
+    eng.run_host(imgs, host, seeds=seeds)
+    snap = {k: v.clone() for k, v in (("blur", host.blur), ("mask", host.mask), ("roi", host.roi), ("hist9", host.hist9),
+                                      ("crop", host.aug["crop"]), ("dist", host.aug["distortion"]), ("rot", host.aug["rotate"]))}
+    torch.cuda.synchronize()
+    x = imgs.to(dev)
+    ref = ops.pipeline_core(x, ops.mask_cfg("hsv_h"), 1.5, (256, 256))
+    aset = augment.AugmentSet(B, 256, 256, dev).run(x, seeds)
+    torch.cuda.synchronize()
+    assert torch.equal(snap["blur"], ref.blur.cpu()) and torch.equal(snap["mask"], ref.mask.cpu())
+    assert torch.equal(snap["roi"], ref.roi.cpu()) and torch.equal(snap["hist9"], ref.hist9.cpu())
+    assert torch.equal(snap["crop"], aset.crop.cpu()) and torch.equal(snap["dist"], aset.distortion.cpu())
+    rot = aset.rotate.cpu()
+    for i in (0, 511, 512, B - 1):
+        nh, nw = host.rotate_hw[i]
+        assert tuple(aset.rotate_hw[i]) == (nh, nw)
+        assert torch.equal(snap["rot"][i, : nh * nw * 3], rot[i, : nh * nw * 3])
+
+
+def test_run_host_ragged_tail(dev):
+    B = 70
+    imgs = torch.from_numpy(synth.leaf_batch(B, 64, 64, 2))
+    seeds = _seeds(B, 9)
+    eng = engine.TransformEngine(64, 64, ops.mask_cfg("hsv_h"), 1.5, (64, 64), dev, chunk=32, augment=True)
+    host = eng.run_host(imgs, seeds=seeds)
+    x = imgs.to(dev)
+    aset = augment.AugmentSet(B, 64, 64, dev).run(x, seeds)
+    ref = ops.pipeline_core(x, ops.mask_cfg("hsv_h"), 1.5, (64, 64))
+    torch.cuda.synchronize()
+    assert torch.equal(host.mask, ref.mask.cpu()) and torch.equal(host.aug["skew"], aset.skew.cpu())
+    assert torch.equal(host.aug["flip"], aset.flip.cpu()) and torch.equal(host.aug["shear"], aset.shear.cpu())
+    with pytest.raises(ValueError):
+        eng.run_host(imgs)          # augment engine without seeds

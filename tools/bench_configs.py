@@ -1,0 +1,168 @@
+"""BASELINE.json configs[2..4] as bounded sub-benchmarks, called by bench.py (sub-records `configs.*` of its JSON line)
+and runnable alone.  Device-timed with CUDA events, max over ranks, inputs resident in HBM.
+
+  c3_balance    class-balancing augmentation of a 64 Ki-image, 8-class imbalanced dataset (36,864 augment tasks),
+                tasks sharded by index across the ranks (strong scaling), class histogram merged by one allreduce
+  c4_1024       1024x1024x3 leaves: the augment warps (skew, shear, rotate), the 5x5 / 15x15 blur and the core transform
+                profile, 256 images per GPU (weak scaling)
+  c5_resize224  augment -> Lanczos 224x224 -> /255 float32 -> DLPack (train.py's leaf_cnn input), batch 32..1024 on one GPU
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+from leaffliction_b200 import augment, balance, ops, synth  # noqa: E402
+
+
+def _timed(fn, reps=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier, images=65536):
+    S = int(x.shape[1])
+    counts = balance.synthetic_class_counts()
+    scale = images / 65536.0
+    names = [c for p in counts.values() for c in p]
+    plants = {p: list(c) for p, c in counts.items()}
+    per_class = [max(1, int(round(n * scale))) for p in counts.values() for n in p.values()]
+    labels = np.repeat(np.arange(len(names)), per_class)
+    N = len(labels)
+    base = x[:128]
+    data = base.repeat((N + 127) // 128, 1, 1, 1)[:N].contiguous()      # the dataset, resident in HBM
+    part = np.bincount(labels[list(balance.shard(N, rank, world))], minlength=len(names)).astype(np.int64)
+    merged, _ = balance.allreduce_histograms(part, device=dev)           # warm-up of the collective (communicator init)
+    t0 = time.perf_counter()
+    merged, _ = balance.allreduce_histograms(part, device=dev)           # the ONE collective of the pass
+    assert merged.tolist() == per_class
+    plan, all_tasks = balance.task_arrays_for_labels(labels, names, plants, seed=42)
+    t_plan = time.perf_counter() - t0
+    mine = all_tasks.shard(rank, world)
+    augment.augment_device(data, mine.slice(0, None, max(1, len(mine) // 256)))      # warm-up: tables, allocator pools
+    augment.augment_device(data, mine)
+    barrier()
+    passes = []
+    for _ in range(2):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        res = augment.augment_device(data, mine)
+        b.record()
+        torch.cuda.synchronize()
+        passes.append((a.elapsed_time(b), (time.perf_counter() - t0) * 1e3))
+        del res
+    dev_ms = max_over_ranks(min(p[0] for p in passes))
+    wall_ms = max_over_ranks(min(p[1] for p in passes))
+    n_tasks = len(all_tasks)
+    del data
+    torch.cuda.empty_cache()
+    return {"workload": f"class balancing: {N} images {S}x{S}x3 in HBM, 8 classes (imbalanced), {n_tasks} augment tasks "
+                        f"(6 ops, SURVEY 8d counts), tasks sharded by index over {world} GPU(s), one histogram allreduce",
+            "scaling": "strong", "n_gpus": world, "tasks": n_tasks, "value": n_tasks / (wall_ms / 1e3), "unit": "augmented images/s",
+            "ms_per_pass_wall": wall_ms, "ms_per_pass_device": dev_ms, "plan_histogram_tasklist_ms": t_plan * 1e3,
+            "algo_bytes_per_task_mean": 2.41e6 / 6, "achieved_gbs": n_tasks * (2.41e6 / 6) / (wall_ms / 1e3) / 1e9,
+            "frac": n_tasks * (2.41e6 / 6) / (wall_ms / 1e3) / 1e9 / peak / world}
+
+
+def c4_1024(dev, rank, world, peak, max_over_ranks, barrier, B=256, S=1024):
+    base = synth.leaf_batch(4, S, S, 4321 + rank)
+    x = torch.from_numpy(base).to(dev).repeat(B // 4, 1, 1, 1).contiguous()
+    N = S * S
+    rng = np.random.default_rng(7 + rank)
+    res = {}
+
+    def add(name, fn, algo_bytes, reps=3):
+        ms = max_over_ranks(_timed(fn, reps))
+        gbs = algo_bytes * B / (ms / 1e3) / 1e9
+        res[name] = {"ms": round(ms, 4), "algo_bytes_per_image": int(algo_bytes), "achieved_gbs": round(gbs, 1), "frac": round(gbs / peak, 4)}
+        return ms
+
+    out = torch.empty_like(x)
+    sk = np.array([[1 + s, 0, -s * S, 0, 1 + s, -s * S, 0, 0] for s in rng.uniform(0.05, 0.15, B)])
+    dsk, pe = torch.from_numpy(sk).to(dev), torch.ones(B, dtype=torch.int32, device=dev)
+    t_skew = add("warp_bicubic_skew", lambda: ops.warp_bicubic(x, dsk, pe, out=out), 6 * N)
+    sh = np.array([[1, k, 0, 0, 1, 0, 0, 0] if h else [1, 0, 0, k, 1, 0, 0, 0] for k, h in zip(rng.uniform(-0.2, 0.2, B), rng.random(B) < 0.5)], np.float64)
+    dsh, pa = torch.from_numpy(sh).to(dev), torch.zeros(B, dtype=torch.int32, device=dev)
+    t_shear = add("warp_bicubic_shear", lambda: ops.warp_bicubic(x, dsh, pa, out=out), 6 * N)
+    params = np.zeros((B, 8), np.int32)
+    px = 0
+    for i, a in enumerate(rng.uniform(-30, 30, B)):
+        m, nw, nh = augment.rotate_matrix(float(a), S, S)
+        params[i, :6], params[i, 6:] = augment.fixed_affine(m), (nw, nh)
+        px += nw * nh
+    slab, _ = ops.rotate_nn(x, params)
+    dpar = torch.from_numpy(params).to(dev)
+    t_rot = add("rotate_nn", lambda: ops.rotate_nn(x, params, 255, dpar, slab), 3 * N + 3 * px / B)
+    del slab
+    t_g5 = add("gauss_u8_5x5", lambda: ops.gauss_u8(x, 5, 1.5), 6 * N)
+    add("gauss_u8_15x15", lambda: ops.gauss_u8(x, 15, 0.0), 6 * N)
+    cfg = ops.mask_cfg("hsv_h")
+    co = ops.alloc_core_outputs(B, S, S, (S, S), dev)
+    add("pipeline_core", lambda: ops.pipeline_core(x, cfg, 1.5, (S, S), co), 7 * N + 3 * N + 9 * 256 * 4 + 80)
+    tot = t_skew + t_shear + t_rot + t_g5
+    by = (6 + 6 + 6) * N + 3 * N + 3 * px / B
+    del x, out, co
+    torch.cuda.empty_cache()
+    return {"workload": f"{B} x {S}x{S}x3 images per GPU in HBM: augment warps (skew, shear, rotate) + 5x5 blur, then 15x15 blur and the core profile",
+            "scaling": "weak", "n_gpus": world, "value": world * B / (tot / 1e3), "unit": "images/s (skew+shear+rotate+blur5 per image)",
+            "achieved_gbs": by * B / (tot / 1e3) / 1e9, "frac": by * B / (tot / 1e3) / 1e9 / peak, "ops": res}
+
+
+def c5_resize224(x, dev, peak):
+    S = int(x.shape[1])
+    N = S * S
+    out = {}
+    for b in (32, 128, 512, 1024):
+        if b > x.shape[0]:
+            continue
+        xs = x[:b]
+        mode = torch.zeros(b, dtype=torch.int32, device=dev)
+        fl = torch.empty_like(xs)
+        plan = ops.CropPlan(np.tile(np.array([0, 0, S, S], np.int32), (b, 1)), (224, 224), dev)
+        o8 = torch.empty((b, 224, 224, 3), dtype=torch.uint8, device=dev)
+        of = torch.empty((b, 224, 224, 3), dtype=torch.float32, device=dev)
+
+        def run():
+            ops.flip(xs, mode, out=fl)
+            ops.crop_lanczos(fl, plan, want_f32=True, out=o8, outf=of)
+            return torch.utils.dlpack.to_dlpack(of)     # zero-copy hand-over to the training framework
+
+        ms = _timed(run, reps=10, warm=2)
+        by = 3 * N + 224 * 224 * 3 * 4                  # 798,720 B per image (read u8, write f32)
+        out[str(b)] = {"ms": round(ms, 4), "images_per_s": round(b / (ms / 1e3)), "achieved_gbs": round(by * b / (ms / 1e3) / 1e9, 1),
+                       "frac": round(by * b / (ms / 1e3) / 1e9 / peak, 4)}
+    best = max(out.values(), key=lambda r: r["images_per_s"])
+    return {"workload": "augment (flip) -> Lanczos 224x224 -> /255 float32 -> DLPack, 256x256x3 inputs in HBM, batch sweep on one GPU",
+            "n_gpus": 1, "value": best["images_per_s"], "unit": "images/s (best batch)", "algo_bytes_per_image": 3 * N + 224 * 224 * 3 * 4,
+            "batches": out}
+
+
+def run_all(x, dev, rank, world, peak, max_over_ranks, barrier):
+    res = {}
+    for name, fn in (("c3_balance", lambda: c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier)),
+                     ("c4_1024", lambda: c4_1024(dev, rank, world, peak, max_over_ranks, barrier)),
+                     ("c5_resize224", lambda: c5_resize224(x, dev, peak))):
+        try:
+            res[name] = fn()
+        except Exception as e:   # noqa: BLE001 -- a sub-record must not take the headline line down with it
+            res[name] = {"error": f"{type(e).__name__}: {e}"}
+            if world > 1:
+                raise          # ranks would fall out of step on the collectives: fail loudly instead
+    return res

@@ -85,7 +85,7 @@ def main():
     dmode = torch.zeros(B, dtype=torch.int32, device=dev)
     fout = torch.empty_like(x)
     lib = ops._lib.load()
-    add("flip", lambda: ops._lib.check(lib.lfx_flip(ops._p(x), ops._p(fout), B, S, S, ops._p(dmode), ops._stream())), 6 * N)
+    add("flip", lambda: ops._lib.check(lib.lfx_flip(ops._p(x), ops._p(fout), B, S, S, ops._p(dmode), None, B, ops._stream())), 6 * N)
     angles = [rng.uniform(-30, 30) for _ in range(B)]
     params = np.zeros((B, 8), np.int32)
     out_px = 0
