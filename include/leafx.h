@@ -55,7 +55,7 @@ int lfx_flip(const uint8_t* src, uint8_t* dst, int B, int H, int W, const int32_
              const int32_t* src_index, int n_src, lfx_stream_t stream);
 
 /* ImageAugmenter.rotate (image_augmenter.py:33-42; PIL rotate NEAREST, expand, white fill :37).
- * params[B][8] = {a0,a1,a2,a3,a4,a5 (16.16 fixed point, libImaging affine_fixed), nw, nh}.
+ * params[B][8] = {a0,a1,a2,a3,a4,a5 (16.16 fixed point, libImaging affine_fixed), nw, nh}; 16-byte aligned.
  * Output image i is written at dst + i*dst_image_stride as [nh_i, nw_i, 3] contiguous;
  * pixels that map outside the source get `fill` in every channel. */
 int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image_stride, int B, int H, int W,

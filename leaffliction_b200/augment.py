@@ -495,7 +495,7 @@ class AugmentSet:
         timed("k_rotate_nn", lambda: ops.rotate_nn(x, ip[1], 255, dparams=d["rot"], out=self.rotate))
         timed("k_warp_bicubic(skew)", lambda: ops.warp_bicubic(x, d["skew_coef"], d["skew_persp"], out=self.skew))
         timed("k_warp_bicubic(shear)", lambda: ops.warp_bicubic(x, d["shear_coef"], d["shear_persp"], out=self.shear))
-        timed("k_crop_lanczos_strip", lambda: ops.crop_lanczos(x, plan, out=self.crop))
+        timed("k_lanczos_dp4a", lambda: ops.crop_lanczos(x, plan, out=self.crop))
         timed("k_distort_hist+lut+apply", lambda: ops.distort(x, self.noise.view(B, H, W, 3), d["cuts"], out=self.distortion,
                                                                hist_ws=self.hist_ws))
         return self
@@ -506,7 +506,7 @@ class AugmentSet:
         B = self.B
         rot_px = int((self.rotate_hw[:, 0].astype(np.int64) * self.rotate_hw[:, 1]).sum())
         return {"k_flip_vec": 2 * n * B, "k_rotate_nn": n * B + 3 * rot_px, "k_warp_bicubic(skew)": 2 * n * B,
-                "k_warp_bicubic(shear)": 2 * n * B, "k_crop_lanczos_strip": 3 * self.crop_px + n * B, "k_distort_hist+lut+apply": 3 * n * B,
+                "k_warp_bicubic(shear)": 2 * n * B, "k_lanczos_dp4a": 3 * self.crop_px + n * B, "k_distort_hist+lut+apply": 3 * n * B,
                 "k_legacy_normal_u8": n * B}
 
     launches_per_run = 9   # noise, flip, rotate, skew, shear, crop, distort hist / lut / apply (+ one memset node)

@@ -2,6 +2,9 @@
 // 16.16 fixed point), bicubic affine/perspective warp (Pillow fp64 semantics), crop + Lanczos
 // resize (22-bit fixed point, H pass -> u8 -> V pass) and distortion (noise + autocontrast).
 // All integer / byte work: HBM-bound, no tensor cores.
+#include <math.h>
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "lfx_common.cuh"
@@ -100,18 +103,22 @@ __global__ void __launch_bounds__(THREADS) k_flip(const uint8_t* __restrict__ sr
 // of one load instruction walk along a rotated scanline, 3 bytes apart times cos -- a handful of 32-byte sectors per
 // request (one thread owning 4 consecutive pixels spread every request over 32 sectors and the kernel was bound by
 // L1 sector throughput).  The bytes are assembled in shared memory and leave as 16-byte coalesced stores.
-constexpr int RT_STEPS = 4;
+constexpr int RT_STEPS = 8;
 constexpr int RT_PX = THREADS * RT_STEPS;
 
+// SMALL: the image has fewer than 2^31 bytes and the output fewer than 2^31 pixels -- every index is 32-bit (the common
+// case; the 64-bit instantiation exists for completeness).
+template <bool SMALL>
 __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
                                                        long long dst_stride, int H, int W,
                                                        const int32_t* __restrict__ params, int fill,
                                                        const int32_t* __restrict__ sidx) {
     __shared__ __align__(16) uint8_t s_px[RT_PX * 3];
     const int img = blockIdx.y;
-    const int32_t* p = params + img * 8;
-    const int a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3], a4 = p[4], a5 = p[5];
-    const int nw = p[6], nh = p[7];
+    const int4 pa = *reinterpret_cast<const int4*>(params + img * 8);
+    const int4 pb = *reinterpret_cast<const int4*>(params + img * 8 + 4);
+    const int a0 = pa.x, a1 = pa.y, a2 = pa.z, a3 = pa.w, a4 = pb.x, a5 = pb.y;
+    const int nw = pb.z, nh = pb.w;
     const long long npx = (long long)nw * nh;
     const long long q0 = (long long)blockIdx.x * RT_PX;
     if (q0 >= npx) return;
@@ -119,7 +126,7 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
     uint8_t* dimg = dst + (size_t)img * dst_stride;
     const int nvalid = (int)min((long long)RT_PX, npx - q0);
     int x, y;
-    if (npx < (1ll << 31)) {   // 32-bit divide in the common case
+    if (SMALL) {
         const int q = (int)q0 + threadIdx.x;
         y = q / nw;
         x = q - y * nw;
@@ -130,8 +137,8 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
     }
     // gather phase: all loads of the RT_STEPS pixels are issued before the first use (addresses of outside pixels are
     // redirected to byte 0 of the image and the fill colour is selected afterwards), then the bytes go to shared memory
-    const bool small = ((long long)H * W * 3 < (1ll << 31));
-    uint8_t r[RT_STEPS], g[RT_STEPS], b[RT_STEPS];
+    uint32_t px[RT_STEPS];   // r | g << 8 | b << 16, or the fill colour
+    const uint32_t fill3 = (uint32_t)(fill & 255) * 0x010101u;
     bool in[RT_STEPS];
 #pragma unroll
     for (int k = 0; k < RT_STEPS; ++k) {
@@ -139,12 +146,10 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
         const int xin = (a2 + y * a1 + x * a0) >> 16;
         const int yin = (a5 + y * a4 + x * a3) >> 16;
         in[k] = (unsigned)xin < (unsigned)W && (unsigned)yin < (unsigned)H;
-        const uint8_t* s = simg;
-        if (small) s += in[k] ? (yin * W + xin) * 3 : 0;
-        else s += in[k] ? ((size_t)yin * W + xin) * 3 : (size_t)0;
-        r[k] = __ldg(s);
-        g[k] = __ldg(s + 1);
-        b[k] = __ldg(s + 2);
+        const uint8_t* s;
+        if (SMALL) s = simg + (unsigned)(in[k] ? (yin * W + xin) * 3 : 0);
+        else s = simg + (in[k] ? ((size_t)yin * W + xin) * 3 : (size_t)0);
+        px[k] = (uint32_t)__ldg(s) | ((uint32_t)__ldg(s + 1) << 8) | ((uint32_t)__ldg(s + 2) << 16);
         x += THREADS;
         while (x >= nw) {
             x -= nw;
@@ -153,12 +158,11 @@ __global__ void __launch_bounds__(THREADS) k_rotate_nn(const uint8_t* __restrict
     }
 #pragma unroll
     for (int k = 0; k < RT_STEPS; ++k) {
-        const int li = k * THREADS + threadIdx.x;
-        if (li < nvalid) {
-            s_px[li * 3] = in[k] ? r[k] : (uint8_t)fill;
-            s_px[li * 3 + 1] = in[k] ? g[k] : (uint8_t)fill;
-            s_px[li * 3 + 2] = in[k] ? b[k] : (uint8_t)fill;
-        }
+        const uint32_t v = in[k] ? px[k] : fill3;
+        uint8_t* o = s_px + (k * THREADS + threadIdx.x) * 3;   // (the tail past nvalid is written too: it is never stored)
+        o[0] = (uint8_t)v;
+        o[1] = (uint8_t)(v >> 8);
+        o[2] = (uint8_t)(v >> 16);
     }
     __syncthreads();
     uint8_t* d = dimg + q0 * 3;
@@ -879,6 +883,241 @@ __global__ void __launch_bounds__(THREADS) k_crop_lanczos_strip(const uint8_t* _
     }
 }
 
+// ---- dp4a version (the default): the same strip decomposition, both passes on the integer dot-product pipe.
+// A 22-bit coefficient splits exactly as k = k0 + 256 k1 + 65536 k2 (k0, k1 unsigned bytes, k2 a signed byte: k <= 2^22),
+// so sum(px * k) = dp4a(px, k0) + 256 dp4a(px, k1) + 65536 dp4a(px, k2) over four taps per instruction (IDP.4A, exact in
+// int32: |sum| < 2^31).  Four consecutive taps of one channel must share a 32-bit word, so
+//   (1) the crop rows are staged raw (16-byte loads), then de-interleaved in shared memory into R / G / B planes;
+//   (2) horizontal pass: one output column per thread walking down the rows; the <= 4*NG taps of the column are an
+//       unaligned byte window of the plane row = NG+1 aligned words + NG funnel shifts; coefficient words in registers;
+//       four consecutive rows of a column are packed into one word of the intermediate M4[row quad][byte column];
+//   (3) vertical pass: a thread owns four adjacent byte columns (one 128-bit load per row quad), the window over the rows
+//       is again NG+1 words + NG funnel shifts (shift and coefficients are per output row: broadcast loads), the four
+//       results leave as one 32-bit store (plus a float4 for the /255 output).
+// Identity passes (Pillow skips a pass whose size does not change) are the coefficient 2^22 on one tap: exact.
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // unsigned bytes x signed bytes
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+constexpr int LZ4_TO = 32;
+
+template <int NG>
+__global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                             float* __restrict__ dstf, int H, int W,
+                                                             const int32_t* __restrict__ box, int OH, int OW,
+                                                             const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
+                                                             int kstride, const int32_t* __restrict__ toff, int mrows_cap,
+                                                             const int32_t* __restrict__ sidx, int nsrc) {
+    extern __shared__ __align__(16) uint8_t sm_lz[];
+    __shared__ float s_f255[256];   // v / 255.0f (normalize_array, image_utils.py:126-130): correctly rounded, tabulated
+    constexpr int VKS = (3 * NG + 3) & ~3;                 // coefficient words per output row (padded to 16 bytes)
+    const int OWB = OW * 3;
+    const int raw_pitch = ((W * 3 + 15) & ~15) + 32;
+    const int mrows4 = (mrows_cap + 3) & ~3;
+    const int nquad = mrows4 / 4 + NG + 1;                 // row quads of M4 (the window of the last row may run past the strip)
+    const int ppitch = ((W + 3) & ~3) + 4 * NG + 4;        // plane row pitch in bytes (taps past the crop read padding)
+    const size_t raw_bytes = (size_t)mrows_cap * raw_pitch, m4_bytes = (size_t)nquad * OWB * 4;
+    const size_t uni = ((raw_bytes > m4_bytes ? raw_bytes : m4_bytes) + 15) & ~(size_t)15;
+    uint8_t* s_raw = sm_lz;                                // [mrows_cap][raw_pitch]        (dead after the de-interleave)
+    uint32_t* s_m4 = reinterpret_cast<uint32_t*>(sm_lz);   // [nquad][OWB] words            (aliases s_raw)
+    uint8_t* s_pl = sm_lz + uni;                           // [3][mrows4][ppitch]
+    uint32_t* s_vk = reinterpret_cast<uint32_t*>(s_pl + (((size_t)3 * mrows4 * ppitch + 15) & ~(size_t)15));  // [LZ4_TO][VKS]
+    int32_t* s_vb = reinterpret_cast<int32_t*>(s_vk + LZ4_TO * VKS);                                          // [LZ4_TO]
+    int32_t* s_mis = s_vb + LZ4_TO;                                                                           // [mrows_cap]
+
+    if (dstf)
+        for (int i = threadIdx.x; i < 256; i += THREADS) s_f255[i] = (float)i / 255.0f;
+    const int img = blockIdx.y;
+    const int o0 = blockIdx.x * LZ4_TO;
+    const int nrow = min(LZ4_TO, OH - o0);
+    const int left = box[img * 4], top = box[img * 4 + 1], cw = box[img * 4 + 2], ch = box[img * 4 + 3];
+    const int32_t* xb = tb + (size_t)toff[img * 4 + 0] * 2;
+    const int32_t* xk = tk + (size_t)toff[img * 4 + 0] * kstride;
+    const int32_t* yb = tb + (size_t)toff[img * 4 + 2] * 2;
+    const int32_t* yk = tk + (size_t)toff[img * 4 + 2] * kstride;
+    const uint8_t* simg = src + (size_t)(sidx ? sidx[img] : img) * H * W * 3;
+    const bool need_h = (cw != OW), need_v = (ch != OH);
+    const int ktaps = min(4 * NG, kstride);
+
+    // coefficient words of one table row: taps 4g..4g+3 of slice s in word [s * NG + g]
+    auto split = [&](const int32_t* k, int cnt, uint32_t* out) {
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int tt = 4 * g + t;
+                const int kv = (tt < ktaps && tt < cnt) ? k[tt] : 0;
+                w0 |= (uint32_t)(kv & 255) << (8 * t);
+                w1 |= (uint32_t)((kv >> 8) & 255) << (8 * t);
+                w2 |= (uint32_t)((kv >> 16) & 255) << (8 * t);
+            }
+            out[g] = w0; out[NG + g] = w1; out[2 * NG + g] = w2;
+        }
+    };
+
+    // ---- crop rows this strip reads + the vertical coefficient words of its output rows
+    int m0, m1;
+    if (need_v) {
+        m0 = yb[o0 * 2];
+        m1 = yb[(o0 + nrow - 1) * 2] + yb[(o0 + nrow - 1) * 2 + 1];
+    } else {
+        m0 = o0;
+        m1 = o0 + nrow;
+    }
+    const int mrows = m1 - m0;   // <= mrows_cap by construction of the launch
+    if (threadIdx.x < nrow) {
+        const int r = threadIdx.x;
+        uint32_t kw[3 * NG];
+        if (need_v) {
+            split(yk + (size_t)(o0 + r) * kstride, yb[(o0 + r) * 2 + 1], kw);
+            s_vb[r] = yb[(o0 + r) * 2] - m0;
+        } else {
+            const int32_t one = 1 << 22;
+            split(&one, 1, kw);
+            s_vb[r] = r;
+        }
+#pragma unroll
+        for (int i = 0; i < 3 * NG; ++i) s_vk[r * VKS + i] = kw[i];
+    }
+    // ---- (1a) stage the crop rows raw: 16-byte loads from the aligned span
+    const int cwb = cw * 3;
+    const size_t g0 = ((size_t)(top + m0) * W + left) * 3;
+    const uint8_t* img_end = src + (size_t)nsrc * H * W * 3;
+    for (int r = threadIdx.x >> 5; r < mrows; r += THREADS / 32) {
+        const uint8_t* g = simg + g0 + (size_t)r * W * 3;
+        uint8_t* d = s_raw + (size_t)r * raw_pitch;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);       // d[mis + i] = g[i]: both sides 16-byte aligned
+        const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
+        const int n16 = (mis + cwb + 15) >> 4;
+        for (int i = threadIdx.x & 31; i < n16; i += 32) {
+            if (reinterpret_cast<const uint8_t*>(g16 + i + 1) <= img_end)
+                reinterpret_cast<uint4*>(d)[i] = ld_stream16(g16 + i);
+            else
+                for (int b = 0; b < 16; ++b) {
+                    const uint8_t* q = reinterpret_cast<const uint8_t*>(g16 + i) + b;
+                    d[i * 16 + b] = q < img_end ? *q : 0;
+                }
+        }
+        if ((threadIdx.x & 31) == 0) s_mis[r] = mis;
+    }
+    __syncthreads();
+    // ---- (1b) de-interleave: 4 pixels (12 bytes at an arbitrary byte offset) -> one word of each plane
+    {
+        const int ng4 = (cw + 3) >> 2;
+        const int plane = mrows4 * ppitch;
+        for (int it = threadIdx.x; it < mrows * ng4; it += THREADS) {
+            const int r = it / ng4, g = it - r * ng4;
+            const int o = s_mis[r] + 12 * g;
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (size_t)r * raw_pitch) + (o >> 2);
+            const int sh = (o & 3) * 8;
+            const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+            const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
+            // w0 = R0 G0 B0 R1, w1 = G1 B1 R2 G2, w2 = B2 R3 G3 B3
+            uint8_t* d = s_pl + (size_t)r * ppitch + 4 * g;
+            *reinterpret_cast<uint32_t*>(d) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+            *reinterpret_cast<uint32_t*>(d + plane) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+            *reinterpret_cast<uint32_t*>(d + 2 * plane) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
+        }
+    }
+    __syncthreads();
+    // ---- (2) horizontal pass -> M4
+    for (int oc = threadIdx.x; oc < OW; oc += THREADS) {
+        uint32_t kw[3 * NG];
+        int xmin;
+        if (need_h) {
+            xmin = xb[oc * 2];
+            split(xk + (size_t)oc * kstride, xb[oc * 2 + 1], kw);
+        } else {
+            const int32_t one = 1 << 22;
+            xmin = oc;
+            split(&one, 1, kw);
+        }
+        const int sh = (xmin & 3) * 8;
+        const uint8_t* pbase = s_pl + (xmin & ~3);
+        const int plane = mrows4 * ppitch;
+        uint32_t* mo = s_m4 + oc * 3;
+        for (int rq = 0; rq < (mrows + 3) >> 2; ++rq, mo += OWB) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uint32_t outw = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t* p = reinterpret_cast<const uint32_t*>(pbase + c * plane + (rq * 4 + i) * ppitch);
+                    uint32_t w[NG + 1];
+#pragma unroll
+                    for (int g = 0; g <= NG; ++g) w[g] = p[g];
+                    int a0 = 1 << 21, a1 = 0, a2 = 0;
+#pragma unroll
+                    for (int g = 0; g < NG; ++g) {
+                        const uint32_t a = __funnelshift_r(w[g], w[g + 1], sh);
+                        a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
+                        a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
+                        a2 = dp4a_us(a, kw[2 * NG + g], a2);
+                    }
+                    const int v = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
+                    outw |= (uint32_t)min(255, max(0, v)) << (8 * i);
+                }
+                mo[c] = outw;
+            }
+        }
+    }
+    __syncthreads();
+    // ---- (3) vertical pass: 4 byte columns per thread
+    {
+        const int G = OWB >> 2;   // column groups per row
+        uint8_t* dimg = dst + ((size_t)img * OH + o0) * OWB;
+        float* fimg = dstf ? dstf + ((size_t)img * OH + o0) * OWB : nullptr;
+        int r = 0, cg = threadIdx.x;
+        for (int it = threadIdx.x; it < nrow * G; it += THREADS, cg += THREADS) {
+            while (cg >= G) {
+                cg -= G;
+                ++r;
+            }
+            const int b = s_vb[r];
+            const int sh = (b & 3) * 8;
+            const uint4* kq = reinterpret_cast<const uint4*>(s_vk + r * VKS);
+            uint32_t kw[VKS];
+#pragma unroll
+            for (int i = 0; i < VKS / 4; ++i) {
+                const uint4 q = kq[i];
+                kw[4 * i] = q.x; kw[4 * i + 1] = q.y; kw[4 * i + 2] = q.z; kw[4 * i + 3] = q.w;
+            }
+            const uint4* mq = reinterpret_cast<const uint4*>(s_m4 + (size_t)(b >> 2) * OWB) + cg;
+            uint4 w[NG + 1];
+#pragma unroll
+            for (int g = 0; g <= NG; ++g) w[g] = mq[(size_t)g * G];
+            uint32_t outw = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int a0 = 1 << 21, a1 = 0, a2 = 0;
+#pragma unroll
+                for (int g = 0; g < NG; ++g) {
+                    const uint32_t lo = j == 0 ? w[g].x : j == 1 ? w[g].y : j == 2 ? w[g].z : w[g].w;
+                    const uint32_t hi = j == 0 ? w[g + 1].x : j == 1 ? w[g + 1].y : j == 2 ? w[g + 1].z : w[g + 1].w;
+                    const uint32_t a = __funnelshift_r(lo, hi, sh);
+                    a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
+                    a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
+                    a2 = dp4a_us(a, kw[2 * NG + g], a2);
+                }
+                const int v = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
+                outw |= (uint32_t)min(255, max(0, v)) << (8 * j);
+            }
+            reinterpret_cast<uint32_t*>(dimg)[(size_t)r * G + cg] = outw;
+            if (fimg) {
+                float4 f;
+                f.x = s_f255[outw & 0xFFu];
+                f.y = s_f255[(outw >> 8) & 0xFFu];
+                f.z = s_f255[(outw >> 16) & 0xFFu];
+                f.w = s_f255[outw >> 24];
+                __stcs(reinterpret_cast<float4*>(fimg) + (size_t)r * G + cg, f);
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------ distortion
 // (1) histogram of x = src + noise (mod 256) per image/channel, (2) autocontrast LUT per
 // image/channel (ImageOps.autocontrast), (3) dst = lut[x].
@@ -1084,7 +1323,11 @@ extern "C" int lfx_rotate_nn(const uint8_t* src, uint8_t* dst, int64_t dst_image
     if (B == 0) return LFX_OK;
     const long long max_px = dst_image_stride / 3;
     dim3 grid(lfx_div_up(max_px, RT_PX), B);
-    k_rotate_nn<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill, src_index);
+    LFX_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0, LFX_ERR_ARG, "rotate_nn: params must be 16-byte aligned");
+    if ((long long)H * W * 3 < (1ll << 31) && max_px < (1ll << 31) - RT_PX)
+        k_rotate_nn<true><<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill, src_index);
+    else
+        k_rotate_nn<false><<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, dst, dst_image_stride, H, W, params, fill, src_index);
     return lfx_check_launch("rotate_nn");
 }
 
@@ -1126,6 +1369,43 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
     LFX_REQUIRE(src && dst && box && tab_bounds && tab_kk && tab_off && B >= 0 && H > 0 && W > 0 && OH > 0 && OW > 0 &&
                     kstride > 0 && B <= 65535,
                 LFX_ERR_ARG, "crop_lanczos: bad arguments");
+    // dp4a kernel: row strips, both passes on IDP.4A (every upscale and downscales up to 2x: <= 12 taps per axis)
+    {
+        auto taps_bound = [](int in, int out) {   // max taps of one output sample: ceil(2 * support), support = 3 * max(in / out, 1)
+            const double sc = (double)in / out;
+            return (int)ceil(6.0 * (sc < 1.0 ? 1.0 : sc) - 1e-9);
+        };
+        const int kb = max(taps_bound(W, OW), taps_bound(H, OH));
+        const int NG = kb <= 8 ? 2 : (kb <= 12 ? 3 : 0);
+        const int mrows_cap = (int)(((long long)LZ4_TO * H + OH - 1) / OH) + 4 * NG + 2;
+        const int mrows4 = (mrows_cap + 3) & ~3, nquad = mrows4 / 4 + NG + 1;
+        const int raw_pitch = ((W * 3 + 15) & ~15) + 32, ppitch = ((W + 3) & ~3) + 4 * NG + 4;
+        const int VKS = (3 * NG + 3) & ~3;
+        const size_t raw_bytes = (size_t)mrows_cap * raw_pitch, m4_bytes = (size_t)nquad * OW * 3 * 4;
+        const size_t smem4 = (((raw_bytes > m4_bytes ? raw_bytes : m4_bytes) + 15) & ~(size_t)15) +
+                             (((size_t)3 * mrows4 * ppitch + 15) & ~(size_t)15) + (size_t)LZ4_TO * VKS * 4 + LZ4_TO * 4 + (size_t)mrows_cap * 4 + 16;
+        static const bool no_dp4a = getenv("LFX_LANCZOS_OLD") != nullptr;   // debug: compare against the previous kernel
+        const bool ok4 = NG != 0 && !no_dp4a && (OW % 4 == 0) && smem4 <= 110 * 1024 && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0) &&
+                         (!dst_f32 || (reinterpret_cast<uintptr_t>(dst_f32) & 15) == 0);
+        if (ok4) {
+            static size_t attr4_[LFX_MAX_DEVICES][2] = {{0}};
+            size_t* attr4 = attr4_[lfx_dev()];
+            const void* fn = NG == 2 ? (const void*)k_lanczos_dp4a<2> : (const void*)k_lanczos_dp4a<3>;
+            if (smem4 > 48 * 1024 && smem4 > attr4[NG - 2]) {
+                cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4);
+                LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "crop_lanczos smem attr: %s", cudaGetErrorString(e));
+                attr4[NG - 2] = smem4;
+            }
+            dim3 grid4(lfx_div_up(OH, LZ4_TO), B);
+            if (NG == 2)
+                k_lanczos_dp4a<2><<<grid4, THREADS, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
+                                                                                 kstride, tab_off, mrows_cap, src_index, nsrc);
+            else
+                k_lanczos_dp4a<3><<<grid4, THREADS, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
+                                                                                 kstride, tab_off, mrows_cap, src_index, nsrc);
+            return lfx_check_launch("crop_lanczos(dp4a)");
+        }
+    }
     // strip kernel: full-width row strips, taps in registers (every upscale and mild downscale: <= 8 taps per axis)
     {
         int lz_to = LZ_TO, mrows_cap = 0;

@@ -14,7 +14,7 @@
 // Arithmetic.  The reference is fp64 (explicit round-to-nearest without FMA contraction: the host libraries are built
 // without FMA); CUDA's log() is within 1 ulp of glibc's, which can move a result only when 5*g lies within an ulp of
 // an integer (probability ~1e-15 per sample).  An fp32 evaluation on the fast units decides first.  With u = 2^-24:
-// x1, x2 carry 2u, r2 5u, L = __logf(r2) an absolute 5u + 4e-7 (its bound on [0.5, 2]; 2 ulp elsewhere), the reciprocal
+// x1, x2 carry 2.25u (the fast path drops the low 26 bits of each double: < 2^-26), r2 5u, L = __logf(r2) an absolute 5u + 4e-7 (its bound on [0.5, 2]; 2 ulp elsewhere), the reciprocal
 // and the reciprocal square root a few ulp, and g = scale * x * sqrt(-2L / r2) the absolute error
 // |g| (0.5 dL/|L| + ~12u).  A value with |g| >= 0.5 has |L| >= 0.005 (x^2 <= r2), so for |scale| <= 8 the error stays
 // below 1.5e-4; below 0.5 the byte is 0 whatever the error.  Attempts whose fp32 radius lies within 1e-6 of 1 (the
@@ -121,17 +121,24 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
             if (t < 156) {
                 slow[c] = !fast;
                 if (fast) {
-                    const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * t);
-                    const uint32_t a = mt_temper(q.x) >> 5, bq = mt_temper(q.y) >> 6, cc = mt_temper(q.z) >> 5, d = mt_temper(q.w) >> 6;
-                    const float x1 = fmaf((float)bq, 0x1p-52f, (float)((int)a - (1 << 26)) * 0x1p-26f);
-                    const float x2 = fmaf((float)d, 0x1p-52f, (float)((int)cc - (1 << 26)) * 0x1p-26f);
+                    // the low words (26 of the 53 bits of each double) move x by less than 2^-26 = u/4: the fast path
+                    // leaves them untempered (budgeted above); the fp64 re-evaluation tempers all four words
+                    const uint2 q = *reinterpret_cast<const uint2*>(mt + 4 * t);
+                    const uint2 q2 = *reinterpret_cast<const uint2*>(mt + 4 * t + 2);
+                    const uint32_t a = mt_temper(q.x) >> 5, cc = mt_temper(q2.x) >> 5;
+                    const float x1 = (float)((int)a - (1 << 26)) * 0x1p-26f;
+                    const float x2 = (float)((int)cc - (1 << 26)) * 0x1p-26f;
                     const float r2 = fmaf(x1, x1, x2 * x2);
                     if (fabsf(r2 - 1.f) <= 1e-6f) {
                         slow[c] = true;
-                    } else if (r2 < 1.f && r2 != 0.f) {
+                    } else if (r2 < 1e-8f) {
+                        slow[c] = true;   // (2^-54 of the attempts) the dropped low words decide whether r2 is zero
+                    } else if (r2 < 1.f) {
                         // fast units (MUFU lg2 / rcp / rsq: a few ulp each, |L| abs 4e-7 near 1) -- inside the error budget above
-                        const float q = -2.f * __logf(r2) * __frcp_rn(r2);
-                        const float f = q * rsqrtf(q);
+                        const float q = __fdividef(-2.f * __logf(r2), r2);
+                        float rs;
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(q));
+                        const float f = q * rs;
                         const bool k0 = byte32(fscale * (f * x2), o0[c]), k1 = byte32(fscale * (f * x1), o1[c]);
                         acc[c] = true;
                         slow[c] = !(k0 && k1);
