@@ -902,17 +902,27 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {   // uns
 }
 
 constexpr int LZ4_TO = 32;
+constexpr int LZ4_T = 512;   // threads: 16 warps per block, two blocks per SM
+
+// clamp(v0..v3, 0, 255) packed into one word (v0 = byte 0): two saturating pack instructions (I2IP)
+__device__ __forceinline__ uint32_t pack_sat_u8x4(int v0, int v1, int v2, int v3) {
+    uint32_t hi, d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(v3), "r"(v2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v1), "r"(v0), "r"(hi));
+    return d;
+}
 
 template <int NG>
-__global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                             float* __restrict__ dstf, int H, int W,
-                                                             const int32_t* __restrict__ box, int OH, int OW,
-                                                             const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
-                                                             int kstride, const int32_t* __restrict__ toff, int mrows_cap,
-                                                             const int32_t* __restrict__ sidx, int nsrc) {
+__global__ void __launch_bounds__(LZ4_T, 2) k_lanczos_dp4a(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
+                                                           float* __restrict__ dstf, int H, int W,
+                                                           const int32_t* __restrict__ box, int OH, int OW,
+                                                           const int32_t* __restrict__ tb, const int32_t* __restrict__ tk,
+                                                           int kstride, const int32_t* __restrict__ toff, int mrows_cap,
+                                                           const int32_t* __restrict__ sidx, int nsrc) {
     extern __shared__ __align__(16) uint8_t sm_lz[];
     __shared__ float s_f255[256];   // v / 255.0f (normalize_array, image_utils.py:126-130): correctly rounded, tabulated
     constexpr int VKS = (3 * NG + 3) & ~3;                 // coefficient words per output row (padded to 16 bytes)
+    constexpr int NWARP = LZ4_T / 32;
     const int OWB = OW * 3;
     const int raw_pitch = ((W * 3 + 15) & ~15) + 32;
     const int mrows4 = (mrows_cap + 3) & ~3;
@@ -927,8 +937,9 @@ __global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __re
     int32_t* s_vb = reinterpret_cast<int32_t*>(s_vk + LZ4_TO * VKS);                                          // [LZ4_TO]
     int32_t* s_mis = s_vb + LZ4_TO;                                                                           // [mrows_cap]
 
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     if (dstf)
-        for (int i = threadIdx.x; i < 256; i += THREADS) s_f255[i] = (float)i / 255.0f;
+        for (int i = threadIdx.x; i < 256; i += LZ4_T) s_f255[i] = (float)i / 255.0f;
     const int img = blockIdx.y;
     const int o0 = blockIdx.x * LZ4_TO;
     const int nrow = min(LZ4_TO, OH - o0);
@@ -968,7 +979,28 @@ __global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __re
         m1 = o0 + nrow;
     }
     const int mrows = m1 - m0;   // <= mrows_cap by construction of the launch
-    if (threadIdx.x < nrow) {
+    // ---- (1a) stage the crop rows raw: 16-byte loads from the aligned span
+    const int cwb = cw * 3;
+    const size_t g0 = ((size_t)(top + m0) * W + left) * 3;
+    const uint8_t* img_end = src + (size_t)nsrc * H * W * 3;
+    for (int r = wid; r < mrows; r += NWARP) {
+        const uint8_t* g = simg + g0 + (size_t)r * W * 3;
+        uint8_t* d = s_raw + (size_t)r * raw_pitch;
+        const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);       // d[mis + i] = g[i]: both sides 16-byte aligned
+        const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
+        const int n16 = (mis + cwb + 15) >> 4;
+        for (int i = lane; i < n16; i += 32) {
+            if (reinterpret_cast<const uint8_t*>(g16 + i + 1) <= img_end)
+                reinterpret_cast<uint4*>(d)[i] = ld_stream16(g16 + i);
+            else
+                for (int b = 0; b < 16; ++b) {
+                    const uint8_t* q = reinterpret_cast<const uint8_t*>(g16 + i) + b;
+                    d[i * 16 + b] = q < img_end ? *q : 0;
+                }
+        }
+        if (lane == 0) s_mis[r] = mis;
+    }
+    if (threadIdx.x < nrow) {   // (after the loads are in flight)
         const int r = threadIdx.x;
         uint32_t kw[3 * NG];
         if (need_v) {
@@ -982,100 +1014,85 @@ __global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __re
 #pragma unroll
         for (int i = 0; i < 3 * NG; ++i) s_vk[r * VKS + i] = kw[i];
     }
-    // ---- (1a) stage the crop rows raw: 16-byte loads from the aligned span
-    const int cwb = cw * 3;
-    const size_t g0 = ((size_t)(top + m0) * W + left) * 3;
-    const uint8_t* img_end = src + (size_t)nsrc * H * W * 3;
-    for (int r = threadIdx.x >> 5; r < mrows; r += THREADS / 32) {
-        const uint8_t* g = simg + g0 + (size_t)r * W * 3;
-        uint8_t* d = s_raw + (size_t)r * raw_pitch;
-        const int mis = (int)(reinterpret_cast<uintptr_t>(g) & 15);       // d[mis + i] = g[i]: both sides 16-byte aligned
-        const uint4* g16 = reinterpret_cast<const uint4*>(g - mis);
-        const int n16 = (mis + cwb + 15) >> 4;
-        for (int i = threadIdx.x & 31; i < n16; i += 32) {
-            if (reinterpret_cast<const uint8_t*>(g16 + i + 1) <= img_end)
-                reinterpret_cast<uint4*>(d)[i] = ld_stream16(g16 + i);
-            else
-                for (int b = 0; b < 16; ++b) {
-                    const uint8_t* q = reinterpret_cast<const uint8_t*>(g16 + i) + b;
-                    d[i * 16 + b] = q < img_end ? *q : 0;
-                }
-        }
-        if ((threadIdx.x & 31) == 0) s_mis[r] = mis;
-    }
     __syncthreads();
-    // ---- (1b) de-interleave: 4 pixels (12 bytes at an arbitrary byte offset) -> one word of each plane
+    // ---- (1b) de-interleave: 4 pixels (12 bytes at an arbitrary byte offset) -> one word of each plane; a warp per row
     {
         const int ng4 = (cw + 3) >> 2;
         const int plane = mrows4 * ppitch;
-        for (int it = threadIdx.x; it < mrows * ng4; it += THREADS) {
-            const int r = it / ng4, g = it - r * ng4;
-            const int o = s_mis[r] + 12 * g;
-            const uint32_t* q = reinterpret_cast<const uint32_t*>(s_raw + (size_t)r * raw_pitch) + (o >> 2);
-            const int sh = (o & 3) * 8;
-            const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
-            const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
-            // w0 = R0 G0 B0 R1, w1 = G1 B1 R2 G2, w2 = B2 R3 G3 B3
-            uint8_t* d = s_pl + (size_t)r * ppitch + 4 * g;
-            *reinterpret_cast<uint32_t*>(d) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
-            *reinterpret_cast<uint32_t*>(d + plane) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
-            *reinterpret_cast<uint32_t*>(d + 2 * plane) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
-        }
-    }
-    __syncthreads();
-    // ---- (2) horizontal pass -> M4
-    for (int oc = threadIdx.x; oc < OW; oc += THREADS) {
-        uint32_t kw[3 * NG];
-        int xmin;
-        if (need_h) {
-            xmin = xb[oc * 2];
-            split(xk + (size_t)oc * kstride, xb[oc * 2 + 1], kw);
-        } else {
-            const int32_t one = 1 << 22;
-            xmin = oc;
-            split(&one, 1, kw);
-        }
-        const int sh = (xmin & 3) * 8;
-        const uint8_t* pbase = s_pl + (xmin & ~3);
-        const int plane = mrows4 * ppitch;
-        uint32_t* mo = s_m4 + oc * 3;
-        for (int rq = 0; rq < (mrows + 3) >> 2; ++rq, mo += OWB) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                uint32_t outw = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint32_t* p = reinterpret_cast<const uint32_t*>(pbase + c * plane + (rq * 4 + i) * ppitch);
-                    uint32_t w[NG + 1];
-#pragma unroll
-                    for (int g = 0; g <= NG; ++g) w[g] = p[g];
-                    int a0 = 1 << 21, a1 = 0, a2 = 0;
-#pragma unroll
-                    for (int g = 0; g < NG; ++g) {
-                        const uint32_t a = __funnelshift_r(w[g], w[g + 1], sh);
-                        a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
-                        a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
-                        a2 = dp4a_us(a, kw[2 * NG + g], a2);
-                    }
-                    const int v = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
-                    outw |= (uint32_t)min(255, max(0, v)) << (8 * i);
-                }
-                mo[c] = outw;
+        for (int r = wid; r < mrows; r += NWARP) {
+            const int mis = s_mis[r];
+            const uint8_t* rawr = s_raw + (size_t)r * raw_pitch;
+            uint8_t* dr = s_pl + (size_t)r * ppitch;
+            for (int g = lane; g < ng4; g += 32) {
+                const int o = mis + 12 * g;
+                const uint32_t* q = reinterpret_cast<const uint32_t*>(rawr) + (o >> 2);
+                const int sh = (o & 3) * 8;
+                const uint32_t q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+                const uint32_t w0 = __funnelshift_r(q0, q1, sh), w1 = __funnelshift_r(q1, q2, sh), w2 = __funnelshift_r(q2, q3, sh);
+                // w0 = R0 G0 B0 R1, w1 = G1 B1 R2 G2, w2 = B2 R3 G3 B3
+                uint8_t* d = dr + 4 * g;
+                *reinterpret_cast<uint32_t*>(d) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+                *reinterpret_cast<uint32_t*>(d + plane) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+                *reinterpret_cast<uint32_t*>(d + 2 * plane) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
             }
         }
     }
     __syncthreads();
-    // ---- (3) vertical pass: 4 byte columns per thread
+    // ---- (2) horizontal pass -> M4.  Thread = (output column, share of the row quads)
     {
-        const int G = OWB >> 2;   // column groups per row
+        const int nq = (mrows + 3) >> 2;
+        const int ncolthreads = min(OW, LZ4_T);
+        const int nshare = max(1, LZ4_T / ncolthreads);            // threads per column (row quads split between them)
+        const int share = threadIdx.x / ncolthreads;
+        const int per = (nq + nshare - 1) / nshare;
+        const int rq0 = share * per, rq1 = min(nq, rq0 + per);
+        for (int oc = threadIdx.x - share * ncolthreads; oc < OW && share < nshare && rq0 < rq1; oc += ncolthreads) {
+            uint32_t kw[3 * NG];
+            int xmin;
+            if (need_h) {
+                xmin = xb[oc * 2];
+                split(xk + (size_t)oc * kstride, xb[oc * 2 + 1], kw);
+            } else {
+                const int32_t one = 1 << 22;
+                xmin = oc;
+                split(&one, 1, kw);
+            }
+            const int sh = (xmin & 3) * 8;
+            const int plane = mrows4 * ppitch;
+            const uint8_t* prow = s_pl + (xmin & ~3) + (size_t)rq0 * 4 * ppitch;
+            uint32_t* mo = s_m4 + (size_t)rq0 * OWB + oc * 3;
+            for (int rq = rq0; rq < rq1; ++rq, mo += OWB, prow += 4 * ppitch) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    int v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t* p = reinterpret_cast<const uint32_t*>(prow + c * plane + i * ppitch);
+                        uint32_t w[NG + 1];
+#pragma unroll
+                        for (int g = 0; g <= NG; ++g) w[g] = p[g];
+                        int a0 = 1 << 21, a1 = 0, a2 = 0;
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+                            const uint32_t a = __funnelshift_r(w[g], w[g + 1], sh);
+                            a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
+                            a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
+                            a2 = dp4a_us(a, kw[2 * NG + g], a2);
+                        }
+                        v[i] = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
+                    }
+                    mo[c] = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- (3) vertical pass: a warp per output row, 4 byte columns per lane and step
+    {
+        const int G = OWB >> 2;   // column groups (words) per row
         uint8_t* dimg = dst + ((size_t)img * OH + o0) * OWB;
         float* fimg = dstf ? dstf + ((size_t)img * OH + o0) * OWB : nullptr;
-        int r = 0, cg = threadIdx.x;
-        for (int it = threadIdx.x; it < nrow * G; it += THREADS, cg += THREADS) {
-            while (cg >= G) {
-                cg -= G;
-                ++r;
-            }
+        for (int r = wid; r < nrow; r += NWARP) {
             const int b = s_vb[r];
             const int sh = (b & 3) * 8;
             const uint4* kq = reinterpret_cast<const uint4*>(s_vk + r * VKS);
@@ -1085,34 +1102,37 @@ __global__ void __launch_bounds__(THREADS, 2) k_lanczos_dp4a(const uint8_t* __re
                 const uint4 q = kq[i];
                 kw[4 * i] = q.x; kw[4 * i + 1] = q.y; kw[4 * i + 2] = q.z; kw[4 * i + 3] = q.w;
             }
-            const uint4* mq = reinterpret_cast<const uint4*>(s_m4 + (size_t)(b >> 2) * OWB) + cg;
-            uint4 w[NG + 1];
+            const uint4* mrow = reinterpret_cast<const uint4*>(s_m4 + (size_t)(b >> 2) * OWB);
+            uint32_t* drow = reinterpret_cast<uint32_t*>(dimg) + (size_t)r * G;
+            for (int cg = lane; cg < G; cg += 32) {
+                uint4 w[NG + 1];
 #pragma unroll
-            for (int g = 0; g <= NG; ++g) w[g] = mq[(size_t)g * G];
-            uint32_t outw = 0;
+                for (int g = 0; g <= NG; ++g) w[g] = mrow[(size_t)g * G + cg];
+                int v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int a0 = 1 << 21, a1 = 0, a2 = 0;
+                for (int j = 0; j < 4; ++j) {
+                    int a0 = 1 << 21, a1 = 0, a2 = 0;
 #pragma unroll
-                for (int g = 0; g < NG; ++g) {
-                    const uint32_t lo = j == 0 ? w[g].x : j == 1 ? w[g].y : j == 2 ? w[g].z : w[g].w;
-                    const uint32_t hi = j == 0 ? w[g + 1].x : j == 1 ? w[g + 1].y : j == 2 ? w[g + 1].z : w[g + 1].w;
-                    const uint32_t a = __funnelshift_r(lo, hi, sh);
-                    a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
-                    a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
-                    a2 = dp4a_us(a, kw[2 * NG + g], a2);
+                    for (int g = 0; g < NG; ++g) {
+                        const uint32_t lo = j == 0 ? w[g].x : j == 1 ? w[g].y : j == 2 ? w[g].z : w[g].w;
+                        const uint32_t hi = j == 0 ? w[g + 1].x : j == 1 ? w[g + 1].y : j == 2 ? w[g + 1].z : w[g + 1].w;
+                        const uint32_t a = __funnelshift_r(lo, hi, sh);
+                        a0 = (int)__dp4a(a, kw[g], (uint32_t)a0);
+                        a1 = (int)__dp4a(a, kw[NG + g], (uint32_t)a1);
+                        a2 = dp4a_us(a, kw[2 * NG + g], a2);
+                    }
+                    v[j] = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
                 }
-                const int v = (a2 * 65536 + (a1 * 256 + a0)) >> 22;
-                outw |= (uint32_t)min(255, max(0, v)) << (8 * j);
-            }
-            reinterpret_cast<uint32_t*>(dimg)[(size_t)r * G + cg] = outw;
-            if (fimg) {
-                float4 f;
-                f.x = s_f255[outw & 0xFFu];
-                f.y = s_f255[(outw >> 8) & 0xFFu];
-                f.z = s_f255[(outw >> 16) & 0xFFu];
-                f.w = s_f255[outw >> 24];
-                __stcs(reinterpret_cast<float4*>(fimg) + (size_t)r * G + cg, f);
+                const uint32_t outw = pack_sat_u8x4(v[0], v[1], v[2], v[3]);
+                drow[cg] = outw;
+                if (fimg) {
+                    float4 f;
+                    f.x = s_f255[outw & 0xFFu];
+                    f.y = s_f255[(outw >> 8) & 0xFFu];
+                    f.z = s_f255[(outw >> 16) & 0xFFu];
+                    f.w = s_f255[outw >> 24];
+                    __stcs(reinterpret_cast<float4*>(fimg) + (size_t)r * G + cg, f);
+                }
             }
         }
     }
@@ -1398,10 +1418,10 @@ extern "C" int lfx_crop_lanczos(const uint8_t* src, uint8_t* dst, float* dst_f32
             }
             dim3 grid4(lfx_div_up(OH, LZ4_TO), B);
             if (NG == 2)
-                k_lanczos_dp4a<2><<<grid4, THREADS, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
+                k_lanczos_dp4a<2><<<grid4, LZ4_T, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
                                                                                  kstride, tab_off, mrows_cap, src_index, nsrc);
             else
-                k_lanczos_dp4a<3><<<grid4, THREADS, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
+                k_lanczos_dp4a<3><<<grid4, LZ4_T, smem4, (cudaStream_t)stream>>>(src, dst, dst_f32, H, W, box, OH, OW, tab_bounds, tab_kk,
                                                                                  kstride, tab_off, mrows_cap, src_index, nsrc);
             return lfx_check_launch("crop_lanczos(dp4a)");
         }

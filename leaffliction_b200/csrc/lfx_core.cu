@@ -306,20 +306,14 @@ __global__ void __launch_bounds__(MT, 2)
     c.sm_geom = reinterpret_cast<uint32_t*>(sm + L.off_runs + RCAP_SMEM * 4);
     c.sm_acc = reinterpret_cast<int*>(sm + L.off_runs + RCAP_SMEM * 8);
     c.sm_ry = reinterpret_cast<uint16_t*>(sm + L.off_runs + RCAP_SMEM * 12);
-    uint32_t* blk_hist = nullptr;
     {
         uint8_t* gp = ws + 512 + (size_t)blockIdx.x * P.ws_per_block;
         auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
         c.gl_parent = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
         c.gl_geom = reinterpret_cast<uint32_t*>(gp); gp += al((size_t)M.rcap_glob * 4);
         c.gl_acc = reinterpret_cast<int*>(gp); gp += al((size_t)M.rcap_glob * 4);
-        c.gl_ry = reinterpret_cast<uint16_t*>(gp); gp += al((size_t)M.rcap_glob * 2);
-        blk_hist = reinterpret_cast<uint32_t*>(gp);
+        c.gl_ry = reinterpret_cast<uint16_t*>(gp);
     }
-    // dataset-level colour histogram: this block's images are summed into its own scratch slice (plain
-    // read-modify-write by the owning thread, bin i always belongs to thread i % MT) and merged into ds_hist once, at exit
-    if (ds_hist)
-        for (int i = threadIdx.x; i < 9 * 256; i += MT) blk_hist[i] = 0u;
     if ((size_t)NW * 12 <= (size_t)RCAP_SMEM * 14) {
         c.hp[0] = P0; c.hp[1] = T3; c.hp[2] = reinterpret_cast<uint32_t*>(c.wbase);
         for (int k = 0; k < 3; ++k) c.hp[3 + k] = reinterpret_cast<uint32_t*>(c.sm_parent) + (size_t)k * NW;
@@ -592,7 +586,9 @@ __global__ void __launch_bounds__(MT, 2)
                         cacc[1] += qh.y & qs.y & qv.y;
                         cacc[2] += qh.z & qs.z & qv.z;
                         cacc[3] += qh.w & qs.w & qv.w;
-                        if (q0 & 1u) {
+                        // hsv3 = H/S/V histograms of the LEAF pixels (hist.py:188) = those of all masked pixels (planes 3..5)
+                        // minus those of the masked non-leaf pixels: only the rare non-leaf pixel pays three more atomics
+                        if (!(q0 & 1u)) {
                             atomicAdd(&s_hist[9 * 256 + h], 1u);
                             atomicAdd(&s_hist[10 * 256 + s], 1u);
                             atomicAdd(&s_hist[11 * 256 + v], 1u);
@@ -685,10 +681,15 @@ __global__ void __launch_bounds__(MT, 2)
             __syncthreads();
             if (hist9)
                 for (int i = threadIdx.x; i < 9 * 256; i += MT) hist9[(size_t)img * 9 * 256 + i] = (int)s_hist[i];
+            // dataset-level colour histogram: reductions without a return value (RED), nothing waits for them
             if (ds_hist)
-                for (int i = threadIdx.x; i < 9 * 256; i += MT) blk_hist[i] += s_hist[i];
+                for (int i = threadIdx.x; i < 9 * 256; i += MT) {
+                    const uint32_t v = s_hist[i];
+                    if (v) atomicAdd(&ds_hist[i], (unsigned long long)v);
+                }
             if (hsv3)
-                for (int i = threadIdx.x; i < 3 * 256; i += MT) hsv3[(size_t)img * 3 * 256 + i] = (int)s_hist[9 * 256 + i];
+                for (int i = threadIdx.x; i < 3 * 256; i += MT)
+                    hsv3[(size_t)img * 3 * 256 + i] = (int)(s_hist[3 * 256 + i] - s_hist[9 * 256 + i]);
             if (counters && threadIdx.x < 16) counters[(size_t)img * 16 + threadIdx.x] = threadIdx.x < 14 ? (int)s_cnt[threadIdx.x] : 0;
         }
         if (threadIdx.x == 0) bulk_wait_read();  // s_out is reused as part of the phase-A/B union next image
@@ -696,11 +697,6 @@ __global__ void __launch_bounds__(MT, 2)
         LFX_TICK(2)
     }
 #undef LFX_TICK
-    if (ds_hist)
-        for (int i = threadIdx.x; i < 9 * 256; i += MT) {
-            const uint32_t v = blk_hist[i];
-            if (v) atomicAdd(&ds_hist[i], (unsigned long long)v);
-        }
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
@@ -753,7 +749,7 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
     }
     P.lay = make_lay(H, W, RH, RW);
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2) + 9 * 256 * 4;
+    P.ws_per_block = al16((size_t)M.rcap_glob * 4) * 3 + al16((size_t)M.rcap_glob * 2);
     if (P.lay.smem_bytes > 226 * 1024) return false;
     *per_sm = max(1, min(2, (228 * 1024) / (P.lay.smem_bytes + 1024 + 1536)));  // + static shared + per-block reserve
     (void)B;
@@ -766,7 +762,7 @@ bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, con
 size_t lfx_core_workspace_bytes(int H, int W) {
     auto al16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
     const size_t rcap = (size_t)H * (W + 2);
-    return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2) + 9 * 256 * 4) * (size_t)(2 * LFX_NUM_SMS) + 256;
+    return 512 + (al16(rcap * 4) * 3 + al16(rcap * 2)) * (size_t)(2 * LFX_NUM_SMS) + 256;
 }
 
 extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
