@@ -197,6 +197,32 @@ int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* info, int B
 int lfx_trace_contour(const uint8_t* mask, const int32_t* info, int32_t* points, int32_t* counts,
                       int64_t* sums, int B, int H, int W, int max_pts, lfx_stream_t stream);
 
+/* apply_analyze_filter's numeric record (analyze.py:43-98) for a batch of traced contours (outputs of
+ * lfx_trace_contour): centroid of the contour polygon (cv2.moments, :43-49), extreme points (:60-64), convex hull (:77,
+ * also mask.py:158), PCA axes of the contour vertices and the vertices with the extreme projections (:88-98).
+ * rec_i32[B][24] = {valid, n_points, cx, cy, left.xy, right.xy, top.xy, bottom.xy, hull_count (negative = -needed when
+ *   max_hull is too small), 0, p0_min.xy, p0_max.xy, p1_min.xy, p1_max.xy, 0, 0};
+ * rec_f64[B][12] = {m00 (polygon area), hull area, mean.xy, eigenvector0.xy, eigenvector1.xy, eigenvalue0, eigenvalue1, 0, 0};
+ * hull_points[B][max_hull][2] (x, y).  `sums` may be NULL (the Green-formula sums are then computed from the points).
+ * Exact integer arithmetic for everything but the PCA (fp64). */
+size_t lfx_analyze_workspace(int B, int H);
+int lfx_analyze_record(const int32_t* points, const int32_t* counts, const int64_t* sums, int32_t* rec_i32,
+                       double* rec_f64, int32_t* hull_points, int B, int H, int W, int max_pts, int max_hull,
+                       void* workspace, size_t workspace_bytes, lfx_stream_t stream);
+
+/* Raw candidate of one threshold strategy, no post-processing (_build_mask_candidates, mask.py:414-443; strategies 0-3:
+ * hsv_h, lab, hsv_s / hsv_v_dark by Otsu): raw [B,H,W] (0/255).  Workspace as lfx_make_mask. */
+int lfx_strategy_raw(const uint8_t* src, uint8_t* raw, int B, int H, int W, const lfx_mask_cfg* cfg /* host */,
+                     void* workspace, size_t workspace_bytes, lfx_stream_t stream);
+
+/* Image-dependent terms of _score_mask (mask.py:143-188) for K (<= 8) post-processed candidate masks per image
+ * (masks [K][B][H][W]), as `mask_strategy: auto` ranks them (:435-461).
+ * feat[K][B][4] (double) = {sum of the Sobel magnitude (float32 values, fp64 sum) over the mask boundary
+ *   dilate3x3 ^ erode3x3, boundary pixels, mask pixels, pixels that are mask and green (H in [green_lo, green_hi], S >= 40)};
+ * minmax[B][2] = {float bits of max |grad|, ~(float bits of min |grad|)} over the whole image (cv2.normalize NORM_MINMAX). */
+int lfx_score_features(const uint8_t* src, const uint8_t* masks, double* feat, uint32_t* minmax, int B, int H, int W,
+                       int K, int green_lo, int green_hi, lfx_stream_t stream);
+
 /* apply_mask (mask_utils.py:10-83): dst = mask > 127 ? src : color_val. */
 int lfx_apply_mask(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int B, int H, int W,
                    int color_val, lfx_stream_t stream);

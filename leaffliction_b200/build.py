@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libleafx.so")
-SOURCES = ["lfx_api.cu", "lfx_color.cu", "lfx_augment.cu", "lfx_gauss.cu", "lfx_mask.cu", "lfx_roi.cu", "lfx_contour.cu", "lfx_front.cu", "lfx_core.cu", "lfx_gauss_tma.cu", "lfx_rng.cu", "lfx_params.cu", "lfx_resize.cu"]
+SOURCES = ["lfx_api.cu", "lfx_color.cu", "lfx_augment.cu", "lfx_gauss.cu", "lfx_mask.cu", "lfx_roi.cu", "lfx_contour.cu", "lfx_front.cu", "lfx_core.cu", "lfx_gauss_tma.cu", "lfx_rng.cu", "lfx_params.cu", "lfx_resize.cu", "lfx_score.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "--use_fast_math=false"]
 

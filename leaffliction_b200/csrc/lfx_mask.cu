@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(MT, 2) k_make_mask(const uint8_t* __restrict__
     uint8_t* s_stage = take(sp, (size_t)P.stage_rows * P.W * 3);
     HsvLut* s_hsv = reinterpret_cast<HsvLut*>(take(sp, sizeof(HsvLut)));
     LabLut* s_lab = reinterpret_cast<LabLut*>(take(sp, sizeof(LabLut)));
-    const bool need_lab = (P.mode == 0) && (P.cfg.strategy == 1 || P.cfg.use_lab_brown);
+    const bool need_lab = (P.mode != 1) && (P.cfg.strategy == 1 || P.cfg.use_lab_brown);
     load_hsv_lut(s_hsv, tab);
     if (need_lab) load_lab_lut(s_lab, tab);
     __syncthreads();
@@ -90,6 +90,11 @@ __global__ void __launch_bounds__(MT, 2) k_make_mask(const uint8_t* __restrict__
             if (P.cfg.extend_brown) pixel_pass<0>(simg, s_stage, s_hsv, s_lab, P0, PB, 0, 0, false, P, c);
         }
         __syncthreads();
+        if (P.mode == 2) {   // raw candidate only (lfx_strategy_raw): the plane goes out as it is
+            plane_to_bytes(P0, mask + img * img_px, c);
+            __syncthreads();
+            continue;
+        }
 
         mask_finish(simg, s_stage, s_hsv, P0, PB, PR, T1, T2, T3, s_info, s_info2, P, c);
         plane_to_bytes(PR, mask + img * img_px, c);
@@ -145,6 +150,11 @@ int launch(const uint8_t* src, const uint8_t* raw, uint8_t* mask, int32_t* info,
     LFX_REQUIRE(rc == LFX_OK, rc, "make_mask: image %dx%d needs %zu bytes of shared memory", H, W, pl.smem);
     LFX_REQUIRE(ws && ws_bytes >= pl.ws_per_block * pl.grid, LFX_ERR_WORKSPACE, "make_mask: workspace %zu < %zu bytes",
                 ws_bytes, pl.ws_per_block * pl.grid);
+    if (mode == 2) {
+        LFX_REQUIRE(src && cfg->strategy >= 0 && cfg->strategy <= 3, LFX_ERR_ARG, "strategy_raw: strategy %d has no raw candidate here",
+                    cfg->strategy);
+        pl.P.cfg.extend_brown = 0;
+    }
     if (mode == 0) {
         const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
         LFX_REQUIRE(mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1), LFX_ERR_UNSUPPORTED,
@@ -207,4 +217,14 @@ extern "C" int lfx_postprocess_mask(const uint8_t* raw, uint8_t* mask, int32_t* 
     cfg.morph_kernel = morph_kernel;
     cfg.brown_morph_kernel = 3;
     return launch(nullptr, raw, mask, info, B, H, W, &cfg, 1, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// Raw candidate of one threshold strategy (mask.py:72-106: hsv_s / hsv_v_dark by Otsu, hsv_h, lab), no post-processing:
+// what _build_mask_candidates hands to _postprocess_mask, one entry per strategy ("auto" scores several of them).
+extern "C" int lfx_strategy_raw(const uint8_t* src, uint8_t* raw, int B, int H, int W, const lfx_mask_cfg* cfg, void* workspace,
+                                size_t workspace_bytes, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(src && raw && cfg, LFX_ERR_ARG, "strategy_raw: NULL argument");
+    return launch(src, nullptr, raw, nullptr, B, H, W, cfg, 2, workspace, workspace_bytes, (cudaStream_t)stream);
 }

@@ -96,6 +96,11 @@ class TransformEngine:
         the dataset-level histogram, merged across ranks by one allreduce -- SURVEY.md 8e)."""
         return self._pipeline(x, out, dataset_hist)
 
+    def analyze_device(self, out: ops.CoreOutputs, max_pts: int = 4096, max_hull: int = 512):
+        """Batched numeric records of apply_analyze_filter (analyze.py:43-98) for the masks of a run_device result:
+        contour points, centroid, extreme points, convex hull, PCA axes -- device tensors, layout in include/leafx.h."""
+        return ops.analyze_records(out.mask, out.info, max_pts, max_hull)
+
     # ---- host buffers in, host buffers out
     def _ensure(self):
         if self._bufs is None:

@@ -50,71 +50,40 @@ def apply_brown_filter(rgb: np.ndarray, mask: Optional[np.ndarray], cfg: Transfo
     return vis, pct, count
 
 
+def record_from_device(rec_i: np.ndarray, rec_f: np.ndarray, hull: np.ndarray) -> Dict:
+    """One image's lfx_analyze_record output (include/leafx.h layout) as the dictionary analyze_record returns."""
+    nh = int(rec_i[12])
+    return dict(centroid=(int(rec_i[2]), int(rec_i[3])), area=float(rec_f[0]), n_points=int(rec_i[1]),
+                left=(int(rec_i[4]), int(rec_i[5])), right=(int(rec_i[6]), int(rec_i[7])),
+                top=(int(rec_i[8]), int(rec_i[9])), bottom=(int(rec_i[10]), int(rec_i[11])),
+                hull=hull[:nh].reshape(-1, 1, 2).astype(np.int32), hull_area=float(rec_f[1]),
+                pca_mean=rec_f[2:4].copy(), pca_eigenvectors=rec_f[4:8].reshape(2, 2).copy(), pca_eigenvalues=rec_f[8:10].copy(),
+                axes=(((int(rec_i[14]), int(rec_i[15])), (int(rec_i[16]), int(rec_i[17]))),
+                      ((int(rec_i[18]), int(rec_i[19])), (int(rec_i[20]), int(rec_i[21])))))
+
+
 def analyze_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray) -> Dict:
-    """Numeric content of apply_analyze_filter: centroid of the contour polygon (cv2.moments),
-    extreme points, bounding box, polygon area, vein-edge mask (Canny 80/160 L2 inside the mask)."""
-    pts = contour[:, 0, :].astype(np.int64)
-    n = len(pts)
-    prev = np.roll(pts, 1, axis=0)
-    d = prev[:, 0] * pts[:, 1] - pts[:, 0] * prev[:, 1]          # Green's formula, exact in int64
-    a00 = float(d.sum())
-    a10 = float((d * (prev[:, 0] + pts[:, 0])).sum())
-    a01 = float((d * (prev[:, 1] + pts[:, 1])).sum())
-    if abs(a00) > 1.1920928955078125e-07:
-        sg = 1.0 if a00 > 0 else -1.0
-        m00, m10, m01 = a00 * (0.5 * sg), a10 * (0.16666666666666666 * sg), a01 * (0.16666666666666666 * sg)
-        cx, cy = int(m10 / m00), int(m01 / m00)
-    else:
-        m00 = 0.0
-        cm = contour[:, 0, :].mean(axis=0)
-        cx, cy = int(cm[0]), int(cm[1])
-    p = contour[:, 0, :]
+    """Numeric content of apply_analyze_filter (analyze.py:43-122) for one image: centroid of the contour polygon
+    (cv2.moments), extreme points, convex hull, PCA axes (all by lfx_analyze_record on the device), vein-edge mask
+    (Canny 80/160 L2 inside the mask).  The batched form is ops.analyze_records / TransformEngine(analyze=True)."""
+    import torch
     ops = _ops()
+    pts = np.ascontiguousarray(contour[:, 0, :], np.int32)
+    H, W = rgb.shape[:2]
+    d_pts = _dev(pts[None])
+    d_cnt = torch.tensor([len(pts)], dtype=torch.int32, device=d_pts.device)
+    max_hull = 512
+    while True:
+        rec = ops.analyze_points(d_pts, d_cnt, H, W, max_hull)
+        ri = rec["rec_i"].cpu().numpy()[0]
+        if ri[12] >= 0:
+            break
+        max_hull = int(-ri[12]) + 8
+    out = record_from_device(ri, rec["rec_f"].cpu().numpy()[0], rec["hull"].cpu().numpy()[0])
     gray = ops.cvt_color(_dev(rgb[None]), "gray")
     edges = ops.canny(gray, 80, 160, True).cpu().numpy()[0]
-    veins = (edges > 0) & (_mask2d(mask) > 0)
-    hull = convex_hull(p)
-    mean, evecs, evals, ends = pca_axes(p)
-    return dict(centroid=(cx, cy), area=m00, n_points=n,
-                left=tuple(p[p[:, 0].argmin()]), right=tuple(p[p[:, 0].argmax()]),
-                top=tuple(p[p[:, 1].argmin()]), bottom=tuple(p[p[:, 1].argmax()]), veins=veins,
-                hull=hull, pca_mean=mean, pca_eigenvectors=evecs, pca_eigenvalues=evals, axes=ends)
-
-
-def convex_hull(pts: np.ndarray) -> np.ndarray:
-    """Vertices of the convex hull of integer points [K,2] -> int32 [M,1,2] (analyze.py:77 cv2.convexHull):
-    Andrew's monotone chain in exact integer arithmetic, collinear points dropped."""
-    q = np.unique(np.asarray(pts, np.int64).reshape(-1, 2), axis=0)      # sorted by x, then y
-    if len(q) <= 2:
-        return q.astype(np.int32).reshape(-1, 1, 2)
-
-    def half(seq):
-        out = []
-        for x, y in seq:
-            while len(out) >= 2 and (out[-1][0] - out[-2][0]) * (y - out[-2][1]) - (out[-1][1] - out[-2][1]) * (x - out[-2][0]) <= 0:
-                out.pop()
-            out.append((int(x), int(y)))
-        return out
-    lower, upper = half(q), half(q[::-1])
-    return np.array(lower[:-1] + upper[:-1], np.int32).reshape(-1, 1, 2)
-
-
-def pca_axes(pts: np.ndarray):
-    """analyze.py:88-98: PCA of the contour points (cv2.PCACompute2 on float32 data) and the contour points with the
-    extreme projections on the major / minor axis -> (mean[2], eigenvectors[2,2] rows, eigenvalues[2],
-    ((p0_min, p0_max), (p1_min, p1_max)))."""
-    d = np.asarray(pts, np.float32).reshape(-1, 2)
-    mean = d.mean(axis=0, dtype=np.float64)
-    c = d.astype(np.float64) - mean
-    cov = (c.T @ c) / max(len(d), 1)
-    w, v = np.linalg.eigh(cov)
-    order = np.argsort(w)[::-1]
-    evals, evecs = w[order], v[:, order].T
-    ends = []
-    for k in range(2):
-        proj = d.astype(np.float64) @ evecs[k]
-        ends.append((tuple(int(t) for t in d[int(proj.argmin())]), tuple(int(t) for t in d[int(proj.argmax())])))
-    return mean, evecs, evals, tuple(ends)
+    out["veins"] = (edges > 0) & (_mask2d(mask) > 0)
+    return out
 
 
 def apply_analyze_filter(rgb: np.ndarray, mask: Optional[np.ndarray], contour: Optional[np.ndarray],

@@ -183,6 +183,65 @@ def trace_contour(mask: torch.Tensor, info: torch.Tensor, max_pts: int = 4096):
     return pts, cnt, sums
 
 
+def analyze_records(mask: torch.Tensor, info: torch.Tensor, max_pts: int = 4096, max_hull: int = 512):
+    """Batched numeric record of apply_analyze_filter (analyze.py:43-98) for the contours selected by make_mask:
+    trace (lfx_trace_contour) + record (lfx_analyze_record), nothing leaves the device.
+    Returns dict(points [B,max_pts,2], counts [B], rec_i [B,24] i32, rec_f [B,12] f64, hull [B,max_hull,2] i32);
+    see include/leafx.h for the field layout."""
+    pts, cnt, sums = trace_contour(mask, info, max_pts)
+    lib = _ready(mask)
+    B, H, W = mask.shape
+    rec_i = torch.empty((B, 24), dtype=torch.int32, device=mask.device)
+    rec_f = torch.empty((B, 12), dtype=torch.float64, device=mask.device)
+    hull = torch.zeros((B, max_hull, 2), dtype=torch.int32, device=mask.device)
+    ws = _workspace(lib.lfx_analyze_workspace(B, H), mask.device)
+    _lib.check(lib.lfx_analyze_record(_p(pts), _p(cnt), _p(sums), _p(rec_i), _p(rec_f), _p(hull), B, H, W, int(max_pts), int(max_hull),
+                                      _p(ws), ws.numel(), _stream()))
+    return dict(points=pts, counts=cnt, rec_i=rec_i, rec_f=rec_f, hull=hull)
+
+
+def analyze_points(points: torch.Tensor, counts: torch.Tensor, H: int, W: int, max_hull: int = 512):
+    """lfx_analyze_record on contour points that are already known (points int32 [B,max_pts,2], counts int32 [B])."""
+    lib = _ready(points)
+    B, max_pts = int(points.shape[0]), int(points.shape[1])
+    rec_i = torch.empty((B, 24), dtype=torch.int32, device=points.device)
+    rec_f = torch.empty((B, 12), dtype=torch.float64, device=points.device)
+    hull = torch.zeros((B, max_hull, 2), dtype=torch.int32, device=points.device)
+    ws = _workspace(lib.lfx_analyze_workspace(B, H), points.device)
+    _lib.check(lib.lfx_analyze_record(_p(points), _p(counts), None, _p(rec_i), _p(rec_f), _p(hull), B, int(H), int(W), max_pts, int(max_hull),
+                                      _p(ws), ws.numel(), _stream()))
+    return dict(points=points, counts=counts, rec_i=rec_i, rec_f=rec_f, hull=hull)
+
+
+def strategy_raw(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
+    """Raw candidate of a threshold strategy (cfg.strategy 0-3), no post-processing: [B,H,W] u8 (mask.py:72-106)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    ws = _workspace(lib.lfx_make_mask_workspace(B, H, W), x.device)
+    _lib.check(lib.lfx_strategy_raw(_p(x), _p(out), B, H, W, C.byref(cfg), _p(ws), ws.numel(), _stream()))
+    return out
+
+
+def score_features(x: torch.Tensor, masks: torch.Tensor, green_hue_range=(25, 100)):
+    """Image-dependent terms of _score_mask (mask.py:160-177) for K candidate masks [K,B,H,W] of the images x [B,H,W,3].
+    Returns (feat [K,B,4] f64 = boundary |grad| sum, boundary px, mask px, green & mask px; gmax [B] f32; gmin [B] f32)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    if masks.dtype != torch.uint8 or masks.dim() != 4 or tuple(masks.shape[1:]) != (B, H, W) or not masks.is_contiguous():
+        raise ValueError("score_features: masks must be a contiguous uint8 [K,B,H,W] tensor")
+    K = masks.shape[0]
+    feat = torch.empty((K, B, 4), dtype=torch.float64, device=x.device)
+    mm = torch.empty((B, 2), dtype=torch.int32, device=x.device)
+    _lib.check(lib.lfx_score_features(_p(x), _p(masks), _p(feat), _p(mm), B, H, W, K, int(green_hue_range[0]), int(green_hue_range[1]),
+                                      _stream()))
+    gmax = mm[:, 0].contiguous().view(torch.float32)
+    gmin = (~mm[:, 1]).contiguous().view(torch.float32)
+    return feat, gmax, gmin
+
+
 def apply_mask(x: torch.Tensor, mask: torch.Tensor, color_val: int = 255) -> torch.Tensor:
     _chk_img(x)
     lib = _ready(x)

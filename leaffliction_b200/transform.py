@@ -33,7 +33,7 @@ CANONICAL_TYPES: Dict[str, str] = {
     "landmarks": "Landmarks", "pseudolandmarks": "Landmarks", "pseudo-landmarks": "Landmarks",
     "hist": "Hist", "histogram": "Hist", "brown": "Brown", "disease": "Brown", "spots": "Brown",
 }
-GPU_STRATEGIES = ("hsv_h", "lab", "hsv_s", "hsv_v_dark", "inclusive", "enhanced")
+GPU_STRATEGIES = ("hsv_h", "lab", "hsv_s", "hsv_v_dark", "inclusive", "enhanced", "auto")
 
 _CONFIG_FIELDS = (
     ("gaussian_sigma", float), ("hsv_channel_for_mask", str), ("fill_size", int), ("morph_kernel", int),
@@ -239,7 +239,9 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
     if abs(scale - 1.0) >= 1e-6:          # _prepare_working_image (mask.py:29-50): INTER_CUBIC upscale before masking
         x = ops.resize_cubic(x, (int(round(H * scale)), int(round(W * scale))))
     raw = None
-    if cfg.mask_strategy in ("inclusive", "enhanced"):
+    if cfg.mask_strategy == "auto":
+        raw, _choice, _scores = auto_candidate(x, cfg)
+    elif cfg.mask_strategy in ("inclusive", "enhanced"):
         try:
             raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
         except Exception as e:
@@ -269,6 +271,93 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
             if c is not None:
                 info_h[i, 1:5] = bounding_rect(c)
     return mask.cpu().numpy(), info_h, contours
+
+
+AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "enhanced", "inclusive")
+
+
+def score_mask_terms(area2: int, hull_area: float, bbox, h: int, w: int, b_strength: float, green_frac: float, cfg) -> float:
+    """_score_mask (mask.py:143-188) from its terms: contour area (2 * area, exact), convex-hull area, bounding box,
+    boundary strength and green fraction.  cnt None is area2 < 0."""
+    if area2 < 0:
+        return -1.0
+    area = area2 / 2.0
+    if area <= 1:
+        return -1.0
+    area_ratio = area / float(h * w)
+    if area_ratio < cfg.min_object_area_ratio or area_ratio > cfg.max_object_area_ratio:
+        return 0.01
+    solidity = (area / hull_area) if hull_area > 1 else 0.0
+    x, y, ww, hh = bbox
+    touches = (x <= 0) or (y <= 0) or (x + ww >= w - 1) or (y + hh >= h - 1)
+    target = 0.35
+    area_term = max(0.0, 1.0 - abs(area_ratio - target) / target)
+    score = 0.35 * area_term + 0.25 * solidity + 0.25 * b_strength + 0.15 * green_frac
+    if touches:
+        score *= 0.75
+    return float(score)
+
+
+def auto_candidate(x, cfg: TransformConfig):
+    """`mask_strategy: auto` (mask.py:435-461) on a device batch x [B,H,W,3]: the six deterministic candidates in the
+    reference's order (hsv_s, hsv_v_dark, hsv_h, lab, enhanced, inclusive -- the k-means candidate is Tier C: cv2.kmeans
+    on OpenCV's RNG, not built), each through _postprocess_mask, scored by _score_mask, the first strictly greater score
+    wins.  Returns (raw candidate of the winner per image [B,H,W] -- all zero when every candidate is rejected, which
+    sends make_mask down the reference's Otsu fallback --, chosen index [B] (-1 = none), scores [K,B]).
+    The scores' float terms are accumulated in fp64 on the device (the reference: float32 NumPy mean); two candidates
+    whose scores differ by less than ~1e-6 may therefore rank differently."""
+    import copy
+
+    import torch
+    ops = _ops()
+    B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    raws = []
+    for st in AUTO_CANDIDATES:
+        if st in ("enhanced", "inclusive"):
+            raws.append(ops.raw_mask_front_end(x, st, mask_cfg_from(cfg, "hsv_h")))
+        else:
+            raws.append(ops.strategy_raw(x, mask_cfg_from(cfg, st)))
+    K = len(raws)
+    masks = torch.empty((K, B, H, W), dtype=torch.uint8, device=x.device)
+    infos, recs = [], []
+    for k in range(K):
+        m, info = ops.postprocess_mask(raws[k], cfg.fill_size, cfg.morph_kernel)
+        masks[k].copy_(m)
+        infos.append(info)
+        recs.append(ops.analyze_records(m, info, max_pts=8192))
+    feat, gmax, gmin = ops.score_features(x, masks, cfg.green_hue_range)
+    feat_h = feat.cpu().numpy()
+    gmax_h, gmin_h = gmax.cpu().numpy().astype(np.float64), gmin.cpu().numpy().astype(np.float64)
+    scores = np.full((K, B), -1.0)
+    for k in range(K):
+        info_h = infos[k].cpu().numpy()
+        rf = recs[k]["rec_f"].cpu().numpy()
+        ri = recs[k]["rec_i"].cpu().numpy()
+        if (ri[:, 1] < 0).any() or (ri[:, 12] < 0).any():
+            raise RuntimeError("auto strategy: contour or hull buffer too small")
+        for i in range(B):
+            if not info_h[i, 0]:
+                continue
+            bsum, bcnt, mpx, gpx = feat_h[k, i]
+            rng_ = gmax_h[i] - gmin_h[i]
+            scale = (1.0 / rng_) if rng_ > 2.220446049250313e-16 else 0.0      # cv2.normalize NORM_MINMAX to [0, 1]
+            b_strength = ((bsum / bcnt) * scale - gmin_h[i] * scale) if bcnt > 0 else 0.0
+            green_frac = gpx / max(1.0, mpx)
+            scores[k, i] = score_mask_terms(int(info_h[i, 5]), float(rf[i, 1]), tuple(int(v) for v in info_h[i, 1:5]), H, W,
+                                            b_strength, green_frac, cfg)
+    choice = np.full(B, -1, np.int64)
+    best = np.full(B, -1.0)
+    for k in range(K):                      # _find_best_mask: strictly greater, candidates in order
+        better = scores[k] > best
+        choice[better] = k
+        best[better] = scores[k][better]
+    raw = torch.zeros((B, H, W), dtype=torch.uint8, device=x.device)
+    for k in range(K):
+        idx = np.nonzero(choice == k)[0]
+        if len(idx):
+            ti = torch.from_numpy(idx).to(x.device)
+            raw[ti] = raws[k][ti]
+    return raw, choice, scores
 
 
 _UPSCALE = None

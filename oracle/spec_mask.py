@@ -302,6 +302,103 @@ def make_mask(rgb: np.ndarray, cfg: Cfg):
     return extend_with_brown(m, rgb, cfg)
 
 
+# ------------------------------------------------------------ _score_mask / "auto" (mask.py:143-188, :435-461)
+def first_pixel(mask: np.ndarray):
+    """(x, y) of the first raster pixel of a non-empty mask: where findContours starts the outer border."""
+    idx = int(np.flatnonzero(mask.ravel() > 0)[0])
+    return idx % mask.shape[1], idx // mask.shape[1]
+
+
+def convex_hull_points(pts: np.ndarray) -> np.ndarray:
+    """Vertices of the convex hull of integer points (cv2.convexHull, mask.py:158, analyze.py:77): Andrew's monotone
+    chain, exact integer arithmetic, collinear points dropped.  int64 [M,2], counter-clockwise in image coordinates."""
+    q = np.unique(np.asarray(pts, np.int64).reshape(-1, 2), axis=0)
+    if len(q) <= 2:
+        return q
+
+    def half(seq):
+        out = []
+        for x, y in seq:
+            while len(out) >= 2 and (out[-1][0] - out[-2][0]) * (y - out[-2][1]) - (out[-1][1] - out[-2][1]) * (x - out[-2][0]) <= 0:
+                out.pop()
+            out.append((int(x), int(y)))
+        return out
+    lower, upper = half(q), half(q[::-1])
+    return np.array(lower[:-1] + upper[:-1], np.int64)
+
+
+def polygon_area2(pts: np.ndarray) -> int:
+    """2 * cv2.contourArea of an integer polygon (exact)."""
+    p = np.asarray(pts, np.int64).reshape(-1, 2)
+    if len(p) < 3:
+        return 0
+    q = np.roll(p, -1, axis=0)
+    return abs(int((p[:, 0] * q[:, 1] - q[:, 0] * p[:, 1]).sum()))
+
+
+def score_features(mask: np.ndarray, rgb: np.ndarray, cfg: Cfg):
+    """The image-dependent terms of _score_mask (mask.py:162-177): boundary strength and green fraction."""
+    gray = sc.rgb_to_gray(rgb)
+    mag = sf.normalize_minmax_f32(sf.sobel_magnitude_f32(gray), 0.0, 1.0)          # :162-165
+    fp3 = sf.ellipse_footprint(3)
+    boundary = (sf.dilate(mask, fp3) > 0) ^ (sf.erode(mask, fp3) > 0)               # :166-169
+    b_strength = float(mag[boundary].mean()) if boundary.sum() > 0 else 0.0         # :170
+    hsv = sc.rgb_to_hsv(rgb)
+    lo, hi = cfg.green_hue_range
+    green = (hsv[..., 0] >= lo) & (hsv[..., 0] <= hi) & (hsv[..., 1] >= 40)         # :172-175
+    denom = max(1, int(mask.astype(np.int64).sum() // 255))
+    green_frac = float((green & (mask > 0)).sum()) / float(denom)                   # :176-177
+    return b_strength, green_frac
+
+
+def score_mask(mask: np.ndarray, info, rgb: np.ndarray, cfg: Cfg) -> float:
+    """_score_mask (mask.py:143-188) for a post-processed candidate (`info` None <=> cnt is None)."""
+    from . import spec_contour
+    if info is None:
+        return -1.0
+    h, w = mask.shape[:2]
+    area = info["area2"] / 2.0
+    if area <= 1:
+        return -1.0
+    area_ratio = area / float(h * w)
+    if area_ratio < cfg.min_object_area_ratio or area_ratio > cfg.max_object_area_ratio:
+        return 0.01
+    cnt = spec_contour.trace_external(mask, first_pixel(mask))
+    hull_area = polygon_area2(convex_hull_points(cnt[:, 0, :])) / 2.0
+    solidity = (area / hull_area) if hull_area > 1 else 0.0
+    b_strength, green_frac = score_features(mask, rgb, cfg)
+    x, y, ww, hh = info["bbox"]
+    touches = (x <= 0) or (y <= 0) or (x + ww >= w - 1) or (y + hh >= h - 1)
+    target = 0.35
+    area_term = max(0.0, 1.0 - abs(area_ratio - target) / target)
+    score = 0.35 * area_term + 0.25 * solidity + 0.25 * b_strength + 0.15 * green_frac
+    if touches:
+        score *= 0.75
+    return float(score)
+
+
+AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "enhanced", "inclusive")
+
+
+def make_mask_auto(rgb: np.ndarray, cfg: Cfg, return_choice: bool = False):
+    """make_mask with mask_strategy "auto" (mask.py:435-441) WITHOUT the k-means candidate (Tier C: cv2.kmeans on
+    OpenCV's RNG): the six deterministic candidates in the reference's order, _find_best_mask's strict-greater selection
+    (:446-461), then the fallback and the brown extension exactly as for a single strategy."""
+    import dataclasses
+    best, best_info, best_score, choice = None, None, -1.0, None
+    for st in AUTO_CANDIDATES:
+        raw = raw_candidate(rgb, dataclasses.replace(cfg, mask_strategy=st))
+        m, info = postprocess(raw, cfg)
+        sc_ = score_mask(m, info, rgb, cfg)
+        if sc_ > best_score:
+            best, best_info, best_score, choice = m, info, sc_, st
+    if best is None:
+        fb = mask_hsv_otsu(rgb, cfg.hsv_channel_for_mask, "light")
+        best, best_info = postprocess(fb, cfg)
+    out = extend_with_brown(best, rgb, cfg)
+    return (out + (choice, best_score)) if return_choice else out
+
+
 def apply_mask(img: np.ndarray, mask: np.ndarray, color: str = "white") -> np.ndarray:
     """mask_utils.py:10-83: binarise at >127, paint the rest 255 or 0."""
     val = 255 if color.lower() == "white" else 0

@@ -146,3 +146,129 @@ def test_run_host_ragged_tail(dev):
     assert torch.equal(host.aug["flip"], aset.flip.cpu()) and torch.equal(host.aug["shear"], aset.shear.cpu())
     with pytest.raises(ValueError):
         eng.run_host(imgs)          # augment engine without seeds
+
+
+# ----------------------------------------------------------------------------- analyze record, strategy raws, score, auto
+def _dev_masks(imgs, dev, strategy="hsv_h"):
+    return ops.make_mask(up(imgs, dev), ops.mask_cfg(strategy))
+
+
+def test_analyze_records_batch_vs_cv2(dev):
+    """lfx_analyze_record (analyze.py:43-98) for a batch: centroid / extreme points equal OpenCV's on the same contour
+    (exact), hull vertex set and hull area equal cv2.convexHull / contourArea (exact), PCA axes equal cv2.PCACompute2
+    up to sign (1e-4: OpenCV computes them in float32)."""
+    cv2 = pytest.importorskip("cv2")
+    from leaffliction_b200 import filters
+    from oracle import spec_contour
+    adv = synth.adversarial_images(64, 64)
+    sets = [synth.leaf_batch(12, 256, 256, 31), np.stack([adv[k] for k in ("frame", "ties", "pinch", "salt")]),
+            synth.leaf_batch(3, 96, 64, 5)]
+    total_seen = 0
+    for imgs in sets:
+        H, W = imgs.shape[1:3]
+        mask, info = _dev_masks(imgs, dev)
+        rec = ops.analyze_records(mask, info, max_pts=4096, max_hull=512)
+        ri, rf, hull = rec["rec_i"].cpu().numpy(), rec["rec_f"].cpu().numpy(), rec["hull"].cpu().numpy()
+        pts, cnt = rec["points"].cpu().numpy(), rec["counts"].cpu().numpy()
+        mask_h, info_h = mask.cpu().numpy(), info.cpu().numpy()
+        for i in range(len(imgs)):
+            if not info_h[i, 0]:
+                assert ri[i, 0] == 0
+                continue
+            total_seen += 1
+            cs, _ = cv2.findContours(mask_h[i], cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+            c = max(cs, key=cv2.contourArea)
+            assert np.array_equal(pts[i, : cnt[i]].reshape(-1, 1, 2), c)              # the traced contour is OpenCV's
+            r = filters.record_from_device(ri[i], rf[i], hull[i])
+            exp = spec_contour.analyze_record(c)
+            for k in ("centroid", "left", "right", "top", "bottom"):
+                assert tuple(int(v) for v in r[k]) == tuple(int(v) for v in exp[k]), (i, k)
+            M = cv2.moments(c)
+            if M["m00"] != 0:
+                assert r["centroid"] == (int(M["m10"] / M["m00"]), int(M["m01"] / M["m00"]))
+                assert r["area"] == M["m00"]
+            hv = cv2.convexHull(c)
+            assert {tuple(p) for p in hv[:, 0, :]} == {tuple(p) for p in r["hull"][:, 0, :]}, i
+            assert r["hull_area"] == cv2.contourArea(hv)
+            data = c[:, 0, :].astype(np.float32)
+            if len(data) >= 3:
+                mean, evec, evals = cv2.PCACompute2(data, mean=None)
+                assert np.allclose(r["pca_mean"], mean[0], atol=1e-3)
+                assert np.allclose(r["pca_eigenvalues"], evals[:, 0], rtol=1e-3, atol=1e-3)
+                if evals[0, 0] - evals[1, 0] > 1e-3 * max(1.0, evals[0, 0]):
+                    for k in range(2):
+                        assert abs(abs(float(np.dot(r["pca_eigenvectors"][k], evec[k]))) - 1.0) < 1e-4
+                        proj = data @ evec[k]
+                        got = {float(np.dot(np.array(p, np.float32), evec[k])) for p in r["axes"][k]}
+                        assert abs(min(got) - float(proj.min())) < 1e-2 and abs(max(got) - float(proj.max())) < 1e-2
+
+
+    assert total_seen >= 14
+
+
+def test_analyze_record_small_hull_buffer(dev):
+    imgs = synth.leaf_batch(2, 256, 256, 31)
+    mask, info = _dev_masks(imgs, dev)
+    rec = ops.analyze_records(mask, info, max_pts=4096, max_hull=4)
+    assert (rec["rec_i"][:, 12].cpu().numpy() < 0).all()          # -needed, nothing written past the buffer
+    rec2 = ops.analyze_records(mask, info, max_pts=16)            # contour buffer too small: no record, count reported
+    assert (rec2["rec_i"][:, 0].cpu().numpy() == 0).all() and (rec2["rec_i"][:, 1].cpu().numpy() < 0).all()
+
+
+@pytest.mark.parametrize("hw", [(256, 256), (64, 96), (61, 97)])
+def test_strategy_raw_candidates(dev, hw):
+    """_build_mask_candidates (mask.py:414-434): the raw candidate of each threshold strategy, before post-processing."""
+    import dataclasses
+    H, W = hw
+    imgs = np.concatenate([synth.leaf_batch(5, H, W, 12), np.random.default_rng(2).integers(0, 256, (1, H, W, 3), dtype=np.uint8)])
+    x = up(imgs, dev)
+    for st, bias in (("hsv_h", "light_bg"), ("lab", "light_bg"), ("hsv_s", "light_bg"), ("hsv_s", "dark_bg"), ("hsv_v_dark", "light_bg")):
+        got = ops.strategy_raw(x, ops.mask_cfg(st, bg_bias=bias)).cpu().numpy()
+        for i in range(len(imgs)):
+            exp = sm.raw_candidate(imgs[i], sm.Cfg(mask_strategy=st, bg_bias=bias))
+            assert np.array_equal(got[i], (exp > 0).astype(np.uint8) * 255), (st, bias, i)
+
+
+def test_score_features_and_auto_strategy(dev):
+    """_score_mask terms on the device (mask.py:160-177) and `mask_strategy: auto` through the drop-in make_mask
+    (mask.py:435-461 minus the Tier C k-means candidate) against the oracle: boundary strength within 1e-6 (float32
+    mean in the reference, fp64 here), counts exact, final mask and bounding box bit-exact, same winner."""
+    import dataclasses
+
+    from leaffliction_b200 import transform
+    imgs = np.concatenate([synth.leaf_batch(10, 256, 256, 4242), np.full((1, 256, 256, 3), 180, np.uint8)])
+    x = up(imgs, dev)
+    scfg = sm.Cfg(mask_strategy="auto")
+    cfg = transform.default_config(mask_strategy="auto", grabcut_refine=False, mask_upscale_factor=1.0, mask_upscale_long_side=0)
+    # terms for two candidates
+    masks = []
+    for st in ("hsv_h", "lab"):
+        raw = ops.strategy_raw(x, ops.mask_cfg(st))
+        m, _ = ops.postprocess_mask(raw, 1000, 3)
+        masks.append(m)
+    stack = torch.stack(masks).contiguous()
+    feat, gmax, gmin = ops.score_features(x, stack, (25, 100))
+    feat, gmax, gmin = feat.cpu().numpy(), gmax.cpu().numpy(), gmin.cpu().numpy()
+    for k in range(2):
+        mk = masks[k].cpu().numpy()
+        for i in range(len(imgs)):
+            b_exp, g_exp = sm.score_features(mk[i], imgs[i], scfg)
+            bsum, bcnt, mpx, gpx = feat[k, i]
+            assert mpx == (mk[i] > 0).sum()
+            assert abs(gpx / max(1.0, mpx) - g_exp) < 1e-12
+            rng_ = float(gmax[i]) - float(gmin[i])
+            b = ((bsum / bcnt) - float(gmin[i])) / rng_ if (bcnt > 0 and rng_ > 0) else 0.0
+            assert abs(b - b_exp) < 1e-6, (k, i, b, b_exp)
+    # the whole auto path through the drop-in API
+    got_masks, info, _contours = transform.make_mask_batch(imgs, cfg)
+    raw, choice, scores = transform.auto_candidate(x, cfg)
+    winners = set()
+    for i in range(len(imgs)):
+        om, oinfo, ochoice, oscore = sm.make_mask_auto(imgs[i], scfg, True)
+        assert np.array_equal(got_masks[i], om), f"image {i}: {(got_masks[i] != om).sum()} px differ"
+        assert (sm.AUTO_CANDIDATES[choice[i]] if choice[i] >= 0 else None) == ochoice, i
+        if ochoice is not None:
+            assert abs(scores[choice[i], i] - oscore) < 1e-6
+            assert tuple(info[i, 1:5]) == tuple(oinfo["bbox"])
+        winners.add(ochoice)
+    assert len(winners) >= 2

@@ -140,3 +140,34 @@ def test_all_background_mask(ns):
             om, info = sm.make_mask(img, sm.Cfg(mask_strategy=strat))
             assert np.array_equal(m, om), (val, strat)
             assert (cnt is None) == (info is None), (val, strat)
+
+
+def test_auto_strategy_without_kmeans(ns, leaves256):
+    """`mask_strategy: auto` (mask.py:435-461) with the k-means candidate disabled on the reference side (it returns an
+    empty mask: score -1, never selected; Tier C) against the oracle's six-candidate restatement: per-candidate
+    _score_mask values (1e-6: float32 mean vs the same formula) and the final mask / contour statistics (bit-exact)."""
+    import dataclasses
+
+    import cv2
+    orig = ns.mask._create_kmeans_mask
+    ns.mask._create_kmeans_mask = lambda rgb, cfg: np.zeros(rgb.shape[:2], np.uint8)
+    try:
+        cfg = ref_harness.ref_config(ns, mask_strategy="auto")
+        scfg = sm.Cfg(mask_strategy="auto")
+        choices = set()
+        for i, img in enumerate(list(leaves256[:24]) + [np.full((64, 64, 3), 200, np.uint8)]):
+            for st in sm.AUTO_CANDIDATES:
+                raw = sm.raw_candidate(img, dataclasses.replace(scfg, mask_strategy=st))
+                rm, rcnt = ns.mask._postprocess_mask(raw, cfg)
+                om, oinfo = sm.postprocess(raw, scfg)
+                assert abs(ns.mask._score_mask(rm, rcnt, img, cfg) - sm.score_mask(om, oinfo, img, scfg)) < 1e-6, (i, st)
+            m, cnt = ns.mask.make_mask(img, cfg)
+            om, info, choice, _score = sm.make_mask_auto(img, scfg, True)
+            choices.add(choice)
+            assert np.array_equal(m, om), f"image {i}: {(m != om).sum()} px differ (oracle chose {choice})"
+            assert (cnt is None) == (info is None)
+            if cnt is not None:
+                assert tuple(cv2.boundingRect(cnt)) == tuple(info["bbox"])
+        assert len(choices - {None}) >= 2          # the selection rule is exercised, not one strategy winning everywhere
+    finally:
+        ns.mask._create_kmeans_mask = orig
