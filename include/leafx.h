@@ -237,7 +237,8 @@ int lfx_gauss_u8(const uint8_t* src, uint8_t* dst, int B, int H, int W, int C, i
 
 /* apply_roi_filter canvas (roi.py:20-46): crop info's bounding box from apply_mask(src, mask,
  * white) (mask may be NULL = no masking), letterbox with cv2.resize(INTER_AREA) into a zero
- * [RH,RW,3] canvas.  Images with info.found == 0 get an all-zero canvas. */
+ * [RH,RW,3] canvas -- an upscale when the box fits the canvas, OpenCV's area averaging when it is larger (images bigger
+ * than roi_size); both bit-exact.  Images with info.found == 0 get an all-zero canvas. */
 int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* info, uint8_t* dst,
                       int B, int H, int W, int RH, int RW, lfx_stream_t stream);
 
@@ -251,8 +252,9 @@ int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* in
 int lfx_color_stats(const uint8_t* src, const uint8_t* mask, int32_t* hist9, int32_t* hsv3,
                     int32_t* counters, int B, int H, int W, lfx_stream_t stream);
 
-/* ---- per-image front ends (one thread block per image, everything in shared memory; images with
- *      H*W <= 65536 such as PlantVillage's 256x256 -- larger ones return LFX_ERR_UNSUPPORTED) ------ */
+/* ---- per-image front ends (one thread block per image).  Images up to ~256x256 (PlantVillage) keep every bit plane and
+ *      the grey image in shared memory; larger ones (512x512, 1024x1024 ...) keep them in the block's global scratch
+ *      (lfx_front_workspace accounts for it).  Rows longer than 1152 pixels return LFX_ERR_UNSUPPORTED. ------------------ */
 
 /* Scratch for the four entry points below (run tables that outgrow shared memory + float planes). */
 size_t lfx_front_workspace(int B, int H, int W);

@@ -131,11 +131,20 @@ def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: b
             if a is not None:
                 by_shape.setdefault(a.shape, []).append(i)
         for ids in by_shape.values():
-            masks, _, contours = T.make_mask_batch(np.stack([arrays[i] for i in ids]), cfg)
+            try:
+                masks, _, contours = T.make_mask_batch(np.stack([arrays[i] for i in ids]), cfg)
+            except Exception as e:      # one shape group that cannot be masked must not end the run (the reference's
+                logging.error("Failed to mask %d image(s) of shape %s - %s", len(ids), arrays[ids[0]].shape, e)   # worker logs and goes on)
+                continue
             for k, i in enumerate(ids):
                 premade[i] = (masks[k], contours[k])
-        for ip, pm in zip(chunk, premade):
-            total += len(process_single_image(ProcessArgs(ip, dst, tuple(types), cfg, skip_existing, overwrite), pm))
+        for ip, a, pm in zip(chunk, arrays, premade):
+            if a is not None and pm is None:
+                continue                # its group failed above
+            try:
+                total += len(process_single_image(ProcessArgs(ip, dst, tuple(types), cfg, skip_existing, overwrite), pm))
+            except Exception as e:      # Transformation.py:700-705: a failing image is logged, the folder run continues
+                logging.error("Failed to process %s - %s", ip, e)
     logging.info("Processed %d images, saved %d outputs", len(imgs), total)
     return total
 

@@ -3,9 +3,9 @@
 //   lfx_raw_mask         _create_inclusive_mask / _create_enhanced_mask      (mask.py:727-831, :610-724)
 //   lfx_brown_spots      apply_brown_filter numeric core                      (brown.py:21-89)
 //   lfx_saliency_blur    apply_blur_filter                                    (blur.py:18-79)
-// One thread block per image; the grey image, every mask plane and the run tables stay in shared
-// memory, so HBM sees one read of the input and one write of the result.  Images must fit that
-// budget (H*W <= 65536, e.g. PlantVillage's 256x256); larger inputs return LFX_ERR_UNSUPPORTED.
+// One thread block per image.  Up to ~256x256 (PlantVillage) the grey image, every mask plane and the run tables stay
+// in shared memory, so HBM sees one read of the input and one write of the result; larger images (512x512, 1024x1024)
+// keep the planes and the grey image in the block's global scratch (L2-resident) and run the same code on them.
 // One block per SM (the whole image lives in shared memory): 1024 threads so that the many short, barrier-separated
 // passes over the bit planes have twice the warps to hide their latency.
 #define LFX_MT 1024
@@ -40,6 +40,7 @@ struct FrontParams {
     lfx_mask_cfg cfg;
     Footprint fp3, fp5, fp7, fp9, fpb;
     int rcap_glob;
+    int planes_in_smem;   // 0: bit planes, grey image and word-base table live in the block's global scratch (large images)
     unsigned long long ws_per_block;
 };
 
@@ -375,10 +376,12 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
         p += (bytes + 15) & ~(size_t)15;
         return r;
     };
+    // images up to ~256x256 keep planes, grey image and word-base table in shared memory; larger ones use the block's
+    // global scratch for them (L2-resident; every helper below takes plain pointers, block barriers order the accesses)
     uint32_t* PL[FP_N];
-    for (int k = 0; k < FP_N; ++k) PL[k] = reinterpret_cast<uint32_t*>(take(sp, (size_t)P.NW * 4));
+    for (int k = 0; k < FP_N; ++k) PL[k] = reinterpret_cast<uint32_t*>(P.planes_in_smem ? take(sp, (size_t)P.NW * 4) : take(gp, (size_t)P.NW * 4));
     for (int k = 0; k < NPLANES; ++k) c.plane[k] = PL[k < FP_N ? k : 0];
-    c.wbase = reinterpret_cast<int*>(take(sp, (size_t)(P.NW + 1) * 4));
+    c.wbase = reinterpret_cast<int*>(P.planes_in_smem ? take(sp, (size_t)(P.NW + 1) * 4) : take(gp, (size_t)(P.NW + 1) * 4));
     // run tables: RCAP_SMEM runs in shared memory, worst case (H * ceil(W/2)) in global scratch
     c.sm_parent = reinterpret_cast<int*>(take(sp, RCAP_SMEM * 4));
     c.sm_geom = reinterpret_cast<uint32_t*>(take(sp, RCAP_SMEM * 4));
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
     c.gl_ry = reinterpret_cast<uint16_t*>(take(gp, (size_t)P.rcap_glob * 2));
     float* fscratch = reinterpret_cast<float*>(take(gp, 2 * (size_t)P.H * P.W * sizeof(float)));
     FrontMem M;
-    M.gray = take(sp, (size_t)P.H * P.W);
+    M.gray = P.planes_in_smem ? take(sp, (size_t)P.H * P.W) : take(gp, (size_t)P.H * P.W);
     M.strip = take(sp, STRIP_BYTES);
     M.stage = take(sp, (size_t)P.stage_rows * P.W * 3);
     M.hsv = reinterpret_cast<HsvLut*>(take(sp, sizeof(HsvLut)));
@@ -627,17 +630,24 @@ __global__ void __launch_bounds__(MT, 1) k_front(const uint8_t* __restrict__ src
     }
 }
 
-size_t front_smem(int H, int W, int stage_rows) {
+size_t front_plane_bytes(int H, int W) {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const int WPR = (W + 31) / 32, NW = H * WPR;
-    return al((size_t)NW * 4) * FP_N + al((size_t)(NW + 1) * 4) + al(RCAP_SMEM * 4) * 3 + al(RCAP_SMEM * 2) + al((size_t)H * W) +
-           al(STRIP_BYTES) + al((size_t)stage_rows * W * 3) + al(sizeof(HsvLut)) + al(sizeof(LabLut));
+    return al((size_t)NW * 4) * FP_N + al((size_t)(NW + 1) * 4) + al((size_t)H * W);
 }
+
+size_t front_smem(int H, int W, int stage_rows, bool planes_in_smem) {
+    auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    return (planes_in_smem ? front_plane_bytes(H, W) : 0) + al(RCAP_SMEM * 4) * 3 + al(RCAP_SMEM * 2) + al(STRIP_BYTES) +
+           al((size_t)stage_rows * W * 3) + al(sizeof(HsvLut)) + al(sizeof(LabLut));
+}
+
+bool front_planes_fit(int H, int W) { return front_smem(H, W, max(1, min(H, 6144 / (W * 3))), true) <= 225 * 1024; }
 
 size_t front_ws_per_block(int H, int W) {
     auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
     const size_t rcap = (size_t)H * ((W + 1) / 2);
-    return al(rcap * 4) * 3 + al(rcap * 2) + al(2 * (size_t)H * W * sizeof(float));
+    return al(rcap * 4) * 3 + al(rcap * 2) + al(2 * (size_t)H * W * sizeof(float)) + (front_planes_fit(H, W) ? 0 : front_plane_bytes(H, W) + 256);
 }
 
 int front_launch(const uint8_t* src, const uint8_t* aux, uint8_t* out, int32_t* stats, void* ws, size_t ws_bytes, int B, int H,
@@ -650,9 +660,10 @@ int front_launch(const uint8_t* src, const uint8_t* aux, uint8_t* out, int32_t* 
     P.H = H; P.W = W; P.WPR = (W + 31) / 32; P.NW = H * P.WPR;
     P.lastmask = (W & 31) ? ((1u << (W & 31)) - 1u) : 0xFFFFFFFFu;
     P.stage_rows = max(1, min(H, 6144 / (W * 3)));
-    const size_t smem = front_smem(H, W, P.stage_rows);
+    P.planes_in_smem = front_planes_fit(H, W) ? 1 : 0;
+    const size_t smem = front_smem(H, W, P.stage_rows, P.planes_in_smem != 0);
     LFX_REQUIRE(smem <= 225 * 1024 && (size_t)W * 4 * 3 <= STRIP_BYTES && (size_t)W * 2 * 16 <= STRIP_BYTES, LFX_ERR_UNSUPPORTED,
-                "%s: image %dx%d needs %zu bytes of shared memory (limit 225 KB: H*W <= ~65536)", what, H, W, smem);
+                "%s: image %dx%d: rows of more than %d pixels do not fit the strip buffer", what, H, W, STRIP_BYTES / 32);
     P.fp3 = make_ellipse(3); P.fp5 = make_ellipse(5); P.fp7 = make_ellipse(7); P.fp9 = make_ellipse(9);
     P.fpb = make_ellipse(P.cfg.brown_morph_kernel > 0 ? P.cfg.brown_morph_kernel : 3);
     int32_t t15[31], t5[31];

@@ -1,6 +1,7 @@
 // apply_roi_filter canvas (srcs/transform/filters/roi.py:20-46): crop the contour's bounding box
-// from the white-masked image, letterbox with cv2.resize(INTER_AREA) (an upscale here: 2-tap
-// fixed-point bilinear with area-mode offsets, OpenCV resize.cpp) into a zero canvas.
+// from the white-masked image, letterbox with cv2.resize(INTER_AREA) into a zero canvas.  A box that fits the canvas is
+// upscaled (2-tap fixed-point bilinear with area-mode offsets, OpenCV resize.cpp): k_roi; a box larger than the canvas
+// (images bigger than roi_size) is area-averaged down: k_roi_down.
 #include "lfx_common.cuh"
 
 namespace {
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(THREADS) k_roi(const uint8_t* __restrict__ src
         const double sc = fmin(__ddiv_rn((double)RW, (double)max(bw, 1)), __ddiv_rn((double)RH, (double)max(bh, 1)));
         nw = max((int)__dmul_rn((double)bw, sc), 1), nh = max((int)__dmul_rn((double)bh, sc), 1);
         oy = (RH - nh) / 2, ox = (RW - nw) / 2;
+        if (nw < bw || nh < bh) return;   // a box larger than the canvas shrinks: k_roi_down writes this image
     }
     for (int i = threadIdx.x; i < rows; i += THREADS) {
         const int d = r0 + i - oy;
@@ -121,6 +123,118 @@ __global__ void __launch_bounds__(THREADS) k_roi(const uint8_t* __restrict__ src
     }
 }
 
+// ---- shrink path: cv2.resize(INTER_AREA) of a bounding box LARGER than the canvas (roi.py:35-38 with w > W or h > H;
+// images bigger than roi_size).  OpenCV resize.cpp: integer factors in both directions -> ResizeAreaFast (integer block
+// sums; 2x2 rounds as (s + 2) >> 2, other factors as cvRound(s * float(1 / area))); every other ratio -> ResizeArea_
+// with computeResizeAreaTab's float32 weights and float32 accumulation in table order, cvRound at the end.  One thread
+// per canvas pixel; arithmetic order and roundings are the library's (no FMA contraction), so the result is bit-exact.
+struct AreaSpan {
+    int s_first, s_full0, s_full1, s_last;   // partial first sample (or -1), full samples [s_full0, s_full1), partial last (or -1)
+    float a_first, a_full, a_last;
+};
+__device__ __forceinline__ AreaSpan area_span(int d, int ssize, int dsize) {
+    const double scale = __ddiv_rn((double)ssize, (double)dsize);
+    const double f1 = __dmul_rn((double)d, scale), f2 = __dadd_rn(f1, scale);
+    const double cell = fmin(scale, __dadd_rn((double)ssize, -f1));
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    AreaSpan a;
+    a.s_first = -1; a.s_last = -1; a.a_first = 0.f; a.a_last = 0.f;
+    if (__dadd_rn((double)s1, -f1) > 1e-3) {
+        a.s_first = s1 - 1;
+        a.a_first = __double2float_rn(__ddiv_rn(__dadd_rn((double)s1, -f1), cell));
+    }
+    a.s_full0 = s1; a.s_full1 = s2;
+    a.a_full = __double2float_rn(__ddiv_rn(1.0, cell));
+    if (__dadd_rn(f2, -(double)s2) > 1e-3) {
+        a.s_last = s2;
+        a.a_last = __double2float_rn(__ddiv_rn(fmin(fmin(__dadd_rn(f2, -(double)s2), 1.0), cell), cell));
+    }
+    return a;
+}
+
+__global__ void __launch_bounds__(THREADS) k_roi_down(const uint8_t* __restrict__ src, const uint8_t* __restrict__ mask,
+                                                      const int32_t* __restrict__ info, uint8_t* __restrict__ dst, int H, int W,
+                                                      int RH, int RW) {
+    const int img = blockIdx.y;
+    const int32_t* inf = info + (size_t)img * 8;
+    const int found = inf[0], bx = inf[1], by = inf[2], bw = inf[3], bh = inf[4];
+    if (!(found && bw > 0 && bh > 0)) return;
+    const double sc = fmin(__ddiv_rn((double)RW, (double)max(bw, 1)), __ddiv_rn((double)RH, (double)max(bh, 1)));
+    const int nw = max((int)__dmul_rn((double)bw, sc), 1), nh = max((int)__dmul_rn((double)bh, sc), 1);
+    if (!(nw < bw || nh < bh)) return;   // k_roi's image
+    const int oy = (RH - nh) / 2, ox = (RW - nw) / 2;
+    const int cc = blockIdx.x * 32 + (threadIdx.x & 31), cr = blockIdx.z * 8 + (threadIdx.x >> 5);
+    if (cc >= RW || cr >= RH) return;
+    uint8_t* o = dst + (((size_t)img * RH + cr) * RW + cc) * 3;
+    const int dx = cc - ox, dy = cr - oy;
+    if ((unsigned)dx >= (unsigned)nw || (unsigned)dy >= (unsigned)nh) {
+        o[0] = 0; o[1] = 0; o[2] = 0;
+        return;
+    }
+    const uint8_t* simg = src + (size_t)img * H * W * 3;
+    const uint8_t* mimg = mask ? mask + (size_t)img * H * W : nullptr;
+    auto px = [&](int sy, int sx, float& r, float& g, float& b) {   // pixel of the white-masked image (Transformation.py:451)
+        const size_t off = (size_t)(by + sy) * W + (bx + sx);
+        const bool m = !mimg || __ldg(mimg + off) > 127;
+        const uint8_t* p = simg + off * 3;
+        r = m ? (float)__ldg(p) : 255.f;
+        g = m ? (float)__ldg(p + 1) : 255.f;
+        b = m ? (float)__ldg(p + 2) : 255.f;
+    };
+    const double fx = __ddiv_rn((double)bw, (double)nw), fy = __ddiv_rn((double)bh, (double)nh);
+    const int ix = (int)(fx + 0.5), iy = (int)(fy + 0.5);
+    if (fabs(fx - ix) < 2.220446049250313e-16 && fabs(fy - iy) < 2.220446049250313e-16) {
+        int sr = 0, sg = 0, sb = 0;
+        for (int y = 0; y < iy; ++y)
+            for (int x = 0; x < ix; ++x) {
+                float r, g, b;
+                px(dy * iy + y, dx * ix + x, r, g, b);
+                sr += (int)r; sg += (int)g; sb += (int)b;
+            }
+        if (ix == 2 && iy == 2) {
+            o[0] = (uint8_t)((sr + 2) >> 2); o[1] = (uint8_t)((sg + 2) >> 2); o[2] = (uint8_t)((sb + 2) >> 2);
+        } else {
+            const float inv = __fdiv_rn(1.f, (float)(ix * iy));
+            o[0] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn((float)sr, inv))));
+            o[1] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn((float)sg, inv))));
+            o[2] = (uint8_t)min(255, max(0, __float2int_rn(__fmul_rn((float)sb, inv))));
+        }
+        return;
+    }
+    const AreaSpan X = area_span(dx, bw, nw), Y = area_span(dy, bh, nh);
+    float ar = 0.f, ag = 0.f, ab = 0.f;
+    bool first = true;
+    auto row = [&](int sy, float beta) {
+        float br = 0.f, bg = 0.f, bb = 0.f, r, g, b;
+        if (X.s_first >= 0) {
+            px(sy, X.s_first, r, g, b);
+            br = __fadd_rn(br, __fmul_rn(r, X.a_first)); bg = __fadd_rn(bg, __fmul_rn(g, X.a_first)); bb = __fadd_rn(bb, __fmul_rn(b, X.a_first));
+        }
+        for (int sx = X.s_full0; sx < X.s_full1; ++sx) {
+            px(sy, sx, r, g, b);
+            br = __fadd_rn(br, __fmul_rn(r, X.a_full)); bg = __fadd_rn(bg, __fmul_rn(g, X.a_full)); bb = __fadd_rn(bb, __fmul_rn(b, X.a_full));
+        }
+        if (X.s_last >= 0) {
+            px(sy, X.s_last, r, g, b);
+            br = __fadd_rn(br, __fmul_rn(r, X.a_last)); bg = __fadd_rn(bg, __fmul_rn(g, X.a_last)); bb = __fadd_rn(bb, __fmul_rn(b, X.a_last));
+        }
+        if (first) {
+            ar = __fmul_rn(beta, br); ag = __fmul_rn(beta, bg); ab = __fmul_rn(beta, bb);
+            first = false;
+        } else {
+            ar = __fadd_rn(ar, __fmul_rn(beta, br)); ag = __fadd_rn(ag, __fmul_rn(beta, bg)); ab = __fadd_rn(ab, __fmul_rn(beta, bb));
+        }
+    };
+    if (Y.s_first >= 0) row(Y.s_first, Y.a_first);
+    for (int sy = Y.s_full0; sy < Y.s_full1; ++sy) row(sy, Y.a_full);
+    if (Y.s_last >= 0) row(Y.s_last, Y.a_last);
+    o[0] = (uint8_t)min(255, max(0, __float2int_rn(ar)));
+    o[1] = (uint8_t)min(255, max(0, __float2int_rn(ag)));
+    o[2] = (uint8_t)min(255, max(0, __float2int_rn(ab)));
+}
+
 }  // namespace
 
 extern "C" int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const int32_t* info, uint8_t* dst, int B, int H,
@@ -129,10 +243,14 @@ extern "C" int lfx_roi_letterbox(const uint8_t* src, const uint8_t* mask, const 
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && info && dst && B >= 0 && H > 0 && W > 0 && RH > 0 && RW > 0 && B <= 65535, LFX_ERR_ARG,
                 "roi_letterbox: bad arguments");
-    LFX_REQUIRE(RW >= W && RH >= H, LFX_ERR_UNSUPPORTED,
-                "roi_letterbox: roi_size (%d,%d) smaller than the image (%d,%d) needs the INTER_AREA shrink path", RH, RW, H, W);
     if (B == 0) return LFX_OK;
     dim3 grid(lfx_div_up(RH, ROI_ROWS), B);
     k_roi<<<grid, THREADS, 0, (cudaStream_t)stream>>>(src, mask, info, dst, H, W, RH, RW);
-    return lfx_check_launch("roi_letterbox");
+    int rc = lfx_check_launch("roi_letterbox");
+    if (rc || (RW >= W && RH >= H)) return rc;
+    // the image is larger than the canvas: bounding boxes that have to shrink are written by the INTER_AREA shrink kernel
+    LFX_REQUIRE(lfx_div_up(RH, 8) <= 65535, LFX_ERR_UNSUPPORTED, "roi_letterbox: canvas too tall");
+    dim3 grid2(lfx_div_up(RW, 32), B, lfx_div_up(RH, 8));
+    k_roi_down<<<grid2, THREADS, 0, (cudaStream_t)stream>>>(src, mask, info, dst, H, W, RH, RW);
+    return lfx_check_launch("roi_letterbox(shrink)");
 }

@@ -272,3 +272,50 @@ def test_score_features_and_auto_strategy(dev):
             assert tuple(info[i, 1:5]) == tuple(oinfo["bbox"])
         winners.add(ochoice)
     assert len(winners) >= 2
+
+
+# ----------------------------------------------------------------------------- images larger than 256x256 / than roi_size
+def test_roi_letterbox_shrink(dev):
+    """roi.py:35-38 when the bounding box is larger than roi_size: cv2.resize(INTER_AREA) averages down (general ratios,
+    integer factors incl. 2x2) -- bit-exact against the oracle (itself pinned on OpenCV in test_oracle_golden.py)."""
+    rng = np.random.default_rng(3)
+    H, W = 300, 340
+    imgs = rng.integers(0, 256, (6, H, W, 3), dtype=np.uint8)
+    mask = (rng.integers(0, 4, (6, H, W), dtype=np.uint8) > 0).astype(np.uint8) * 255
+    boxes = [(10, 20, 320, 270), (0, 0, 256, 256), (5, 7, 300, 128), (30, 40, 64, 50), (1, 1, 338, 298), (0, 0, 340, 300)]
+    info = np.zeros((6, 8), np.int32)
+    for i, (x, y, w, h) in enumerate(boxes):
+        info[i, :5] = (1, x, y, w, h)
+    for roi in ((128, 128), (100, 160)):
+        got = ops.roi_letterbox(up(imgs, dev), up(mask, dev), up(info, dev), roi).cpu().numpy()
+        for i, b in enumerate(boxes):
+            white = sm.apply_mask(imgs[i], mask[i], "white")
+            assert np.array_equal(got[i], sm.roi_letterbox(white, b, roi)), (roi, i)
+
+
+@pytest.mark.parametrize("size", [512, 1024])
+def test_default_strategy_on_large_images(dev, size):
+    """The reference's default strategy (inclusive, config.yaml:7) and the other front ends on images larger than
+    256x256: the planes live in global scratch instead of shared memory, the results stay bit-exact."""
+    from leaffliction_b200 import transform
+    imgs = synth.leaf_batch(2, size, size, 99)
+    x = up(imgs, dev)
+    for which in ("inclusive", "enhanced"):
+        raw = ops.raw_mask_front_end(x, which, ops.mask_cfg("hsv_h")).cpu().numpy()
+        for i in range(len(imgs)):
+            exp = sm.raw_candidate(imgs[i], sm.Cfg(mask_strategy=which))
+            assert np.array_equal(raw[i], (exp > 0).astype(np.uint8) * 255), (which, i)
+    cfg = transform.default_config(mask_strategy="inclusive", grabcut_refine=False, mask_upscale_factor=1.0, mask_upscale_long_side=0)
+    masks, info, contours = transform.make_mask_batch(imgs, cfg)
+    for i in range(len(imgs)):
+        om, oinfo = sm.make_mask(imgs[i], sm.Cfg(mask_strategy="inclusive"))
+        assert np.array_equal(masks[i], om)
+        assert tuple(info[i, 1:5]) == tuple(oinfo["bbox"])
+        # ROI of a large image into the reference's 256x256 canvas (shrink) and the brown filter
+        white = sm.apply_mask(imgs[i], om, "white")
+        canvas, _vis, box = transform.apply_roi_filter(white, contours[i], cfg)
+        assert np.array_equal(canvas, sm.roi_letterbox(white, box, cfg.roi_size))
+    spots, stats = ops.brown_spots(x, up(masks, dev), ops.mask_cfg("hsv_h"))
+    for i in range(len(imgs)):
+        es, _pct, ecount = sm.brown_spots(imgs[i], masks[i], sm.Cfg())
+        assert np.array_equal(spots[i].cpu().numpy(), es) and int(stats[i, 1]) == ecount

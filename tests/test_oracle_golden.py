@@ -186,3 +186,22 @@ def test_resize_specs_against_opencv():
         assert np.abs(sf.resize_cubic_u8(img, (ow, oh)).astype(int) - ref).max() <= 1
         m = rng.integers(0, 2, (oh, ow), dtype=np.uint8) * 255
         assert np.array_equal(sf.resize_nearest_u8(m, (w, h)), cv2.resize(m, (w, h), interpolation=cv2.INTER_NEAREST))
+
+
+def test_resize_area_down_against_opencv():
+    """The INTER_AREA shrink restatement (ROI letterbox of a bounding box larger than roi_size, roi.py:35-38) equals
+    cv2.resize bit for bit: integer factors (2x2, 3x3, 4x4, mixed), general ratios, one axis unchanged."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(6)
+    for (w, h), (nw, nh) in (((300, 400), (256, 192)), ((512, 400), (256, 200)), ((700, 650), (256, 237)), ((384, 384), (128, 128)),
+                             ((257, 300), (219, 256)), ((512, 256), (128, 128)), ((301, 299), (256, 254)), ((256, 300), (256, 100)),
+                             ((97, 61), (33, 21))):
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(sm.resize_area_down(img, nw, nh), cv2.resize(img, (nw, nh), interpolation=cv2.INTER_AREA)), ((w, h), (nw, nh))
+    big = rng.integers(0, 256, (300, 340, 3), dtype=np.uint8)      # through the letterbox itself
+    x, y, w, h = 10, 20, 320, 270
+    sc_ = min(128 / w, 128 / h)
+    nw, nh = max(int(w * sc_), 1), max(int(h * sc_), 1)
+    exp = np.zeros((128, 128, 3), np.uint8)
+    exp[(128 - nh) // 2:(128 - nh) // 2 + nh, (128 - nw) // 2:(128 - nw) // 2 + nw] = cv2.resize(big[y:y + h, x:x + w], (nw, nh), interpolation=cv2.INTER_AREA)
+    assert np.array_equal(sm.roi_letterbox(big, (x, y, w, h), (128, 128)), exp)
