@@ -192,6 +192,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the c3 / c4 / c5 sub-records")
     ap.add_argument("--transform-only", action="store_true", help="debug: time the transform half alone")
+    ap.add_argument("--serial", action="store_true", help="debug: every kernel of the step back to back on one stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -226,13 +227,18 @@ def main():
     engine = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, chunk=512, augment=not args.transform_only)
     out = ops.alloc_core_outputs(B, S, S, (256, 256), dev)
     ds_hist = torch.zeros((9, 256), dtype=torch.int64, device=dev)
-    augset = None if args.transform_only else aug_mod.AugmentSet(B, S, S, dev)
+    augset = None if args.transform_only else aug_mod.AugmentSet(B, S, S, dev, concurrent=not args.serial)
     seeds = task_seeds(B, rank)
 
     def step():
+        # three streams: the noise generator, the five geometric augment kernels and k_core run side by side (all of them
+        # are issue- or latency-bound: together they keep the schedulers busier than back to back); the distortion,
+        # which needs the noise, closes the step on the main stream
+        if augset is not None:
+            augset.start(x, seeds)               # augment half: 6 ops x B images (side streams)
         engine.run_device(x, out, ds_hist)       # k_core: transform half + the rank's dataset colour histogram
         if augset is not None:
-            augset.run(x, seeds)                 # augment half: 6 ops x B images
+            augset.finish()
 
     def merge():
         if world > 1:  # ONE allreduce per dataset pass, inside the timed region
@@ -393,6 +399,7 @@ def main():
                        "l2_policy": f"inputs larger than L2 ({B * N * 3 / 1e6:.0f} MB per step vs 126 MB L2)",
                        "images_per_gpu": B, "parallelism": f"image-sharded x{world}",
                        "augment_outputs_per_image": 6 if augset is not None else 0,
+                       "streams": 1 if (args.serial or augset is None) else 3,
                        "dataset_histogram_matches_per_image_sum": ds_ok, "host_binding": binding},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "configs": configs,
             "gpu_launches": launches * args.steps,

@@ -431,9 +431,15 @@ class AugmentSet:
 
     OPS = ("flip", "rotate", "skew", "shear", "crop", "distortion")
 
-    def __init__(self, B: int, H: int, W: int, device):
+    def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False):
+        """`concurrent`: launch the noise generator and the five geometric kernels on two side streams, so that they share
+        the SMs with each other and with whatever the caller queues on its own stream between start() and finish()
+        (every kernel of this path is issue- or latency-bound, none fills the machine alone)."""
         import torch
         self.B, self.H, self.W, self.device = int(B), int(H), int(W), device
+        self.concurrent = bool(concurrent)
+        self._streams = None
+        self._pending = None
         u8 = dict(dtype=torch.uint8, device=device)
         self.flip = torch.empty((B, H, W, 3), **u8)
         self.skew = torch.empty((B, H, W, 3), **u8)
@@ -457,6 +463,12 @@ class AugmentSet:
     def run(self, x, seeds: np.ndarray, timings: dict = None):
         """x: uint8 [B,H,W,3] on the device; seeds: int [6,B] (one task seed per op and image, non-zero).
         `timings`: optional dict filled with per-kernel milliseconds (synchronising CUDA events: profiling runs only)."""
+        self.start(x, seeds, timings)
+        return self.finish(timings)
+
+    def start(self, x, seeds: np.ndarray, timings: dict = None):
+        """Queue noise, flip, rotate, skew, shear and crop (on the side streams when `concurrent`); finish() queues the
+        distortion, which needs the noise, on the caller's stream and joins the side streams."""
         import torch
         ops = _ops()
         B, H, W = self.B, self.H, self.W
@@ -466,8 +478,19 @@ class AugmentSet:
         if self._up is None:
             self._up = ops.PackedUpload(self.device)
         tr = np.repeat(np.arange(6, dtype=np.int32), B)
+        cur = torch.cuda.current_stream(self.device)
+        side = self.concurrent and timings is None
+        if side:
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            ev0 = torch.cuda.Event()
+            ev0.record(cur)            # inputs ready, previous readers of our output buffers done
+            for st in self._streams:
+                st.wait_event(ev0)
+        s_noise, s_geo = self._streams if side else (cur, cur)
         # noise first: it needs only the seeds and runs while the host draws the other parameters
-        d0 = self._up.upload({"seeds": (seeds[5] & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})
+        with torch.cuda.stream(s_noise):
+            d0 = self._up.upload({"seeds": (seeds[5] & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})
 
         def timed(name, fn):
             if timings is None:
@@ -480,22 +503,54 @@ class AugmentSet:
             timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
             return r
 
-        timed("k_legacy_normal_u8", lambda: ops.legacy_normal_noise(seeds[5], H * W * 3, NOISE_LEVEL, self.device,
-                                                                    dseeds=d0["seeds"], out=self.noise))
+        with torch.cuda.stream(s_noise):
+            timed("k_legacy_normal_u8", lambda: ops.legacy_normal_noise(seeds[5], H * W * 3, NOISE_LEVEL, self.device,
+                                                                        dseeds=d0["seeds"], out=self.noise))
+            ev_noise = torch.cuda.Event()
+            ev_noise.record(s_noise)
         ip, dp = draw_params_batch(tr, seeds.reshape(-1), H, W)
         ip, dp = ip.reshape(6, B, 8), dp.reshape(6, B, 8)
         plan = ops.CropPlan(ip[4, :, :4], (H, W), self.device, upload=False)
-        d = self._up.upload({"flip_mode": ip[0, :, 0], "rot": ip[1], "skew_coef": dp[2], "skew_persp": ip[2, :, 0],
-                             "shear_coef": dp[3], "shear_persp": ip[3, :, 0], "crop_box": plan.h_box, "crop_off": plan.h_off,
-                             "cuts": ip[5, :, 0]})
-        plan.box, plan.off = d["crop_box"], d["crop_off"]
         self.rotate_hw = ip[1][:, [7, 6]]
         self.crop_px = int((ip[4, :, 2].astype(np.int64) * ip[4, :, 3]).sum())
-        timed("k_flip_vec", lambda: ops.flip(x, d["flip_mode"], out=self.flip))
-        timed("k_rotate_nn", lambda: ops.rotate_nn(x, ip[1], 255, dparams=d["rot"], out=self.rotate))
-        timed("k_warp_bicubic(skew)", lambda: ops.warp_bicubic(x, d["skew_coef"], d["skew_persp"], out=self.skew))
-        timed("k_warp_bicubic(shear)", lambda: ops.warp_bicubic(x, d["shear_coef"], d["shear_persp"], out=self.shear))
-        timed("k_lanczos_dp4a", lambda: ops.crop_lanczos(x, plan, out=self.crop))
+        with torch.cuda.stream(s_geo):
+            d = self._up.upload({"flip_mode": ip[0, :, 0], "rot": ip[1], "skew_coef": dp[2], "skew_persp": ip[2, :, 0],
+                                 "shear_coef": dp[3], "shear_persp": ip[3, :, 0], "crop_box": plan.h_box, "crop_off": plan.h_off,
+                                 "cuts": ip[5, :, 0]})
+            plan.box, plan.off = d["crop_box"], d["crop_off"]
+            timed("k_flip_vec", lambda: ops.flip(x, d["flip_mode"], out=self.flip))
+            timed("k_rotate_nn", lambda: ops.rotate_nn(x, ip[1], 255, dparams=d["rot"], out=self.rotate))
+            timed("k_warp_bicubic(skew)", lambda: ops.warp_bicubic(x, d["skew_coef"], d["skew_persp"], out=self.skew))
+            timed("k_warp_bicubic(shear)", lambda: ops.warp_bicubic(x, d["shear_coef"], d["shear_persp"], out=self.shear))
+            timed("k_lanczos_dp4a", lambda: ops.crop_lanczos(x, plan, out=self.crop))
+            ev_geo = torch.cuda.Event()
+            ev_geo.record(s_geo)
+        self._pending = (x, d, ev_noise, ev_geo, side)
+        return self
+
+    def finish(self, timings: dict = None):
+        import torch
+        ops = _ops()
+        if self._pending is None:
+            raise RuntimeError("AugmentSet.finish() without start()")
+        x, d, ev_noise, ev_geo, side = self._pending
+        self._pending = None
+        B, H, W = self.B, self.H, self.W
+        cur = torch.cuda.current_stream(self.device)
+        if side:
+            cur.wait_event(ev_noise)
+            cur.wait_event(ev_geo)     # (also orders the upload of `cuts`, made on the geometry stream)
+
+        def timed(name, fn):
+            if timings is None:
+                return fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            r = fn()
+            b.record()
+            b.synchronize()
+            timings[name] = timings.get(name, 0.0) + a.elapsed_time(b)
+            return r
         timed("k_distort_hist+lut+apply", lambda: ops.distort(x, self.noise.view(B, H, W, 3), d["cuts"], out=self.distortion,
                                                                hist_ws=self.hist_ws))
         return self

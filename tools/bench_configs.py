@@ -154,9 +154,26 @@ def c5_resize224(x, dev, peak):
             "batches": out}
 
 
+def p0_default_strategy(x, dev, rank, world, peak, max_over_ranks, barrier, n=2048):
+    """The core transform profile with the reference YAML's default mask strategy (config.yaml:7 `inclusive`; parity profile
+    P0: grabCut off, no upscale): front-end kernel + make_mask on its candidate + blur + ROI + statistics."""
+    from leaffliction_b200 import engine as eng
+    xs = x[:n]
+    S = int(x.shape[1])
+    e = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, front="inclusive")
+    out = ops.alloc_core_outputs(len(xs), S, S, (256, 256), dev)
+    ms = max_over_ranks(_timed(lambda: e.run_device(xs, out), reps=3, warm=2))
+    by = 7 * S * S + 3 * 256 * 256 + 9 * 256 * 4 + 80
+    return {"workload": f"core transform profile, mask_strategy inclusive (the reference's default), {len(xs)} x {S}x{S}x3 images per GPU in HBM",
+            "parity_profile": "P0 (config.yaml defaults, grabcut_refine false, no upscale)", "scaling": "weak", "n_gpus": world,
+            "value": world * len(xs) / (ms / 1e3), "unit": "images/s", "ms": round(ms, 4), "launches": 5,
+            "achieved_gbs": by * len(xs) / (ms / 1e3) / 1e9, "frac": by * len(xs) / (ms / 1e3) / 1e9 / peak}
+
+
 def run_all(x, dev, rank, world, peak, max_over_ranks, barrier):
     res = {}
-    for name, fn in (("c3_balance", lambda: c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier)),
+    for name, fn in (("p0_default_strategy", lambda: p0_default_strategy(x, dev, rank, world, peak, max_over_ranks, barrier)),
+                     ("c3_balance", lambda: c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c4_1024", lambda: c4_1024(dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c5_resize224", lambda: c5_resize224(x, dev, peak))):
         try:
