@@ -289,12 +289,15 @@ int lfx_saliency_blur(const uint8_t* src, const uint8_t* mask, uint8_t* dst, int
 /* Fused core transform profile (BASELINE config 2: blur + mask + ROI + histograms), equivalent to
  * lfx_gauss_u8(5x5) + lfx_make_mask + lfx_roi_letterbox + lfx_color_stats in one submission.
  * dataset_hist9 (optional, device int64 [9][256], needs hist9): the batch's histograms are ADDED to it -- the
- * per-rank partial of the dataset-level colour histogram that one allreduce merges. */
+ * per-rank partial of the dataset-level colour histogram that one allreduce merges.
+ * raw (NULL unless cfg->strategy == 4): the raw candidate [B,H,W] of a composite strategy (lfx_raw_mask: inclusive, the
+ * reference's default, or enhanced) -- the default-strategy profile is then lfx_raw_mask + this one call. */
 size_t lfx_pipeline_core_workspace(int B, int H, int W);
 int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info,
                       uint8_t* roi, int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H,
                       int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg /* host */,
-                      void* workspace, size_t workspace_bytes, int64_t* dataset_hist9, lfx_stream_t stream);
+                      void* workspace, size_t workspace_bytes, int64_t* dataset_hist9, const uint8_t* raw,
+                      lfx_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -68,7 +68,7 @@ _SIGS = {
     "lfx_resize_cubic": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "lfx_resize_nearest": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "lfx_pipeline_core": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, C.c_double,
-                                    C.POINTER(MaskCfg), _P, C.c_size_t, _P, _P]),
+                                    C.POINTER(MaskCfg), _P, C.c_size_t, _P, _P, _P]),
 }
 
 _lib = None

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(MT, 2)
     k_core(const uint8_t* __restrict__ src, uint8_t* __restrict__ blur, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
            uint8_t* __restrict__ roi, int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3, int32_t* __restrict__ counters,
            int B, const CoreParams P, uint8_t* __restrict__ ws, const LfxTables* __restrict__ tab,
-           const uint4* __restrict__ cat_lut, unsigned long long* __restrict__ ds_hist) {
+           const uint4* __restrict__ cat_lut, unsigned long long* __restrict__ ds_hist, const uint8_t* __restrict__ raw) {
     extern __shared__ __align__(128) uint8_t sm[];
     __shared__ int s_tmp[40];
     __shared__ unsigned long long s_best;
@@ -424,6 +424,8 @@ __global__ void __launch_bounds__(MT, 2)
                     b1 = ((unsigned)(h - M.cfg.brown_lo) <= (unsigned)(M.cfg.brown_hi - M.cfg.brown_lo)) &&
                          (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
                 }
+                // strategy 4: the candidate comes from a front-end kernel (inclusive / enhanced, lfx_raw_mask) as bytes
+                if (raw) b0 = __ldg(raw + (size_t)img * img_px + (size_t)(y0 + ry) * W + w * 32 + lane) != 0;
                 const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
                 const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
                 if (lane == 0) {
@@ -451,7 +453,7 @@ __global__ void __launch_bounds__(MT, 2)
         c.status = 0;
         c.tacc = tacc;
         c.tk0 = tk0;
-        if (M.cfg.strategy >= 2) {
+        if (M.cfg.strategy == 2 || M.cfg.strategy == 3) {
             // hsv_s (Otsu on S, 'light' unless dark_bg) / hsv_v_dark (Otsu on V, 'dark'), mask.py:76-84: the threshold needs
             // the whole histogram, so the candidate plane is built by two more passes over the (L2-resident) image
             const int chan = M.cfg.strategy == 2 ? 1 : 2;
@@ -712,7 +714,7 @@ __global__ void k_hist_accum(const int32_t* __restrict__ hist9, int B, unsigned 
 // Shared-memory plan of the fused kernel; false when this shape / config takes the general path.
 bool core_plan(int B, int H, int W, int RH, int RW, const lfx_mask_cfg* cfg, const int32_t* taps, CoreParams* out, int* per_sm) {
     if (W % 32 != 0 || W < 32 || H < 3 || (long long)H * W > 65536 || H > TR * TR) return false;
-    if (!cfg || cfg->strategy < 0 || cfg->strategy > 3) return false;   // 2 / 3: Otsu on S / V, one extra pass in phase B
+    if (!cfg || cfg->strategy < 0 || cfg->strategy > 4) return false;   // 2 / 3: Otsu on S / V, one extra pass in phase B; 4: external raw
     if ((RW * 3) % 16 != 0 || RW < W || RH < H || RW > 1024 || RH > 1024) return false;
     if (taps[0] != taps[4] || taps[1] != taps[3]) return false;
     for (int i = 0; i < 5; ++i)
@@ -774,7 +776,7 @@ extern "C" size_t lfx_pipeline_core_workspace(int B, int H, int W) {
 // negative = error.  Also serves lfx_make_mask (blur / roi / stats pointers NULL: phases A-pixel + B only).
 int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
                  int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
-                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist) {
+                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist, const uint8_t* raw) {
     int rc;
     int32_t taps[31];
     CoreParams P;
@@ -783,6 +785,7 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
                          (reinterpret_cast<uintptr_t>(blur) % 4 == 0);
     const int mk = cfg->morph_kernel, bk = cfg->brown_morph_kernel;
     const bool morph_ok = mk >= 1 && mk <= 19 && (mk & 1) && bk >= 1 && bk <= 19 && (bk & 1);
+    if ((cfg->strategy == 4) != (raw != nullptr)) return 1;
     if (!(aligned && morph_ok && lfx_gauss_taps(5, gaussian_sigma, taps) == LFX_OK && core_plan(B, H, W, RH, RW, cfg, taps, &P, &per_sm)))
         return 1;
     const uint4* cat_lut = lfx_cat_lut();
@@ -806,10 +809,10 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     P.timing = timing ? 1 : 0;
     if (s256)
         k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                        (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist);
+                                                        (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist, raw);
     else
         k_core<false><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
-                                                         (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist);
+                                                         (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist, raw);
     if (timing) {  // debug only: synchronises and prints the phase split
         unsigned long long t[32] = {0};
         cudaStreamSynchronize(st);
@@ -834,7 +837,7 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
 extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi,
                                  int32_t* hist9, int32_t* hsv3, int32_t* counters, int B, int H, int W, int RH, int RW,
                                  double gaussian_sigma, const lfx_mask_cfg* cfg, void* workspace, size_t workspace_bytes,
-                                 int64_t* dataset_hist9, lfx_stream_t stream) {
+                                 int64_t* dataset_hist9, const uint8_t* raw, lfx_stream_t stream) {
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(src && mask && info && cfg, LFX_ERR_ARG, "pipeline_core: NULL argument");
@@ -842,8 +845,9 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long* ds_hist = reinterpret_cast<unsigned long long*>(dataset_hist9);
     LFX_REQUIRE(!ds_hist || hist9, LFX_ERR_ARG, "pipeline_core: dataset_hist9 needs hist9");
+    LFX_REQUIRE((cfg->strategy == 4) == (raw != nullptr), LFX_ERR_ARG, "pipeline_core: strategy 4 <=> a raw candidate is given");
     int rc = lfx_core_try(src, blur, mask, info, roi, hist9, hsv3, counters, B, H, W, RH, RW, gaussian_sigma, cfg, workspace,
-                          workspace_bytes, st, ds_hist);
+                          workspace_bytes, st, ds_hist, raw);
     if (rc <= 0) return rc;
 
     // ---- general path: the stand-alone kernels back to back
@@ -851,7 +855,7 @@ extern "C" int lfx_pipeline_core(const uint8_t* src, uint8_t* blur, uint8_t* mas
         rc = lfx_gauss_u8(src, blur, B, H, W, 3, 5, gaussian_sigma, stream);
         if (rc) return rc;
     }
-    rc = lfx_make_mask(src, nullptr, mask, info, B, H, W, cfg, workspace, workspace_bytes, stream);
+    rc = lfx_make_mask(src, raw, mask, info, B, H, W, cfg, workspace, workspace_bytes, stream);
     if (rc) return rc;
     if (roi) {
         rc = lfx_roi_letterbox(src, mask, info, roi, B, H, W, RH, RW, stream);

@@ -12,7 +12,7 @@
 size_t lfx_core_workspace_bytes(int H, int W);
 int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info, uint8_t* roi, int32_t* hist9, int32_t* hsv3,
                  int32_t* counters, int B, int H, int W, int RH, int RW, double gaussian_sigma, const lfx_mask_cfg* cfg,
-                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist);
+                 void* workspace, size_t workspace_bytes, cudaStream_t st, unsigned long long* ds_hist, const uint8_t* raw);
 
 namespace {
 
@@ -194,10 +194,10 @@ extern "C" int lfx_make_mask(const uint8_t* src, const uint8_t* raw, uint8_t* ma
     LFX_REQUIRE_READY();
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(mask && info && cfg, LFX_ERR_ARG, "make_mask: NULL argument");
-    if (!raw && src && (cfg->strategy == 0 || cfg->strategy == 1) && B > 0 && H > 0 && W > 0) {
-        // threshold strategies on fused-kernel shapes: k_core without its blur / ROI / statistics phases
+    if (src && ((!raw && (cfg->strategy == 0 || cfg->strategy == 1)) || (raw && cfg->strategy == 4)) && B > 0 && H > 0 && W > 0) {
+        // threshold strategies and external candidates on fused-kernel shapes: k_core without its blur / ROI / statistics phases
         const int rc = lfx_core_try(src, nullptr, mask, info, nullptr, nullptr, nullptr, nullptr, B, H, W, H, W, 1.5, cfg, workspace,
-                                    workspace_bytes, (cudaStream_t)stream, nullptr);
+                                    workspace_bytes, (cudaStream_t)stream, nullptr, raw);
         if (rc <= 0) return rc;
     }
     return launch(src, raw, mask, info, B, H, W, cfg, 0, workspace, workspace_bytes, (cudaStream_t)stream);

@@ -109,18 +109,18 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
         }
         // ---- phase 2: the 156 attempts of the block.  The five rounds are independent of each other (no barrier, no
         // shared-memory write), so they are unrolled: the long fp32 chains (log, divide, square root) of one round hide
-        // behind the others -- with ~10 warps per scheduler the kernel was latency-bound with one round in flight.
-        bool acc[5], slow[5];
-        uint8_t o0[5], o1[5];
+        // behind the others.  Result of a round, one word per lane: byte 0 / 1 = the two output bytes, bit 16 = accepted,
+        // bit 17 = fp64 has to decide (kept in registers: arrays of flags and bytes ended up in local memory).
+        constexpr uint32_t ACC = 1u << 16, SLOW = 1u << 17;
+        uint32_t res[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             const int t = c * 32 + lane;
-            acc[c] = false;
-            slow[c] = false;
-            o0[c] = o1[c] = 0;
+            uint32_t r = 0u;
             if (t < 156) {
-                slow[c] = !fast;
-                if (fast) {
+                if (!fast) {
+                    r = SLOW;
+                } else {
                     // the low words (26 of the 53 bits of each double) move x by less than 2^-26 = u/4: the fast path
                     // leaves them untempered (budgeted above); the fp64 re-evaluation tempers all four words
                     const uint2 q = *reinterpret_cast<const uint2*>(mt + 4 * t);
@@ -129,41 +129,45 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
                     const float x1 = (float)((int)a - (1 << 26)) * 0x1p-26f;
                     const float x2 = (float)((int)cc - (1 << 26)) * 0x1p-26f;
                     const float r2 = fmaf(x1, x1, x2 * x2);
-                    if (fabsf(r2 - 1.f) <= 1e-6f) {
-                        slow[c] = true;
-                    } else if (r2 < 1e-8f) {
-                        slow[c] = true;   // (2^-54 of the attempts) the dropped low words decide whether r2 is zero
+                    if (fabsf(r2 - 1.f) <= 1e-6f || r2 < 1e-8f) {
+                        r = SLOW;   // the acceptance test (or, 2^-54 of the attempts, whether r2 is zero) needs the exact radius
                     } else if (r2 < 1.f) {
                         // fast units (MUFU lg2 / rcp / rsq: a few ulp each, |L| abs 4e-7 near 1) -- inside the error budget above
-                        const float q = __fdividef(-2.f * __logf(r2), r2);
+                        const float q3 = __fdividef(-2.f * __logf(r2), r2);
                         float rs;
-                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(q));
-                        const float f = q * rs;
-                        const bool k0 = byte32(fscale * (f * x2), o0[c]), k1 = byte32(fscale * (f * x1), o1[c]);
-                        acc[c] = true;
-                        slow[c] = !(k0 && k1);
+                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(q3));
+                        const float f = fscale * (q3 * rs);
+                        uint8_t b0, b1;
+                        const bool k0 = byte32(f * x2, b0), k1 = byte32(f * x1, b1);
+                        r = (uint32_t)b0 | ((uint32_t)b1 << 8) | ACC | ((k0 && k1) ? 0u : SLOW);
                     }
                 }
             }
+            res[c] = r;
         }
-        // the rare fp64 re-evaluations after all five fast rounds (a call in the middle would serialise them)
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            if (slow[c]) {
-                const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * (c * 32 + lane));
-                acc[c] = attempt64(mt_temper(q.x) >> 5, mt_temper(q.y) >> 6, mt_temper(q.z) >> 5, mt_temper(q.w) >> 6, loc, scale, o0[c], o1[c]);
+        // the rare fp64 re-evaluations after all five fast rounds (0.15 % of the attempts: one warp in five has any)
+        if (__any_sync(0xffffffffu, ((res[0] | res[1] | res[2] | res[3] | res[4]) & SLOW) != 0u)) {
+#pragma unroll 1
+            for (int c = 0; c < 5; ++c) {
+                if (res[c] & SLOW) {
+                    const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * (c * 32 + lane));
+                    uint8_t b0 = 0, b1 = 0;
+                    const bool ok = attempt64(mt_temper(q.x) >> 5, mt_temper(q.y) >> 6, mt_temper(q.z) >> 5, mt_temper(q.w) >> 6, loc, scale, b0, b1);
+                    res[c] = ok ? ((uint32_t)b0 | ((uint32_t)b1 << 8) | ACC) : 0u;
+                }
             }
         }
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, acc[c]);
-            if (acc[c]) {
+            const bool acc = (res[c] & ACC) != 0u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+            if (acc) {
                 const int k = produced + 2 * __popc(bal & ((1u << lane) - 1u));
                 if (k + 1 < n && pair_ok) {
-                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)(o0[c] | (o1[c] << 8));
+                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)res[c];
                 } else {
-                    if (k < n) o[k] = o0[c];
-                    if (k + 1 < n) o[k + 1] = o1[c];
+                    if (k < n) o[k] = (uint8_t)res[c];
+                    if (k + 1 < n) o[k + 1] = (uint8_t)(res[c] >> 8);
                 }
             }
             produced += 2 * __popc(bal);

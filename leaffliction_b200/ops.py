@@ -312,7 +312,8 @@ def alloc_core_outputs(B, H, W, roi_size, device) -> CoreOutputs:
 
 
 def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                  out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None) -> CoreOutputs:
+                  out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None,
+                  raw: Optional[torch.Tensor] = None) -> CoreOutputs:
     """Core transform profile (BASELINE config 2): 5x5 Gaussian blur + make_mask + masked ROI
     letterbox + RGB/HSV/LAB histograms and hist.py counters, one submission.
     `dataset_hist` (int64 [9,256] on the device): the batch's histograms are added to it by the kernel."""
@@ -327,7 +328,7 @@ def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, ro
     ws = _workspace(lib.lfx_pipeline_core_workspace(B, H, W), x.device)
     _lib.check(lib.lfx_pipeline_core(_p(x), _p(out.blur), _p(out.mask), _p(out.info), _p(out.roi), _p(out.hist9),
                                      _p(out.hsv3), _p(out.counters), B, H, W, int(roi_size[0]), int(roi_size[1]),
-                                     float(gaussian_sigma), C.byref(cfg), _p(ws), ws.numel(), _p(dataset_hist), _stream()))
+                                     float(gaussian_sigma), C.byref(cfg), _p(ws), ws.numel(), _p(dataset_hist), _p(raw), _stream()))
     return out
 
 
@@ -338,21 +339,11 @@ def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: fl
     letterbox and colour statistics -- the same outputs as pipeline_core."""
     import copy
     _chk_img(x)
-    B, H, W, _ = x.shape
     raw = raw_mask_front_end(x, which, cfg)
     cfg4 = copy.copy(cfg)
     cfg4.strategy = STRATEGY_IDS["external"]
-    mask, info = make_mask(x, cfg4, raw)
-    blur = gauss_u8(x, 5, gaussian_sigma)
-    roi = roi_letterbox(x, mask, info, roi_size)
-    h9, h3, cn = color_stats(x, mask)
-    if dataset_hist is not None:
-        dataset_hist.view(-1).add_(h9.sum(dim=0, dtype=torch.int64).view(-1))
-    if out is None:
-        return CoreOutputs(blur, mask, info, roi, h9, h3, cn)
-    for dst, srct in ((out.blur, blur), (out.mask, mask), (out.info, info), (out.roi, roi), (out.hist9, h9), (out.hsv3, h3), (out.counters, cn)):
-        dst.copy_(srct)
-    return out
+    # two launches: the front-end kernel, then the fused core kernel on its candidate (strategy 4)
+    return pipeline_core(x, cfg4, gaussian_sigma, roi_size, out, dataset_hist, raw)
 
 
 # --------------------------------------------------------------------------- augmentations
