@@ -126,7 +126,9 @@ int make_plan(int B, int H, int W, const lfx_mask_cfg* cfg, int mode, Plan* out)
     const size_t plane_bytes = al((size_t)P.NW * 4) * NPLANES + al((size_t)(P.NW + 1) * 4);
     P.planes_in_smem = plane_bytes <= 72 * 1024;
     const int rb = W * 3;
-    P.stage_rows = max(1, STAGE_BYTES / rb);
+    // staged RGB rows of the pixel passes: 6 KB next to shared-memory planes; large images (planes in global scratch) have the
+    // shared memory to stage 48 KB at a time (two blocks per SM still fit) -- 16 rows of a 1024-wide image instead of 2
+    P.stage_rows = max(1, (P.planes_in_smem ? STAGE_BYTES : 48 * 1024) / rb);
     if (P.stage_rows > H) P.stage_rows = H;
     size_t smem = al(RCAP_SMEM * 4) * 3 + al(RCAP_SMEM * 2) + al((size_t)P.stage_rows * rb) + al(sizeof(HsvLut)) + al(sizeof(LabLut));
     if (P.planes_in_smem) smem += plane_bytes;
