@@ -96,3 +96,28 @@ def test_dataset_balancer_balances(tmp_path):
     assert b.completed == 6 and b.failed == 0
     names = sorted(p.name for p in (target / "Apple" / "Apple_scab").iterdir())
     assert sum("_aug_" in n for n in names) == 3
+
+
+def test_transformation_cli_default_config_large_and_broken_images(tmp_path):
+    """the reference's DEFAULT config (mask_strategy inclusive, roi_size 256) on images larger than 256x256
+    (512x512: front-end planes in global scratch, ROI shrink path), mixed shapes in one folder, plus a file that cannot
+    be decoded: the folder run logs it and goes on (Transformation.py:700-705), the other images get all their outputs."""
+    src = tmp_path / "in"
+    src.mkdir()
+    big = _write_leaf(src / "big.JPG", 1, 512)
+    small = _write_leaf(src / "small.JPG", 2, 256)
+    (src / "broken.JPG").write_bytes(b"not a jpeg")
+    cfgp = tmp_path / "cfg.yaml"
+    txt = TC.PACKAGED_CONFIG.read_text().replace("grabcut_refine: true", "grabcut_refine: false")
+    txt = txt.replace("mask_upscale_factor: 1.3", "mask_upscale_factor: 1.0").replace("mask_upscale_long_side: 1500", "mask_upscale_long_side: 0")
+    cfgp.write_text(txt)
+    dst = tmp_path / "out"
+    TC.main(["-src", str(src), "-dst", str(dst), "--types", "mask,roi,analyze,brown,blur", "--config", str(cfgp)])
+    scfg = sm.Cfg(mask_strategy="inclusive")
+    for name, img in (("big", big), ("small", small)):
+        m, _info = sm.make_mask(img, scfg)
+        got = np.asarray(Image.open(dst / f"{name}__T_Mask.jpg").convert("RGB"))
+        assert np.array_equal(got, _jpeg_roundtrip(sm.apply_mask(img, m, "black"), quality=95)), name
+        for t in ("ROI", "Analyze", "Brown", "Blur"):
+            assert (dst / f"{name}__T_{t}.jpg").exists(), (name, t)
+    assert not list(dst.glob("broken__T_*"))
