@@ -319,3 +319,20 @@ def test_default_strategy_on_large_images(dev, size):
     for i in range(len(imgs)):
         es, _pct, ecount = sm.brown_spots(imgs[i], masks[i], sm.Cfg())
         assert np.array_equal(spots[i].cpu().numpy(), es) and int(stats[i, 1]) == ecount
+
+
+@pytest.mark.parametrize("hw,out", [((116, 116), (916, 916)), ((300, 400), (224, 300)), ((256, 256), (224, 224)), ((90, 64), (128, 96))])
+def test_lanczos_dp4a_tap_counts(dev, hw, out):
+    """Resize ratios around the 8-tap / 12-tap limits of the dp4a Lanczos kernel (a 116 -> 916 upscale has 7-tap rows, a
+    400 -> 300 downscale 9-tap rows): uint8 and /255 float outputs against the oracle (Pillow's 22-bit fixed point)."""
+    H, W = hw
+    OH, OW = out
+    rng = np.random.default_rng(17)
+    imgs = rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8)
+    boxes = np.array([[0, 0, W, H], [1, 2, W - 3, H - 5], [W // 4, H // 4, W // 2, H // 2]], np.int32)
+    got, gotf = ops.crop_lanczos(up(imgs, dev), boxes, (OH, OW), want_f32=True)
+    got, gotf = got.cpu().numpy(), gotf.cpu().numpy()
+    for i, (l, t, w, h) in enumerate(boxes):
+        exp = sa.resize_lanczos(np.ascontiguousarray(imgs[i][t:t + h, l:l + w]), OW, OH)
+        assert np.array_equal(got[i], exp), (i, (got[i] != exp).sum())
+        assert np.array_equal(gotf[i], exp.astype(np.float32) / np.float32(255.0))
