@@ -157,3 +157,42 @@ def test_gloo_world2_histogram_allreduce(tmp_path):
         assert counts == serial                          # merged class histogram == serial count_images
         assert cc == exp_cls.tolist()
     assert res[0][3:] == res[1][3:]
+
+
+def _prep_worker(rank, world, port, src, dst, q):
+    """Both ranks call the balancer's directory preparation; rank 0's source directory does not exist."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        b = balance.DatasetBalancer(source_dir=src, target_dir=dst, seed=42, rank=rank, world=world)
+        try:
+            b._prepare_target_directory()
+            q.put((rank, "ok", sorted(k for k in b._get_images_by_class())))
+        except Exception as e:   # noqa: BLE001
+            q.put((rank, type(e).__name__, str(e)[:60]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_prepare_failure_reaches_every_rank(tmp_path):
+    """a rank-0 failure while preparing the target directory used to leave the other ranks in a barrier.
+    Now every rank raises (rank 0 its own error, the others a RuntimeError) and nobody hangs; with a valid source both
+    ranks list the same classes, from source_dir (immune to files other ranks are already writing into target_dir)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    for src, expect_ok in ((str(tmp_path / "missing"), False), (str(_make_tree(tmp_path / "tree", {"Apple": {"Apple_a": 3, "Apple_b": 1}})), True)):
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_prep_worker, args=(r, 2, port, src, str(tmp_path / ("out_ok" if expect_ok else "out_bad")), q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        res = sorted(q.get(timeout=120) for _ in procs)
+        for p in procs:
+            p.join(60)
+            assert p.exitcode == 0
+        if expect_ok:
+            assert [r[1] for r in res] == ["ok", "ok"] and res[0][2] == res[1][2] == ["Apple_a", "Apple_b"]
+        else:
+            assert res[0][1] == "FileNotFoundError" and res[1][1] == "RuntimeError"
