@@ -198,20 +198,30 @@ __device__ __forceinline__ double cubic64(double v1, double v2, double v3, doubl
     const double p4 = __dadd_rn(__dadd_rn(__dadd_rn(-v1, v2), -v3), v4);
     return __dadd_rn(p1, __dmul_rn(d, __dadd_rn(p2, __dmul_rn(d, __dadd_rn(p3, __dmul_rn(d, p4))))));
 }
-// cubic32 on inputs carrying a 2^23 bias (integers 0..255): differences are exact, the bias cancels
-__device__ __forceinline__ float cubic32b(float v1, float v2, float v3, float v4, float d) {
-    const float p2 = v3 - v1;
-    const float p3 = 2.f * (v1 - v2) + v3 - v4;
-    const float p4 = -v1 + v2 - v3 + v4;
-    return (v2 - 8388608.f) + d * (p2 + d * (p3 + d * p4));
-}
-__device__ __forceinline__ float cubic32(float v1, float v2, float v3, float v4, float d) {
-    const float p2 = v3 - v1;
-    const float p3 = 2.f * (v1 - v2) + v3 - v4;
-    const float p4 = -v1 + v2 - v3 + v4;
-    return v2 + d * (p2 + d * (p3 + d * p4));
-}
 __device__ __forceinline__ float biased(uint8_t v) { return __uint_as_float(0x4B000000u | v); }  // 2^23 + v: a LOP3, no I2F
+// The same cubic in DIFFERENCE form: cubic(v1..v4, d) = v2 + Wa (v1 - v2) + Wb (v3 - v2) + Wc (v4 - v2) with
+// Wa = -d + 2d^2 - d^3, Wb = d + d^2 - d^3, Wc = -d^2 + d^3 (collect Pillow's Horner form by tap).  The weights depend on
+// the fractional offset only -- one set per output column (horizontal pass) and per output row (vertical pass) -- and an
+// evaluation is 3 differences + 3 FMAs instead of 11 operations; differences of biased taps are exact.
+// fp32 error: weights carry <= 3 roundings (2e-7 relative, |W| <= 1), a horizontal value < 2e-4 (differences <= 255), a
+// vertical one 1.7 x that + 2e-4 < 5.4e-4: inside the 1.1e-3 budget LFX_WARP_EPS was chosen for.  d = 0 gives W = 0 and
+// the value v2 exactly, as in the Horner form.
+struct CubW {
+    float a, b, c;
+};
+__device__ __forceinline__ CubW cubic_weights(float d) {
+    CubW w;
+    w.a = d * (-1.f + d * (2.f - d));
+    w.b = d * (1.f + d * (1.f - d));
+    w.c = d * d * (d - 1.f);
+    return w;
+}
+__device__ __forceinline__ float cubw_b(float v1, float v2, float v3, float v4, const CubW& w) {   // 2^23-biased taps
+    return (v2 - 8388608.f) + w.a * (v1 - v2) + w.b * (v3 - v2) + w.c * (v4 - v2);
+}
+__device__ __forceinline__ float cubw(float v1, float v2, float v3, float v4, const CubW& w) {
+    return v2 + w.a * (v1 - v2) + w.b * (v3 - v2) + w.c * (v4 - v2);
+}
 // Truncated byte of the fp32 value + whether fp64 must decide.  Adding 2^23 rounds f to the nearest integer r (ties
 // irrelevant: they are risky); the low bits of that sum ARE r, so neither F2I nor FRND (quarter-rate pipe) is needed.
 // risky <=> f within EPS of an integer (either side), or outside (EPS, 255 - EPS).
@@ -285,7 +295,7 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const WarpView& v, int H, int 
     int xo[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
-    const float fdx = (float)dx, fdy = (float)dy;
+    const CubW wx = cubic_weights((float)dx), wy = cubic_weights((float)dy);
     uint32_t risky = 0u;
     // cubic(v1..v4, 0) == v2 exactly (v2 + 0 * finite), in fp32 and in fp64 alike.  The reference's shear maps one axis
     // with the identity (image_augmenter.py:82: yin = yc or xin = xc), so a whole image has dy == 0 or dx == 0:
@@ -294,7 +304,7 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const WarpView& v, int H, int 
         const uint8_t* rp = v.base + warp_row_off(v, yf, H);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float fv = cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), fdx);
+            const float fv = cubw_b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]), biased(rp[xo[3] + c]), wx);
             bool rk;
             res[c] = warp_trunc(fv, rk);
             risky |= rk ? (1u << c) : 0u;
@@ -308,8 +318,8 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const WarpView& v, int H, int 
     if (dx == 0.0) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            // biased taps: every difference is an exact integer, so this equals cubic32 on the plain values
-            const float fv = cubic32b(biased(rp0[xo[1] + c]), biased(rp1[xo[1] + c]), biased(rp2[xo[1] + c]), biased(rp3[xo[1] + c]), fdy);
+            // biased taps: every difference is an exact integer, so this equals the cubic on the plain values
+            const float fv = cubw_b(biased(rp0[xo[1] + c]), biased(rp1[xo[1] + c]), biased(rp2[xo[1] + c]), biased(rp3[xo[1] + c]), wy);
             bool rk;
             res[c] = warp_trunc(fv, rk);
             risky |= rk ? (1u << c) : 0u;
@@ -318,11 +328,11 @@ __device__ __forceinline__ uint32_t bicubic_pixel(const WarpView& v, int H, int 
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float v0 = cubic32b(biased(rp0[xo[0] + c]), biased(rp0[xo[1] + c]), biased(rp0[xo[2] + c]), biased(rp0[xo[3] + c]), fdx);
-        const float v1 = cubic32b(biased(rp1[xo[0] + c]), biased(rp1[xo[1] + c]), biased(rp1[xo[2] + c]), biased(rp1[xo[3] + c]), fdx);
-        const float v2 = cubic32b(biased(rp2[xo[0] + c]), biased(rp2[xo[1] + c]), biased(rp2[xo[2] + c]), biased(rp2[xo[3] + c]), fdx);
-        const float v3 = cubic32b(biased(rp3[xo[0] + c]), biased(rp3[xo[1] + c]), biased(rp3[xo[2] + c]), biased(rp3[xo[3] + c]), fdx);
-        const float fv = cubic32(v0, v1, v2, v3, fdy);
+        const float v0 = cubw_b(biased(rp0[xo[0] + c]), biased(rp0[xo[1] + c]), biased(rp0[xo[2] + c]), biased(rp0[xo[3] + c]), wx);
+        const float v1 = cubw_b(biased(rp1[xo[0] + c]), biased(rp1[xo[1] + c]), biased(rp1[xo[2] + c]), biased(rp1[xo[3] + c]), wx);
+        const float v2 = cubw_b(biased(rp2[xo[0] + c]), biased(rp2[xo[1] + c]), biased(rp2[xo[2] + c]), biased(rp2[xo[3] + c]), wx);
+        const float v3 = cubw_b(biased(rp3[xo[0] + c]), biased(rp3[xo[1] + c]), biased(rp3[xo[2] + c]), biased(rp3[xo[3] + c]), wx);
+        const float fv = cubw(v0, v1, v2, v3, wy);
         bool rk;
         res[c] = warp_trunc(fv, rk);
         risky |= rk ? (1u << c) : 0u;
@@ -369,7 +379,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
     __shared__ uint16_t s_queue[WB_QCAP];
     __shared__ int s_qn;
     __shared__ int s_yf[WB_ROWS];      // axis-aligned maps: floor(yin - 0.5) of each band row (INT_MIN: row outside the source)
-    __shared__ float s_fdy[WB_ROWS];   // ... and its fractional part
+    __shared__ float4 s_wy[WB_ROWS];   // ... and the cubic weights (a, b, c) of its fractional part
     __shared__ double s_trow[WB_ROWS]; // a4 * yc of each band row (maps whose yin also depends on x add their column term)
     const int img = blockIdx.y;
     const int band = TILED ? blockIdx.x / ntx : blockIdx.x, tx = TILED ? blockIdx.x - band * ntx : 0;
@@ -394,7 +404,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
         yin = __dadd_rn(yin, -0.5);
         const int yf = (int)floor(yin);
         s_yf[threadIdx.x] = yok ? yf : INT_MIN;
-        s_fdy[threadIdx.x] = (float)__dadd_rn(yin, -(double)yf);
+        const CubW w = cubic_weights((float)__dadd_rn(yin, -(double)yf));
+        s_wy[threadIdx.x] = make_float4(w.a, w.b, w.c, 0.f);
     }
     // number of column slices: the smallest of 1, 2, 4, 8 whose source rectangles all fit in shared memory
     int nsl = 0;
@@ -485,6 +496,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     xin = __dadd_rn(xin, -0.5);
                     const int xf = (int)floor(xin);
                     const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                    const CubW wx = cubic_weights(fdx);
                     const double tcol = __dmul_rn(a[3], xc);
                     int xo[4];
 #pragma unroll
@@ -495,16 +507,17 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
                     for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
                         int yf;
-                        float fdy;
+                        CubW wy;
                         if (ROWONLY) {
                             yf = s_yf[y - y0];
-                            fdy = s_fdy[y - y0];
+                            const float4 q = s_wy[y - y0];
+                            wy.a = q.x, wy.b = q.y, wy.c = q.z;
                         } else {   // yin = (a3*xc + a4*yc) + a5, the generic path's operations in the generic path's order
                             double yin = __dadd_rn(__dadd_rn(tcol, s_trow[y - y0]), a[5]);
                             const bool yok = !(yin < 0.0 || yin >= (double)H);
                             yin = __dadd_rn(yin, -0.5);
                             yf = (int)floor(yin);
-                            fdy = (float)__dadd_rn(yin, -(double)yf);
+                            wy = cubic_weights((float)__dadd_rn(yin, -(double)yf));
                             if (!yok) yf = INT_MIN;
                         }
                         if (!xok || yf == INT_MIN) {
@@ -519,17 +532,17 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
                                 hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
-                                // dx = 0: cubic32b(.., 0) = (v2 - 2^23) + 0 exactly -- the tap itself
+                                // dx = 0: the cubic is (v2 - 2^23) + 0 exactly -- the tap itself
                                 hw[c][3] = (!ROWONLY && fdx == 0.f) ? biased(rp[xo[1] + c]) - 8388608.f
-                                                                    : cubic32b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]),
-                                                                   biased(rp[xo[3] + c]), fdx);
+                                                                    : cubw_b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]),
+                                                                             biased(rp[xo[3] + c]), wx);
                             }
                         }
                         base = yb;
                         uint32_t risky = 0u;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float fv = cubic32(hw[c][0], hw[c][1], hw[c][2], hw[c][3], fdy);
+                            const float fv = cubw(hw[c][0], hw[c][1], hw[c][2], hw[c][3], wy);
                             bool rk;
                             dcol[c] = warp_trunc(fv, rk);
                             risky |= rk ? (1u << c) : 0u;
@@ -569,13 +582,13 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                     if (!(xin < 0.0 || xin >= (double)W)) {
                         xin = __dadd_rn(xin, -0.5);
                         const int xf = (int)floor(xin);
-                        const float fdx = (float)__dadd_rn(xin, -(double)xf);
+                        const CubW wx = cubic_weights((float)__dadd_rn(xin, -(double)xf));
                         const int xa = min(max(xf - 1, 0), W - 1) * 3, xb = min(max(xf, 0), W - 1) * 3;
                         const int xc2 = min(max(xf + 1, 0), W - 1) * 3, xd = min(max(xf + 2, 0), W - 1) * 3;
                         uint32_t risky = 0u;
 #pragma unroll
                         for (int c = 0; c < 3; ++c) {
-                            const float fv = cubic32b(biased(rp[xa + c]), biased(rp[xb + c]), biased(rp[xc2 + c]), biased(rp[xd + c]), fdx);
+                            const float fv = cubw_b(biased(rp[xa + c]), biased(rp[xb + c]), biased(rp[xc2 + c]), biased(rp[xd + c]), wx);
                             bool rk;
                             r3[c] = warp_trunc(fv, rk);
                             risky |= rk ? (1u << c) : 0u;
