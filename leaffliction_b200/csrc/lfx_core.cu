@@ -382,15 +382,9 @@ __global__ void __launch_bounds__(MT, 2)
             const int npix = nr * WPR;
             const int extra = (nvw > 0 && nfree > 0) ? min(npix / nfree, 8) : 0;  // ~ one vpass item = 8 pixel items
             const int head = extra * nfree;
-            for (int k = 0; k < 2; ++k) {
-              int item, iend, istep;
-              if (k == 0) {
-                  if (wid < nvw || extra == 0) continue;
-                  item = wid - nvw; iend = head; istep = nfree;
-              } else {
-                  item = head + wid; iend = npix; istep = NWARPS;
-              }
-              for (; item < iend; item += istep) {
+            // strategy 4: the candidate comes from a front-end kernel (inclusive / enhanced, lfx_raw_mask) as bytes
+            const uint8_t* rawt = raw ? raw + (size_t)img * img_px + (size_t)y0 * W : nullptr;
+            auto pixel_item = [&](int item) {
                 int ry, w;
                 split_index(c, item, ry, w);
                 const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
@@ -425,7 +419,7 @@ __global__ void __launch_bounds__(MT, 2)
                          (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
                 }
                 // strategy 4: the candidate comes from a front-end kernel (inclusive / enhanced, lfx_raw_mask) as bytes
-                if (raw) b0 = __ldg(raw + (size_t)img * img_px + (size_t)(y0 + ry) * W + w * 32 + lane) != 0;
+                if (rawt) b0 = __ldg(rawt + ry * W + w * 32 + lane) != 0;
                 const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
                 const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
                 if (lane == 0) {
@@ -433,8 +427,12 @@ __global__ void __launch_bounds__(MT, 2)
                     P0[idx] = m0;
                     PB[idx] = m1;
                 }
-              }
-            }
+            };
+            // head start of the warps without vertical-pass work, then every warp: the second loop has a compile-time stride
+            // (NWARPS items = NWARPS / WPR rows in the static instantiation), so its addresses are plain pointer increments
+            if (wid >= nvw && extra != 0)
+                for (int item = wid - nvw; item < head; item += nfree) pixel_item(item);
+            for (int item = head + wid; item < npix; item += NWARPS) pixel_item(item);
             __syncthreads();
             if (threadIdx.x == 0 && t + 1 < ntiles)
                 issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0, pol_keep);
