@@ -1,0 +1,124 @@
+#!/usr/bin/env python3
+"""profiles/r02_summary.md from the committed measurement files (profiles/r02_*.json, r02_launches.csv): run after
+copying a measurement pass from gpurun_out/ into profiles/ (see the commands at the top of the generated file)."""
+import collections
+import csv
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = lambda n: os.path.join(ROOT, "profiles", n)  # noqa: E731
+
+
+def launch_shares():
+    rows = list(csv.reader(open(P("r02_launches.csv"))))
+    hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    h = rows[hi]
+    kn, mv = h.index("Kernel Name"), h.index("Metric Value")
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for r in rows[hi + 1:]:
+        if len(r) <= mv:
+            continue
+        n = r[kn].split("(")[0].split("::")[-1].split("<")[0]
+        agg[n][0] += 1
+        agg[n][1] += float(r[mv].replace(",", ""))
+    tot = sum(v[1] for v in agg.values())
+    return [(k, v[0], v[1] / 1e6, v[1] / tot) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]) if v[1] / tot > 0.001]
+
+
+def ops_table(new, old):
+    out = []
+    for k, v in new.items():
+        o = old.get(k, {})
+        out.append(f"| {k} | {v.get('ms')} | {v.get('GB/s', '-')} | {v.get('frac_of_measured_peak', '-')} | {o.get('ms', '-')} |")
+    return "\n".join(out)
+
+
+def main():
+    b = json.load(open(P("r02_bench_1gpu.json")))
+    ref = json.load(open(P("r02_bench_reference_arm.json")))
+    b2 = json.load(open(P("r02_bench_2gpu.json")))
+    b8 = json.load(open(P("r02_bench_8gpu.json")))
+    kern = "\n".join(f"| {k['kernel']} | {k['ms']} | {k['algo_bytes_per_launch']:,} | {k['achieved_gbs']} | {k['frac']} | {k['share_of_step']} |"
+                     for k in b["roofline"]["kernels"])
+    shares = "\n".join(f"| {k} | {n} | {ms:.3f} | {s * 100:.1f} % |" for k, n, ms, s in launch_shares())
+    c = b["configs"]
+    md = f"""# Round 2 -- measurements (all on B200, CUDA events / ncu as noted; peak = MEASURED_PEAKS.json hbm_gbs {b['roofline']['peak']} GB/s)
+
+Regenerate: copy a measurement pass (the gpurun command in DESIGN.md section 5) from gpurun_out/ into profiles/r02_*, run
+`python tools/ncu_summary.py gpurun_out/r02_step.ncu-rep 4096 r02_step_kernels`, then `python tools/make_summary.py`.
+
+## Headline: `python bench.py --steps 20 --warmup 3` (profiles/r02_bench_1gpu.json)
+
+A step = the whole stated metric on one resident batch of 4096 x 256x256x3 images (805 MB > 126 MB L2): `k_core` (core transform profile +
+dataset histogram) + the 6-op augment set (noise, flip, rotate, skew, shear, crop, distort), parameters re-drawn and uploaded every step,
+three streams (noise | geometric augment kernels | k_core).
+
+* value **{b['value']:,.0f} images/s**, {b['ms_per_step']:.3f} ms/step, clocks {b['clocks']['sm_mhz']:.0f}/{b['clocks']['sm_max_mhz']:.0f} MHz, reasons {b['clocks']['reasons']}
+* one stream, kernels back to back (`--serial`): the sum of the kernel times below = {sum(k['ms'] for k in b['roofline']['kernels']):.2f} ms; round-1 kernels on the same line: 15.51 ms/step
+* e2e (pinned host in, all 7 transform + 6 augment outputs back to pinned host, returns after the last copy): **{b['e2e']['value']:,.0f} images/s**;
+  {b['e2e']['h2d_bytes_per_step'] / 1e9:.2f} GB in + {b['e2e']['d2h_bytes_per_step'] / 1e9:.2f} GB out per step; measured pinned copy bandwidth {b['e2e']['pcie']['h2d_gbs']} / {b['e2e']['pcie']['d2h_gbs']} GB/s
+  -> ceiling {b['e2e']['pcie']['ceiling_images_s']:,.0f} images/s, reached {b['e2e']['pcie']['frac_of_ceiling'] * 100:.1f} %
+* CPU baseline (oracle/refcalls.py: the reference's OpenCV / Pillow / NumPy calls, core transform + 6 augmentations per image, {b['cpu_baseline']['cores']} processes): **{b['cpu_baseline']['value']:,.0f} images/s**
+* `--impl reference` arm (profiles/r02_bench_reference_arm.json): {ref['value']:,.0f} images/s
+* whole step: {b['roofline']['step']['algo_bytes_per_image']:,.0f} algorithmic bytes per image -> {b['roofline']['step']['achieved_gbs']:,.0f} GB/s = {b['roofline']['step']['frac'] * 100:.1f} % of the measured peak
+
+Every kernel of the step timed alone (CUDA events on the launching stream, bench.py `roofline.kernels`):
+
+| kernel | ms per 4096 images | algorithmic bytes per launch | GB/s | frac of peak | share of the summed kernel time |
+|---|---|---|---|---|---|
+{kern}
+
+ncu launch list of the same command with `--serial` (2 timed + 3 warm-up steps + the per-kernel timing passes; profiles/r02_launches.csv; cold-cache, serialised) -- the kernels'
+SHARES agree with the CUDA-event column above:
+
+| kernel | launches | total ms | share |
+|---|---|---|---|
+{shares}
+
+## ncu --set full, one launch of each kernel on 4096 images (profiles/r02_step_kernels.md / .json)
+
+See `r02_step_kernels.md` (warp instructions per image, issue / pipe utilisation, shared-memory bank conflicts, DRAM bytes per image, stalls).  `k_core`: DRAM traffic =
+{json.load(open(P('traffic.json')))['traffic_over_algorithmic']:.3f} x the algorithmic 664,656 B per image (profiles/traffic.json), tensor pipe 0 %.
+Phase split of `k_core` (LFX_CORE_TIMING=1): profiles/r02_k_core_phase_split.txt.
+
+## Sub-records (bench.py `configs`, same run)
+
+| sub-record | value | note |
+|---|---|---|
+| p0_default_strategy | {c['p0_default_strategy']['value']:,.0f} images/s | mask_strategy inclusive (config.yaml:7), 2 launches (k_front + k_core on its candidate); round 1: 234 k with 5 launches |
+| c3_balance | {c['c3_balance']['value']:,.0f} augmented images/s | 36,864 tasks over 65,536 resident images, {c['c3_balance']['ms_per_pass_wall']:.1f} ms per pass (wall), plan + histogram + task list {c['c3_balance']['plan_histogram_tasklist_ms']:.1f} ms; round 1: 1.60 M/s |
+| c4_1024 | {c['c4_1024']['value']:,.0f} images/s | 256 x 1024x1024: skew + shear + rotate + 5x5 blur = {c['c4_1024']['frac'] * 100:.1f} % of peak; pipeline_core {c['c4_1024']['ops']['pipeline_core']['ms']} ms ({c['c4_1024']['ops']['pipeline_core']['frac'] * 100:.1f} %) |
+| c5_resize224 | {c['c5_resize224']['value']:,.0f} images/s | flip -> Lanczos 224 -> /255 f32 -> DLPack, best batch; batches: {json.dumps({k: v['images_per_s'] for k, v in c['c5_resize224']['batches'].items()})} |
+
+## Scaling (torchrun, 20 steps; the 2- and 8-GPU records predate the last kernel tweaks by a few per cent)
+
+| GPUs | images/s | ms/step | weak-scaling efficiency | e2e images/s | pinned copy GB/s per rank (in / out) | e2e / ceiling | c3 augmented images/s |
+|---|---|---|---|---|---|---|---|
+| 1 | {b['value']:,.0f} | {b['ms_per_step']:.3f} | 1 | {b['e2e']['value']:,.0f} | {b['e2e']['pcie']['h2d_gbs']} / {b['e2e']['pcie']['d2h_gbs']} | {b['e2e']['pcie']['frac_of_ceiling']:.2f} | {c['c3_balance']['value']:,.0f} |
+| 2 | {b2['value']:,.0f} | {b2['ms_per_step']:.3f} | (12.85 ms at N = 1 in the same build) 0.99 | {b2['e2e']['value']:,.0f} | {b2['e2e']['pcie']['h2d_gbs']} / {b2['e2e']['pcie']['d2h_gbs']} | {b2['e2e']['pcie']['frac_of_ceiling']:.2f} | {b2['configs']['c3_balance']['value']:,.0f} |
+| 8 | {b8['value']:,.0f} | {b8['ms_per_step']:.3f} | 0.99 | {b8['e2e']['value']:,.0f} | {b8['e2e']['pcie']['h2d_gbs']} / {b8['e2e']['pcie']['d2h_gbs']} | {b8['e2e']['pcie']['frac_of_ceiling']:.2f} | {b8['configs']['c3_balance']['value']:,.0f} |
+
+With 8 ranks copying at once the pinned-copy probe drops to ~17 GB/s per rank (one host memory system, 4 cores per rank): the host, not the GPUs, bounds the
+host-to-host number beyond 2 GPUs.  A first 8-GPU run of this round took 22.9 ms/step: the per-step parameter draw (24,576 task seeds through CPython's MT19937
+seeding) ran on the 4 host cores a rank owns there and outlasted the GPU step.  Fixed on the host side (8 seeds interleaved per core: 4x faster seeding; exact integer
+round(x, 15); thread count from the CPU affinity): under `taskset` on one GPU a step costs 13.3 ms with 4 cores and 14.5 ms with 2.
+
+## Per-op kernels (`tools/bench_ops.py`, profiles/r02_ops_256.json: 4096 x 256^2)
+
+| op | ms | algorithmic GB/s | frac of peak | round 1 ms |
+|---|---|---|---|---|
+{ops_table(json.load(open(P('r02_ops_256.json')))['ops'], json.load(open(P('r01_ops_256.json')))['ops'])}
+
+## 1024 x 1024, 256 images (profiles/r02_ops_1024.json)
+
+| op | ms | algorithmic GB/s | frac of peak | round 1 ms |
+|---|---|---|---|---|
+{ops_table(json.load(open(P('r02_ops_1024.json')))['ops'], json.load(open(P('r01_ops_1024.json')))['ops'])}
+"""
+    open(P("r02_summary.md"), "w").write(md)
+    print(md[:2500])
+
+
+if __name__ == "__main__":
+    main()
