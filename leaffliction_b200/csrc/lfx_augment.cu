@@ -222,15 +222,40 @@ __device__ __forceinline__ float cubw_b(float v1, float v2, float v3, float v4, 
 __device__ __forceinline__ float cubw(float v1, float v2, float v3, float v4, const CubW& w) {
     return v2 + w.a * (v1 - v2) + w.b * (v3 - v2) + w.c * (v4 - v2);
 }
-// Truncated byte of the fp32 value + whether fp64 must decide.  Adding 2^23 rounds f to the nearest integer r (ties
-// irrelevant: they are risky); the low bits of that sum ARE r, so neither F2I nor FRND (quarter-rate pipe) is needed.
-// risky <=> f within EPS of an integer (either side), or outside (EPS, 255 - EPS).
+// Clamped, truncated byte of the fp32 value + whether fp64 must decide (Geometry.c: v <= 0 -> 0, v >= 255 -> 255, else
+// (UINT8)v).  With a = f - 0.5, a + 1.5 * 2^23 rounds a to the nearest integer, which is floor(f) unless f is an
+// integer (a tie) -- a value nobody trusts anyway: risky <=> f within EPS of an integer (either side), i.e.
+// |a - rint(a)| > 0.5 - EPS.  The integer sits in the low bits of the sum (biased by 2^22), so clamping the raw bits to
+// [bits(M), bits(M) + 255] is the clamp to 0..255 -- no F2I / FRND (quarter-rate pipe), no select.  Values beyond the
+// range by more than EPS are decided here (0 or 255); NaN compares false and goes to fp64.
 __device__ __forceinline__ uint8_t warp_trunc(float f, bool& risky) {
-    const float fb = f + 8388608.f;
-    const float r = fb - 8388608.f;
-    risky = !(fabsf(f - r) >= LFX_WARP_EPS) || !(f >= LFX_WARP_EPS) || !(f <= 255.f - LFX_WARP_EPS);   // NaN-safe
-    return (uint8_t)((__float_as_uint(fb) & 0x1FFu) - (r > f ? 1u : 0u));
+    const float a = f - 0.5f;
+    const float t = a + 12582912.f;
+    const float d = a - (t - 12582912.f);
+    risky = !(fabsf(d) <= 0.5f - LFX_WARP_EPS);
+    const int bits = min(max(__float_as_int(t), 0x4B400000), 0x4B4000FF);
+    return (uint8_t)bits;
 }
+// The 4 x 3 taps of one row of a PADDED staged rectangle (two replicated pixels left and right of every row, so no
+// column clamp): 12 consecutive bytes from byte offset boff = wb + s, fetched as four aligned words, aligned by three
+// funnel shifts and turned into 2^23-biased floats by one PRMT each -- 19 instructions instead of 12 byte loads + 12
+// adds + the clamps.  t[3 * tap + channel].
+__device__ __forceinline__ void taps12_biased(const uint8_t* wp, uint32_t s8, float t[12]) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(wp);
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    const uint32_t n0 = __funnelshift_r(w0, w1, s8), n1 = __funnelshift_r(w1, w2, s8), n2 = __funnelshift_r(w2, w3, s8);
+    constexpr uint32_t C = 0x4B000000u;
+    t[0] = __uint_as_float(__byte_perm(n0, C, 0x7540)); t[1] = __uint_as_float(__byte_perm(n0, C, 0x7541));
+    t[2] = __uint_as_float(__byte_perm(n0, C, 0x7542)); t[3] = __uint_as_float(__byte_perm(n0, C, 0x7543));
+    t[4] = __uint_as_float(__byte_perm(n1, C, 0x7540)); t[5] = __uint_as_float(__byte_perm(n1, C, 0x7541));
+    t[6] = __uint_as_float(__byte_perm(n1, C, 0x7542)); t[7] = __uint_as_float(__byte_perm(n1, C, 0x7543));
+    t[8] = __uint_as_float(__byte_perm(n2, C, 0x7540)); t[9] = __uint_as_float(__byte_perm(n2, C, 0x7541));
+    t[10] = __uint_as_float(__byte_perm(n2, C, 0x7542)); t[11] = __uint_as_float(__byte_perm(n2, C, 0x7543));
+}
+constexpr int WB_PAD = 16;   // bytes before / after every padded row (the two replicated pixels sit next to the row)
+// row pitch of the padded rectangle: a multiple of 128 bytes, so that equal word columns of different rows share a bank and
+// the lanes of a warp (24 distinct word columns) conflict only where two neighbours read the same word of different rows
+__host__ __device__ constexpr int warp_pad_pitch(int W) { return (W * 3 + 2 * WB_PAD + 127) & ~127; }
 
 // Source coordinates of output pixel (x, y) exactly as Pillow computes them; false = outside (pixel stays 0).
 __device__ __forceinline__ bool warp_coords(int x, int y, int H, int W, const double* a, bool is_persp, int& xf, int& yf, double& dx,
@@ -282,6 +307,17 @@ __device__ __noinline__ uint8_t bicubic_value64(const uint8_t* base, int pitch, 
     }
     const double r = cubic64(dv[0], dv[1], dv[2], dv[3], dy);
     return r <= 0.0 ? 0 : (r >= 255.0 ? 255 : (uint8_t)(int)r);
+}
+
+// Row coordinate of an a1 = 0 map, yin = (a3*xc + a4*yc) + a5 with the generic path's operations in the generic path's
+// order: cubic weights (a, b, c) of the fractional part and, in .w, the bits of floor(yin - 0.5) (INT_MIN: outside).
+__device__ __noinline__ float4 warp_row_coords64(double tcol, double trow, double a5, int H) {
+    double yin = __dadd_rn(__dadd_rn(tcol, trow), a5);
+    const bool yok = !(yin < 0.0 || yin >= (double)H);
+    yin = __dadd_rn(yin, -0.5);
+    const int yf = (int)floor(yin);
+    const CubW w = cubic_weights((float)__dadd_rn(yin, -(double)yf));
+    return make_float4(w.a, w.b, w.c, __int_as_float(yok ? yf : INT_MIN));
 }
 
 // One output pixel of PIL's transform(..., BICUBIC) by the fp32 fast path: res[] holds the truncated fp32 values,
@@ -368,18 +404,21 @@ __device__ __forceinline__ void warp_src_rect(const double* ad, int xa, int xb, 
     c1 = max(c0, (int)fmaxf(fminf(xhi + 3.75f, (float)(W - 1)), 0.f));
 }
 
-// TILED = false is the W <= WB_COLS instantiation: one tile per band, whole rows staged as one contiguous copy, no slices
-// (a rectangle that does not fit falls back to global taps) -- the column bookkeeping folds away at compile time.
+// TILED = false is the W <= WB_COLS instantiation: one tile per band, whole rows staged, no slices (a rectangle that
+// does not fit falls back to global taps) -- the column bookkeeping folds away at compile time.  When every row start
+// is 16-byte aligned the rows are staged PADDED (pitch W*3 + 32: two replicated border pixels on either side), so the
+// specialised paths fetch their taps without column clamps (taps12_biased).
 template <bool TILED>
 __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int H,
                                                           int W, const double* __restrict__ coef,
                                                           const int32_t* __restrict__ persp, int smem_cap, int ntx,
-                                                          const int32_t* __restrict__ sidx, int nsrc) {
+                                                          const int32_t* __restrict__ sidx, int nsrc, uint32_t m32) {
     extern __shared__ __align__(16) uint8_t s_rows[];
     __shared__ uint16_t s_queue[WB_QCAP];
     __shared__ int s_qn;
-    __shared__ int s_yf[WB_ROWS];      // axis-aligned maps: floor(yin - 0.5) of each band row (INT_MIN: row outside the source)
-    __shared__ float4 s_wy[WB_ROWS];   // ... and the cubic weights (a, b, c) of its fractional part
+    // axis-aligned maps: the cubic weights (a, b, c) of each band row and, in .w, the bits of floor(yin - 0.5) (INT_MIN: row
+    // outside the source)
+    __shared__ float4 s_wy[WB_ROWS];
     __shared__ double s_trow[WB_ROWS]; // a4 * yc of each band row (maps whose yin also depends on x add their column term)
     const int img = blockIdx.y;
     const int band = TILED ? blockIdx.x / ntx : blockIdx.x, tx = TILED ? blockIdx.x - band * ntx : 0;
@@ -403,17 +442,18 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
         const bool yok = !(yin < 0.0 || yin >= (double)H);
         yin = __dadd_rn(yin, -0.5);
         const int yf = (int)floor(yin);
-        s_yf[threadIdx.x] = yok ? yf : INT_MIN;
         const CubW w = cubic_weights((float)__dadd_rn(yin, -(double)yf));
-        s_wy[threadIdx.x] = make_float4(w.a, w.b, w.c, 0.f);
+        s_wy[threadIdx.x] = make_float4(w.a, w.b, w.c, __int_as_float(yok ? yf : INT_MIN));
     }
     // number of column slices: the smallest of 1, 2, 4, 8 whose source rectangles all fit in shared memory
     int nsl = 0;
+    bool pad = false;
     if (!TILED) {
         if (affine && smem_cap > 0) {
             int r0, r1, c0, c1;
             warp_src_rect(a, 0, W, y0, y1, H, W, r0, r1, c0, c1);
-            nsl = ((r1 - r0 + 1) * W * 3 <= smem_cap) ? 1 : 0;
+            pad = al16 && (r1 - r0 + 1) * warp_pad_pitch(W) <= smem_cap;
+            nsl = (pad || (r1 - r0 + 1) * W * 3 <= smem_cap) ? 1 : 0;
         }
     } else if (affine && smem_cap > 0) {
         for (int n = 1; n <= 8 && !nsl; n *= 2) {
@@ -436,8 +476,29 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
             if (nsl) {
                 int r0, r1, c0, c1;
                 warp_src_rect(a, 0, W, y0, y1, H, W, r0, r1, c0, c1);
-                v = WarpView{s_rows, W * 3, r0, 0};
-                block_load_bytes(s_rows, simg + (size_t)r0 * W * 3, (r1 - r0 + 1) * W * 3);
+                const int rows = r1 - r0 + 1;
+                const uint8_t* g = simg + (size_t)r0 * W * 3;
+                if (pad) {
+                    const int pitch = warp_pad_pitch(W), n16 = (W * 3) >> 4;
+                    v = WarpView{s_rows, pitch, r0, -WB_PAD};
+                    // the source rows are contiguous: chunk i of the rectangle is row i / n16, chunk i % n16 of that row
+                    // (m32 = ceil(2^32 / n16) from the host: the quotient is one multiply-high)
+                    for (int i = threadIdx.x; i < rows * n16; i += THREADS) {
+                        const int r = (int)__umulhi((uint32_t)i, m32), k = i - r * n16;
+                        *reinterpret_cast<uint4*>(s_rows + r * pitch + WB_PAD + k * 16) = ld_stream16(g + (size_t)i * 16);
+                    }
+                    __syncthreads();
+                    if (threadIdx.x < rows) {   // columns -2, -1 repeat column 0; W, W+1 repeat W-1 (Pillow clamps the tap index)
+                        uint8_t* d = s_rows + threadIdx.x * pitch + WB_PAD;
+                        const uint32_t p = *reinterpret_cast<const uint32_t*>(d) & 0xFFFFFFu;              // pixel 0
+                        const uint32_t q = *reinterpret_cast<const uint32_t*>(d + W * 3 - 4) >> 8;         // pixel W-1
+                        *reinterpret_cast<uint4*>(d - 16) = make_uint4(0u, 0u, p << 16, (p >> 16) | (p << 8));      // .. p p
+                        *reinterpret_cast<uint4*>(d + W * 3) = make_uint4(q | (q << 24), q >> 8, 0u, 0u);           // q q ..
+                    }
+                } else {
+                    v = WarpView{s_rows, W * 3, r0, 0};
+                    block_load_bytes(s_rows, g, rows * W * 3);
+                }
             }
         } else if (nsl) {
             int r0, r1, c0, c1;
@@ -475,142 +536,236 @@ __global__ void __launch_bounds__(THREADS, 3) k_warp_bicubic(const uint8_t* __re
                 *out = bicubic_value64(v.base, v.pitch, v.r0, v.cb, H, W, x, y, c, a, is_persp);
         };
 
-        if (nsl && a[1] == 0.0) {
+        if (nsl && (TILED || pad) && a[1] == 0.0) {   // (an unpadded rectangle of the small-image instantiation: general path)
             // ---- maps whose xin depends on x only (a1 = 0): the reference's skew (image_augmenter.py:50-58: a zoom + shift,
             // a3 = 0 too) and its vertical shear ([1, 0, 0, k, 1, 0], :82: xin = xc, so dx = 0 and the horizontal cubic is the
             // tap itself).  The horizontal cubic of source row r at column x serves every output row of that column whose
             // 4-row window contains r: one output column per thread walking down the band with a rolling window of the
             // four row values per channel; the arithmetic (and so the fp64 decision) is the generic path's, value by value.
+            // Risky values are noted in one bit mask per channel (bit = row of the strip) and queued after the walk: the
+            // walk itself stays free of divergent branches.
             const bool rowonly = (a[3] == 0.0);   // yin depends on y only: row coordinates precomputed per band
             const int ncol = min(tw, THREADS);
             const int strips = max(1, THREADS / ncol);
             const int strip = threadIdx.x / ncol, cx = threadIdx.x - strip * ncol;
             const int rows_per = (y1 - y0 + strips - 1) / strips;
             const int ya = y0 + strip * rows_per, yb_end = min(y1, ya + rows_per);
-            auto columns = [&](auto rowonly_t) {
+            const uint32_t wy_addr = (uint32_t)__cvta_generic_to_shared(s_wy);
+            auto columns = [&](auto rowonly_t, auto pad_t) {
                 constexpr bool ROWONLY = decltype(rowonly_t)::value;
+                constexpr bool PADV = decltype(pad_t)::value;
                 for (int x = x0 + cx; x < x1; x += ncol) {
                     const double xc = (double)x + 0.5;
                     double xin = __dadd_rn(__dmul_rn(a[0], xc), a[2]);
                     const bool xok = !(xin < 0.0 || xin >= (double)W);
                     xin = __dadd_rn(xin, -0.5);
-                    const int xf = (int)floor(xin);
+                    const int xf = xok ? (int)floor(xin) : 0;
                     const float fdx = (float)__dadd_rn(xin, -(double)xf);
                     const CubW wx = cubic_weights(fdx);
                     const double tcol = __dmul_rn(a[3], xc);
                     int xo[4];
 #pragma unroll
                     for (int t = 0; t < 4; ++t) xo[t] = min(max(xf - 1 + t, 0), W - 1) * 3;
-                    // (initialised: rotating indeterminate values is undefined behaviour, and the compiler used it)
+                    // padded rows: tap column xf - 1 starts at byte 3 * (xf - 1) + WB_PAD of its row
+                    const int boff = 3 * xf - 3 + WB_PAD;
+                    const uint8_t* colp = s_rows + (boff & ~3);
+                    const uint32_t s8 = (uint32_t)(boff & 3) * 8u;
+                    // The walk is driven by SOURCE rows, four per round of the outer loop, so that the slot a row value lands
+                    // in (and the order the vertical cubic reads the four slots in) is known at compile time -- no rotation of
+                    // the window registers.  r_next = next source row to push (unclamped); an output row with
+                    // floor(yin - 0.5) = yf is emitted when the last four pushes were rows yf - 1 .. yf + 2 (r_next = yf + 3);
+                    // a row that needs a window which is not the continuation of the current one restarts at yf - 1.
                     float hw[3][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-                    int base = -(1 << 30);  // source row of hw[.][0]
+                    int r_next = -(1 << 30);
+                    int y = ya;
                     uint8_t* dcol = dimg + ((size_t)ya * W + x) * 3;
-                    for (int y = ya; y < yb_end; ++y, dcol += W * 3) {
-                        int yf;
-                        CubW wy;
-                        if (ROWONLY) {
-                            yf = s_yf[y - y0];
-                            const float4 q = s_wy[y - y0];
-                            wy.a = q.x, wy.b = q.y, wy.c = q.z;
-                        } else {   // yin = (a3*xc + a4*yc) + a5, the generic path's operations in the generic path's order
-                            double yin = __dadd_rn(__dadd_rn(tcol, s_trow[y - y0]), a[5]);
-                            const bool yok = !(yin < 0.0 || yin >= (double)H);
-                            yin = __dadd_rn(yin, -0.5);
-                            yf = (int)floor(yin);
-                            wy = cubic_weights((float)__dadd_rn(yin, -(double)yf));
-                            if (!yok) yf = INT_MIN;
-                        }
-                        if (!xok || yf == INT_MIN) {
-                            dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
-                            continue;
-                        }
-                        const int yb = yf - 1;
-                        int shift = yb - base;
-                        if (shift < 0 || shift > 4) shift = 4;
-                        for (int k = 0; k < shift; ++k) {
-                            const uint8_t* rp = s_rows + warp_row_off(v, yb + 4 - shift + k, H);   // shared loads, not generic
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                hw[c][0] = hw[c][1], hw[c][1] = hw[c][2], hw[c][2] = hw[c][3];
-                                // dx = 0: the cubic is (v2 - 2^23) + 0 exactly -- the tap itself
-                                hw[c][3] = (!ROWONLY && fdx == 0.f) ? biased(rp[xo[1] + c]) - 8388608.f
-                                                                    : cubw_b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]),
-                                                                             biased(rp[xo[3] + c]), wx);
-                            }
-                        }
-                        base = yb;
-                        uint32_t risky = 0u;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float fv = cubw(hw[c][0], hw[c][1], hw[c][2], hw[c][3], wy);
-                            bool rk;
-                            dcol[c] = warp_trunc(fv, rk);
-                            risky |= rk ? (1u << c) : 0u;
-                        }
-                        if (risky) {
-                            const int v0 = ((y - y0) * tw + (x - x0)) * 3;
-                            if (risky & 1u) defer(v0 + 0, x, y, 0, dcol + 0);
-                            if (risky & 2u) defer(v0 + 1, x, y, 1, dcol + 1);
-                            if (risky & 4u) defer(v0 + 2, x, y, 2, dcol + 2);
+                    // risky rows of this column, per channel: one bit per row of the strip, the LAST row in bit 0 (the masks
+                    // shift left once per row: rm + rm + risky is a single add-with-carry)
+                    uint32_t rm0 = 0u, rm1 = 0u, rm2 = 0u;
+                    int yf = 0;
+                    CubW wy{0.f, 0.f, 0.f};
+                    bool pend = false;
+                    // Vertical shear (a4 = 1, a5 = 0: yin = a3*xc + yc): along a column yin advances by exactly one per row up to
+                    // the rounding of the fp64 sum (< 1e-9 for coordinates below 2^20), so floor(yin - 0.5) advances by one and
+                    // the fractional part -- all the fp32 weights see -- is the column's, unless it lies within 1e-6 of 0, 0.5
+                    // or 1 (where a floor or the inside test 0 <= yin < H could flip between rows: those columns keep the
+                    // per-row arithmetic).  yin >= 0 <=> yf >= 0, or yf = -1 with a fraction >= 0.5; yin < H likewise.
+                    bool colfast = false;
+                    int yf0 = 0, yf_lo = 0, yf_hi = -1;
+                    if (!ROWONLY && xok && a[4] == 1.0 && a[5] == 0.0) {
+                        const double t0 = __dadd_rn(__dadd_rn(__dadd_rn(tcol, s_trow[ya - y0]), a[5]), -0.5);
+                        const double fl0 = floor(t0), fr = __dadd_rn(t0, -fl0), m = fabs(fr - 0.5);
+                        if (m > 1e-6 && m < 0.5 - 1e-6 && fabs(t0) < 1048576.0) {
+                            colfast = true;
+                            yf0 = (int)fl0;
+                            wy = cubic_weights((float)fr);
+                            yf_lo = fr >= 0.5 ? -1 : 0;
+                            yf_hi = fr >= 0.5 ? H - 2 : H - 1;
                         }
                     }
+                    // coordinates of the next output row that has a source pixel (rows without one are stored as zeros here)
+                    auto fetch = [&]() {
+                        pend = false;
+                        while (y < yb_end) {
+                            if (ROWONLY) {
+                                float4 q;   // s_wy[y - y0] through a hoisted shared-window address (the compiler re-derived it per row)
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w) : "r"(wy_addr + 16u * (uint32_t)(y - y0)));
+                                wy.a = q.x, wy.b = q.y, wy.c = q.z;
+                                yf = __float_as_int(q.w);
+                            } else if (colfast) {   // unit row step: the row index advances by one, the fractional part stays
+                                yf = yf0 + (y - ya);
+                                if (yf < yf_lo || yf > yf_hi) yf = INT_MIN;
+                            } else {   // any other map of this family: per-row fp64 (out of line -- it is the rare case here and
+                                       // five inlined copies of it pushed the walk out of the instruction cache)
+                                const float4 q = warp_row_coords64(tcol, s_trow[y - y0], a[5], H);
+                                wy.a = q.x, wy.b = q.y, wy.c = q.z;
+                                yf = __float_as_int(q.w);
+                            }
+                            if (xok && yf != INT_MIN) {
+                                pend = true;
+                                break;
+                            }
+                            dcol[0] = 0, dcol[1] = 0, dcol[2] = 0;
+                            rm0 += rm0, rm1 += rm1, rm2 += rm2;
+                            ++y, dcol += W * 3;
+                        }
+                    };
+                    fetch();
+                    while (pend) {
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            // window (oldest .. newest) = slots p, p+1, p+2, p+3 (mod 4)
+                            while (pend && yf + 3 == r_next) {
+                                bool rk;
+                                dcol[0] = warp_trunc(cubw(hw[0][p], hw[0][(p + 1) & 3], hw[0][(p + 2) & 3], hw[0][(p + 3) & 3], wy), rk);
+                                rm0 = rm0 + rm0 + (rk ? 1u : 0u);
+                                dcol[1] = warp_trunc(cubw(hw[1][p], hw[1][(p + 1) & 3], hw[1][(p + 2) & 3], hw[1][(p + 3) & 3], wy), rk);
+                                rm1 = rm1 + rm1 + (rk ? 1u : 0u);
+                                dcol[2] = warp_trunc(cubw(hw[2][p], hw[2][(p + 1) & 3], hw[2][(p + 2) & 3], hw[2][(p + 3) & 3], wy), rk);
+                                rm2 = rm2 + rm2 + (rk ? 1u : 0u);
+                                ++y, dcol += W * 3;
+                                fetch();
+                            }
+                            if (!pend) break;
+                            if (yf + 3 < r_next || yf - 1 > r_next) r_next = yf - 1;
+                            const int roff = warp_row_off(v, r_next, H);   // (row - r0) * pitch - cb, row clamped into the image
+                            ++r_next;
+                            if (PADV) {
+                                float t[12];
+                                taps12_biased(colp + (roff - WB_PAD), s8, t);   // cb = -WB_PAD is already inside boff
+#pragma unroll
+                                for (int c = 0; c < 3; ++c)   // dx = 0: the cubic is (v2 - 2^23) + 0 exactly -- the tap itself
+                                    hw[c][p] = (!ROWONLY && fdx == 0.f) ? t[3 + c] - 8388608.f : cubw_b(t[c], t[3 + c], t[6 + c], t[9 + c], wx);
+                            } else {
+                                const uint8_t* rp = s_rows + roff;   // shared loads, not generic
+#pragma unroll
+                                for (int c = 0; c < 3; ++c)
+                                    hw[c][p] = (!ROWONLY && fdx == 0.f) ? biased(rp[xo[1] + c]) - 8388608.f
+                                                                        : cubw_b(biased(rp[xo[0] + c]), biased(rp[xo[1] + c]), biased(rp[xo[2] + c]),
+                                                                                 biased(rp[xo[3] + c]), wx);
+                            }
+                        }
+                    }
+                    const int nrows = yb_end - ya;
+                    auto flush = [&](uint32_t m, int c) {
+                        while (m) {
+                            const int yr = ya + nrows - __ffs(m);   // bit b = row ya + nrows - 1 - b
+                            m &= m - 1u;
+                            defer(((yr - y0) * tw + (x - x0)) * 3 + c, x, yr, c, dimg + ((size_t)yr * W + x) * 3 + c);
+                        }
+                    };
+                    flush(rm0, 0);
+                    flush(rm1, 1);
+                    flush(rm2, 2);
                 }
             };
-            if (strip < strips) {
+            if (strip < strips) {   // one layout per instantiation (padded <=> !TILED): half the code
                 if (rowonly)
-                    columns(std::true_type{});
+                    columns(std::true_type{}, std::integral_constant<bool, !TILED>{});
                 else
-                    columns(std::false_type{});
+                    columns(std::false_type{}, std::integral_constant<bool, !TILED>{});
             }
-        } else if (nsl && (tw & 3) == 0 && a[3] == 0.0 && a[4] == 1.0 && a[5] == 0.0) {
+        } else if (nsl && (TILED || pad) && (tw & 3) == 0 && a[3] == 0.0 && a[4] == 1.0 && a[5] == 0.0) {
             // ---- identity-y maps (the reference's horizontal shear [1, k, 0, 0, 1, 0], image_augmenter.py:82): yin = yc exactly,
             // so yf = y, dy = 0 and cubic(.., 0) = v2: output row y is a 4-tap filter of source row y.  Same thread layout as
             // the general path (4 consecutive pixels of a row per thread) with the row terms hoisted and no row arithmetic.
+            // Risky values are noted in a bit mask (12 bits per round of the loop) and queued after the loop.
             const int band_px = (y1 - y0) * tw;
             const int twsh = ((tw & (tw - 1)) == 0) ? 31 - __clz(tw) : -1;
-            for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
-                const int qy = twsh >= 0 ? (q >> twsh) : q / tw, qx = q - qy * tw;
-                const int y = y0 + qy;
-                const uint8_t* rp = s_rows + (y - v.r0) * v.pitch - v.cb;
-                const double trow = __dmul_rn(a[1], (double)y + 0.5);
-                uint8_t out[12];
+            auto rows4 = [&](auto pad_t) {
+                constexpr bool PADV = decltype(pad_t)::value;
+                unsigned long long rlo = 0ull, rhi = 0ull;   // rounds 0-4 / 5-9 of this thread, 12 bits each
+                int it = 0;
+                for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4, ++it) {
+                    const int qy = twsh >= 0 ? (q >> twsh) : q / tw, qx = q - qy * tw;
+                    const int y = y0 + qy;
+                    const uint8_t* rp = s_rows + (y - v.r0) * v.pitch - v.cb;
+                    const double trow = __dmul_rn(a[1], (double)y + 0.5);
+                    uint8_t out[12];
+                    uint32_t m12 = 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int x = x0 + qx + k;
-                    double xin = __dadd_rn(__dadd_rn(__dmul_rn(a[0], (double)x + 0.5), trow), a[2]);
-                    uint8_t r3[3] = {0, 0, 0};
-                    if (!(xin < 0.0 || xin >= (double)W)) {
-                        xin = __dadd_rn(xin, -0.5);
-                        const int xf = (int)floor(xin);
-                        const CubW wx = cubic_weights((float)__dadd_rn(xin, -(double)xf));
-                        const int xa = min(max(xf - 1, 0), W - 1) * 3, xb = min(max(xf, 0), W - 1) * 3;
-                        const int xc2 = min(max(xf + 1, 0), W - 1) * 3, xd = min(max(xf + 2, 0), W - 1) * 3;
-                        uint32_t risky = 0u;
+                    for (int k = 0; k < 4; ++k) {
+                        const int x = x0 + qx + k;
+                        double xin = __dadd_rn(__dadd_rn(__dmul_rn(a[0], (double)x + 0.5), trow), a[2]);
+                        uint8_t r3[3] = {0, 0, 0};
+                        if (!(xin < 0.0 || xin >= (double)W)) {
+                            xin = __dadd_rn(xin, -0.5);
+                            const int xf = (int)floor(xin);
+                            const CubW wx = cubic_weights((float)__dadd_rn(xin, -(double)xf));
+                            float t[12];
+                            if (PADV) {
+                                const int boff = 3 * xf - 3;   // rp already points at column 0 of the padded row
+                                taps12_biased(rp + (boff & ~3), (uint32_t)(boff & 3) * 8u, t);
+                            } else {
+                                const int xa = min(max(xf - 1, 0), W - 1) * 3, xb = min(max(xf, 0), W - 1) * 3;
+                                const int xc2 = min(max(xf + 1, 0), W - 1) * 3, xd = min(max(xf + 2, 0), W - 1) * 3;
 #pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float fv = cubw_b(biased(rp[xa + c]), biased(rp[xb + c]), biased(rp[xc2 + c]), biased(rp[xd + c]), wx);
-                            bool rk;
-                            r3[c] = warp_trunc(fv, rk);
-                            risky |= rk ? (1u << c) : 0u;
+                                for (int c = 0; c < 3; ++c)
+                                    t[c] = biased(rp[xa + c]), t[3 + c] = biased(rp[xb + c]), t[6 + c] = biased(rp[xc2 + c]), t[9 + c] = biased(rp[xd + c]);
+                            }
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                bool rk;
+                                r3[c] = warp_trunc(cubw_b(t[c], t[3 + c], t[6 + c], t[9 + c], wx), rk);
+                                if (rk) m12 |= 1u << (k * 3 + c);
+                            }
                         }
-                        if (risky) {
-                            if (risky & 1u) defer((q + k) * 3 + 0, x, y, 0, &r3[0]);
-                            if (risky & 2u) defer((q + k) * 3 + 1, x, y, 1, &r3[1]);
-                            if (risky & 4u) defer((q + k) * 3 + 2, x, y, 2, &r3[2]);
-                        }
+                        out[k * 3] = r3[0], out[k * 3 + 1] = r3[1], out[k * 3 + 2] = r3[2];
                     }
-                    out[k * 3] = r3[0], out[k * 3 + 1] = r3[1], out[k * 3 + 2] = r3[2];
+                    uint8_t* d = dimg + ((size_t)y * W + x0 + qx) * 3;
+                    if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                        uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
+                        d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+                        d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+                        d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+                    } else {
+                        for (int i = 0; i < 12; ++i) d[i] = out[i];
+                    }
+                    if (it < 5)
+                        rlo |= (unsigned long long)m12 << (12 * it);
+                    else if (it < 10)
+                        rhi |= (unsigned long long)m12 << (12 * (it - 5));
+                    else   // (bands of more than 10 rounds do not occur with WB_ROWS x WB_COLS tiles; kept for safety)
+                        for (; m12; m12 &= m12 - 1u) {
+                            const int bit = __ffs(m12) - 1, k = bit / 3, c = bit - 3 * k;
+                            defer((q + k) * 3 + c, x0 + qx + k, y, c, d + k * 3 + c);
+                        }
                 }
-                uint8_t* d = dimg + ((size_t)y * W + x0 + qx) * 3;
-                if ((reinterpret_cast<uintptr_t>(d) & 3) == 0) {
-                    uint32_t* d32 = reinterpret_cast<uint32_t*>(d);
-                    d32[0] = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
-                    d32[1] = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
-                    d32[2] = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
-                } else {
-                    for (int i = 0; i < 12; ++i) d[i] = out[i];
-                }
-            }
+                auto flush = [&](unsigned long long m, int it0) {
+                    while (m) {
+                        const int bit = __ffsll((long long)m) - 1;
+                        m &= m - 1ull;
+                        const int r = bit / 12, kc = bit - 12 * r, k = kc / 3, c = kc - 3 * k;
+                        const int q = threadIdx.x * 4 + (it0 + r) * THREADS * 4;
+                        const int qy = twsh >= 0 ? (q >> twsh) : q / tw, qx = q - qy * tw;
+                        const int x = x0 + qx + k, y = y0 + qy;
+                        defer((q + k) * 3 + c, x, y, c, dimg + ((size_t)y * W + x) * 3 + c);
+                    }
+                };
+                flush(rlo, 0);
+                flush(rhi, 5);
+            };
+            rows4(std::integral_constant<bool, !TILED>{});
         } else {
             const int band_px = (y1 - y0) * tw;
             for (int q = threadIdx.x * 4; q < band_px; q += THREADS * 4) {
@@ -1385,10 +1540,12 @@ extern "C" int lfx_warp_bicubic(const uint8_t* src, uint8_t* dst, int B, int H, 
     }
     const int ntx = lfx_div_up(W, WB_COLS);
     dim3 grid(lfx_div_up(H, WB_ROWS) * ntx, B);
+    const uint32_t n16 = (uint32_t)max(1, (W * 3) >> 4);
+    const uint32_t m32 = (uint32_t)((0x100000000ull + n16 - 1) / n16);   // i / n16 = umulhi(i, m32) for i < 2^32 / n16
     if (ntx == 1)
-        k_warp_bicubic<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc);
+        k_warp_bicubic<false><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc, m32);
     else
-        k_warp_bicubic<true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc);
+        k_warp_bicubic<true><<<grid, THREADS, smem, (cudaStream_t)stream>>>(src, dst, H, W, coef, perspective, smem, ntx, src_index, nsrc, m32);
     return lfx_check_launch("warp_bicubic");
 }
 

@@ -6,10 +6,11 @@
 //
 // One warp per stream (image): the 624-word state lives in shared memory.  A 624-word block is exactly 156 attempts
 // and attempt t consumes words 4t..4t+3, so lane j of round c twists the four words of attempt t = 32c + j itself
-// (ascending quads, loads - __syncwarp - stores: every operand is then either still old or already new exactly as in
-// the sequential generator: word i reads i+1 -- old, or new[0] for i = 623 -- and i+397, which is old for i < 227 and
-// was stored by an earlier round otherwise), tempers them in registers and evaluates its attempt; accepted attempts
-// are compacted with a warp ballot.
+// (ascending quads; every operand is either still old or already new exactly as in the sequential generator: word i
+// reads i+1 -- old, passed between neighbouring lanes by shuffle, or new[0] for i = 623 -- and i+397, which is old for
+// i < 227 and was stored by an earlier round otherwise), tempers the two words the fast path needs straight from its
+// registers and evaluates its attempt; accepted attempts are compacted with a warp ballot.  ~105 warp instructions per
+// round (the first version, which twisted the block, re-read it and branched per attempt, needed 195).
 //
 // Arithmetic.  The reference is fp64 (explicit round-to-nearest without FMA contraction: the host libraries are built
 // without FMA); CUDA's log() is within 1 ulp of glibc's, which can move a result only when 5*g lies within an ulp of
@@ -34,11 +35,6 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= (y >> 18);
     return y;
 }
-__device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t nxt, uint32_t far) {
-    const uint32_t y = (cur & 0x80000000u) | (nxt & 0x7FFFFFFFu);
-    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
-}
-
 // fp64 reference evaluation of one attempt -> accepted?, the two bytes
 __device__ __noinline__ bool attempt64(uint32_t a, uint32_t bq, uint32_t c, uint32_t d, double loc, double scale, uint8_t& o0, uint8_t& o1) {
     const double d1 = __ddiv_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)bq), 9007199254740992.0);
@@ -54,18 +50,26 @@ __device__ __noinline__ bool attempt64(uint32_t a, uint32_t bq, uint32_t c, uint
     return true;
 }
 
-// byte of an fp32 value known to within 7e-5; false when fp64 has to decide
-__device__ __forceinline__ bool byte32(float g, uint8_t& o) {
-    if (fabsf(g) < 0.5f) {
-        o = 0;
-        return true;
-    }
-    o = (uint8_t)(int)g;
-    return fabsf(g - rintf(g)) >= LFX_RNG_EPS;
+// (cur & 0x80000000) | (nxt & 0x7FFFFFFF) as ONE bit-select (LOP3 0xE4), then the twist: 5 instructions per word
+__device__ __forceinline__ uint32_t mt_twist5(uint32_t cur, uint32_t nxt, uint32_t far) {
+    uint32_t y;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xE4;" : "=r"(y) : "r"(cur), "r"(nxt));
+    uint32_t mag;   // (nxt & 1) * 0x9908B0DF as an IMAD: the multiply pipe is idle, the logic pipe is the busy one
+    asm("mul.lo.u32 %0, %1, 0x9908B0DF;" : "=r"(mag) : "r"(nxt & 1u));
+    return far ^ (y >> 1) ^ mag;
+}
+// the top 27 bits of the tempered word (genrand_res53's a = genrand() >> 5), last temper step folded into the shift
+__device__ __forceinline__ uint32_t mt_temper_hi27(uint32_t y) {
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9D2C5680u;
+    y ^= (y << 15) & 0xEFC60000u;
+    return (y >> 5) ^ (y >> 23);
 }
 
+// FAST: loc == 0 and |scale| <= 8 (the fp32 error bound in the header); otherwise every attempt is evaluated in fp64.
+template <bool FAST>
 __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint32_t* __restrict__ seeds, uint8_t* __restrict__ out, int B,
-                                                                    int n, double loc, double scale, int fast) {
+                                                                    int n, double loc, double scale) {
     __shared__ __align__(16) uint32_t s_mt[RNG_WARPS][624];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int b = blockIdx.x * RNG_WARPS + wid;
@@ -80,74 +84,84 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
     }
     __syncwarp();
     uint8_t* o = out + (size_t)b * n;
+    asm volatile("" : "+l"(o));   // keep the stream's base in registers (the compiler re-derived it from the parameters per store)
     const bool pair_ok = ((reinterpret_cast<uintptr_t>(o) & 1) == 0);
     const float fscale = (float)scale;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    // Round c (0..4) gives lane j the quad of attempt t = 32c + j: words i0 = 128c + 4j .. i0 + 3.  Word i needs word i + 1
+    // (old; the first word of the NEXT lane's quad comes by shuffle, so no lane reads a word another lane stores in the
+    // same round) and word i + 397 mod 624: quad i0 + 396 (.y .z .w) and the word after it.  i0 + 396 < 624 in round 0
+    // and for lanes < 25 of round 1 (old values, stored by rounds 3 / 4 only); it wraps to i0 - 228 otherwise (new
+    // values, stored by earlier rounds).  Everything but round 1's lane-dependent wrap folds into immediate offsets.
+    uint32_t* const mq = mt + 4 * lane;
+    const uint32_t* const far1 = mq + 128 + (lane < 25 ? 396 : -228);
+    const uint32_t* const far1n = (lane == 24) ? mt : far1 + 4;   // word 624 = word 0 (new)
+    constexpr uint32_t ACC = 1u << 31, SLOW = 1u << 30;   // ACC in the sign bit: one compare
     int produced = 0;  // normals written so far (warp-uniform, always even)
     while (produced < n) {
-        // ---- phase 1: twist the whole 624-word block in place, five rounds of one quad per lane
-#pragma unroll 1
-        for (int t0 = 0; t0 < 156; t0 += 32) {
-            const int t = t0 + lane;
-            const bool act = t < 156;
-            uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-            if (act) {
-                const int i0 = 4 * t;
-                const uint4 q = *reinterpret_cast<const uint4*>(mt + i0);
-                const uint32_t nx = mt[i0 + 4 == 624 ? 0 : i0 + 4];
-                int j = i0 + 396;  // quad holding words i0+397..i0+399 in .y .z .w (i0 + 397 = 1 mod 4)
-                if (j >= 624) j -= 624;
-                const uint4 m = *reinterpret_cast<const uint4*>(mt + j);
-                const uint32_t m3 = mt[j + 4 == 624 ? 0 : j + 4];
-                w0 = mt_twist(q.x, q.y, m.y);
-                w1 = mt_twist(q.y, q.z, m.z);
-                w2 = mt_twist(q.z, q.w, m.w);
-                w3 = mt_twist(q.w, nx, m3);
-            }
-            __syncwarp();
-            if (act) *reinterpret_cast<uint4*>(mt + 4 * t) = make_uint4(w0, w1, w2, w3);
-            __syncwarp();
-        }
-        // ---- phase 2: the 156 attempts of the block.  The five rounds are independent of each other (no barrier, no
-        // shared-memory write), so they are unrolled: the long fp32 chains (log, divide, square root) of one round hide
-        // behind the others.  Result of a round, one word per lane: byte 0 / 1 = the two output bytes, bit 16 = accepted,
-        // bit 17 = fp64 has to decide (kept in registers: arrays of flags and bytes ended up in local memory).
-        constexpr uint32_t ACC = 1u << 16, SLOW = 1u << 17;
+        // Result of a round, one word per lane: byte 0 / 1 = the two output bytes, bit 31 = accepted, bit 30 = fp64 has
+        // to decide.  The rounds are unrolled: the fp32 chain (log, reciprocal, square root) of one hides behind the
+        // twist of the next.
         uint32_t res[5];
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-            const int t = c * 32 + lane;
+            const bool act = (c < 4) || (lane < 28);   // 156 = 4 * 32 + 28 attempts per block
+            uint4 q = make_uint4(0u, 0u, 0u, 0u);
+            if (act) q = *reinterpret_cast<const uint4*>(mq + 128 * c);
+            uint32_t nx = __shfl_down_sync(0xffffffffu, q.x, 1);
+            if (c < 4) {
+                if (lane == 31) nx = mq[128 * c + 4];   // first word of the next round: still old
+            } else {
+                if (lane == 27) nx = mt[0];             // word 624 = word 0, new since round 0
+            }
+            uint32_t w0 = 0u, w2 = 0u;
+            if (act) {
+                const uint32_t* fp = (c == 0) ? mq + 396 : (c == 1) ? far1 : mq + (128 * c - 228);
+                const uint32_t* fn = (c == 1) ? far1n : fp + 4;
+                const uint4 m = *reinterpret_cast<const uint4*>(fp);
+                const uint32_t m3 = *fn;
+                w0 = mt_twist5(q.x, q.y, m.y);
+                const uint32_t w1 = mt_twist5(q.y, q.z, m.z);
+                w2 = mt_twist5(q.z, q.w, m.w);
+                const uint32_t w3 = mt_twist5(q.w, nx, m3);
+                *reinterpret_cast<uint4*>(mq + 128 * c) = make_uint4(w0, w1, w2, w3);
+            }
+            __syncwarp();   // the next rounds read these words
             uint32_t r = 0u;
-            if (t < 156) {
-                if (!fast) {
-                    r = SLOW;
-                } else {
-                    // the low words (26 of the 53 bits of each double) move x by less than 2^-26 = u/4: the fast path
-                    // leaves them untempered (budgeted above); the fp64 re-evaluation tempers all four words
-                    const uint2 q = *reinterpret_cast<const uint2*>(mt + 4 * t);
-                    const uint2 q2 = *reinterpret_cast<const uint2*>(mt + 4 * t + 2);
-                    const uint32_t a = mt_temper(q.x) >> 5, cc = mt_temper(q2.x) >> 5;
-                    const float x1 = (float)((int)a - (1 << 26)) * 0x1p-26f;
-                    const float x2 = (float)((int)cc - (1 << 26)) * 0x1p-26f;
-                    const float r2 = fmaf(x1, x1, x2 * x2);
-                    if (fabsf(r2 - 1.f) <= 1e-6f || r2 < 1e-8f) {
-                        r = SLOW;   // the acceptance test (or, 2^-54 of the attempts, whether r2 is zero) needs the exact radius
-                    } else if (r2 < 1.f) {
-                        // fast units (MUFU lg2 / rcp / rsq: a few ulp each, |L| abs 4e-7 near 1) -- inside the error budget above
-                        const float q3 = __fdividef(-2.f * __logf(r2), r2);
-                        float rs;
-                        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(q3));
-                        const float f = fscale * (q3 * rs);
-                        uint8_t b0, b1;
-                        const bool k0 = byte32(f * x2, b0), k1 = byte32(f * x1, b1);
-                        r = (uint32_t)b0 | ((uint32_t)b1 << 8) | ACC | ((k0 && k1) ? 0u : SLOW);
-                    }
-                }
+            if (!FAST) {
+                r = act ? SLOW : 0u;
+            } else {
+                // the low words (26 of the 53 bits of each double) move x by less than 2^-26 = u/4: the fast path leaves
+                // them untempered (budgeted above); the fp64 re-evaluation tempers all four words.  Branch-free: a warp
+                // always holds accepted attempts, so rejected lanes just compute a value nobody selects.
+                const uint32_t a = mt_temper_hi27(w0), cc = mt_temper_hi27(w2);
+                const float x1 = (float)((int)a - (1 << 26)) * 0x1p-26f;
+                const float x2 = (float)((int)cc - (1 << 26)) * 0x1p-26f;
+                const float r2 = fmaf(x1, x1, x2 * x2);
+                // fast units (MUFU lg2 / rcp / rsq: a few ulp each, |L| abs 4e-7 near 1) -- inside the error budget above
+                float l2, rc, rs;
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(r2));
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(r2));
+                const float q3 = (l2 * -1.3862943611198906f) * rc;   // -2 ln(r2) / r2
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(q3));
+                const float f = fscale * (q3 * rs);
+                const float g0 = f * x2, g1 = f * x1;
+                const int i0 = (int)g0, i1 = (int)g1;   // |g| < 0.5 truncates to 0 whatever the error
+                const bool k0 = (fabsf(g0) < 0.5f) || (fabsf(g0 - rintf(g0)) >= LFX_RNG_EPS);
+                const bool k1 = (fabsf(g1) < 0.5f) || (fabsf(g1 - rintf(g1)) >= LFX_RNG_EPS);
+                // 1e-8 <= r2 < 1 - 1e-6: decided here; r2 > 1 + 1e-6: rejected; between (the acceptance test itself, or
+                // -- 2^-54 of the attempts -- whether r2 is zero): the exact radius is needed
+                const bool in_fast = (r2 >= 1e-8f) && (r2 < 1.f - 1e-6f);
+                const bool out = r2 > 1.f + 1e-6f;
+                const uint32_t bytes = __byte_perm((uint32_t)i0 & 0xFFu, (uint32_t)i1, 0x3340);
+                r = in_fast ? (bytes | ACC | ((k0 && k1) ? 0u : SLOW)) : (out ? 0u : SLOW);
+                if (!act) r = 0u;
             }
             res[c] = r;
         }
         // the rare fp64 re-evaluations after all five fast rounds (0.15 % of the attempts: one warp in five has any)
         if (__any_sync(0xffffffffu, ((res[0] | res[1] | res[2] | res[3] | res[4]) & SLOW) != 0u)) {
-#pragma unroll 1
+#pragma unroll   // (res[] indexed by a run-time c would live in local memory)
             for (int c = 0; c < 5; ++c) {
                 if (res[c] & SLOW) {
                     const uint4 q = *reinterpret_cast<const uint4*>(mt + 4 * (c * 32 + lane));
@@ -157,20 +171,30 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
                 }
             }
         }
+        if (pair_ok && produced + 2 * 156 <= n) {   // the whole block fits: 16-bit stores, no per-lane bound checks
+            uint32_t pairs = (uint32_t)produced >> 1;
 #pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            const bool acc = (res[c] & ACC) != 0u;
-            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-            if (acc) {
-                const int k = produced + 2 * __popc(bal & ((1u << lane) - 1u));
-                if (k + 1 < n && pair_ok) {
-                    *reinterpret_cast<uint16_t*>(o + k) = (uint16_t)res[c];
-                } else {
+            for (int c = 0; c < 5; ++c) {
+                const bool acc = (int)res[c] < 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+                uint64_t dst;   // o + 2 * (pairs + rank among the accepted lanes): one IMAD.WIDE
+                asm("mad.wide.u32 %0, %1, 2, %2;" : "=l"(dst) : "r"(pairs + __popc(bal & lt_mask)), "l"(o));
+                if (acc) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)res[c];
+                pairs += __popc(bal);
+            }
+            produced = (int)(pairs << 1);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                const bool acc = (int)res[c] < 0;
+                const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+                if (acc) {
+                    const int k = produced + 2 * __popc(bal & lt_mask);
                     if (k < n) o[k] = (uint8_t)res[c];
                     if (k + 1 < n) o[k + 1] = (uint8_t)(res[c] >> 8);
                 }
+                produced += 2 * __popc(bal);
             }
-            produced += 2 * __popc(bal);
         }
     }
 }
@@ -181,7 +205,10 @@ extern "C" int lfx_legacy_normal_u8(const uint32_t* seeds, uint8_t* out, int B, 
     LFX_REQUIRE_READY();
     if (B == 0 || n == 0) return LFX_OK;
     LFX_REQUIRE(seeds && out && B > 0 && n > 0, LFX_ERR_ARG, "legacy_normal_u8: bad arguments");
-    const int fast = (loc == 0.0 && fabs(scale) <= 8.0) ? 1 : 0;   // the fp32 error bound above assumes |g| <= 8 * 12
-    k_legacy_normal_u8<<<lfx_div_up(B, RNG_WARPS), RNG_WARPS * 32, 0, (cudaStream_t)stream>>>(seeds, out, B, n, loc, scale, fast);
+    const bool fast = (loc == 0.0 && fabs(scale) <= 8.0);   // the fp32 error bound above assumes |g| <= 8 * 12
+    if (fast)
+        k_legacy_normal_u8<true><<<lfx_div_up(B, RNG_WARPS), RNG_WARPS * 32, 0, (cudaStream_t)stream>>>(seeds, out, B, n, loc, scale);
+    else
+        k_legacy_normal_u8<false><<<lfx_div_up(B, RNG_WARPS), RNG_WARPS * 32, 0, (cudaStream_t)stream>>>(seeds, out, B, n, loc, scale);
     return lfx_check_launch("legacy_normal_u8");
 }
