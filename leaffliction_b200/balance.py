@@ -164,7 +164,7 @@ class DatasetBalancer:
     the augmentations themselves run as GPU batches of `batch` tasks on this rank's shard."""
 
     def __init__(self, manifest_path=None, source_dir="images", target_dir="augmented_directory", seed=42, workers=None,
-                 rank: int = 0, world: int = 1, batch: int = 256):
+                 rank: int = 0, world: int = 1, batch: int = 256, gpu_jpeg: bool = False):
         from . import augment
         self.manifest_path = Path(manifest_path) if manifest_path else None
         self.source_dir = Path(source_dir)
@@ -173,6 +173,9 @@ class DatasetBalancer:
         # JPEG decode / encode threads (Pillow releases the GIL there); the reference's default is one process per core
         self.workers = max(1, int(workers)) if workers else max(1, min(8, os.cpu_count() or 1))
         self.rank, self.world, self.batch = int(rank), int(world), int(batch)
+        # gpu_jpeg: sources are decoded and outputs encoded by nvJPEG (leaffliction_b200.jpegio), pixels stay in HBM between
+        # the two; the default keeps the reference's Pillow codec, so that outputs match it bit for bit before encoding
+        self.gpu_jpeg = bool(gpu_jpeg)
         self.counts: Dict[str, Dict[str, int]] = {}
         self.plan: Dict[str, Dict[str, int]] = {}
         self.completed = 0
@@ -261,6 +264,10 @@ class DatasetBalancer:
         with ThreadPoolExecutor(max_workers=self.workers) as io:
             for b0 in range(0, len(mine), self.batch):
                 chunk = mine[b0:b0 + self.batch]
+                if self.gpu_jpeg:
+                    chunk = self._run_chunk_on_device(chunk)     # returns the tasks it could not take (other sizes, bad files)
+                    if not chunk:
+                        continue
                 loaded = list(io.map(try_load, chunk))
                 good = [t for t, a in zip(chunk, loaded) if a is not None]
                 imgs = [a for a in loaded if a is not None]
@@ -276,6 +283,49 @@ class DatasetBalancer:
         done, _ = allreduce_histograms(np.array([self.completed, self.failed], np.int64))
         logger.info(f"Augmentation complete: {int(done[0])} images generated, {int(done[1])} failed")
         self._barrier()
+
+    def _run_chunk_on_device(self, chunk):
+        """nvJPEG file boundary: the chunk's distinct sources are decoded into one device batch, the tasks run on it in place
+        (augment.augment_device: kernels read source src_index[i]), every output is encoded from device memory.  Tasks whose
+        source has another size than the chunk's first image, or does not decode, are returned for the host-codec path."""
+        import dataclasses
+
+        from . import augment, jpegio
+        srcs = sorted({str(t.source_img) for t in chunk})
+        index = {p: i for i, p in enumerate(srcs)}
+        try:
+            blobs = jpegio.read_files(srcs, self.workers)
+            first = next((b for b in blobs if b), None)
+            if first is None:
+                return chunk
+            H, W, _ = jpegio.probe(first)
+            x, status = jpegio.decode_batch(blobs, H, W)
+        except Exception as e:
+            logger.error(f"nvJPEG decode failed, host codec takes this batch - {e}")
+            return chunk
+        good = [t for t in chunk if status[index[str(t.source_img)]] == 0]
+        rest = [t for t in chunk if status[index[str(t.source_img)]] != 0]
+        if not good:
+            return rest
+        try:
+            out = augment.augment_device(x, [dataclasses.replace(t, source_index=index[str(t.source_img)]) for t in good])
+            written = 0
+            for key, val in out.items():
+                if key == "rotate":
+                    ids, slab, hw = val
+                    for k, i in enumerate(ids):
+                        nh, nw = int(hw[k][0]), int(hw[k][1])
+                        img = slab[k, :nh * nw * 3].view(1, nh, nw, 3)
+                        written += sum(jpegio.encode_to_files(img, [good[i].output_path], 95, 420, 1))
+                else:
+                    ids, batch = val
+                    written += sum(jpegio.encode_to_files(batch, [good[i].output_path for i in ids], 95, 420, self.workers))
+            self.completed += written
+            self.failed += len(good) - written
+        except Exception as e:
+            logger.error(f"Batch failed - {e}")
+            self.failed += len(good)
+        return rest
 
     def run(self):
         logger.info("=== Dataset Balancing System ===")

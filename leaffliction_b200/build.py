@@ -10,6 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libleafx.so")
+OUT_JPEG = os.path.join(HERE, "libleafx_jpeg.so")     # nvJPEG file boundary (include/leafx_jpeg.h), a separate object
 SOURCES = ["lfx_api.cu", "lfx_color.cu", "lfx_augment.cu", "lfx_gauss.cu", "lfx_mask.cu", "lfx_roi.cu", "lfx_contour.cu", "lfx_front.cu", "lfx_core.cu", "lfx_gauss_tma.cu", "lfx_rng.cu", "lfx_params.cu", "lfx_resize.cu", "lfx_score.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "--use_fast_math=false"]
@@ -26,8 +27,22 @@ def _stale() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "leafx.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "lfx_jpeg.cu"] + [os.path.join(HERE, "..", "include", "leafx.h")]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_jpeg(force: bool = False) -> str:
+    """libleafx_jpeg.so = csrc/lfx_jpeg.cu + libnvjpeg (CUDA toolkit)."""
+    src = os.path.join(CSRC, "lfx_jpeg.cu")
+    hdr = os.path.join(HERE, "..", "include", "leafx_jpeg.h")
+    if not force and os.path.exists(OUT_JPEG) and os.path.getmtime(OUT_JPEG) >= max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return OUT_JPEG
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+           src, "-o", OUT_JPEG, "-lnvjpeg", "-lcudart", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"nvcc failed for lfx_jpeg.cu:\n{r.stdout}\n{r.stderr}")
+    return OUT_JPEG
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -61,3 +76,4 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_jpeg(force="--force" in sys.argv))

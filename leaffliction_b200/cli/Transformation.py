@@ -45,6 +45,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--skip-existing", action="store_true", help="Skip images whose outputs already exist")
     p.add_argument("--overwrite", action="store_true", help="Overwrite existing outputs")
     p.add_argument("--preview", action="store_true", help="Force saving outputs (no GUI popups)")
+    p.add_argument("--gpu-jpeg", action="store_true", help="(extension, folder mode) decode the sources and encode the outputs on the "
+                                                            "GPU with nvJPEG instead of Pillow")
     return p
 
 
@@ -56,13 +58,16 @@ def _want(params: ProcessArgs, out: Path) -> bool:
     return params.overwrite or (not params.skip_existing or not out.exists())   # Transformation.py:461
 
 
-def process_single_image(params: ProcessArgs, premade=None) -> List[Path]:
-    """Transformation.py:423-536.  `premade` = (mask, contour) from a batched make_mask (folder mode)."""
-    try:
-        rgb = T.pil_read_rgb(params.img_path)
-    except Exception as exc:
-        logging.error("Failed to read %s (%s)", params.img_path, exc)
-        return []
+def process_single_image(params: ProcessArgs, premade=None, rgb=None, sink=None) -> List[Path]:
+    """Transformation.py:423-536.  `premade` = (mask, contour) from a batched make_mask (folder mode); `rgb` = the already
+    decoded image; `sink`: a list that receives (path, image) instead of the file being written here (folder mode with
+    --gpu-jpeg encodes them as one batch)."""
+    if rgb is None:
+        try:
+            rgb = T.pil_read_rgb(params.img_path)
+        except Exception as exc:
+            logging.error("Failed to read %s (%s)", params.img_path, exc)
+            return []
     pipe = T.TransformPipeline(params.cfg)
     names = T.output_names(params.img_path.stem)
     saved: List[Path] = []
@@ -74,8 +79,11 @@ def process_single_image(params: ProcessArgs, premade=None) -> List[Path]:
 
     def save(kind, img):
         out = params.out_dir / names[kind]
-        if _want(params, out):
-            T.imwrite_rgb(out, img)
+        if _want(params, out) and img is not None:
+            if sink is not None:
+                sink.append((out, np.ascontiguousarray(img)))
+            else:
+                T.imwrite_rgb(out, img)
             saved.append(out)
 
     if "Mask" in params.types:
@@ -102,10 +110,57 @@ def process_single_image(params: ProcessArgs, premade=None) -> List[Path]:
     return saved
 
 
+def _decode_chunk_nvjpeg(chunk, nthreads):
+    """Sources of one chunk through nvJPEG, grouped by header size; anything it refuses falls back to Pillow."""
+    from leaffliction_b200 import jpegio
+    blobs = jpegio.read_files(chunk, nthreads)
+    arrays = [None] * len(chunk)
+    groups = {}
+    for i, b in enumerate(blobs):
+        try:
+            h, w, _ = jpegio.probe(b) if b else (0, 0, 0)
+        except Exception:
+            h = w = 0
+        if h and w:
+            groups.setdefault((h, w), []).append(i)
+    for (h, w), ids in groups.items():
+        x, status = jpegio.decode_batch([blobs[i] for i in ids], h, w)
+        host = x.cpu().numpy()
+        for k, i in enumerate(ids):
+            if status[k] == 0:
+                arrays[i] = host[k]
+    for i, a in enumerate(arrays):
+        if a is None:
+            try:
+                arrays[i] = T.pil_read_rgb(chunk[i])
+            except Exception:
+                pass
+    return arrays
+
+
+def _encode_sink_nvjpeg(sink, nthreads):
+    """(path, image) pairs -> files, one nvJPEG batch per image shape (grey images are replicated to RGB)."""
+    import torch
+
+    from leaffliction_b200 import jpegio
+    groups = {}
+    for k, (_, img) in enumerate(sink):
+        if img.ndim == 2:
+            sink[k] = (sink[k][0], np.repeat(img[:, :, None], 3, axis=2))
+        groups.setdefault(sink[k][1].shape, []).append(k)
+    for ids in groups.values():
+        batch = torch.from_numpy(np.stack([sink[k][1] for k in ids])).cuda()
+        ok = jpegio.encode_to_files(batch, [sink[k][0] for k in ids], 95, 420, nthreads)
+        for k, good in zip(ids, ok):
+            if not good:
+                T.imwrite_rgb(sink[k][0], sink[k][1])
+
+
 def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: bool, overwrite: bool, batch: int = 256,
-               workers: int = 0):
+               workers: int = 0, gpu_jpeg: bool = False):
     """Folder mode (:664-699): images grouped by shape, make_mask batched per group on the GPU; `workers` threads
-    decode the JPEGs (0 = auto = min(8, cpu // 2), the reference's rule :672-674)."""
+    decode the JPEGs (0 = auto = min(8, cpu // 2), the reference's rule :672-674).  `gpu_jpeg`: the codec runs on the GPU
+    (nvJPEG) for sources and outputs."""
     import os
     from concurrent.futures import ThreadPoolExecutor
     nthreads = workers if workers and workers > 0 else max(1, min(8, (os.cpu_count() or 2) // 2))
@@ -123,8 +178,12 @@ def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: b
     total = 0
     for b0 in range(0, len(imgs), batch):
         chunk = imgs[b0:b0 + batch]
-        with ThreadPoolExecutor(max_workers=nthreads) as io:
-            arrays = list(io.map(try_read, chunk))
+        if gpu_jpeg:
+            arrays = _decode_chunk_nvjpeg(chunk, nthreads)
+        else:
+            with ThreadPoolExecutor(max_workers=nthreads) as io:
+                arrays = list(io.map(try_read, chunk))
+        sink = [] if gpu_jpeg else None
         premade = [None] * len(chunk)
         by_shape = {}
         for i, a in enumerate(arrays):
@@ -142,9 +201,11 @@ def run_folder(src: Path, dst: Path, types: Sequence[str], cfg, skip_existing: b
             if a is not None and pm is None:
                 continue                # its group failed above
             try:
-                total += len(process_single_image(ProcessArgs(ip, dst, tuple(types), cfg, skip_existing, overwrite), pm))
+                total += len(process_single_image(ProcessArgs(ip, dst, tuple(types), cfg, skip_existing, overwrite), pm, rgb=a, sink=sink))
             except Exception as e:      # Transformation.py:700-705: a failing image is logged, the folder run continues
                 logging.error("Failed to process %s - %s", ip, e)
+        if sink:
+            _encode_sink_nvjpeg(sink, nthreads)
     logging.info("Processed %d images, saved %d outputs", len(imgs), total)
     return total
 
@@ -177,7 +238,7 @@ def main(argv=None) -> None:
             logging.error("Source directory does not exist: %s", src)
             return
         dst.mkdir(parents=True, exist_ok=True)
-        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite, workers=args.workers)
+        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite, workers=args.workers, gpu_jpeg=args.gpu_jpeg)
         return
     logging.error("Must specify either single image or --src/--dst for folder mode")
 

@@ -91,3 +91,24 @@ def test_cubic_table_matches_oracle_taps():
         assert lib.lfx_cubic_table(a, b, f.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p)) == 0
         s, ww = sf.cubic_taps(a, b)
         assert np.array_equal(f, s) and np.array_equal(w, ww), (a, b)
+
+
+def test_jpeg_library_exports_header_symbols_and_has_no_cpu_fallback():
+    """include/leafx_jpeg.h (nvJPEG file boundary): libleafx_jpeg.so loads, exports every declared symbol, and refuses
+    to initialise without a CUDA device."""
+    import torch
+
+    from leaffliction_b200 import jpegio
+    txt = open(os.path.join(ROOT, "include", "leafx_jpeg.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lfx_jpeg_[a-z0-9_]+)\s*\(", txt)))
+    assert len(names) == 8
+    lib = jpegio.load()
+    assert not [n for n in names if not hasattr(lib, n)]
+    assert set(names) == set(jpegio.exported_symbols())
+    if not torch.cuda.is_available():
+        assert lib.lfx_jpeg_init(0, 0, 1) == -2
+        assert b"no CPU fallback" in lib.lfx_jpeg_last_error()
+        assert lib.lfx_jpeg_backend() == -1
+        with pytest.raises(jpegio.JpegError):
+            jpegio.decode_batch([b"x"], 8, 8)
