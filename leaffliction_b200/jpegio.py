@@ -68,8 +68,9 @@ def _check(rc: int):
         raise JpegError(f"libleafx_jpeg error {rc}: {(load().lfx_jpeg_last_error() or b'').decode()}")
 
 
-def init(device: int = 0, backend: int = 0, threads: Optional[int] = None):
-    """lfx_jpeg_init; `threads` encoder states (default: the CPU affinity, at most 16)."""
+def init(device: int = 0, backend: int = 2, threads: Optional[int] = None):
+    """lfx_jpeg_init; backend 2 = nvJPEG GPU_HYBRID (Huffman decode on the GPU: 38 k 256x256 images/s on a B200 against 3 k
+    with the default backend, profiles/r02_jpeg.json); `threads` encoder states (default: the CPU affinity, at most 16)."""
     global _inited
     lib = load()
     if threads is None:

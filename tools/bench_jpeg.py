@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--size", type=int, default=256)
-    ap.add_argument("--backend", type=int, default=0)
+    ap.add_argument("--backend", type=int, default=2)
     ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     import torch
