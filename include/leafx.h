@@ -215,6 +215,15 @@ int lfx_analyze_record(const int32_t* points, const int32_t* counts, const int64
 int lfx_strategy_raw(const uint8_t* src, uint8_t* raw, int B, int H, int W, const lfx_mask_cfg* cfg /* host */,
                      void* workspace, size_t workspace_bytes, lfx_stream_t stream);
 
+/* k-means raw candidate: `_create_kmeans_mask` (srcs/transform/filters/mask.py:109-140) = cv2.setRNGSeed(seed = 12345),
+ * cv2.kmeans(K = 3, (EPS + MAX_ITER, 20, 0.5), 1 attempt, KMEANS_PP_CENTERS), cluster chosen by hue / bg_bias / saturation.
+ * cv::kmeans and cv::RNG are restated exactly (labels and centres bit-identical to OpenCV 4.13, tests/test_gpu_kmeans.py).
+ * Only images whose longer side is 256 (the reference's working size: no INTER_AREA copy) -- others: LFX_ERR_UNSUPPORTED.
+ * raw [B,H,W] (0/255); optional centers [B,3,3] (float32) and kinfo [B,4] = {picked cluster, iterations, empty-cluster
+ * events, points}; bias: 0 = auto, 1 = dark_bg, 2 = light_bg (TransformConfig.bg_bias). */
+int lfx_kmeans_raw(const uint8_t* src, uint8_t* raw, float* centers, int32_t* kinfo, int B, int H, int W, int green_lo,
+                   int green_hi, int bias, uint32_t seed, lfx_stream_t stream);
+
 /* Image-dependent terms of _score_mask (mask.py:143-188) for K (<= 8) post-processed candidate masks per image
  * (masks [K][B][H][W]), as `mask_strategy: auto` ranks them (:435-461).
  * feat[K][B][4] (double) = {sum of the Sobel magnitude (float32 values, fp64 sum) over the mask boundary

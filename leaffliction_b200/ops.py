@@ -224,6 +224,25 @@ def strategy_raw(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
     return out
 
 
+KMEANS_BIAS = {"auto": 0, "dark_bg": 1, "light_bg": 2}
+
+
+def kmeans_raw(x: torch.Tensor, green_hue_range=(25, 100), bg_bias: str = "auto", seed: int = 12345, details: bool = False):
+    """`_create_kmeans_mask` (mask.py:109-140) on a device batch whose longer side is 256: raw candidate [B,H,W] u8
+    (0/255); with `details` also (centers float32 [B,3,3], kinfo int32 [B,4] = picked cluster, iterations, empty-cluster
+    events, points).  cv2.kmeans / cv::RNG restated exactly (lfx_kmeans.cu)."""
+    _chk_img(x)
+    lib = _ready(x)
+    B, H, W, _ = x.shape
+    out = torch.empty((B, H, W), dtype=torch.uint8, device=x.device)
+    cen = torch.empty((B, 3, 3), dtype=torch.float32, device=x.device) if details else None
+    ki = torch.empty((B, 4), dtype=torch.int32, device=x.device) if details else None
+    bias = KMEANS_BIAS.get((bg_bias or "auto").lower(), 0)
+    _lib.check(lib.lfx_kmeans_raw(_p(x), _p(out), _p(cen) if details else None, _p(ki) if details else None, B, H, W,
+                                  int(green_hue_range[0]), int(green_hue_range[1]), bias, int(seed) & 0xFFFFFFFF, _stream()))
+    return (out, cen, ki) if details else out
+
+
 def score_features(x: torch.Tensor, masks: torch.Tensor, green_hue_range=(25, 100)):
     """Image-dependent terms of _score_mask (mask.py:160-177) for K candidate masks [K,B,H,W] of the images x [B,H,W,3].
     Returns (feat [K,B,4] f64 = boundary |grad| sum, boundary px, mask px, green & mask px; gmax [B] f32; gmin [B] f32)."""

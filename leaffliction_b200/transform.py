@@ -33,7 +33,7 @@ CANONICAL_TYPES: Dict[str, str] = {
     "landmarks": "Landmarks", "pseudolandmarks": "Landmarks", "pseudo-landmarks": "Landmarks",
     "hist": "Hist", "histogram": "Hist", "brown": "Brown", "disease": "Brown", "spots": "Brown",
 }
-GPU_STRATEGIES = ("hsv_h", "lab", "hsv_s", "hsv_v_dark", "inclusive", "enhanced", "auto")
+GPU_STRATEGIES = ("hsv_h", "lab", "hsv_s", "hsv_v_dark", "inclusive", "enhanced", "kmeans", "auto")
 
 _CONFIG_FIELDS = (
     ("gaussian_sigma", float), ("hsv_channel_for_mask", str), ("fill_size", int), ("morph_kernel", int),
@@ -241,6 +241,8 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
     raw = None
     if cfg.mask_strategy == "auto":
         raw, _choice, _scores = auto_candidate(x, cfg)
+    elif cfg.mask_strategy == "kmeans":
+        raw = ops.kmeans_raw(x, cfg.green_hue_range, cfg.bg_bias)      # longer side 256 only (LeafxError otherwise)
     elif cfg.mask_strategy in ("inclusive", "enhanced"):
         try:
             raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
@@ -273,7 +275,7 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
     return mask.cpu().numpy(), info_h, contours
 
 
-AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "enhanced", "inclusive")
+AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "kmeans", "enhanced", "inclusive")     # mask.py:435-441
 
 
 def score_mask_terms(area2: int, hull_area: float, bbox, h: int, w: int, b_strength: float, green_frac: float, cfg) -> float:
@@ -299,10 +301,10 @@ def score_mask_terms(area2: int, hull_area: float, bbox, h: int, w: int, b_stren
 
 
 def auto_candidate(x, cfg: TransformConfig):
-    """`mask_strategy: auto` (mask.py:435-461) on a device batch x [B,H,W,3]: the six deterministic candidates in the
-    reference's order (hsv_s, hsv_v_dark, hsv_h, lab, enhanced, inclusive -- the k-means candidate is Tier C: cv2.kmeans
-    on OpenCV's RNG, not built), each through _postprocess_mask, scored by _score_mask, the first strictly greater score
-    wins.  Returns (raw candidate of the winner per image [B,H,W] -- all zero when every candidate is rejected, which
+    """`mask_strategy: auto` (mask.py:435-461) on a device batch x [B,H,W,3]: the seven candidates in the reference's
+    order (hsv_s, hsv_v_dark, hsv_h, lab, kmeans, enhanced, inclusive; the k-means candidate exists for images whose longer
+    side is 256, the reference's own k-means working size -- other sizes run the six others with a warning), each through
+    _postprocess_mask, scored by _score_mask, the first strictly greater score wins.  Returns (raw candidate of the winner per image [B,H,W] -- all zero when every candidate is rejected, which
     sends make_mask down the reference's Otsu fallback --, chosen index [B] (-1 = none), scores [K,B]).
     The scores' float terms are accumulated in fp64 on the device (the reference: float32 NumPy mean); two candidates
     whose scores differ by less than ~1e-6 may therefore rank differently."""
@@ -312,8 +314,14 @@ def auto_candidate(x, cfg: TransformConfig):
     ops = _ops()
     B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
     raws = []
-    for st in AUTO_CANDIDATES:
-        if st in ("enhanced", "inclusive"):
+    names = AUTO_CANDIDATES
+    if max(H, W) != 256:
+        _warn_once("auto-kmeans", "auto strategy: the k-means candidate needs a 256-pixel longer side; ranking the six others")
+        names = tuple(n for n in AUTO_CANDIDATES if n != "kmeans")
+    for st in names:
+        if st == "kmeans":
+            raws.append(ops.kmeans_raw(x, cfg.green_hue_range, cfg.bg_bias))
+        elif st in ("enhanced", "inclusive"):
             raws.append(ops.raw_mask_front_end(x, st, mask_cfg_from(cfg, "hsv_h")))
         else:
             raws.append(ops.strategy_raw(x, mask_cfg_from(cfg, st)))

@@ -255,6 +255,9 @@ def raw_candidate(rgb, cfg: Cfg):
         return mask_enhanced(rgb, cfg)
     if st == "inclusive":
         return mask_inclusive(rgb, cfg)
+    if st == "kmeans":
+        from . import spec_kmeans
+        return spec_kmeans.kmeans_mask(rgb, cfg)
     raise ValueError(f"strategy {st!r} is outside the bit-exact contract (SURVEY.md section 8a tier C)")
 
 
@@ -377,16 +380,18 @@ def score_mask(mask: np.ndarray, info, rgb: np.ndarray, cfg: Cfg) -> float:
     return float(score)
 
 
-AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "enhanced", "inclusive")
+AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "kmeans", "enhanced", "inclusive")
 
 
-def make_mask_auto(rgb: np.ndarray, cfg: Cfg, return_choice: bool = False):
-    """make_mask with mask_strategy "auto" (mask.py:435-441) WITHOUT the k-means candidate (Tier C: cv2.kmeans on
-    OpenCV's RNG): the six deterministic candidates in the reference's order, _find_best_mask's strict-greater selection
-    (:446-461), then the fallback and the brown extension exactly as for a single strategy."""
+def make_mask_auto(rgb: np.ndarray, cfg: Cfg, return_choice: bool = False, with_kmeans: bool = True):
+    """make_mask with mask_strategy "auto" (mask.py:435-441): the seven candidates in the reference's order (the k-means
+    one -- spec_kmeans, cv2.kmeans restated -- can be left out: `with_kmeans=False`), _find_best_mask's strict-greater
+    selection (:446-461), then the fallback and the brown extension exactly as for a single strategy."""
     import dataclasses
     best, best_info, best_score, choice = None, None, -1.0, None
     for st in AUTO_CANDIDATES:
+        if st == "kmeans" and not with_kmeans:
+            continue
         raw = raw_candidate(rgb, dataclasses.replace(cfg, mask_strategy=st))
         m, info = postprocess(raw, cfg)
         sc_ = score_mask(m, info, rgb, cfg)

@@ -1,0 +1,75 @@
+"""GPU parity of the k-means mask candidate (SURVEY.md 8a tier C row c2, 8f rank 4): lfx_kmeans_raw against
+oracle/spec_kmeans.py, which tests/test_reference_differential.py pins bit for bit on cv2.kmeans and on the reference's
+`_create_kmeans_mask` (srcs/transform/filters/mask.py:109-140).  Everything here is bit-exact: centres (float32), iteration
+counts, candidate masks for the three bg_bias settings, `mask_strategy: kmeans` through the drop-in make_mask."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from leaffliction_b200 import ops, synth, transform
+from oracle import spec_kmeans as sk
+from oracle import spec_mask as sm
+
+pytestmark = pytest.mark.gpu
+
+
+def _images():
+    g = np.random.default_rng(11)
+    leaves = [synth.leaf_image(100 + i, 256, 256) for i in range(40)]
+    odd = [np.full((256, 256, 3), 77, np.uint8),                                                  # one colour: two empty clusters
+           (g.integers(0, 2, (256, 256, 1), dtype=np.uint8) * 200).repeat(3, 2),                    # two colours: one empty cluster
+           g.integers(0, 256, (256, 256, 3), dtype=np.uint8)]                                      # noise: runs to the iteration cap
+    return leaves + odd
+
+
+def test_kmeans_centres_iterations_and_masks_match_the_oracle(dev):
+    imgs = np.stack(_images())
+    x = torch.from_numpy(imgs).to(dev)
+    exp = [sk.kmeans3(im.reshape(-1, 3)) for im in imgs]
+    for bias in ("auto", "light_bg", "dark_bg"):
+        raw, cen, ki = ops.kmeans_raw(x, (25, 100), bias, details=True)
+        raw, cen, ki = raw.cpu().numpy(), cen.cpu().numpy(), ki.cpu().numpy()
+        scfg = sm.Cfg(mask_strategy="kmeans", bg_bias=bias)
+        for i, (labels, centers, it) in enumerate(exp):
+            assert np.array_equal(cen[i], centers), (bias, i, cen[i], centers)
+            assert ki[i, 1] == it and ki[i, 3] == imgs[i].shape[0] * imgs[i].shape[1], (bias, i, ki[i], it)
+            pick = sk.pick_cluster(centers, scfg)
+            assert ki[i, 0] == pick, (bias, i)
+            assert np.array_equal(raw[i], ((labels.reshape(256, 256) == pick) * 255).astype(np.uint8)), (bias, i)
+    assert ki[40, 2] == 2 and ki[41, 2] == 1 and ki[0, 2] == 0           # empty-cluster events of the degenerate images
+    assert max(e[2] for e in exp) >= 15                                  # long runs are covered
+
+
+@pytest.mark.parametrize("shape", [(256, 192), (64, 256), (256, 256)])
+def test_kmeans_other_shapes_with_a_256_long_side(dev, shape):
+    H, W = shape
+    imgs = np.stack([synth.leaf_image(7 + i, H, W) for i in range(6)])
+    raw = ops.kmeans_raw(torch.from_numpy(imgs).to(dev), (25, 100), "light_bg").cpu().numpy()
+    scfg = sm.Cfg(mask_strategy="kmeans")
+    for i in range(len(imgs)):
+        assert np.array_equal(raw[i], sk.kmeans_mask(imgs[i], scfg)), i
+
+
+def test_kmeans_rejects_other_sizes(dev):
+    from leaffliction_b200._lib import ERR_UNSUPPORTED, LeafxError
+    with pytest.raises(LeafxError) as e:
+        ops.kmeans_raw(torch.zeros((1, 128, 128, 3), dtype=torch.uint8, device=dev))
+    assert e.value.code == ERR_UNSUPPORTED
+
+
+def test_make_mask_with_kmeans_strategy(dev):
+    """`mask_strategy: kmeans` through the drop-in make_mask (candidate -> _postprocess_mask -> fallback -> brown extension)."""
+    imgs = synth.leaf_batch(12, 256, 256, 777)
+    for bias in ("light_bg", "auto"):
+        cfg = transform.default_config(mask_strategy="kmeans", bg_bias=bias, grabcut_refine=False, mask_upscale_factor=1.0,
+                                       mask_upscale_long_side=0)
+        scfg = sm.Cfg(mask_strategy="kmeans", bg_bias=bias)
+        masks, info, contours = transform.make_mask_batch(imgs, cfg)
+        for i in range(len(imgs)):
+            om, oinfo = sm.make_mask(imgs[i], scfg)
+            assert np.array_equal(masks[i], om), (bias, i, int((masks[i] != om).sum()))
+            assert (contours[i] is None) == (oinfo is None)
+            if oinfo is not None:
+                assert tuple(info[i, 1:5]) == tuple(oinfo["bbox"])

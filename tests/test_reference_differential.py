@@ -162,7 +162,7 @@ def test_auto_strategy_without_kmeans(ns, leaves256):
                 om, oinfo = sm.postprocess(raw, scfg)
                 assert abs(ns.mask._score_mask(rm, rcnt, img, cfg) - sm.score_mask(om, oinfo, img, scfg)) < 1e-6, (i, st)
             m, cnt = ns.mask.make_mask(img, cfg)
-            om, info, choice, _score = sm.make_mask_auto(img, scfg, True)
+            om, info, choice, _score = sm.make_mask_auto(img, scfg, True, with_kmeans=False)
             choices.add(choice)
             assert np.array_equal(m, om), f"image {i}: {(m != om).sum()} px differ (oracle chose {choice})"
             assert (cnt is None) == (info is None)
@@ -171,3 +171,50 @@ def test_auto_strategy_without_kmeans(ns, leaves256):
         assert len(choices - {None}) >= 2          # the selection rule is exercised, not one strategy winning everywhere
     finally:
         ns.mask._create_kmeans_mask = orig
+
+
+def test_kmeans_candidate_and_full_auto(ns, leaves256):
+    """Tier C row c2 pinned: the reference's `_create_kmeans_mask` (mask.py:109-140: cv2.setRNGSeed(12345) + cv2.kmeans)
+    against oracle/spec_kmeans.py -- cv2.kmeans' labels and centres bit for bit, the candidate mask for the three bg_bias
+    settings, non-256 sizes (INTER_AREA working copy + INTER_NEAREST back), degenerate images (empty-cluster rule), then
+    `mask_strategy: kmeans` and the full seven-candidate `auto` through the reference's make_mask."""
+    import dataclasses
+
+    import cv2
+
+    from oracle import spec_kmeans as sk
+    crit = (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 20, 0.5)
+    g = np.random.default_rng(11)
+    extra = [np.full((256, 256, 3), 77, np.uint8), np.zeros((64, 256, 3), np.uint8),
+             g.integers(0, 256, (256, 200, 3), dtype=np.uint8), (g.integers(0, 2, (256, 256, 1), dtype=np.uint8) * 200).repeat(3, 2)]
+    for i, img in enumerate(list(leaves256[:32]) + extra):
+        cv2.setRNGSeed(12345)
+        _c, labels, centers = cv2.kmeans(img.reshape(-1, 3).astype(np.float32), 3, None, crit, 1, cv2.KMEANS_PP_CENTERS)
+        ol, oc, _it = sk.kmeans3(img.reshape(-1, 3))
+        assert np.array_equal(labels.ravel(), ol) and np.array_equal(centers, oc), i
+    sizes = [(256, 256), (256, 192), (128, 128), (300, 400), (512, 512)]
+    from leaffliction_b200 import synth
+    for bias in ("light_bg", "dark_bg", "auto"):
+        cfg = ref_harness.ref_config(ns, mask_strategy="kmeans", bg_bias=bias)
+        scfg = sm.Cfg(mask_strategy="kmeans", bg_bias=bias)
+        for k, (h, w) in enumerate(sizes):
+            img = synth.leaf_image(40 + k, h, w)
+            assert np.array_equal(ns.mask._create_kmeans_mask(img, cfg), sk.kmeans_mask(img, scfg)), (bias, h, w)
+        for i, img in enumerate(leaves256[:8]):
+            m, cnt = ns.mask.make_mask(img, cfg)
+            om, info = sm.make_mask(img, scfg)
+            assert np.array_equal(m, om), (bias, i)
+            assert (cnt is None) == (info is None)
+    cfg = ref_harness.ref_config(ns, mask_strategy="auto")
+    scfg = sm.Cfg(mask_strategy="auto")
+    choices = set()
+    for i, img in enumerate(leaves256[:24]):
+        raw = sm.raw_candidate(img, dataclasses.replace(scfg, mask_strategy="kmeans"))
+        rm, rcnt = ns.mask._postprocess_mask(raw, cfg)
+        omk, oinfo = sm.postprocess(raw, scfg)
+        assert abs(ns.mask._score_mask(rm, rcnt, img, cfg) - sm.score_mask(omk, oinfo, img, scfg)) < 1e-6, i
+        m, cnt = ns.mask.make_mask(img, cfg)
+        om, info, choice, _score = sm.make_mask_auto(img, scfg, True)
+        choices.add(choice)
+        assert np.array_equal(m, om), f"image {i}: {(m != om).sum()} px differ (oracle chose {choice})"
+    assert len(choices - {None}) >= 2
