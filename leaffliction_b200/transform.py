@@ -242,7 +242,7 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
     if cfg.mask_strategy == "auto":
         raw, _choice, _scores = auto_candidate(x, cfg)
     elif cfg.mask_strategy == "kmeans":
-        raw = ops.kmeans_raw(x, cfg.green_hue_range, cfg.bg_bias)      # longer side 256 only (LeafxError otherwise)
+        raw = kmeans_candidate(x, cfg)
     elif cfg.mask_strategy in ("inclusive", "enhanced"):
         try:
             raw = ops.raw_mask_front_end(x, cfg.mask_strategy, mask_cfg_from(cfg))
@@ -278,6 +278,26 @@ def make_mask_batch(rgb_batch: np.ndarray, cfg: TransformConfig):
 AUTO_CANDIDATES = ("hsv_s", "hsv_v_dark", "hsv_h", "lab", "kmeans", "enhanced", "inclusive")     # mask.py:435-441
 
 
+def kmeans_candidate(x, cfg: TransformConfig):
+    """`_create_kmeans_mask` (mask.py:109-140) for a device batch of any size: INTER_AREA working copy with a 256-pixel
+    longer side (mask.py:113-118; the letterbox kernel with the whole image as its box: same cv2.resize arithmetic, same
+    max(int(w * scale), 1) sizes), lfx_kmeans_raw on it, INTER_NEAREST back (mask.py:139)."""
+    import torch
+    ops = _ops()
+    B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+    if max(H, W) == 256:
+        return ops.kmeans_raw(x, cfg.green_hue_range, cfg.bg_bias)
+    scale = 256 / max(H, W)
+    sw, sh = max(1, int(W * scale)), max(1, int(H * scale))
+    info = torch.tensor([[1, 0, 0, W, H, 0, 0, 0]] * B, dtype=torch.int32, device=x.device)
+    canvas = ops.roi_letterbox(x, None, info, (256, 256))
+    oy, ox = (256 - sh) // 2, (256 - sw) // 2
+    small = canvas[:, oy:oy + sh, ox:ox + sw, :].contiguous()
+    if max(sh, sw) != 256:                       # cannot happen for scale = 256 / max(H, W); guards the kernel's contract
+        raise ValueError("kmeans_candidate: working copy without a 256-pixel side")
+    return ops.resize_nearest(ops.kmeans_raw(small, cfg.green_hue_range, cfg.bg_bias), (H, W))
+
+
 def score_mask_terms(area2: int, hull_area: float, bbox, h: int, w: int, b_strength: float, green_frac: float, cfg) -> float:
     """_score_mask (mask.py:143-188) from its terms: contour area (2 * area, exact), convex-hull area, bounding box,
     boundary strength and green fraction.  cnt None is area2 < 0."""
@@ -302,8 +322,7 @@ def score_mask_terms(area2: int, hull_area: float, bbox, h: int, w: int, b_stren
 
 def auto_candidate(x, cfg: TransformConfig):
     """`mask_strategy: auto` (mask.py:435-461) on a device batch x [B,H,W,3]: the seven candidates in the reference's
-    order (hsv_s, hsv_v_dark, hsv_h, lab, kmeans, enhanced, inclusive; the k-means candidate exists for images whose longer
-    side is 256, the reference's own k-means working size -- other sizes run the six others with a warning), each through
+    order (hsv_s, hsv_v_dark, hsv_h, lab, kmeans, enhanced, inclusive), each through
     _postprocess_mask, scored by _score_mask, the first strictly greater score wins.  Returns (raw candidate of the winner per image [B,H,W] -- all zero when every candidate is rejected, which
     sends make_mask down the reference's Otsu fallback --, chosen index [B] (-1 = none), scores [K,B]).
     The scores' float terms are accumulated in fp64 on the device (the reference: float32 NumPy mean); two candidates
@@ -314,13 +333,9 @@ def auto_candidate(x, cfg: TransformConfig):
     ops = _ops()
     B, H, W = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
     raws = []
-    names = AUTO_CANDIDATES
-    if max(H, W) != 256:
-        _warn_once("auto-kmeans", "auto strategy: the k-means candidate needs a 256-pixel longer side; ranking the six others")
-        names = tuple(n for n in AUTO_CANDIDATES if n != "kmeans")
-    for st in names:
+    for st in AUTO_CANDIDATES:
         if st == "kmeans":
-            raws.append(ops.kmeans_raw(x, cfg.green_hue_range, cfg.bg_bias))
+            raws.append(kmeans_candidate(x, cfg))
         elif st in ("enhanced", "inclusive"):
             raws.append(ops.raw_mask_front_end(x, st, mask_cfg_from(cfg, "hsv_h")))
         else:

@@ -73,3 +73,17 @@ def test_make_mask_with_kmeans_strategy(dev):
             assert (contours[i] is None) == (oinfo is None)
             if oinfo is not None:
                 assert tuple(info[i, 1:5]) == tuple(oinfo["bbox"])
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (300, 400), (512, 512), (100, 37)])
+def test_kmeans_candidate_any_size(dev, shape):
+    """Sizes whose longer side is not 256: INTER_AREA working copy (up or down), k-means, INTER_NEAREST back
+    (mask.py:113-118,139) -- bit-exact against the oracle, which is pinned on the reference for these sizes too."""
+    H, W = shape
+    imgs = np.stack([synth.leaf_image(300 + i, H, W) for i in range(5)])
+    cfg = transform.default_config(mask_strategy="kmeans", grabcut_refine=False, mask_upscale_factor=1.0, mask_upscale_long_side=0)
+    raw = transform.kmeans_candidate(torch.from_numpy(imgs).to(dev), cfg).cpu().numpy()
+    scfg = sm.Cfg(mask_strategy="kmeans")
+    for i in range(len(imgs)):
+        exp = sk.kmeans_mask(imgs[i], scfg)
+        assert np.array_equal(raw[i], exp), (i, int((raw[i] != exp).sum()))
