@@ -123,6 +123,13 @@ def cpu_reference_rate(images, seeds, cores, pool):
     return n / dt, dt
 
 
+def workload_config(batch, size, world, aug_outputs=6):
+    """The `config` object of BOTH arms (this implementation and `--impl reference`): what is computed, not how."""
+    return {"workload": workload_text(batch, size), "parity_profile": PARITY,
+            "l2_policy": f"inputs larger than L2 ({batch * size * size * 3 / 1e6:.0f} MB per step vs 126 MB L2)",
+            "images_per_gpu": batch, "parallelism": f"image-sharded x{world}", "augment_outputs_per_image": aug_outputs}
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -153,7 +160,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": workload_text(args.batch, args.size), "parity_profile": PARITY},
+        "config": workload_config(args.batch, args.size, args.gpus),
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{sample} images of the {args.batch}-image batch per step x {args.steps} steps; "
                                    f"oracle/refcalls.py = the reference's OpenCV/Pillow/NumPy/SciPy calls on in-memory "
@@ -395,12 +402,9 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": workload_text(B, S), "parity_profile": PARITY,
-                       "l2_policy": f"inputs larger than L2 ({B * N * 3 / 1e6:.0f} MB per step vs 126 MB L2)",
-                       "images_per_gpu": B, "parallelism": f"image-sharded x{world}",
-                       "augment_outputs_per_image": 6 if augset is not None else 0,
-                       "streams": 1 if (args.serial or augset is None) else 3,
-                       "dataset_histogram_matches_per_image_sum": ds_ok, "host_binding": binding},
+            "config": workload_config(B, S, world, 6 if augset is not None else 0),
+            "run": {"streams": 1 if (args.serial or augset is None) else 3,
+                    "dataset_histogram_matches_per_image_sum": ds_ok, "host_binding": binding},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "configs": configs,
             "gpu_launches": launches * args.steps,
         }
