@@ -253,10 +253,17 @@ struct Geo {
     int found, bx, by, bw, bh, nw, nh, ox, oy;
 };
 
+// streaming byte store of the low byte of a 32-bit register (st.u8 truncates: no `& 0xff` in front of it)
+__device__ __forceinline__ void st_cs_u8(uint8_t* p, uint32_t v) {
+    asm volatile("st.global.cs.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- the kernel
 // S = true: compile-time 256x256 image, 256x256 canvas (PlantVillage, BASELINE configs 1-3); S = false: any
 // W % 32 == 0, H*W <= 65536 shape with run-time geometry.
-template <bool S>
+// F = true (only with S): the P1 configuration -- strategy hsv_h with both hue ranges below 150 (hue_direct), no Lab, no external
+// candidate: the pixel pass carries no run-time strategy selection.
+template <bool S, bool F = false>
 __global__ void __launch_bounds__(MT, 2)
     k_core(const uint8_t* __restrict__ src, uint8_t* __restrict__ blur, uint8_t* __restrict__ mask, int32_t* __restrict__ info,
            uint8_t* __restrict__ roi, int32_t* __restrict__ hist9, int32_t* __restrict__ hsv3, int32_t* __restrict__ counters,
@@ -384,13 +391,20 @@ __global__ void __launch_bounds__(MT, 2)
             const int head = extra * nfree;
             // strategy 4: the candidate comes from a front-end kernel (inclusive / enhanced, lfx_raw_mask) as bytes
             const uint8_t* rawt = raw ? raw + (size_t)img * img_px + (size_t)y0 * W : nullptr;
-            auto pixel_item = [&](int item) {
-                int ry, w;
-                split_index(c, item, ry, w);
-                const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
+            // one warp item = 32 consecutive pixels of a row: px = this lane's pixel in the staged tile, item = word index in the tile
+            auto pixel_px = [&](const uint8_t* px, int item) {
                 const int r = px[0], g = px[1], b = px[2];
                 bool b0, b1;
-                if (P.hue_direct) {
+                if constexpr (F) {
+                    const int v = max(r, max(g, b)), d = v - min(r, min(g, b));
+                    const int ts = d * s_hsv->sdiv[v] + 2048;
+                    const int hr = g - b, hg = b - r + 2 * d, hb = r - g + 4 * d;      // selects, not branches: the lanes of a warp differ
+                    int hh = (v == g) ? hg : hb;
+                    hh = (v == r) ? hr : hh;
+                    const int th = hh * s_hsv->hdiv[d] + 2048;
+                    b0 = ((unsigned)(th - P.g_lo12) < (unsigned)P.g_span12) && (ts >= (40 << 12));   // mask.py:90
+                    b1 = ((unsigned)(th - P.b_lo12) < (unsigned)P.b_span12) && (ts >= P.b_smin12) && (v <= M.cfg.brown_v_max);
+                } else if (P.hue_direct) {
                     // H = th >> 12 (+180 when negative), S = ts >> 12 (rgb2hsv): lo <= H <= hi  <=>  lo << 12 <= th < (hi + 1) << 12
                     // for ranges below 150 (a negative th maps to H >= 150, so no wrap-around case), S >= T  <=>  ts >= T << 12:
                     // the two shifts and the hue fix-up are not needed for the predicates
@@ -419,7 +433,8 @@ __global__ void __launch_bounds__(MT, 2)
                          (s >= M.cfg.brown_s_min) && (v <= M.cfg.brown_v_max);
                 }
                 // strategy 4: the candidate comes from a front-end kernel (inclusive / enhanced, lfx_raw_mask) as bytes
-                if (rawt) b0 = __ldg(rawt + ry * W + w * 32 + lane) != 0;
+                if constexpr (!F)
+                    if (rawt) b0 = __ldg(rawt + item * 32 + lane) != 0;     // item * 32 = ry * W + w * 32
                 const uint32_t m0 = __ballot_sync(0xffffffffu, b0);
                 const uint32_t m1 = __ballot_sync(0xffffffffu, b1);
                 if (lane == 0) {
@@ -428,11 +443,23 @@ __global__ void __launch_bounds__(MT, 2)
                     PB[idx] = m1;
                 }
             };
+            auto pixel_item = [&](int item) {
+                int ry, w;
+                split_index(c, item, ry, w);
+                pixel_px(s_src + ((ry + 2) * RB + (w * 32 + lane) * 3), item);
+            };
             // head start of the warps without vertical-pass work, then every warp: the second loop has a compile-time stride
-            // (NWARPS items = NWARPS / WPR rows in the static instantiation), so its addresses are plain pointer increments
+            // (NWARPS items = NWARPS / WPR rows in the static instantiation), so its pixel address is a plain pointer increment
             if (wid >= nvw && extra != 0)
                 for (int item = wid - nvw; item < head; item += nfree) pixel_item(item);
-            for (int item = head + wid; item < npix; item += NWARPS) pixel_item(item);
+            if constexpr (S) {
+                static_assert(NWARPS % 8 == 0, "a warp keeps its word column");
+                int item = head + wid;
+                const uint8_t* px = s_src + (((item >> 3) + 2) * 768 + ((item & 7) * 32 + lane) * 3);
+                for (; item < npix; item += NWARPS, px += (NWARPS / 8) * 768) pixel_px(px, item);
+            } else {
+                for (int item = head + wid; item < npix; item += NWARPS) pixel_item(item);
+            }
             __syncthreads();
             if (threadIdx.x == 0 && t + 1 < ntiles)
                 issue_tile_load(simg, s_src, &s_bar, y0 + TR, min(TR, H - y0 - TR), H, RB, nullptr, nullptr, 0, pol_keep);
@@ -556,42 +583,64 @@ __global__ void __launch_bounds__(MT, 2)
             LFX_TICK(17)
             if (want_stats) {
                 // contiguous rows per warp: every warp sees all word columns (the leaf sits in the middle ones)
+                auto stats_px = [&](const uint8_t* px) {
+                    const int r = px[0], g = px[1], b = px[2];
+                    int h, s, v, Ll, A, Bv;
+                    {   // rgb2hsv with the hue numerator chosen by selects (the lanes of a warp differ: no branch)
+                        v = max(r, max(g, b));
+                        const int d = v - min(r, min(g, b));
+                        s = (d * s_hsv->sdiv[v] + 2048) >> 12;
+                        const int hr = g - b, hg = b - r + 2 * d, hb = r - g + 4 * d;
+                        int hh = (v == g) ? hg : hb;
+                        hh = (v == r) ? hr : hh;
+                        hh = (hh * s_hsv->hdiv[d] + 2048) >> 12;
+                        h = hh < 0 ? hh + 180 : hh;
+                    }
+                    rgb2lab(r, g, b, s_lab, Ll, A, Bv);
+                    atomicAdd(&s_hist[0 * 256 + r], 1u);
+                    atomicAdd(&s_hist[1 * 256 + g], 1u);
+                    atomicAdd(&s_hist[2 * 256 + b], 1u);
+                    atomicAdd(&s_hist[3 * 256 + h], 1u);
+                    atomicAdd(&s_hist[4 * 256 + s], 1u);
+                    atomicAdd(&s_hist[5 * 256 + v], 1u);
+                    atomicAdd(&s_hist[6 * 256 + Ll], 1u);
+                    atomicAdd(&s_hist[7 * 256 + A], 1u);
+                    atomicAdd(&s_hist[8 * 256 + Bv], 1u);
+                    // leaf mask + 8 categories + 5 hue ranges (hist.py:188,38-65,248-256): per-channel LUTs of
+                    // byte-packed 0/1 flags, AND = joint predicate, packed 8-bit counters (<= 128 px / thread)
+                    const uint4 qh = s_cat[h], qs = s_cat[256 + s], qv = s_cat[512 + v];
+                    const uint32_t q0 = qh.x & qs.x & qv.x;
+                    cacc[0] += q0;
+                    cacc[1] += qh.y & qs.y & qv.y;
+                    cacc[2] += qh.z & qs.z & qv.z;
+                    cacc[3] += qh.w & qs.w & qv.w;
+                    // hsv3 = H/S/V histograms of the LEAF pixels (hist.py:188) = those of all masked pixels (planes 3..5)
+                    // minus those of the masked non-leaf pixels: only the rare non-leaf pixel pays three more atomics
+                    if (!(q0 & 1u)) {
+                        atomicAdd(&s_hist[9 * 256 + h], 1u);
+                        atomicAdd(&s_hist[10 * 256 + s], 1u);
+                        atomicAdd(&s_hist[11 * 256 + v], 1u);
+                    }
+                };
                 const int ipw = (nr * WPR + NWARPS - 1) / NWARPS;
                 const int iend = min(nr * WPR, (wid + 1) * ipw);
-                for (int item = wid * ipw; item < iend; ++item) {
-                    const uint32_t m = PR[y0 * WPR + item];
-                    if (m == 0u) continue;
-                    if ((m >> lane) & 1u) {
-                        int ry, w;
-                        split_index(c, item, ry, w);
-                        const uint8_t* px = s_src + ((ry + 2) * RB + (w * 32 + lane) * 3);
-                        const int r = px[0], g = px[1], b = px[2];
-                        int h, s, v, Ll, A, Bv;
-                        rgb2hsv(r, g, b, s_hsv, h, s, v);
-                        rgb2lab(r, g, b, s_lab, Ll, A, Bv);
-                        atomicAdd(&s_hist[0 * 256 + r], 1u);
-                        atomicAdd(&s_hist[1 * 256 + g], 1u);
-                        atomicAdd(&s_hist[2 * 256 + b], 1u);
-                        atomicAdd(&s_hist[3 * 256 + h], 1u);
-                        atomicAdd(&s_hist[4 * 256 + s], 1u);
-                        atomicAdd(&s_hist[5 * 256 + v], 1u);
-                        atomicAdd(&s_hist[6 * 256 + Ll], 1u);
-                        atomicAdd(&s_hist[7 * 256 + A], 1u);
-                        atomicAdd(&s_hist[8 * 256 + Bv], 1u);
-                        // leaf mask + 8 categories + 5 hue ranges (hist.py:188,38-65,248-256): per-channel LUTs of
-                        // byte-packed 0/1 flags, AND = joint predicate, packed 8-bit counters (<= 128 px / thread)
-                        const uint4 qh = s_cat[h], qs = s_cat[256 + s], qv = s_cat[512 + v];
-                        const uint32_t q0 = qh.x & qs.x & qv.x;
-                        cacc[0] += q0;
-                        cacc[1] += qh.y & qs.y & qv.y;
-                        cacc[2] += qh.z & qs.z & qv.z;
-                        cacc[3] += qh.w & qs.w & qv.w;
-                        // hsv3 = H/S/V histograms of the LEAF pixels (hist.py:188) = those of all masked pixels (planes 3..5)
-                        // minus those of the masked non-leaf pixels: only the rare non-leaf pixel pays three more atomics
-                        if (!(q0 & 1u)) {
-                            atomicAdd(&s_hist[9 * 256 + h], 1u);
-                            atomicAdd(&s_hist[10 * 256 + s], 1u);
-                            atomicAdd(&s_hist[11 * 256 + v], 1u);
+                if constexpr (S) {
+                    // rows are contiguous in the staged tile (768 = 8 words x 96 bytes): item -> pixel is one linear map
+                    const uint8_t* px = s_src + 2 * 768 + (wid * ipw) * 96 + lane * 3;
+                    const uint32_t* pm = PR + y0 * WPR + wid * ipw;
+                    for (int k = 0; k < iend - wid * ipw; ++k, px += 96) {
+                        const uint32_t m = pm[k];
+                        if (m == 0u) continue;
+                        if ((m >> lane) & 1u) stats_px(px);
+                    }
+                } else {
+                    for (int item = wid * ipw; item < iend; ++item) {
+                        const uint32_t m = PR[y0 * WPR + item];
+                        if (m == 0u) continue;
+                        if ((m >> lane) & 1u) {
+                            int ry, w;
+                            split_index(c, item, ry, w);
+                            stats_px(s_src + ((ry + 2) * RB + (w * 32 + lane) * 3));
                         }
                     }
                 }
@@ -661,9 +710,9 @@ __global__ void __launch_bounds__(MT, 2)
                             // VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>; a + b <= 2049 keeps it in 0..255.
                             // (ya*h >> 16) as the high word of (ya << 16) * h: one IMAD.HI with the addend fused
                             const uint32_t ya = (uint32_t)ty.y << 16, yb = (uint32_t)ty.y & 0xFFFF0000u;
-                            __stcs(o + 0, (uint8_t)((__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2));
-                            __stcs(o + 1, (uint8_t)((__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2));
-                            __stcs(o + 2, (uint8_t)((__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2));
+                            st_cs_u8(o + 0, (__umulhi(ya, h0r) + __umulhi(yb, h1r) + 2u) >> 2);
+                            st_cs_u8(o + 1, (__umulhi(ya, h0g) + __umulhi(yb, h1g) + 2u) >> 2);
+                            st_cs_u8(o + 2, (__umulhi(ya, h0b) + __umulhi(yb, h1b) + 2u) >> 2);
                         }
                     }
                 }
@@ -792,20 +841,25 @@ int lfx_core_try(const uint8_t* src, uint8_t* blur, uint8_t* mask, int32_t* info
     const size_t need = 512 + (size_t)P.ws_per_block * grid;
     LFX_REQUIRE(workspace && workspace_bytes >= need, LFX_ERR_WORKSPACE, "pipeline_core: workspace %zu < %zu bytes", workspace_bytes, need);
     const bool s256 = (H == 256 && W == 256 && RH == 256 && RW == 256);
-    static int attr_[LFX_MAX_DEVICES][2] = {{0}};
+    const bool fast = s256 && P.hue_direct && cfg->strategy == 0 && raw == nullptr;
+    const int variant = fast ? 2 : (s256 ? 1 : 0);
+    static int attr_[LFX_MAX_DEVICES][3] = {{0}};
     int* attr = attr_[lfx_dev()];
-    if (P.lay.smem_bytes > attr[s256]) {
-        const void* fn = s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
+    if (P.lay.smem_bytes > attr[variant]) {
+        const void* fn = fast ? (const void*)k_core<true, true> : s256 ? (const void*)k_core<true> : (const void*)k_core<false>;
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, P.lay.smem_bytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core smem attr (%d bytes): %s", P.lay.smem_bytes, cudaGetErrorString(e));
-        attr[s256] = P.lay.smem_bytes;
+        attr[variant] = P.lay.smem_bytes;
     }
     cudaError_t e = cudaMemsetAsync(workspace, 0, 512, st);
     LFX_REQUIRE(e == cudaSuccess, LFX_ERR_CUDA, "pipeline_core memset: %s", cudaGetErrorString(e));
     static const bool timing = getenv("LFX_CORE_TIMING") && atoi(getenv("LFX_CORE_TIMING")) > 0;
     P.timing = timing ? 1 : 0;
-    if (s256)
+    if (fast)
+        k_core<true, true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
+                                                              (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist, raw);
+    else if (s256)
         k_core<true><<<grid, MT, P.lay.smem_bytes, st>>>(src, blur, mask, info, roi, hist9, hsv3, counters, B, P,
                                                         (uint8_t*)workspace, lfx_tables(), cat_lut, ds_hist, raw);
     else
