@@ -121,6 +121,14 @@ enum { LFX_AUG_FLIP = 0, LFX_AUG_ROTATE = 1, LFX_AUG_SKEW = 2, LFX_AUG_SHEAR = 3
 int lfx_draw_augment_params(const int32_t* transform, const uint32_t* seed, int B, int H, int W,
                             int32_t* iparams, double* dparams, int threads);
 
+/* The seeding half of lfx_draw_augment_params on the device: words[B][nwords] (device) = the first nwords (<= 226) 32-bit
+ * outputs of Python's `random` after random.seed(seeds[i]) (image_augmenter.py:16-18; 0 <= seed < 2^32), one thread per
+ * task.  lfx_draw_augment_params_words (host) then draws the parameters from a HOST copy of those words, in the same order
+ * and with the same results as lfx_draw_augment_params; a task that needs more words is seeded on the host. */
+int lfx_seed_words(const uint32_t* seeds, int B, int nwords, uint32_t* words, lfx_stream_t stream);
+int lfx_draw_augment_params_words(const int32_t* transform, const uint32_t* seed, const uint32_t* words, int nwords, int B,
+                                  int H, int W, int32_t* iparams, double* dparams);
+
 /* ---- transform path: srcs/transform/filters/*.py, srcs/utils/mask_utils.py -------------------- */
 
 /* Host-side: the task list of the balancing pass for an in-memory dataset (dataset_balancer.py:115-129 after

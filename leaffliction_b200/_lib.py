@@ -64,6 +64,8 @@ _SIGS = {
     "lfx_pipeline_core_workspace": (C.c_size_t, [_I, _I, _I]),
     "lfx_legacy_normal_u8": (C.c_int, [_P, _P, _I, _I, C.c_double, C.c_double, _P]),
     "lfx_draw_augment_params": (C.c_int, [_P, _P, _I, _I, _I, _P, _P, _I]),
+    "lfx_seed_words": (C.c_int, [_P, _I, _I, _P, _P]),
+    "lfx_draw_augment_params_words": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P, _P]),
     "lfx_draw_balance_tasks": (C.c_int, [C.c_uint32, _I, _P, _P, _P, _P]),
     "lfx_cubic_table": (C.c_int, [_I, _I, _P, _P]),
     "lfx_resize_cubic": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),

@@ -12,6 +12,8 @@ host (Pillow, quality 95 -- image_utils.py:19-59; out of scope per SURVEY.md sec
 """
 from __future__ import annotations
 
+import os
+
 import logging
 import math
 import random
@@ -326,6 +328,24 @@ def draw_params_batch(transforms, seeds, h: int, w: int, threads: int = 0):
     return ip, dp
 
 
+def draw_params_from_words(transforms: np.ndarray, seeds32: np.ndarray, words: np.ndarray, h: int, w: int):
+    """draw_params_batch with the MT19937 seeding already done on the device: words uint32 [B, n] = the first outputs of every
+    task's `random` stream (ops.seed_words).  Same results (tests/test_params_cpu.py); seeds must be non-zero."""
+    import ctypes as C
+    from . import _lib
+    tr = np.ascontiguousarray(transforms, dtype=np.int32)
+    sd = np.ascontiguousarray(seeds32, dtype=np.uint32)
+    wd = np.ascontiguousarray(words).view(np.uint32)
+    B = len(tr)
+    if wd.shape[0] != B or len(sd) != B:
+        raise ValueError("draw_params_from_words: one row of words and one seed per task")
+    ip, dp = np.zeros((B, 8), np.int32), np.zeros((B, 8), np.float64)
+    P = C.c_void_p
+    _lib.check(_lib.load().lfx_draw_augment_params_words(tr.ctypes.data_as(P), sd.ctypes.data_as(P), wd.ctypes.data_as(P), int(wd.shape[1]),
+                                                         B, int(h), int(w), ip.ctypes.data_as(P), dp.ctypes.data_as(P)))
+    return ip, dp
+
+
 class TaskArrays:
     """Struct-of-arrays view of a task list: transform codes, seeds, dataset index of the source image."""
 
@@ -371,7 +391,16 @@ def augment_device(x, tasks, device_noise: bool = True):
         sd = ta.seed[dist_ids]
         dseeds = up.upload({"seeds": (sd & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})["seeds"]
         noise = ops.legacy_normal_noise(sd, h * w * 3, NOISE_LEVEL, dev, dseeds=dseeds).view(len(dist_ids), h, w, 3)
-    ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
+    few_cores = len(os.sched_getaffinity(0)) < 8     # with >= 8 cores the native host drawer is quicker than a device round trip
+    if device_noise and few_cores and len(ta) >= 512 and (ta.seed != 0).all() and int(ta.seed.max()) <= 0xFFFFFFFF:
+        # the seedings of all tasks as one small kernel (lfx_seed_words); the host consumes the first words of each stream
+        # (a rank of an 8-GPU box owns 4 cores: 4608 seedings there cost as much as the rank's augment kernels)
+        sd32 = (ta.seed & 0xFFFFFFFF).astype(np.uint32)
+        d_all = up.upload({"all_seeds": sd32.view(np.int32)})["all_seeds"]
+        words = ops.seed_words(d_all, AugmentSet.SEED_WORDS).cpu().numpy()
+        ip, dp = draw_params_from_words(ta.transform, sd32, words, h, w)
+    else:
+        ip, dp = draw_params_batch(ta.transform, ta.seed, h, w)
     # every per-task parameter array of every op goes to the device in ONE pinned, non-blocking transfer; the kernel
     # launches that follow never wait for the stream to drain
     groups = {"flip": ids_of("flip"), "rotate": ids_of("rotate"), "warp": ids_of("skew", "shear"), "crop": ids_of("crop"),
@@ -431,13 +460,20 @@ class AugmentSet:
 
     OPS = ("flip", "rotate", "skew", "shear", "crop", "distortion")
 
-    def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False):
-        """`concurrent`: launch the noise generator and the five geometric kernels on two side streams, so that they share
+    SEED_WORDS = 16    # stream outputs fetched per task; draws that need more (~1 in 10^4 tasks) are seeded on the host
+
+    def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False, device_seeding: bool = True):
+        """`device_seeding`: the 6 B `random.seed(task seed)` calls of a step run as one small kernel (lfx_seed_words) on a
+        high-priority stream; the host only consumes the first words of each stream (a host core spends ~1.8 us per
+        seeding, which outlasts the GPU step once a rank owns only a few cores).
+        `concurrent`: launch the noise generator and the five geometric kernels on two side streams, so that they share
         the SMs with each other and with whatever the caller queues on its own stream between start() and finish()
         (every kernel of this path is issue- or latency-bound, none fills the machine alone)."""
         import torch
         self.B, self.H, self.W, self.device = int(B), int(H), int(W), device
         self.concurrent = bool(concurrent)
+        self.device_seeding = bool(device_seeding)
+        self._seed_bufs = None
         self._streams = None
         self._pending = None
         u8 = dict(dtype=torch.uint8, device=device)
@@ -488,6 +524,25 @@ class AugmentSet:
             for st in self._streams:
                 st.wait_event(ev0)
         s_noise, s_geo = self._streams if side else (cur, cur)
+        if self.device_seeding:
+            # the step's 6 B seedings: a 25-us kernel on a high-priority stream of its own (it must not queue behind the
+            # previous step's kernels), words back to pinned memory while the noise kernel is being launched
+            if self._seed_bufs is None:
+                nw = self.SEED_WORDS
+                self._seed_bufs = (torch.cuda.Stream(self.device, priority=-1),
+                                   torch.empty(6 * B, dtype=torch.int32).pin_memory(),
+                                   torch.empty(6 * B, dtype=torch.int32, device=self.device),
+                                   torch.empty((6 * B, nw), dtype=torch.int32, device=self.device),
+                                   torch.empty((6 * B, nw), dtype=torch.int32).pin_memory())
+            s_seed, h_seeds, d_seeds, d_words, h_words = self._seed_bufs
+            sd32 = (seeds.reshape(-1) & 0xFFFFFFFF).astype(np.uint32)
+            h_seeds.numpy()[:] = sd32.view(np.int32)
+            with torch.cuda.stream(s_seed):
+                d_seeds.copy_(h_seeds, non_blocking=True)
+                ops.seed_words(d_seeds, self.SEED_WORDS, out=d_words)
+                h_words.copy_(d_words, non_blocking=True)
+                ev_words = torch.cuda.Event()
+                ev_words.record(s_seed)
         # noise first: it needs only the seeds and runs while the host draws the other parameters
         with torch.cuda.stream(s_noise):
             d0 = self._up.upload({"seeds": (seeds[5] & 0xFFFFFFFF).astype(np.uint32).view(np.int32)})
@@ -508,7 +563,11 @@ class AugmentSet:
                                                                         dseeds=d0["seeds"], out=self.noise))
             ev_noise = torch.cuda.Event()
             ev_noise.record(s_noise)
-        ip, dp = draw_params_batch(tr, seeds.reshape(-1), H, W)
+        if self.device_seeding:
+            ev_words.synchronize()
+            ip, dp = draw_params_from_words(tr, sd32, h_words.numpy(), H, W)
+        else:
+            ip, dp = draw_params_batch(tr, seeds.reshape(-1), H, W)
         ip, dp = ip.reshape(6, B, 8), dp.reshape(6, B, 8)
         plan = ops.CropPlan(ip[4, :, :4], (H, W), self.device, upload=False)
         self.rotate_hw = ip[1][:, [7, 6]]
@@ -564,4 +623,4 @@ class AugmentSet:
                 "k_warp_bicubic(shear)": 2 * n * B, "k_lanczos_dp4a": 3 * self.crop_px + n * B, "k_distort_hist+lut+apply": 3 * n * B,
                 "k_legacy_normal_u8": n * B}
 
-    launches_per_run = 9   # noise, flip, rotate, skew, shear, crop, distort hist / lut / apply (+ one memset node)
+    launches_per_run = 10  # seed words, noise, flip, rotate, skew, shear, crop, distort hist / lut / apply (+ one memset node)

@@ -99,7 +99,24 @@ struct PyRandom {
 
     // The reference generator twists a whole block in place in ascending order; doing the same word by word on
     // demand is identical (word i only reads words that are still old, or already new, exactly as there).
+    // words drawn elsewhere (lfx_seed_words): the first n_pre tempered outputs of this seed; `starved` is set when a draw
+    // needs more than that (the caller then seeds on the host and draws again)
+    const uint32_t* pre = nullptr;
+    int n_pre = 0, i_pre = 0;
+    bool starved = false;
+    void attach_words(const uint32_t* wds, int n) {
+        pre = wds;
+        n_pre = n;
+        i_pre = 0;
+        starved = false;
+    }
+
     uint32_t next_u32() {
+        if (pre) {
+            if (i_pre < n_pre) return pre[i_pre++];
+            starved = true;
+            return 0u;          // randbelow(n) accepts 0: every rejection loop ends
+        }
         if (idx == MT_N) idx = 0;
         const int i = idx++;
         const int i1 = (i + 1 == MT_N) ? 0 : i + 1;
@@ -281,6 +298,29 @@ extern "C" int lfx_draw_augment_params(const int32_t* transform, const uint32_t*
             if (lo < hi) pool.emplace_back(work, lo, hi);
         }
         for (auto& th : pool) th.join();
+    }
+    return LFX_OK;
+}
+
+// lfx_draw_augment_params with the seeding done on the device: words[B][nwords] (HOST copy of lfx_seed_words' output) = the
+// first outputs of each task's stream.  A task whose draws need more words (rejection sampling: ~2^-(nwords-3) of the tasks)
+// is seeded here as lfx_draw_augment_params would.
+extern "C" int lfx_draw_augment_params_words(const int32_t* transform, const uint32_t* seed, const uint32_t* words, int nwords, int B,
+                                             int H, int W, int32_t* iparams, double* dparams) {
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(transform && seed && words && iparams && dparams && B > 0 && H > 0 && W > 0 && nwords >= 4, LFX_ERR_ARG,
+                "draw_augment_params_words: bad arguments");
+    PyRandom r;
+    for (int i = 0; i < B; ++i) {
+        LFX_REQUIRE(transform[i] >= LFX_AUG_FLIP && transform[i] <= LFX_AUG_DISTORTION, LFX_ERR_ARG,
+                    "draw_augment_params_words: unknown transform %d at task %d", transform[i], i);
+        r.attach_words(words + (size_t)i * nwords, nwords);
+        draw_one(r, transform[i], H, W, iparams + (size_t)i * 8, dparams + (size_t)i * 8);
+        if (r.starved) {
+            r.pre = nullptr;
+            r.seed(seed[i]);
+            draw_one(r, transform[i], H, W, iparams + (size_t)i * 8, dparams + (size_t)i * 8);
+        }
     }
     return LFX_OK;
 }

@@ -199,7 +199,56 @@ __global__ void __launch_bounds__(RNG_WARPS * 32) k_legacy_normal_u8(const uint3
     }
 }
 
+// CPython's random.seed(int) for 0 <= int < 2^32 (MT19937ar init_genrand(19650218) + init_by_array({key}, 1)) and the
+// first `nwords` tempered 32-bit outputs, one thread per task seed: the 1247-step dependent seeding chain that costs a host
+// core ~1.8 us per task (lfx_params.cu) is ~25 us of latency here for ANY number of tasks.  The state lives in local memory
+// (word i of every thread of a warp is one coalesced line); the first outputs only read words n, n+1 and n+397 of the
+// seeded state (n < 227), so no block twist is needed.
+__global__ void __launch_bounds__(128) k_seed_words(const uint32_t* __restrict__ seeds, int B, int nwords, uint32_t* __restrict__ words) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B) return;
+    uint32_t mt[624];
+    const uint32_t key = seeds[t];
+    uint32_t base = 19650218u, prev = base;
+    mt[0] = prev;
+#pragma unroll 8
+    for (int i = 1; i < 624; ++i) {          // init_genrand word i, then the first init_by_array loop on it
+        base = 1812433253u * (base ^ (base >> 30)) + (uint32_t)i;
+        prev = (base ^ ((prev ^ (prev >> 30)) * 1664525u)) + key;
+        mt[i] = prev;
+    }
+    uint32_t m0 = prev;                      // the wrap: mt[0] = mt[623], then word 1 again (624th step)
+    uint32_t m1 = (mt[1] ^ ((m0 ^ (m0 >> 30)) * 1664525u)) + key;
+    prev = m1;
+#pragma unroll 8
+    for (int i = 2; i < 624; ++i) {          // second loop: 623 steps from word 2
+        prev = (mt[i] ^ ((prev ^ (prev >> 30)) * 1566083941u)) - (uint32_t)i;
+        mt[i] = prev;
+    }
+    m0 = prev;
+    m1 = (m1 ^ ((m0 ^ (m0 >> 30)) * 1566083941u)) - 1u;
+    mt[1] = m1;
+    mt[0] = 0x80000000u;
+    for (int n = 0; n < nwords; ++n) {
+        const uint32_t y = (mt[n] & 0x80000000u) | (mt[n + 1] & 0x7FFFFFFFu);
+        uint32_t v = mt[n + 397] ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+        v ^= (v >> 11);
+        v ^= (v << 7) & 0x9D2C5680u;
+        v ^= (v << 15) & 0xEFC60000u;
+        v ^= (v >> 18);
+        words[(size_t)t * nwords + n] = v;
+    }
+}
+
 }  // namespace
+
+extern "C" int lfx_seed_words(const uint32_t* seeds, int B, int nwords, uint32_t* words, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(seeds && words && B > 0 && nwords >= 1 && nwords <= 226, LFX_ERR_ARG, "seed_words: bad arguments (1 <= nwords <= 226)");
+    k_seed_words<<<lfx_div_up(B, 128), 128, 0, (cudaStream_t)stream>>>(seeds, B, nwords, words);
+    return lfx_check_launch("seed_words");
+}
 
 extern "C" int lfx_legacy_normal_u8(const uint32_t* seeds, uint8_t* out, int B, int n, double loc, double scale, lfx_stream_t stream) {
     LFX_REQUIRE_READY();

@@ -224,6 +224,20 @@ def strategy_raw(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
     return out
 
 
+def seed_words(dseeds: torch.Tensor, nwords: int = 16, out: torch.Tensor = None) -> torch.Tensor:
+    """First `nwords` 32-bit outputs of Python's `random` after random.seed(s) for every task seed s (int32 / uint32 bits,
+    device tensor [B]) -> int32 [B, nwords] on the device (lfx_seed_words: CPython's init_by_array seeding, one thread per
+    task)."""
+    if not dseeds.is_cuda or dseeds.dtype != torch.int32 or not dseeds.is_contiguous():
+        raise ValueError("seed_words: contiguous int32 CUDA tensor expected")
+    lib = _ready(dseeds)
+    B = dseeds.numel()
+    if out is None:
+        out = torch.empty((B, nwords), dtype=torch.int32, device=dseeds.device)
+    _lib.check(lib.lfx_seed_words(_p(dseeds), B, int(nwords), _p(out), _stream()))
+    return out
+
+
 KMEANS_BIAS = {"auto": 0, "dark_bg": 1, "light_bg": 2}
 
 

@@ -336,3 +336,29 @@ def test_lanczos_dp4a_tap_counts(dev, hw, out):
         exp = sa.resize_lanczos(np.ascontiguousarray(imgs[i][t:t + h, l:l + w]), OW, OH)
         assert np.array_equal(got[i], exp), (i, (got[i] != exp).sum())
         assert np.array_equal(gotf[i], exp.astype(np.float32) / np.float32(255.0))
+
+
+def test_seed_words_match_cpython_random(dev):
+    """lfx_seed_words: the first outputs of Python's `random` after random.seed(s), one thread per seed (MT19937ar
+    init_by_array restated on the device), against the interpreter -- and the AugmentSet built on it against the
+    host-seeded AugmentSet (same parameters, same images)."""
+    import random
+
+    from leaffliction_b200 import augment
+    rng = np.random.default_rng(5)
+    seeds = np.concatenate([[1, 2, 42, 999983, 1000000, 2**31 - 1, 2**31, 2**32 - 1], rng.integers(1, 2**32, 3000)]).astype(np.uint32)
+    d = torch.from_numpy(seeds.view(np.int32)).to(dev)
+    for nw in (1, 16, 226):
+        got = ops.seed_words(d, nw).cpu().numpy().view(np.uint32)
+        for i in list(range(8)) + list(range(8, len(seeds), 97)):
+            random.seed(int(seeds[i]))
+            assert [random.getrandbits(32) for _ in range(nw)] == got[i].tolist(), (nw, i)
+    B = 96
+    x = up(synth.leaf_batch(B, 256, 256, 99), dev)
+    task_seeds = rng.integers(1, 1000001, (6, B)).astype(np.int64)
+    a = augment.AugmentSet(B, 256, 256, dev, device_seeding=True).run(x, task_seeds)
+    b = augment.AugmentSet(B, 256, 256, dev, device_seeding=False).run(x, task_seeds)
+    torch.cuda.synchronize()
+    for name in ("flip", "skew", "shear", "crop", "distortion", "rotate"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert np.array_equal(a.rotate_hw, b.rotate_hw)

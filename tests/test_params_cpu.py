@@ -130,3 +130,28 @@ def test_native_params_property_random_shapes_and_seeds():
         if code == 1:
             assert ip[0, 6] >= 1 and ip[0, 7] >= 1 and -30.0 <= dp[0, 0] <= 30.0
     check()
+
+
+def test_params_from_stream_words_match_the_interpreter():
+    """lfx_draw_augment_params_words (the host half of the device-seeded path): given the first outputs of each task's
+    `random` stream -- produced here by the interpreter itself, on the GPU by lfx_seed_words -- it returns exactly what
+    lfx_draw_augment_params returns; with too few words the task is re-seeded on the host (same results)."""
+    import random
+
+    from leaffliction_b200 import augment
+    rng = np.random.default_rng(77)
+    B = 1200
+    tr = rng.integers(0, 6, B).astype(np.int32)
+    seeds = rng.integers(1, 1000001, B).astype(np.int64)
+    seeds[:4] = (1, 2**31, 2**32 - 1, 999983)
+    ip0, dp0 = augment.draw_params_batch(tr, seeds, 256, 256)
+    for nw in (16, 4):
+        words = np.zeros((B, nw), np.uint32)
+        for i, sd in enumerate(seeds):
+            random.seed(int(sd))
+            words[i] = [random.getrandbits(32) for _ in range(nw)]
+        ip, dp = augment.draw_params_from_words(tr, seeds.astype(np.uint32), words, 256, 256)
+        assert np.array_equal(ip, ip0) and np.array_equal(dp, dp0), nw
+    ip1, dp1 = augment.draw_params_from_words(tr, seeds.astype(np.uint32), words, 96, 160)
+    ip2, dp2 = augment.draw_params_batch(tr, seeds, 96, 160)
+    assert np.array_equal(ip1, ip2) and np.array_equal(dp1, dp2)
