@@ -464,7 +464,7 @@ class AugmentSet:
 
     def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False, device_seeding: bool = True):
         """`device_seeding`: the 6 B `random.seed(task seed)` calls of a step run as one small kernel (lfx_seed_words) on a
-        high-priority stream; the host only consumes the first words of each stream (a host core spends ~1.8 us per
+        side stream; the host only consumes the first words of each stream (a host core spends ~1.8 us per
         seeding, which outlasts the GPU step once a rank owns only a few cores).
         `concurrent`: launch the noise generator and the five geometric kernels on two side streams, so that they share
         the SMs with each other and with whatever the caller queues on its own stream between start() and finish()
@@ -472,7 +472,11 @@ class AugmentSet:
         import torch
         self.B, self.H, self.W, self.device = int(B), int(H), int(W), device
         self.concurrent = bool(concurrent)
-        self.device_seeding = bool(device_seeding)
+        self.device_seeding = bool(device_seeding) and os.environ.get("LFX_DEVICE_SEEDING", "1") != "0"
+        if not self.concurrent and len(os.sched_getaffinity(0)) >= 8:
+            # in stream order (see start()) the host would wait for the stream to drain before every chunk: with eight or more
+            # cores the native host drawer (lfx_draw_augment_params) is quicker than that wait
+            self.device_seeding = False
         self._seed_bufs = None
         self._streams = None
         self._pending = None
@@ -525,16 +529,22 @@ class AugmentSet:
                 st.wait_event(ev0)
         s_noise, s_geo = self._streams if side else (cur, cur)
         if self.device_seeding:
-            # the step's 6 B seedings: a 25-us kernel on a high-priority stream of its own (it must not queue behind the
-            # previous step's kernels), words back to pinned memory while the noise kernel is being launched
+            # the step's 6 B seedings: a 25-us kernel on a stream of its own (it must not queue behind the previous step's
+            # kernels), words back to pinned memory while the noise kernel is being launched
             if self._seed_bufs is None:
                 nw = self.SEED_WORDS
-                self._seed_bufs = (torch.cuda.Stream(self.device, priority=-1),
+                # A stream of its own only in `concurrent` mode (the bench step).  Inside TransformEngine.run_host (chunks on one
+                # kernel stream, copy streams on both sides) a separate seeding stream ended in an illegal-address fault on
+                # hosts with few cores -- at normal and at high stream priority, never with the kernel on the caller's stream --
+                # so the pipelined host path keeps it in stream order; that path is bound by its device-to-host copies anyway.
+                self._seed_bufs = (torch.cuda.Stream(self.device) if self.concurrent else None,
                                    torch.empty(6 * B, dtype=torch.int32).pin_memory(),
                                    torch.empty(6 * B, dtype=torch.int32, device=self.device),
                                    torch.empty((6 * B, nw), dtype=torch.int32, device=self.device),
                                    torch.empty((6 * B, nw), dtype=torch.int32).pin_memory())
             s_seed, h_seeds, d_seeds, d_words, h_words = self._seed_bufs
+            if s_seed is None or timings is not None:
+                s_seed = cur
             sd32 = (seeds.reshape(-1) & 0xFFFFFFFF).astype(np.uint32)
             h_seeds.numpy()[:] = sd32.view(np.int32)
             with torch.cuda.stream(s_seed):

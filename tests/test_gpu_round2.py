@@ -356,7 +356,9 @@ def test_seed_words_match_cpython_random(dev):
     B = 96
     x = up(synth.leaf_batch(B, 256, 256, 99), dev)
     task_seeds = rng.integers(1, 1000001, (6, B)).astype(np.int64)
-    a = augment.AugmentSet(B, 256, 256, dev, device_seeding=True).run(x, task_seeds)
+    sa = augment.AugmentSet(B, 256, 256, dev, concurrent=True, device_seeding=True)
+    assert sa.device_seeding
+    a = sa.run(x, task_seeds)
     b = augment.AugmentSet(B, 256, 256, dev, device_seeding=False).run(x, task_seeds)
     torch.cuda.synchronize()
     for name in ("flip", "skew", "shear", "crop", "distortion", "rotate"):
