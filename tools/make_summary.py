@@ -26,6 +26,14 @@ def launch_shares():
     return [(k, v[0], v[1] / 1e6, v[1] / tot) for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]) if v[1] / tot > 0.001]
 
 
+def jpeg_table():
+    j = json.load(open(P("r02_jpeg.json")))
+    return (f"| | nvJPEG on the B200 (libleafx_jpeg.so) | Pillow on {j['host_cores']} host threads |\n|---|---|---|\n"
+            f"| decode, images/s | {j['decode_images_per_s']:,.0f} (GPU_HYBRID backend, pixels land in HBM) | {j['pillow_decode_images_per_s']:,.0f} |\n"
+            f"| encode, images/s | {j['encode_images_per_s']:,.0f} ({j['host_cores']} encoder states / streams, from device memory) | {j['pillow_encode_images_per_s']:,.0f} |\n"
+            f"| bytes over PCIe per image | {j['pcie_bytes_per_image']['jpeg_q95']:,.0f} (bitstream) | {j['pcie_bytes_per_image']['raw_rgb']:,} (raw RGB) |")
+
+
 def ops_table(new, old):
     out = []
     for k, v in new.items():
@@ -91,18 +99,23 @@ Phase split of `k_core` (LFX_CORE_TIMING=1): profiles/r02_k_core_phase_split.txt
 | c4_1024 | {c['c4_1024']['value']:,.0f} images/s | 256 x 1024x1024: skew + shear + rotate + 5x5 blur = {c['c4_1024']['frac'] * 100:.1f} % of peak; pipeline_core {c['c4_1024']['ops']['pipeline_core']['ms']} ms ({c['c4_1024']['ops']['pipeline_core']['frac'] * 100:.1f} %) |
 | c5_resize224 | {c['c5_resize224']['value']:,.0f} images/s | flip -> Lanczos 224 -> /255 f32 -> DLPack, best batch; batches: {json.dumps({k: v['images_per_s'] for k, v in c['c5_resize224']['batches'].items()})} |
 
-## Scaling (torchrun, 20 steps; the 2- and 8-GPU records predate the last kernel tweaks by a few per cent)
+## Scaling (torchrun, 20 steps)
 
 | GPUs | images/s | ms/step | weak-scaling efficiency | e2e images/s | pinned copy GB/s per rank (in / out) | e2e / ceiling | c3 augmented images/s |
 |---|---|---|---|---|---|---|---|
 | 1 | {b['value']:,.0f} | {b['ms_per_step']:.3f} | 1 | {b['e2e']['value']:,.0f} | {b['e2e']['pcie']['h2d_gbs']} / {b['e2e']['pcie']['d2h_gbs']} | {b['e2e']['pcie']['frac_of_ceiling']:.2f} | {c['c3_balance']['value']:,.0f} |
-| 2 | {b2['value']:,.0f} | {b2['ms_per_step']:.3f} | (12.85 ms at N = 1 in the same build) 0.99 | {b2['e2e']['value']:,.0f} | {b2['e2e']['pcie']['h2d_gbs']} / {b2['e2e']['pcie']['d2h_gbs']} | {b2['e2e']['pcie']['frac_of_ceiling']:.2f} | {b2['configs']['c3_balance']['value']:,.0f} |
-| 8 | {b8['value']:,.0f} | {b8['ms_per_step']:.3f} | 0.99 | {b8['e2e']['value']:,.0f} | {b8['e2e']['pcie']['h2d_gbs']} / {b8['e2e']['pcie']['d2h_gbs']} | {b8['e2e']['pcie']['frac_of_ceiling']:.2f} | {b8['configs']['c3_balance']['value']:,.0f} |
+| 2 | {b2['value']:,.0f} | {b2['ms_per_step']:.3f} | {b['ms_per_step'] / b2['ms_per_step']:.3f} | {b2['e2e']['value']:,.0f} | {b2['e2e']['pcie']['h2d_gbs']} / {b2['e2e']['pcie']['d2h_gbs']} | {b2['e2e']['pcie']['frac_of_ceiling']:.2f} | {b2['configs']['c3_balance']['value']:,.0f} |
+| 8 | {b8['value']:,.0f} | {b8['ms_per_step']:.3f} | {b['ms_per_step'] / b8['ms_per_step']:.3f} | {b8['e2e']['value']:,.0f} | {b8['e2e']['pcie']['h2d_gbs']} / {b8['e2e']['pcie']['d2h_gbs']} | {b8['e2e']['pcie']['frac_of_ceiling']:.2f} | {b8['configs']['c3_balance']['value']:,.0f} |
 
-With 8 ranks copying at once the pinned-copy probe drops to ~17 GB/s per rank (one host memory system, 4 cores per rank): the host, not the GPUs, bounds the
-host-to-host number beyond 2 GPUs.  A first 8-GPU run of this round took 22.9 ms/step: the per-step parameter draw (24,576 task seeds through CPython's MT19937
-seeding) ran on the 4 host cores a rank owns there and outlasted the GPU step.  Fixed on the host side (8 seeds interleaved per core: 4x faster seeding; exact integer
-round(x, 15); thread count from the CPU affinity): under `taskset` on one GPU a step costs 13.3 ms with 4 cores and 14.5 ms with 2.
+With 8 ranks copying at once the pinned-copy probe drops to ~17-20 GB/s per rank (one host memory system, 4 cores per rank): the host, not the GPUs, bounds the
+host-to-host number beyond 2 GPUs.  The per-step parameter draw (24,576 `random.seed(task seed)` calls, CPython's MT19937 init_by_array) used to run on the
+rank's host cores (1.8 us per seeding and core: 11.5 ms/step at 8 GPUs with 4 cores per rank, 13.3 / 14.5 ms under `taskset` with 4 / 2 cores on one GPU); it is now
+one small kernel per step (`lfx_seed_words`, one thread per task, ~25 us), the host only consumes the first 16 words of each stream: 11.10 ms/step with 2, 4 or
+16 cores, 8-GPU weak scaling 0.967 -> {b['ms_per_step'] / b8['ms_per_step']:.3f}, class balancing at 8 GPUs 9.35 M -> {b8['configs']['c3_balance']['value'] / 1e6:.1f} M augmented images/s.
+
+## JPEG file boundary (`tools/bench_jpeg.py`, profiles/r02_jpeg.json: 4096 x 256^2, quality 95)
+
+{jpeg_table()}
 
 ## Per-op kernels (`tools/bench_ops.py`, profiles/r02_ops_256.json: 4096 x 256^2)
 
