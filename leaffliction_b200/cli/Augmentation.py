@@ -43,8 +43,6 @@ def build_parser() -> argparse.ArgumentParser:
                                                    "artifacts/example for single images)")
     parser.add_argument("-seed", "--seed", type=int, default=DEFAULT_SEED, help="Random seed for reproducible results")
     parser.add_argument("--workers", type=int, default=None, help="JPEG I/O threads (default min(8, cores)); the GPU batches themselves ignore it")
-    parser.add_argument("--gpu-jpeg", action="store_true", help="(extension) decode / encode the JPEG files on the GPU with nvJPEG "
-                                                                 "instead of Pillow; pixels stay in device memory between the two")
     return parser
 
 
@@ -79,7 +77,7 @@ def dataset_mode_dir(args, source_dir: Path):
         torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
         dist.init_process_group("nccl")
     balancer = DatasetBalancer(source_dir=str(source_dir), target_dir=str(target_dir), seed=args.seed, workers=args.workers,
-                               rank=rank, world=world, gpu_jpeg=getattr(args, "gpu_jpeg", False))
+                               rank=rank, world=world, gpu_jpeg=os.environ.get("LEAFX_GPU_JPEG", "0") == "1")
     balancer.run()
     if rank == 0:
         rows = count_images(target_dir, None)

@@ -9,6 +9,7 @@ from __future__ import annotations
 import argparse
 import json
 import logging
+import os
 import re
 from dataclasses import dataclass
 from pathlib import Path
@@ -45,8 +46,6 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--skip-existing", action="store_true", help="Skip images whose outputs already exist")
     p.add_argument("--overwrite", action="store_true", help="Overwrite existing outputs")
     p.add_argument("--preview", action="store_true", help="Force saving outputs (no GUI popups)")
-    p.add_argument("--gpu-jpeg", action="store_true", help="(extension, folder mode) decode the sources and encode the outputs on the "
-                                                            "GPU with nvJPEG instead of Pillow")
     return p
 
 
@@ -61,7 +60,7 @@ def _want(params: ProcessArgs, out: Path) -> bool:
 def process_single_image(params: ProcessArgs, premade=None, rgb=None, sink=None) -> List[Path]:
     """Transformation.py:423-536.  `premade` = (mask, contour) from a batched make_mask (folder mode); `rgb` = the already
     decoded image; `sink`: a list that receives (path, image) instead of the file being written here (folder mode with
-    --gpu-jpeg encodes them as one batch)."""
+    LEAFX_GPU_JPEG=1 encodes them as one batch)."""
     if rgb is None:
         try:
             rgb = T.pil_read_rgb(params.img_path)
@@ -238,7 +237,9 @@ def main(argv=None) -> None:
             logging.error("Source directory does not exist: %s", src)
             return
         dst.mkdir(parents=True, exist_ok=True)
-        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite, workers=args.workers, gpu_jpeg=args.gpu_jpeg)
+        # LEAFX_GPU_JPEG=1: nvJPEG decode / encode in folder mode (an environment switch: the flag set stays the reference's)
+        run_folder(src, dst, types, cfg, args.skip_existing, args.overwrite, workers=args.workers,
+                   gpu_jpeg=os.environ.get("LEAFX_GPU_JPEG", "0") == "1")
         return
     logging.error("Must specify either single image or --src/--dst for folder mode")
 

@@ -28,6 +28,7 @@ def test_augmentation_flags():
     assert f["output"][0] == ("-out", "--output")
     assert f["seed"] == (("-seed", "--seed"), 42, "int", None)
     assert f["workers"][0] == ("--workers",)
+    assert set(f) == {"input_path", "output", "seed", "workers"}
     a = A.parse_args(["images/", "-out", "o", "-seed", "7", "--workers", "3"])
     assert (a.input_path, a.output, a.seed, a.workers) == ("images/", "o", 7, 3)
     assert A.TRANSFORMATIONS == ["flip", "rotate", "skew", "shear", "crop", "distortion"]

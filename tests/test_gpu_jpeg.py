@@ -140,7 +140,7 @@ def test_dataset_balancer_with_gpu_jpeg(tmp_path):
         assert _psnr(a, b) > 30.0, (n, _psnr(a, b))
 
 
-def test_transformation_folder_with_gpu_jpeg(tmp_path):
+def test_transformation_folder_with_gpu_jpeg(tmp_path, monkeypatch):
     src = tmp_path / "in"
     src.mkdir()
     for i in range(3):
@@ -154,7 +154,9 @@ def test_transformation_folder_with_gpu_jpeg(tmp_path):
     cfgp.write_text(txt)
     d_host, d_gpu = tmp_path / "host", tmp_path / "gpu"
     TC.main(["-src", str(src), "-dst", str(d_host), "--types", "mask,roi,blur", "--config", str(cfgp)])
-    TC.main(["-src", str(src), "-dst", str(d_gpu), "--types", "mask,roi,blur", "--config", str(cfgp), "--gpu-jpeg"])
+    monkeypatch.setenv("LEAFX_GPU_JPEG", "1")
+    TC.main(["-src", str(src), "-dst", str(d_gpu), "--types", "mask,roi,blur", "--config", str(cfgp)])
+    monkeypatch.delenv("LEAFX_GPU_JPEG")
     n1 = sorted(p.name for p in d_host.iterdir())
     n2 = sorted(p.name for p in d_gpu.iterdir())
     assert n1 == n2 and len(n1) == 12 and not any(n.startswith("broken") for n in n1)
