@@ -87,3 +87,31 @@ def test_kmeans_candidate_any_size(dev, shape):
     for i in range(len(imgs)):
         exp = sk.kmeans_mask(imgs[i], scfg)
         assert np.array_equal(raw[i], exp), (i, int((raw[i] != exp).sum()))
+
+
+def test_kmeans_and_auto_against_the_reference_made_fixture(dev):
+    """CUDA against tests/golden/golden_v1.npz directly (arrays produced by the reference's own `_create_kmeans_mask` and
+    `make_mask(mask_strategy="auto")`, make_golden.py): 64x64 / 96x64 / 256x256 leaves and adversarial images."""
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import make_golden as mg
+    G = np.load(os.path.join(here, "golden", "golden_v1.npz"))
+    imgs = mg.inputs()
+    for k in [f for f in G.files if f.startswith("kmeans_raw/")]:
+        _, bias, name = k.split("/")
+        cfg = transform.default_config(mask_strategy="kmeans", bg_bias=bias, grabcut_refine=False, mask_upscale_factor=1.0,
+                                       mask_upscale_long_side=0)
+        got = transform.kmeans_candidate(torch.from_numpy(imgs[name][None]).to(dev), cfg).cpu().numpy()[0]
+        assert np.array_equal(got, G[k]), f"{k}: {(got != G[k]).sum()} px differ"
+    for strat in ("kmeans", "auto"):
+        cfg = transform.default_config(mask_strategy=strat, grabcut_refine=False, mask_upscale_factor=1.0, mask_upscale_long_side=0)
+        for k in [f for f in G.files if f.startswith(f"mask/{strat}/")]:
+            name = k.split("/")[-1]
+            masks, info, contours = transform.make_mask_batch(imgs[name][None], cfg)
+            assert np.array_equal(masks[0], G[k]), f"{k}: {(masks[0] != G[k]).sum()} px differ"
+            bk = f"bbox/{strat}/{name}"
+            assert (contours[0] is not None) == (bk in G.files), k
+            if contours[0] is not None:
+                assert tuple(int(v) for v in info[0, 1:5]) == tuple(int(v) for v in G[bk]), k

@@ -82,6 +82,28 @@ def test_make_mask_matches_reference(strategy):
             assert int(G[f"area2/{strategy}/{name}"][0]) == info["area2"], k
 
 
+def test_kmeans_candidate_and_auto_match_reference():
+    """oracle/spec_kmeans.py (cv2.kmeans + cv::RNG restated) against the reference's `_create_kmeans_mask` outputs, and the
+    seven-candidate `mask_strategy: auto` against the reference's make_mask -- from the fixture, so it runs anywhere."""
+    from oracle import spec_kmeans as sk
+    keys = _keys("kmeans_raw/")
+    assert len(keys) == 15
+    for k in keys:
+        _, bias, name = k.split("/")
+        got = sk.kmeans_mask(IMGS[name], sm.Cfg(mask_strategy="kmeans", bg_bias=bias))
+        assert np.array_equal(got, G[k]), f"{k}: {(got != G[k]).sum()} px differ"
+    keys = _keys("mask/auto/")
+    assert len(keys) == 5
+    for k in keys:
+        name = k.split("/")[-1]
+        m, info = sm.make_mask_auto(IMGS[name], sm.Cfg(mask_strategy="auto"))
+        assert np.array_equal(m, G[k]), f"{k}: {(m != G[k]).sum()} px differ"
+        bk = f"bbox/auto/{name}"
+        assert (info is not None) == (bk in G.files), k
+        if info is not None:
+            assert tuple(int(v) for v in G[bk]) == info["bbox"], k
+
+
 @pytest.mark.parametrize("name", ["leaf64_0", "leaf96x64", "leaf256", "adv_frame"])
 def test_transform_filters_match_reference(name):
     img = IMGS[name]
