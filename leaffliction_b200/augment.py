@@ -495,6 +495,10 @@ class AugmentSet:
         self.rotate = torch.empty((B, self.rotate_stride), **u8)
         self.rotate_hw = None              # int32 [B,2] (nh, nw) on the host
         self._up = None
+        # every Lanczos table a crop of this image size can need (nw = int(W * r), r in [0.8, 0.95], image_augmenter.py:100-103),
+        # so that the device copy of the tables is uploaded once and never replaced under queued kernels
+        _ops()._lanczos.prefill(int(W * 0.8), int(W * 0.95) + 1, W)
+        _ops()._lanczos.prefill(int(H * 0.8), int(H * 0.95) + 1, H)
 
     def out_bytes_per_image(self, rotate_px_mean: float) -> float:
         n = self.H * self.W * 3

@@ -459,13 +459,22 @@ class LanczosTables:
         self.kstride = 0
         self.nrows = 0
         self._dev = None
+        self._retired = []   # superseded device copies: kernels already queued on other streams may still read them
+
+    def prefill(self, in_lo: int, in_hi: int, out_size: int):
+        """Tables for every source size in [in_lo, in_hi] at once (ImageAugmenter.crop draws nw = int(W * r), r in [0.8, 0.95]):
+        the device copy then never changes while crops of that image size are in flight."""
+        for sz in range(max(1, int(in_lo)), int(in_hi) + 1):
+            self.get(sz, out_size)
 
     def _ensure_stride(self, ks):
         if ks > self.kstride:
             new = ((ks + 7) // 8) * 8
             self.kk = [np.pad(k, ((0, 0), (0, new - k.shape[1]))) for k in self.kk]
             self.kstride = new
-            self._dev = None
+            if self._dev is not None:
+                self._retired.append(self._dev)
+                self._dev = None
 
     def get(self, in_size: int, out_size: int):
         key = (int(in_size), int(out_size))
@@ -484,13 +493,15 @@ class LanczosTables:
             self.bounds.append(b)
             self.kk.append(k)
             self.nrows += key[1]
-            self._dev = None
         return self.rows[key]
 
     def device(self, device):
-        if self._dev is None or self._dev[0].device != device:
-            self._dev = (_dev(np.concatenate(self.bounds), np.int32, device), _dev(np.concatenate(self.kk), np.int32, device))
-        return self._dev
+        if self._dev is None or self._dev[0].device != device or self._dev[2] != self.nrows:
+            if self._dev is not None:
+                self._retired.append(self._dev)      # never handed back to the allocator while a queued kernel may use it
+                del self._retired[:-64]
+            self._dev = (_dev(np.concatenate(self.bounds), np.int32, device), _dev(np.concatenate(self.kk), np.int32, device), self.nrows)
+        return self._dev[0], self._dev[1]
 
 
 _lanczos = LanczosTables()
