@@ -234,13 +234,13 @@ def main():
     engine = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, chunk=512, augment=not args.transform_only)
     out = ops.alloc_core_outputs(B, S, S, (256, 256), dev)
     ds_hist = torch.zeros((9, 256), dtype=torch.int64, device=dev)
-    augset = None if args.transform_only else aug_mod.AugmentSet(B, S, S, dev, concurrent=not args.serial)
+    augset = None if args.transform_only else aug_mod.AugmentSet(B, S, S, dev, concurrent=not args.serial, pipelined=not args.serial)
     seeds = task_seeds(B, rank)
 
     def step():
-        # three streams: the noise generator, the five geometric augment kernels and k_core run side by side (all of them
-        # are issue- or latency-bound: together they keep the schedulers busier than back to back); the distortion,
-        # which needs the noise, closes the step on the main stream
+        # three streams: noise + distortion, the five geometric augment kernels, and k_core run side by side (all but the
+        # distortion are issue- or latency-bound: together they keep the schedulers busier than back to back); the steps
+        # are pipelined: each stream is in order with itself, the streams are joined once per timed pass (merge())
         if augset is not None:
             augset.start(x, seeds)               # augment half: 6 ops x B images (side streams)
         engine.run_device(x, out, ds_hist)       # k_core: transform half + the rank's dataset colour histogram
@@ -248,6 +248,8 @@ def main():
             augset.finish()
 
     def merge():
+        if augset is not None:
+            augset.join()      # pipelined steps: the caller's stream waits for the augment streams once per pass
         if world > 1:  # ONE allreduce per dataset pass, inside the timed region
             dist.all_reduce(ds_hist)
 

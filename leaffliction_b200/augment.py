@@ -462,7 +462,7 @@ class AugmentSet:
 
     SEED_WORDS = 16    # stream outputs fetched per task; draws that need more (~1 in 10^4 tasks) are seeded on the host
 
-    def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False, device_seeding: bool = True):
+    def __init__(self, B: int, H: int, W: int, device, concurrent: bool = False, device_seeding: bool = True, pipelined: bool = False):
         """`device_seeding`: the 6 B `random.seed(task seed)` calls of a step run as one small kernel (lfx_seed_words) on a
         side stream; the host only consumes the first words of each stream (a host core spends ~1.8 us per
         seeding, which outlasts the GPU step once a rank owns only a few cores).
@@ -472,6 +472,12 @@ class AugmentSet:
         import torch
         self.B, self.H, self.W, self.device = int(B), int(H), int(W), device
         self.concurrent = bool(concurrent)
+        # pipelined (with `concurrent`): the distortion runs on the noise stream, right behind its noise, and finish() does NOT
+        # join the side streams into the caller's stream -- consecutive steps overlap (the memory-bound distortion of step i runs
+        # under the issue-bound geometric kernels and k_core of step i + 1).  Each side stream is in order with itself, so the
+        # set's own buffers are safe; the CALLER must call join() before it reads any output or overwrites `x`.
+        self.pipelined = bool(pipelined) and self.concurrent
+        self._done = None
         self.device_seeding = bool(device_seeding) and os.environ.get("LFX_DEVICE_SEEDING", "1") != "0"
         if not self.concurrent and len(os.sched_getaffinity(0)) >= 8:
             # in stream order (see start()) the host would wait for the stream to drain before every chunk: with eight or more
@@ -586,6 +592,13 @@ class AugmentSet:
         plan = ops.CropPlan(ip[4, :, :4], (H, W), self.device, upload=False)
         self.rotate_hw = ip[1][:, [7, 6]]
         self.crop_px = int((ip[4, :, 2].astype(np.int64) * ip[4, :, 3]).sum())
+        if side and self.pipelined:
+            with torch.cuda.stream(s_noise):
+                # the cut-offs go up on the noise stream (their buffer is then allocated, used and recycled on ONE stream)
+                dc = self._up.upload({"cuts": ip[5, :, 0]})
+                ops.distort(x, self.noise.view(B, H, W, 3), dc["cuts"], out=self.distortion, hist_ws=self.hist_ws)
+                ev_noise = torch.cuda.Event()
+                ev_noise.record(s_noise)
         with torch.cuda.stream(s_geo):
             d = self._up.upload({"flip_mode": ip[0, :, 0], "rot": ip[1], "skew_coef": dp[2], "skew_persp": ip[2, :, 0],
                                  "shear_coef": dp[3], "shear_persp": ip[3, :, 0], "crop_box": plan.h_box, "crop_off": plan.h_off,
@@ -599,6 +612,18 @@ class AugmentSet:
             ev_geo = torch.cuda.Event()
             ev_geo.record(s_geo)
         self._pending = (x, d, ev_noise, ev_geo, side)
+        if side and self.pipelined:
+            self._done = (ev_noise, ev_geo)
+        return self
+
+    def join(self):
+        """pipelined mode: make the caller's stream wait for everything queued so far (no-op otherwise)."""
+        import torch
+        if self._done is not None:
+            cur = torch.cuda.current_stream(self.device)
+            for ev in self._done:
+                cur.wait_event(ev)
+            self._done = None
         return self
 
     def finish(self, timings: dict = None):
@@ -608,6 +633,8 @@ class AugmentSet:
             raise RuntimeError("AugmentSet.finish() without start()")
         x, d, ev_noise, ev_geo, side = self._pending
         self._pending = None
+        if side and self.pipelined:
+            return self                    # the distortion is already queued behind its noise; join() orders the caller's stream
         B, H, W = self.B, self.H, self.W
         cur = torch.cuda.current_stream(self.device)
         if side:

@@ -367,3 +367,27 @@ def test_seed_words_match_cpython_random(dev):
     for i, (nh, nw) in enumerate(a.rotate_hw):          # the slab beyond an image's own extent is never written
         n = int(nh) * int(nw) * 3
         assert torch.equal(a.rotate[i, :n], b.rotate[i, :n]), ("rotate", i)
+
+
+def test_pipelined_augment_set_equals_the_joined_one(dev):
+    """AugmentSet(concurrent=True, pipelined=True): steps overlap on the side streams and the caller joins once (join());
+    the outputs of the LAST step equal those of a plain AugmentSet run with the same seeds."""
+    from leaffliction_b200 import augment
+    rng = np.random.default_rng(12)
+    B = 64
+    x = up(synth.leaf_batch(B, 256, 256, 31), dev)
+    p = augment.AugmentSet(B, 256, 256, dev, concurrent=True, pipelined=True)
+    q = augment.AugmentSet(B, 256, 256, dev)
+    for _ in range(4):
+        seeds = rng.integers(1, 1000001, (6, B)).astype(np.int64)
+        p.start(x, seeds)
+        p.finish()
+    p.join()
+    q.run(x, seeds)
+    torch.cuda.synchronize()
+    for name in ("flip", "skew", "shear", "crop", "distortion"):
+        assert torch.equal(getattr(p, name), getattr(q, name)), name
+    assert np.array_equal(p.rotate_hw, q.rotate_hw)
+    for i, (nh, nw) in enumerate(p.rotate_hw):
+        n = int(nh) * int(nw) * 3
+        assert torch.equal(p.rotate[i, :n], q.rotate[i, :n]), ("rotate", i)
