@@ -80,6 +80,14 @@ def main():
         res["saliency_blur(1024 img)"] = {"ms": round(t, 4), "images_per_s": round(nsub / (t / 1e3))}
         t = timed(lambda: ops.brown_spots(xs, ms_, cfg), args.reps)
         res["brown_spots(1024 img)"] = {"ms": round(t, 4), "images_per_s": round(nsub / (t / 1e3))}
+        if max(S, S) == 256:   # k-means candidate (cv2.kmeans restated): the image stays in shared memory for every pass
+            t = timed(lambda: ops.kmeans_raw(xs), args.reps)
+            res["kmeans_raw(1024 img)"] = {"ms": round(t, 4), "images_per_s": round(nsub / (t / 1e3))}
+    dsd = torch.arange(1, 6 * B + 1, dtype=torch.int32, device=dev)
+    t = timed(lambda: ops.seed_words(dsd, 16), args.reps)
+    res[f"seed_words({6 * B} task seeds)"] = {"ms": round(t, 4), "seedings_per_s": round(6 * B / (t / 1e3))}
+    if N <= 65536:
+        pass
 
     # ---- augmentations (parameters drawn like the reference)
     dmode = torch.zeros(B, dtype=torch.int32, device=dev)
