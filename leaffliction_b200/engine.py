@@ -64,9 +64,10 @@ def alloc_host_outputs(B, H, W, roi_size=(256, 256), augment: bool = False) -> H
 class TransformEngine:
     def __init__(self, H: int, W: int, cfg=None, gaussian_sigma: float = 1.5, roi_size=(256, 256),
                  device: Optional[torch.device] = None, chunk: int = 512, front: Optional[str] = None,
-                 augment: bool = False):
+                 augment: bool = False, bg_bias: str = "light_bg"):
         """`front`: None = the strategy in `cfg` (hsv_h / lab / hsv_s / hsv_v_dark, fused kernel where the shape allows);
-        'inclusive' (the reference's default strategy) or 'enhanced' = raw candidate by the front-end kernel first.
+        'inclusive' (the reference's default strategy) or 'enhanced' = raw candidate by the front-end kernel first;
+        'kmeans' = the k-means candidate (cv2.kmeans restated, `bg_bias` as TransformConfig.bg_bias; longer side 256).
         `augment`: run_host also produces the six ImageAugmenter outputs of every image (needs `seeds` per call)."""
         if not torch.cuda.is_available():
             raise RuntimeError("TransformEngine needs a CUDA device: leaffliction_b200 has no CPU fallback")
@@ -76,9 +77,10 @@ class TransformEngine:
         self.sigma = float(gaussian_sigma)
         self.roi_size = (int(roi_size[0]), int(roi_size[1]))
         self.chunk = int(chunk)
-        if front not in (None, "inclusive", "enhanced"):
-            raise ValueError(f"front must be None, 'inclusive' or 'enhanced', not {front!r}")
+        if front not in (None, "inclusive", "enhanced", "kmeans"):
+            raise ValueError(f"front must be None, 'inclusive', 'enhanced' or 'kmeans', not {front!r}")
         self.front = front
+        self.bg_bias = bg_bias
         self.augment = bool(augment)
         self._aug = None
         self._bufs = None
@@ -87,7 +89,7 @@ class TransformEngine:
     # ---- device-resident
     def _pipeline(self, x, out, dataset_hist=None):
         if self.front:
-            return ops.pipeline_front(x, self.front, self.cfg, self.sigma, self.roi_size, out, dataset_hist)
+            return ops.pipeline_front(x, self.front, self.cfg, self.sigma, self.roi_size, out, dataset_hist, self.bg_bias)
         return ops.pipeline_core(x, self.cfg, self.sigma, self.roi_size, out, dataset_hist)
 
     def run_device(self, x: torch.Tensor, out: Optional[ops.CoreOutputs] = None,

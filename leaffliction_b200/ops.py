@@ -366,13 +366,14 @@ def pipeline_core(x: torch.Tensor, cfg: MaskCfg, gaussian_sigma: float = 1.5, ro
 
 
 def pipeline_front(x: torch.Tensor, which: str, cfg: MaskCfg, gaussian_sigma: float = 1.5, roi_size=(256, 256),
-                   out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None) -> CoreOutputs:
-    """The core transform profile with the reference's DEFAULT mask strategies ('inclusive', config.yaml:7, or 'enhanced'):
-    raw candidate by the front-end kernel (lfx_raw_mask), then make_mask on that candidate (strategy 4), 5x5 blur, masked ROI
-    letterbox and colour statistics -- the same outputs as pipeline_core."""
+                   out: Optional[CoreOutputs] = None, dataset_hist: Optional[torch.Tensor] = None, bg_bias: str = "light_bg") -> CoreOutputs:
+    """The core transform profile with the reference's DEFAULT mask strategies ('inclusive', config.yaml:7, or 'enhanced'), or
+    with the k-means candidate ('kmeans', mask.py:109-140; images whose longer side is 256): raw candidate by the front-end
+    kernel (lfx_raw_mask / lfx_kmeans_raw), then make_mask on that candidate (strategy 4), 5x5 blur, masked ROI letterbox and
+    colour statistics -- the same outputs as pipeline_core."""
     import copy
     _chk_img(x)
-    raw = raw_mask_front_end(x, which, cfg)
+    raw = kmeans_raw(x, (cfg.green_lo, cfg.green_hi), bg_bias) if which == "kmeans" else raw_mask_front_end(x, which, cfg)
     cfg4 = copy.copy(cfg)
     cfg4.strategy = STRATEGY_IDS["external"]
     # two launches: the front-end kernel, then the fused core kernel on its candidate (strategy 4)

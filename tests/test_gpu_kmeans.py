@@ -115,3 +115,20 @@ def test_kmeans_and_auto_against_the_reference_made_fixture(dev):
             assert (contours[0] is not None) == (bk in G.files), k
             if contours[0] is not None:
                 assert tuple(int(v) for v in info[0, 1:5]) == tuple(int(v) for v in G[bk]), k
+
+
+def test_engine_with_the_kmeans_front(dev):
+    """TransformEngine(front="kmeans"): the batched core profile on the k-means candidate -- mask, bbox and histograms against
+    the oracle's make_mask(mask_strategy="kmeans") + hist9."""
+    from leaffliction_b200 import engine
+    imgs = synth.leaf_batch(10, 256, 256, 2024)
+    eng = engine.TransformEngine(256, 256, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev, front="kmeans", bg_bias="light_bg")
+    out = eng.run_device(torch.from_numpy(imgs).to(dev))
+    torch.cuda.synchronize()
+    scfg = sm.Cfg(mask_strategy="kmeans", bg_bias="light_bg")
+    for i in range(len(imgs)):
+        om, oinfo = sm.make_mask(imgs[i], scfg)
+        assert np.array_equal(out.mask[i].cpu().numpy(), om), i
+        if oinfo is not None:
+            assert tuple(out.info[i, 1:5].cpu().numpy()) == tuple(oinfo["bbox"]), i
+        assert np.array_equal(out.hist9[i].cpu().numpy(), sm.hist9(imgs[i], om)), i
