@@ -203,8 +203,69 @@ def p0_default_strategy(x, dev, rank, world, peak, max_over_ranks, barrier, n=20
             "achieved_gbs": by * len(xs) / (ms / 1e3) / 1e9, "frac": by * len(xs) / (ms / 1e3) / 1e9 / peak}
 
 
+def f2_jpeg(x, dev, n=1024):
+    """SURVEY 8f rank 2, the file boundary: JPEG bitstreams in host memory -> nvJPEG decode into the device batch -> core
+    transform profile -> nvJPEG encode of the blur and ROI outputs -> bitstreams in host memory (what folder mode does per
+    image with Pillow / cv2.imwrite).  Next to it, the codec work alone through Pillow on every host core."""
+    import io
+    import os
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    from PIL import Image
+
+    from leaffliction_b200 import engine as eng
+    from leaffliction_b200 import jpegio
+    S = int(x.shape[1])
+    imgs = x[:n].cpu().numpy()
+    cores = len(os.sched_getaffinity(0))
+
+    def enc(a):
+        b = io.BytesIO()
+        Image.fromarray(a).save(b, format="JPEG", quality=95)
+        return b.getvalue()
+
+    def dec(b):
+        return np.asarray(Image.open(io.BytesIO(b)).convert("RGB"))
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        blobs = list(ex.map(enc, imgs))
+        t0 = time.perf_counter()
+        arrs = list(ex.map(dec, blobs))
+        list(ex.map(enc, arrs))
+        list(ex.map(enc, arrs))              # two outputs per image, as below
+        t_host = time.perf_counter() - t0
+    e = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev)
+    out = ops.alloc_core_outputs(n, S, S, (256, 256), dev)
+    xin = torch.empty((n, S, S, 3), dtype=torch.uint8, device=dev)
+
+    def step():
+        jpegio.decode_batch(blobs, S, S, out=xin)
+        e.run_device(xin, out)
+        a = jpegio.encode_batch(out.blur)
+        b = jpegio.encode_batch(out.roi)
+        return len(a) + len(b)
+    step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        step()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"workload": f"{n} JPEG files ({S}x{S}, q95) in host memory -> nvJPEG decode -> core transform profile -> nvJPEG encode of "
+                        "blur + ROI -> bitstreams in host memory", "n_gpus": 1, "value": n / dt, "unit": "images/s", "ms": round(dt * 1e3, 2),
+            "bytes_over_pcie_per_image": int(np.mean([len(b) for b in blobs])) * 3, "raw_bytes_per_image": 3 * S * S * 3,
+            "host_codec_only": {"value": n / t_host, "unit": "images/s", "cores": cores,
+                                "what": "Pillow decode + two Pillow encodes per image on all host cores, no transform"}}
+
+
 def run_all(x, dev, rank, world, peak, max_over_ranks, barrier):
     res = {}
+    if world == 1:
+        try:
+            res["f2_jpeg"] = f2_jpeg(x, dev)
+        except Exception as e:   # noqa: BLE001
+            res["f2_jpeg"] = {"error": f"{type(e).__name__}: {e}"}
     for name, fn in (("p0_default_strategy", lambda: p0_default_strategy(x, dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c3_balance", lambda: c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c4_1024", lambda: c4_1024(dev, rank, world, peak, max_over_ranks, barrier)),
