@@ -73,7 +73,10 @@ __device__ __forceinline__ void rgb2hsv(int r, int g, int b, const HsvLut* lut, 
     const int mn = min(r, min(g, b));
     const int d = v - mn;
     s = (d * lut->sdiv[v] + 2048) >> 12;
-    int hh = (v == r) ? (g - b) : (v == g) ? (b - r + 2 * d) : (r - g + 4 * d);
+    // the hue numerator by selects: the lanes of a warp take different cases, a branch would run all of them in turn
+    const int hr = g - b, hg = b - r + 2 * d, hb = r - g + 4 * d;
+    int hh = (v == g) ? hg : hb;
+    hh = (v == r) ? hr : hh;
     hh = (hh * lut->hdiv[d] + 2048) >> 12;  // arithmetic shift == floor, as in OpenCV
     h = hh < 0 ? hh + 180 : hh;
 }
