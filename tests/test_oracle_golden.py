@@ -168,6 +168,27 @@ def test_known_answer_constants():
         assert (nw, nh) == (size, size), angle
 
 
+def test_exhaustive_colour_tables_and_cutoff_kats():
+    """SURVEY 8c KATs: SHA-256 of the GRAY / HSV / LAB conversion of ALL 2^24 colours (digests taken from cv2.cvtColor of
+    opencv-python-headless 4.13.0 in the build container; the oracle must reproduce them, and the GPU suite compares the CUDA
+    kernels with the oracle on the same exhaustive lattice), and the autocontrast cut-offs of seeds 42 / 7 / 999983."""
+    import hashlib
+    import random
+    r, g, b = np.meshgrid(*[np.arange(256, dtype=np.uint8)] * 3, indexing="ij")
+    lat = np.stack([r, g, b], -1).reshape(4096, 4096, 3)
+    want = {"gray": "6d4f6d7f4301c52d2672db66451b4a06a5502bef956dd81b577660f956f410ae",
+            "hsv": "a5b38b214f65aed9d382cc07bf40311aff2e3e324c98da86df77bef285f224eb",
+            "lab": "b3067516fa862bb008af4ffb4da5555722524a70776bf7ffd523a90f4331480c"}
+    for name, fn in (("gray", sc.rgb_to_gray), ("hsv", sc.rgb_to_hsv), ("lab", sc.rgb_to_lab)):
+        assert hashlib.sha256(np.ascontiguousarray(fn(lat)).tobytes()).hexdigest() == want[name], name
+    for seed, cutoff in ((42, 1.2788535969157675), (7, 0.6476655296663247), (999983, 1.9837290261359528)):
+        random.seed(seed)
+        assert random.uniform(0, 2) == cutoff                      # image_augmenter.py:126 on a freshly seeded augmenter
+        from leaffliction_b200 import augment
+        ip, dp = augment.draw_params_batch(np.array([augment.TRANSFORM_CODE["distortion"]], np.int32), [seed], 256, 256)
+        assert dp[0, 0] == cutoff and ip[0, 0] == int(256 * 256 * cutoff // 100)
+
+
 # ----------------------------------------------------------------------------- live cross-checks (same image on the GPU box)
 def test_oracle_vs_live_libraries():
     """The spec functions against Pillow / OpenCV in this interpreter (both boxes carry the same versions)."""
