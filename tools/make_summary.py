@@ -47,6 +47,7 @@ def main():
     ref = json.load(open(P("r02_bench_reference_arm.json")))
     b2 = json.load(open(P("r02_bench_2gpu.json")))
     b8 = json.load(open(P("r02_bench_8gpu.json")))
+    b4 = json.load(open(P("r02_bench_4gpu.json")))
     kern = "\n".join(f"| {k['kernel']} | {k['ms']} | {k['algo_bytes_per_launch']:,} | {k['achieved_gbs']} | {k['frac']} | {k['share_of_step']} |"
                      for k in b["roofline"]["kernels"])
     shares = "\n".join(f"| {k} | {n} | {ms:.3f} | {s * 100:.1f} % |" for k, n, ms, s in launch_shares())
@@ -106,6 +107,7 @@ Phase split of `k_core` (LFX_CORE_TIMING=1): profiles/r02_k_core_phase_split.txt
 |---|---|---|---|---|---|---|---|
 | 1 | {b['value']:,.0f} | {b['ms_per_step']:.3f} | 1 | {b['e2e']['value']:,.0f} | {b['e2e']['pcie']['h2d_gbs']} / {b['e2e']['pcie']['d2h_gbs']} | {b['e2e']['pcie']['frac_of_ceiling']:.2f} | {c['c3_balance']['value']:,.0f} |
 | 2 | {b2['value']:,.0f} | {b2['ms_per_step']:.3f} | {b['ms_per_step'] / b2['ms_per_step']:.3f} | {b2['e2e']['value']:,.0f} | {b2['e2e']['pcie']['h2d_gbs']} / {b2['e2e']['pcie']['d2h_gbs']} | {b2['e2e']['pcie']['frac_of_ceiling']:.2f} | {b2['configs']['c3_balance']['value']:,.0f} |
+| 4 | {b4['value']:,.0f} | {b4['ms_per_step']:.3f} | {b['ms_per_step'] / b4['ms_per_step']:.3f} | {b4['e2e']['value']:,.0f} | {b4['e2e']['pcie']['h2d_gbs']} / {b4['e2e']['pcie']['d2h_gbs']} | {b4['e2e']['pcie']['frac_of_ceiling']:.2f} | {b4['configs']['c3_balance']['value']:,.0f} |
 | 8 | {b8['value']:,.0f} | {b8['ms_per_step']:.3f} | {b['ms_per_step'] / b8['ms_per_step']:.3f} | {b8['e2e']['value']:,.0f} | {b8['e2e']['pcie']['h2d_gbs']} / {b8['e2e']['pcie']['d2h_gbs']} | {b8['e2e']['pcie']['frac_of_ceiling']:.2f} | {b8['configs']['c3_balance']['value']:,.0f} |
 
 With 8 ranks copying at once the pinned-copy probe drops to ~17-20 GB/s per rank (one host memory system, 4 cores per rank): the host, not the GPUs, bounds the
