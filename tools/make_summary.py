@@ -101,7 +101,7 @@ Phase split of `k_core` (LFX_CORE_TIMING=1): profiles/r02_k_core_phase_split.txt
 | f2_jpeg | {c.get('f2_jpeg', {}).get('value', 0):,.0f} images/s | JPEG bitstreams in host memory -> nvJPEG decode -> core transform -> nvJPEG encode of blur + ROI -> bitstreams; codec alone through Pillow on all host cores: {c.get('f2_jpeg', {}).get('host_codec_only', {}).get('value', 0):,.0f} images/s |
 | c5_resize224 | {c['c5_resize224']['value']:,.0f} images/s | flip -> Lanczos 224 -> /255 f32 -> DLPack, best batch; batches: {json.dumps({k: v['images_per_s'] for k, v in c['c5_resize224']['batches'].items()})} |
 
-## Scaling (torchrun, 20 steps)
+## Scaling (torchrun, 20 steps; the 8-GPU record predates the pipelined steps -- its 11.24 ms/step is 0.988 of that build's 11.11 ms at N = 1)
 
 | GPUs | images/s | ms/step | weak-scaling efficiency | e2e images/s | pinned copy GB/s per rank (in / out) | e2e / ceiling | c3 augmented images/s |
 |---|---|---|---|---|---|---|---|
