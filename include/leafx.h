@@ -218,6 +218,25 @@ int lfx_analyze_record(const int32_t* points, const int32_t* counts, const int64
                        double* rec_f64, int32_t* hull_points, int B, int H, int W, int max_pts, int max_hull,
                        void* workspace, size_t workspace_bytes, lfx_stream_t stream);
 
+/* Overlay drawing, bit-identical to OpenCV 4.13's rasterisers (drawing.cpp: Line2 / FillConvexPoly /
+ * ThickLine / Circle / LineAA / PolyLine in 16.16 fixed point), one thread block per image, later primitives over earlier
+ * ones in the reference's order.
+ * lfx_analyze_overlay = the image apply_analyze_filter returns (analyze.py:37-122): overlay [B,H,W,3] = rgb with the contour
+ *   (drawContours, red, 2 px), the centroid cross (drawMarker 14 / 2 px), for the left / right / top / bottom points a filled
+ *   circle r = 3 and an anti-aliased ray from the centroid, the anti-aliased convex hull (vertex order of cv2.convexHull),
+ *   the two PCA axes (2 px) and, when `edges` (lfx_canny 80 / 160 L2 of the grey image) and `mask` are given, the vein
+ *   pixels edges & mask in cyan.  points / counts come from lfx_trace_contour, rec_i32 / hull_points from
+ *   lfx_analyze_record (same max_pts / max_hull; hull_count must be >= 0).  Images without a contour (rec_i32[0] == 0) are
+ *   copied unchanged (the reference's "Analyze: no object" text banner is not drawn).
+ * lfx_draw_rectangles = the `vis` image of apply_roi_filter (roi.py:43-44): cv2.rectangle(vis, (x, y), (x + w, y + h),
+ *   colour, thickness) for info[B][8] = {found, x, y, w, h, ...} (lfx_make_mask's layout); color_rgb = r | g << 8 | b << 16.
+ * Neither works in place. */
+int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, const int32_t* counts, const int32_t* rec_i32,
+                        const int32_t* hull_points, const uint8_t* edges, const uint8_t* mask, uint8_t* overlay,
+                        int B, int H, int W, int max_pts, int max_hull, lfx_stream_t stream);
+int lfx_draw_rectangles(const uint8_t* rgb, const int32_t* info, uint8_t* vis, int B, int H, int W, uint32_t color_rgb,
+                        int thickness, lfx_stream_t stream);
+
 /* Raw candidate of one threshold strategy, no post-processing (_build_mask_candidates, mask.py:414-443; strategies 0-3:
  * hsv_h, lab, hsv_s / hsv_v_dark by Otsu): raw [B,H,W] (0/255).  Workspace as lfx_make_mask. */
 int lfx_strategy_raw(const uint8_t* src, uint8_t* raw, int B, int H, int W, const lfx_mask_cfg* cfg /* host */,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libleafx.so")
 OUT_JPEG = os.path.join(HERE, "libleafx_jpeg.so")     # nvJPEG file boundary (include/leafx_jpeg.h), a separate object
-SOURCES = ["lfx_api.cu", "lfx_color.cu", "lfx_augment.cu", "lfx_gauss.cu", "lfx_mask.cu", "lfx_roi.cu", "lfx_contour.cu", "lfx_front.cu", "lfx_core.cu", "lfx_gauss_tma.cu", "lfx_rng.cu", "lfx_params.cu", "lfx_resize.cu", "lfx_score.cu", "lfx_kmeans.cu"]
+SOURCES = ["lfx_api.cu", "lfx_color.cu", "lfx_augment.cu", "lfx_gauss.cu", "lfx_mask.cu", "lfx_roi.cu", "lfx_contour.cu", "lfx_front.cu", "lfx_core.cu", "lfx_gauss_tma.cu", "lfx_rng.cu", "lfx_params.cu", "lfx_resize.cu", "lfx_score.cu", "lfx_kmeans.cu", "lfx_draw.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off", "--use_fast_math=false"]
 

@@ -1,0 +1,478 @@
+// Overlay rasterisers: the OpenCV drawing calls of apply_analyze_filter (analyze.py:37-122) and
+// apply_roi_filter (roi.py:43-44) on a resident batch, one thread block per image, bit-identical to cv2 4.13
+// (drawing.cpp: Line2 / FillConvexPoly / ThickLine / Circle / LineAA / PolyLine in 16.16 fixed point).
+//
+// Order is part of the result (later primitives overwrite or blend with earlier ones), so every image is drawn in the
+// reference's order.  Inside one step the work is spread over the block where the writes cannot collide:
+//   * the contour's 2-px segments and the rectangle's edges are one colour -> one thread per segment, any order;
+//   * one anti-aliased line touches three distinct pixels per step along its major axis -> one thread per step;
+//   * markers, circles, PCA axes: a handful of pixels, drawn by thread 0.
+// HBM traffic is the copy rgb -> overlay (6N bytes per image) plus the edge / mask planes (2N); everything drawn
+// afterwards hits lines the block has just written (L1 / L2).
+#include <math.h>
+
+#include "lfx_common.cuh"
+
+namespace {
+
+typedef long long i64;
+constexpr int XY_SHIFT = 16;
+constexpr i64 XY_ONE = 1 << XY_SHIFT;
+
+struct Img {
+    uint8_t* p;
+    int H, W;
+};
+struct Pt {
+    i64 x, y;
+};
+
+__constant__ uint8_t c_filter[64] = {
+    168, 177, 185, 194, 202, 210, 218, 224, 231, 236, 241, 246, 249, 252, 254, 254,
+    254, 254, 252, 249, 246, 241, 236, 231, 224, 218, 210, 202, 194, 185, 177, 168,
+    158, 149, 140, 131, 122, 114, 105, 97,  89,  82,  75,  68,  62,  56,  50,  45,
+    40,  36,  32,  28,  25,  22,  19,  16,  14,  12,  11,  9,   8,   7,   5,   5};
+__constant__ uint8_t c_slope[32] = {181, 181, 181, 182, 182, 183, 184, 185, 187, 188, 190, 192, 194, 196, 198, 201,
+                                    203, 206, 209, 211, 214, 218, 221, 224, 227, 231, 235, 238, 242, 246, 250, 254};
+
+__device__ __forceinline__ void put(const Img& im, int x, int y, uint32_t col) {
+    uint8_t* t = im.p + ((size_t)y * im.W + x) * 3;
+    t[0] = (uint8_t)(col & 255);
+    t[1] = (uint8_t)((col >> 8) & 255);
+    t[2] = (uint8_t)((col >> 16) & 255);
+}
+__device__ __forceinline__ void put_chk(const Img& im, int x, int y, uint32_t col) {
+    if ((unsigned)x < (unsigned)im.W && (unsigned)y < (unsigned)im.H) put(im, x, y, col);
+}
+__device__ __forceinline__ void hline(const Img& im, int y, int xa, int xb, uint32_t col) {
+    for (int x = xa; x <= xb; ++x) put(im, x, y, col);
+}
+
+// cv::clipLine(Size2l, Point2l&, Point2l&): the cut points are computed in double and truncated.
+__device__ bool clip_line(i64 width, i64 height, Pt& a, Pt& b) {
+    const i64 right = width - 1, bottom = height - 1;
+    if (width <= 0 || height <= 0) return false;
+    i64 &x1 = a.x, &y1 = a.y, &x2 = b.x, &y2 = b.y;
+    int c1 = (x1 < 0) + (x1 > right) * 2 + (y1 < 0) * 4 + (y1 > bottom) * 8;
+    int c2 = (x2 < 0) + (x2 > right) * 2 + (y2 < 0) * 4 + (y2 > bottom) * 8;
+    if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+        i64 t;
+        if (c1 & 12) {
+            t = c1 < 8 ? 0 : bottom;
+            x1 += (i64)__ddiv_rn(__dmul_rn((double)(t - y1), (double)(x2 - x1)), (double)(y2 - y1));
+            y1 = t;
+            c1 = (x1 < 0) + (x1 > right) * 2;
+        }
+        if (c2 & 12) {
+            t = c2 < 8 ? 0 : bottom;
+            x2 += (i64)__ddiv_rn(__dmul_rn((double)(t - y2), (double)(x2 - x1)), (double)(y2 - y1));
+            y2 = t;
+            c2 = (x2 < 0) + (x2 > right) * 2;
+        }
+        if ((c1 & c2) == 0 && (c1 | c2) != 0) {
+            if (c1) {
+                t = c1 == 1 ? 0 : right;
+                y1 += (i64)__ddiv_rn(__dmul_rn((double)(t - x1), (double)(y2 - y1)), (double)(x2 - x1));
+                x1 = t;
+                c1 = 0;
+            }
+            if (c2) {
+                t = c2 == 1 ? 0 : right;
+                y2 += (i64)__ddiv_rn(__dmul_rn((double)(t - x2), (double)(y2 - y1)), (double)(x2 - x1));
+                x2 = t;
+                c2 = 0;
+            }
+        }
+    }
+    return (c1 | c2) == 0;
+}
+
+// drawing.cpp Line2: 8-connected DDA between 16.16 end points (the outline FillConvexPoly draws for shift != 0).
+__device__ void line2(const Img& im, Pt p1, Pt p2, uint32_t col) {
+    if (!clip_line((i64)im.W << XY_SHIFT, (i64)im.H << XY_SHIFT, p1, p2)) return;
+    i64 dx = p2.x - p1.x, dy = p2.y - p1.y;
+    const i64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    i64 x_step, y_step;
+    int ecount;
+    if (ax > ay) {
+        if (dx < 0) {
+            dy = -dy;
+            Pt t = p1; p1 = p2; p2 = t;
+        }
+        x_step = XY_ONE;
+        y_step = (dy << XY_SHIFT) / (ax | 1);
+        ecount = (int)((p2.x - p1.x) >> XY_SHIFT);
+    } else {
+        if (dy < 0) {
+            dx = -dx;
+            Pt t = p1; p1 = p2; p2 = t;
+        }
+        x_step = (dx << XY_SHIFT) / (ay | 1);
+        y_step = XY_ONE;
+        ecount = (int)((p2.y - p1.y) >> XY_SHIFT);
+    }
+    p1.x += XY_ONE >> 1;
+    p1.y += XY_ONE >> 1;
+    put_chk(im, (int)((p2.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((p2.y + (XY_ONE >> 1)) >> XY_SHIFT), col);
+    if (ax > ay) {
+        i64 x = p1.x >> XY_SHIFT;
+        for (; ecount >= 0; --ecount, ++x, p1.y += y_step) put_chk(im, (int)x, (int)(p1.y >> XY_SHIFT), col);
+    } else {
+        i64 y = p1.y >> XY_SHIFT;
+        for (; ecount >= 0; --ecount, ++y, p1.x += x_step) put_chk(im, (int)(p1.x >> XY_SHIFT), (int)y, col);
+    }
+}
+
+// drawing.cpp FillConvexPoly(LINE_8, shift = XY_SHIFT) for the 4-vertex polygon of a thick segment.
+__device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col) {
+    constexpr int npts = 4;
+    const i64 delta = XY_ONE >> 1;
+    i64 xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
+    int imin = 0;
+    Pt p0 = v[npts - 1];
+    for (int i = 0; i < npts; ++i) {
+        const Pt p = v[i];
+        if (p.y < ymin) {
+            ymin = p.y;
+            imin = i;
+        }
+        ymax = p.y > ymax ? p.y : ymax;
+        xmax = p.x > xmax ? p.x : xmax;
+        xmin = p.x < xmin ? p.x : xmin;
+        line2(im, p0, p, col);
+        p0 = p;
+    }
+    xmin = (xmin + delta) >> XY_SHIFT;
+    xmax = (xmax + delta) >> XY_SHIFT;
+    ymin = (ymin + delta) >> XY_SHIFT;
+    ymax = (ymax + delta) >> XY_SHIFT;
+    if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= im.W || (int)ymin >= im.H) return;
+    if (ymax > im.H - 1) ymax = im.H - 1;
+    int e_idx[2] = {imin, imin}, e_ye[2] = {(int)ymin, (int)ymin};
+    const int e_di[2] = {1, npts - 1};
+    i64 e_x[2] = {-XY_ONE, -XY_ONE}, e_dx[2] = {0, 0};
+    int edges = npts;
+    int y = (int)ymin;
+    do {
+        for (int i = 0; i < 2; ++i) {
+            if (y >= e_ye[i]) {
+                int idx0 = e_idx[i];
+                const int di = e_di[i];
+                int idx = idx0 + di;
+                if (idx >= npts) idx -= npts;
+                for (; edges-- > 0;) {
+                    const int ty = (int)((v[idx].y + delta) >> XY_SHIFT);
+                    if (ty > y) {
+                        const i64 xs = v[idx0].x, xe = v[idx].x;
+                        e_ye[i] = ty;
+                        e_dx[i] = ((xe - xs) * 2 + (ty - y)) / (2 * (i64)(ty - y));
+                        e_x[i] = xs;
+                        e_idx[i] = idx;
+                        break;
+                    }
+                    idx0 = idx;
+                    idx += di;
+                    if (idx >= npts) idx -= npts;
+                }
+            }
+        }
+        if (edges < 0) break;
+        if (y >= 0) {
+            const int left = e_x[0] > e_x[1] ? 1 : 0, right = 1 - left;
+            int xx1 = (int)((e_x[left] + delta) >> XY_SHIFT);
+            int xx2 = (int)((e_x[right] + delta) >> XY_SHIFT);
+            if (xx2 >= 0 && xx1 < im.W) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= im.W) xx2 = im.W - 1;
+                hline(im, y, xx1, xx2, col);
+            }
+        }
+        e_x[0] += e_dx[0];
+        e_x[1] += e_dx[1];
+    } while (++y <= (int)ymax);
+}
+
+// drawing.cpp Circle(fill = 1): midpoint circle, four clipped spans per step.
+__device__ void circle_filled(const Img& im, int cx, int cy, int radius, uint32_t col) {
+    int err = 0, dx = radius, dy = 0, plus = 1, minus = (radius << 1) - 1;
+    auto span = [&](int y, int xa, int xb) {
+        if ((unsigned)y < (unsigned)im.H) hline(im, y, max(xa, 0), min(xb, im.W - 1), col);
+    };
+    while (dx >= dy) {
+        span(cy - dy, cx - dx, cx + dx);
+        span(cy + dy, cx - dx, cx + dx);
+        span(cy - dx, cx - dy, cx + dy);
+        span(cy + dx, cx - dy, cx + dy);
+        ++dy;
+        err += plus;
+        plus += 2;
+        const int m = (err <= 0) - 1;
+        err -= minus & m;
+        dx += m;
+        minus -= m & 2;
+    }
+}
+
+// drawing.cpp ThickLine (LINE_8, shift 0, thickness >= 2) as cv::line / PolyLine reach it: the segment is first clipped to
+// the image grown by `thickness`, then drawn as the polygon around it plus round caps (flags bit 0: at p0, bit 1: at p1).
+__device__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32_t col, int thickness, int flags) {
+    Pt a = {(i64)x0 + thickness, (i64)y0 + thickness}, b = {(i64)x1 + thickness, (i64)y1 + thickness};
+    if (!clip_line((i64)im.W + 2 * thickness, (i64)im.H + 2 * thickness, a, b)) return;
+    Pt q0 = {(a.x - thickness) << XY_SHIFT, (a.y - thickness) << XY_SHIFT};
+    Pt q1 = {(b.x - thickness) << XY_SHIFT, (b.y - thickness) << XY_SHIFT};
+    const double inv = 1.0 / 65536.0;
+    const double dx = (double)(q0.x - q1.x) * inv, dy = (double)(q1.y - q0.y) * inv;
+    double r = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    const int odd = thickness & 1;
+    const i64 th = (i64)thickness << (XY_SHIFT - 1);
+    if (fabs(r) > 2.220446049250313e-16) {
+        r = __ddiv_rn((double)th + odd * 32768.0, __dsqrt_rn(r));
+        const i64 dpx = __double2ll_rn(__dmul_rn(dy, r)), dpy = __double2ll_rn(__dmul_rn(dx, r));
+        const Pt pt[4] = {{q0.x + dpx, q0.y + dpy}, {q0.x - dpx, q0.y - dpy}, {q1.x - dpx, q1.y - dpy}, {q1.x + dpx, q1.y + dpy}};
+        fill_convex_poly4(im, pt, col);
+    }
+    const int rad = (int)((th + (XY_ONE >> 1)) >> XY_SHIFT);
+    if (flags & 1) circle_filled(im, (int)((q0.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((q0.y + (XY_ONE >> 1)) >> XY_SHIFT), rad, col);
+    if (flags & 2) circle_filled(im, (int)((q1.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((q1.y + (XY_ONE >> 1)) >> XY_SHIFT), rad, col);
+}
+
+__device__ __forceinline__ void blend_aa(const Img& im, int x, int y, int a, int cr, int cg, int cb) {
+    uint8_t* t = im.p + ((size_t)y * im.W + x) * 3;
+    int v = t[0];
+    v += ((cr - v) * a + 127) >> 8;
+    v += ((cr - v) * a + 127) >> 8;
+    t[0] = (uint8_t)v;
+    v = t[1];
+    v += ((cg - v) * a + 127) >> 8;
+    v += ((cg - v) * a + 127) >> 8;
+    t[1] = (uint8_t)v;
+    v = t[2];
+    v += ((cb - v) * a + 127) >> 8;
+    v += ((cb - v) * a + 127) >> 8;
+    t[2] = (uint8_t)v;
+}
+
+// drawing.cpp LineAA between integer pixel end points, called by EVERY thread of the block (the set-up is recomputed per
+// thread, the steps along the major axis are dealt out).  The caller synchronises the block afterwards.
+__device__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1, uint32_t col) {
+    Pt p1 = {(i64)px0 << XY_SHIFT, (i64)py0 << XY_SHIFT}, p2 = {(i64)px1 << XY_SHIFT, (i64)py1 << XY_SHIFT};
+    if (!clip_line((i64)im.W << XY_SHIFT, (i64)im.H << XY_SHIFT, p1, p2)) return;
+    i64 dx = p2.x - p1.x, dy = p2.y - p1.y;
+    const i64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
+    const bool xmajor = ax > ay;
+    i64 step, i, j, minor0;
+    int ecount, major0, slope;
+    if (xmajor) {
+        if (dx < 0) {
+            dy = -dy;
+            Pt t = p1; p1 = p2; p2 = t;
+        }
+        step = (dy << XY_SHIFT) / (ax | 1);
+        p2.x += XY_ONE;
+        ecount = (int)((p2.x >> XY_SHIFT) - (p1.x >> XY_SHIFT));
+        j = -(p1.x & (XY_ONE - 1));
+        p1.y += ((step * j) >> XY_SHIFT) + (XY_ONE >> 1);
+        i = (p1.x >> (XY_SHIFT - 7)) & 0x78;
+        j = (p2.x >> (XY_SHIFT - 7)) & 0x78;
+        major0 = (int)(p1.x >> XY_SHIFT);
+        minor0 = p1.y;
+    } else {
+        if (dy < 0) {
+            dx = -dx;
+            Pt t = p1; p1 = p2; p2 = t;
+        }
+        step = (dx << XY_SHIFT) / (ay | 1);
+        p2.y += XY_ONE;
+        ecount = (int)((p2.y >> XY_SHIFT) - (p1.y >> XY_SHIFT));
+        j = -(p1.y & (XY_ONE - 1));
+        p1.x += ((step * j) >> XY_SHIFT) + (XY_ONE >> 1);
+        i = (p1.y >> (XY_SHIFT - 7)) & 0x78;
+        j = (p2.y >> (XY_SHIFT - 7)) & 0x78;
+        major0 = (int)(p1.y >> XY_SHIFT);
+        minor0 = p1.x;
+    }
+    slope = (int)((step >> (XY_SHIFT - 5)) & 0x3f);
+    slope ^= step < 0 ? 0x3f : 0;
+    slope = (slope & 0x20) ? 0x100 : c_slope[slope];
+    int ep[9];
+    {
+        const int ii = (int)i, jj = (int)j;
+        const int t0 = slope << 7, t1 = ((0x78 - ii) | 4) * slope, t2 = (jj | 4) * slope;
+        ep[0] = 0;
+        ep[8] = slope;
+        ep[1] = ep[3] = (((((jj - ii) & 0x78) | 4) * slope) >> 8) & 0x1ff;
+        ep[2] = (t1 >> 8) & 0x1ff;
+        ep[4] = (((((jj - ii) + 0x80) | 4) * slope) >> 8) & 0x1ff;
+        ep[5] = ((t1 + t0) >> 8) & 0x1ff;
+        ep[6] = (t2 >> 8) & 0x1ff;
+        ep[7] = ((t2 + t0) >> 8) & 0x1ff;
+    }
+    const int cr = col & 255, cg = (col >> 8) & 255, cb = (col >> 16) & 255;
+    const int major_lim = xmajor ? im.W : im.H, minor_lim = xmajor ? im.H : im.W;
+    for (int s = threadIdx.x; s <= ecount; s += blockDim.x) {
+        const int mj = major0 + s;
+        if ((unsigned)mj >= (unsigned)major_lim) continue;
+        const i64 mcoord = minor0 + step * s;
+        const int scount = s, ec = ecount - s;
+        const int m0 = (int)(mcoord >> XY_SHIFT) - 1;
+        const int ep_corr = ep[(((scount >= 2) + 1) & (scount | 2)) * 3 + (((ec >= 2) + 1) & (ec | 2))];
+        const int dist = (int)((mcoord >> (XY_SHIFT - 5)) & 31);
+        const int f[3] = {c_filter[dist + 32], c_filter[dist], c_filter[63 - dist]};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int a = ((ep_corr * f[k]) >> 8) & 0xff;
+            const int mn = m0 + k;
+            if ((unsigned)mn < (unsigned)minor_lim) {
+                if (xmajor) blend_aa(im, mj, mn, a, cr, cg, cb);
+                else blend_aa(im, mn, mj, a, cr, cg, cb);
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void block_copy_image(uint8_t* dst, const uint8_t* src, size_t nbytes) {
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const size_t n16 = nbytes >> 4;
+        for (size_t k = threadIdx.x; k < n16; k += blockDim.x) reinterpret_cast<uint4*>(dst)[k] = ld_stream16(src + k * 16);
+        for (size_t k = (n16 << 4) + threadIdx.x; k < nbytes; k += blockDim.x) dst[k] = src[k];
+    } else {
+        for (size_t k = threadIdx.x; k < nbytes; k += blockDim.x) dst[k] = src[k];
+    }
+}
+
+__host__ __device__ constexpr uint32_t rgb_u32(int r, int g, int b) { return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16); }
+
+// apply_analyze_filter's overlay (analyze.py:37-122) for one image per block.
+__global__ void __launch_bounds__(256) k_analyze_overlay(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ points,
+                                                          const int32_t* __restrict__ counts, const int32_t* __restrict__ rec_i,
+                                                          const int32_t* __restrict__ hull, const uint8_t* __restrict__ edges,
+                                                          const uint8_t* __restrict__ mask, uint8_t* overlay, int H, int W,
+                                                          int max_pts, int max_hull) {
+    const int img = blockIdx.x;
+    const size_t npx = (size_t)H * W;
+    Img im = {overlay + (size_t)img * npx * 3, H, W};
+    block_copy_image(im.p, rgb + (size_t)img * npx * 3, npx * 3);
+    const int32_t* ri = rec_i + (size_t)img * 24;
+    const int n = counts[img];
+    if (ri[0] == 0 || n <= 0 || n > max_pts) return;   // no contour: the image is returned as it is (the text banner of analyze.py:29 is not drawn)
+    __syncthreads();
+    const int32_t* p = points + (size_t)img * max_pts * 2;
+    // :40  drawContours(thickness 2): PolyLine, segment k joins vertex k-1 -> k, round cap at k
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int kp = k == 0 ? n - 1 : k - 1;
+        thick_line(im, p[2 * kp], p[2 * kp + 1], p[2 * k], p[2 * k + 1], rgb_u32(255, 0, 0), 2, 2);
+    }
+    __syncthreads();
+    const int cx = ri[2], cy = ri[3];
+    constexpr uint32_t yellow = rgb_u32(255, 255, 0);
+    // :50-57 drawMarker(MARKER_CROSS, 14, 2); :65-75 the four extreme points: filled circle, then the anti-aliased ray
+    for (int e = 0; e < 4; ++e) {
+        const int ex = ri[4 + 2 * e], ey = ri[5 + 2 * e];
+        if (threadIdx.x == 0) {
+            if (e == 0) {
+                thick_line(im, cx - 7, cy, cx + 7, cy, yellow, 2, 3);
+                thick_line(im, cx, cy - 7, cx, cy + 7, yellow, 2, 3);
+            }
+            circle_filled(im, ex, ey, 3, yellow);
+        }
+        __syncthreads();
+        line_aa_block(im, cx, cy, ex, ey, yellow);
+        __syncthreads();
+    }
+    // :77-85 hull polyline, anti-aliased, in cv2.convexHull's vertex order: the device hull (counter-clockwise, starting
+    // at the top-most vertex) rotated to start at the hull vertex met LAST along the contour
+    const int nh = ri[12];
+    if (nh > 0 && nh <= max_hull) {
+        const int32_t* hp = hull + (size_t)img * max_hull * 2;
+        __shared__ int s_best;
+        if (threadIdx.x == 0) s_best = -1;
+        __syncthreads();
+        if (nh >= 3) {
+            for (int k = threadIdx.x; k < nh; k += blockDim.x) {
+                const int hx = hp[2 * k], hy = hp[2 * k + 1];
+                int last = -1;
+                for (int t = n - 1; t >= 0; --t)
+                    if (p[2 * t] == hx && p[2 * t + 1] == hy) {
+                        last = t;
+                        break;
+                    }
+                if (last >= 0) atomicMax(&s_best, last * 1024 + k);
+            }
+            __syncthreads();
+        }
+        const int start = (nh >= 3 && s_best >= 0) ? (s_best & 1023) : 0;
+        for (int k = 0; k < nh; ++k) {
+            int a = start + k - 1, b = start + k;
+            if (k == 0) a = start + nh - 1;
+            a %= nh;
+            b %= nh;
+            line_aa_block(im, hp[2 * a], hp[2 * a + 1], hp[2 * b], hp[2 * b + 1], rgb_u32(0, 255, 0));
+            __syncthreads();
+        }
+    }
+    // :88-112 PCA axes, 2 px
+    if (threadIdx.x == 0) {
+        thick_line(im, ri[14], ri[15], ri[16], ri[17], yellow, 2, 3);
+        thick_line(im, ri[18], ri[19], ri[20], ri[21], rgb_u32(255, 0, 255), 2, 3);
+    }
+    __syncthreads();
+    // :115-122 vein edges inside the mask, cyan
+    if (edges && mask) {
+        const uint8_t* e = edges + (size_t)img * npx;
+        const uint8_t* m = mask + (size_t)img * npx;
+        for (size_t k = threadIdx.x; k < npx; k += blockDim.x)
+            if (e[k] && m[k]) {
+                uint8_t* t = im.p + k * 3;
+                t[0] = 0;
+                t[1] = 255;
+                t[2] = 255;
+            }
+    }
+}
+
+// roi.py:44: vis = rgb.copy(); cv2.rectangle(vis, (x, y), (x + w, y + h), colour, thickness): PolyLine over the four corners.
+__global__ void __launch_bounds__(256) k_draw_rectangles(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ info,
+                                                          uint8_t* vis, int H, int W, uint32_t col, int thickness) {
+    const int img = blockIdx.x;
+    const size_t npx = (size_t)H * W;
+    Img im = {vis + (size_t)img * npx * 3, H, W};
+    block_copy_image(im.p, rgb + (size_t)img * npx * 3, npx * 3);
+    const int32_t* bi = info + (size_t)img * 8;
+    if (bi[0] == 0 || bi[3] <= 0 || bi[4] <= 0) return;
+    __syncthreads();
+    for (int k = threadIdx.x; k < 4; k += blockDim.x) {   // one colour: the four edges in any order
+        const int x0 = bi[1], y0 = bi[2], x1 = bi[1] + bi[3], y1 = bi[2] + bi[4];
+        const int vx[4] = {x0, x1, x1, x0}, vy[4] = {y0, y0, y1, y1};
+        const int kp = (k + 3) & 3;
+        thick_line(im, vx[kp], vy[kp], vx[k], vy[k], col, thickness, 2);
+    }
+}
+
+}  // namespace
+
+extern "C" int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, const int32_t* counts, const int32_t* rec_i32,
+                                   const int32_t* hull_points, const uint8_t* edges, const uint8_t* mask, uint8_t* overlay,
+                                   int B, int H, int W, int max_pts, int max_hull, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(rgb && points && counts && rec_i32 && hull_points && overlay && B > 0 && H > 0 && W > 0 && max_pts > 0 && max_hull > 0,
+                LFX_ERR_ARG, "analyze_overlay: bad arguments");
+    LFX_REQUIRE((edges == nullptr) == (mask == nullptr), LFX_ERR_ARG, "analyze_overlay: edges and mask go together");
+    LFX_REQUIRE(max_hull <= 1023 && H <= 16384 && W <= 16384, LFX_ERR_UNSUPPORTED, "analyze_overlay: max_hull <= 1023, image side <= 16384");
+    LFX_REQUIRE(rgb != overlay, LFX_ERR_ARG, "analyze_overlay: in-place operation is not supported");
+    k_analyze_overlay<<<B, 256, 0, (cudaStream_t)stream>>>(rgb, points, counts, rec_i32, hull_points, edges, mask, overlay, H, W, max_pts,
+                                                          max_hull);
+    return lfx_check_launch("analyze_overlay");
+}
+
+extern "C" int lfx_draw_rectangles(const uint8_t* rgb, const int32_t* info, uint8_t* vis, int B, int H, int W, uint32_t color_rgb,
+                                   int thickness, lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(rgb && info && vis && B > 0 && H > 0 && W > 0, LFX_ERR_ARG, "draw_rectangles: bad arguments");
+    LFX_REQUIRE(thickness >= 2 && thickness <= 64 && H <= 16384 && W <= 16384, LFX_ERR_UNSUPPORTED,
+                "draw_rectangles: thickness 2..64, image side <= 16384");
+    LFX_REQUIRE(rgb != vis, LFX_ERR_ARG, "draw_rectangles: in-place operation is not supported");
+    k_draw_rectangles<<<B, 256, 0, (cudaStream_t)stream>>>(rgb, info, vis, H, W, color_rgb, thickness);
+    return lfx_check_launch("draw_rectangles");
+}

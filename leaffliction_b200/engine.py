@@ -103,6 +103,19 @@ class TransformEngine:
         contour points, centroid, extreme points, convex hull, PCA axes -- device tensors, layout in include/leafx.h."""
         return ops.analyze_records(out.mask, out.info, max_pts, max_hull)
 
+    def overlays_device(self, x: torch.Tensor, out: ops.CoreOutputs, masked: Optional[torch.Tensor] = None,
+                        max_pts: int = 4096, max_hull: int = 512):
+        """The two overlay images of the reference's folder run for a whole batch, nothing leaves the device:
+        (analyze overlay, ROI rectangle image) = apply_analyze_filter's image (analyze.py:37-122) and apply_roi_filter's
+        `vis` (roi.py:43-44), both drawn over `masked`, the white-background masked image the reference's folder run hands
+        to its filters (default: apply_mask(x, mask, white)).  Launches on top of run_device: apply_mask, contour trace,
+        record, grey, Canny, overlay, rectangles."""
+        if masked is None:
+            masked = ops.apply_mask(x, out.mask, 255)
+        rec = ops.analyze_records(out.mask, out.info, max_pts, max_hull)
+        edges = ops.canny(ops.cvt_color(masked, "gray"), 80, 160, True)
+        return ops.analyze_overlay(masked, rec, edges, out.mask), ops.draw_rectangles(masked, out.info)
+
     # ---- host buffers in, host buffers out
     def _ensure(self):
         if self._bufs is None:

@@ -62,10 +62,8 @@ def record_from_device(rec_i: np.ndarray, rec_f: np.ndarray, hull: np.ndarray) -
                       ((int(rec_i[18]), int(rec_i[19])), (int(rec_i[20]), int(rec_i[21])))))
 
 
-def analyze_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray) -> Dict:
-    """Numeric content of apply_analyze_filter (analyze.py:43-122) for one image: centroid of the contour polygon
-    (cv2.moments), extreme points, convex hull, PCA axes (all by lfx_analyze_record on the device), vein-edge mask
-    (Canny 80/160 L2 inside the mask).  The batched form is ops.analyze_records / TransformEngine(analyze=True)."""
+def _device_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray):
+    """(device record of lfx_analyze_record for one contour, device rgb, device edges, device mask)."""
     import torch
     ops = _ops()
     pts = np.ascontiguousarray(contour[:, 0, :], np.int32)
@@ -75,30 +73,35 @@ def analyze_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray) -> Di
     max_hull = 512
     while True:
         rec = ops.analyze_points(d_pts, d_cnt, H, W, max_hull)
-        ri = rec["rec_i"].cpu().numpy()[0]
-        if ri[12] >= 0:
+        nh = int(rec["rec_i"][0, 12])
+        if nh >= 0:
             break
-        max_hull = int(-ri[12]) + 8
-    out = record_from_device(ri, rec["rec_f"].cpu().numpy()[0], rec["hull"].cpu().numpy()[0])
-    gray = ops.cvt_color(_dev(rgb[None]), "gray")
-    edges = ops.canny(gray, 80, 160, True).cpu().numpy()[0]
-    out["veins"] = (edges > 0) & (_mask2d(mask) > 0)
+        max_hull = -nh + 8
+    d_rgb = _dev(rgb[None])
+    edges = ops.canny(ops.cvt_color(d_rgb, "gray"), 80, 160, True)
+    return rec, d_rgb, edges, _dev(np.ascontiguousarray(_mask2d(mask))[None])
+
+
+def analyze_record(rgb: np.ndarray, mask: np.ndarray, contour: np.ndarray) -> Dict:
+    """Numeric content of apply_analyze_filter (analyze.py:43-122) for one image: centroid of the contour polygon
+    (cv2.moments), extreme points, convex hull, PCA axes (all by lfx_analyze_record on the device), vein-edge mask
+    (Canny 80/160 L2 inside the mask).  The batched form is ops.analyze_records / TransformEngine(analyze=True)."""
+    rec, _, edges, d_mask = _device_record(rgb, mask, contour)
+    out = record_from_device(rec["rec_i"].cpu().numpy()[0], rec["rec_f"].cpu().numpy()[0], rec["hull"].cpu().numpy()[0])
+    out["veins"] = ((edges > 0) & (d_mask > 0)).cpu().numpy()[0]
     return out
 
 
 def apply_analyze_filter(rgb: np.ndarray, mask: Optional[np.ndarray], contour: Optional[np.ndarray],
                          cfg: TransformConfig) -> np.ndarray:
-    """Overlay with the exact (non anti-aliased) elements: cyan vein edges, centroid and extreme-point
-    markers.  Lines/hull/PCA axes (LINE_AA drawing) are cosmetic and not rasterised here."""
+    """The overlay of analyze.py:37-122, drawn on the device by lfx_analyze_overlay with OpenCV's rasterisers restated
+    (contour, centroid cross, extreme points with anti-aliased rays, anti-aliased hull, PCA axes, cyan vein edges):
+    bit-identical to the reference's image whenever the PCA end points are (no tied projections).  Without a contour the
+    reference returns the image with an "Analyze: no object" text banner (putText); here the image is returned unchanged."""
     if contour is None or mask is None:
         return rgb.copy()
-    rec = analyze_record(rgb, mask, contour)
-    overlay = rgb.copy()
-    H, W = overlay.shape[:2]
-    for (x, y) in (rec["left"], rec["right"], rec["top"], rec["bottom"], rec["centroid"]):
-        overlay[max(0, int(y) - 2):min(H, int(y) + 3), max(0, int(x) - 2):min(W, int(x) + 3)] = (255, 255, 0)
-    overlay[rec["veins"]] = (0, 255, 255)
-    return overlay
+    rec, d_rgb, edges, d_mask = _device_record(rgb, mask, contour)
+    return _ops().analyze_overlay(d_rgb, rec, edges, d_mask).cpu().numpy()[0]
 
 
 def histogram_stats(rgb: np.ndarray) -> Dict:

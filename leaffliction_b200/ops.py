@@ -213,6 +213,49 @@ def analyze_points(points: torch.Tensor, counts: torch.Tensor, H: int, W: int, m
     return dict(points=points, counts=counts, rec_i=rec_i, rec_f=rec_f, hull=hull)
 
 
+def analyze_overlay(rgb: torch.Tensor, rec: dict, edges: torch.Tensor = None, mask: torch.Tensor = None) -> torch.Tensor:
+    """The overlay image apply_analyze_filter returns (analyze.py:37-122) for a batch: rgb [B,H,W,3] u8 + the record of
+    analyze_records / analyze_points (points, counts, rec_i, hull) -> overlay [B,H,W,3], bit-identical to the OpenCV drawing
+    calls (contour, centroid cross, extreme-point circles and anti-aliased rays, anti-aliased hull, PCA axes); with `edges`
+    (canny(gray, 80, 160, True)) and `mask` the vein pixels edges & mask are painted cyan.  Images without a contour are
+    copied.  Raises when a hull did not fit max_hull (rec_i[:, 12] < 0): re-run the record with a larger max_hull."""
+    _chk_img(rgb)
+    lib = _ready(rgb)
+    B, H, W, _ = rgb.shape
+    pts, cnt, rec_i, hull = rec["points"], rec["counts"], rec["rec_i"], rec["hull"]
+    for t, dt in ((pts, torch.int32), (cnt, torch.int32), (rec_i, torch.int32), (hull, torch.int32)):
+        if not t.is_cuda or t.dtype != dt or not t.is_contiguous() or int(t.shape[0]) != B:
+            raise ValueError("analyze_overlay: record tensors must be contiguous int32 CUDA tensors of the batch")
+    if (edges is None) != (mask is None):
+        raise ValueError("analyze_overlay: edges and mask go together")
+    if edges is not None:
+        _chk_img(edges, None)
+        _chk_img(mask, None)
+        if tuple(edges.shape) != (B, H, W) or tuple(mask.shape) != (B, H, W):
+            raise ValueError("analyze_overlay: edges / mask must be [B,H,W]")
+    if bool((rec_i[:, 12] < 0).any()):
+        raise ValueError("analyze_overlay: a hull did not fit max_hull; run the record again with a larger max_hull")
+    out = torch.empty_like(rgb)
+    _lib.check(lib.lfx_analyze_overlay(_p(rgb), _p(pts), _p(cnt), _p(rec_i), _p(hull), _p(edges) if edges is not None else None,
+                                       _p(mask) if mask is not None else None, _p(out), B, H, W, int(pts.shape[1]), int(hull.shape[1]),
+                                       _stream()))
+    return out
+
+
+def draw_rectangles(rgb: torch.Tensor, info: torch.Tensor, color=(255, 0, 0), thickness: int = 2) -> torch.Tensor:
+    """`vis` of apply_roi_filter (roi.py:43-44) for a batch: cv2.rectangle(vis, (x, y), (x + w, y + h), color, thickness) with
+    info [B,8] i32 = {found, x, y, w, h, ...} (make_mask's layout); bit-identical to OpenCV."""
+    _chk_img(rgb)
+    lib = _ready(rgb)
+    B, H, W, _ = rgb.shape
+    if not info.is_cuda or info.dtype != torch.int32 or not info.is_contiguous() or tuple(info.shape) != (B, 8):
+        raise ValueError("draw_rectangles: info must be a contiguous int32 CUDA tensor [B,8]")
+    out = torch.empty_like(rgb)
+    col = int(color[0]) | (int(color[1]) << 8) | (int(color[2]) << 16)
+    _lib.check(lib.lfx_draw_rectangles(_p(rgb), _p(info), _p(out), B, H, W, col, int(thickness), _stream()))
+    return out
+
+
 def strategy_raw(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
     """Raw candidate of a threshold strategy (cfg.strategy 0-3), no post-processing: [B,H,W] u8 (mask.py:72-106)."""
     _chk_img(x)

@@ -464,21 +464,10 @@ def bounding_rect(contour: np.ndarray) -> Tuple[int, int, int, int]:
 
 
 def draw_rectangle(img: np.ndarray, x, y, w, h, color=(255, 0, 0)) -> np.ndarray:
-    """cv2.rectangle(vis,(x,y),(x+w,y+h),color,2) for axis-aligned boxes: a 2-px outline covering
-    rows/cols {c, c+1}... overlay drawing is cosmetic (SURVEY.md 8f #3); clipped to the image."""
-    out = img.copy()
-    H, W = out.shape[:2]
-    x1, y1 = x + w, y + h
-
-    def fill(ya, yb, xa, xb):
-        ya, yb, xa, xb = max(ya, 0), min(yb, H), max(xa, 0), min(xb, W)
-        if ya < yb and xa < xb:
-            out[ya:yb, xa:xb] = color
-    fill(y - 1, y + 1, x - 1, x1 + 1)
-    fill(y1 - 1, y1 + 1, x - 1, x1 + 1)
-    fill(y - 1, y1 + 1, x - 1, x + 1)
-    fill(y - 1, y1 + 1, x1 - 1, x1 + 1)
-    return out
+    """cv2.rectangle(vis, (x, y), (x + w, y + h), color, 2) on a copy (roi.py:43-44), drawn by lfx_draw_rectangles
+    (OpenCV's 2-px PolyLine restated, bit-identical, clipped at the image border like OpenCV)."""
+    info = np.array([[1, x, y, w, h, 0, 0, 0]], np.int32)
+    return _ops().draw_rectangles(_dev(np.ascontiguousarray(img)[None]), _dev(info), color, 2).cpu().numpy()[0]
 
 
 def apply_roi_filter(rgb: np.ndarray, contour: Optional[np.ndarray], cfg: TransformConfig):

@@ -147,3 +147,24 @@ def test_overlays_against_the_reference_functions():
         mine = img.copy()
         sd.rectangle2(mine, *box)
         assert np.array_equal(mine, vis)
+
+
+def _golden_cases():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_draw_v1.npz"))
+    keys = sorted({k.rsplit("_rgb", 1)[0] for k in g.files if k.endswith("_rgb")})
+    return g, keys
+
+
+def test_oracle_against_golden_overlays():
+    """tests/golden/golden_draw_v1.npz holds the outputs of the reference's own apply_analyze_filter / apply_roi_filter
+    (make_golden_draw.py); the oracle reproduces them from the stored inputs, without OpenCV."""
+    g, keys = _golden_cases()
+    assert len(keys) >= 5
+    for k in keys:
+        rgb, mask, c = g[k + "_rgb"], g[k + "_mask"], g[k + "_contour"]
+        veins = (g[k + "_edges"] > 0) & (mask > 0)
+        assert np.array_equal(sd.analyze_overlay(rgb, c, sd.overlay_record(c), veins), g[k + "_analyze"]), k
+        vis = rgb.copy()
+        sd.rectangle2(vis, *[int(v) for v in g[k + "_roi_box"]])
+        assert np.array_equal(vis, g[k + "_roi_vis"]), k

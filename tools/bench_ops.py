@@ -86,8 +86,13 @@ def main():
     dsd = torch.arange(1, 6 * B + 1, dtype=torch.int32, device=dev)
     t = timed(lambda: ops.seed_words(dsd, 16), args.reps)
     res[f"seed_words({6 * B} task seeds)"] = {"ms": round(t, 4), "seedings_per_s": round(6 * B / (t / 1e3))}
-    if N <= 65536:
-        pass
+    # ---- overlay images: contour trace + record, then the OpenCV rasterisers restated
+    rec = ops.analyze_records(mask, info, max_pts=8192, max_hull=1000)
+    if int(rec["counts"].min()) >= 0 and int(rec["rec_i"][:, 12].min()) >= 0:
+        add("analyze_records (trace + record)", lambda: ops.analyze_records(mask, info, max_pts=8192, max_hull=1000), N)
+        edges0 = torch.zeros_like(mask)
+        add("analyze_overlay", lambda: ops.analyze_overlay(x, rec, edges0, mask), 8 * N)
+        add("draw_rectangles", lambda: ops.draw_rectangles(x, info), 6 * N)
 
     # ---- augmentations (parameters drawn like the reference)
     dmode = torch.zeros(B, dtype=torch.int32, device=dev)
