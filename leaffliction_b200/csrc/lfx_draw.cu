@@ -7,8 +7,10 @@
 //   * the contour's 2-px segments and the rectangle's edges are one colour -> one thread per segment, any order;
 //   * one anti-aliased line touches three distinct pixels per step along its major axis -> one thread per step;
 //   * markers, circles, PCA axes: a handful of pixels, drawn by thread 0.
+//   * a 2-px line is one colour as well: its outline steps and fill rows are closed forms of OpenCV's incremental DDA /
+//     scan conversion, so the block shares them for the long lines (PCA axes, marker).
 // HBM traffic is the copy rgb -> overlay (6N bytes per image) plus the edge / mask planes (2N); everything drawn
-// afterwards hits lines the block has just written (L1 / L2).
+// afterwards hits lines the block has just written (L2).
 #include <math.h>
 
 #include "lfx_common.cuh"
@@ -88,43 +90,45 @@ __device__ bool clip_line(i64 width, i64 height, Pt& a, Pt& b) {
 }
 
 // drawing.cpp Line2: 8-connected DDA between 16.16 end points (the outline FillConvexPoly draws for shift != 0).
-__device__ void line2(const Img& im, Pt p1, Pt p2, uint32_t col) {
+// Steps t0, t0 + ts, ... are drawn by the caller (a lone thread passes 0, 1; a block passes threadIdx.x, blockDim.x: the
+// step-s pixel is the closed form of the DDA, y1 + s * y_step, so the steps are independent).
+__device__ void line2(const Img& im, Pt p1, Pt p2, uint32_t col, int t0, int ts) {
     if (!clip_line((i64)im.W << XY_SHIFT, (i64)im.H << XY_SHIFT, p1, p2)) return;
     i64 dx = p2.x - p1.x, dy = p2.y - p1.y;
     const i64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
-    i64 x_step, y_step;
+    i64 step;
     int ecount;
     if (ax > ay) {
         if (dx < 0) {
             dy = -dy;
             Pt t = p1; p1 = p2; p2 = t;
         }
-        x_step = XY_ONE;
-        y_step = (dy << XY_SHIFT) / (ax | 1);
+        step = (dy << XY_SHIFT) / (ax | 1);
         ecount = (int)((p2.x - p1.x) >> XY_SHIFT);
     } else {
         if (dy < 0) {
             dx = -dx;
             Pt t = p1; p1 = p2; p2 = t;
         }
-        x_step = (dx << XY_SHIFT) / (ay | 1);
-        y_step = XY_ONE;
+        step = (dx << XY_SHIFT) / (ay | 1);
         ecount = (int)((p2.y - p1.y) >> XY_SHIFT);
     }
     p1.x += XY_ONE >> 1;
     p1.y += XY_ONE >> 1;
-    put_chk(im, (int)((p2.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((p2.y + (XY_ONE >> 1)) >> XY_SHIFT), col);
+    if (t0 == 0) put_chk(im, (int)((p2.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((p2.y + (XY_ONE >> 1)) >> XY_SHIFT), col);
     if (ax > ay) {
-        i64 x = p1.x >> XY_SHIFT;
-        for (; ecount >= 0; --ecount, ++x, p1.y += y_step) put_chk(im, (int)x, (int)(p1.y >> XY_SHIFT), col);
+        const int x0 = (int)(p1.x >> XY_SHIFT);
+        for (int s = t0; s <= ecount; s += ts) put_chk(im, x0 + s, (int)((p1.y + step * s) >> XY_SHIFT), col);
     } else {
-        i64 y = p1.y >> XY_SHIFT;
-        for (; ecount >= 0; --ecount, ++y, p1.x += x_step) put_chk(im, (int)(p1.x >> XY_SHIFT), (int)y, col);
+        const int y0 = (int)(p1.y >> XY_SHIFT);
+        for (int s = t0; s <= ecount; s += ts) put_chk(im, (int)((p1.x + step * s) >> XY_SHIFT), y0 + s, col);
     }
 }
 
-// drawing.cpp FillConvexPoly(LINE_8, shift = XY_SHIFT) for the 4-vertex polygon of a thick segment.
-__device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col) {
+// drawing.cpp FillConvexPoly(LINE_8, shift = XY_SHIFT) for the 4-vertex polygon of a thick segment.  OpenCV walks the rows
+// top to bottom and adds each chain's slope once per row; between two vertex events the row-r edge position is
+// x + slope * (r - r0), so the rows of one stretch are independent: the caller's threads (t0, ts as in line2) share them.
+__device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col, int t0, int ts) {
     constexpr int npts = 4;
     const i64 delta = XY_ONE >> 1;
     i64 xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
@@ -139,7 +143,7 @@ __device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col) {
         ymax = p.y > ymax ? p.y : ymax;
         xmax = p.x > xmax ? p.x : xmax;
         xmin = p.x < xmin ? p.x : xmin;
-        line2(im, p0, p, col);
+        line2(im, p0, p, col, t0, ts);
         p0 = p;
     }
     xmin = (xmin + delta) >> XY_SHIFT;
@@ -153,7 +157,7 @@ __device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col) {
     i64 e_x[2] = {-XY_ONE, -XY_ONE}, e_dx[2] = {0, 0};
     int edges = npts;
     int y = (int)ymin;
-    do {
+    while (true) {
         for (int i = 0; i < 2; ++i) {
             if (y >= e_ye[i]) {
                 int idx0 = e_idx[i];
@@ -177,19 +181,25 @@ __device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col) {
             }
         }
         if (edges < 0) break;
-        if (y >= 0) {
-            const int left = e_x[0] > e_x[1] ? 1 : 0, right = 1 - left;
-            int xx1 = (int)((e_x[left] + delta) >> XY_SHIFT);
-            int xx2 = (int)((e_x[right] + delta) >> XY_SHIFT);
+        // rows y .. yn-1: no vertex event (both chains end at or after yn)
+        int yn = min(e_ye[0], e_ye[1]);
+        if (yn <= y) yn = y + 1;
+        if (yn > (int)ymax + 1) yn = (int)ymax + 1;
+        for (int r = max(y, 0) + t0; r < yn; r += ts) {
+            const i64 xa = e_x[0] + e_dx[0] * (r - y), xb = e_x[1] + e_dx[1] * (r - y);
+            int xx1 = (int)(((xa > xb ? xb : xa) + delta) >> XY_SHIFT);
+            int xx2 = (int)(((xa > xb ? xa : xb) + delta) >> XY_SHIFT);
             if (xx2 >= 0 && xx1 < im.W) {
                 if (xx1 < 0) xx1 = 0;
                 if (xx2 >= im.W) xx2 = im.W - 1;
-                hline(im, y, xx1, xx2, col);
+                hline(im, r, xx1, xx2, col);
             }
         }
-        e_x[0] += e_dx[0];
-        e_x[1] += e_dx[1];
-    } while (++y <= (int)ymax);
+        e_x[0] += e_dx[0] * (yn - y);
+        e_x[1] += e_dx[1] * (yn - y);
+        y = yn;
+        if (y > (int)ymax) break;
+    }
 }
 
 // drawing.cpp Circle(fill = 1): midpoint circle, four clipped spans per step.
@@ -215,7 +225,9 @@ __device__ void circle_filled(const Img& im, int cx, int cy, int radius, uint32_
 
 // drawing.cpp ThickLine (LINE_8, shift 0, thickness >= 2) as cv::line / PolyLine reach it: the segment is first clipped to
 // the image grown by `thickness`, then drawn as the polygon around it plus round caps (flags bit 0: at p0, bit 1: at p1).
-__device__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32_t col, int thickness, int flags) {
+// One colour, so the pixels can be written in any order: a lone thread draws everything (t0 = 0, ts = 1), a block shares the
+// polygon's outline steps and rows (t0 = threadIdx.x, ts = blockDim.x; the caps go to thread 0).
+__device__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32_t col, int thickness, int flags, int t0 = 0, int ts = 1) {
     Pt a = {(i64)x0 + thickness, (i64)y0 + thickness}, b = {(i64)x1 + thickness, (i64)y1 + thickness};
     if (!clip_line((i64)im.W + 2 * thickness, (i64)im.H + 2 * thickness, a, b)) return;
     Pt q0 = {(a.x - thickness) << XY_SHIFT, (a.y - thickness) << XY_SHIFT};
@@ -229,9 +241,10 @@ __device__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32
         r = __ddiv_rn((double)th + odd * 32768.0, __dsqrt_rn(r));
         const i64 dpx = __double2ll_rn(__dmul_rn(dy, r)), dpy = __double2ll_rn(__dmul_rn(dx, r));
         const Pt pt[4] = {{q0.x + dpx, q0.y + dpy}, {q0.x - dpx, q0.y - dpy}, {q1.x - dpx, q1.y - dpy}, {q1.x + dpx, q1.y + dpy}};
-        fill_convex_poly4(im, pt, col);
+        fill_convex_poly4(im, pt, col, t0, ts);
     }
     const int rad = (int)((th + (XY_ONE >> 1)) >> XY_SHIFT);
+    if (t0 != 0) return;
     if (flags & 1) circle_filled(im, (int)((q0.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((q0.y + (XY_ONE >> 1)) >> XY_SHIFT), rad, col);
     if (flags & 2) circle_filled(im, (int)((q1.x + (XY_ONE >> 1)) >> XY_SHIFT), (int)((q1.y + (XY_ONE >> 1)) >> XY_SHIFT), rad, col);
 }
@@ -333,7 +346,15 @@ __device__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1,
 __device__ __forceinline__ void block_copy_image(uint8_t* dst, const uint8_t* src, size_t nbytes) {
     if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
         const size_t n16 = nbytes >> 4;
-        for (size_t k = threadIdx.x; k < n16; k += blockDim.x) reinterpret_cast<uint4*>(dst)[k] = ld_stream16(src + k * 16);
+        size_t k = threadIdx.x;
+        for (; k + 3 * (size_t)blockDim.x < n16; k += 4 * (size_t)blockDim.x) {   // four loads in flight per thread
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = ld_stream16(src + (k + (size_t)j * blockDim.x) * 16);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(dst)[k + (size_t)j * blockDim.x] = v[j];
+        }
+        for (; k < n16; k += blockDim.x) reinterpret_cast<uint4*>(dst)[k] = ld_stream16(src + k * 16);
         for (size_t k = (n16 << 4) + threadIdx.x; k < nbytes; k += blockDim.x) dst[k] = src[k];
     } else {
         for (size_t k = threadIdx.x; k < nbytes; k += blockDim.x) dst[k] = src[k];
@@ -365,16 +386,14 @@ __global__ void __launch_bounds__(256) k_analyze_overlay(const uint8_t* __restri
     __syncthreads();
     const int cx = ri[2], cy = ri[3];
     constexpr uint32_t yellow = rgb_u32(255, 255, 0);
+    const int t0 = threadIdx.x, ts = blockDim.x;
     // :50-57 drawMarker(MARKER_CROSS, 14, 2); :65-75 the four extreme points: filled circle, then the anti-aliased ray
+    // (marker and circles are one colour; a ray blends with what is under it, so it waits for them)
+    thick_line(im, cx - 7, cy, cx + 7, cy, yellow, 2, 3, t0, ts);
+    thick_line(im, cx, cy - 7, cx, cy + 7, yellow, 2, 3, t0, ts);
     for (int e = 0; e < 4; ++e) {
         const int ex = ri[4 + 2 * e], ey = ri[5 + 2 * e];
-        if (threadIdx.x == 0) {
-            if (e == 0) {
-                thick_line(im, cx - 7, cy, cx + 7, cy, yellow, 2, 3);
-                thick_line(im, cx, cy - 7, cx, cy + 7, yellow, 2, 3);
-            }
-            circle_filled(im, ex, ey, 3, yellow);
-        }
+        if (threadIdx.x == 0) circle_filled(im, ex, ey, 3, yellow);
         __syncthreads();
         line_aa_block(im, cx, cy, ex, ey, yellow);
         __syncthreads();
@@ -410,23 +429,49 @@ __global__ void __launch_bounds__(256) k_analyze_overlay(const uint8_t* __restri
             __syncthreads();
         }
     }
-    // :88-112 PCA axes, 2 px
-    if (threadIdx.x == 0) {
-        thick_line(im, ri[14], ri[15], ri[16], ri[17], yellow, 2, 3);
-        thick_line(im, ri[18], ri[19], ri[20], ri[21], rgb_u32(255, 0, 255), 2, 3);
-    }
+    // :88-112 PCA axes, 2 px: each line shared by the block, the second over the first
+    thick_line(im, ri[14], ri[15], ri[16], ri[17], yellow, 2, 3, t0, ts);
     __syncthreads();
-    // :115-122 vein edges inside the mask, cyan
+    thick_line(im, ri[18], ri[19], ri[20], ri[21], rgb_u32(255, 0, 255), 2, 3, t0, ts);
+    __syncthreads();
+    // :115-122 vein edges inside the mask, cyan.  Edge pixels are sparse: 16 pixels per load, four loads in flight, the mask is
+    // only read where an edge byte is set.
     if (edges && mask) {
         const uint8_t* e = edges + (size_t)img * npx;
         const uint8_t* m = mask + (size_t)img * npx;
-        for (size_t k = threadIdx.x; k < npx; k += blockDim.x)
-            if (e[k] && m[k]) {
-                uint8_t* t = im.p + k * 3;
-                t[0] = 0;
-                t[1] = 255;
-                t[2] = 255;
+        auto paint = [&](size_t k) {
+            uint8_t* t = im.p + k * 3;
+            t[0] = 0;
+            t[1] = 255;
+            t[2] = 255;
+        };
+        size_t done = 0;
+        if (((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(m)) & 15) == 0) {
+            const size_t n16 = npx >> 4;
+            for (size_t k0 = threadIdx.x; k0 < n16; k0 += 4 * (size_t)blockDim.x) {
+                uint4 ev[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const size_t k = k0 + (size_t)j * blockDim.x;
+                    ev[j] = k < n16 ? __ldg(reinterpret_cast<const uint4*>(e) + k) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if ((ev[j].x | ev[j].y | ev[j].z | ev[j].w) == 0) continue;
+                    const size_t k = k0 + (size_t)j * blockDim.x;
+                    const uint4 mv = __ldg(reinterpret_cast<const uint4*>(m) + k);
+                    const uint32_t ew[4] = {ev[j].x, ev[j].y, ev[j].z, ev[j].w}, mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            if (((ew[w] >> (8 * b)) & 255) && ((mw[w] >> (8 * b)) & 255)) paint(k * 16 + w * 4 + b);
+                }
             }
+            done = n16 << 4;
+        }
+        for (size_t k = done + threadIdx.x; k < npx; k += blockDim.x)
+            if (e[k] && m[k]) paint(k);
     }
 }
 
@@ -460,7 +505,9 @@ extern "C" int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, co
     LFX_REQUIRE((edges == nullptr) == (mask == nullptr), LFX_ERR_ARG, "analyze_overlay: edges and mask go together");
     LFX_REQUIRE(max_hull <= 1023 && H <= 16384 && W <= 16384, LFX_ERR_UNSUPPORTED, "analyze_overlay: max_hull <= 1023, image side <= 16384");
     LFX_REQUIRE(rgb != overlay, LFX_ERR_ARG, "analyze_overlay: in-place operation is not supported");
-    k_analyze_overlay<<<B, 256, 0, (cudaStream_t)stream>>>(rgb, points, counts, rec_i32, hull_points, edges, mask, overlay, H, W, max_pts,
+    // 64 threads per image: the drawing is a chain of short dependent steps, so many small blocks per SM beat few wide ones
+    // (4096 x 256^2: 5.5 ms with 256 threads, 2.5 with 128, 2.1 with 64, 2.15 with 32)
+    k_analyze_overlay<<<B, 64, 0, (cudaStream_t)stream>>>(rgb, points, counts, rec_i32, hull_points, edges, mask, overlay, H, W, max_pts,
                                                           max_hull);
     return lfx_check_launch("analyze_overlay");
 }

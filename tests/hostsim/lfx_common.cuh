@@ -25,3 +25,6 @@ static inline long long __double2ll_rn(double a) { return llrint(a); }
 static inline int atomicMax(int* p, int v) { int o = *p; if (v > o) *p = v; return o; }
 struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 ld_stream16(const void* p) { uint4 r; memcpy(&r, p, 16); return r; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
+static inline uint4 __ldg(const uint4* p) { return *p; }
+typedef uintptr_t lfx_uintptr_shim;

@@ -29,6 +29,12 @@ extern "C" void host_thick_line(uint8_t* img, int H, int W, int x0, int y0, int 
     Img im = {img, H, W}; thick_line(im, x0, y0, x1, y1, col, th, flags); }
 extern "C" void host_line_aa(uint8_t* img, int H, int W, int x0, int y0, int x1, int y1, uint32_t col) {
     Img im = {img, H, W}; line_aa_block(im, x0, y0, x1, y1, col); }
+extern "C" void host_thick_line_shared(uint8_t* img, int H, int W, int x0, int y0, int x1, int y1, uint32_t col, int th, int flags, int ts) {
+    Img im = {img, H, W}; for (int t0 = ts - 1; t0 >= 0; --t0) thick_line(im, x0, y0, x1, y1, col, th, flags, t0, ts); }
+extern "C" void host_line_aa_shared(uint8_t* img, int H, int W, int x0, int y0, int x1, int y1, uint32_t col, int ts) {
+    Img im = {img, H, W}; blockDim.x = ts;
+    for (int t0 = ts - 1; t0 >= 0; --t0) { threadIdx.x = t0; line_aa_block(im, x0, y0, x1, y1, col); }
+    blockDim.x = 1; threadIdx.x = 0; }
 extern "C" void host_circle(uint8_t* img, int H, int W, int x, int y, int r, uint32_t col) {
     Img im = {img, H, W}; circle_filled(im, x, y, r, col); }
 '''
@@ -93,9 +99,14 @@ def test_primitives_host_sim_vs_oracle(sim):
             a = img.copy(); sd.thick_line(a, p0, p1, col, th, 3)
             b = img.copy(); sim.host_thick_line(P(b), H, W, *p0, *p1, u32(col), th, 3)
             assert np.array_equal(a, b), ("thick", th, p0, p1)
+            for ts in (3, 32):      # the work of one primitive dealt out to `ts` threads (run one after the other, last first)
+                b = img.copy(); sim.host_thick_line_shared(P(b), H, W, *p0, *p1, u32(col), th, 3, ts)
+                assert np.array_equal(a, b), ("thick shared", th, ts, p0, p1)
         a = img.copy(); sd.line_aa_px(a, p0, p1, col)
         b = img.copy(); sim.host_line_aa(P(b), H, W, *p0, *p1, u32(col))
         assert np.array_equal(a, b), ("aa", p0, p1)
+        b = img.copy(); sim.host_line_aa_shared(P(b), H, W, *p0, *p1, u32(col), 5)
+        assert np.array_equal(a, b), ("aa shared", p0, p1)
         a = img.copy(); sd.circle_filled(a, p0, 3, col)
         b = img.copy(); sim.host_circle(P(b), H, W, *p0, 3, u32(col))
         assert np.array_equal(a, b), ("circle", p0)
