@@ -92,7 +92,7 @@ __device__ bool clip_line(i64 width, i64 height, Pt& a, Pt& b) {
 // drawing.cpp Line2: 8-connected DDA between 16.16 end points (the outline FillConvexPoly draws for shift != 0).
 // Steps t0, t0 + ts, ... are drawn by the caller (a lone thread passes 0, 1; a block passes threadIdx.x, blockDim.x: the
 // step-s pixel is the closed form of the DDA, y1 + s * y_step, so the steps are independent).
-__device__ void line2(const Img& im, Pt p1, Pt p2, uint32_t col, int t0, int ts) {
+__device__ __noinline__ void line2(const Img& im, Pt p1, Pt p2, uint32_t col, int t0, int ts) {
     if (!clip_line((i64)im.W << XY_SHIFT, (i64)im.H << XY_SHIFT, p1, p2)) return;
     i64 dx = p2.x - p1.x, dy = p2.y - p1.y;
     const i64 ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy;
@@ -134,6 +134,7 @@ __device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col, int 
     i64 xmin = v[0].x, xmax = v[0].x, ymin = v[0].y, ymax = v[0].y;
     int imin = 0;
     Pt p0 = v[npts - 1];
+#pragma unroll
     for (int i = 0; i < npts; ++i) {
         const Pt p = v[i];
         if (p.y < ymin) {
@@ -152,22 +153,25 @@ __device__ void fill_convex_poly4(const Img& im, const Pt* v, uint32_t col, int 
     ymax = (ymax + delta) >> XY_SHIFT;
     if ((int)xmax < 0 || (int)ymax < 0 || (int)xmin >= im.W || (int)ymin >= im.H) return;
     if (ymax > im.H - 1) ymax = im.H - 1;
+    // the four vertices by selects and the two chains unrolled: nothing here is indexed at run time, so nothing lives in local memory
+    auto vx = [&](int k) { return k == 0 ? v[0].x : k == 1 ? v[1].x : k == 2 ? v[2].x : v[3].x; };
+    auto vy = [&](int k) { return k == 0 ? v[0].y : k == 1 ? v[1].y : k == 2 ? v[2].y : v[3].y; };
     int e_idx[2] = {imin, imin}, e_ye[2] = {(int)ymin, (int)ymin};
-    const int e_di[2] = {1, npts - 1};
     i64 e_x[2] = {-XY_ONE, -XY_ONE}, e_dx[2] = {0, 0};
     int edges = npts;
     int y = (int)ymin;
     while (true) {
+#pragma unroll
         for (int i = 0; i < 2; ++i) {
             if (y >= e_ye[i]) {
                 int idx0 = e_idx[i];
-                const int di = e_di[i];
+                const int di = i == 0 ? 1 : npts - 1;
                 int idx = idx0 + di;
                 if (idx >= npts) idx -= npts;
                 for (; edges-- > 0;) {
-                    const int ty = (int)((v[idx].y + delta) >> XY_SHIFT);
+                    const int ty = (int)((vy(idx) + delta) >> XY_SHIFT);
                     if (ty > y) {
-                        const i64 xs = v[idx0].x, xe = v[idx].x;
+                        const i64 xs = vx(idx0), xe = vx(idx);
                         e_ye[i] = ty;
                         e_dx[i] = ((xe - xs) * 2 + (ty - y)) / (2 * (i64)(ty - y));
                         e_x[i] = xs;
@@ -224,10 +228,11 @@ __device__ void circle_filled(const Img& im, int cx, int cy, int radius, uint32_
 }
 
 // drawing.cpp ThickLine (LINE_8, shift 0, thickness >= 2) as cv::line / PolyLine reach it: the segment is first clipped to
-// the image grown by `thickness`, then drawn as the polygon around it plus round caps (flags bit 0: at p0, bit 1: at p1).
+// the image grown by `thickness`, then drawn as the polygon around it plus round caps (one out-of-line copy: inlined at its
+// six call sites the kernel was 13 k instructions and a fifth of its stalls were instruction fetches) (flags bit 0: at p0, bit 1: at p1).
 // One colour, so the pixels can be written in any order: a lone thread draws everything (t0 = 0, ts = 1), a block shares the
 // polygon's outline steps and rows (t0 = threadIdx.x, ts = blockDim.x; the caps go to thread 0).
-__device__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32_t col, int thickness, int flags, int t0 = 0, int ts = 1) {
+__device__ __noinline__ void thick_line(const Img& im, int x0, int y0, int x1, int y1, uint32_t col, int thickness, int flags, int t0 = 0, int ts = 1) {
     Pt a = {(i64)x0 + thickness, (i64)y0 + thickness}, b = {(i64)x1 + thickness, (i64)y1 + thickness};
     if (!clip_line((i64)im.W + 2 * thickness, (i64)im.H + 2 * thickness, a, b)) return;
     Pt q0 = {(a.x - thickness) << XY_SHIFT, (a.y - thickness) << XY_SHIFT};
@@ -267,7 +272,7 @@ __device__ __forceinline__ void blend_aa(const Img& im, int x, int y, int a, int
 
 // drawing.cpp LineAA between integer pixel end points, called by EVERY thread of the block (the set-up is recomputed per
 // thread, the steps along the major axis are dealt out).  The caller synchronises the block afterwards.
-__device__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1, uint32_t col) {
+__device__ __noinline__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1, uint32_t col) {
     Pt p1 = {(i64)px0 << XY_SHIFT, (i64)py0 << XY_SHIFT}, p2 = {(i64)px1 << XY_SHIFT, (i64)py1 << XY_SHIFT};
     if (!clip_line((i64)im.W << XY_SHIFT, (i64)im.H << XY_SHIFT, p1, p2)) return;
     i64 dx = p2.x - p1.x, dy = p2.y - p1.y;
@@ -307,19 +312,20 @@ __device__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1,
     slope = (int)((step >> (XY_SHIFT - 5)) & 0x3f);
     slope ^= step < 0 ? 0x3f : 0;
     slope = (slope & 0x20) ? 0x100 : c_slope[slope];
-    int ep[9];
+    int ep1, ep2, ep4, ep5, ep6, ep7;   // end-point correction table (entries 0 = 0, 3 = 1, 8 = slope), read through selects
     {
         const int ii = (int)i, jj = (int)j;
         const int t0 = slope << 7, t1 = ((0x78 - ii) | 4) * slope, t2 = (jj | 4) * slope;
-        ep[0] = 0;
-        ep[8] = slope;
-        ep[1] = ep[3] = (((((jj - ii) & 0x78) | 4) * slope) >> 8) & 0x1ff;
-        ep[2] = (t1 >> 8) & 0x1ff;
-        ep[4] = (((((jj - ii) + 0x80) | 4) * slope) >> 8) & 0x1ff;
-        ep[5] = ((t1 + t0) >> 8) & 0x1ff;
-        ep[6] = (t2 >> 8) & 0x1ff;
-        ep[7] = ((t2 + t0) >> 8) & 0x1ff;
+        ep1 = (((((jj - ii) & 0x78) | 4) * slope) >> 8) & 0x1ff;
+        ep2 = (t1 >> 8) & 0x1ff;
+        ep4 = (((((jj - ii) + 0x80) | 4) * slope) >> 8) & 0x1ff;
+        ep5 = ((t1 + t0) >> 8) & 0x1ff;
+        ep6 = (t2 >> 8) & 0x1ff;
+        ep7 = ((t2 + t0) >> 8) & 0x1ff;
     }
+    auto ep = [&](int k) {
+        return k == 8 ? slope : k == 0 ? 0 : (k == 1 || k == 3) ? ep1 : k == 2 ? ep2 : k == 4 ? ep4 : k == 5 ? ep5 : k == 6 ? ep6 : ep7;
+    };
     const int cr = col & 255, cg = (col >> 8) & 255, cb = (col >> 16) & 255;
     const int major_lim = xmajor ? im.W : im.H, minor_lim = xmajor ? im.H : im.W;
     for (int s = threadIdx.x; s <= ecount; s += blockDim.x) {
@@ -328,7 +334,7 @@ __device__ void line_aa_block(const Img& im, int px0, int py0, int px1, int py1,
         const i64 mcoord = minor0 + step * s;
         const int scount = s, ec = ecount - s;
         const int m0 = (int)(mcoord >> XY_SHIFT) - 1;
-        const int ep_corr = ep[(((scount >= 2) + 1) & (scount | 2)) * 3 + (((ec >= 2) + 1) & (ec | 2))];
+        const int ep_corr = ep((((scount >= 2) + 1) & (scount | 2)) * 3 + (((ec >= 2) + 1) & (ec | 2)));
         const int dist = (int)((mcoord >> (XY_SHIFT - 5)) & 31);
         const int f[3] = {c_filter[dist + 32], c_filter[dist], c_filter[63 - dist]};
 #pragma unroll
@@ -364,7 +370,7 @@ __device__ __forceinline__ void block_copy_image(uint8_t* dst, const uint8_t* sr
 __host__ __device__ constexpr uint32_t rgb_u32(int r, int g, int b) { return (uint32_t)r | ((uint32_t)g << 8) | ((uint32_t)b << 16); }
 
 // apply_analyze_filter's overlay (analyze.py:37-122) for one image per block.
-__global__ void __launch_bounds__(256) k_analyze_overlay(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ points,
+__global__ void __launch_bounds__(64, 16) k_analyze_overlay(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ points,
                                                           const int32_t* __restrict__ counts, const int32_t* __restrict__ rec_i,
                                                           const int32_t* __restrict__ hull, const uint8_t* __restrict__ edges,
                                                           const uint8_t* __restrict__ mask, uint8_t* overlay, int H, int W,
@@ -506,7 +512,7 @@ extern "C" int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, co
     LFX_REQUIRE(max_hull <= 1023 && H <= 16384 && W <= 16384, LFX_ERR_UNSUPPORTED, "analyze_overlay: max_hull <= 1023, image side <= 16384");
     LFX_REQUIRE(rgb != overlay, LFX_ERR_ARG, "analyze_overlay: in-place operation is not supported");
     // 64 threads per image: the drawing is a chain of short dependent steps, so many small blocks per SM beat few wide ones
-    // (4096 x 256^2: 5.5 ms with 256 threads, 2.5 with 128, 2.1 with 64, 2.15 with 32)
+    // (4096 x 256^2: 5.5 ms with 256 threads, 2.5 with 128, 2.1 with 64, 2.15 with 32; 64 registers -> 16 blocks per SM: 1.75 ms)
     k_analyze_overlay<<<B, 64, 0, (cudaStream_t)stream>>>(rgb, points, counts, rec_i32, hull_points, edges, mask, overlay, H, W, max_pts,
                                                           max_hull);
     return lfx_check_launch("analyze_overlay");

@@ -13,7 +13,7 @@ using std::max; using std::min;
 #define __shared__ static
 #define __forceinline__ inline
 #define __restrict__
-#define __launch_bounds__(x)
+#define __launch_bounds__(...)
 struct Dim3 { unsigned x, y, z; };
 static Dim3 threadIdx = {0,0,0}, blockIdx = {0,0,0}, blockDim = {1,1,1};
 static inline void __syncthreads() {}
@@ -28,3 +28,4 @@ static inline uint4 ld_stream16(const void* p) { uint4 r; memcpy(&r, p, 16); ret
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 r = {x, y, z, w}; return r; }
 static inline uint4 __ldg(const uint4* p) { return *p; }
 typedef uintptr_t lfx_uintptr_shim;
+#define __noinline__
