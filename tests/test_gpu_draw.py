@@ -75,7 +75,7 @@ def _expected(img, mask, edges, pts, ri, rf, hull):
     return sd.analyze_overlay(img, pts, r, (edges > 0) & (mask > 0))
 
 
-@pytest.mark.parametrize("hw,n,seed", [((96, 96), 10, 5), ((256, 256), 6, 17), ((64, 100), 4, 2)])
+@pytest.mark.parametrize("hw,n,seed", [((96, 96), 10, 5), ((256, 256), 6, 17), ((64, 100), 4, 2), ((384, 512), 2, 9)])
 def test_analyze_overlay_batch_vs_oracle(dev, hw, n, seed):
     """A whole batch in one launch against the oracle drawing from the SAME record (so that the rasterisation, the block-level
     parallel order and the hull re-ordering are what is tested; the record itself is tested in test_gpu_round2)."""
@@ -148,3 +148,10 @@ def test_engine_overlays_device(dev):
     edges = ops.canny(ops.cvt_color(masked, "gray"), 80, 160, True)
     assert torch.equal(over, ops.analyze_overlay(masked, rec, edges, out.mask))
     assert int((over != masked).any(dim=3).sum()) > 1000
+
+
+def test_no_contour_is_a_copy(dev):
+    """analyze.py:28-29 without a contour: the image comes back unchanged (the reference adds a text banner, which is not drawn)."""
+    img = synth.leaf_image(0, 64, 64)
+    got = filters.apply_analyze_filter(img, None, None, transform.default_config())
+    assert np.array_equal(got, img) and got is not img
