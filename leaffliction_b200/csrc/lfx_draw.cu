@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(64, 16) k_analyze_overlay(const uint8_t* __res
 }
 
 // roi.py:44: vis = rgb.copy(); cv2.rectangle(vis, (x, y), (x + w, y + h), colour, thickness): PolyLine over the four corners.
-__global__ void __launch_bounds__(256) k_draw_rectangles(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ info,
+__global__ void __launch_bounds__(256, 4) k_draw_rectangles(const uint8_t* __restrict__ rgb, const int32_t* __restrict__ info,
                                                           uint8_t* vis, int H, int W, uint32_t col, int thickness) {
     const int img = blockIdx.x;
     const size_t npx = (size_t)H * W;
@@ -491,11 +491,13 @@ __global__ void __launch_bounds__(256) k_draw_rectangles(const uint8_t* __restri
     const int32_t* bi = info + (size_t)img * 8;
     if (bi[0] == 0 || bi[3] <= 0 || bi[4] <= 0) return;
     __syncthreads();
-    for (int k = threadIdx.x; k < 4; k += blockDim.x) {   // one colour: the four edges in any order
-        const int x0 = bi[1], y0 = bi[2], x1 = bi[1] + bi[3], y1 = bi[2] + bi[4];
-        const int vx[4] = {x0, x1, x1, x0}, vy[4] = {y0, y0, y1, y1};
+    // one colour, so the four edges need no order among themselves: each is shared by the whole block
+    const int x0 = bi[1], y0 = bi[2], x1 = bi[1] + bi[3], y1 = bi[2] + bi[4];
+    const int vx[4] = {x0, x1, x1, x0}, vy[4] = {y0, y0, y1, y1};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
         const int kp = (k + 3) & 3;
-        thick_line(im, vx[kp], vy[kp], vx[k], vy[k], col, thickness, 2);
+        thick_line(im, vx[kp], vy[kp], vx[k], vy[k], col, thickness, 2, threadIdx.x, blockDim.x);
     }
 }
 
