@@ -237,6 +237,20 @@ int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, const int32_t
 int lfx_draw_rectangles(const uint8_t* rgb, const int32_t* info, uint8_t* vis, int B, int H, int W, uint32_t color_rgb,
                         int thickness, lfx_stream_t stream);
 
+/* The same rasterisers as a general op: prims[B][max_prims][8] (int32) = {kind, x0, y0, x1, y1, color_rgb, size, 0}, counts[B]
+ * primitives per image, drawn IN PLACE on img [B,H,W,3] in list order (later primitives over earlier ones), each bit-identical
+ * to the OpenCV call:
+ *   LFX_DRAW_LINE           cv2.line(img, (x0,y0), (x1,y1), color, thickness = size >= 2)            (LINE_8)
+ *   LFX_DRAW_LINE_AA        cv2.line(img, (x0,y0), (x1,y1), color, 1, cv2.LINE_AA)
+ *   LFX_DRAW_CIRCLE_FILLED  cv2.circle(img, (x0,y0), radius = size, color, -1)
+ *   LFX_DRAW_RECTANGLE      cv2.rectangle(img, (x0,y0), (x1,y1), color, thickness = size >= 2)
+ *   LFX_DRAW_MARKER_CROSS   cv2.drawMarker(img, (x0,y0), color, cv2.MARKER_CROSS, markerSize = x1, thickness = size >= 2)
+ * Entries of any other kind (or with a size outside the stated range) are skipped.  End points may lie outside the image. */
+enum { LFX_DRAW_NONE = 0, LFX_DRAW_LINE = 1, LFX_DRAW_LINE_AA = 2, LFX_DRAW_CIRCLE_FILLED = 3, LFX_DRAW_RECTANGLE = 4,
+       LFX_DRAW_MARKER_CROSS = 5 };
+int lfx_draw_primitives(uint8_t* img, const int32_t* prims, const int32_t* counts, int B, int H, int W, int max_prims,
+                        lfx_stream_t stream);
+
 /* Raw candidate of one threshold strategy, no post-processing (_build_mask_candidates, mask.py:414-443; strategies 0-3:
  * hsv_h, lab, hsv_s / hsv_v_dark by Otsu): raw [B,H,W] (0/255).  Workspace as lfx_make_mask. */
 int lfx_strategy_raw(const uint8_t* src, uint8_t* raw, int B, int H, int W, const lfx_mask_cfg* cfg /* host */,

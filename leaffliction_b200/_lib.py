@@ -50,6 +50,7 @@ _SIGS = {
     "lfx_analyze_workspace": (C.c_size_t, [_I, _I]),
     "lfx_analyze_record": (C.c_int, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, C.c_size_t, _P]),
     "lfx_analyze_overlay": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "lfx_draw_primitives": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "lfx_draw_rectangles": (C.c_int, [_P, _P, _P, _I, _I, _I, C.c_uint32, _I, _P]),
     "lfx_strategy_raw": (C.c_int, [_P, _P, _I, _I, _I, C.POINTER(MaskCfg), _P, C.c_size_t, _P]),
     "lfx_kmeans_raw": (C.c_int, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, C.c_uint32, _P]),

@@ -501,6 +501,38 @@ __global__ void __launch_bounds__(256, 4) k_draw_rectangles(const uint8_t* __res
     }
 }
 
+// A caller-supplied list of primitives per image, drawn in list order (each primitive shared by the block, a barrier between
+// two primitives): the rasterisers above as a general op (cv2.line 2 px and wider / anti-aliased, filled cv2.circle,
+// cv2.rectangle, cv2.drawMarker cross).
+__global__ void __launch_bounds__(64, 16) k_draw_primitives(uint8_t* img, const int32_t* __restrict__ prims, const int32_t* __restrict__ counts,
+                                                             int H, int W, int max_prims) {
+    const int b = blockIdx.x;
+    Img im = {img + (size_t)b * H * W * 3, H, W};
+    const int n = min(counts[b], max_prims);
+    const int t0 = threadIdx.x, ts = blockDim.x;
+    for (int k = 0; k < n; ++k) {
+        const int32_t* q = prims + ((size_t)b * max_prims + k) * 8;
+        const int kind = q[0], x0 = q[1], y0 = q[2], x1 = q[3], y1 = q[4], size = q[6];
+        const uint32_t col = (uint32_t)q[5];
+        if (kind == LFX_DRAW_LINE && size >= 2) {
+            thick_line(im, x0, y0, x1, y1, col, size, 3, t0, ts);
+        } else if (kind == LFX_DRAW_LINE_AA) {
+            line_aa_block(im, x0, y0, x1, y1, col);
+        } else if (kind == LFX_DRAW_CIRCLE_FILLED && size >= 0) {
+            if (t0 == 0) circle_filled(im, x0, y0, size, col);
+        } else if (kind == LFX_DRAW_RECTANGLE && size >= 2) {
+            const int vx[4] = {x0, x1, x1, x0}, vy[4] = {y0, y0, y1, y1};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) thick_line(im, vx[(e + 3) & 3], vy[(e + 3) & 3], vx[e], vy[e], col, size, 2, t0, ts);
+        } else if (kind == LFX_DRAW_MARKER_CROSS && size >= 2) {
+            const int h = x1 / 2;
+            thick_line(im, x0 - h, y0, x0 + h, y0, col, size, 3, t0, ts);
+            thick_line(im, x0, y0 - h, x0, y0 + h, col, size, 3, t0, ts);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" int lfx_analyze_overlay(const uint8_t* rgb, const int32_t* points, const int32_t* counts, const int32_t* rec_i32,
@@ -530,4 +562,14 @@ extern "C" int lfx_draw_rectangles(const uint8_t* rgb, const int32_t* info, uint
     LFX_REQUIRE(rgb != vis, LFX_ERR_ARG, "draw_rectangles: in-place operation is not supported");
     k_draw_rectangles<<<B, 256, 0, (cudaStream_t)stream>>>(rgb, info, vis, H, W, color_rgb, thickness);
     return lfx_check_launch("draw_rectangles");
+}
+
+extern "C" int lfx_draw_primitives(uint8_t* img, const int32_t* prims, const int32_t* counts, int B, int H, int W, int max_prims,
+                                   lfx_stream_t stream) {
+    LFX_REQUIRE_READY();
+    if (B == 0) return LFX_OK;
+    LFX_REQUIRE(img && prims && counts && B > 0 && H > 0 && W > 0 && max_prims > 0, LFX_ERR_ARG, "draw_primitives: bad arguments");
+    LFX_REQUIRE(H <= 16384 && W <= 16384, LFX_ERR_UNSUPPORTED, "draw_primitives: image side <= 16384");
+    k_draw_primitives<<<B, 64, 0, (cudaStream_t)stream>>>(img, prims, counts, H, W, max_prims);
+    return lfx_check_launch("draw_primitives");
 }

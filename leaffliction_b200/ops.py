@@ -256,6 +256,30 @@ def draw_rectangles(rgb: torch.Tensor, info: torch.Tensor, color=(255, 0, 0), th
     return out
 
 
+DRAW_LINE, DRAW_LINE_AA, DRAW_CIRCLE_FILLED, DRAW_RECTANGLE, DRAW_MARKER_CROSS = 1, 2, 3, 4, 5
+
+
+def draw_primitives(img: torch.Tensor, prims, counts=None) -> torch.Tensor:
+    """OpenCV's rasterisers as a general op, IN PLACE on img [B,H,W,3] u8: prims [B,P,8] int32 rows
+    (kind, x0, y0, x1, y1, r | g << 8 | b << 16, size, 0) drawn in list order per image, each bit-identical to the cv2 call
+    (DRAW_LINE = cv2.line thickness `size` >= 2; DRAW_LINE_AA = cv2.line 1 px LINE_AA; DRAW_CIRCLE_FILLED = cv2.circle radius
+    `size` filled; DRAW_RECTANGLE = cv2.rectangle thickness `size` >= 2; DRAW_MARKER_CROSS = cv2.drawMarker cross, markerSize
+    x1, thickness `size`).  counts [B] int32 (default: every row of prims).  Returns img."""
+    _chk_img(img)
+    lib = _ready(img)
+    B, H, W, _ = img.shape
+    prims = _dev(prims, np.int32, img.device)
+    if prims.dtype != torch.int32 or prims.dim() != 3 or int(prims.shape[0]) != B or int(prims.shape[2]) != 8 or not prims.is_contiguous():
+        raise ValueError("draw_primitives: prims must be a contiguous int32 tensor [B,P,8]")
+    P = int(prims.shape[1])
+    counts = torch.full((B,), P, dtype=torch.int32, device=img.device) if counts is None else _dev(counts, np.int32, img.device)
+    if counts.dtype != torch.int32 or tuple(counts.shape) != (B,):
+        raise ValueError("draw_primitives: counts must be int32 [B]")
+    if P:
+        _lib.check(lib.lfx_draw_primitives(_p(img), _p(prims), _p(counts), B, H, W, P, _stream()))
+    return img
+
+
 def strategy_raw(x: torch.Tensor, cfg: MaskCfg) -> torch.Tensor:
     """Raw candidate of a threshold strategy (cfg.strategy 0-3), no post-processing: [B,H,W] u8 (mask.py:72-106)."""
     _chk_img(x)

@@ -438,3 +438,21 @@ def overlay_record(contour: np.ndarray) -> dict:
             axes.append((tuple(int(t) for t in pts[int(proj.argmin())]), tuple(int(t) for t in pts[int(proj.argmax())])))
         rec["axes"] = tuple(axes)
     return rec
+
+
+def draw_primitives(img: np.ndarray, prims) -> np.ndarray:
+    """The primitive list of lfx_draw_primitives (include/leafx.h) on ONE image, in place, through the functions above:
+    rows (kind, x0, y0, x1, y1, r | g << 8 | b << 16, size, 0)."""
+    for kind, x0, y0, x1, y1, c, size, _ in np.asarray(prims).reshape(-1, 8).tolist():
+        col = (c & 255, (c >> 8) & 255, (c >> 16) & 255)
+        if kind == 1 and size >= 2:
+            thick_line(img, (x0, y0), (x1, y1), col, size, 3)
+        elif kind == 2:
+            line_aa_px(img, (x0, y0), (x1, y1), col)
+        elif kind == 3 and size >= 0:
+            circle_filled(img, (x0, y0), size, col)
+        elif kind == 4 and size >= 2:
+            polylines_closed(img, [(x0, y0), (x1, y0), (x1, y1), (x0, y1)], col, size, aa=False)
+        elif kind == 5 and size >= 2:
+            draw_marker_cross(img, (x0, y0), col, x1, size)
+    return img

@@ -29,3 +29,5 @@ static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
 static inline uint4 __ldg(const uint4* p) { return *p; }
 typedef uintptr_t lfx_uintptr_shim;
 #define __noinline__
+enum { LFX_DRAW_NONE = 0, LFX_DRAW_LINE = 1, LFX_DRAW_LINE_AA = 2, LFX_DRAW_CIRCLE_FILLED = 3, LFX_DRAW_RECTANGLE = 4,
+       LFX_DRAW_MARKER_CROSS = 5 };   // include/leafx.h

@@ -25,6 +25,9 @@ extern "C" void host_analyze_overlay(const uint8_t* rgb, const int32_t* points, 
 extern "C" void host_draw_rectangles(const uint8_t* rgb, const int32_t* info, uint8_t* vis, int B, int H, int W, uint32_t col, int thickness) {
     for (int b = 0; b < B; ++b) { blockIdx.x = b; k_draw_rectangles(rgb, info, vis, H, W, col, thickness); }
 }
+extern "C" void host_draw_primitives(uint8_t* img, const int32_t* prims, const int32_t* counts, int B, int H, int W, int max_prims) {
+    for (int b = 0; b < B; ++b) { blockIdx.x = b; k_draw_primitives(img, prims, counts, H, W, max_prims); }
+}
 extern "C" void host_thick_line(uint8_t* img, int H, int W, int x0, int y0, int x1, int y1, uint32_t col, int th, int flags) {
     Img im = {img, H, W}; thick_line(im, x0, y0, x1, y1, col, th, flags); }
 extern "C" void host_line_aa(uint8_t* img, int H, int W, int x0, int y0, int x1, int y1, uint32_t col) {
@@ -133,3 +136,33 @@ def test_overlays_host_sim_vs_golden(sim):
         box = g[k + "_roi_box"]
         sim.host_draw_rectangles(P(rgb), P(np.array([[1, *box, 0, 0, 0]], np.int32)), P(vis), 1, H, W, u32((255, 0, 0)), 2)
         assert np.array_equal(vis, g[k + "_roi_vis"]), k
+
+
+def random_primitives(rng, B, P, H, W, margin=8):
+    """[B,P,8] rows for lfx_draw_primitives: every kind, end points inside and outside the image, overlapping on purpose."""
+    prims = np.zeros((B, P, 8), np.int32)
+    prims[..., 0] = rng.integers(1, 6, size=(B, P))
+    prims[..., 1] = rng.integers(-margin, W + margin, size=(B, P))
+    prims[..., 2] = rng.integers(-margin, H + margin, size=(B, P))
+    prims[..., 3] = rng.integers(-margin, W + margin, size=(B, P))
+    prims[..., 4] = rng.integers(-margin, H + margin, size=(B, P))
+    prims[..., 5] = rng.integers(0, 1 << 24, size=(B, P))
+    kind = prims[..., 0]
+    prims[..., 6] = np.where(kind == 3, rng.integers(0, 7, size=(B, P)), rng.integers(2, 5, size=(B, P)))
+    mk = kind == 5
+    prims[..., 3] = np.where(mk, rng.integers(4, 21, size=(B, P)), prims[..., 3])     # markerSize
+    return prims
+
+
+def test_primitive_lists_host_sim_vs_oracle(sim):
+    rng = np.random.default_rng(21)
+    B, P, H, W = 12, 9, 40, 56
+    imgs = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    prims = random_primitives(rng, B, P, H, W)
+    counts = rng.integers(0, P + 1, size=B).astype(np.int32)
+    got = imgs.copy()
+    sim.host_draw_primitives(got.ctypes.data_as(C.c_void_p), prims.ctypes.data_as(C.c_void_p),
+                             counts.ctypes.data_as(C.c_void_p), B, H, W, P)
+    for b in range(B):
+        exp = sd.draw_primitives(imgs[b].copy(), prims[b, :counts[b]])
+        assert np.array_equal(got[b], exp), (b, prims[b, :counts[b]].tolist())

@@ -155,3 +155,39 @@ def test_no_contour_is_a_copy(dev):
     img = synth.leaf_image(0, 64, 64)
     got = filters.apply_analyze_filter(img, None, None, transform.default_config())
     assert np.array_equal(got, img) and got is not img
+
+
+def test_draw_primitives_random_lists(dev):
+    """lfx_draw_primitives: lists of every kind (2-4 px lines, anti-aliased lines, filled circles, rectangles, cross markers), end
+    points inside and outside the image, overlapping, ragged counts: each image against the oracle drawing the same list in order."""
+    from test_draw_hostsim_cpu import random_primitives
+    rng = np.random.default_rng(8)
+    for (B, P, H, W) in ((48, 12, 40, 56), (6, 30, 256, 256)):
+        imgs = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+        prims = random_primitives(rng, B, P, H, W, margin=12)
+        counts = rng.integers(0, P + 1, size=B).astype(np.int32)
+        counts[0] = P
+        got = ops.draw_primitives(up(imgs, dev), prims, counts).cpu().numpy()
+        for b in range(B):
+            exp = sd.draw_primitives(imgs[b].copy(), prims[b, :counts[b]])
+            assert np.array_equal(got[b], exp), (H, W, b, prims[b, :counts[b]].tolist())
+
+
+def test_draw_primitives_every_direction(dev):
+    """One anti-aliased line, then one 2-px line, from the image centre to EVERY pixel of a 41 x 41 window around it (all slopes,
+    all octants, the degenerate point; part of the window lies outside the image): 1681 images, each against the oracle."""
+    H = W = 36
+    c = 17
+    targets = [(c + dx, c + dy) for dy in range(-20, 21) for dx in range(-20, 21)]
+    B = len(targets)
+    rng = np.random.default_rng(12)
+    base = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    imgs = np.repeat(base[None], B, axis=0)
+    prims = np.zeros((B, 2, 8), np.int32)
+    for b, (x, y) in enumerate(targets):
+        prims[b, 0] = (ops.DRAW_LINE_AA, c, c, x, y, 0x20C0FF, 1, 0)
+        prims[b, 1] = (ops.DRAW_LINE, x, y, c - 3, c + 2, 0xFF4010, 2, 0)
+    got = ops.draw_primitives(up(imgs, dev), prims).cpu().numpy()
+    for b in range(B):
+        exp = sd.draw_primitives(base.copy(), prims[b])
+        assert np.array_equal(got[b], exp), targets[b]

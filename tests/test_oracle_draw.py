@@ -168,3 +168,27 @@ def test_oracle_against_golden_overlays():
         vis = rgb.copy()
         sd.rectangle2(vis, *[int(v) for v in g[k + "_roi_box"]])
         assert np.array_equal(vis, g[k + "_roi_vis"]), k
+
+
+def test_primitive_list_against_cv2():
+    """oracle.spec_draw.draw_primitives (the list format of lfx_draw_primitives) == the cv2 calls it stands for, in order."""
+    from test_draw_hostsim_cpu import random_primitives
+    rng = np.random.default_rng(4)
+    B, P, H, W = 20, 8, 40, 56
+    imgs = rng.integers(0, 256, size=(B, H, W, 3), dtype=np.uint8)
+    prims = random_primitives(rng, B, P, H, W)
+    for b in range(B):
+        exp = imgs[b].copy()
+        for kind, x0, y0, x1, y1, c, size, _ in prims[b].tolist():
+            col = (c & 255, (c >> 8) & 255, (c >> 16) & 255)
+            if kind == 1:
+                cv2.line(exp, (x0, y0), (x1, y1), col, size)
+            elif kind == 2:
+                cv2.line(exp, (x0, y0), (x1, y1), col, 1, cv2.LINE_AA)
+            elif kind == 3:
+                cv2.circle(exp, (x0, y0), size, col, -1)
+            elif kind == 4:
+                cv2.rectangle(exp, (x0, y0), (x1, y1), col, size)
+            elif kind == 5:
+                cv2.drawMarker(exp, (x0, y0), col, markerType=cv2.MARKER_CROSS, markerSize=x1, thickness=size)
+        assert np.array_equal(sd.draw_primitives(imgs[b].copy(), prims[b]), exp), b
