@@ -11,26 +11,17 @@
 
 namespace {
 
-__device__ __forceinline__ bool on(const uint8_t* m, int H, int W, int x, int y) {
-    return x >= 0 && x < W && y >= 0 && y < H && __ldg(m + (size_t)y * W + x) != 0;
-}
-
-__global__ void k_trace_contour(const uint8_t* __restrict__ mask, const int32_t* __restrict__ info,
-                                int32_t* __restrict__ points, int32_t* __restrict__ counts,
-                                long long* __restrict__ sums, int B, int H, int W, int max_pts) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
-    if (img >= B) return;
-    const int32_t* inf = info + (size_t)img * 8;
-    long long* sm = sums ? sums + (size_t)img * 3 : nullptr;
-    if (!inf[0]) {
-        counts[img] = 0;
-        if (sm) sm[0] = sm[1] = sm[2] = 0;
-        return;
-    }
-    const uint8_t* m = mask + (size_t)img * H * W;
-    int32_t* out = points + (size_t)img * max_pts * 2;
-    const int dx[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-    const int dy[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// The walk itself, for ONE image, by ONE thread; `on(x, y)` tells whether a pixel belongs to the component's mask.
+template <class OnFn>
+__device__ __forceinline__ void trace_walk(OnFn on, const int32_t* __restrict__ inf, int32_t* __restrict__ out, int32_t* __restrict__ count,
+                                           long long* __restrict__ sm, int H, int W, int max_pts) {
+    // direction s = 0..7 (E, NE, N, NW, W, SW, S, SE) -> step; two bits per direction (step + 1) in a constant, so that the
+    // dependent chain of the walk carries no table look-up: dx = {1,1,0,-1,-1,-1,0,1}, dy = {0,-1,-1,-1,0,1,1,1}
+    struct Dir {
+        __device__ __forceinline__ int operator[](int s) const { return (int)((code >> (2 * s)) & 3u) - 1; }
+        unsigned code;
+    };
+    const Dir dx = {0x901Au}, dy = {0xA901u};
     const int x0 = inf[7] >> 8, y0 = inf[2];
     int n = 0;
     long long a00 = 0, a10 = 0, a01 = 0;
@@ -57,8 +48,8 @@ __global__ void k_trace_contour(const uint8_t* __restrict__ mask, const int32_t*
     const int s_end0 = 4;
     do {
         s = (s - 1) & 7;
-    } while (!on(m, H, W, x0 + dx[s], y0 + dy[s]) && s != s_end0);
-    if (!on(m, H, W, x0 + dx[s], y0 + dy[s])) {
+    } while (!on(x0 + dx[s], y0 + dy[s]) && s != s_end0);
+    if (!on(x0 + dx[s], y0 + dy[s])) {
         emit(x0, y0);  // isolated pixel
     } else {
         const int x1 = x0 + dx[s], y1 = y0 + dy[s];
@@ -70,7 +61,7 @@ __global__ void k_trace_contour(const uint8_t* __restrict__ mask, const int32_t*
                 ++s;
                 x4 = x3 + dx[s & 7];
                 y4 = y3 + dy[s & 7];
-                if (on(m, H, W, x4, y4)) break;
+                if (on(x4, y4)) break;
             }
             s &= 7;
             if (s != prev_s) {  // CHAIN_APPROX_SIMPLE: keep direction changes only
@@ -92,12 +83,80 @@ __global__ void k_trace_contour(const uint8_t* __restrict__ mask, const int32_t*
         a10 += d * (lx + fx);
         a01 += d * (ly + fy);
     }
-    counts[img] = n <= max_pts ? n : -n;
+    *count = n <= max_pts ? n : -n;
     if (sm) {
         sm[0] = a00;
         sm[1] = a10;
         sm[2] = a01;
     }
+}
+
+// General shapes: one thread per image, the mask read from global memory (the lanes of a warp walk their own borders in
+// lock-step).
+__global__ void k_trace_contour(const uint8_t* __restrict__ mask, const int32_t* __restrict__ info,
+                                int32_t* __restrict__ points, int32_t* __restrict__ counts,
+                                long long* __restrict__ sums, int B, int H, int W, int max_pts) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= B) return;
+    const int32_t* inf = info + (size_t)img * 8;
+    long long* sm = sums ? sums + (size_t)img * 3 : nullptr;
+    if (!inf[0]) {
+        counts[img] = 0;
+        if (sm) sm[0] = sm[1] = sm[2] = 0;
+        return;
+    }
+    const uint8_t* m = mask + (size_t)img * H * W;
+    auto on = [&](int x, int y) { return x >= 0 && x < W && y >= 0 && y < H && __ldg(m + (size_t)y * W + x) != 0; };
+    trace_walk(on, inf, points + (size_t)img * max_pts * 2, counts + img, sm, H, W, max_pts);
+}
+
+// Images whose bit plane fits shared memory (H * ceil(W / 32) words <= 48 KB: up to 512 x 768): one 32-thread block per image
+// packs the mask into a bit plane (32 pixels per word), then lane 0 walks the border out of shared memory.  The walk is a chain
+// of dependent neighbour tests (2-5 per border pixel); from global memory each one is an L2 round trip and the 32 walks of a
+// warp advance at the pace of the slowest, here it is a shared-memory read and every image has its own warp.
+__global__ void __launch_bounds__(32) k_trace_contour_bits(const uint8_t* __restrict__ mask, const int32_t* __restrict__ info,
+                                                            int32_t* __restrict__ points, int32_t* __restrict__ counts,
+                                                            long long* __restrict__ sums, int H, int W, int max_pts) {
+    extern __shared__ uint32_t s_bits[];
+    const int img = blockIdx.x;
+    const int32_t* inf = info + (size_t)img * 8;
+    long long* sm = sums ? sums + (size_t)img * 3 : nullptr;
+    if (!inf[0]) {
+        if (threadIdx.x == 0) {
+            counts[img] = 0;
+            if (sm) sm[0] = sm[1] = sm[2] = 0;
+        }
+        return;
+    }
+    const uint8_t* m = mask + (size_t)img * H * W;
+    const int wpr = (W + 31) >> 5;
+    const bool vec = (W & 31) == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0;
+    for (int w = threadIdx.x; w < H * wpr; w += blockDim.x) {
+        const int y = w / wpr, xw = w - y * wpr;
+        const uint8_t* row = m + (size_t)y * W + xw * 32;
+        uint32_t bits = 0;
+        if (vec) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(row) + q);
+                const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((ws[j] >> (8 * b)) & 255) bits |= 1u << (q * 16 + j * 4 + b);
+            }
+        } else {
+            const int nb = min(32, W - xw * 32);
+            for (int b = 0; b < nb; ++b)
+                if (row[b]) bits |= 1u << b;
+        }
+        s_bits[w] = bits;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    auto on = [&](int x, int y) { return x >= 0 && x < W && y >= 0 && y < H && ((s_bits[y * wpr + (x >> 5)] >> (x & 31)) & 1u) != 0; };
+    trace_walk(on, inf, points + (size_t)img * max_pts * 2, counts + img, sm, H, W, max_pts);
 }
 
 // ---- numeric record of apply_analyze_filter (analyze.py:43-98) + convex hull, one thread per image.
@@ -288,7 +347,12 @@ extern "C" int lfx_trace_contour(const uint8_t* mask, const int32_t* info, int32
     if (B == 0) return LFX_OK;
     LFX_REQUIRE(mask && info && points && counts && B > 0 && H > 0 && W > 0 && max_pts > 0, LFX_ERR_ARG,
                 "trace_contour: bad arguments");
-    k_trace_contour<<<lfx_div_up(B, 64), 64, 0, (cudaStream_t)stream>>>(mask, info, points, counts,
-                                                                       reinterpret_cast<long long*>(sums), B, H, W, max_pts);
+    const size_t plane = (size_t)H * ((W + 31) >> 5) * sizeof(uint32_t);
+    if (plane <= 48 * 1024)
+        k_trace_contour_bits<<<B, 32, plane, (cudaStream_t)stream>>>(mask, info, points, counts, reinterpret_cast<long long*>(sums), H, W,
+                                                                   max_pts);
+    else
+        k_trace_contour<<<lfx_div_up(B, 64), 64, 0, (cudaStream_t)stream>>>(mask, info, points, counts,
+                                                                           reinterpret_cast<long long*>(sums), B, H, W, max_pts);
     return lfx_check_launch("trace_contour");
 }

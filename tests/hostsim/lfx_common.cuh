@@ -31,3 +31,5 @@ typedef uintptr_t lfx_uintptr_shim;
 #define __noinline__
 enum { LFX_DRAW_NONE = 0, LFX_DRAW_LINE = 1, LFX_DRAW_LINE_AA = 2, LFX_DRAW_CIRCLE_FILLED = 3, LFX_DRAW_RECTANGLE = 4,
        LFX_DRAW_MARKER_CROSS = 5 };   // include/leafx.h
+static inline uint8_t __ldg(const uint8_t* p) { return *p; }
+static inline void __syncwarp() {}

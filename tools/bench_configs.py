@@ -6,6 +6,8 @@ and runnable alone.  Device-timed with CUDA events, max over ranks, inputs resid
   c4_1024       1024x1024x3 leaves: the augment warps (skew, shear, rotate), the 5x5 / 15x15 blur and the core transform
                 profile, 256 images per GPU (weak scaling)
   c5_resize224  augment -> Lanczos 224x224 -> /255 float32 -> DLPack (train.py's leaf_cnn input), batch 32..1024 on one GPU
+  f2_jpeg       JPEG bitstreams in -> nvJPEG decode -> core transform -> nvJPEG encode -> bitstreams out (one GPU)
+  f3_overlays   the Analyze overlay and the ROI rectangle image of every image of a resident batch (one GPU)
 """
 from __future__ import annotations
 
@@ -259,6 +261,38 @@ def f2_jpeg(x, dev, n=1024):
                                 "what": "Pillow decode + two Pillow encodes per image on all host cores, no transform"}}
 
 
+def f3_overlays(x, dev, peak, n=2048):
+    """SURVEY 8f rank 3: the two overlay images of the reference's folder run (apply_analyze_filter's image, analyze.py:37-122;
+    the rectangle view of apply_roi_filter, roi.py:43-44) for a resident batch, from the outputs of the core transform: masked
+    image, contour trace + record, grey + Canny, the overlay kernel, the rectangle kernel (bit-identical to the OpenCV calls)."""
+    from leaffliction_b200 import engine as eng
+    xs = x[:n]
+    S = int(x.shape[1])
+    N = S * S
+    e = eng.TransformEngine(S, S, ops.mask_cfg("hsv_h"), 1.5, (256, 256), dev)
+    out = e.run_device(xs)
+    ms = _timed(lambda: e.overlays_device(xs, out), reps=3, warm=2)
+    masked = ops.apply_mask(xs, out.mask, 255)
+    rec = ops.analyze_records(out.mask, out.info, 4096, 512)
+    gray = ops.cvt_color(masked, "gray")
+    edges = ops.canny(gray, 80, 160, True)
+    stages = {"apply_mask": (lambda: ops.apply_mask(xs, out.mask, 255), 7 * N),
+              "trace_contour+analyze_record": (lambda: ops.analyze_records(out.mask, out.info, 4096, 512), N),
+              "grey": (lambda: ops.cvt_color(masked, "gray"), 4 * N),
+              "canny": (lambda: ops.canny(gray, 80, 160, True), 2 * N),
+              "analyze_overlay": (lambda: ops.analyze_overlay(masked, rec, edges, out.mask), 8 * N),
+              "draw_rectangles": (lambda: ops.draw_rectangles(masked, out.info), 6 * N)}
+    per = {}
+    for k, (fn, by) in stages.items():
+        t = _timed(fn, reps=3, warm=1)
+        per[k] = {"ms": round(t, 4), "algo_bytes_per_image": by, "frac": round(by * len(xs) / (t / 1e3) / 1e9 / peak, 4)}
+    by_all = sum(v[1] for v in stages.values())
+    return {"workload": f"Analyze overlay + ROI rectangle image for {len(xs)} x {S}x{S}x3 images in HBM, from the core transform's mask / box "
+                        "(OpenCV's drawing restated on the device, bit-identical)", "n_gpus": 1, "value": len(xs) / (ms / 1e3),
+            "unit": "images/s (both overlay images per image)", "ms": round(ms, 4), "launches": 7, "algo_bytes_per_image": by_all,
+            "achieved_gbs": by_all * len(xs) / (ms / 1e3) / 1e9, "frac": by_all * len(xs) / (ms / 1e3) / 1e9 / peak, "stages": per}
+
+
 def run_all(x, dev, rank, world, peak, max_over_ranks, barrier):
     res = {}
     if world == 1:
@@ -266,6 +300,10 @@ def run_all(x, dev, rank, world, peak, max_over_ranks, barrier):
             res["f2_jpeg"] = f2_jpeg(x, dev)
         except Exception as e:   # noqa: BLE001
             res["f2_jpeg"] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            res["f3_overlays"] = f3_overlays(x, dev, peak)
+        except Exception as e:   # noqa: BLE001
+            res["f3_overlays"] = {"error": f"{type(e).__name__}: {e}"}
     for name, fn in (("p0_default_strategy", lambda: p0_default_strategy(x, dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c3_balance", lambda: c3_balance(x, dev, rank, world, peak, max_over_ranks, barrier)),
                      ("c4_1024", lambda: c4_1024(dev, rank, world, peak, max_over_ranks, barrier)),

@@ -99,6 +99,7 @@ Phase split of `k_core` (LFX_CORE_TIMING=1): profiles/r02_k_core_phase_split.txt
 | c3_balance | {c['c3_balance']['value']:,.0f} augmented images/s | 36,864 tasks over 65,536 resident images, {c['c3_balance']['ms_per_pass_wall']:.1f} ms per pass (wall), plan + histogram + task list {c['c3_balance']['plan_histogram_tasklist_ms']:.1f} ms; round 1: 1.60 M/s |
 | c4_1024 | {c['c4_1024']['value']:,.0f} images/s | 256 x 1024x1024: skew + shear + rotate + 5x5 blur = {c['c4_1024']['frac'] * 100:.1f} % of peak; pipeline_core {c['c4_1024']['ops']['pipeline_core']['ms']} ms ({c['c4_1024']['ops']['pipeline_core']['frac'] * 100:.1f} %) |
 | f2_jpeg | {c.get('f2_jpeg', {}).get('value', 0):,.0f} images/s | JPEG bitstreams in host memory -> nvJPEG decode -> core transform -> nvJPEG encode of blur + ROI -> bitstreams; codec alone through Pillow on all host cores: {c.get('f2_jpeg', {}).get('host_codec_only', {}).get('value', 0):,.0f} images/s |
+| f3_overlays | {c.get('f3_overlays', {}).get('value', 0):,.0f} images/s | Analyze overlay + ROI rectangle image per image (masked image, contour trace + record, grey + Canny, overlay kernel, rectangle kernel): {c.get('f3_overlays', {}).get('ms', 0)} ms per 2048 images, {100 * c.get('f3_overlays', {}).get('frac', 0):.1f} % of peak; stages: {json.dumps({k: v['ms'] for k, v in c.get('f3_overlays', {}).get('stages', {}).items()})} |
 | c5_resize224 | {c['c5_resize224']['value']:,.0f} images/s | flip -> Lanczos 224 -> /255 f32 -> DLPack, best batch; batches: {json.dumps({k: v['images_per_s'] for k, v in c['c5_resize224']['batches'].items()})} |
 
 ## Scaling (torchrun, 20 steps; the 8-GPU record predates the pipelined steps -- its 11.24 ms/step is 0.988 of that build's 11.11 ms at N = 1)
