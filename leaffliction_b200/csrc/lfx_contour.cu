@@ -166,28 +166,46 @@ __device__ __forceinline__ long long cross3(int ax, int ay, int bx, int by, int 
     return (long long)(bx - ax) * (cy - ay) - (long long)(by - ay) * (cx - ax);
 }
 
+// SMEM = false: one thread per image, scratch (row extremes, hull sequence and stack) in the caller's global workspace.
+// SMEM = true (6H + 8 words fit shared memory, H <= 2000): one 32-thread block per image, the scratch in shared memory; the record
+// is still computed by ONE thread in the same order (bit-identical results) -- the hull's stack and the row extremes are
+// read-modify-write chains, an L2 round trip per access from global memory, a shared-memory access here.
+template <bool SMEM>
 __global__ void k_analyze_record(const int32_t* __restrict__ points, const int32_t* __restrict__ counts,
                                  const long long* __restrict__ sums, int32_t* __restrict__ rec_i, double* __restrict__ rec_f,
                                  int32_t* __restrict__ hull, int32_t* __restrict__ ws, int B, int H, int max_pts, int max_hull) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ int32_t s_ws[];
+    const int img = SMEM ? (int)blockIdx.x : (int)(blockIdx.x * blockDim.x + threadIdx.x);
     if (img >= B) return;
+    const bool lead = !SMEM || threadIdx.x == 0;
     int32_t* ri = rec_i + (size_t)img * 24;
     double* rf = rec_f + (size_t)img * 12;
-    for (int k = 0; k < 24; ++k) ri[k] = 0;
-    for (int k = 0; k < 12; ++k) rf[k] = 0.0;
+    if (lead) {
+        for (int k = 0; k < 24; ++k) ri[k] = 0;
+        for (int k = 0; k < 12; ++k) rf[k] = 0.0;
+    }
     const int n = counts[img];
     if (n <= 0 || n > max_pts) {   // no contour, or the point buffer was too small (count < 0)
-        ri[1] = n;
+        if (lead) ri[1] = n;
         return;
     }
     const int32_t* p = points + (size_t)img * max_pts * 2;
-    int32_t* minx = ws + (size_t)img * (6 * (size_t)H + 8);
+    int32_t* minx = SMEM ? s_ws : ws + (size_t)img * (6 * (size_t)H + 8);
     int32_t* maxx = minx + H;
     int32_t* seq = maxx + H;          // [2H] packed x | y << 16
     int32_t* stk = seq + 2 * H;       // [2H + 8]
-    for (int y = 0; y < H; ++y) {
-        minx[y] = INT_MAX;
-        maxx[y] = INT_MIN;
+    if (SMEM) {
+        for (int y = threadIdx.x; y < H; y += blockDim.x) {
+            minx[y] = INT_MAX;
+            maxx[y] = INT_MIN;
+        }
+        __syncthreads();
+        if (threadIdx.x != 0) return;
+    } else {
+        for (int y = 0; y < H; ++y) {
+            minx[y] = INT_MAX;
+            maxx[y] = INT_MIN;
+        }
     }
     // ---- extreme points (first argmin / argmax, analyze.py:60-64), row extremes, sums for the PCA
     int lx = p[0], ly = p[1], rx = p[0], ry = p[1], tx = p[0], ty = p[1], bx = p[0], by = p[1];
@@ -335,9 +353,14 @@ extern "C" int lfx_analyze_record(const int32_t* points, const int32_t* counts, 
     LFX_REQUIRE(H <= 32767 && W <= 65535, LFX_ERR_UNSUPPORTED, "analyze_record: image too large for the packed hull points");
     LFX_REQUIRE(workspace && workspace_bytes >= lfx_analyze_workspace(B, H), LFX_ERR_WORKSPACE, "analyze_record: workspace %zu < %zu bytes",
                 workspace_bytes, lfx_analyze_workspace(B, H));
-    k_analyze_record<<<lfx_div_up(B, 64), 64, 0, (cudaStream_t)stream>>>(points, counts, reinterpret_cast<const long long*>(sums), rec_i32,
-                                                                        rec_f64, hull_points, reinterpret_cast<int32_t*>(workspace), B, H,
-                                                                        max_pts, max_hull);
+    const size_t scratch = (6 * (size_t)H + 8) * sizeof(int32_t);
+    if (scratch <= 48 * 1024)
+        k_analyze_record<true><<<B, 32, scratch, (cudaStream_t)stream>>>(points, counts, reinterpret_cast<const long long*>(sums), rec_i32,
+                                                                       rec_f64, hull_points, nullptr, B, H, max_pts, max_hull);
+    else
+        k_analyze_record<false><<<lfx_div_up(B, 64), 64, 0, (cudaStream_t)stream>>>(points, counts, reinterpret_cast<const long long*>(sums),
+                                                                                   rec_i32, rec_f64, hull_points,
+                                                                                   reinterpret_cast<int32_t*>(workspace), B, H, max_pts, max_hull);
     return lfx_check_launch("analyze_record");
 }
 
