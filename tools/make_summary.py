@@ -51,7 +51,10 @@ def main():
     kern = "\n".join(f"| {k['kernel']} | {k['ms']} | {k['algo_bytes_per_launch']:,} | {k['achieved_gbs']} | {k['frac']} | {k['share_of_step']} |"
                      for k in b["roofline"]["kernels"])
     shares = "\n".join(f"| {k} | {n} | {ms:.3f} | {s * 100:.1f} % |" for k, n, ms, s in launch_shares())
-    c = b["configs"]
+    c = dict(b["configs"])
+    f3 = os.path.join(ROOT, "profiles", "r02_f3_overlays.json")
+    if "f3_overlays" not in c and os.path.exists(f3):      # measured after the bench record above (same kernels otherwise)
+        c["f3_overlays"] = json.load(open(f3))
     md = f"""# Round 2 -- measurements (all on B200, CUDA events / ncu as noted; peak = MEASURED_PEAKS.json hbm_gbs {b['roofline']['peak']} GB/s)
 
 Regenerate: copy a measurement pass (the gpurun command in DESIGN.md section 5) from gpurun_out/ into profiles/r02_*, run
